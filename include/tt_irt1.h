@@ -1,0 +1,110 @@
+/*
+ * tt_irt1.h -- C-ABI of the B200-native linear-spline inverse Rosenblatt transform.
+ *
+ * Two shared libraries are built from the same sources (tt-irt_b200/Makefile):
+ *   tt-irt_b200/tt_irt_py/tt_irt1_int32.so   TTIRT_INT = int        (Python ctypes caller)
+ *   tt-irt_b200/lib/libtt_irt1_int64.so      TTIRT_INT = long long  (Matlab MEX caller)
+ * Both are self-contained (static cudart, no BLAS) and export
+ *   (1) the reference's entry point `tt_irt1` with its exact signature, and
+ *   (2) the width-independent extended entry points `ttirt_*` declared below
+ *       (device-resident sampling, cached models).
+ *
+ * All pointers are plain host or device addresses; no torch / C++ types cross this boundary.
+ * There is NO CPU fallback: without a usable CUDA device every entry point fails loudly
+ * (message on stderr, outputs NaN-filled, non-zero status where a status is returned).
+ */
+#ifndef TT_IRT1_H
+#define TT_IRT1_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define TTIRT_API __attribute__((visibility("default")))
+#else
+#define TTIRT_API
+#endif
+
+#ifndef TTIRT_INT
+#define TTIRT_INT int /* the reference's `lapackint`: tt_irt1_int32.c:20 (int) / tt_irt1_int64.c:20 (long long) */
+#endif
+
+/*
+ * Drop-in replacement for the reference routine
+ *   python/tt_irt_py/tt_irt1_int32.c:34   void tt_irt1(lapackint d, lapackint *n, double *xs, lapackint *ttrank,
+ *   matlab/utils/tt_irt1_int64.c:34                    double *ttcore, lapackint M, double *q, double *z, double *lPz)
+ * bound by  python/tt_irt_py/tt_irt.py:23-25,51  (ctypes, c_int)  and  matlab/utils/tt_irt_mex.c:5,39 (mwIndex).
+ *
+ *   d       dimension
+ *   n       mode sizes (d)
+ *   xs      grid points of all dimensions stacked (sum n)
+ *   ttrank  TT ranks (d+1), ttrank[0] = ttrank[d] = 1
+ *   ttcore  TT cores, core k column-major r_k x n_k x r_{k+1}, stacked (sum r n r)
+ *   M       number of seed points
+ *   q       seeds in [0,1], column-major M x d           (host, read only)
+ *   z       samples, column-major M x d                  (host, caller-allocated, fully overwritten)
+ *   lPz     log sampling density at z, length M          (host, caller-allocated, fully overwritten)
+ *
+ * Returns nothing (as the reference).  On any failure (no device, bad shape, CUDA error) it prints
+ * one line to stderr and fills z and lPz with NaN; it never aborts the host process.
+ * Environment: TTIRT_MODE=fast|strict (default fast), TTIRT_DEVICES=<count>|all (default 1),
+ * TTIRT_DEVICE=<first ordinal> (default 0), TTIRT_CHUNK=<samples per chunk>, TTIRT_VERBOSE=1.
+ */
+TTIRT_API void tt_irt1(TTIRT_INT d, TTIRT_INT *n, double *xs, TTIRT_INT *ttrank, double *ttcore, TTIRT_INT M,
+             double *q, double *z, double *lPz);
+
+/* ------------------------------------------------------------------------------------------
+ * Extended entry points (identical in both libraries; all sizes are int64_t).
+ * ---------------------------------------------------------------------------------------- */
+
+typedef struct ttirt_model ttirt_model; /* opaque: cores + marginal products resident on one device */
+
+enum { TTIRT_MODE_FAST = 0, TTIRT_MODE_STRICT = 1 };
+
+/* Upload grid and cores to `device`, run the right-to-left marginalisation sweep there
+ * (reference tt_irt1_int32.c:59-82) and keep P_k = core_k x_3 C_k resident.  NULL on failure. */
+TTIRT_API ttirt_model *ttirt_model_create(int64_t d, const int64_t *n, const double *xs, const int64_t *ttrank,
+                                const double *ttcore, int device);
+TTIRT_API void ttirt_model_destroy(ttirt_model *model);
+
+/* Copy the sweep's results back: pk_out receives P_0..P_{d-1} stacked (sum r_k n_k, each column-major
+ * r_k x n_k), marg_out the right marginals C_0..C_{d-1} stacked (sum r_{k+1}).  Either may be NULL. */
+TTIRT_API int ttirt_model_get_sweep(const ttirt_model *model, double *pk_out, double *marg_out);
+
+/* Sample with everything resident in device memory.  d_q / d_z are column-major with leading
+ * dimensions ldq / ldz (>= M); d_lpz has length M; d_idx (may be NULL) receives the grid-interval
+ * index chosen per (sample, dimension), int32, column-major with leading dimension ldz.
+ * Work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream) and the
+ * call returns without synchronising.  mode: TTIRT_MODE_FAST or TTIRT_MODE_STRICT.  0 on success. */
+TTIRT_API int ttirt_sample_device(ttirt_model *model, int64_t M, const double *d_q, int64_t ldq, double *d_z,
+                        int64_t ldz, double *d_lpz, int32_t *d_idx, int mode, void *stream);
+
+/* Sample with host buffers (column-major, leading dimension ld >= M for q/z/idx): chunked
+ * H2D -> kernels -> D2H pipeline on the model's device, rows [0, M).  h_idx may be NULL.
+ * Blocks until the outputs are complete.  0 on success. */
+TTIRT_API int ttirt_sample_host(ttirt_model *model, int64_t M, const double *h_q, double *h_z, double *h_lpz,
+                      int32_t *h_idx, int64_t ld, int mode);
+
+/* Whole call on host buffers: create models on n_devices devices starting at first_device, shard the
+ * M rows contiguously across them (one host thread per device, no collective), free everything.
+ * This is what tt_irt1() runs.  0 on success. */
+TTIRT_API int ttirt_run_host(int64_t d, const int64_t *n, const double *xs, const int64_t *ttrank,
+                   const double *ttcore, int64_t M, const double *h_q, double *h_z, double *h_lpz,
+                   int32_t *h_idx, int mode, int first_device, int n_devices);
+
+/* Number of this library's kernels launched by the calling process so far (bench.py's gpu_launches). */
+TTIRT_API int64_t ttirt_kernel_launches(void);
+/* Last error message of the calling thread ("" if none). */
+TTIRT_API const char *ttirt_last_error(void);
+/* Number of visible CUDA devices (0 if none / driver missing). */
+TTIRT_API int ttirt_device_count(void);
+/* Samples per chunk used by the pipelines (0 restores the default). */
+TTIRT_API void ttirt_set_chunk(int64_t samples);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TT_IRT1_H */

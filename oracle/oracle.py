@@ -27,8 +27,26 @@ def _load(path):
     if path not in _LIBS:
         if not os.path.exists(path):
             raise FileNotFoundError(path + " (run `make -C oracle`)")
+        if path.endswith("_openblas.so"):
+            _preload_blas_deps(path)
         _LIBS[path] = C.CDLL(path)
     return _LIBS[path]
+
+
+def _preload_blas_deps(path):
+    """The wheel-bundled OpenBLAS needs its sibling libquadmath/libgfortran, which carry no RUNPATH."""
+    import glob
+    import re
+    out = subprocess.run(["readelf", "-d", path], capture_output=True, text=True).stdout
+    m = re.search(r"(?:RUNPATH|RPATH).*\[(.*?)\]", out)
+    if not m:
+        return
+    for pat in ("libquadmath*", "libgfortran*"):
+        for f in sorted(glob.glob(os.path.join(m.group(1), pat))):
+            try:
+                C.CDLL(f, mode=C.RTLD_GLOBAL)
+            except OSError:
+                pass
 
 
 def ref_lib_path(width=32, blas="shim"):
@@ -49,7 +67,7 @@ def _dp(a):
 
 def oracle_run(n, xs, ranks, cores, q, rows=None, extras=False):
     """Run the restatement. q is (M, d) (any order; read column-major). Returns Z (M,d) F-order, lPz (M,)
-    and, with extras=True, also idx (M,d) int32, kappa (M,d), gap (M,d)."""
+    and, with extras=True, also idx (M,d) int32, kappa (M,d), gap (M,d), cond (M,d)."""
     lib = _load(os.path.join(ORACLE_DIR, "liboracle_tt_irt1.so"))
     q = np.asfortranarray(q, dtype=np.float64)
     M, d = q.shape
@@ -64,21 +82,23 @@ def oracle_run(n, xs, ranks, cores, q, rows=None, extras=False):
     idx = np.zeros((M, d), dtype=np.int32, order="F") if extras else None
     kap = np.zeros((M, d), dtype=np.float64, order="F") if extras else None
     gap = np.zeros((M, d), dtype=np.float64, order="F") if extras else None
+    cond = np.zeros((M, d), dtype=np.float64, order="F") if extras else None
     m0, m1 = (0, M) if rows is None else rows
     fn = lib.tt_irt1_oracle_rows
     fn.restype = C.c_int
     ip = C.POINTER(C.c_longlong)
     fn.argtypes = [C.c_longlong, ip, C.POINTER(C.c_double), ip, C.POINTER(C.c_double), C.c_longlong,
                    C.c_longlong, C.c_longlong, C.POINTER(C.c_double), C.POINTER(C.c_double),
-                   C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+                   C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                   C.POINTER(C.c_double)]
     rc = fn(d, n64.ctypes.data_as(ip), _dp(xs), r64.ctypes.data_as(ip), _dp(cores), M, m0, m1,
             _dp(q), _dp(Z), _dp(lPz),
             idx.ctypes.data_as(C.POINTER(C.c_int)) if extras else None,
-            _dp(kap) if extras else None, _dp(gap) if extras else None)
+            _dp(kap) if extras else None, _dp(gap) if extras else None, _dp(cond) if extras else None)
     if rc != 0:
         raise RuntimeError("oracle failed")
     if extras:
-        return Z, lPz, idx, kap, gap
+        return Z, lPz, idx, kap, gap, cond
     return Z, lPz
 
 

@@ -25,7 +25,8 @@
  * Beyond (z, lPz) it can export, for the parity protocol, the grid-interval
  * index chosen per (sample, dimension), the cancellation factor kappa of the
  * reference's quadratic formula (tt_irt1_int32.c:150-156), and the distance of
- * q to the nearest normalised-CDF node (how robust the index is).
+ * q to the nearest normalised-CDF node (how robust the index is), and a first-order
+ * condition estimate of xk (the entry-wise Z tolerance of the parity tests).
  */
 #include <math.h>
 #include <stdlib.h>
@@ -105,7 +106,7 @@ static void model_free(model_t *md) {
 
 /* One sample, all dimensions.  left: r_k left-interface vector (ref row of fkm1). */
 static void walk_sample(const model_t *md, oidx M, oidx m, const double *q, double *z, double *lPz,
-                        int *idx, double *kappa, double *gap,
+                        int *idx, double *kappa, double *gap, double *cond,
                         double *left, double *next, double *p, double *cdf, double *slab) {
   double lp = 0.0;
   left[0] = 1.0; /* ref :90, assumes r_0 = 1 */
@@ -170,6 +171,15 @@ static void walk_sample(const model_t *md, oidx M, oidx m, const double *q, doub
     /* log-density of the interpolated conditional (ref :161-165) */
     const double w1 = (x2 - xk) / hq, w2 = (xk - x1) / hq;
     lp += log(fabs(p[lo] * w1 + p[lo + 1] * w2));
+    if (cond) {
+      /* first-order sensitivity of xk to O(eps) perturbations of (cdf, p): the true
+         root sensitivity (1 + max(c1,c2) h)/p(xk) plus the formula's cancellation term */
+      const double pint = fabs(p[lo] * w1 + p[lo + 1] * w2);
+      const double den = fabs(-Bq + root);
+      const double kap = (Aq == 0.0) ? 1.0 : (den > 0.0 ? fabs(Bq) / den : INFINITY);
+      const double xa = fabs(x1) > fabs(x2) ? fabs(x1) : fabs(x2);
+      cond[m + M * k] = (1.0 + (c1 > c2 ? c1 : c2) * hq) / pint + kap * xa;
+    }
     /* interface update: slab = w1*core[:,lo,:] + w2*core[:,lo+1,:]; left <- left*slab (ref :167-177) */
     if (k < md->d - 1) {
       for (oidx b = 0; b < rn; b++) {
@@ -195,7 +205,7 @@ static void walk_sample(const model_t *md, oidx M, oidx m, const double *q, doub
    only (M is still the leading dimension), so callers can shard over host threads. */
 int tt_irt1_oracle_rows(oidx d, const oidx *n, const double *xs, const oidx *ttrank, const double *ttcore,
                         oidx M, oidx m_begin, oidx m_end, const double *q, double *z, double *lPz,
-                        int *idx, double *kappa, double *gap) {
+                        int *idx, double *kappa, double *gap, double *cond) {
   model_t md; memset(&md, 0, sizeof(md));
   md.d = d; md.n = n; md.r = ttrank; md.xs = xs; md.core = ttcore;
   if (d < 1 || model_build(&md) != 0) { model_free(&md); return -1; }
@@ -204,15 +214,15 @@ int tt_irt1_oracle_rows(oidx d, const oidx *n, const double *xs, const oidx *ttr
   double *p = (double *)malloc(sizeof(double) * nm), *cdf = (double *)malloc(sizeof(double) * nm);
   double *slab = (double *)malloc(sizeof(double) * rm * rm);
   for (oidx m = m_begin; m < m_end; m++)
-    walk_sample(&md, M, m, q, z, lPz, idx, kappa, gap, left, next, p, cdf, slab);
+    walk_sample(&md, M, m, q, z, lPz, idx, kappa, gap, cond, left, next, p, cdf, slab);
   free(left); free(next); free(p); free(cdf); free(slab);
   model_free(&md);
   return 0;
 }
 
 int tt_irt1_oracle(oidx d, const oidx *n, const double *xs, const oidx *ttrank, const double *ttcore,
-                   oidx M, const double *q, double *z, double *lPz, int *idx, double *kappa, double *gap) {
-  return tt_irt1_oracle_rows(d, n, xs, ttrank, ttcore, M, 0, M, q, z, lPz, idx, kappa, gap);
+                   oidx M, const double *q, double *z, double *lPz, int *idx, double *kappa, double *gap, double *cond) {
+  return tt_irt1_oracle_rows(d, n, xs, ttrank, ttcore, M, 0, M, q, z, lPz, idx, kappa, gap, cond);
 }
 
 /* The right marginals and core*marginal products alone (checks the device sweep). */

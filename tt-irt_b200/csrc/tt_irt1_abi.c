@@ -1,0 +1,66 @@
+/*
+ * The reference's entry point, unchanged:  void tt_irt1(lapackint d, lapackint *n, double *xs,
+ * lapackint *ttrank, double *ttcore, lapackint M, double *q, double *z, double *lPz)
+ * (python/tt_irt_py/tt_irt1_int32.c:34, matlab/utils/tt_irt1_int64.c:34).  Plain C host code: it
+ * widens the integer arguments and hands the call to the CUDA engine through the extended C-ABI in
+ * include/tt_irt1.h.  Built twice: -DTTIRT_INT=int and -DTTIRT_INT="long long".
+ * No CPU fallback: on failure the outputs are NaN-filled and one line goes to stderr.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/tt_irt1.h"
+
+static void nan_fill(double *p, int64_t count) {
+  int64_t i;
+  if (!p) return;
+  for (i = 0; i < count; i++) p[i] = NAN;
+}
+
+void tt_irt1(TTIRT_INT d, TTIRT_INT *n, double *xs, TTIRT_INT *ttrank, double *ttcore, TTIRT_INT M,
+             double *q, double *z, double *lPz) {
+  int64_t *n64, *r64, k;
+  int mode = TTIRT_MODE_FAST, first = 0, ndev = 1, rc;
+  const char *e;
+
+  if (d < 1 || M < 0 || !n || !xs || !ttrank || !ttcore || (M > 0 && (!q || !z || !lPz))) {
+    fprintf(stderr, "tt_irt1[b200]: invalid arguments\n");
+    if (d >= 1 && M > 0) { nan_fill(z, (int64_t)M * d); nan_fill(lPz, M); }
+    return;
+  }
+  if (M == 0) return;
+  n64 = (int64_t *)malloc(sizeof(int64_t) * (size_t)d);
+  r64 = (int64_t *)malloc(sizeof(int64_t) * ((size_t)d + 1));
+  if (!n64 || !r64) {
+    fprintf(stderr, "tt_irt1[b200]: out of host memory\n");
+    free(n64); free(r64);
+    nan_fill(z, (int64_t)M * d); nan_fill(lPz, M);
+    return;
+  }
+  for (k = 0; k < d; k++) n64[k] = (int64_t)n[k];
+  for (k = 0; k <= d; k++) r64[k] = (int64_t)ttrank[k];
+
+  if ((e = getenv("TTIRT_MODE")) != NULL && strcmp(e, "strict") == 0) mode = TTIRT_MODE_STRICT;
+  if ((e = getenv("TTIRT_DEVICE")) != NULL) first = atoi(e);
+  if ((e = getenv("TTIRT_DEVICES")) != NULL) {
+    if (strcmp(e, "all") == 0) ndev = ttirt_device_count() - first;
+    else ndev = atoi(e);
+    if (ndev < 1) ndev = 1;
+  }
+  /* never more devices than 64-sample blocks */
+  while (ndev > 1 && (int64_t)M / ndev < 64) ndev--;
+
+  rc = ttirt_run_host(d, n64, xs, r64, ttcore, M, q, z, lPz, NULL, mode, first, ndev);
+  if (rc != 0) {
+    nan_fill(z, (int64_t)M * d);
+    nan_fill(lPz, M);
+  } else if (getenv("TTIRT_VERBOSE") != NULL) {
+    fprintf(stderr, "tt_irt1[b200]: M=%lld d=%lld mode=%s devices=%d launches=%lld\n", (long long)M, (long long)d,
+            mode == TTIRT_MODE_STRICT ? "strict" : "fast", ndev, (long long)ttirt_kernel_launches());
+  }
+  free(n64);
+  free(r64);
+}

@@ -1,0 +1,76 @@
+// Shared declarations for the B200-native tt_irt1 engine (internal; the public C-ABI is include/tt_irt1.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ttirt {
+
+// Per-dimension metadata, resident on the device next to the cores.
+struct DimInfo {
+  int n;            // grid size n_k
+  int r0, r1;       // r_k, r_{k+1}
+  int pad;
+  int64_t off_x;    // start of grid k in xs        (reference psxs, tt_irt1_int32.c:43-49)
+  int64_t off_c;    // start of core k in ttcore    (reference pstt, :55-57)
+  int64_t off_p;    // start of P_k (r_k x n_k)     in the stacked product buffer
+  int64_t off_m;    // start of C_k (r_{k+1})       in the stacked marginal buffer
+};
+
+struct CellOut {
+  double xk, w1, w2, logp;
+};
+
+// The reference's per-sample tail (tt_irt1_int32.c:146-165): closed-form root of the piecewise-quadratic
+// CDF on [x1, x2], interpolation weights and log of the interpolated conditional density.  Written with
+// explicit round-to-nearest intrinsics so that no FMA contraction can change the operation order: the
+// reference's formula cancels and is mirrored verbatim, not "fixed".
+__device__ __forceinline__ CellOut invert_cell(double qk, double cdf_lo, double c1, double c2, double x1, double x2) {
+  CellOut o;
+  const double hq = __dsub_rn(x2, x1);
+  const double Aq = __ddiv_rn(__dmul_rn(0.5, __dsub_rn(c2, c1)), hq);
+  const double Bq = __ddiv_rn(__dsub_rn(__dmul_rn(c1, x2), __dmul_rn(c2, x1)), hq);
+  double Dq = __dadd_rn(__dmul_rn(__dmul_rn(2.0, Aq), x1), Bq);
+  Dq = __dmul_rn(Dq, Dq);
+  const double dq = __dsub_rn(qk, cdf_lo);
+  Dq = __dadd_rn(Dq, __dmul_rn(__dmul_rn(4.0, Aq), dq));
+  const double root = __dsqrt_rn(fabs(Dq));
+  double xk = __ddiv_rn(__dmul_rn(0.5, __dadd_rn(-Bq, root)), Aq);
+  if (Aq == 0.0) xk = __dadd_rn(x1, __ddiv_rn(dq, Bq));
+  o.xk = xk;
+  o.w1 = __ddiv_rn(__dsub_rn(x2, xk), hq);
+  o.w2 = __ddiv_rn(__dsub_rn(xk, x1), hq);
+  o.logp = log(fabs(__dadd_rn(__dmul_rn(c1, o.w1), __dmul_rn(c2, o.w2))));
+  return o;
+}
+
+// Arguments of one fused "transition" launch of the fast path: interface update through dimension k
+// (binned by the interval chosen there) followed by the whole conditional step of dimension k+1.
+struct TransArgs {
+  const double *core;        // core_k, column-major r0 x n0 x r1
+  const double *pnext;       // P_{k+1}, column-major r1 x n1
+  const double *xnext;       // grid of dimension k+1 (n1)
+  int r0, n0, r1, n1;
+  int last;                  // k+1 == d-1: no further interface update
+  int rows;                  // samples in this chunk
+  double *F;                 // left-interface rows, rows x ldf, updated in place
+  int ldf;
+  const int *perm;           // samples ordered by the interval chosen in dimension k
+  const int *bin_start;      // n0 entries (+1)
+  const int *bin_tile_start; // n0 entries (+1), prefix of ceil(count / rows per CTA tile)
+  int *idx;                  // per sample: interval index (out: dimension k+1)
+  double *w1, *w2;           // per sample: interpolation weights (in: dimension k, out: k+1)
+  double *lp;                // per sample: running log-density
+  const double *q;           // column k+1 of q for this chunk
+  double *z;                 // column k+1 of z
+  int32_t *idx_out;          // column k+1 of the exported index array (may be NULL)
+  double *lpz;               // final log-density (written when last)
+  int *hist_next;            // n1-1 counters for binning dimension k+1 (unused when last)
+};
+
+// fast-path shape classes: (rank tiles of 8, grid tiles of 8)
+int fast_class_for(int rmax, int nmax);             // -1: shape outside the fast path
+int fast_rows_per_cta(int cls);
+cudaError_t launch_transition(int cls, const TransArgs &a, int sm_count, cudaStream_t st);
+cudaError_t fast_init(int device);                  // opt in to large dynamic shared memory
+
+}  // namespace ttirt

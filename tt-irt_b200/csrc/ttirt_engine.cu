@@ -1,0 +1,585 @@
+// B200-native engine behind the tt_irt1 C-ABI (include/tt_irt1.h).
+//
+//   model_create : upload grid + cores, right-to-left marginalisation sweep on the device
+//                  (reference tt_irt1_int32.c:59-82), stage-0 tables.
+//   sample       : per chunk of samples
+//                    fast   : stage-0 kernel, then per dimension {bin scan, bin scatter, fused transition}
+//                    strict : one thread per sample, every operation in the reference's order
+//                  host-buffer mode adds a chunked H2D / compute / D2H pipeline over several streams.
+// There is no CPU fallback anywhere in this file: without a device every entry point fails.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/tt_irt1.h"
+#include "ttirt_common.cuh"
+
+using namespace ttirt;
+
+// ------------------------------------------------------------------------------------------------
+// errors, counters, options
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+static std::atomic<int64_t> g_chunk{0};
+
+static int fail(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  if (getenv("TTIRT_QUIET") == nullptr) fprintf(stderr, "tt_irt1[b200]: %s\n", g_err);
+  return -1;
+}
+
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+#define LAUNCHED() g_launches.fetch_add(1, std::memory_order_relaxed)
+
+static int64_t default_chunk() {
+  int64_t c = g_chunk.load();
+  if (c > 0) return c;
+  const char *e = getenv("TTIRT_CHUNK");
+  if (e && atoll(e) > 0) return atoll(e);
+  return (int64_t)1 << 20;
+}
+
+// ------------------------------------------------------------------------------------------------
+// model
+// ------------------------------------------------------------------------------------------------
+constexpr int kSlots = 3;
+
+struct Workspace {
+  int64_t cap = 0;       // samples
+  bool strict = false, host = false, want_idx = false;
+  double *F = nullptr;   // cap x ldf
+  int *idx = nullptr, *perm = nullptr;
+  double *w1 = nullptr, *w2 = nullptr, *lp = nullptr;
+  int *hist = nullptr;   // d x nbpad
+  int *bin_start = nullptr, *bin_tile_start = nullptr, *cursor = nullptr;
+  // strict scratch
+  double *left = nullptr, *pbuf = nullptr, *cbuf = nullptr;
+  // host-mode staging
+  double *q = nullptr, *z = nullptr, *lpz = nullptr;
+  int32_t *idx_out = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+};
+
+struct ttirt_model {
+  int device = 0, sm_count = 148;
+  int64_t d = 0;
+  std::vector<int64_t> n, r;
+  std::vector<DimInfo> dims;
+  int64_t rmax = 1, nmax = 2, nbpad = 0, sum_pk = 0, sum_mg = 0;
+  int ldf = 8;
+  int fast_cls = -1;
+  double *d_xs = nullptr, *d_core = nullptr, *d_pk = nullptr, *d_marg = nullptr;
+  double *d_p0 = nullptr, *d_cdf0 = nullptr;
+  DimInfo *d_dims = nullptr;
+  Workspace ws[kSlots];
+};
+
+static void ws_free(Workspace &w) {
+  cudaFree(w.F); cudaFree(w.idx); cudaFree(w.perm); cudaFree(w.w1); cudaFree(w.w2); cudaFree(w.lp);
+  cudaFree(w.hist); cudaFree(w.bin_start); cudaFree(w.bin_tile_start); cudaFree(w.cursor);
+  cudaFree(w.left); cudaFree(w.pbuf); cudaFree(w.cbuf);
+  cudaFree(w.q); cudaFree(w.z); cudaFree(w.lpz); cudaFree(w.idx_out);
+  if (w.stream) cudaStreamDestroy(w.stream);
+  if (w.done) cudaEventDestroy(w.done);
+  w = Workspace();
+}
+
+static int ws_ensure(ttirt_model *md, Workspace &w, int64_t rows, bool strict, bool host, bool want_idx) {
+  if (w.cap >= rows && (w.strict || !strict) && (w.host || !host) && (w.want_idx || !(host && want_idx))) return 0;
+  cudaStream_t keep_s = w.stream; cudaEvent_t keep_e = w.done;
+  w.stream = nullptr; w.done = nullptr;
+  const bool s = strict || w.strict, h = host || w.host, wi = want_idx || w.want_idx;
+  const int64_t cap = rows > w.cap ? rows : w.cap;
+  ws_free(w);
+  w.stream = keep_s; w.done = keep_e;
+  w.cap = cap; w.strict = s; w.host = h; w.want_idx = wi;
+  const int64_t d = md->d;
+  CK(cudaMalloc(&w.F, sizeof(double) * cap * md->ldf));
+  CK(cudaMalloc(&w.idx, sizeof(int) * cap));
+  CK(cudaMalloc(&w.perm, sizeof(int) * cap));
+  CK(cudaMalloc(&w.w1, sizeof(double) * cap));
+  CK(cudaMalloc(&w.w2, sizeof(double) * cap));
+  CK(cudaMalloc(&w.lp, sizeof(double) * cap));
+  CK(cudaMalloc(&w.hist, sizeof(int) * d * md->nbpad));
+  CK(cudaMalloc(&w.bin_start, sizeof(int) * (md->nbpad + 1)));
+  CK(cudaMalloc(&w.bin_tile_start, sizeof(int) * (md->nbpad + 1)));
+  CK(cudaMalloc(&w.cursor, sizeof(int) * (md->nbpad + 1)));
+  if (s) {
+    CK(cudaMalloc(&w.left, sizeof(double) * 2 * md->rmax * cap));
+    CK(cudaMalloc(&w.pbuf, sizeof(double) * md->nmax * cap));
+    CK(cudaMalloc(&w.cbuf, sizeof(double) * md->nmax * cap));
+  }
+  if (h) {
+    CK(cudaMalloc(&w.q, sizeof(double) * cap * d));
+    CK(cudaMalloc(&w.z, sizeof(double) * cap * d));
+    CK(cudaMalloc(&w.lpz, sizeof(double) * cap));
+    if (wi) CK(cudaMalloc(&w.idx_out, sizeof(int32_t) * cap * d));
+  }
+  if (!w.stream) CK(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+  if (!w.done) CK(cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels: sweep
+// ------------------------------------------------------------------------------------------------
+// P[i] = sum_l core[i + l*rows] * marg[l], one sequential chain per output element in l order and
+// without FMA contraction: the netlib dgemm order the oracle pins (reference :72).
+__global__ void sweep_contract_kernel(const double *__restrict__ core, const double *__restrict__ marg, double *P,
+                                      int rows, int rr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  double s = 0.0;
+  for (int l = 0; l < rr; l++) s = __dadd_rn(s, __dmul_rn(marg[l], core[i + (int64_t)l * rows]));
+  P[i] = s;
+}
+
+// C_{k-1}[a] = sum_j (P[a,j] + P[a,j+1]) * h_j * 0.5, accumulated in j order (reference :76-81).
+__global__ void sweep_integrate_kernel(const double *__restrict__ P, const double *__restrict__ x, double *marg_out,
+                                       int rk, int nk) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= rk) return;
+  double s = 0.0;
+  for (int j = 0; j + 1 < nk; j++) {
+    const double h = __dsub_rn(x[j + 1], x[j]);
+    s = __dadd_rn(s, __dmul_rn(__dmul_rn(__dadd_rn(P[a + j * rk], P[a + (j + 1) * rk]), h), 0.5));
+  }
+  marg_out[a] = s;
+}
+
+// One sample's conditional on a grid, strict arithmetic (reference :105-130): abs, trapezoid prefix,
+// zero-mass fallback, reciprocal normalisation.  p and cdf are strided arrays (stride st).
+__device__ void strict_cdf(double *p, double *cdf, const double *x, int nk, int64_t st) {
+  cdf[0] = 0.0;
+  for (int j = 1; j < nk; j++) {
+    const double hq = __dmul_rn(__dsub_rn(x[j], x[j - 1]), 0.5);
+    double c = cdf[(j - 1) * st];
+    c = __dadd_rn(c, __dmul_rn(hq, p[(j - 1) * st]));
+    c = __dadd_rn(c, __dmul_rn(hq, p[j * st]));
+    cdf[j * st] = c;
+  }
+  if (cdf[(nk - 1) * st] == 0.0) {
+    const double u = __ddiv_rn(1.0, (double)(nk - 1));
+    for (int j = 0; j < nk; j++) { p[j * st] = __dmul_rn(1.0, u); cdf[j * st] = __dmul_rn((double)j, u); }
+  }
+  const double s = __ddiv_rn(1.0, cdf[(nk - 1) * st]);
+  for (int j = 0; j < nk; j++) { cdf[j * st] = __dmul_rn(cdf[j * st], s); p[j * st] = __dmul_rn(p[j * st], s); }
+}
+
+// bisection with strict '>' (reference :134-142)
+__device__ __forceinline__ int strict_search(const double *cdf, int nk, int64_t st, double qk) {
+  int lo = 0, hi = nk - 1;
+  while (hi - lo > 1) {
+    const int mid = (int)((double)(lo + hi) * 0.5);
+    if (qk > cdf[mid * st]) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// Stage-0 tables: the first conditional is the same for every sample (r_0 = 1, left interface {1}).
+__global__ void stage0_table_kernel(const double *__restrict__ P0, const double *__restrict__ x, double *p0, double *cdf0, int n0) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  for (int j = 0; j < n0; j++) p0[j] = fabs(__dadd_rn(0.0, __dmul_rn(P0[j], 1.0)));
+  strict_cdf(p0, cdf0, x, n0, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels: strict path (any shape).  One thread per sample, all dimensions, reference operation order.
+// Scratch is sample-minor so that neighbouring threads touch neighbouring addresses.
+// ------------------------------------------------------------------------------------------------
+__global__ void strict_kernel(const DimInfo *__restrict__ dims, int d, const double *__restrict__ xs,
+                              const double *__restrict__ core, const double *__restrict__ pk, int rows,
+                              const double *__restrict__ q, int64_t ldq, double *z, int64_t ldz, double *lpz,
+                              int32_t *idx_out, double *left, double *pbuf, double *cbuf, int rmax) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= rows) return;
+  const int64_t st = rows;
+  double *la = left + m, *lb = left + (int64_t)rmax * rows + m;
+  double *p = pbuf + m, *cdf = cbuf + m;
+  la[0] = 1.0;
+  double lp = 0.0;
+  for (int k = 0; k < d; k++) {
+    const DimInfo di = dims[k];
+    const int rk = di.r0, nk = di.n, rn = di.r1;
+    const double *x = xs + di.off_x, *P = pk + di.off_p, *ck = core + di.off_c;
+    const double qk = q[m + ldq * k];
+    for (int j = 0; j < nk; j++) {
+      double s = 0.0;
+      for (int a = 0; a < rk; a++) s = __dadd_rn(s, __dmul_rn(P[a + j * rk], la[a * st]));
+      p[j * st] = fabs(s);
+    }
+    strict_cdf(p, cdf, x, nk, st);
+    const int lo = strict_search(cdf, nk, st, qk);
+    const double c1 = p[lo * st], c2 = p[(lo + 1) * st];
+    const CellOut o = invert_cell(qk, cdf[lo * st], c1, c2, x[lo], x[lo + 1]);
+    z[m + ldz * k] = o.xk;
+    if (idx_out) idx_out[m + ldz * k] = lo;
+    lp = __dadd_rn(lp, o.logp);
+    if (k < d - 1) {
+      for (int b = 0; b < rn; b++) {
+        const double *s1 = ck + (int64_t)lo * rk + (int64_t)b * rk * nk, *s2 = s1 + rk;
+        double s = 0.0;
+        for (int a = 0; a < rk; a++) {
+          double tv = __dmul_rn(o.w1, s1[a]);
+          tv = __dadd_rn(tv, __dmul_rn(o.w2, s2[a]));
+          s = __dadd_rn(s, __dmul_rn(tv, la[a * st]));
+        }
+        lb[b * st] = s;
+      }
+      double *tmp = la; la = lb; lb = tmp;
+    }
+  }
+  lpz[m] = lp;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels: fast path, stage 0 and binning
+// ------------------------------------------------------------------------------------------------
+__global__ void stage0_kernel(const double *__restrict__ p0, const double *__restrict__ cdf0, const double *__restrict__ x,
+                              int n0, int rows, const double *__restrict__ q, double *z, int32_t *idx_out, int *idx,
+                              double *w1, double *w2, double *lp, double *lpz, double *F, int ldf, int *hist, int last) {
+  extern __shared__ double sm[];
+  double *sp = sm, *sc = sm + n0, *sx = sm + 2 * n0;
+  int *sh = reinterpret_cast<int *>(sm + 3 * n0);
+  for (int i = threadIdx.x; i < n0; i += blockDim.x) { sp[i] = p0[i]; sc[i] = cdf0[i]; sx[i] = x[i]; sh[i] = 0; }
+  __syncthreads();
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m < rows) {
+    const double qk = q[m];
+    const int lo = strict_search(sc, n0, 1, qk);
+    const CellOut o = invert_cell(qk, sc[lo], sp[lo], sp[lo + 1], sx[lo], sx[lo + 1]);
+    z[m] = o.xk;
+    if (idx_out) idx_out[m] = lo;
+    const double l0 = __dadd_rn(0.0, o.logp);
+    if (last) {
+      lpz[m] = l0;
+    } else {
+      idx[m] = lo; w1[m] = o.w1; w2[m] = o.w2; lp[m] = l0;
+      double2 *f = reinterpret_cast<double2 *>(F + (size_t)m * ldf);
+      f[0] = make_double2(1.0, 0.0); f[1] = make_double2(0.0, 0.0);
+      f[2] = make_double2(0.0, 0.0); f[3] = make_double2(0.0, 0.0);
+      atomicAdd(&sh[lo], 1);
+    }
+  }
+  if (!last) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < n0 - 1; i += blockDim.x)
+      if (sh[i]) atomicAdd(hist + i, sh[i]);
+  }
+}
+
+// exclusive scans of the interval histogram: sorted-row offsets and CTA-tile offsets per bin
+__global__ void bin_scan_kernel(const int *__restrict__ hist, int nb, int rows_per_tile, int *bin_start,
+                                int *bin_tile_start, int *cursor) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int s = 0, t = 0;
+  for (int b = 0; b < nb; b++) {
+    bin_start[b] = s; bin_tile_start[b] = t; cursor[b] = s;
+    const int c = hist[b];
+    s += c; t += (c + rows_per_tile - 1) / rows_per_tile;
+  }
+  bin_start[nb] = s; bin_tile_start[nb] = t;
+}
+
+// counting-sort scatter: perm[position] = sample, positions grouped by interval
+__global__ void bin_scatter_kernel(const int *__restrict__ idx, int rows, int nb, int *cursor, int *perm) {
+  extern __shared__ int sh[];  // nb counts, then nb bases
+  int *cnt = sh, *base = sh + nb;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) cnt[i] = 0;
+  __syncthreads();
+  constexpr int PER = 4;
+  int myb[PER], myr[PER];
+  const int m0 = (blockIdx.x * blockDim.x) * PER + threadIdx.x;
+#pragma unroll
+  for (int u = 0; u < PER; u++) {
+    const int m = m0 + u * blockDim.x;
+    myb[u] = -1;
+    if (m < rows) { myb[u] = idx[m]; myr[u] = atomicAdd(&cnt[myb[u]], 1); }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) base[i] = cnt[i] ? atomicAdd(cursor + i, cnt[i]) : 0;
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < PER; u++) {
+    const int m = m0 + u * blockDim.x;
+    if (myb[u] >= 0) perm[base[myb[u]] + myr[u]] = m;
+  }
+}
+
+__global__ void fill_nan_kernel(double *p, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = __longlong_as_double(0x7ff8000000000000LL);
+}
+
+// ------------------------------------------------------------------------------------------------
+// model create / destroy
+// ------------------------------------------------------------------------------------------------
+extern "C" int ttirt_device_count(void) {
+  int c = 0;
+  if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return c;
+}
+
+extern "C" void ttirt_model_destroy(ttirt_model *md) {
+  if (!md) return;
+  cudaSetDevice(md->device);
+  for (auto &w : md->ws) ws_free(w);
+  cudaFree(md->d_xs); cudaFree(md->d_core); cudaFree(md->d_pk); cudaFree(md->d_marg);
+  cudaFree(md->d_p0); cudaFree(md->d_cdf0); cudaFree(md->d_dims);
+  delete md;
+}
+
+static int model_build(ttirt_model *md, const int64_t *n, const double *xs, const int64_t *rk, const double *core) {
+  const int64_t d = md->d;
+  if (rk[0] != 1 || rk[d] != 1) return fail("ttrank[0] and ttrank[d] must be 1 (got %lld, %lld)", (long long)rk[0], (long long)rk[d]);
+  md->n.assign(n, n + d);
+  md->r.assign(rk, rk + d + 1);
+  md->dims.resize(d);
+  int64_t ox = 0, oc = 0, op = 0, om = 0;
+  for (int64_t k = 0; k < d; k++) {
+    if (n[k] < 2) return fail("n[%lld] = %lld: every grid needs at least 2 points", (long long)k, (long long)n[k]);
+    if (rk[k] < 1 || rk[k + 1] < 1) return fail("non-positive TT rank at %lld", (long long)k);
+    if (n[k] > (1 << 20) || rk[k] > (1 << 14)) return fail("shape too large at dimension %lld", (long long)k);
+    DimInfo &di = md->dims[k];
+    di.n = (int)n[k]; di.r0 = (int)rk[k]; di.r1 = (int)rk[k + 1]; di.pad = 0;
+    di.off_x = ox; di.off_c = oc; di.off_p = op; di.off_m = om;
+    ox += n[k]; oc += rk[k] * n[k] * rk[k + 1]; op += rk[k] * n[k]; om += rk[k + 1];
+    if (rk[k + 1] > md->rmax) md->rmax = rk[k + 1];
+    if (n[k] > md->nmax) md->nmax = n[k];
+  }
+  md->sum_pk = op; md->sum_mg = om;
+  md->nbpad = (md->nmax + 7) & ~(int64_t)7;
+  md->fast_cls = fast_class_for((int)md->rmax, (int)md->nmax);
+  md->ldf = (int)((md->rmax + 7) & ~(int64_t)7);
+  if (md->ldf < 8) md->ldf = 8;
+
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, md->device));
+  if (prop.major < 10) return fail("device %d (%s, sm_%d%d) is not a Blackwell B200-class GPU", md->device, prop.name, prop.major, prop.minor);
+  md->sm_count = prop.multiProcessorCount;
+  CK(fast_init(md->device));
+
+  CK(cudaMalloc(&md->d_xs, sizeof(double) * ox));
+  CK(cudaMalloc(&md->d_core, sizeof(double) * oc));
+  CK(cudaMalloc(&md->d_pk, sizeof(double) * op));
+  CK(cudaMalloc(&md->d_marg, sizeof(double) * om));
+  CK(cudaMalloc(&md->d_p0, sizeof(double) * n[0]));
+  CK(cudaMalloc(&md->d_cdf0, sizeof(double) * n[0]));
+  CK(cudaMalloc(&md->d_dims, sizeof(DimInfo) * d));
+  CK(cudaMemcpy(md->d_xs, xs, sizeof(double) * ox, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(md->d_core, core, sizeof(double) * oc, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(md->d_dims, md->dims.data(), sizeof(DimInfo) * d, cudaMemcpyHostToDevice));
+
+  // right-to-left sweep: C_{d-1} = {1}; P_k = core_k x_3 C_k; C_{k-1} = trapezoid(P_k)
+  const double one = 1.0;
+  CK(cudaMemcpy(md->d_marg + md->dims[d - 1].off_m, &one, sizeof(double), cudaMemcpyHostToDevice));
+  for (int64_t k = d - 1; k >= 0; k--) {
+    const DimInfo &di = md->dims[k];
+    const int rows = di.r0 * di.n;
+    sweep_contract_kernel<<<(rows + 127) / 128, 128>>>(md->d_core + di.off_c, md->d_marg + di.off_m, md->d_pk + di.off_p, rows, di.r1);
+    LAUNCHED();
+    if (k > 0) {
+      sweep_integrate_kernel<<<(di.r0 + 127) / 128, 128>>>(md->d_pk + di.off_p, md->d_xs + di.off_x,
+                                                           md->d_marg + md->dims[k - 1].off_m, di.r0, di.n);
+      LAUNCHED();
+    }
+  }
+  stage0_table_kernel<<<1, 32>>>(md->d_pk, md->d_xs, md->d_p0, md->d_cdf0, md->dims[0].n);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  return 0;
+}
+
+extern "C" ttirt_model *ttirt_model_create(int64_t d, const int64_t *n, const double *xs, const int64_t *ttrank,
+                                           const double *ttcore, int device) {
+  g_err[0] = 0;
+  if (d < 1 || !n || !xs || !ttrank || !ttcore) { fail("bad arguments to ttirt_model_create"); return nullptr; }
+  int cnt = ttirt_device_count();
+  if (cnt <= 0) { fail("no CUDA device available (this library has no CPU fallback)"); return nullptr; }
+  if (device < 0 || device >= cnt) { fail("device %d out of range (%d visible)", device, cnt); return nullptr; }
+  if (cudaSetDevice(device) != cudaSuccess) { fail("cudaSetDevice(%d) failed", device); return nullptr; }
+  ttirt_model *md = new ttirt_model();
+  md->device = device; md->d = d;
+  if (model_build(md, n, xs, ttrank, ttcore) != 0) { ttirt_model_destroy(md); return nullptr; }
+  return md;
+}
+
+extern "C" int ttirt_model_get_sweep(const ttirt_model *md, double *pk_out, double *marg_out) {
+  if (!md) return fail("null model");
+  CK(cudaSetDevice(md->device));
+  if (pk_out) CK(cudaMemcpy(pk_out, md->d_pk, sizeof(double) * md->sum_pk, cudaMemcpyDeviceToHost));
+  if (marg_out) CK(cudaMemcpy(marg_out, md->d_marg, sizeof(double) * md->sum_mg, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one chunk, device-resident buffers, enqueued on st
+// ------------------------------------------------------------------------------------------------
+static int run_chunk(ttirt_model *md, Workspace &w, int64_t rows, const double *q, int64_t ldq, double *z, int64_t ldz,
+                     double *lpz, int32_t *idx_out, int mode, cudaStream_t st) {
+  const int d = (int)md->d;
+  if (rows <= 0) return 0;
+  if (mode == TTIRT_MODE_STRICT || md->fast_cls < 0) {
+    strict_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(md->d_dims, d, md->d_xs, md->d_core, md->d_pk, (int)rows, q, ldq,
+                                                                  z, ldz, lpz, idx_out, w.left, w.pbuf, w.cbuf, (int)md->rmax);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    return 0;
+  }
+  const int rows_tile = fast_rows_per_cta(md->fast_cls);
+  const int nbpad = (int)md->nbpad;
+  if (d > 1) CK(cudaMemsetAsync(w.hist, 0, sizeof(int) * d * nbpad, st));
+  {
+    const DimInfo &d0 = md->dims[0];
+    const size_t sm = sizeof(double) * 3 * d0.n + sizeof(int) * d0.n;
+    stage0_kernel<<<(unsigned)((rows + 255) / 256), 256, sm, st>>>(md->d_p0, md->d_cdf0, md->d_xs + d0.off_x, d0.n, (int)rows, q, z,
+                                                                   idx_out, w.idx, w.w1, w.w2, w.lp, lpz, w.F, md->ldf, w.hist, d == 1);
+    LAUNCHED();
+    CK(cudaGetLastError());
+  }
+  for (int k = 0; k + 1 < d; k++) {
+    const DimInfo &dk = md->dims[k], &dn = md->dims[k + 1];
+    const int nb = dk.n - 1;
+    bin_scan_kernel<<<1, 32, 0, st>>>(w.hist + (size_t)k * nbpad, nb, rows_tile, w.bin_start, w.bin_tile_start, w.cursor);
+    LAUNCHED();
+    bin_scatter_kernel<<<(unsigned)((rows + 1023) / 1024), 256, sizeof(int) * 2 * nb, st>>>(w.idx, (int)rows, nb, w.cursor, w.perm);
+    LAUNCHED();
+    TransArgs a;
+    a.core = md->d_core + dk.off_c; a.pnext = md->d_pk + dn.off_p; a.xnext = md->d_xs + dn.off_x;
+    a.r0 = dk.r0; a.n0 = dk.n; a.r1 = dk.r1; a.n1 = dn.n;
+    a.last = (k + 1 == d - 1); a.rows = (int)rows; a.F = w.F; a.ldf = md->ldf;
+    a.perm = w.perm; a.bin_start = w.bin_start; a.bin_tile_start = w.bin_tile_start;
+    a.idx = w.idx; a.w1 = w.w1; a.w2 = w.w2; a.lp = w.lp;
+    a.q = q + ldq * (k + 1); a.z = z + ldz * (k + 1);
+    a.idx_out = idx_out ? idx_out + ldz * (k + 1) : nullptr;
+    a.lpz = lpz; a.hist_next = w.hist + (size_t)(k + 1) * nbpad;
+    CK(launch_transition(md->fast_cls, a, md->sm_count, st));
+    LAUNCHED();
+  }
+  return 0;
+}
+
+extern "C" int ttirt_sample_device(ttirt_model *md, int64_t M, const double *d_q, int64_t ldq, double *d_z, int64_t ldz,
+                                   double *d_lpz, int32_t *d_idx, int mode, void *stream) {
+  g_err[0] = 0;
+  if (!md) return fail("null model");
+  if (M < 0 || ldq < M || ldz < M) return fail("bad M / leading dimensions");
+  if (M == 0) return 0;
+  CK(cudaSetDevice(md->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool strict = (mode == TTIRT_MODE_STRICT) || md->fast_cls < 0;
+  const int64_t chunk = std::min<int64_t>(M, default_chunk());
+  Workspace &w = md->ws[0];
+  if (w.cap < chunk || (strict && !w.strict)) {
+    CK(cudaStreamSynchronize(st));  // a previous call on this stream may still use the old scratch
+    if (ws_ensure(md, w, chunk, strict, false, false) != 0) return -1;
+  }
+  for (int64_t m0 = 0; m0 < M; m0 += chunk) {
+    const int64_t rows = std::min(chunk, M - m0);
+    if (run_chunk(md, w, rows, d_q + m0, ldq, d_z + m0, ldz, d_lpz + m0, d_idx ? d_idx + m0 : nullptr, mode, st) != 0) return -1;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host buffers: chunked H2D -> kernels -> D2H over kSlots streams
+// ------------------------------------------------------------------------------------------------
+static int sample_host_rows(ttirt_model *md, int64_t m_begin, int64_t m_end, const double *h_q, double *h_z, double *h_lpz,
+                            int32_t *h_idx, int64_t ld, int mode) {
+  const int64_t M = m_end - m_begin;
+  if (M <= 0) return 0;
+  CK(cudaSetDevice(md->device));
+  const int d = (int)md->d;
+  const bool strict = (mode == TTIRT_MODE_STRICT) || md->fast_cls < 0;
+  int64_t chunk = default_chunk();
+  if (M < chunk * kSlots) chunk = std::max<int64_t>((M + kSlots - 1) / kSlots, std::min<int64_t>(M, 1 << 16));
+  const int64_t nchunks = (M + chunk - 1) / chunk;
+  const int nslots = (int)std::min<int64_t>(kSlots, nchunks);
+  for (int s = 0; s < nslots; s++)
+    if (ws_ensure(md, md->ws[s], chunk, strict, true, h_idx != nullptr) != 0) return -1;
+  for (int64_t c = 0; c < nchunks; c++) {
+    Workspace &w = md->ws[c % kSlots];
+    const int64_t m0 = m_begin + c * chunk, rows = std::min(chunk, m_end - m0);
+    if (c >= kSlots) CK(cudaEventSynchronize(w.done));
+    CK(cudaMemcpy2DAsync(w.q, sizeof(double) * rows, h_q + m0, sizeof(double) * ld, sizeof(double) * rows, d,
+                         cudaMemcpyHostToDevice, w.stream));
+    if (run_chunk(md, w, rows, w.q, rows, w.z, rows, w.lpz, h_idx ? w.idx_out : nullptr, mode, w.stream) != 0) return -1;
+    CK(cudaMemcpy2DAsync(h_z + m0, sizeof(double) * ld, w.z, sizeof(double) * rows, sizeof(double) * rows, d,
+                         cudaMemcpyDeviceToHost, w.stream));
+    CK(cudaMemcpyAsync(h_lpz + m0, w.lpz, sizeof(double) * rows, cudaMemcpyDeviceToHost, w.stream));
+    if (h_idx)
+      CK(cudaMemcpy2DAsync(h_idx + m0, sizeof(int32_t) * ld, w.idx_out, sizeof(int32_t) * rows, sizeof(int32_t) * rows, d,
+                           cudaMemcpyDeviceToHost, w.stream));
+    CK(cudaEventRecord(w.done, w.stream));
+  }
+  for (int s = 0; s < nslots; s++) CK(cudaStreamSynchronize(md->ws[s].stream));
+  return 0;
+}
+
+extern "C" int ttirt_sample_host(ttirt_model *md, int64_t M, const double *h_q, double *h_z, double *h_lpz, int32_t *h_idx,
+                                 int64_t ld, int mode) {
+  g_err[0] = 0;
+  if (!md) return fail("null model");
+  if (M < 0 || ld < M) return fail("bad M / leading dimension");
+  return sample_host_rows(md, 0, M, h_q, h_z, h_lpz, h_idx, ld, mode);
+}
+
+extern "C" int ttirt_run_host(int64_t d, const int64_t *n, const double *xs, const int64_t *ttrank, const double *ttcore,
+                              int64_t M, const double *h_q, double *h_z, double *h_lpz, int32_t *h_idx, int mode,
+                              int first_device, int n_devices) {
+  g_err[0] = 0;
+  if (M < 0) return fail("negative M");
+  const int cnt = ttirt_device_count();
+  if (cnt <= 0) return fail("no CUDA device available (this library has no CPU fallback)");
+  if (n_devices <= 0 || first_device < 0 || first_device + n_devices > cnt)
+    return fail("device range [%d, %d) not available (%d visible)", first_device, first_device + n_devices, cnt);
+  if (M == 0) return 0;
+  if (n_devices == 1) {
+    ttirt_model *md = ttirt_model_create(d, n, xs, ttrank, ttcore, first_device);
+    if (!md) return -1;
+    const int rc = sample_host_rows(md, 0, M, h_q, h_z, h_lpz, h_idx, M, mode);
+    ttirt_model_destroy(md);
+    return rc;
+  }
+  // samples are independent: contiguous row shards, one host thread per device, no collective
+  std::vector<int> rcs(n_devices, 0);
+  std::vector<std::string> errs(n_devices);
+  std::vector<std::thread> th;
+  for (int g = 0; g < n_devices; g++) {
+    th.emplace_back([&, g]() {
+      const int64_t m0 = M * g / n_devices, m1 = M * (g + 1) / n_devices;
+      ttirt_model *md = ttirt_model_create(d, n, xs, ttrank, ttcore, first_device + g);
+      if (!md) { rcs[g] = -1; errs[g] = g_err; return; }
+      rcs[g] = sample_host_rows(md, m0, m1, h_q, h_z, h_lpz, h_idx, M, mode);
+      if (rcs[g] != 0) errs[g] = g_err;
+      ttirt_model_destroy(md);
+    });
+  }
+  for (auto &t : th) t.join();
+  for (int g = 0; g < n_devices; g++)
+    if (rcs[g] != 0) return fail("device %d: %s", first_device + g, errs[g].c_str());
+  return 0;
+}
+
+extern "C" int64_t ttirt_kernel_launches(void) { return g_launches.load(); }
+extern "C" const char *ttirt_last_error(void) { return g_err; }
+extern "C" void ttirt_set_chunk(int64_t samples) { g_chunk.store(samples > 0 ? samples : 0); }
