@@ -95,6 +95,13 @@ TTIRT_API int ttirt_run_host(int64_t d, const int64_t *n, const double *xs, cons
                    const double *ttcore, int64_t M, const double *h_q, double *h_z, double *h_lpz,
                    int32_t *h_idx, int mode, int first_device, int n_devices);
 
+/* Per-launch CUDA-event timing of the dominant kernel (the fused transition kernel) for calls to
+ * ttirt_sample_device on this model: enable(1) clears and starts, read() synchronises and returns the summed
+ * kernel time in ms, the number of launches timed and their algorithmic FP64 flops
+ * (rows * (4 r_k r_{k+1} + 2 r_{k+1} n_{k+1}) per launch). */
+TTIRT_API void ttirt_profile_enable(ttirt_model *model, int on);
+TTIRT_API int ttirt_profile_read(ttirt_model *model, double *ms_total, int64_t *launches, double *flops_total);
+
 /* Number of this library's kernels launched by the calling process so far (bench.py's gpu_launches). */
 TTIRT_API int64_t ttirt_kernel_launches(void);
 /* Last error message of the calling thread ("" if none). */

@@ -4,6 +4,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o fp64_peak fp64_peak.cu
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <cuda_runtime.h>
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
@@ -59,6 +60,7 @@ static double time_ms(F launch, int reps) {
 }
 
 int main(int argc, char **argv) {
+  bool quick = argc > 1 && std::string(argv[1]) == "--quick";
   int dev = 0; CK(cudaSetDevice(dev));
   cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, dev));
   int sms = p.multiProcessorCount;
@@ -66,9 +68,9 @@ int main(int argc, char **argv) {
   printf("{\"gpu\": \"%s\", \"sms\": %d", p.name, sms);
   double best_dfma = 0, best_dmma = 0;
   // burst (short) and sustained (seconds long) variants
-  for (int pass = 0; pass < 2; pass++) {
-    int iters = pass == 0 ? 20000 : 200000;
-    int reps = pass == 0 ? 5 : 10;
+  for (int pass = quick ? 1 : 0; pass < 2; pass++) {
+    int iters = pass == 0 ? 20000 : (quick ? 100000 : 200000);
+    int reps = pass == 0 ? 5 : (quick ? 3 : 10);
     for (int wpb = 4; wpb <= 8; wpb *= 2) {
       int blocks = sms * (wpb == 8 ? 2 : 4);
       int threads = wpb * 32;
@@ -84,7 +86,7 @@ int main(int argc, char **argv) {
     }
   }
   // single-warp-per-SMSP DMMA issue rate: 4 warps/SM, 1 block/SM -> cycles per DMMA
-  {
+  if (!quick) {
     int iters = 50000;
     double ms = time_ms([&] { dmma_kernel<16><<<sms, 128>>>(out, iters, 1.0000001, 1e-9); }, 5);
     double tf = 2.0 * 256 * 16 * (double)iters * sms * 4 / (ms * 1e-3) / 1e12;

@@ -90,6 +90,11 @@ struct ttirt_model {
   double *d_p0 = nullptr, *d_cdf0 = nullptr;
   DimInfo *d_dims = nullptr;
   Workspace ws[kSlots];
+  // optional per-launch timing of the dominant (transition) kernel, for bench.py's roofline
+  bool profile = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  size_t prof_used = 0;
+  double prof_flops = 0.0;
 };
 
 static void ws_free(Workspace &w) {
@@ -342,6 +347,7 @@ extern "C" void ttirt_model_destroy(ttirt_model *md) {
   if (!md) return;
   cudaSetDevice(md->device);
   for (auto &w : md->ws) ws_free(w);
+  for (auto &p : md->prof_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   cudaFree(md->d_xs); cudaFree(md->d_core); cudaFree(md->d_pk); cudaFree(md->d_marg);
   cudaFree(md->d_p0); cudaFree(md->d_cdf0); cudaFree(md->d_dims);
   delete md;
@@ -472,8 +478,21 @@ static int run_chunk(ttirt_model *md, Workspace &w, int64_t rows, const double *
     a.q = q + ldq * (k + 1); a.z = z + ldz * (k + 1);
     a.idx_out = idx_out ? idx_out + ldz * (k + 1) : nullptr;
     a.lpz = lpz; a.hist_next = w.hist + (size_t)(k + 1) * nbpad;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (md->profile) {
+      if (md->prof_used == md->prof_events.size()) {
+        cudaEvent_t x, y;
+        CK(cudaEventCreate(&x)); CK(cudaEventCreate(&y));
+        md->prof_events.emplace_back(x, y);
+      }
+      e0 = md->prof_events[md->prof_used].first; e1 = md->prof_events[md->prof_used].second;
+      md->prof_used++;
+      md->prof_flops += (double)rows * (4.0 * dk.r0 * dk.r1 + 2.0 * dk.r1 * dn.n);
+      CK(cudaEventRecord(e0, st));
+    }
     CK(launch_transition(md->fast_cls, a, md->sm_count, st));
     LAUNCHED();
+    if (e1) CK(cudaEventRecord(e1, st));
   }
   return 0;
 }
@@ -577,6 +596,27 @@ extern "C" int ttirt_run_host(int64_t d, const int64_t *n, const double *xs, con
   for (auto &t : th) t.join();
   for (int g = 0; g < n_devices; g++)
     if (rcs[g] != 0) return fail("device %d: %s", first_device + g, errs[g].c_str());
+  return 0;
+}
+
+extern "C" void ttirt_profile_enable(ttirt_model *md, int on) {
+  if (!md) return;
+  md->profile = on != 0; md->prof_used = 0; md->prof_flops = 0.0;
+}
+
+extern "C" int ttirt_profile_read(ttirt_model *md, double *ms_total, int64_t *launches, double *flops_total) {
+  if (!md) return fail("null model");
+  CK(cudaSetDevice(md->device));
+  double ms = 0.0;
+  for (size_t i = 0; i < md->prof_used; i++) {
+    CK(cudaEventSynchronize(md->prof_events[i].second));
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, md->prof_events[i].first, md->prof_events[i].second));
+    ms += t;
+  }
+  if (ms_total) *ms_total = ms;
+  if (launches) *launches = (int64_t)md->prof_used;
+  if (flops_total) *flops_total = md->prof_flops;
   return 0;
 }
 

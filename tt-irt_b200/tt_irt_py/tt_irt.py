@@ -50,6 +50,10 @@ def load_library():
         lib.ttirt_run_host.restype = c_int
         lib.ttirt_run_host.argtypes = [c_longlong, lp, dp, lp, dp, c_longlong, dp, dp, dp, c_void_p, c_int, c_int, c_int]
         lib.ttirt_kernel_launches.restype = c_longlong
+        lib.ttirt_profile_enable.restype = None
+        lib.ttirt_profile_enable.argtypes = [c_void_p, c_int]
+        lib.ttirt_profile_read.restype = c_int
+        lib.ttirt_profile_read.argtypes = [c_void_p, dp, lp, dp]
         lib.ttirt_last_error.restype = c_char_p
         lib.ttirt_device_count.restype = c_int
         lib.ttirt_set_chunk.restype = None
@@ -178,6 +182,17 @@ class Model(object):
         if rc != 0:
             _raise_last(self._lib, "ttirt_sample_host")
         return (Z, lPz, idx) if want_idx else (Z, lPz)
+
+    def profile_enable(self, on=True):
+        self._lib.ttirt_profile_enable(self._h, 1 if on else 0)
+
+    def profile_read(self):
+        """(summed transition-kernel ms, launches timed, algorithmic flops of those launches)."""
+        ms, n, fl = c_double(0), c_longlong(0), c_double(0)
+        from ctypes import byref
+        if self._lib.ttirt_profile_read(self._h, byref(ms), byref(n), byref(fl)) != 0:
+            _raise_last(self._lib, "ttirt_profile_read")
+        return ms.value, n.value, fl.value
 
     def sample_device(self, M, q_ptr, ldq, z_ptr, ldz, lpz_ptr, idx_ptr=None, mode=MODE_FAST, stream=None):
         """Raw device pointers (ints); enqueues on `stream` (cudaStream_t as int) without synchronising."""
