@@ -59,8 +59,13 @@ struct SmemLayout {
   static constexpr size_t bytes = sizeof(double) * (2 * SLAB + PN + 2 * 8 * NT) + sizeof(int) * (2 * (NBMAX + 1) + NBMAX);
 };
 
-template <int RT, int NT, int WARPS>
+// EXACT: r0 == r1 == 8*RT and ceil(n1/8) == NT, so every tile loop runs its full static trip count and no
+// guard branches are compiled in (the steady state of a uniform-rank TT).  TAIL1 (EXACT only): n1 == 8*(NT-1)+1,
+// the usual 2^p+1 grid; the lone last grid column is then a 4-lane DFMA dot product instead of a whole DMMA
+// column tile that would be 7/8 padding.
+template <int RT, int NT, int WARPS, bool EXACT, bool TAIL1>
 __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransArgs a) {
+  static_assert(EXACT || !TAIL1, "TAIL1 needs EXACT");
   using L = SmemLayout<RT, NT>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *slab0 = reinterpret_cast<double *>(smem_raw);
@@ -77,8 +82,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
   constexpr int NTHR = WARPS * 32, ROWS_CTA = WARPS * 16;
 
   const int r0 = a.r0, r1 = a.r1, n1 = a.n1, nb0 = a.n0 - 1;
-  const int KP0 = (r0 + 15) & ~15, KP1 = (r1 + 15) & ~15;
-  const int ks0 = (r0 + 7) >> 3, rt_act = (r1 + 7) >> 3, nt_act = (n1 + 7) >> 3;
+  constexpr int KP0 = L::KPMAX, KP1 = L::KPMAX;  // compile-time column pitch: B-fragment offsets fold into immediates
+  constexpr int NTD = TAIL1 ? NT - 1 : NT;       // grid column tiles computed by DMMA
+  const int ks0 = EXACT ? RT : (r0 + 7) >> 3, rt_act = EXACT ? RT : (r1 + 7) >> 3, nt_act = EXACT ? NT : (n1 + 7) >> 3;
 
   for (int i = tid; i <= nb0; i += NTHR) {
     bts[i] = a.bin_tile_start[i];
@@ -89,7 +95,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
     xg[i] = (i < n1) ? a.xnext[i] : 0.0;
     if (i < L::NBMAX) hist[i] = 0;
   }
-  stage_b(Ps, a.pnext, r1, n1, r1, KP1, 8 * nt_act, tid, NTHR);
+  stage_b(Ps, a.pnext, r1, n1, r1, KP1, 8 * NT, tid, NTHR);
   __syncthreads();
 
   const int total_tiles = bts[nb0];
@@ -109,16 +115,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
     } else {
       __syncthreads();  // every warp is done with the previous bin's slabs
       if (cur0 == b) {
-        stage_b(slab1, a.core + (int64_t)(b + 1) * r0, r0, r1, slab_cs, KP0, 8 * rt_act, tid, NTHR); cur1 = b + 1;
+        stage_b(slab1, a.core + (int64_t)(b + 1) * r0, r0, r1, slab_cs, KP0, 8 * RT, tid, NTHR); cur1 = b + 1;
       } else if (cur1 == b) {
-        stage_b(slab0, a.core + (int64_t)(b + 1) * r0, r0, r1, slab_cs, KP0, 8 * rt_act, tid, NTHR); cur0 = b + 1;
+        stage_b(slab0, a.core + (int64_t)(b + 1) * r0, r0, r1, slab_cs, KP0, 8 * RT, tid, NTHR); cur0 = b + 1;
       } else if (cur0 == b + 1) {
-        stage_b(slab1, a.core + (int64_t)b * r0, r0, r1, slab_cs, KP0, 8 * rt_act, tid, NTHR); cur1 = b;
+        stage_b(slab1, a.core + (int64_t)b * r0, r0, r1, slab_cs, KP0, 8 * RT, tid, NTHR); cur1 = b;
       } else if (cur1 == b + 1) {
-        stage_b(slab0, a.core + (int64_t)b * r0, r0, r1, slab_cs, KP0, 8 * rt_act, tid, NTHR); cur0 = b;
+        stage_b(slab0, a.core + (int64_t)b * r0, r0, r1, slab_cs, KP0, 8 * RT, tid, NTHR); cur0 = b;
       } else {
-        stage_b(slab0, a.core + (int64_t)b * r0, r0, r1, slab_cs, KP0, 8 * rt_act, tid, NTHR); cur0 = b;
-        stage_b(slab1, a.core + (int64_t)(b + 1) * r0, r0, r1, slab_cs, KP0, 8 * rt_act, tid, NTHR); cur1 = b + 1;
+        stage_b(slab0, a.core + (int64_t)b * r0, r0, r1, slab_cs, KP0, 8 * RT, tid, NTHR); cur0 = b;
+        stage_b(slab1, a.core + (int64_t)(b + 1) * r0, r0, r1, slab_cs, KP0, 8 * RT, tid, NTHR); cur1 = b + 1;
       }
       __syncthreads();
       if (cur0 == b) { sl_lo = slab0; sl_hi = slab1; } else { sl_lo = slab1; sl_hi = slab0; }
@@ -137,7 +143,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
     double2 fa[RT], fb[RT];
 #pragma unroll
     for (int j = 0; j < RT; j++)
-      if (j < ks0) {
+      if (EXACT || j < ks0) {
         fa[j] = *reinterpret_cast<const double2 *>(FA + 8 * j);
         fb[j] = *reinterpret_cast<const double2 *>(FB + 8 * j);
       }
@@ -148,7 +154,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
     for (int j = 0; j < RT; j++) { acc[0][j][0] = acc[0][j][1] = acc[1][j][0] = acc[1][j][1] = 0.0; }
 #pragma unroll
     for (int j = 0; j < RT; j++) {
-      if (j < ks0) {
+      if (EXACT || j < ks0) {
 #pragma unroll
         for (int e = 0; e < 2; e++) {
           const double xa = e ? fa[j].y : fa[j].x, xb = e ? fb[j].y : fb[j].x;
@@ -156,7 +162,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
           const int sw = (((2 * j + e) ^ (g & 3)) << 2) | t;
 #pragma unroll
           for (int jj = 0; jj < RT; jj++) {
-            if (jj < rt_act) {
+            if (EXACT || jj < rt_act) {
               const int off = (8 * jj + g) * KP0 + sw;
               const double b1 = sl_lo[off], b2 = sl_hi[off];
               dmma884(acc[0][jj][0], acc[0][jj][1], a1A, b1);
@@ -171,7 +177,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
     if (!a.last) {
 #pragma unroll
       for (int jj = 0; jj < RT; jj++)
-        if (jj < rt_act) {
+        if (EXACT || jj < rt_act) {
           if (vA) *reinterpret_cast<double2 *>(FA + 8 * jj) = make_double2(acc[0][jj][0], acc[0][jj][1]);
           if (vB) *reinterpret_cast<double2 *>(FB + 8 * jj) = make_double2(acc[1][jj][0], acc[1][jj][1]);
         }
@@ -183,14 +189,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
     for (int j = 0; j <= NT; j++) { c[0][j][0] = c[0][j][1] = c[1][j][0] = c[1][j][1] = 0.0; }
 #pragma unroll
     for (int jj = 0; jj < RT; jj++) {
-      if (jj < rt_act) {
+      if (EXACT || jj < rt_act) {
 #pragma unroll
         for (int e = 0; e < 2; e++) {
           const double a0 = acc[0][jj][e], a1 = acc[1][jj][e];
           const int sw = (((2 * jj + e) ^ (g & 3)) << 2) | t;
 #pragma unroll
-          for (int jn = 0; jn < NT; jn++) {
-            if (jn < nt_act) {
+          for (int jn = 0; jn < NTD; jn++) {
+            if (EXACT || jn < nt_act) {
               const double bv = Ps[(8 * jn + g) * KP1 + sw];
               dmma884(c[0][jn][0], c[0][jn][1], a0, bv);
               dmma884(c[1][jn][0], c[1][jn][1], a1, bv);
@@ -198,6 +204,24 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
           }
         }
       }
+    }
+
+    if (TAIL1) {
+      // last grid column (node 8*(NT-1)): quad-distributed dot product, result kept on lane t == 0
+      double tA = 0.0, tB = 0.0;
+#pragma unroll
+      for (int jj = 0; jj < RT; jj++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const double pv = Ps[(8 * (NT - 1)) * KP1 + ((2 * jj + e) << 2) + t];
+          tA = fma(acc[0][jj][e], pv, tA);
+          tB = fma(acc[1][jj][e], pv, tB);
+        }
+      }
+      tA += __shfl_xor_sync(FULL, tA, 1); tA += __shfl_xor_sync(FULL, tA, 2);
+      tB += __shfl_xor_sync(FULL, tB, 1); tB += __shfl_xor_sync(FULL, tB, 2);
+      c[0][NT - 1][0] = (t == 0) ? tA : 0.0;
+      c[1][NT - 1][0] = (t == 0) ? tB : 0.0;
     }
 
     // ---- (3) CDF, search: both 8-row tiles, all lanes ----------------------------------------------
@@ -213,7 +237,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
 #pragma unroll
       for (int jn = 0; jn < NT; jn++) {
         S0[jn] = 0.0; S1[jn] = 0.0;
-        if (jn < nt_act) {
+        if (TAIL1 && jn == NT - 1) continue;  // the lone last node starts no cell and is never a search candidate
+        if (EXACT || jn < nt_act) {
           const double p0 = c[i][jn][0], p1 = c[i][jn][1];
           const double var = (t == 0) ? c[i][jn + 1][0] : p0;
           const double nxt = __shfl_sync(FULL, var, (t == 3) ? lane - 3 : lane + 1);
@@ -235,8 +260,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
       const double sc = 1.0 / total;
       int cnt = 0;
 #pragma unroll
-      for (int jn = 0; jn < NT; jn++) {
-        if (jn < nt_act) {
+      for (int jn = 0; jn < NTD; jn++) {
+        if (EXACT || jn < nt_act) {
           const int node0 = 8 * jn + 2 * t;
           cnt += (node0 >= 1 && node0 <= n1 - 2 && qv > S0[jn] * sc) ? 1 : 0;
           cnt += (node0 + 1 <= n1 - 2 && qv > S1[jn] * sc) ? 1 : 0;
@@ -297,13 +322,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
   }
 }
 
-template <int RT, int NT, int WARPS>
-cudaError_t launch_one(const TransArgs &a, int sm_count, cudaStream_t st) {
+template <int RT, int NT, int WARPS, bool EXACT, bool TAIL1>
+cudaError_t launch_variant(const TransArgs &a, int sm_count, cudaStream_t st) {
   using L = SmemLayout<RT, NT>;
   static int occ = 0;
   if (occ == 0) {
     int o = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, transition_kernel<RT, NT, WARPS>, WARPS * 32, L::bytes);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, transition_kernel<RT, NT, WARPS, EXACT, TAIL1>, WARPS * 32, L::bytes);
     if (e != cudaSuccess) return e;
     occ = o > 0 ? o : 1;
   }
@@ -312,14 +337,25 @@ cudaError_t launch_one(const TransArgs &a, int sm_count, cudaStream_t st) {
   int64_t grid = (int64_t)sm_count * occ;
   if (grid > max_tiles) grid = max_tiles;
   if (grid < 1) grid = 1;
-  transition_kernel<RT, NT, WARPS><<<(unsigned)grid, WARPS * 32, L::bytes, st>>>(a);
+  transition_kernel<RT, NT, WARPS, EXACT, TAIL1><<<(unsigned)grid, WARPS * 32, L::bytes, st>>>(a);
   return cudaGetLastError();
+}
+
+template <int RT, int NT, int WARPS>
+cudaError_t launch_one(const TransArgs &a, int sm_count, cudaStream_t st) {
+  const bool exact = a.r0 == 8 * RT && a.r1 == 8 * RT && (a.n1 + 7) / 8 == NT;
+  if (exact && a.n1 == 8 * (NT - 1) + 1) return launch_variant<RT, NT, WARPS, true, true>(a, sm_count, st);
+  if (exact) return launch_variant<RT, NT, WARPS, true, false>(a, sm_count, st);
+  return launch_variant<RT, NT, WARPS, false, false>(a, sm_count, st);
 }
 
 template <int RT, int NT, int WARPS>
 cudaError_t init_one() {
   using L = SmemLayout<RT, NT>;
-  return cudaFuncSetAttribute(transition_kernel<RT, NT, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes);
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(transition_kernel<RT, NT, WARPS, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(transition_kernel<RT, NT, WARPS, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(transition_kernel<RT, NT, WARPS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes);
 }
 
 constexpr int kWarps = 8;
