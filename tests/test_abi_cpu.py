@@ -1,0 +1,117 @@
+"""CPU tests of the C-ABI boundary: both libraries load without a GPU, export every symbol that
+include/tt_irt1.h declares, fail loudly (no CPU fallback) when no device is present, and the host-side
+mirror of the reference wrapper keeps the reference's argument handling."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB32 = os.path.join(ROOT, "tt-irt_b200", "tt_irt_py", "tt_irt1_int32.so")
+LIB64 = os.path.join(ROOT, "tt-irt_b200", "lib", "libtt_irt1_int64.so")
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "tt_irt1.h")).read()
+    return sorted(set(re.findall(r"^TTIRT_API\s+[\w\s\*]+?\b(\w+)\s*\(", src, flags=re.M)))
+
+
+@pytest.fixture(scope="module")
+def libs():
+    if not (os.path.exists(LIB32) and os.path.exists(LIB64)):
+        import __graft_entry__
+        __graft_entry__.build()
+    return ctypes.CDLL(LIB32), ctypes.CDLL(LIB64)
+
+
+def test_header_declares_the_reference_entry_point():
+    syms = _declared_symbols()
+    assert "tt_irt1" in syms and len(syms) >= 12
+
+
+def test_both_libraries_export_every_declared_symbol(libs):
+    for lib in libs:
+        for s in _declared_symbols():
+            assert hasattr(lib, s), s
+
+
+def test_libraries_are_self_contained():
+    """No BLAS / cudart / torch dependency: the reference .so relied on preloaded BLAS symbols (setup.py:3),
+    the drop-in must resolve everything itself (static cudart)."""
+    import subprocess
+    for so in (LIB32, LIB64):
+        out = subprocess.run(["ldd", so], capture_output=True, text=True).stdout
+        assert "blas" not in out.lower() and "cudart" not in out.lower() and "torch" not in out.lower(), out
+        undefined = subprocess.run(["nm", "-D", "--undefined-only", so], capture_output=True, text=True).stdout
+        assert "dgemm_" not in undefined and "daxpy_" not in undefined
+
+
+def test_only_the_abi_is_exported():
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", LIB32], capture_output=True, text=True).stdout
+    names = [l.split()[-1] for l in out.splitlines() if " T " in l]
+    assert sorted(names) == _declared_symbols()
+
+
+def _gpu_count(lib):
+    lib.ttirt_device_count.restype = ctypes.c_int
+    return lib.ttirt_device_count()
+
+
+def test_no_cpu_fallback_without_device(libs):
+    """Without a CUDA device the drop-in symbol must not compute anything: outputs are NaN-filled."""
+    lib32, lib64 = libs
+    if _gpu_count(lib32) > 0:
+        pytest.skip("a GPU is present")
+    from tt_irt_py import synth
+    ns, xs, rk, c = synth.make_tt(3, 5, 2, seed=1)
+    q = synth.make_q(16, 3, seed=2)
+    for lib, it, ct in ((lib32, np.int32, ctypes.c_int), (lib64, np.int64, ctypes.c_longlong)):
+        Z = np.zeros((16, 3), order="F"); l = np.zeros(16)
+        n_ = ns.astype(it); r_ = rk.astype(it)
+        dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ct)
+        lib.tt_irt1.restype = None
+        lib.tt_irt1.argtypes = [ct, ip, dp, ip, dp, ct, dp, dp, dp]
+        lib.tt_irt1(3, n_.ctypes.data_as(ip), xs.ctypes.data_as(dp), r_.ctypes.data_as(ip), c.ctypes.data_as(dp), 16,
+                    q.ctypes.data_as(dp), Z.ctypes.data_as(dp), l.ctypes.data_as(dp))
+        assert np.isnan(Z).all() and np.isnan(l).all()
+    lib32.ttirt_last_error.restype = ctypes.c_char_p
+    assert b"no CUDA device" in lib32.ttirt_last_error() or b"CPU fallback" in lib32.ttirt_last_error()
+
+
+def test_python_mirror_raises_without_device(libs):
+    from tt_irt_py import synth, tt_irt
+    if tt_irt.device_count() > 0:
+        pytest.skip("a GPU is present")
+    ns, xs, rk, c = synth.make_tt(3, 5, 2, seed=1)
+    with pytest.raises(RuntimeError):
+        tt_irt.Model(ns, xs, rk, c)
+    with pytest.raises(RuntimeError):
+        tt_irt.run_host(ns, xs, rk, c, synth.make_q(8, 3))
+
+
+def test_wrapper_repacks_discontiguous_cores():
+    """Reference tt_irt.py:27-34 copies each core by its position vector ps (ttpy may leave gaps)."""
+    from tt_irt_py import tt_irt
+
+    class F(object):
+        pass
+    f = F()
+    f.d = 2; f.n = np.array([2, 3], dtype=np.int32); f.r = np.array([1, 2, 1], dtype=np.int32)
+    a, b = np.arange(4.0), 10 + np.arange(6.0)
+    f.core = np.concatenate([a, [99.0, 98.0], b])   # a gap between the cores
+    f.ps = np.array([1, 7, 13])                      # 1-based starts
+    np.testing.assert_array_equal(tt_irt._packed_cores(f), np.concatenate([a, b]))
+    t = tt_irt.TTTensor([2, 3], [1, 2, 1], np.concatenate([a, b]))
+    assert t.ps.tolist() == [1, 5, 11] and t.d == 2
+    with pytest.raises(ValueError):
+        tt_irt.TTTensor([2, 3], [1, 2, 1], np.arange(5.0))
+
+
+def test_flop_model_matches_survey():
+    from tt_irt_py import synth
+    for (d, n, r, w) in [(32, 65, 64, 749826), (40, 33, 32, 238210), (8, 17, 8, 3506), (8, 17, 16, 10050), (11, 17, 16, 14754)]:
+        ns, xs, rk, c = synth.make_tt(d, n, r, seed=0) if d * n * r * r < 2e6 else (np.full(d, n), None, np.array([1] + [r] * (d - 1) + [1]), None)
+        assert synth.flops_per_sample(ns, rk) == w
