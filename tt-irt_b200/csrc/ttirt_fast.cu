@@ -30,15 +30,34 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
       : "d"(a), "d"(b));
 }
 
-// Shared-memory image of a B operand (K x NC, column-major in global memory with column stride cs).
-// Column c lives at c*KP.  Within a column the contraction index a is permuted so that the four
-// values a thread quad needs for one k-step are adjacent: chunk ch = 2*(a/8) + (a&1), lane (a&7)/2;
-// chunks are XOR-swizzled with the column's low bits, which makes the quad-strided 8-byte loads of a
-// half-warp hit 16 distinct bank pairs (no padding needed).  Entries outside K x NC are zero.
-__device__ __forceinline__ int b_phys(int c, int a, int KP) {
-  const int ch = ((a >> 3) << 1) | (a & 1);
-  return c * KP + (((ch ^ (c & 3)) << 2) | ((a & 7) >> 1));
+// ---- TMA bulk copy + mbarrier (sm_90+/sm_100a): global rows -> shared memory, completion by transaction bytes ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+
+// Shared-memory image of a B operand (K x NC, column-major in global memory with column stride cs).
+// Column c lives at c*KP.  Rows keep their natural order inside groups of 8 and the groups are XOR-swizzled
+// with the column's parity: a thread quad reads, per pair of k-steps, 16 bytes per lane (LDS.128: rows
+// 8j+2t, 8j+2t+1 of column 8jj+g) and the two columns served by one quarter-warp wavefront fall into
+// different 64-byte halves of the bank window, so the loads are conflict-free without padding.
+// The contraction index is consumed in the permuted order (8j+2t+e for k-step 2j+e, lane t) on BOTH MMA
+// operands, which is what lets phase (2) use phase (1)'s accumulators as its A fragments in place.
+// Entries outside K x NC are zero.
+__device__ __forceinline__ int b_phys(int c, int a, int KP) { return c * KP + ((((a >> 3) ^ (c & 1)) << 3) | (a & 7)); }
 
 __device__ void stage_b(double *dst, const double *__restrict__ src, int K, int NC, int64_t cs, int KP, int NCP,
                         int tid, int nthr) {
@@ -50,41 +69,55 @@ __device__ void stage_b(double *dst, const double *__restrict__ src, int K, int 
   }
 }
 
-template <int RT, int NT>
+template <int RT, int NT, int WARPS>
 struct SmemLayout {
   static constexpr int KPMAX = (8 * RT + 15) & ~15;
   static constexpr int SLAB = 8 * RT * KPMAX;      // doubles per slab buffer
   static constexpr int PN = 8 * NT * KPMAX;        // doubles for P_{k+1}
   static constexpr int NBMAX = 8 * NT;             // >= n - 1 intervals
-  static constexpr size_t bytes = sizeof(double) * (2 * SLAB + PN + 2 * 8 * NT) + sizeof(int) * (2 * (NBMAX + 1) + NBMAX);
+  static constexpr int FPITCH = 8 * RT + 8;        // doubles per staged left-interface row (+64 B: rows g, g+1 hit different bank halves)
+  static constexpr int FTILE = 16 * FPITCH;        // doubles per warp
+  static constexpr size_t bytes = sizeof(double) * (2 * SLAB + PN + 2 * 8 * NT + WARPS * FTILE) + sizeof(uint64_t) * WARPS +
+                                  sizeof(int) * (2 * (NBMAX + 1) + NBMAX);
 };
 
 // EXACT: r0 == r1 == 8*RT and ceil(n1/8) == NT, so every tile loop runs its full static trip count and no
 // guard branches are compiled in (the steady state of a uniform-rank TT).  TAIL1 (EXACT only): n1 == 8*(NT-1)+1,
 // the usual 2^p+1 grid; the lone last grid column is then a 4-lane DFMA dot product instead of a whole DMMA
 // column tile that would be 7/8 padding.
+//
+// Row gather: the 16 left-interface rows of a warp's NEXT tile are fetched by TMA bulk copies (cp.async.bulk,
+// one 8*r0-byte row per lane, completion counted on a per-warp mbarrier) into a per-warp shared tile as soon
+// as the current tile's update phase has consumed that tile, i.e. a whole pdf + inversion phase ahead of use.
+// The dependent perm -> row latency (two DRAM round trips) therefore never sits in front of the DMMA stream.
 template <int RT, int NT, int WARPS, bool EXACT, bool TAIL1>
 __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransArgs a) {
   static_assert(EXACT || !TAIL1, "TAIL1 needs EXACT");
-  using L = SmemLayout<RT, NT>;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using L = SmemLayout<RT, NT, WARPS>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   double *slab0 = reinterpret_cast<double *>(smem_raw);
   double *slab1 = slab0 + L::SLAB;
   double *Ps = slab1 + L::SLAB;
-  double *hh = Ps + L::PN;           // half grid steps of dimension k+1, zero beyond n1-2
+  double *ft_all = Ps + L::PN;       // per-warp staged left-interface rows
+  double *hh = ft_all + WARPS * L::FTILE;  // half grid steps of dimension k+1, zero beyond n1-2
   double *xg = hh + 8 * NT;          // grid of dimension k+1
-  int *bts = reinterpret_cast<int *>(xg + 8 * NT);  // bin -> first CTA tile
-  int *bst = bts + (L::NBMAX + 1);                   // bin -> first sorted row
-  int *hist = bst + (L::NBMAX + 1);                  // histogram of the intervals chosen in dimension k+1
+  uint64_t *bars = reinterpret_cast<uint64_t *>(xg + 8 * NT);
+  int *bts = reinterpret_cast<int *>(bars + WARPS);  // bin -> first CTA tile
+  int *bst = bts + (L::NBMAX + 1);                    // bin -> first sorted row
+  int *hist = bst + (L::NBMAX + 1);                   // histogram of the intervals chosen in dimension k+1
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   constexpr int NTHR = WARPS * 32, ROWS_CTA = WARPS * 16;
+  constexpr int FP = L::FPITCH;
+  double *ft = ft_all + warp * L::FTILE;
+  uint64_t *bar = bars + warp;
 
   const int r0 = a.r0, r1 = a.r1, n1 = a.n1, nb0 = a.n0 - 1;
-  constexpr int KP0 = L::KPMAX, KP1 = L::KPMAX;  // compile-time column pitch: B-fragment offsets fold into immediates
+  constexpr int KP = L::KPMAX;                   // compile-time column pitch: B-fragment offsets fold into immediates
   constexpr int NTD = TAIL1 ? NT - 1 : NT;       // grid column tiles computed by DMMA
   const int ks0 = EXACT ? RT : (r0 + 7) >> 3, rt_act = EXACT ? RT : (r1 + 7) >> 3, nt_act = EXACT ? NT : (n1 + 7) >> 3;
+  const uint32_t row_bytes = (uint32_t)(8 * ks0) * 8u;   // bytes of a left-interface row that the update reads
 
   for (int i = tid; i <= nb0; i += NTHR) {
     bts[i] = a.bin_tile_start[i];
@@ -95,7 +128,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
     xg[i] = (i < n1) ? a.xnext[i] : 0.0;
     if (i < L::NBMAX) hist[i] = 0;
   }
-  stage_b(Ps, a.pnext, r1, n1, r1, KP1, 8 * NT, tid, NTHR);
+  if (lane == 0) mbar_init(bar, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  stage_b(Ps, a.pnext, r1, n1, r1, KP, 8 * NT, tid, NTHR);
   __syncthreads();
 
   const int total_tiles = bts[nb0];
@@ -104,10 +139,50 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
   const int64_t slab_cs = (int64_t)r0 * a.n0;
 
   int cur0 = -1, cur1 = -1;  // interval slab held by slab0 / slab1
-  int b = 0;
+  int b = 0;                 // bin of the current tile
+  int bh = 0;                // bin hint of the row look-ahead (monotone)
+  const double *sl_lo = slab0, *sl_hi = slab1;
+
+  // rows of this warp in CTA tile `tile`: first sorted row and number of valid rows (0 past the end)
+  auto rows_of = [&](int tile, int &nv) -> int {
+    if (tile >= t_end) { nv = 0; return 0; }
+    while (tile >= bts[bh + 1]) ++bh;
+    const int row0 = bst[bh] + (tile - bts[bh]) * ROWS_CTA + warp * 16;
+    nv = max(0, min(16, bst[bh + 1] - row0));
+    return row0;
+  };
+  // sample ids of a tile: lane l (and l+16) holds the id of row l & 15; rows past nv repeat row 0
+  auto load_ids = [&](int row0, int nv) -> int { return nv > 0 ? a.perm[row0 + ((lane & 15) < nv ? (lane & 15) : 0)] : 0; };
+
+  uint32_t phase = 0;
+  int nvC = 0, nvN = 0;      // valid rows: current tile / next tile
+  int idC = 0, idN = 0;      // row ids (lane-distributed) of the current / next tile
+  // TMA gather of the rows whose ids are idN into this warp's shared tile
+  auto issue_gather = [&](int ids, int nv) {
+    if (nv > 0) {
+      if (lane == 0) mbar_arrive_expect_tx(bar, 16u * row_bytes);
+      __syncwarp();
+      if (lane < 16) bulk_g2s(ft + lane * FP, a.F + (size_t)ids * a.ldf, row_bytes, bar);
+    }
+  };
+  double w1A = 0, w2A = 0, w1B = 0, w2B = 0, qA = 0, qB = 0, lpA = 0, lpB = 0;       // current tile
+  double w1An = 0, w2An = 0, w1Bn = 0, w2Bn = 0, qAn = 0, qBn = 0, lpAn = 0, lpBn = 0;  // next tile (in flight)
+  int mA = 0, mB = 0, mAn = 0, mBn = 0;
+  {
+    const int rowC = rows_of(t_begin, nvC);
+    idC = load_ids(rowC, nvC);
+    const int rowN = rows_of(t_begin + 1, nvN);
+    idN = load_ids(rowN, nvN);
+    issue_gather(idC, nvC);
+    mA = __shfl_sync(FULL, idC, g); mB = __shfl_sync(FULL, idC, g + 8);
+    if (nvC > 0) {
+      w1A = a.w1[mA]; w2A = a.w2[mA]; w1B = a.w1[mB]; w2B = a.w2[mB];
+      qA = a.q[mA]; qB = a.q[mB]; lpA = a.lp[mA]; lpB = a.lp[mB];
+    }
+  }
+
   for (int tile = t_begin; tile < t_end; ++tile) {
     while (tile >= bts[b + 1]) ++b;
-    const double *sl_lo, *sl_hi;
     if (cur0 == b && cur1 == b + 1) {
       sl_lo = slab0; sl_hi = slab1;
     } else if (cur1 == b && cur0 == b + 1) {
@@ -115,115 +190,124 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
     } else {
       __syncthreads();  // every warp is done with the previous bin's slabs
       if (cur0 == b) {
-        stage_b(slab1, a.core + (int64_t)(b + 1) * r0, r0, r1, slab_cs, KP0, 8 * RT, tid, NTHR); cur1 = b + 1;
+        stage_b(slab1, a.core + (int64_t)(b + 1) * r0, r0, r1, slab_cs, KP, 8 * RT, tid, NTHR); cur1 = b + 1;
       } else if (cur1 == b) {
-        stage_b(slab0, a.core + (int64_t)(b + 1) * r0, r0, r1, slab_cs, KP0, 8 * RT, tid, NTHR); cur0 = b + 1;
+        stage_b(slab0, a.core + (int64_t)(b + 1) * r0, r0, r1, slab_cs, KP, 8 * RT, tid, NTHR); cur0 = b + 1;
       } else if (cur0 == b + 1) {
-        stage_b(slab1, a.core + (int64_t)b * r0, r0, r1, slab_cs, KP0, 8 * RT, tid, NTHR); cur1 = b;
+        stage_b(slab1, a.core + (int64_t)b * r0, r0, r1, slab_cs, KP, 8 * RT, tid, NTHR); cur1 = b;
       } else if (cur1 == b + 1) {
-        stage_b(slab0, a.core + (int64_t)b * r0, r0, r1, slab_cs, KP0, 8 * RT, tid, NTHR); cur0 = b;
+        stage_b(slab0, a.core + (int64_t)b * r0, r0, r1, slab_cs, KP, 8 * RT, tid, NTHR); cur0 = b;
       } else {
-        stage_b(slab0, a.core + (int64_t)b * r0, r0, r1, slab_cs, KP0, 8 * RT, tid, NTHR); cur0 = b;
-        stage_b(slab1, a.core + (int64_t)(b + 1) * r0, r0, r1, slab_cs, KP0, 8 * RT, tid, NTHR); cur1 = b + 1;
+        stage_b(slab0, a.core + (int64_t)b * r0, r0, r1, slab_cs, KP, 8 * RT, tid, NTHR); cur0 = b;
+        stage_b(slab1, a.core + (int64_t)(b + 1) * r0, r0, r1, slab_cs, KP, 8 * RT, tid, NTHR); cur1 = b + 1;
       }
       __syncthreads();
       if (cur0 == b) { sl_lo = slab0; sl_hi = slab1; } else { sl_lo = slab1; sl_hi = slab0; }
     }
 
-    const int row0 = bst[b] + (tile - bts[b]) * ROWS_CTA + warp * 16;
-    const int nvalid = min(16, bst[b + 1] - row0);
-    if (nvalid <= 0) continue;  // warp-uniform; no barrier below
-
-    // ---- rows of this warp: g and g+8 of its 16-sample tile --------------------------------------
+    const int nvalid = nvC;
     const bool vA = g < nvalid, vB = (g + 8) < nvalid;
-    const int mA = a.perm[row0 + (vA ? g : 0)], mB = a.perm[row0 + (vB ? g + 8 : 0)];
-    const double w1A = a.w1[mA], w2A = a.w2[mA], w1B = a.w1[mB], w2B = a.w2[mB];
-    const double qA = a.q[mA], qB = a.q[mB];
-    double *FA = a.F + (size_t)mA * a.ldf + 2 * t, *FB = a.F + (size_t)mB * a.ldf + 2 * t;
-    double2 fa[RT], fb[RT];
-#pragma unroll
-    for (int j = 0; j < RT; j++)
-      if (EXACT || j < ks0) {
-        fa[j] = *reinterpret_cast<const double2 *>(FA + 8 * j);
-        fb[j] = *reinterpret_cast<const double2 *>(FB + 8 * j);
-      }
-
-    // ---- (1) interface update ---------------------------------------------------------------------
-    double acc[2][RT][2];
-#pragma unroll
-    for (int j = 0; j < RT; j++) { acc[0][j][0] = acc[0][j][1] = acc[1][j][0] = acc[1][j][1] = 0.0; }
-#pragma unroll
-    for (int j = 0; j < RT; j++) {
-      if (EXACT || j < ks0) {
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-          const double xa = e ? fa[j].y : fa[j].x, xb = e ? fb[j].y : fb[j].x;
-          const double a1A = w1A * xa, a2A = w2A * xa, a1B = w1B * xb, a2B = w2B * xb;
-          const int sw = (((2 * j + e) ^ (g & 3)) << 2) | t;
-#pragma unroll
-          for (int jj = 0; jj < RT; jj++) {
-            if (EXACT || jj < rt_act) {
-              const int off = (8 * jj + g) * KP0 + sw;
-              const double b1 = sl_lo[off], b2 = sl_hi[off];
-              dmma884(acc[0][jj][0], acc[0][jj][1], a1A, b1);
-              dmma884(acc[1][jj][0], acc[1][jj][1], a1B, b1);
-              dmma884(acc[0][jj][0], acc[0][jj][1], a2A, b2);
-              dmma884(acc[1][jj][0], acc[1][jj][1], a2B, b2);
-            }
-          }
-        }
-      }
-    }
-    if (!a.last) {
-#pragma unroll
-      for (int jj = 0; jj < RT; jj++)
-        if (EXACT || jj < rt_act) {
-          if (vA) *reinterpret_cast<double2 *>(FA + 8 * jj) = make_double2(acc[0][jj][0], acc[0][jj][1]);
-          if (vB) *reinterpret_cast<double2 *>(FB + 8 * jj) = make_double2(acc[1][jj][0], acc[1][jj][1]);
-        }
-    }
-
-    // ---- (2) conditional pdf on the grid of dimension k+1 ----------------------------------------
     double c[2][NT + 1][2];
 #pragma unroll
     for (int j = 0; j <= NT; j++) { c[0][j][0] = c[0][j][1] = c[1][j][0] = c[1][j][1] = 0.0; }
+
+    if (nvalid > 0) {
+      // ---- (1) interface update: A fragments from the TMA-staged rows ------------------------------
+      while (!mbar_try_wait(bar, phase)) {}
+      phase ^= 1;
+      double acc[2][RT][2];
 #pragma unroll
-    for (int jj = 0; jj < RT; jj++) {
-      if (EXACT || jj < rt_act) {
+      for (int j = 0; j < RT; j++) { acc[0][j][0] = acc[0][j][1] = acc[1][j][0] = acc[1][j][1] = 0.0; }
+      const double *fra = ft + g * FP + 2 * t, *frb = ft + (g + 8) * FP + 2 * t;
 #pragma unroll
-        for (int e = 0; e < 2; e++) {
-          const double a0 = acc[0][jj][e], a1 = acc[1][jj][e];
-          const int sw = (((2 * jj + e) ^ (g & 3)) << 2) | t;
+      for (int j = 0; j < RT; j++) {
+        if (EXACT || j < ks0) {
+          const double2 fa = *reinterpret_cast<const double2 *>(fra + 8 * j);
+          const double2 fb = *reinterpret_cast<const double2 *>(frb + 8 * j);
+          const double a1A0 = w1A * fa.x, a2A0 = w2A * fa.x, a1B0 = w1B * fb.x, a2B0 = w2B * fb.x;
+          const double a1A1 = w1A * fa.y, a2A1 = w2A * fa.y, a1B1 = w1B * fb.y, a2B1 = w2B * fb.y;
+          const int sw = ((j ^ (g & 1)) << 3) | (t << 1);
 #pragma unroll
-          for (int jn = 0; jn < NTD; jn++) {
-            if (EXACT || jn < nt_act) {
-              const double bv = Ps[(8 * jn + g) * KP1 + sw];
-              dmma884(c[0][jn][0], c[0][jn][1], a0, bv);
-              dmma884(c[1][jn][0], c[1][jn][1], a1, bv);
+          for (int jj = 0; jj < RT; jj++) {
+            if (EXACT || jj < rt_act) {
+              const int off = (8 * jj + g) * KP + sw;
+              const double2 b1 = *reinterpret_cast<const double2 *>(sl_lo + off);
+              const double2 b2 = *reinterpret_cast<const double2 *>(sl_hi + off);
+              dmma884(acc[0][jj][0], acc[0][jj][1], a1A0, b1.x);
+              dmma884(acc[1][jj][0], acc[1][jj][1], a1B0, b1.x);
+              dmma884(acc[0][jj][0], acc[0][jj][1], a2A0, b2.x);
+              dmma884(acc[1][jj][0], acc[1][jj][1], a2B0, b2.x);
+              dmma884(acc[0][jj][0], acc[0][jj][1], a1A1, b1.y);
+              dmma884(acc[1][jj][0], acc[1][jj][1], a1B1, b1.y);
+              dmma884(acc[0][jj][0], acc[0][jj][1], a2A1, b2.y);
+              dmma884(acc[1][jj][0], acc[1][jj][1], a2B1, b2.y);
             }
           }
         }
       }
-    }
-
-    if (TAIL1) {
-      // last grid column (node 8*(NT-1)): quad-distributed dot product, result kept on lane t == 0
-      double tA = 0.0, tB = 0.0;
+      // ---- the staged tile is consumed: launch the next tile's gather and scalar loads now ---------
+      __syncwarp();
+      issue_gather(idN, nvN);
+      mAn = __shfl_sync(FULL, idN, g); mBn = __shfl_sync(FULL, idN, g + 8);
+      if (nvN > 0) {
+        w1An = a.w1[mAn]; w2An = a.w2[mAn]; w1Bn = a.w1[mBn]; w2Bn = a.w2[mBn];
+        qAn = a.q[mAn]; qBn = a.q[mBn]; lpAn = a.lp[mAn]; lpBn = a.lp[mBn];
+      }
+      if (!a.last) {
+        double *FA = a.F + (size_t)mA * a.ldf + 2 * t, *FB = a.F + (size_t)mB * a.ldf + 2 * t;
+#pragma unroll
+        for (int jj = 0; jj < RT; jj++)
+          if (EXACT || jj < rt_act) {
+            if (vA) *reinterpret_cast<double2 *>(FA + 8 * jj) = make_double2(acc[0][jj][0], acc[0][jj][1]);
+            if (vB) *reinterpret_cast<double2 *>(FB + 8 * jj) = make_double2(acc[1][jj][0], acc[1][jj][1]);
+          }
+      }
+      // ---- (2) conditional pdf on the grid of dimension k+1 ----------------------------------------
 #pragma unroll
       for (int jj = 0; jj < RT; jj++) {
+        if (EXACT || jj < rt_act) {
+          const int sw = ((jj ^ (g & 1)) << 3) | (t << 1);
 #pragma unroll
-        for (int e = 0; e < 2; e++) {
-          const double pv = Ps[(8 * (NT - 1)) * KP1 + ((2 * jj + e) << 2) + t];
-          tA = fma(acc[0][jj][e], pv, tA);
-          tB = fma(acc[1][jj][e], pv, tB);
+          for (int jn = 0; jn < NTD; jn++) {
+            if (EXACT || jn < nt_act) {
+              const double2 bv = *reinterpret_cast<const double2 *>(Ps + (8 * jn + g) * KP + sw);
+              dmma884(c[0][jn][0], c[0][jn][1], acc[0][jj][0], bv.x);
+              dmma884(c[1][jn][0], c[1][jn][1], acc[1][jj][0], bv.x);
+              dmma884(c[0][jn][0], c[0][jn][1], acc[0][jj][1], bv.y);
+              dmma884(c[1][jn][0], c[1][jn][1], acc[1][jj][1], bv.y);
+            }
+          }
         }
       }
-      tA += __shfl_xor_sync(FULL, tA, 1); tA += __shfl_xor_sync(FULL, tA, 2);
-      tB += __shfl_xor_sync(FULL, tB, 1); tB += __shfl_xor_sync(FULL, tB, 2);
-      c[0][NT - 1][0] = (t == 0) ? tA : 0.0;
-      c[1][NT - 1][0] = (t == 0) ? tB : 0.0;
+      if (TAIL1) {
+        // last grid column (node 8*(NT-1), even column: no swizzle): quad-distributed dot product
+        double tA = 0.0, tB = 0.0;
+#pragma unroll
+        for (int jj = 0; jj < RT; jj++) {
+          const double2 pv = *reinterpret_cast<const double2 *>(Ps + (8 * (NT - 1)) * KP + (jj << 3) + (t << 1));
+          tA = fma(acc[0][jj][0], pv.x, tA); tB = fma(acc[1][jj][0], pv.x, tB);
+          tA = fma(acc[0][jj][1], pv.y, tA); tB = fma(acc[1][jj][1], pv.y, tB);
+        }
+        tA += __shfl_xor_sync(FULL, tA, 1); tA += __shfl_xor_sync(FULL, tA, 2);
+        tB += __shfl_xor_sync(FULL, tB, 1); tB += __shfl_xor_sync(FULL, tB, 2);
+        c[0][NT - 1][0] = (t == 0) ? tA : 0.0;
+        c[1][NT - 1][0] = (t == 0) ? tB : 0.0;
+      }
+    } else {
+      // this warp has no rows in this tile: keep the pipeline moving
+      issue_gather(idN, nvN);
+      mAn = __shfl_sync(FULL, idN, g); mBn = __shfl_sync(FULL, idN, g + 8);
+      if (nvN > 0) {
+        w1An = a.w1[mAn]; w2An = a.w2[mAn]; w1Bn = a.w1[mBn]; w2Bn = a.w2[mBn];
+        qAn = a.q[mAn]; qBn = a.q[mBn]; lpAn = a.lp[mAn]; lpBn = a.lp[mBn];
+      }
     }
+    // ids of the tile after next
+    int nvNN = 0;
+    const int rowNN = rows_of(tile + 2, nvNN);
+    const int idNN = load_ids(rowNN, nvNN);
 
+    if (nvalid > 0) {
     // ---- (3) CDF, search: both 8-row tiles, all lanes ----------------------------------------------
     double cdf_lo[2], c1v[2], c2v[2];
     int i0v[2];
@@ -306,13 +390,19 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
         if (a.idx_out) a.idx_out[m] = i0;
         if (!a.last) {
           a.idx[m] = i0; a.w1[m] = o.w1; a.w2[m] = o.w2;
-          a.lp[m] = a.lp[m] + o.logp;
+          a.lp[m] = (sel ? lpB : lpA) + o.logp;
           atomicAdd(&hist[i0], 1);
         } else {
-          a.lpz[m] = a.lp[m] + o.logp;
+          a.lpz[m] = (sel ? lpB : lpA) + o.logp;
         }
       }
     }
+    }  // nvalid > 0
+
+    // ---- rotate the row pipeline --------------------------------------------------------------------
+    nvC = nvN; idC = idN; mA = mAn; mB = mBn;
+    w1A = w1An; w2A = w2An; w1B = w1Bn; w2B = w2Bn; qA = qAn; qB = qBn; lpA = lpAn; lpB = lpBn;
+    nvN = nvNN; idN = idNN;
   }
 
   if (!a.last) {
@@ -324,7 +414,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
 
 template <int RT, int NT, int WARPS, bool EXACT, bool TAIL1>
 cudaError_t launch_variant(const TransArgs &a, int sm_count, cudaStream_t st) {
-  using L = SmemLayout<RT, NT>;
+  using L = SmemLayout<RT, NT, WARPS>;
   static int occ = 0;
   if (occ == 0) {
     int o = 0;
@@ -351,7 +441,7 @@ cudaError_t launch_one(const TransArgs &a, int sm_count, cudaStream_t st) {
 
 template <int RT, int NT, int WARPS>
 cudaError_t init_one() {
-  using L = SmemLayout<RT, NT>;
+  using L = SmemLayout<RT, NT, WARPS>;
   cudaError_t e;
   if ((e = cudaFuncSetAttribute(transition_kernel<RT, NT, WARPS, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(transition_kernel<RT, NT, WARPS, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes)) != cudaSuccess) return e;
