@@ -77,7 +77,7 @@ struct SmemLayout {
   static constexpr int NBMAX = 8 * NT;             // >= n - 1 intervals
   static constexpr int FPITCH = 8 * RT + 8;        // doubles per staged left-interface row (+64 B: rows g, g+1 hit different bank halves)
   static constexpr int FTILE = 16 * FPITCH;        // doubles per warp
-  static constexpr size_t bytes = sizeof(double) * (2 * SLAB + PN + 2 * 8 * NT + WARPS * FTILE) + sizeof(uint64_t) * WARPS +
+  static constexpr size_t bytes = sizeof(double) * (2 * SLAB + PN + 3 * 8 * NT + WARPS * FTILE) + sizeof(uint64_t) * WARPS +
                                   sizeof(int) * (2 * (NBMAX + 1) + NBMAX);
 };
 
@@ -101,7 +101,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
   double *ft_all = Ps + L::PN;       // per-warp staged left-interface rows
   double *hh = ft_all + WARPS * L::FTILE;  // half grid steps of dimension k+1, zero beyond n1-2
   double *xg = hh + 8 * NT;          // grid of dimension k+1
-  uint64_t *bars = reinterpret_cast<uint64_t *>(xg + 8 * NT);
+  double *ihs = xg + 8 * NT;         // reciprocal cell widths of dimension k+1
+  uint64_t *bars = reinterpret_cast<uint64_t *>(ihs + 8 * NT);
   int *bts = reinterpret_cast<int *>(bars + WARPS);  // bin -> first CTA tile
   int *bst = bts + (L::NBMAX + 1);                    // bin -> first sorted row
   int *hist = bst + (L::NBMAX + 1);                   // histogram of the intervals chosen in dimension k+1
@@ -126,6 +127,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
   for (int i = tid; i < 8 * NT; i += NTHR) {
     hh[i] = (i + 1 < n1) ? 0.5 * (a.xnext[i + 1] - a.xnext[i]) : 0.0;
     xg[i] = (i < n1) ? a.xnext[i] : 0.0;
+    ihs[i] = (i + 1 < n1) ? 1.0 / (a.xnext[i + 1] - a.xnext[i]) : 0.0;
     if (i < L::NBMAX) hist[i] = 0;
   }
   if (lane == 0) mbar_init(bar, 1);
@@ -181,6 +183,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
     }
   }
 
+  // Warps w and w+4 share an SM sub-partition (one FP64/DMMA pipe).  Started together and sharing the pipe
+  // fairly they stay in lock-step, so both sit in the latency-bound inversion phase at the same time with the
+  // pipe idle; a start offset of about half a tile (preserved by the same fairness) interleaves their phases.
+  if (warp >= WARPS / 2 && a.stagger_ns) __nanosleep(a.stagger_ns);
+
   for (int tile = t_begin; tile < t_end; ++tile) {
     while (tile >= bts[b + 1]) ++b;
     if (cur0 == b && cur1 == b + 1) {
@@ -203,6 +210,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
       }
       __syncthreads();
       if (cur0 == b) { sl_lo = slab0; sl_hi = slab1; } else { sl_lo = slab1; sl_hi = slab0; }
+      if (warp >= WARPS / 2 && a.stagger_ns) __nanosleep(a.stagger_ns);
     }
 
     const int nvalid = nvC;
@@ -342,13 +350,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
       }
       const double total = carry;
       const double sc = 1.0 / total;
+      const double qt = qv * total;   // q > S/total  <=>  q*total > S up to one rounding: decided on the unnormalised CDF
       int cnt = 0;
 #pragma unroll
       for (int jn = 0; jn < NTD; jn++) {
         if (EXACT || jn < nt_act) {
           const int node0 = 8 * jn + 2 * t;
-          cnt += (node0 >= 1 && node0 <= n1 - 2 && qv > S0[jn] * sc) ? 1 : 0;
-          cnt += (node0 + 1 <= n1 - 2 && qv > S1[jn] * sc) ? 1 : 0;
+          cnt += (node0 >= 1 && node0 <= n1 - 2 && qt > S0[jn]) ? 1 : 0;
+          cnt += (node0 + 1 <= n1 - 2 && qt > S1[jn]) ? 1 : 0;
         }
       }
       cnt += __shfl_xor_sync(FULL, cnt, 1);
@@ -383,8 +392,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
       const bool valid = (t < 2) && (sel ? vB : vA);
       const int m = sel ? mB : mA;
       const int i0 = sel ? i0v[1] : i0v[0];
-      const CellOut o = invert_cell(sel ? qB : qA, sel ? cdf_lo[1] : cdf_lo[0], sel ? c1v[1] : c1v[0],
-                                    sel ? c2v[1] : c2v[0], xg[i0], xg[i0 + 1]);
+      const CellOut o = invert_cell_fast(sel ? qB : qA, sel ? cdf_lo[1] : cdf_lo[0], sel ? c1v[1] : c1v[0],
+                                         sel ? c2v[1] : c2v[0], xg[i0], xg[i0 + 1], ihs[i0]);
       if (valid) {
         a.z[m] = o.xk;
         if (a.idx_out) a.idx_out[m] = i0;
