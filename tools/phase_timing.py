@@ -1,0 +1,34 @@
+"""Per-phase cycle breakdown of the transition kernel (debug build with -DTTIRT_PHASE_TIMING).
+usage: python tools/phase_timing.py tools/pt_w8.so [log2m]"""
+import ctypes, os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tt-irt_b200"))
+from tt_irt_py import synth
+import torch
+lib = ctypes.CDLL(os.path.abspath(sys.argv[1]))
+log2m = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+d, n, r, M = 32, 65, 64, 1 << log2m
+ns, xs, rk, c = synth.make_tt(d, n, r, seed=2026)
+lp, dp = ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_double)
+lib.ttirt_model_create.restype = ctypes.c_void_p
+lib.ttirt_model_create.argtypes = [ctypes.c_longlong, lp, dp, lp, dp, ctypes.c_int]
+lib.ttirt_sample_device.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+n64 = ns.astype(np.int64); r64 = rk.astype(np.int64)
+md = lib.ttirt_model_create(d, n64.ctypes.data_as(lp), xs.ctypes.data_as(dp), r64.ctypes.data_as(lp), c.ctypes.data_as(dp), 0)
+q = torch.rand((d, M), dtype=torch.float64, device="cuda"); z = torch.empty_like(q); l = torch.empty(M, dtype=torch.float64, device="cuda")
+out = (ctypes.c_ulonglong * 40)()
+for it in range(3):
+    lib.ttirt_sample_device(ctypes.c_void_p(md), M, ctypes.c_void_p(q.data_ptr()), M, ctypes.c_void_p(z.data_ptr()), M, ctypes.c_void_p(l.data_ptr()), None, 0, None)
+    torch.cuda.synchronize()
+    lib.ttirt_debug_phase_cycles(out)
+v = np.array(list(out)[:8], dtype=np.float64)
+per_warp = np.array(list(out)[8:], dtype=np.float64)
+names = ["slab/bin", "wait TMA", "update MMA", "issue+F' store", "pdf MMA+tailcol", "cdf+search", "inversion tail+out", "loop head"]
+tot = v.sum()
+warps = int(os.environ.get("PT_WARPS", "8")); mt = int(os.environ.get("PT_MT", "2"))
+ntiles = 31.0 * M / (8 * mt)          # warp-tiles per call (31 transitions)
+for nm, x in zip(names, v):
+    print("%-20s %6.2f%%  %8.0f cycles per warp-tile" % (nm, 100 * x / tot, x / ntiles))
+print("total %.0f cycles per warp-tile" % (tot / ntiles))
+print("loop time per warp id (mean cycles per launch per CTA):", np.round(per_warp[:warps] / (31.0 * 148)).astype(int).tolist())

@@ -54,6 +54,12 @@ static unsigned stagger_ns() {
   return (unsigned)v;
 }
 
+static unsigned stagger_mask() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("TTIRT_STAGGER_MASK"); v = e ? atoi(e) : 4; }
+  return (unsigned)v;
+}
+
 static int64_t default_chunk() {
   int64_t c = g_chunk.load();
   if (c > 0) return c;
@@ -484,7 +490,7 @@ static int run_chunk(ttirt_model *md, Workspace &w, int64_t rows, const double *
     a.q = q + ldq * (k + 1); a.z = z + ldz * (k + 1);
     a.idx_out = idx_out ? idx_out + ldz * (k + 1) : nullptr;
     a.lpz = lpz; a.hist_next = w.hist + (size_t)(k + 1) * nbpad;
-    a.stagger_ns = stagger_ns();
+    a.stagger_ns = stagger_ns(); a.stagger_mask = stagger_mask();
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (md->profile) {
       if (md->prof_used == md->prof_events.size()) {
@@ -626,6 +632,11 @@ extern "C" int ttirt_profile_read(ttirt_model *md, double *ms_total, int64_t *la
   if (flops_total) *flops_total = md->prof_flops;
   return 0;
 }
+
+#ifdef TTIRT_PHASE_TIMING
+namespace ttirt { void phase_cycles_read(unsigned long long *out); }
+extern "C" __attribute__((visibility("default"))) void ttirt_debug_phase_cycles(unsigned long long *out) { cudaDeviceSynchronize(); ttirt::phase_cycles_read(out); }
+#endif
 
 extern "C" int64_t ttirt_kernel_launches(void) { return g_launches.load(); }
 extern "C" const char *ttirt_last_error(void) { return g_err; }

@@ -18,7 +18,25 @@
 // with each other except when their CTA moves to the next interval bin and restages a slab.
 #include "ttirt_common.cuh"
 
+#ifndef TTIRT_WARPS
+#define TTIRT_WARPS 8    // warps per CTA (one CTA per SM)
+#endif
+#ifndef TTIRT_MT
+#define TTIRT_MT 2       // 8-row MMA tiles per warp
+#endif
+
 namespace ttirt {
+
+#ifdef TTIRT_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[8 + 32];
+#define PT_DECL unsigned long long pt_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pt_t = clock64(); const long long pt_start = pt_t;
+#define PT_MARK(k) { const long long n_ = clock64(); pt_[k] += (unsigned long long)(n_ - pt_t); pt_t = n_; }
+#define PT_FLUSH if (lane == 0) { for (int k_ = 0; k_ < 8; k_++) atomicAdd(&g_phase_cycles[k_], pt_[k_]); atomicAdd(&g_phase_cycles[8 + warp], (unsigned long long)(clock64() - pt_start)); }
+#else
+#define PT_DECL
+#define PT_MARK(k)
+#define PT_FLUSH
+#endif
 
 namespace {
 
@@ -69,14 +87,14 @@ __device__ void stage_b(double *dst, const double *__restrict__ src, int K, int 
   }
 }
 
-template <int RT, int NT, int WARPS>
+template <int RT, int NT, int WARPS, int MT>
 struct SmemLayout {
   static constexpr int KPMAX = (8 * RT + 15) & ~15;
   static constexpr int SLAB = 8 * RT * KPMAX;      // doubles per slab buffer
   static constexpr int PN = 8 * NT * KPMAX;        // doubles for P_{k+1}
   static constexpr int NBMAX = 8 * NT;             // >= n - 1 intervals
   static constexpr int FPITCH = 8 * RT + 8;        // doubles per staged left-interface row (+64 B: rows g, g+1 hit different bank halves)
-  static constexpr int FTILE = 16 * FPITCH;        // doubles per warp
+  static constexpr int FTILE = 8 * MT * FPITCH;    // doubles per warp
   static constexpr size_t bytes = sizeof(double) * (2 * SLAB + PN + 3 * 8 * NT + WARPS * FTILE) + sizeof(uint64_t) * WARPS +
                                   sizeof(int) * (2 * (NBMAX + 1) + NBMAX);
 };
@@ -86,14 +104,20 @@ struct SmemLayout {
 // the usual 2^p+1 grid; the lone last grid column is then a 4-lane DFMA dot product instead of a whole DMMA
 // column tile that would be 7/8 padding.
 //
-// Row gather: the 16 left-interface rows of a warp's NEXT tile are fetched by TMA bulk copies (cp.async.bulk,
+// MT: 8-row MMA tiles per warp.  A warp owns 8*MT samples end to end.  MT = 1 with 16 warps (128 registers per
+// thread) puts four warps on every SM sub-partition: while one warp walks the latency-bound CDF / inversion
+// phase three others feed the DMMA pipe.  MT = 2 with 8 warps halves the B-operand shared-memory traffic per
+// DMMA but leaves only two warps per sub-partition.
+//
+// Row gather: the left-interface rows of a warp's NEXT tile are fetched by TMA bulk copies (cp.async.bulk,
 // one 8*r0-byte row per lane, completion counted on a per-warp mbarrier) into a per-warp shared tile as soon
 // as the current tile's update phase has consumed that tile, i.e. a whole pdf + inversion phase ahead of use.
 // The dependent perm -> row latency (two DRAM round trips) therefore never sits in front of the DMMA stream.
-template <int RT, int NT, int WARPS, bool EXACT, bool TAIL1>
+template <int RT, int NT, int WARPS, int MT, bool EXACT, bool TAIL1>
 __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransArgs a) {
   static_assert(EXACT || !TAIL1, "TAIL1 needs EXACT");
-  using L = SmemLayout<RT, NT, WARPS>;
+  static_assert(MT == 1 || MT == 2, "one or two 8-row tiles per warp");
+  using L = SmemLayout<RT, NT, WARPS, MT>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *slab0 = reinterpret_cast<double *>(smem_raw);
   double *slab1 = slab0 + L::SLAB;
@@ -109,7 +133,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  constexpr int NTHR = WARPS * 32, ROWS_CTA = WARPS * 16;
+  constexpr int NTHR = WARPS * 32, WROWS = 8 * MT, ROWS_CTA = WARPS * WROWS;
   constexpr int FP = L::FPITCH;
   double *ft = ft_all + warp * L::FTILE;
   uint64_t *bar = bars + warp;
@@ -149,46 +173,59 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
   auto rows_of = [&](int tile, int &nv) -> int {
     if (tile >= t_end) { nv = 0; return 0; }
     while (tile >= bts[bh + 1]) ++bh;
-    const int row0 = bst[bh] + (tile - bts[bh]) * ROWS_CTA + warp * 16;
-    nv = max(0, min(16, bst[bh + 1] - row0));
+    const int row0 = bst[bh] + (tile - bts[bh]) * ROWS_CTA + warp * WROWS;
+    nv = max(0, min(WROWS, bst[bh + 1] - row0));
     return row0;
   };
-  // sample ids of a tile: lane l (and l+16) holds the id of row l & 15; rows past nv repeat row 0
-  auto load_ids = [&](int row0, int nv) -> int { return nv > 0 ? a.perm[row0 + ((lane & 15) < nv ? (lane & 15) : 0)] : 0; };
+  // sample ids of a tile: lane l holds the id of row l % WROWS; rows past nv repeat row 0
+  auto load_ids = [&](int row0, int nv) -> int {
+    const int r = lane & (WROWS - 1);
+    return nv > 0 ? a.perm[row0 + (r < nv ? r : 0)] : 0;
+  };
 
   uint32_t phase = 0;
   int nvC = 0, nvN = 0;      // valid rows: current tile / next tile
-  int idC = 0, idN = 0;      // row ids (lane-distributed) of the current / next tile
-  // TMA gather of the rows whose ids are idN into this warp's shared tile
+  int idN = 0;               // row ids (lane-distributed) of the next tile
+  // TMA gather of the rows whose ids are `ids` into this warp's shared tile
   auto issue_gather = [&](int ids, int nv) {
     if (nv > 0) {
-      if (lane == 0) mbar_arrive_expect_tx(bar, 16u * row_bytes);
+      if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)WROWS * row_bytes);
       __syncwarp();
-      if (lane < 16) bulk_g2s(ft + lane * FP, a.F + (size_t)ids * a.ldf, row_bytes, bar);
+      if (lane < WROWS) bulk_g2s(ft + lane * FP, a.F + (size_t)ids * a.ldf, row_bytes, bar);
     }
   };
-  double w1A = 0, w2A = 0, w1B = 0, w2B = 0, qA = 0, qB = 0, lpA = 0, lpB = 0;       // current tile
-  double w1An = 0, w2An = 0, w1Bn = 0, w2Bn = 0, qAn = 0, qBn = 0, lpAn = 0, lpBn = 0;  // next tile (in flight)
-  int mA = 0, mB = 0, mAn = 0, mBn = 0;
+  // per-row scalars, m-tile i = rows 8i+g: current tile and next tile (in flight)
+  int mrow[MT], mrow_n[MT];
+  double w1[MT], w2[MT], qv_[MT], lp_[MT], w1n[MT], w2n[MT], qn[MT], lpn[MT];
+#pragma unroll
+  for (int i = 0; i < MT; i++) { mrow[i] = mrow_n[i] = 0; w1[i] = w2[i] = qv_[i] = lp_[i] = w1n[i] = w2n[i] = qn[i] = lpn[i] = 0.0; }
+  auto load_scalars_next = [&]() {
+#pragma unroll
+    for (int i = 0; i < MT; i++) mrow_n[i] = __shfl_sync(FULL, idN, 8 * i + g);
+    if (nvN > 0) {
+#pragma unroll
+      for (int i = 0; i < MT; i++) {
+        w1n[i] = a.w1[mrow_n[i]]; w2n[i] = a.w2[mrow_n[i]]; qn[i] = a.q[mrow_n[i]]; lpn[i] = a.lp[mrow_n[i]];
+      }
+    }
+  };
   {
     const int rowC = rows_of(t_begin, nvC);
-    idC = load_ids(rowC, nvC);
+    const int idC = load_ids(rowC, nvC);
+    issue_gather(idC, nvC);
+    idN = idC; nvN = nvC;
+    load_scalars_next();
+#pragma unroll
+    for (int i = 0; i < MT; i++) { mrow[i] = mrow_n[i]; w1[i] = w1n[i]; w2[i] = w2n[i]; qv_[i] = qn[i]; lp_[i] = lpn[i]; }
     const int rowN = rows_of(t_begin + 1, nvN);
     idN = load_ids(rowN, nvN);
-    issue_gather(idC, nvC);
-    mA = __shfl_sync(FULL, idC, g); mB = __shfl_sync(FULL, idC, g + 8);
-    if (nvC > 0) {
-      w1A = a.w1[mA]; w2A = a.w2[mA]; w1B = a.w1[mB]; w2B = a.w2[mB];
-      qA = a.q[mA]; qB = a.q[mB]; lpA = a.lp[mA]; lpB = a.lp[mB];
-    }
   }
 
-  // Warps w and w+4 share an SM sub-partition (one FP64/DMMA pipe).  Started together and sharing the pipe
-  // fairly they stay in lock-step, so both sit in the latency-bound inversion phase at the same time with the
-  // pipe idle; a start offset of about half a tile (preserved by the same fairness) interleaves their phases.
-  if (warp >= WARPS / 2 && a.stagger_ns) __nanosleep(a.stagger_ns);
-
+  // optional start offset for a subset of the warps (breaks the lock-step of warps sharing a pipe)
+  if (a.stagger_ns && (warp & a.stagger_mask)) __nanosleep(a.stagger_ns);
+  PT_DECL
   for (int tile = t_begin; tile < t_end; ++tile) {
+    PT_MARK(7)
     while (tile >= bts[b + 1]) ++b;
     if (cur0 == b && cur1 == b + 1) {
       sl_lo = slab0; sl_hi = slab1;
@@ -210,30 +247,35 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
       }
       __syncthreads();
       if (cur0 == b) { sl_lo = slab0; sl_hi = slab1; } else { sl_lo = slab1; sl_hi = slab0; }
-      if (warp >= WARPS / 2 && a.stagger_ns) __nanosleep(a.stagger_ns);
     }
 
+    PT_MARK(0)
     const int nvalid = nvC;
-    const bool vA = g < nvalid, vB = (g + 8) < nvalid;
-    double c[2][NT + 1][2];
+    double c[MT][NT + 1][2];
 #pragma unroll
-    for (int j = 0; j <= NT; j++) { c[0][j][0] = c[0][j][1] = c[1][j][0] = c[1][j][1] = 0.0; }
+    for (int i = 0; i < MT; i++)
+#pragma unroll
+      for (int j = 0; j <= NT; j++) c[i][j][0] = c[i][j][1] = 0.0;
 
     if (nvalid > 0) {
       // ---- (1) interface update: A fragments from the TMA-staged rows ------------------------------
       while (!mbar_try_wait(bar, phase)) {}
       phase ^= 1;
-      double acc[2][RT][2];
+      PT_MARK(1)
+      double acc[MT][RT][2];
 #pragma unroll
-      for (int j = 0; j < RT; j++) { acc[0][j][0] = acc[0][j][1] = acc[1][j][0] = acc[1][j][1] = 0.0; }
-      const double *fra = ft + g * FP + 2 * t, *frb = ft + (g + 8) * FP + 2 * t;
+      for (int i = 0; i < MT; i++)
+#pragma unroll
+        for (int j = 0; j < RT; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 #pragma unroll
       for (int j = 0; j < RT; j++) {
         if (EXACT || j < ks0) {
-          const double2 fa = *reinterpret_cast<const double2 *>(fra + 8 * j);
-          const double2 fb = *reinterpret_cast<const double2 *>(frb + 8 * j);
-          const double a1A0 = w1A * fa.x, a2A0 = w2A * fa.x, a1B0 = w1B * fb.x, a2B0 = w2B * fb.x;
-          const double a1A1 = w1A * fa.y, a2A1 = w2A * fa.y, a1B1 = w1B * fb.y, a2B1 = w2B * fb.y;
+          double a1[MT][2], a2[MT][2];
+#pragma unroll
+          for (int i = 0; i < MT; i++) {
+            const double2 f = *reinterpret_cast<const double2 *>(ft + (8 * i + g) * FP + 2 * t + 8 * j);
+            a1[i][0] = w1[i] * f.x; a2[i][0] = w2[i] * f.x; a1[i][1] = w1[i] * f.y; a2[i][1] = w2[i] * f.y;
+          }
           const int sw = ((j ^ (g & 1)) << 3) | (t << 1);
 #pragma unroll
           for (int jj = 0; jj < RT; jj++) {
@@ -241,35 +283,29 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
               const int off = (8 * jj + g) * KP + sw;
               const double2 b1 = *reinterpret_cast<const double2 *>(sl_lo + off);
               const double2 b2 = *reinterpret_cast<const double2 *>(sl_hi + off);
-              dmma884(acc[0][jj][0], acc[0][jj][1], a1A0, b1.x);
-              dmma884(acc[1][jj][0], acc[1][jj][1], a1B0, b1.x);
-              dmma884(acc[0][jj][0], acc[0][jj][1], a2A0, b2.x);
-              dmma884(acc[1][jj][0], acc[1][jj][1], a2B0, b2.x);
-              dmma884(acc[0][jj][0], acc[0][jj][1], a1A1, b1.y);
-              dmma884(acc[1][jj][0], acc[1][jj][1], a1B1, b1.y);
-              dmma884(acc[0][jj][0], acc[0][jj][1], a2A1, b2.y);
-              dmma884(acc[1][jj][0], acc[1][jj][1], a2B1, b2.y);
+#pragma unroll
+              for (int i = 0; i < MT; i++) dmma884(acc[i][jj][0], acc[i][jj][1], a1[i][0], b1.x);
+#pragma unroll
+              for (int i = 0; i < MT; i++) dmma884(acc[i][jj][0], acc[i][jj][1], a2[i][0], b2.x);
+#pragma unroll
+              for (int i = 0; i < MT; i++) dmma884(acc[i][jj][0], acc[i][jj][1], a1[i][1], b1.y);
+#pragma unroll
+              for (int i = 0; i < MT; i++) dmma884(acc[i][jj][0], acc[i][jj][1], a2[i][1], b2.y);
             }
           }
         }
       }
+      PT_MARK(2)
       // ---- the staged tile is consumed: launch the next tile's gather and scalar loads now ---------
       __syncwarp();
       issue_gather(idN, nvN);
-      mAn = __shfl_sync(FULL, idN, g); mBn = __shfl_sync(FULL, idN, g + 8);
-      if (nvN > 0) {
-        w1An = a.w1[mAn]; w2An = a.w2[mAn]; w1Bn = a.w1[mBn]; w2Bn = a.w2[mBn];
-        qAn = a.q[mAn]; qBn = a.q[mBn]; lpAn = a.lp[mAn]; lpBn = a.lp[mBn];
-      }
-      if (!a.last) {
-        double *FA = a.F + (size_t)mA * a.ldf + 2 * t, *FB = a.F + (size_t)mB * a.ldf + 2 * t;
+      load_scalars_next();
+      // F' rows go out one 64-byte segment per pdf k-pair (below), so the stores trickle out under the DMMA stream
+      double *Fo[MT];
 #pragma unroll
-        for (int jj = 0; jj < RT; jj++)
-          if (EXACT || jj < rt_act) {
-            if (vA) *reinterpret_cast<double2 *>(FA + 8 * jj) = make_double2(acc[0][jj][0], acc[0][jj][1]);
-            if (vB) *reinterpret_cast<double2 *>(FB + 8 * jj) = make_double2(acc[1][jj][0], acc[1][jj][1]);
-          }
-      }
+      for (int i = 0; i < MT; i++) Fo[i] = a.F + (size_t)mrow[i] * a.ldf + 2 * t;
+      const bool do_store = !a.last;
+      PT_MARK(3)
       // ---- (2) conditional pdf on the grid of dimension k+1 ----------------------------------------
 #pragma unroll
       for (int jj = 0; jj < RT; jj++) {
@@ -279,141 +315,149 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
           for (int jn = 0; jn < NTD; jn++) {
             if (EXACT || jn < nt_act) {
               const double2 bv = *reinterpret_cast<const double2 *>(Ps + (8 * jn + g) * KP + sw);
-              dmma884(c[0][jn][0], c[0][jn][1], acc[0][jj][0], bv.x);
-              dmma884(c[1][jn][0], c[1][jn][1], acc[1][jj][0], bv.x);
-              dmma884(c[0][jn][0], c[0][jn][1], acc[0][jj][1], bv.y);
-              dmma884(c[1][jn][0], c[1][jn][1], acc[1][jj][1], bv.y);
+#pragma unroll
+              for (int i = 0; i < MT; i++) dmma884(c[i][jn][0], c[i][jn][1], acc[i][jj][0], bv.x);
+#pragma unroll
+              for (int i = 0; i < MT; i++) dmma884(c[i][jn][0], c[i][jn][1], acc[i][jj][1], bv.y);
             }
+          }
+          if (do_store) {
+#pragma unroll
+            for (int i = 0; i < MT; i++)
+              if (8 * i + g < nvalid) *reinterpret_cast<double2 *>(Fo[i] + 8 * jj) = make_double2(acc[i][jj][0], acc[i][jj][1]);
           }
         }
       }
       if (TAIL1) {
         // last grid column (node 8*(NT-1), even column: no swizzle): quad-distributed dot product
-        double tA = 0.0, tB = 0.0;
+        double tl[MT];
+#pragma unroll
+        for (int i = 0; i < MT; i++) tl[i] = 0.0;
 #pragma unroll
         for (int jj = 0; jj < RT; jj++) {
           const double2 pv = *reinterpret_cast<const double2 *>(Ps + (8 * (NT - 1)) * KP + (jj << 3) + (t << 1));
-          tA = fma(acc[0][jj][0], pv.x, tA); tB = fma(acc[1][jj][0], pv.x, tB);
-          tA = fma(acc[0][jj][1], pv.y, tA); tB = fma(acc[1][jj][1], pv.y, tB);
+#pragma unroll
+          for (int i = 0; i < MT; i++) { tl[i] = fma(acc[i][jj][0], pv.x, tl[i]); tl[i] = fma(acc[i][jj][1], pv.y, tl[i]); }
         }
-        tA += __shfl_xor_sync(FULL, tA, 1); tA += __shfl_xor_sync(FULL, tA, 2);
-        tB += __shfl_xor_sync(FULL, tB, 1); tB += __shfl_xor_sync(FULL, tB, 2);
-        c[0][NT - 1][0] = (t == 0) ? tA : 0.0;
-        c[1][NT - 1][0] = (t == 0) ? tB : 0.0;
+#pragma unroll
+        for (int i = 0; i < MT; i++) {
+          tl[i] += __shfl_xor_sync(FULL, tl[i], 1); tl[i] += __shfl_xor_sync(FULL, tl[i], 2);
+          c[i][NT - 1][0] = (t == 0) ? tl[i] : 0.0;
+        }
       }
     } else {
       // this warp has no rows in this tile: keep the pipeline moving
       issue_gather(idN, nvN);
-      mAn = __shfl_sync(FULL, idN, g); mBn = __shfl_sync(FULL, idN, g + 8);
-      if (nvN > 0) {
-        w1An = a.w1[mAn]; w2An = a.w2[mAn]; w1Bn = a.w1[mBn]; w2Bn = a.w2[mBn];
-        qAn = a.q[mAn]; qBn = a.q[mBn]; lpAn = a.lp[mAn]; lpBn = a.lp[mBn];
-      }
+      load_scalars_next();
     }
+    PT_MARK(4)
     // ids of the tile after next
     int nvNN = 0;
     const int rowNN = rows_of(tile + 2, nvNN);
     const int idNN = load_ids(rowNN, nvNN);
 
     if (nvalid > 0) {
-    // ---- (3) CDF, search: both 8-row tiles, all lanes ----------------------------------------------
-    double cdf_lo[2], c1v[2], c2v[2];
-    int i0v[2];
+      // ---- (3) CDF, search: every 8-row tile, all lanes ----------------------------------------------
+      double cdf_lo[MT], c1v[MT], c2v[MT];
+      int i0v[MT];
 #pragma unroll
-    for (int i = 0; i < 2; i++) {
-      const double qv = i ? qB : qA;
+      for (int i = 0; i < MT; i++) {
+        const double qv = qv_[i];
 #pragma unroll
-      for (int jn = 0; jn < NT; jn++) { c[i][jn][0] = fabs(c[i][jn][0]); c[i][jn][1] = fabs(c[i][jn][1]); }
-      double S0[NT], S1[NT];
-      double carry = 0.0;
+        for (int jn = 0; jn < NT; jn++) { c[i][jn][0] = fabs(c[i][jn][0]); c[i][jn][1] = fabs(c[i][jn][1]); }
+        double S0[NT], S1[NT];
+        double carry = 0.0;
 #pragma unroll
-      for (int jn = 0; jn < NT; jn++) {
-        S0[jn] = 0.0; S1[jn] = 0.0;
-        if (TAIL1 && jn == NT - 1) continue;  // the lone last node starts no cell and is never a search candidate
-        if (EXACT || jn < nt_act) {
-          const double p0 = c[i][jn][0], p1 = c[i][jn][1];
-          const double var = (t == 0) ? c[i][jn + 1][0] : p0;
-          const double nxt = __shfl_sync(FULL, var, (t == 3) ? lane - 3 : lane + 1);
-          const double Ta = hh[8 * jn + 2 * t] * (p0 + p1), Tb = hh[8 * jn + 2 * t + 1] * (p1 + nxt);
-          double incl = Ta + Tb;
-          double v = __shfl_up_sync(FULL, incl, 1, 4);
-          if (t >= 1) incl += v;
-          v = __shfl_up_sync(FULL, incl, 2, 4);
-          if (t >= 2) incl += v;
-          double excl = __shfl_up_sync(FULL, incl, 1, 4);
-          if (t == 0) excl = 0.0;
-          const double tot = __shfl_sync(FULL, incl, 3, 4);
-          S0[jn] = carry + excl;
-          S1[jn] = S0[jn] + Ta;
-          carry += tot;
+        for (int jn = 0; jn < NT; jn++) {
+          S0[jn] = 0.0; S1[jn] = 0.0;
+          if (TAIL1 && jn == NT - 1) continue;  // the lone last node starts no cell and is never a search candidate
+          if (EXACT || jn < nt_act) {
+            const double p0 = c[i][jn][0], p1 = c[i][jn][1];
+            const double var = (t == 0) ? c[i][jn + 1][0] : p0;
+            const double nxt = __shfl_sync(FULL, var, (t == 3) ? lane - 3 : lane + 1);
+            const double Ta = hh[8 * jn + 2 * t] * (p0 + p1), Tb = hh[8 * jn + 2 * t + 1] * (p1 + nxt);
+            double incl = Ta + Tb;
+            double v = __shfl_up_sync(FULL, incl, 1, 4);
+            if (t >= 1) incl += v;
+            v = __shfl_up_sync(FULL, incl, 2, 4);
+            if (t >= 2) incl += v;
+            double excl = __shfl_up_sync(FULL, incl, 1, 4);
+            if (t == 0) excl = 0.0;
+            const double tot = __shfl_sync(FULL, incl, 3, 4);
+            S0[jn] = carry + excl;
+            S1[jn] = S0[jn] + Ta;
+            carry += tot;
+          }
+        }
+        const double total = carry;
+        const double sc = 1.0 / total;
+        const double qt = qv * total;   // q > S/total  <=>  q*total > S up to one rounding: decided on the unnormalised CDF
+        int cnt = 0;
+#pragma unroll
+        for (int jn = 0; jn < NTD; jn++) {
+          if (EXACT || jn < nt_act) {
+            const int node0 = 8 * jn + 2 * t;
+            cnt += (node0 >= 1 && node0 <= n1 - 2 && qt > S0[jn]) ? 1 : 0;
+            cnt += (node0 + 1 <= n1 - 2 && qt > S1[jn]) ? 1 : 0;
+          }
+        }
+        cnt += __shfl_xor_sync(FULL, cnt, 1);
+        cnt += __shfl_xor_sync(FULL, cnt, 2);
+        const int i0 = cnt, i1 = cnt + 1;
+        const int js = i0 >> 3, ts = (i0 & 7) >> 1, es = i0 & 1;
+        const int jq = i1 >> 3, tq = (i1 & 7) >> 1, eq = i1 & 1;
+        double selS = 0.0, selP = 0.0, selQ = 0.0;
+#pragma unroll
+        for (int jn = 0; jn < NT; jn++) {
+          if (jn == js) { selS = es ? S1[jn] : S0[jn]; selP = es ? c[i][jn][1] : c[i][jn][0]; }
+          if (jn == jq) { selQ = eq ? c[i][jn][1] : c[i][jn][0]; }
+        }
+        const int base = lane & ~3;
+        selS = __shfl_sync(FULL, selS, base | ts);
+        selP = __shfl_sync(FULL, selP, base | ts);
+        selQ = __shfl_sync(FULL, selQ, base | tq);
+        cdf_lo[i] = selS * sc; c1v[i] = selP * sc; c2v[i] = selQ * sc; i0v[i] = i0;
+        if (total == 0.0) {
+          // zero-mass conditional: uniform in index space (reference tt_irt1_int32.c:116-125)
+          const double u = 1.0 / (double)(n1 - 1);
+          const double s2 = 1.0 / ((double)(n1 - 1) * u);
+          int k0 = 0;
+          for (int j = 1; j <= n1 - 2; j++) k0 += (qv > ((double)j * u) * s2) ? 1 : 0;
+          i0v[i] = k0; cdf_lo[i] = ((double)k0 * u) * s2; c1v[i] = u * s2; c2v[i] = u * s2;
         }
       }
-      const double total = carry;
-      const double sc = 1.0 / total;
-      const double qt = qv * total;   // q > S/total  <=>  q*total > S up to one rounding: decided on the unnormalised CDF
-      int cnt = 0;
-#pragma unroll
-      for (int jn = 0; jn < NTD; jn++) {
-        if (EXACT || jn < nt_act) {
-          const int node0 = 8 * jn + 2 * t;
-          cnt += (node0 >= 1 && node0 <= n1 - 2 && qt > S0[jn]) ? 1 : 0;
-          cnt += (node0 + 1 <= n1 - 2 && qt > S1[jn]) ? 1 : 0;
-        }
-      }
-      cnt += __shfl_xor_sync(FULL, cnt, 1);
-      cnt += __shfl_xor_sync(FULL, cnt, 2);
-      const int i0 = cnt, i1 = cnt + 1;
-      const int js = i0 >> 3, ts = (i0 & 7) >> 1, es = i0 & 1;
-      const int jq = i1 >> 3, tq = (i1 & 7) >> 1, eq = i1 & 1;
-      double selS = 0.0, selP = 0.0, selQ = 0.0;
-#pragma unroll
-      for (int jn = 0; jn < NT; jn++) {
-        if (jn == js) { selS = es ? S1[jn] : S0[jn]; selP = es ? c[i][jn][1] : c[i][jn][0]; }
-        if (jn == jq) { selQ = eq ? c[i][jn][1] : c[i][jn][0]; }
-      }
-      const int base = lane & ~3;
-      selS = __shfl_sync(FULL, selS, base | ts);
-      selP = __shfl_sync(FULL, selP, base | ts);
-      selQ = __shfl_sync(FULL, selQ, base | tq);
-      cdf_lo[i] = selS * sc; c1v[i] = selP * sc; c2v[i] = selQ * sc; i0v[i] = i0;
-      if (total == 0.0) {
-        // zero-mass conditional: uniform in index space (reference tt_irt1_int32.c:116-125)
-        const double u = 1.0 / (double)(n1 - 1);
-        const double s2 = 1.0 / ((double)(n1 - 1) * u);
-        int k0 = 0;
-        for (int j = 1; j <= n1 - 2; j++) k0 += (qv > ((double)j * u) * s2) ? 1 : 0;
-        i0v[i] = k0; cdf_lo[i] = ((double)k0 * u) * s2; c1v[i] = u * s2; c2v[i] = u * s2;
-      }
-    }
 
-    // ---- inversion tail: lane t=0 of a quad finishes row g, lane t=1 row g+8 ---------------------
-    {
-      const int sel = t & 1;
-      const bool valid = (t < 2) && (sel ? vB : vA);
-      const int m = sel ? mB : mA;
-      const int i0 = sel ? i0v[1] : i0v[0];
-      const CellOut o = invert_cell_fast(sel ? qB : qA, sel ? cdf_lo[1] : cdf_lo[0], sel ? c1v[1] : c1v[0],
-                                         sel ? c2v[1] : c2v[0], xg[i0], xg[i0 + 1], ihs[i0]);
-      if (valid) {
-        a.z[m] = o.xk;
-        if (a.idx_out) a.idx_out[m] = i0;
-        if (!a.last) {
-          a.idx[m] = i0; a.w1[m] = o.w1; a.w2[m] = o.w2;
-          a.lp[m] = (sel ? lpB : lpA) + o.logp;
-          atomicAdd(&hist[i0], 1);
-        } else {
-          a.lpz[m] = (sel ? lpB : lpA) + o.logp;
+      PT_MARK(5)
+      // ---- inversion tail: lane t = i of a quad finishes row 8i + g ---------------------------------
+      {
+        const int sel = (MT == 2) ? (t & 1) : 0;
+        const bool valid = (t < MT) && (8 * sel + g < nvalid);
+        const int m = mrow[sel];
+        const int i0 = i0v[sel];
+        const CellOut o = invert_cell_fast(qv_[sel], cdf_lo[sel], c1v[sel], c2v[sel], xg[i0], xg[i0 + 1], ihs[i0]);
+        if (valid) {
+          a.z[m] = o.xk;
+          if (a.idx_out) a.idx_out[m] = i0;
+          if (!a.last) {
+            a.idx[m] = i0; a.w1[m] = o.w1; a.w2[m] = o.w2;
+            a.lp[m] = lp_[sel] + o.logp;
+            atomicAdd(&hist[i0], 1);
+          } else {
+            a.lpz[m] = lp_[sel] + o.logp;
+          }
         }
       }
-    }
     }  // nvalid > 0
 
+    PT_MARK(6)
     // ---- rotate the row pipeline --------------------------------------------------------------------
-    nvC = nvN; idC = idN; mA = mAn; mB = mBn;
-    w1A = w1An; w2A = w2An; w1B = w1Bn; w2B = w2Bn; qA = qAn; qB = qBn; lpA = lpAn; lpB = lpBn;
+    nvC = nvN;
+#pragma unroll
+    for (int i = 0; i < MT; i++) { mrow[i] = mrow_n[i]; w1[i] = w1n[i]; w2[i] = w2n[i]; qv_[i] = qn[i]; lp_[i] = lpn[i]; }
     nvN = nvNN; idN = idNN;
   }
 
+  PT_FLUSH
   if (!a.last) {
     __syncthreads();
     for (int i = tid; i < n1 - 1; i += NTHR)
@@ -421,43 +465,44 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
   }
 }
 
-template <int RT, int NT, int WARPS, bool EXACT, bool TAIL1>
+template <int RT, int NT, int WARPS, int MT, bool EXACT, bool TAIL1>
 cudaError_t launch_variant(const TransArgs &a, int sm_count, cudaStream_t st) {
-  using L = SmemLayout<RT, NT, WARPS>;
+  using L = SmemLayout<RT, NT, WARPS, MT>;
   static int occ = 0;
   if (occ == 0) {
     int o = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, transition_kernel<RT, NT, WARPS, EXACT, TAIL1>, WARPS * 32, L::bytes);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, transition_kernel<RT, NT, WARPS, MT, EXACT, TAIL1>, WARPS * 32, L::bytes);
     if (e != cudaSuccess) return e;
     occ = o > 0 ? o : 1;
   }
-  const int rows_cta = WARPS * 16;
+  const int rows_cta = WARPS * 8 * MT;
   int64_t max_tiles = ((int64_t)a.rows + rows_cta - 1) / rows_cta + (a.n0 - 1);
   int64_t grid = (int64_t)sm_count * occ;
   if (grid > max_tiles) grid = max_tiles;
   if (grid < 1) grid = 1;
-  transition_kernel<RT, NT, WARPS, EXACT, TAIL1><<<(unsigned)grid, WARPS * 32, L::bytes, st>>>(a);
+  transition_kernel<RT, NT, WARPS, MT, EXACT, TAIL1><<<(unsigned)grid, WARPS * 32, L::bytes, st>>>(a);
   return cudaGetLastError();
 }
 
-template <int RT, int NT, int WARPS>
+template <int RT, int NT, int WARPS, int MT>
 cudaError_t launch_one(const TransArgs &a, int sm_count, cudaStream_t st) {
   const bool exact = a.r0 == 8 * RT && a.r1 == 8 * RT && (a.n1 + 7) / 8 == NT;
-  if (exact && a.n1 == 8 * (NT - 1) + 1) return launch_variant<RT, NT, WARPS, true, true>(a, sm_count, st);
-  if (exact) return launch_variant<RT, NT, WARPS, true, false>(a, sm_count, st);
-  return launch_variant<RT, NT, WARPS, false, false>(a, sm_count, st);
+  if (exact && a.n1 == 8 * (NT - 1) + 1) return launch_variant<RT, NT, WARPS, MT, true, true>(a, sm_count, st);
+  if (exact) return launch_variant<RT, NT, WARPS, MT, true, false>(a, sm_count, st);
+  return launch_variant<RT, NT, WARPS, MT, false, false>(a, sm_count, st);
 }
 
-template <int RT, int NT, int WARPS>
+template <int RT, int NT, int WARPS, int MT>
 cudaError_t init_one() {
-  using L = SmemLayout<RT, NT, WARPS>;
+  using L = SmemLayout<RT, NT, WARPS, MT>;
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(transition_kernel<RT, NT, WARPS, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(transition_kernel<RT, NT, WARPS, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes)) != cudaSuccess) return e;
-  return cudaFuncSetAttribute(transition_kernel<RT, NT, WARPS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes);
+  if ((e = cudaFuncSetAttribute(transition_kernel<RT, NT, WARPS, MT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(transition_kernel<RT, NT, WARPS, MT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(transition_kernel<RT, NT, WARPS, MT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes);
 }
 
-constexpr int kWarps = 8;
+constexpr int kWarps = TTIRT_WARPS;
+constexpr int kMT = TTIRT_MT;
 
 }  // namespace
 
@@ -468,23 +513,31 @@ int fast_class_for(int rmax, int nmax) {
   return -1;
 }
 
-int fast_rows_per_cta(int) { return kWarps * 16; }
+int fast_rows_per_cta(int) { return kWarps * 8 * kMT; }
 
 cudaError_t fast_init(int) {
   cudaError_t e;
-  if ((e = init_one<2, 3, kWarps>()) != cudaSuccess) return e;
-  if ((e = init_one<4, 5, kWarps>()) != cudaSuccess) return e;
-  if ((e = init_one<8, 9, kWarps>()) != cudaSuccess) return e;
+  if ((e = init_one<2, 3, kWarps, kMT>()) != cudaSuccess) return e;
+  if ((e = init_one<4, 5, kWarps, kMT>()) != cudaSuccess) return e;
+  if ((e = init_one<8, 9, kWarps, kMT>()) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
 cudaError_t launch_transition(int cls, const TransArgs &a, int sm_count, cudaStream_t st) {
   switch (cls) {
-    case 0: return launch_one<2, 3, kWarps>(a, sm_count, st);
-    case 1: return launch_one<4, 5, kWarps>(a, sm_count, st);
-    case 2: return launch_one<8, 9, kWarps>(a, sm_count, st);
+    case 0: return launch_one<2, 3, kWarps, kMT>(a, sm_count, st);
+    case 1: return launch_one<4, 5, kWarps, kMT>(a, sm_count, st);
+    case 2: return launch_one<8, 9, kWarps, kMT>(a, sm_count, st);
     default: return cudaErrorInvalidValue;
   }
 }
+
+#ifdef TTIRT_PHASE_TIMING
+void phase_cycles_read(unsigned long long *out) {
+  cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(unsigned long long) * 40);
+  unsigned long long z[40] = {0};
+  cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z));
+}
+#endif
 
 }  // namespace ttirt
