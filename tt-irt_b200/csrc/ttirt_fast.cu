@@ -67,6 +67,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
   return ok != 0;
 }
 
+// ---- cp.async (LDGSTS): 16 bytes per lane, global -> shared, per-thread completion groups ---------------------
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // Shared-memory image of a B operand (K x NC, column-major in global memory with column stride cs).
 // Column c lives at c*KP.  Rows keep their natural order inside groups of 8 and the groups are XOR-swizzled
 // with the column's parity: a thread quad reads, per pair of k-steps, 16 bytes per lane (LDS.128: rows
@@ -186,12 +193,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
   uint32_t phase = 0;
   int nvC = 0, nvN = 0;      // valid rows: current tile / next tile
   int idN = 0;               // row ids (lane-distributed) of the next tile
-  // TMA gather of the rows whose ids are `ids` into this warp's shared tile
+  // Gather of the rows whose ids are `ids` into this warp's shared tile: one cp.async (LDGSTS) instruction per row,
+  // 16 bytes per lane, so a row is one coalesced 8*r0-byte segment.  (Sixteen single-row cp.async.bulk copies per
+  // tile were measured at ~1000 cycles of issue time per tile; this costs ~150.)
   auto issue_gather = [&](int ids, int nv) {
     if (nv > 0) {
-      if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)WROWS * row_bytes);
-      __syncwarp();
-      if (lane < WROWS) bulk_g2s(ft + lane * FP, a.F + (size_t)ids * a.ldf, row_bytes, bar);
+#pragma unroll
+      for (int r = 0; r < WROWS; r++) {
+        const int id = __shfl_sync(FULL, ids, r);
+        if (16u * lane < row_bytes)
+          cp_async16(reinterpret_cast<char *>(ft + r * FP) + 16 * lane, reinterpret_cast<const char *>(a.F + (size_t)id * a.ldf) + 16 * lane);
+      }
+      cp_async_commit();
     }
   };
   // per-row scalars, m-tile i = rows 8i+g: current tile and next tile (in flight)
@@ -259,8 +272,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
 
     if (nvalid > 0) {
       // ---- (1) interface update: A fragments from the TMA-staged rows ------------------------------
-      while (!mbar_try_wait(bar, phase)) {}
-      phase ^= 1;
+      cp_async_wait_all();
+      __syncwarp();
       PT_MARK(1)
       double acc[MT][RT][2];
 #pragma unroll
@@ -299,6 +312,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
       // ---- the staged tile is consumed: launch the next tile's gather and scalar loads now ---------
       __syncwarp();
       issue_gather(idN, nvN);
+      PT_MARK(7)
       load_scalars_next();
       // F' rows go out one 64-byte segment per pdf k-pair (below), so the stores trickle out under the DMMA stream
       double *Fo[MT];
