@@ -535,6 +535,23 @@ extern "C" int ttirt_sample_device(ttirt_model *md, int64_t M, const double *d_q
 // ------------------------------------------------------------------------------------------------
 // host buffers: chunked H2D -> kernels -> D2H over kSlots streams
 // ------------------------------------------------------------------------------------------------
+// Page-lock a caller buffer for the duration of a call when it is ordinary pageable memory and large enough for
+// the registration to pay for itself (asynchronous, full-rate PCIe copies instead of staged synchronous ones).
+// Off by default (measured on B200: cudaHostRegister of 8.6 GB per call costs ~1 s, more than the staged copies
+// it replaces); TTIRT_PIN=1 enables it for callers that reuse the same buffers.  Returns true when registered here.
+static bool pin_if_pageable(const void *p, size_t bytes) {
+  static int mode = -1;
+  if (mode < 0) { const char *e = getenv("TTIRT_PIN"); mode = e ? atoi(e) + 1 : 1; }   // 1 off (default: registering 8 GB per call costs more than it saves), 2 on
+  if (!p || bytes == 0 || mode == 1) return false;
+  if (bytes < ((size_t)32 << 20)) return false;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  if (at.type != cudaMemoryTypeUnregistered) return false;
+  if (cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); return false; }
+  return true;
+}
+static void unpin(const void *p, bool pinned) { if (pinned) { cudaHostUnregister(const_cast<void *>(p)); } }
+
 static int sample_host_rows(ttirt_model *md, int64_t m_begin, int64_t m_end, const double *h_q, double *h_z, double *h_lpz,
                             int32_t *h_idx, int64_t ld, int mode) {
   const int64_t M = m_end - m_begin;
@@ -572,7 +589,12 @@ extern "C" int ttirt_sample_host(ttirt_model *md, int64_t M, const double *h_q, 
   g_err[0] = 0;
   if (!md) return fail("null model");
   if (M < 0 || ld < M) return fail("bad M / leading dimension");
-  return sample_host_rows(md, 0, M, h_q, h_z, h_lpz, h_idx, ld, mode);
+  CK(cudaSetDevice(md->device));
+  const bool pq = pin_if_pageable(h_q, sizeof(double) * ld * md->d), pz = pin_if_pageable(h_z, sizeof(double) * ld * md->d),
+             pl = pin_if_pageable(h_lpz, sizeof(double) * M);
+  const int rc = sample_host_rows(md, 0, M, h_q, h_z, h_lpz, h_idx, ld, mode);
+  unpin(h_q, pq); unpin(h_z, pz); unpin(h_lpz, pl);
+  return rc;
 }
 
 extern "C" int ttirt_run_host(int64_t d, const int64_t *n, const double *xs, const int64_t *ttrank, const double *ttcore,
@@ -585,6 +607,13 @@ extern "C" int ttirt_run_host(int64_t d, const int64_t *n, const double *xs, con
   if (n_devices <= 0 || first_device < 0 || first_device + n_devices > cnt)
     return fail("device range [%d, %d) not available (%d visible)", first_device, first_device + n_devices, cnt);
   if (M == 0) return 0;
+  if (cudaSetDevice(first_device) != cudaSuccess) return fail("cudaSetDevice(%d) failed", first_device);
+  const bool pq = pin_if_pageable(h_q, sizeof(double) * M * d), pz = pin_if_pageable(h_z, sizeof(double) * M * d),
+             pl = pin_if_pageable(h_lpz, sizeof(double) * M);
+  struct Unpin {
+    const void *q, *z, *l; bool pq, pz, pl;
+    ~Unpin() { unpin(q, pq); unpin(z, pz); unpin(l, pl); }
+  } unpin_guard{h_q, h_z, h_lpz, pq, pz, pl};
   if (n_devices == 1) {
     ttirt_model *md = ttirt_model_create(d, n, xs, ttrank, ttcore, first_device);
     if (!md) return -1;

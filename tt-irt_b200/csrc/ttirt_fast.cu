@@ -48,24 +48,7 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
       : "d"(a), "d"(b));
 }
 
-// ---- TMA bulk copy + mbarrier (sm_90+/sm_100a): global rows -> shared memory, completion by transaction bytes ----
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  return ok != 0;
-}
 
 // ---- cp.async (LDGSTS): 16 bytes per lane, global -> shared, per-thread completion groups ---------------------
 __device__ __forceinline__ void cp_async16(void *dst, const void *src) {
@@ -102,7 +85,7 @@ struct SmemLayout {
   static constexpr int NBMAX = 8 * NT;             // >= n - 1 intervals
   static constexpr int FPITCH = 8 * RT + 8;        // doubles per staged left-interface row (+64 B: rows g, g+1 hit different bank halves)
   static constexpr int FTILE = 8 * MT * FPITCH;    // doubles per warp
-  static constexpr size_t bytes = sizeof(double) * (2 * SLAB + PN + 3 * 8 * NT + WARPS * FTILE) + sizeof(uint64_t) * WARPS +
+  static constexpr size_t bytes = sizeof(double) * (2 * SLAB + PN + 3 * 8 * NT + WARPS * FTILE) +
                                   sizeof(int) * (2 * (NBMAX + 1) + NBMAX);
 };
 
@@ -116,10 +99,10 @@ struct SmemLayout {
 // phase three others feed the DMMA pipe.  MT = 2 with 8 warps halves the B-operand shared-memory traffic per
 // DMMA but leaves only two warps per sub-partition.
 //
-// Row gather: the left-interface rows of a warp's NEXT tile are fetched by TMA bulk copies (cp.async.bulk,
-// one 8*r0-byte row per lane, completion counted on a per-warp mbarrier) into a per-warp shared tile as soon
-// as the current tile's update phase has consumed that tile, i.e. a whole pdf + inversion phase ahead of use.
-// The dependent perm -> row latency (two DRAM round trips) therefore never sits in front of the DMMA stream.
+// Row gather: the left-interface rows of a warp's NEXT tile are fetched asynchronously (cp.async / LDGSTS, one
+// coalesced 8*r0-byte row per instruction) into a per-warp shared tile as soon as the current tile's update
+// phase has consumed that tile, i.e. a whole pdf + inversion phase ahead of use.  The dependent perm -> row
+// latency (two DRAM round trips) therefore never sits in front of the DMMA stream.
 template <int RT, int NT, int WARPS, int MT, bool EXACT, bool TAIL1>
 __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransArgs a) {
   static_assert(EXACT || !TAIL1, "TAIL1 needs EXACT");
@@ -133,8 +116,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
   double *hh = ft_all + WARPS * L::FTILE;  // half grid steps of dimension k+1, zero beyond n1-2
   double *xg = hh + 8 * NT;          // grid of dimension k+1
   double *ihs = xg + 8 * NT;         // reciprocal cell widths of dimension k+1
-  uint64_t *bars = reinterpret_cast<uint64_t *>(ihs + 8 * NT);
-  int *bts = reinterpret_cast<int *>(bars + WARPS);  // bin -> first CTA tile
+  int *bts = reinterpret_cast<int *>(ihs + 8 * NT);  // bin -> first CTA tile
   int *bst = bts + (L::NBMAX + 1);                    // bin -> first sorted row
   int *hist = bst + (L::NBMAX + 1);                   // histogram of the intervals chosen in dimension k+1
 
@@ -143,7 +125,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
   constexpr int NTHR = WARPS * 32, WROWS = 8 * MT, ROWS_CTA = WARPS * WROWS;
   constexpr int FP = L::FPITCH;
   double *ft = ft_all + warp * L::FTILE;
-  uint64_t *bar = bars + warp;
 
   const int r0 = a.r0, r1 = a.r1, n1 = a.n1, nb0 = a.n0 - 1;
   constexpr int KP = L::KPMAX;                   // compile-time column pitch: B-fragment offsets fold into immediates
@@ -161,8 +142,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
     ihs[i] = (i + 1 < n1) ? 1.0 / (a.xnext[i + 1] - a.xnext[i]) : 0.0;
     if (i < L::NBMAX) hist[i] = 0;
   }
-  if (lane == 0) mbar_init(bar, 1);
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   stage_b(Ps, a.pnext, r1, n1, r1, KP, 8 * NT, tid, NTHR);
   __syncthreads();
 
@@ -190,7 +169,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
     return nv > 0 ? a.perm[row0 + (r < nv ? r : 0)] : 0;
   };
 
-  uint32_t phase = 0;
   int nvC = 0, nvN = 0;      // valid rows: current tile / next tile
   int idN = 0;               // row ids (lane-distributed) of the next tile
   // Gather of the rows whose ids are `ids` into this warp's shared tile: one cp.async (LDGSTS) instruction per row,
@@ -371,77 +349,92 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
     const int idNN = load_ids(rowNN, nvNN);
 
     if (nvalid > 0) {
-      // ---- (3) CDF, search: every 8-row tile, all lanes ----------------------------------------------
+      // ---- (3) CDF, search: all lanes; the MT row tiles are advanced together (independent chains interleave) ----
       double cdf_lo[MT], c1v[MT], c2v[MT];
       int i0v[MT];
+      {
+        double S0[MT][NT], S1[MT][NT], carry[MT];
 #pragma unroll
-      for (int i = 0; i < MT; i++) {
-        const double qv = qv_[i];
+        for (int i = 0; i < MT; i++) {
+          carry[i] = 0.0;
 #pragma unroll
-        for (int jn = 0; jn < NT; jn++) { c[i][jn][0] = fabs(c[i][jn][0]); c[i][jn][1] = fabs(c[i][jn][1]); }
-        double S0[NT], S1[NT];
-        double carry = 0.0;
+          for (int jn = 0; jn < NT; jn++) { c[i][jn][0] = fabs(c[i][jn][0]); c[i][jn][1] = fabs(c[i][jn][1]); S0[i][jn] = 0.0; S1[i][jn] = 0.0; }
+        }
 #pragma unroll
         for (int jn = 0; jn < NT; jn++) {
-          S0[jn] = 0.0; S1[jn] = 0.0;
           if (TAIL1 && jn == NT - 1) continue;  // the lone last node starts no cell and is never a search candidate
           if (EXACT || jn < nt_act) {
-            const double p0 = c[i][jn][0], p1 = c[i][jn][1];
-            const double var = (t == 0) ? c[i][jn + 1][0] : p0;
-            const double nxt = __shfl_sync(FULL, var, (t == 3) ? lane - 3 : lane + 1);
-            const double Ta = hh[8 * jn + 2 * t] * (p0 + p1), Tb = hh[8 * jn + 2 * t + 1] * (p1 + nxt);
-            double incl = Ta + Tb;
-            double v = __shfl_up_sync(FULL, incl, 1, 4);
-            if (t >= 1) incl += v;
-            v = __shfl_up_sync(FULL, incl, 2, 4);
-            if (t >= 2) incl += v;
-            double excl = __shfl_up_sync(FULL, incl, 1, 4);
-            if (t == 0) excl = 0.0;
-            const double tot = __shfl_sync(FULL, incl, 3, 4);
-            S0[jn] = carry + excl;
-            S1[jn] = S0[jn] + Ta;
-            carry += tot;
+            const double h0 = hh[8 * jn + 2 * t], h1 = hh[8 * jn + 2 * t + 1];
+            double Ta[MT], incl[MT];
+#pragma unroll
+            for (int i = 0; i < MT; i++) {
+              const double p0 = c[i][jn][0], p1 = c[i][jn][1];
+              const double var = (t == 0) ? c[i][jn + 1][0] : p0;
+              const double nxt = __shfl_sync(FULL, var, (t == 3) ? lane - 3 : lane + 1);
+              Ta[i] = h0 * (p0 + p1);
+              incl[i] = Ta[i] + h1 * (p1 + nxt);
+            }
+#pragma unroll
+            for (int i = 0; i < MT; i++) { const double v = __shfl_up_sync(FULL, incl[i], 1, 4); if (t >= 1) incl[i] += v; }
+#pragma unroll
+            for (int i = 0; i < MT; i++) { const double v = __shfl_up_sync(FULL, incl[i], 2, 4); if (t >= 2) incl[i] += v; }
+#pragma unroll
+            for (int i = 0; i < MT; i++) {
+              double excl = __shfl_up_sync(FULL, incl[i], 1, 4);
+              if (t == 0) excl = 0.0;
+              const double tot = __shfl_sync(FULL, incl[i], 3, 4);
+              S0[i][jn] = carry[i] + excl;
+              S1[i][jn] = S0[i][jn] + Ta[i];
+              carry[i] += tot;
+            }
           }
         }
-        const double total = carry;
-        const double sc = 1.0 / total;
-        const double qt = qv * total;   // q > S/total  <=>  q*total > S up to one rounding: decided on the unnormalised CDF
-        int cnt = 0;
+        double sc[MT], qt[MT];
+        int cnt[MT];
+#pragma unroll
+        for (int i = 0; i < MT; i++) { sc[i] = 1.0 / carry[i]; qt[i] = qv_[i] * carry[i]; cnt[i] = 0; }  // q > S/total <=> q*total > S
 #pragma unroll
         for (int jn = 0; jn < NTD; jn++) {
           if (EXACT || jn < nt_act) {
             const int node0 = 8 * jn + 2 * t;
-            cnt += (node0 >= 1 && node0 <= n1 - 2 && qt > S0[jn]) ? 1 : 0;
-            cnt += (node0 + 1 <= n1 - 2 && qt > S1[jn]) ? 1 : 0;
+#pragma unroll
+            for (int i = 0; i < MT; i++) {
+              cnt[i] += (node0 >= 1 && node0 <= n1 - 2 && qt[i] > S0[i][jn]) ? 1 : 0;
+              cnt[i] += (node0 + 1 <= n1 - 2 && qt[i] > S1[i][jn]) ? 1 : 0;
+            }
           }
         }
-        cnt += __shfl_xor_sync(FULL, cnt, 1);
-        cnt += __shfl_xor_sync(FULL, cnt, 2);
-        const int i0 = cnt, i1 = cnt + 1;
-        const int js = i0 >> 3, ts = (i0 & 7) >> 1, es = i0 & 1;
-        const int jq = i1 >> 3, tq = (i1 & 7) >> 1, eq = i1 & 1;
-        double selS = 0.0, selP = 0.0, selQ = 0.0;
 #pragma unroll
-        for (int jn = 0; jn < NT; jn++) {
-          if (jn == js) { selS = es ? S1[jn] : S0[jn]; selP = es ? c[i][jn][1] : c[i][jn][0]; }
-          if (jn == jq) { selQ = eq ? c[i][jn][1] : c[i][jn][0]; }
-        }
-        const int base = lane & ~3;
-        selS = __shfl_sync(FULL, selS, base | ts);
-        selP = __shfl_sync(FULL, selP, base | ts);
-        selQ = __shfl_sync(FULL, selQ, base | tq);
-        cdf_lo[i] = selS * sc; c1v[i] = selP * sc; c2v[i] = selQ * sc; i0v[i] = i0;
-        if (total == 0.0) {
-          // zero-mass conditional: uniform in index space (reference tt_irt1_int32.c:116-125)
-          const double u = 1.0 / (double)(n1 - 1);
-          const double s2 = 1.0 / ((double)(n1 - 1) * u);
-          int k0 = 0;
-          for (int j = 1; j <= n1 - 2; j++) k0 += (qv > ((double)j * u) * s2) ? 1 : 0;
-          i0v[i] = k0; cdf_lo[i] = ((double)k0 * u) * s2; c1v[i] = u * s2; c2v[i] = u * s2;
+        for (int i = 0; i < MT; i++) { cnt[i] += __shfl_xor_sync(FULL, cnt[i], 1); }
+#pragma unroll
+        for (int i = 0; i < MT; i++) { cnt[i] += __shfl_xor_sync(FULL, cnt[i], 2); }
+#pragma unroll
+        for (int i = 0; i < MT; i++) {
+          const int i0 = cnt[i], i1 = cnt[i] + 1;
+          const int js = i0 >> 3, ts = (i0 & 7) >> 1, es = i0 & 1;
+          const int jq = i1 >> 3, tq = (i1 & 7) >> 1, eq = i1 & 1;
+          double selS = 0.0, selP = 0.0, selQ = 0.0;
+#pragma unroll
+          for (int jn = 0; jn < NT; jn++) {
+            if (jn == js) { selS = es ? S1[i][jn] : S0[i][jn]; selP = es ? c[i][jn][1] : c[i][jn][0]; }
+            if (jn == jq) { selQ = eq ? c[i][jn][1] : c[i][jn][0]; }
+          }
+          const int base = lane & ~3;
+          selS = __shfl_sync(FULL, selS, base | ts);
+          selP = __shfl_sync(FULL, selP, base | ts);
+          selQ = __shfl_sync(FULL, selQ, base | tq);
+          cdf_lo[i] = selS * sc[i]; c1v[i] = selP * sc[i]; c2v[i] = selQ * sc[i]; i0v[i] = i0;
+          if (carry[i] == 0.0) {
+            // zero-mass conditional: uniform in index space (reference tt_irt1_int32.c:116-125)
+            const double u = 1.0 / (double)(n1 - 1);
+            const double s2 = 1.0 / ((double)(n1 - 1) * u);
+            int k0 = 0;
+            for (int j = 1; j <= n1 - 2; j++) k0 += (qv_[i] > ((double)j * u) * s2) ? 1 : 0;
+            i0v[i] = k0; cdf_lo[i] = ((double)k0 * u) * s2; c1v[i] = u * s2; c2v[i] = u * s2;
+          }
         }
       }
 
-      PT_MARK(5)
       // ---- inversion tail: lane t = i of a quad finishes row 8i + g ---------------------------------
       {
         const int sel = (MT == 2) ? (t & 1) : 0;
