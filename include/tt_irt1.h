@@ -51,7 +51,8 @@ extern "C" {
  * Returns nothing (as the reference).  On any failure (no device, bad shape, CUDA error) it prints
  * one line to stderr and fills z and lPz with NaN; it never aborts the host process.
  * Environment: TTIRT_MODE=fast|strict (default fast), TTIRT_DEVICES=<count>|all (default 1),
- * TTIRT_DEVICE=<first ordinal> (default 0), TTIRT_CHUNK=<samples per chunk>, TTIRT_VERBOSE=1.
+ * TTIRT_DEVICE=<first ordinal> (default 0), TTIRT_CHUNK=<samples per chunk>, TTIRT_CACHE=0 (free all device
+ * memory before returning), TTIRT_TRACE=1 (host-side phase times on stderr), TTIRT_VERBOSE=1.
  */
 TTIRT_API void tt_irt1(TTIRT_INT d, TTIRT_INT *n, double *xs, TTIRT_INT *ttrank, double *ttcore, TTIRT_INT M,
              double *q, double *z, double *lPz);
@@ -89,7 +90,8 @@ TTIRT_API int ttirt_sample_host(ttirt_model *model, int64_t M, const double *h_q
                       int32_t *h_idx, int64_t ld, int mode);
 
 /* Whole call on host buffers: create models on n_devices devices starting at first_device, shard the
- * M rows contiguously across them (one host thread per device, no collective), free everything.
+ * M rows contiguously across them (one host thread per device, no collective).  Grid and cores are uploaded and
+ * the sweep is run on every call; only device allocations are reused between calls (see ttirt_cache_clear).
  * This is what tt_irt1() runs.  0 on success. */
 TTIRT_API int ttirt_run_host(int64_t d, const int64_t *n, const double *xs, const int64_t *ttrank,
                    const double *ttcore, int64_t M, const double *h_q, double *h_z, double *h_lpz,
@@ -110,6 +112,9 @@ TTIRT_API const char *ttirt_last_error(void);
 TTIRT_API int ttirt_device_count(void);
 /* Samples per chunk used by the pipelines (0 restores the default). */
 TTIRT_API void ttirt_set_chunk(int64_t samples);
+/* tt_irt1 / ttirt_run_host keep their device allocations (never any results) per device for the next call of the
+ * same shape; this releases them.  TTIRT_CACHE=0 in the environment disables the reuse altogether. */
+TTIRT_API void ttirt_cache_clear(void);
 
 #ifdef __cplusplus
 }

@@ -9,12 +9,14 @@
 // There is no CPU fallback anywhere in this file: without a device every entry point fails.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -95,7 +97,7 @@ struct ttirt_model {
   int64_t d = 0;
   std::vector<int64_t> n, r;
   std::vector<DimInfo> dims;
-  int64_t rmax = 1, nmax = 2, nbpad = 0, sum_pk = 0, sum_mg = 0;
+  int64_t rmax = 1, nmax = 2, nbpad = 0, sum_pk = 0, sum_mg = 0, sum_x = 0, sum_c = 0;
   int ldf = 8;
   int fast_cls = -1;
   double *d_xs = nullptr, *d_core = nullptr, *d_pk = nullptr, *d_marg = nullptr;
@@ -365,6 +367,32 @@ extern "C" void ttirt_model_destroy(ttirt_model *md) {
   delete md;
 }
 
+// Upload grid and cores into an allocated model of matching shape and run the right-to-left sweep:
+// C_{d-1} = {1}; P_k = core_k x_3 C_k; C_{k-1} = trapezoid(P_k)   (reference tt_irt1_int32.c:59-82)
+static int model_load(ttirt_model *md, const double *xs, const double *core) {
+  const int64_t d = md->d;
+  CK(cudaMemcpy(md->d_xs, xs, sizeof(double) * md->sum_x, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(md->d_core, core, sizeof(double) * md->sum_c, cudaMemcpyHostToDevice));
+  const double one = 1.0;
+  CK(cudaMemcpy(md->d_marg + md->dims[d - 1].off_m, &one, sizeof(double), cudaMemcpyHostToDevice));
+  for (int64_t k = d - 1; k >= 0; k--) {
+    const DimInfo &di = md->dims[k];
+    const int rows = di.r0 * di.n;
+    sweep_contract_kernel<<<(rows + 127) / 128, 128>>>(md->d_core + di.off_c, md->d_marg + di.off_m, md->d_pk + di.off_p, rows, di.r1);
+    LAUNCHED();
+    if (k > 0) {
+      sweep_integrate_kernel<<<(di.r0 + 127) / 128, 128>>>(md->d_pk + di.off_p, md->d_xs + di.off_x,
+                                                           md->d_marg + md->dims[k - 1].off_m, di.r0, di.n);
+      LAUNCHED();
+    }
+  }
+  stage0_table_kernel<<<1, 32>>>(md->d_pk, md->d_xs, md->d_p0, md->d_cdf0, md->dims[0].n);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  return 0;
+}
+
 static int model_build(ttirt_model *md, const int64_t *n, const double *xs, const int64_t *rk, const double *core) {
   const int64_t d = md->d;
   if (rk[0] != 1 || rk[d] != 1) return fail("ttrank[0] and ttrank[d] must be 1 (got %lld, %lld)", (long long)rk[0], (long long)rk[d]);
@@ -402,29 +430,9 @@ static int model_build(ttirt_model *md, const int64_t *n, const double *xs, cons
   CK(cudaMalloc(&md->d_p0, sizeof(double) * n[0]));
   CK(cudaMalloc(&md->d_cdf0, sizeof(double) * n[0]));
   CK(cudaMalloc(&md->d_dims, sizeof(DimInfo) * d));
-  CK(cudaMemcpy(md->d_xs, xs, sizeof(double) * ox, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(md->d_core, core, sizeof(double) * oc, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(md->d_dims, md->dims.data(), sizeof(DimInfo) * d, cudaMemcpyHostToDevice));
-
-  // right-to-left sweep: C_{d-1} = {1}; P_k = core_k x_3 C_k; C_{k-1} = trapezoid(P_k)
-  const double one = 1.0;
-  CK(cudaMemcpy(md->d_marg + md->dims[d - 1].off_m, &one, sizeof(double), cudaMemcpyHostToDevice));
-  for (int64_t k = d - 1; k >= 0; k--) {
-    const DimInfo &di = md->dims[k];
-    const int rows = di.r0 * di.n;
-    sweep_contract_kernel<<<(rows + 127) / 128, 128>>>(md->d_core + di.off_c, md->d_marg + di.off_m, md->d_pk + di.off_p, rows, di.r1);
-    LAUNCHED();
-    if (k > 0) {
-      sweep_integrate_kernel<<<(di.r0 + 127) / 128, 128>>>(md->d_pk + di.off_p, md->d_xs + di.off_x,
-                                                           md->d_marg + md->dims[k - 1].off_m, di.r0, di.n);
-      LAUNCHED();
-    }
-  }
-  stage0_table_kernel<<<1, 32>>>(md->d_pk, md->d_xs, md->d_p0, md->d_cdf0, md->dims[0].n);
-  LAUNCHED();
-  CK(cudaGetLastError());
-  CK(cudaDeviceSynchronize());
-  return 0;
+  md->sum_x = ox; md->sum_c = oc;
+  return model_load(md, xs, core);
 }
 
 extern "C" ttirt_model *ttirt_model_create(int64_t d, const int64_t *n, const double *xs, const int64_t *ttrank,
@@ -597,11 +605,83 @@ extern "C" int ttirt_sample_host(ttirt_model *md, int64_t M, const double *h_q, 
   return rc;
 }
 
+// ------------------------------------------------------------------------------------------------
+// The drop-in call.  The reference's tt_irt1 keeps no state between calls and neither does this one as far as
+// the caller can tell, but device allocations (the model's buffers and the three pipeline workspaces, ~3.5 GB at
+// the metric shape) are kept per device and reused by the next call of the same shape: MH / IW drivers call the
+// sampler repeatedly on one TT (reference test_shock_absorber_tt.py:138-153).  Cores and grid are uploaded and
+// the sweep is redone on every call, so results never depend on a previous call.  TTIRT_CACHE=0 disables the
+// reuse; ttirt_cache_clear() releases everything.
+// ------------------------------------------------------------------------------------------------
+namespace {
+constexpr int kMaxDevices = 64;
+struct EngineSlot {
+  std::mutex mu;
+  ttirt_model *md = nullptr;
+};
+EngineSlot g_slots[kMaxDevices];
+
+bool cache_enabled() {
+  const char *e = getenv("TTIRT_CACHE");
+  return !(e && atoi(e) == 0);
+}
+
+bool trace_on() {
+  static int v = -1;
+  if (v < 0) v = getenv("TTIRT_TRACE") != nullptr;
+  return v != 0;
+}
+
+double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+bool same_shape(const ttirt_model *md, int64_t d, const int64_t *n, const int64_t *rk) {
+  if (!md || md->d != d) return false;
+  for (int64_t k = 0; k < d; k++) if (md->n[k] != n[k]) return false;
+  for (int64_t k = 0; k <= d; k++) if (md->r[k] != rk[k]) return false;
+  return true;
+}
+
+// rows [m0, m1) of one call on one device, through that device's cached engine
+int run_on_device(int device, int64_t d, const int64_t *n, const double *xs, const int64_t *rk, const double *core,
+                  int64_t m0, int64_t m1, const double *h_q, double *h_z, double *h_lpz, int32_t *h_idx, int64_t ld, int mode) {
+  if (device < 0 || device >= kMaxDevices) return fail("device %d out of range", device);
+  EngineSlot &sl = g_slots[device];
+  std::lock_guard<std::mutex> lock(sl.mu);
+  const double t0 = now_s();
+  if (same_shape(sl.md, d, n, rk)) {
+    if (cudaSetDevice(device) != cudaSuccess) return fail("cudaSetDevice(%d) failed", device);
+    if (model_load(sl.md, xs, core) != 0) { ttirt_model_destroy(sl.md); sl.md = nullptr; return -1; }
+  } else {
+    ttirt_model_destroy(sl.md);
+    sl.md = ttirt_model_create(d, n, xs, rk, core, device);
+    if (!sl.md) return -1;
+  }
+  const double t1 = now_s();
+  const int rc = sample_host_rows(sl.md, m0, m1, h_q, h_z, h_lpz, h_idx, ld, mode);
+  const double t2 = now_s();
+  if (!cache_enabled() || rc != 0) { ttirt_model_destroy(sl.md); sl.md = nullptr; }
+  if (trace_on())
+    fprintf(stderr, "tt_irt1[b200] trace: device %d rows %lld: model %.1f ms, pipeline %.1f ms, release %.1f ms\n", device,
+            (long long)(m1 - m0), 1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (now_s() - t2));
+  return rc;
+}
+}  // namespace
+
+extern "C" void ttirt_cache_clear(void) {
+  for (int g = 0; g < kMaxDevices; g++) {
+    std::lock_guard<std::mutex> lock(g_slots[g].mu);
+    if (g_slots[g].md) { ttirt_model_destroy(g_slots[g].md); g_slots[g].md = nullptr; }
+  }
+}
+
 extern "C" int ttirt_run_host(int64_t d, const int64_t *n, const double *xs, const int64_t *ttrank, const double *ttcore,
                               int64_t M, const double *h_q, double *h_z, double *h_lpz, int32_t *h_idx, int mode,
                               int first_device, int n_devices) {
   g_err[0] = 0;
   if (M < 0) return fail("negative M");
+  if (d < 1 || !n || !xs || !ttrank || !ttcore) return fail("bad arguments to ttirt_run_host");
   const int cnt = ttirt_device_count();
   if (cnt <= 0) return fail("no CUDA device available (this library has no CPU fallback)");
   if (n_devices <= 0 || first_device < 0 || first_device + n_devices > cnt)
@@ -614,13 +694,7 @@ extern "C" int ttirt_run_host(int64_t d, const int64_t *n, const double *xs, con
     const void *q, *z, *l; bool pq, pz, pl;
     ~Unpin() { unpin(q, pq); unpin(z, pz); unpin(l, pl); }
   } unpin_guard{h_q, h_z, h_lpz, pq, pz, pl};
-  if (n_devices == 1) {
-    ttirt_model *md = ttirt_model_create(d, n, xs, ttrank, ttcore, first_device);
-    if (!md) return -1;
-    const int rc = sample_host_rows(md, 0, M, h_q, h_z, h_lpz, h_idx, M, mode);
-    ttirt_model_destroy(md);
-    return rc;
-  }
+  if (n_devices == 1) return run_on_device(first_device, d, n, xs, ttrank, ttcore, 0, M, h_q, h_z, h_lpz, h_idx, M, mode);
   // samples are independent: contiguous row shards, one host thread per device, no collective
   std::vector<int> rcs(n_devices, 0);
   std::vector<std::string> errs(n_devices);
@@ -628,11 +702,8 @@ extern "C" int ttirt_run_host(int64_t d, const int64_t *n, const double *xs, con
   for (int g = 0; g < n_devices; g++) {
     th.emplace_back([&, g]() {
       const int64_t m0 = M * g / n_devices, m1 = M * (g + 1) / n_devices;
-      ttirt_model *md = ttirt_model_create(d, n, xs, ttrank, ttcore, first_device + g);
-      if (!md) { rcs[g] = -1; errs[g] = g_err; return; }
-      rcs[g] = sample_host_rows(md, m0, m1, h_q, h_z, h_lpz, h_idx, M, mode);
+      rcs[g] = run_on_device(first_device + g, d, n, xs, ttrank, ttcore, m0, m1, h_q, h_z, h_lpz, h_idx, M, mode);
       if (rcs[g] != 0) errs[g] = g_err;
-      ttirt_model_destroy(md);
     });
   }
   for (auto &t : th) t.join();

@@ -435,6 +435,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
         }
       }
 
+      PT_MARK(5)
       // ---- inversion tail: lane t = i of a quad finishes row 8i + g ---------------------------------
       {
         const int sel = (MT == 2) ? (t & 1) : 0;
