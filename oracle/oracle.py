@@ -67,7 +67,8 @@ def _dp(a):
 
 def oracle_run(n, xs, ranks, cores, q, rows=None, extras=False):
     """Run the restatement. q is (M, d) (any order; read column-major). Returns Z (M,d) F-order, lPz (M,)
-    and, with extras=True, also idx (M,d) int32, kappa (M,d), gap (M,d), cond (M,d)."""
+    and, with extras=True, also idx (M,d) int32, kappa (M,d), gap (M,d), cond (M,d), lsens (M,d)
+    (cond: sensitivity of x_k to rounding, lsens: |d log p / d x_k|; both feed the parity tolerances)."""
     lib = _load(os.path.join(ORACLE_DIR, "liboracle_tt_irt1.so"))
     q = np.asfortranarray(q, dtype=np.float64)
     M, d = q.shape
@@ -83,6 +84,7 @@ def oracle_run(n, xs, ranks, cores, q, rows=None, extras=False):
     kap = np.zeros((M, d), dtype=np.float64, order="F") if extras else None
     gap = np.zeros((M, d), dtype=np.float64, order="F") if extras else None
     cond = np.zeros((M, d), dtype=np.float64, order="F") if extras else None
+    lsens = np.zeros((M, d), dtype=np.float64, order="F") if extras else None
     m0, m1 = (0, M) if rows is None else rows
     fn = lib.tt_irt1_oracle_rows
     fn.restype = C.c_int
@@ -90,15 +92,15 @@ def oracle_run(n, xs, ranks, cores, q, rows=None, extras=False):
     fn.argtypes = [C.c_longlong, ip, C.POINTER(C.c_double), ip, C.POINTER(C.c_double), C.c_longlong,
                    C.c_longlong, C.c_longlong, C.POINTER(C.c_double), C.POINTER(C.c_double),
                    C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double),
-                   C.POINTER(C.c_double)]
+                   C.POINTER(C.c_double), C.POINTER(C.c_double)]
     rc = fn(d, n64.ctypes.data_as(ip), _dp(xs), r64.ctypes.data_as(ip), _dp(cores), M, m0, m1,
             _dp(q), _dp(Z), _dp(lPz),
             idx.ctypes.data_as(C.POINTER(C.c_int)) if extras else None,
-            _dp(kap) if extras else None, _dp(gap) if extras else None, _dp(cond) if extras else None)
+            _dp(kap) if extras else None, _dp(gap) if extras else None, _dp(cond) if extras else None, _dp(lsens) if extras else None)
     if rc != 0:
         raise RuntimeError("oracle failed")
     if extras:
-        return Z, lPz, idx, kap, gap, cond
+        return Z, lPz, idx, kap, gap, cond, lsens
     return Z, lPz
 
 

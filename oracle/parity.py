@@ -6,12 +6,15 @@ few Z entries when only its BLAS summation order changes (r
 tests/test_oracle.py).  The protocol therefore is, per entry (m, k):
 
     idx   : equal to the oracle's, except where the oracle reports q within `gap_tol` of a CDF node
-    lPz   : |d| <= 1e-12 * max(1, |lPz|)
+    lPz   : |d| <= 1e-12 * max(1, |lPz|) + sum_k lsens_k * CFAC * eps * cumsum_k(cond)
     Z     : |d| <= 1e-12 * max(1, |Z|) + CFAC * eps * cumsum_k(cond)
 
 cond is the oracle's first-order sensitivity of x_k to O(eps) perturbations of (cdf, p) including the
 formula's cancellation factor; the cumulative sum carries an ill-conditioned early coordinate into the
-later ones.  The reference's own OpenBLAS-vs-netlib spread sits below 2 * eps * cumsum(cond) on every
+later ones.  lsens_k = |d log p(x_k) / d x_k| of the interpolated conditional carries the same admitted
+perturbation of x_k into the log-density: an entry whose Z is ill-conditioned has an equally ill-conditioned lPz
+(the reference's own two BLAS builds show lPz differences of 0.4 * |dZ| on such entries, tools/lpz_outlier.py).
+The reference's own OpenBLAS-vs-netlib spread sits below 2 * eps * cumsum(cond) on every
 BASELINE shape (tests/test_oracle.py asserts that), CFAC = 8 leaves a 4x margin.
 """
 import numpy as np
@@ -25,7 +28,16 @@ def z_tolerance(Z_ref, cond):
     return RTOL * np.maximum(1.0, np.abs(Z_ref)) + CFAC * EPS * np.cumsum(cond, axis=1)
 
 
-def compare(Z, lPz, idx, Z_ref, lPz_ref, idx_ref, cond, gap, gap_tol=1e-13):
+def lpz_tolerance(lPz_ref, cond, lsens):
+    tol = RTOL * np.maximum(1.0, np.abs(lPz_ref))
+    if lsens is not None:
+        with np.errstate(invalid="ignore"):
+            extra = np.nansum(np.where(np.isfinite(lsens), lsens, 0.0) * CFAC * EPS * np.cumsum(cond, axis=1), axis=1)
+        tol = tol + extra
+    return tol
+
+
+def compare(Z, lPz, idx, Z_ref, lPz_ref, idx_ref, cond, gap, lsens=None, gap_tol=1e-13):
     """Returns a dict of parity statistics and a list of failure strings (empty = parity holds)."""
     fails = []
     stats = {}
@@ -53,8 +65,11 @@ def compare(Z, lPz, idx, Z_ref, lPz_ref, idx_ref, cond, gap, gap_tol=1e-13):
     fin = np.isfinite(lPz_ref) & ok_rows
     dl = np.abs(lPz - lPz_ref)[fin] / np.maximum(1.0, np.abs(lPz_ref[fin]))
     stats["lpz_max_rel"] = float(dl.max()) if dl.size else 0.0
-    if dl.size and not (dl <= RTOL).all():
-        fails.append("%d lPz entries differ by more than 1e-12 relative (max %.2e)" % (int((dl > RTOL).sum()), dl.max()))
+    ltol = lpz_tolerance(lPz_ref, cond, lsens)[fin]
+    lratio = np.abs(lPz - lPz_ref)[fin] / ltol
+    stats["lpz_max_over_tol"] = float(lratio.max()) if lratio.size else 0.0
+    if lratio.size and not (lratio <= 1.0).all():
+        fails.append("%d lPz entries outside tolerance (max relative difference %.2e, worst ratio %.2f)" % (int((lratio > 1.0).sum()), dl.max(), lratio.max()))
     same_nonfinite = np.array_equal(np.isfinite(lPz_ref), np.isfinite(lPz) | ~ok_rows | ~np.isfinite(lPz_ref))
     if not same_nonfinite:
         fails.append("non-finite lPz pattern differs")

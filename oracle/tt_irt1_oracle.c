@@ -106,7 +106,7 @@ static void model_free(model_t *md) {
 
 /* One sample, all dimensions.  left: r_k left-interface vector (ref row of fkm1). */
 static void walk_sample(const model_t *md, oidx M, oidx m, const double *q, double *z, double *lPz,
-                        int *idx, double *kappa, double *gap, double *cond,
+                        int *idx, double *kappa, double *gap, double *cond, double *lsens,
                         double *left, double *next, double *p, double *cdf, double *slab) {
   double lp = 0.0;
   left[0] = 1.0; /* ref :90, assumes r_0 = 1 */
@@ -180,6 +180,11 @@ static void walk_sample(const model_t *md, oidx M, oidx m, const double *q, doub
       const double xa = fabs(x1) > fabs(x2) ? fabs(x1) : fabs(x2);
       cond[m + M * k] = (1.0 + (c1 > c2 ? c1 : c2) * hq) / pint + kap * xa;
     }
+    if (lsens) {
+      /* |d log p(x_k) / d x_k| of the interpolated conditional: how a perturbation of xk shows up in lPz */
+      const double pint = fabs(p[lo] * w1 + p[lo + 1] * w2);
+      lsens[m + M * k] = pint > 0.0 ? fabs(c2 - c1) / (hq * pint) : INFINITY;
+    }
     /* interface update: slab = w1*core[:,lo,:] + w2*core[:,lo+1,:]; left <- left*slab (ref :167-177) */
     if (k < md->d - 1) {
       for (oidx b = 0; b < rn; b++) {
@@ -205,7 +210,7 @@ static void walk_sample(const model_t *md, oidx M, oidx m, const double *q, doub
    only (M is still the leading dimension), so callers can shard over host threads. */
 int tt_irt1_oracle_rows(oidx d, const oidx *n, const double *xs, const oidx *ttrank, const double *ttcore,
                         oidx M, oidx m_begin, oidx m_end, const double *q, double *z, double *lPz,
-                        int *idx, double *kappa, double *gap, double *cond) {
+                        int *idx, double *kappa, double *gap, double *cond, double *lsens) {
   model_t md; memset(&md, 0, sizeof(md));
   md.d = d; md.n = n; md.r = ttrank; md.xs = xs; md.core = ttcore;
   if (d < 1 || model_build(&md) != 0) { model_free(&md); return -1; }
@@ -214,15 +219,15 @@ int tt_irt1_oracle_rows(oidx d, const oidx *n, const double *xs, const oidx *ttr
   double *p = (double *)malloc(sizeof(double) * nm), *cdf = (double *)malloc(sizeof(double) * nm);
   double *slab = (double *)malloc(sizeof(double) * rm * rm);
   for (oidx m = m_begin; m < m_end; m++)
-    walk_sample(&md, M, m, q, z, lPz, idx, kappa, gap, cond, left, next, p, cdf, slab);
+    walk_sample(&md, M, m, q, z, lPz, idx, kappa, gap, cond, lsens, left, next, p, cdf, slab);
   free(left); free(next); free(p); free(cdf); free(slab);
   model_free(&md);
   return 0;
 }
 
 int tt_irt1_oracle(oidx d, const oidx *n, const double *xs, const oidx *ttrank, const double *ttcore,
-                   oidx M, const double *q, double *z, double *lPz, int *idx, double *kappa, double *gap, double *cond) {
-  return tt_irt1_oracle_rows(d, n, xs, ttrank, ttcore, M, 0, M, q, z, lPz, idx, kappa, gap, cond);
+                   oidx M, const double *q, double *z, double *lPz, int *idx, double *kappa, double *gap, double *cond, double *lsens) {
+  return tt_irt1_oracle_rows(d, n, xs, ttrank, ttcore, M, 0, M, q, z, lPz, idx, kappa, gap, cond, lsens);
 }
 
 /* The right marginals and core*marginal products alone (checks the device sweep). */

@@ -4,7 +4,8 @@ golden outputs of the unmodified reference.
 Bars (DESIGN.md "Parity", oracle/parity.py):
   strict mode : Z and interval indices BIT-EXACT against the oracle; lPz to 1e-14 relative (device log vs glibc log)
   fast mode   : interval indices bit-exact (flips only admissible where q sits on a CDF node to 1e-13),
-                lPz within 1e-12 relative, Z within 1e-12 relative + 8 eps cumsum(cond) entry by entry
+                Z within 1e-12 relative + 8 eps cumsum(cond) entry by entry, lPz within 1e-12 relative + the same
+                admitted Z perturbation carried through the density slope (oracle/parity.py)
   full sizes  : size-independent properties (row-subset invariance against the oracle, shard invariance,
                 monotonicity in q, Z inside its grid interval, determinism)
 """
@@ -54,7 +55,7 @@ SHAPES = [
 def test_strict_is_bitexact_and_fast_within_protocol(oracle_mod, d, n, r, M, cores, grid):
     ns, xs, rk, c = synth.make_tt(d, n, r, seed=100 + d + n + r, cores=cores, grid=grid)
     q = synth.make_q(M, d, seed=7)
-    Zo, lo, io, kap, gap, cond = _oracle(oracle_mod, ns, xs, rk, c, q)
+    Zo, lo, io, kap, gap, cond, lsens = _oracle(oracle_mod, ns, xs, rk, c, q)
     md = tt_irt.Model(ns, xs, rk, c)
     try:
         P, Mg = md.sweep()
@@ -68,7 +69,7 @@ def test_strict_is_bitexact_and_fast_within_protocol(oracle_mod, d, n, r, M, cor
         assert np.array_equal(Zs, Zo)
         np.testing.assert_allclose(ls, lo, rtol=1e-14, atol=1e-14)
         Zf, lf, ifx = md.sample(q, mode=tt_irt.MODE_FAST, want_idx=True)
-        stats, fails = oracle_mod.parity.compare(Zf, lf, ifx, Zo, lo, io, cond, gap)
+        stats, fails = oracle_mod.parity.compare(Zf, lf, ifx, Zo, lo, io, cond, gap, lsens=lsens)
         assert not fails, (fails, stats)
         assert stats["idx_flips"] == 0, stats
     finally:
@@ -82,13 +83,13 @@ def test_ragged_modes_and_ranks(oracle_mod):
     xs = np.concatenate([np.sort(rng.random(n)) for n in ns])
     c = rng.random(int((rk[:-1] * ns * rk[1:]).sum()))
     q = synth.make_q(2000, 6, seed=3)
-    Zo, lo, io, kap, gap, cond = _oracle(oracle_mod, ns, xs, rk, c, q)
+    Zo, lo, io, kap, gap, cond, lsens = _oracle(oracle_mod, ns, xs, rk, c, q)
     md = tt_irt.Model(ns, xs, rk, c)
     try:
         Zs, ls, isx = md.sample(q, mode=tt_irt.MODE_STRICT, want_idx=True)
         assert np.array_equal(Zs, Zo) and np.array_equal(isx, io)
         Zf, lf, ifx = md.sample(q, mode=tt_irt.MODE_FAST, want_idx=True)
-        stats, fails = oracle_mod.parity.compare(Zf, lf, ifx, Zo, lo, io, cond, gap)
+        stats, fails = oracle_mod.parity.compare(Zf, lf, ifx, Zo, lo, io, cond, gap, lsens=lsens)
         assert not fails, (fails, stats)
     finally:
         md.close()
@@ -129,8 +130,8 @@ def test_against_golden_reference_outputs(oracle_mod, golden_dir, name):
             spread = np.abs(g["Z_shim"] - g["Z_openblas"]).max() if "Z_openblas" in g else 1e-9
             assert np.abs(Z - g["Z_shim"]).max() <= max(20 * spread, 1e-11)
         else:
-            Zo, lo, io, kap, gap, cond = _oracle(oracle_mod, ns, xs, rk, c, q)
-            stats, fails = oracle_mod.parity.compare(Z, l, None, g["Z_shim"], g["lPz_shim"], None, cond, gap)
+            Zo, lo, io, kap, gap, cond, lsens = _oracle(oracle_mod, ns, xs, rk, c, q)
+            stats, fails = oracle_mod.parity.compare(Z, l, None, g["Z_shim"], g["lPz_shim"], None, cond, gap, lsens=lsens)
             assert not fails, (fails, stats)
 
 
@@ -144,8 +145,8 @@ def test_python_wrapper_matches_reference_call_shape(oracle_mod):
     f = tt_irt.TTTensor(ns, rk, c)
     Z, lPz = tt_irt.tt_irt1(q, f, xs.reshape(-1, 1))
     assert Z.shape == (M, d) and Z.flags.f_contiguous and lPz.shape == (M,)
-    Zo, lo, io, kap, gap, cond = _oracle(oracle_mod, ns, xs, rk, c, q)
-    stats, fails = oracle_mod.parity.compare(Z, lPz, None, Zo, lo, None, cond, gap)
+    Zo, lo, io, kap, gap, cond, lsens = _oracle(oracle_mod, ns, xs, rk, c, q)
+    stats, fails = oracle_mod.parity.compare(Z, lPz, None, Zo, lo, None, cond, gap, lsens=lsens)
     assert not fails, (fails, stats)
 
 
@@ -175,7 +176,7 @@ def test_kat_zero_mass_fallback_and_sign_flip(oracle_mod):
     c = np.zeros(5 * 2 + 2 * 4)
     c[:10] = 1.0                      # first core positive, second core zero: zero-mass conditional in dim 1
     q = synth.make_q(400, 2, seed=2)
-    Zo, lo, io, _, gap, cond = _oracle(oracle_mod, ns, xs, rk, c, q)
+    Zo, lo, io, _, gap, cond, lsens = _oracle(oracle_mod, ns, xs, rk, c, q)
     for mode in (tt_irt.MODE_FAST, tt_irt.MODE_STRICT):
         md = tt_irt.Model(ns, xs, rk, c)
         Z, l, idx = md.sample(q, mode=mode, want_idx=True)
@@ -193,7 +194,7 @@ def test_kat_zero_mass_fallback_and_sign_flip(oracle_mod):
 def test_edge_seeds_and_empty_and_tiny_batches(oracle_mod):
     ns, xs, rk, c = synth.make_tt(3, 9, 4, seed=8)
     q = np.asfortranarray(np.array([[0.0, 0.0, 0.0], [1.0, 1.0, 1.0], [0.0, 1.0, 0.5]]))
-    Zo, lo, io, _, gap, cond = _oracle(oracle_mod, ns, xs, rk, c, q)
+    Zo, lo, io, _, gap, cond, lsens = _oracle(oracle_mod, ns, xs, rk, c, q)
     md = tt_irt.Model(ns, xs, rk, c)
     try:
         for mode in (tt_irt.MODE_FAST, tt_irt.MODE_STRICT):
@@ -204,9 +205,9 @@ def test_edge_seeds_and_empty_and_tiny_batches(oracle_mod):
         assert Z.shape == (0, 3) and l.shape == (0,)
         for M in (1, 15, 16, 17, 127, 129):      # ragged against the 16-row warp tile and 128-row CTA tile
             qq = synth.make_q(M, 3, seed=M)
-            Zr, lr, ir, _, gp, cd = _oracle(oracle_mod, ns, xs, rk, c, qq)
+            Zr, lr, ir, _, gp, cd, ls = _oracle(oracle_mod, ns, xs, rk, c, qq)
             Z, l, idx = md.sample(qq, want_idx=True)
-            stats, fails = oracle_mod.parity.compare(Z, l, idx, Zr, lr, ir, cd, gp)
+            stats, fails = oracle_mod.parity.compare(Z, l, idx, Zr, lr, ir, cd, gp, lsens=ls)
             assert not fails, (M, fails)
     finally:
         md.close()
@@ -238,8 +239,8 @@ def test_full_size_rows_subset_and_shards(oracle_mod):
     lo_edge = np.take_along_axis(x.T, idx, axis=0); hi_edge = np.take_along_axis(x.T, idx + 1, axis=0)
     assert (Z >= lo_edge - 1e-9).all() and (Z <= hi_edge + 1e-9).all()
     rows = np.concatenate([np.arange(0, 192), np.arange((1 << 18) - 64, (1 << 18) + 64), np.arange(M - 128, M)])
-    Zo, lo, io, kap, gap, cond = _oracle(oracle_mod, ns, xs, rk, c, q[rows])
-    stats, fails = oracle_mod.parity.compare(Z[rows], l[rows], idx[rows], Zo, lo, io, cond, gap)
+    Zo, lo, io, kap, gap, cond, lsens = _oracle(oracle_mod, ns, xs, rk, c, q[rows])
+    stats, fails = oracle_mod.parity.compare(Z[rows], l[rows], idx[rows], Zo, lo, io, cond, gap, lsens=lsens)
     assert not fails, (fails, stats)
     # a different chunking / a second call: bitwise identical (no order-dependent arithmetic)
     md = tt_irt.Model(ns, xs, rk, c)
@@ -270,8 +271,8 @@ def test_monotone_in_first_coordinate_and_int64_abi(oracle_mod):
     order = np.argsort(q[:, 0], kind="stable")
     assert (np.diff(Z[order, 0]) >= 0).all()
     rows = np.arange(0, 256)
-    Zo, lo, io, kap, gap, cond = _oracle(oracle_mod, ns, xs, rk, c, q[rows])
-    stats, fails = oracle_mod.parity.compare(Z[rows], l[rows], None, Zo, lo, None, cond, gap)
+    Zo, lo, io, kap, gap, cond, lsens = _oracle(oracle_mod, ns, xs, rk, c, q[rows])
+    stats, fails = oracle_mod.parity.compare(Z[rows], l[rows], None, Zo, lo, None, cond, gap, lsens=lsens)
     assert not fails, (fails, stats)
 
 

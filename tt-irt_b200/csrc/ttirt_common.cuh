@@ -43,25 +43,71 @@ __device__ __forceinline__ CellOut invert_cell(double qk, double cdf_lo, double 
   return o;
 }
 
-// Fast-path variant: the four divisions by the cell width h = x2 - x1 become multiplications by a tabulated
-// 1/h (one rounding each, same size as the rounding the reference's own divisions commit); the division by
-// Aq, the square root and the logarithm stay.  Cuts the dependent FP64 chain of the tail roughly in half.
-__device__ __forceinline__ CellOut invert_cell_fast(double qk, double cdf_lo, double c1, double c2, double x1, double x2, double ih) {
-  CellOut o;
+// Fast-path variant.  It works on the conditional scaled by an exact power of two instead of normalised by its
+// mass (the root x_k and the weights are invariant under a common scaling of c1, c2 and q - cdf_lo), so no
+// reciprocal of the mass is needed.  The four divisions by the cell width h = x2 - x1 become multiplications by a
+// tabulated 1/h and the division by Aq a multiplication by its reciprocal, which is taken as soon as Aq exists and
+// so leaves the dependent chain (one extra rounding each, the size of the roundings the reference's own
+// divisions commit).  The logarithm is not taken here: the tail returns the interpolated (scaled) conditional
+// density and the caller keeps the running product in the split form of lp_accumulate().
+//   dq = q * mass - cdf_lo  (scaled),  c1, c2 = |pdf| at the cell's nodes (scaled)
+#ifndef TTIRT_XK_DIV
+#define TTIRT_XK_DIV 0
+#endif
+struct CellFast {
+  double xk, w1, w2, dens;
+};
+__device__ __forceinline__ CellFast invert_cell_fast(double dq, double c1, double c2, double x1, double x2, double ih) {
+  CellFast o;
   const double Aq = __dmul_rn(__dmul_rn(0.5, __dsub_rn(c2, c1)), ih);
+  const double rA = __drcp_rn(Aq);
   const double Bq = __dmul_rn(__dsub_rn(__dmul_rn(c1, x2), __dmul_rn(c2, x1)), ih);
   double Dq = __dadd_rn(__dmul_rn(__dmul_rn(2.0, Aq), x1), Bq);
   Dq = __dmul_rn(Dq, Dq);
-  const double dq = __dsub_rn(qk, cdf_lo);
   Dq = __dadd_rn(Dq, __dmul_rn(__dmul_rn(4.0, Aq), dq));
   const double root = __dsqrt_rn(fabs(Dq));
-  double xk = __ddiv_rn(__dmul_rn(0.5, __dadd_rn(-Bq, root)), Aq);
+  double xk = TTIRT_XK_DIV ? __ddiv_rn(__dmul_rn(0.5, __dadd_rn(-Bq, root)), Aq) : __dmul_rn(__dmul_rn(0.5, __dadd_rn(-Bq, root)), rA);
   if (Aq == 0.0) xk = __dadd_rn(x1, __ddiv_rn(dq, Bq));
   o.xk = xk;
   o.w1 = __dmul_rn(__dsub_rn(x2, xk), ih);
   o.w2 = __dmul_rn(__dsub_rn(xk, x1), ih);
-  o.logp = log(fabs(__dadd_rn(__dmul_rn(c1, o.w1), __dmul_rn(c2, o.w2))));
+  o.dens = fabs(__dadd_rn(__dmul_rn(c1, o.w1), __dmul_rn(c2, o.w2)));
   return o;
+}
+
+// Running log-density of the fast path: lPz = sum_k log(dens_k / mass_k) (reference tt_irt1_int32.c:116-130,
+// 161-165) is carried as two running products in split form, Pn * 2^E over the densities and Pd over the masses,
+// both mantissas in [1, 2), and the one logarithm is taken after the last dimension.  Zero, infinite and NaN
+// products stay as they are and give -inf / inf / NaN as a sum of logarithms would.
+__device__ __forceinline__ int split_exponent(double &P) {
+  int e = 0;
+  int hi = __double2hiint(P);
+  int ex = (hi >> 20) & 0x7ff;
+  if (ex == 0 && P != 0.0) {  // subnormal: rescale before splitting
+    P = __dmul_rn(P, 18014398509481984.0);  // 2^54
+    e = -54;
+    hi = __double2hiint(P);
+    ex = (hi >> 20) & 0x7ff;
+  }
+  if (ex != 0 && ex != 0x7ff) {
+    e += ex - 1023;
+    P = __hiloint2double((hi & 0x800fffff) | 0x3ff00000, __double2loint(P));
+  }
+  return e;
+}
+__device__ __forceinline__ void lp_accumulate(double &Pn, double &Pd, int &E, double dens, double mass) {
+  Pn = __dmul_rn(Pn, dens);
+  E += split_exponent(Pn);
+  Pd = __dmul_rn(Pd, mass);
+  E -= split_exponent(Pd);
+}
+__device__ __forceinline__ double lp_finish(double Pn, double Pd, int E) {
+  return fma((double)E, 0.6931471805599453094, log(__ddiv_rn(Pn, Pd)));
+}
+// 2^-e(x) for a positive normal x (1.0 otherwise): scaling by it is exact
+__device__ __forceinline__ double pow2_scale(double x) {
+  const int ex = (__double2hiint(x) >> 20) & 0x7ff;
+  return (ex != 0 && ex != 0x7ff) ? __hiloint2double((2046 - ex) << 20, 0) : 1.0;
 }
 
 // Arguments of one fused "transition" launch of the fast path: interface update through dimension k
@@ -80,7 +126,9 @@ struct TransArgs {
   const int *bin_tile_start; // n0 entries (+1), prefix of ceil(count / rows per CTA tile)
   int *idx;                  // per sample: interval index (out: dimension k+1)
   double *w1, *w2;           // per sample: interpolation weights (in: dimension k, out: k+1)
-  double *lp;                // per sample: running log-density
+  double *lp;                // per sample: running product of the scaled densities, mantissa (see lp_accumulate)
+  double *lpd;               // per sample: running product of the scaled masses, mantissa
+  int *lpe;                  // per sample: exponent of the ratio of the two products
   const double *q;           // column k+1 of q for this chunk
   double *z;                 // column k+1 of z
   int32_t *idx_out;          // column k+1 of the exported index array (may be NULL)

@@ -80,7 +80,8 @@ struct Workspace {
   bool strict = false, host = false, want_idx = false;
   double *F = nullptr;   // cap x ldf
   int *idx = nullptr, *perm = nullptr;
-  double *w1 = nullptr, *w2 = nullptr, *lp = nullptr;
+  double *w1 = nullptr, *w2 = nullptr, *lp = nullptr, *lpd = nullptr;
+  int *lpe = nullptr;
   int *hist = nullptr;   // d x nbpad
   int *bin_start = nullptr, *bin_tile_start = nullptr, *cursor = nullptr;
   // strict scratch
@@ -112,7 +113,7 @@ struct ttirt_model {
 };
 
 static void ws_free(Workspace &w) {
-  cudaFree(w.F); cudaFree(w.idx); cudaFree(w.perm); cudaFree(w.w1); cudaFree(w.w2); cudaFree(w.lp);
+  cudaFree(w.F); cudaFree(w.idx); cudaFree(w.perm); cudaFree(w.w1); cudaFree(w.w2); cudaFree(w.lp); cudaFree(w.lpd); cudaFree(w.lpe);
   cudaFree(w.hist); cudaFree(w.bin_start); cudaFree(w.bin_tile_start); cudaFree(w.cursor);
   cudaFree(w.left); cudaFree(w.pbuf); cudaFree(w.cbuf);
   cudaFree(w.q); cudaFree(w.z); cudaFree(w.lpz); cudaFree(w.idx_out);
@@ -137,6 +138,8 @@ static int ws_ensure(ttirt_model *md, Workspace &w, int64_t rows, bool strict, b
   CK(cudaMalloc(&w.w1, sizeof(double) * cap));
   CK(cudaMalloc(&w.w2, sizeof(double) * cap));
   CK(cudaMalloc(&w.lp, sizeof(double) * cap));
+  CK(cudaMalloc(&w.lpd, sizeof(double) * cap));
+  CK(cudaMalloc(&w.lpe, sizeof(int) * cap));
   CK(cudaMalloc(&w.hist, sizeof(int) * d * md->nbpad));
   CK(cudaMalloc(&w.bin_start, sizeof(int) * (md->nbpad + 1)));
   CK(cudaMalloc(&w.bin_tile_start, sizeof(int) * (md->nbpad + 1)));
@@ -274,7 +277,7 @@ __global__ void strict_kernel(const DimInfo *__restrict__ dims, int d, const dou
 // ------------------------------------------------------------------------------------------------
 __global__ void stage0_kernel(const double *__restrict__ p0, const double *__restrict__ cdf0, const double *__restrict__ x,
                               int n0, int rows, const double *__restrict__ q, double *z, int32_t *idx_out, int *idx,
-                              double *w1, double *w2, double *lp, double *lpz, double *F, int ldf, int *hist, int last) {
+                              double *w1, double *w2, double *lp, double *lpd, int *lpe, double *lpz, double *F, int ldf, int *hist, int last) {
   extern __shared__ double sm[];
   double *sp = sm, *sc = sm + n0, *sx = sm + 2 * n0;
   int *sh = reinterpret_cast<int *>(sm + 3 * n0);
@@ -291,7 +294,11 @@ __global__ void stage0_kernel(const double *__restrict__ p0, const double *__res
     if (last) {
       lpz[m] = l0;
     } else {
-      idx[m] = lo; w1[m] = o.w1; w2[m] = o.w2; lp[m] = l0;
+      idx[m] = lo; w1[m] = o.w1; w2[m] = o.w2;
+      double Pn = 1.0, Pd = 1.0;
+      int E = 0;
+      lp_accumulate(Pn, Pd, E, fabs(__dadd_rn(__dmul_rn(sp[lo], o.w1), __dmul_rn(sp[lo + 1], o.w2))), 1.0);  // sp is normalised
+      lp[m] = Pn; lpd[m] = Pd; lpe[m] = E;
       double2 *f = reinterpret_cast<double2 *>(F + (size_t)m * ldf);
       f[0] = make_double2(1.0, 0.0); f[1] = make_double2(0.0, 0.0);
       f[2] = make_double2(0.0, 0.0); f[3] = make_double2(0.0, 0.0);
@@ -478,7 +485,7 @@ static int run_chunk(ttirt_model *md, Workspace &w, int64_t rows, const double *
     const DimInfo &d0 = md->dims[0];
     const size_t sm = sizeof(double) * 3 * d0.n + sizeof(int) * d0.n;
     stage0_kernel<<<(unsigned)((rows + 255) / 256), 256, sm, st>>>(md->d_p0, md->d_cdf0, md->d_xs + d0.off_x, d0.n, (int)rows, q, z,
-                                                                   idx_out, w.idx, w.w1, w.w2, w.lp, lpz, w.F, md->ldf, w.hist, d == 1);
+                                                                   idx_out, w.idx, w.w1, w.w2, w.lp, w.lpd, w.lpe, lpz, w.F, md->ldf, w.hist, d == 1);
     LAUNCHED();
     CK(cudaGetLastError());
   }
@@ -494,7 +501,7 @@ static int run_chunk(ttirt_model *md, Workspace &w, int64_t rows, const double *
     a.r0 = dk.r0; a.n0 = dk.n; a.r1 = dk.r1; a.n1 = dn.n;
     a.last = (k + 1 == d - 1); a.rows = (int)rows; a.F = w.F; a.ldf = md->ldf;
     a.perm = w.perm; a.bin_start = w.bin_start; a.bin_tile_start = w.bin_tile_start;
-    a.idx = w.idx; a.w1 = w.w1; a.w2 = w.w2; a.lp = w.lp;
+    a.idx = w.idx; a.w1 = w.w1; a.w2 = w.w2; a.lp = w.lp; a.lpd = w.lpd; a.lpe = w.lpe;
     a.q = q + ldq * (k + 1); a.z = z + ldz * (k + 1);
     a.idx_out = idx_out ? idx_out + ldz * (k + 1) : nullptr;
     a.lpz = lpz; a.hist_next = w.hist + (size_t)(k + 1) * nbpad;

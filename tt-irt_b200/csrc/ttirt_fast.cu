@@ -18,13 +18,6 @@
 // with each other except when their CTA moves to the next interval bin and restages a slab.
 #include "ttirt_common.cuh"
 
-#ifndef TTIRT_WARPS
-#define TTIRT_WARPS 8    // warps per CTA (one CTA per SM)
-#endif
-#ifndef TTIRT_MT
-#define TTIRT_MT 2       // 8-row MMA tiles per warp
-#endif
-
 namespace ttirt {
 
 #ifdef TTIRT_PHASE_TIMING
@@ -77,67 +70,93 @@ __device__ void stage_b(double *dst, const double *__restrict__ src, int K, int 
   }
 }
 
-template <int RT, int NT, int WARPS, int MT>
+constexpr int MMA_WARPS = 8;    // two per SM sub-partition: they share the FP64 tensor pipe
+constexpr int TAIL_WARPS = 4;   // one per SM sub-partition: CDF, search, inversion of the tiles its two MMA warps produce
+constexpr int MT = 2;           // 8-row MMA tiles per MMA warp
+constexpr int WROWS = 8 * MT;   // samples per warp tile
+constexpr int NTHR = 32 * (MMA_WARPS + TAIL_WARPS);
+constexpr int ROWS_CTA = MMA_WARPS * WROWS;
+// register file split (setmaxnreg, per warpgroup of four warps): launched at 168 per thread, the tail warpgroup
+// shrinks to TAIL_REGS and the two MMA warpgroups grow to MMA_REGS; 32 * (8 * 192 + 4 * 120) = 32 * 12 * 168: the pool is exactly what the launch allocated
+constexpr int MMA_REGS = 192, TAIL_REGS = 120;
+
+template <int RT, int NT, bool TAIL1>
 struct SmemLayout {
   static constexpr int KPMAX = (8 * RT + 15) & ~15;
   static constexpr int SLAB = 8 * RT * KPMAX;      // doubles per slab buffer
   static constexpr int PN = 8 * NT * KPMAX;        // doubles for P_{k+1}
   static constexpr int NBMAX = 8 * NT;             // >= n - 1 intervals
   static constexpr int FPITCH = 8 * RT + 8;        // doubles per staged left-interface row (+64 B: rows g, g+1 hit different bank halves)
-  static constexpr int FTILE = 8 * MT * FPITCH;    // doubles per warp
-  static constexpr size_t bytes = sizeof(double) * (2 * SLAB + PN + 3 * 8 * NT + WARPS * FTILE) +
-                                  sizeof(int) * (2 * (NBMAX + 1) + NBMAX);
+  static constexpr int FTILE = WROWS * FPITCH;     // doubles of staged rows per MMA warp
+  // parked |pdf| tile of one warp tile, [node][row]: pitch 18 makes the MMA warps' fragment stores (rows g, nodes 2t)
+  // and the tail warp's row-per-lane reads both bank-conflict free
+  static constexpr int NPD = TAIL1 ? 8 * (NT - 1) + 1 : 8 * NT;
+  static constexpr int RS = WROWS + 2;
+  static constexpr int PB = NPD * RS;
+  static constexpr int HS = TAIL1 ? 4 * (NT - 1) : 4 * NT;   // cells walked by each of the two lanes of a row
+  static constexpr int HB = HS / 4;                // ... as four blocks of HB consecutive cells, walked side by side
+  static constexpr int NHH = 2 * HS + 8;           // half cell widths, zero beyond cell n1-2
+  static constexpr size_t bytes = sizeof(double) * (2 * SLAB + PN + MMA_WARPS * FTILE + TAIL_WARPS * PB + NHH + 2 * 8 * NT) +
+                                  sizeof(int) * (2 * (NBMAX + 1) + NBMAX + TAIL_WARPS * (WROWS + 1));
 };
+
+// Named barriers (id 0 is __syncthreads).  Tile hand-over between an MMA warp and its tail warp is a 64-thread
+// barrier on which one side only arrives: shared-memory ordering without a memory fence, which would also wait
+// for the F' stores and the row gather still in flight.
+//   1                 the eight MMA warps (slab restaging at a bin change)
+//   2 + tw            FULL : a producer of buffer tw arrives after parking a tile, tail warp tw waits
+//   6 + 4*p + tw      EMPTY: tail warp tw arrives when producer p (0 / 1) may overwrite the buffer, producer p waits
+__device__ __forceinline__ void bar_mma_warps() { asm volatile("bar.sync 1, %0;" ::"n"(32 * MMA_WARPS) : "memory"); }
+__device__ __forceinline__ void bar_pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void bar_pair_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 
 // EXACT: r0 == r1 == 8*RT and ceil(n1/8) == NT, so every tile loop runs its full static trip count and no
 // guard branches are compiled in (the steady state of a uniform-rank TT).  TAIL1 (EXACT only): n1 == 8*(NT-1)+1,
 // the usual 2^p+1 grid; the lone last grid column is then a 4-lane DFMA dot product instead of a whole DMMA
 // column tile that would be 7/8 padding.
 //
-// MT: 8-row MMA tiles per warp.  A warp owns 8*MT samples end to end.  MT = 1 with 16 warps (128 registers per
-// thread) puts four warps on every SM sub-partition: while one warp walks the latency-bound CDF / inversion
-// phase three others feed the DMMA pipe.  MT = 2 with 8 warps halves the B-operand shared-memory traffic per
-// DMMA but leaves only two warps per sub-partition.
+// Warp roles.  On B200 the scalar FP64 instructions of the CDF / inversion phase go through the same pipe as DMMA:
+// while a warp walks that dependent chain its DMMA stream stops, and a partner warp streaming DMMAs stretches the
+// chain ~3x.  So the chain is taken off the MMA warps altogether.  Eight MMA warps (two per SM sub-partition) do
+// nothing but gather -> interface update -> pdf contraction and park the |pdf| tile (16 rows x n1 nodes) in shared
+// memory; four tail warps (one per sub-partition) turn parked tiles into samples.  Each tail warp owns one tile
+// buffer that its two MMA warps fill in strict alternation; hand-over is by named barriers (below).
 //
-// Row gather: the left-interface rows of a warp's NEXT tile are fetched asynchronously (cp.async / LDGSTS, one
+// Row gather: the left-interface rows of an MMA warp's NEXT tile are fetched asynchronously (cp.async / LDGSTS, one
 // coalesced 8*r0-byte row per instruction) into a per-warp shared tile as soon as the current tile's update
-// phase has consumed that tile, i.e. a whole pdf + inversion phase ahead of use.  The dependent perm -> row
-// latency (two DRAM round trips) therefore never sits in front of the DMMA stream.
-template <int RT, int NT, int WARPS, int MT, bool EXACT, bool TAIL1>
-__global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransArgs a) {
+// phase has consumed that tile, i.e. a whole pdf phase ahead of use.
+template <int RT, int NT, bool EXACT, bool TAIL1>
+__global__ void __launch_bounds__(NTHR, 1) transition_kernel(const TransArgs a) {
   static_assert(EXACT || !TAIL1, "TAIL1 needs EXACT");
-  static_assert(MT == 1 || MT == 2, "one or two 8-row tiles per warp");
-  using L = SmemLayout<RT, NT, WARPS, MT>;
+  using L = SmemLayout<RT, NT, TAIL1>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *slab0 = reinterpret_cast<double *>(smem_raw);
   double *slab1 = slab0 + L::SLAB;
   double *Ps = slab1 + L::SLAB;
-  double *ft_all = Ps + L::PN;       // per-warp staged left-interface rows
-  double *hh = ft_all + WARPS * L::FTILE;  // half grid steps of dimension k+1, zero beyond n1-2
-  double *xg = hh + 8 * NT;          // grid of dimension k+1
-  double *ihs = xg + 8 * NT;         // reciprocal cell widths of dimension k+1
+  double *ft_all = Ps + L::PN;                     // per-MMA-warp staged left-interface rows
+  double *pb_all = ft_all + MMA_WARPS * L::FTILE;  // per-tail-warp parked |pdf| tile
+  double *hh = pb_all + TAIL_WARPS * L::PB;        // half grid steps of dimension k+1, zero beyond cell n1-2
+  double *xg = hh + L::NHH;                        // grid of dimension k+1
+  double *ihs = xg + 8 * NT;                       // reciprocal cell widths of dimension k+1
   int *bts = reinterpret_cast<int *>(ihs + 8 * NT);  // bin -> first CTA tile
   int *bst = bts + (L::NBMAX + 1);                    // bin -> first sorted row
   int *hist = bst + (L::NBMAX + 1);                   // histogram of the intervals chosen in dimension k+1
+  int *ids_all = hist + L::NBMAX;                     // per tail warp: sample ids of the parked tile
+  int *nv_all = ids_all + TAIL_WARPS * WROWS;         // per tail warp: valid rows of the parked tile
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = lane >> 2, t = lane & 3;
-  constexpr int NTHR = WARPS * 32, WROWS = 8 * MT, ROWS_CTA = WARPS * WROWS;
-  constexpr int FP = L::FPITCH;
-  double *ft = ft_all + warp * L::FTILE;
+  constexpr int FP = L::FPITCH, RS = L::RS;
 
   const int r0 = a.r0, r1 = a.r1, n1 = a.n1, nb0 = a.n0 - 1;
   constexpr int KP = L::KPMAX;                   // compile-time column pitch: B-fragment offsets fold into immediates
   constexpr int NTD = TAIL1 ? NT - 1 : NT;       // grid column tiles computed by DMMA
-  const int ks0 = EXACT ? RT : (r0 + 7) >> 3, rt_act = EXACT ? RT : (r1 + 7) >> 3, nt_act = EXACT ? NT : (n1 + 7) >> 3;
-  const uint32_t row_bytes = (uint32_t)(8 * ks0) * 8u;   // bytes of a left-interface row that the update reads
 
   for (int i = tid; i <= nb0; i += NTHR) {
     bts[i] = a.bin_tile_start[i];
     bst[i] = a.bin_start[i];
   }
+  for (int i = tid; i < L::NHH; i += NTHR) hh[i] = (i + 1 < n1) ? 0.5 * (a.xnext[i + 1] - a.xnext[i]) : 0.0;
   for (int i = tid; i < 8 * NT; i += NTHR) {
-    hh[i] = (i + 1 < n1) ? 0.5 * (a.xnext[i + 1] - a.xnext[i]) : 0.0;
     xg[i] = (i < n1) ? a.xnext[i] : 0.0;
     ihs[i] = (i + 1 < n1) ? 1.0 / (a.xnext[i + 1] - a.xnext[i]) : 0.0;
     if (i < L::NBMAX) hist[i] = 0;
@@ -148,324 +167,341 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
   const int total_tiles = bts[nb0];
   const int t_begin = (int)(((int64_t)blockIdx.x * total_tiles) / gridDim.x);
   const int t_end = (int)(((int64_t)(blockIdx.x + 1) * total_tiles) / gridDim.x);
-  const int64_t slab_cs = (int64_t)r0 * a.n0;
 
-  int cur0 = -1, cur1 = -1;  // interval slab held by slab0 / slab1
-  int b = 0;                 // bin of the current tile
-  int bh = 0;                // bin hint of the row look-ahead (monotone)
-  const double *sl_lo = slab0, *sl_hi = slab1;
-
-  // rows of this warp in CTA tile `tile`: first sorted row and number of valid rows (0 past the end)
-  auto rows_of = [&](int tile, int &nv) -> int {
-    if (tile >= t_end) { nv = 0; return 0; }
-    while (tile >= bts[bh + 1]) ++bh;
-    const int row0 = bst[bh] + (tile - bts[bh]) * ROWS_CTA + warp * WROWS;
-    nv = max(0, min(WROWS, bst[bh + 1] - row0));
-    return row0;
-  };
-  // sample ids of a tile: lane l holds the id of row l % WROWS; rows past nv repeat row 0
-  auto load_ids = [&](int row0, int nv) -> int {
-    const int r = lane & (WROWS - 1);
-    return nv > 0 ? a.perm[row0 + (r < nv ? r : 0)] : 0;
-  };
-
-  int nvC = 0, nvN = 0;      // valid rows: current tile / next tile
-  int idN = 0;               // row ids (lane-distributed) of the next tile
-  // Gather of the rows whose ids are `ids` into this warp's shared tile: one cp.async (LDGSTS) instruction per row,
-  // 16 bytes per lane, so a row is one coalesced 8*r0-byte segment.  (Sixteen single-row cp.async.bulk copies per
-  // tile were measured at ~1000 cycles of issue time per tile; this costs ~150.)
-  auto issue_gather = [&](int ids, int nv) {
-    if (nv > 0) {
-#pragma unroll
-      for (int r = 0; r < WROWS; r++) {
-        const int id = __shfl_sync(FULL, ids, r);
-        if (16u * lane < row_bytes)
-          cp_async16(reinterpret_cast<char *>(ft + r * FP) + 16 * lane, reinterpret_cast<const char *>(a.F + (size_t)id * a.ldf) + 16 * lane);
+  if (warp >= MMA_WARPS) {
+    // =========================================== tail warps ===========================================
+    // Lanes l and l+16 share row l & 15 of the parked tile: each walks HS cells of the trapezoid CDF (reference
+    // tt_irt1_int32.c:107-113), lane l the lower half of the grid and lane l+16 the upper half.
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TAIL_REGS));
+    const int tw = warp - MMA_WARPS, row = lane & 15, hf = lane >> 4;
+    const double *pbr = pb_all + tw * L::PB + row;
+    const int *ids = ids_all + tw * WROWS;
+    constexpr int HS = L::HS;
+    const int c0 = hf * HS, nlast = n1 - 1;
+    auto node = [&](int j) -> int { return TAIL1 ? j : min(j, nlast); };  // TAIL1: 2*HS == n1-1, never out of range
+    const int uses = 2 * (t_end - t_begin);
+    constexpr int HB = L::HB;
+    for (int seq = 0; seq < uses; ++seq) {
+      bar_pair_sync(2 + tw);                        // FULL: the tile of producer seq & 1 is parked
+      const int nv = nv_all[tw];
+      if (nv == 0) {
+        if (seq + 1 < uses) bar_pair_arrive(6 + 4 * ((seq + 1) & 1) + tw);
+        continue;
       }
-      cp_async_commit();
-    }
-  };
-  // per-row scalars, m-tile i = rows 8i+g: current tile and next tile (in flight)
-  int mrow[MT], mrow_n[MT];
-  double w1[MT], w2[MT], qv_[MT], lp_[MT], w1n[MT], w2n[MT], qn[MT], lpn[MT];
+      const int m = ids[row];
+      const double qv = a.q[m];
+      double lpN = a.lp[m], lpD = a.lpd[m];
+      int lpE = a.lpe[m];
+      // one pass over the parked |pdf|: local trapezoid prefix of each of this lane's four blocks of cells (four
+      // independent chains), kept in registers.  FP64 instructions are what the tail competes with the DMMA
+      // stream for, so everything after this pass that can be done on integer bit patterns is.
+      double Lp[4][HB];
 #pragma unroll
-  for (int i = 0; i < MT; i++) { mrow[i] = mrow_n[i] = 0; w1[i] = w2[i] = qv_[i] = lp_[i] = w1n[i] = w2n[i] = qn[i] = lpn[i] = 0.0; }
-  auto load_scalars_next = [&]() {
+      for (int c = 0; c < HB; ++c) {
 #pragma unroll
-    for (int i = 0; i < MT; i++) mrow_n[i] = __shfl_sync(FULL, idN, 8 * i + g);
-    if (nvN > 0) {
+        for (int k = 0; k < 4; k++) {
+          const int nd = c0 + k * HB + c;
+          const double s2n = fabs(pbr[node(nd) * RS]) + fabs(pbr[node(nd + 1) * RS]);
+          Lp[k][c] = fma(hh[nd], s2n, c ? Lp[k][c - 1] : 0.0);
+        }
+      }
+      const double th = (Lp[0][HB - 1] + Lp[1][HB - 1]) + (Lp[2][HB - 1] + Lp[3][HB - 1]);
+      const double ot = __shfl_xor_sync(FULL, th, 16);
+      const double tot0 = hf ? ot : th, tot1 = hf ? th : ot;
+      const double total = tot0 + tot1;            // mass of the row's conditional (reference :107-113, cdf[n-1])
+      const double qt = qv * total;                // q > cdf/mass  <=>  q*mass > cdf (unnormalised compare)
+      // search (reference :134-142): last node 1 <= nd <= n1-2 whose CDF is below q.  The CDF at node nd of block k is
+      // base_k + Lp[k][c-1]; non-negative doubles order like their bit patterns, so the 64 compares are integer ones.
+      int il = -1;
+      double qsel = qt, Lsel = 0.0;
+      {
+        double base = hf ? tot0 : 0.0;
 #pragma unroll
-      for (int i = 0; i < MT; i++) {
-        w1n[i] = a.w1[mrow_n[i]]; w2n[i] = a.w2[mrow_n[i]]; qn[i] = a.q[mrow_n[i]]; lpn[i] = a.lp[mrow_n[i]];
+        for (int k = 0; k < 4; k++) {
+          const double qk = qt - base;
+          const long long qb = __double_as_longlong(qk);
+#pragma unroll
+          for (int c = 0; c < HB; ++c) {
+            const int nd = c0 + k * HB + c;
+            const double Lprev = c ? Lp[k][c - 1] : 0.0;
+            bool below = qb > __double_as_longlong(Lprev);
+            if (TAIL1) { if (k == 0 && c == 0) below = below && hf; }   // node 0 is no candidate; 2*HS - 1 == n1 - 2
+            else below = below && nd >= 1 && nd <= n1 - 2;
+            if (below) { il = nd; qsel = qk; Lsel = Lprev; }
+          }
+          base += Lp[k][HB - 1];
+        }
+      }
+      double dq = qsel - Lsel;                     // q*mass - cdf at the chosen node
+      const int il_o = __shfl_xor_sync(FULL, il, 16);
+      const double dq_o = __shfl_xor_sync(FULL, dq, 16);
+      const int il_hi = hf ? il : il_o, il_lo = hf ? il_o : il;
+      const double dq_hi = hf ? dq : dq_o, dq_lo = hf ? dq_o : dq;
+      int i0 = il_hi >= 0 ? il_hi : (il_lo >= 0 ? il_lo : 0);
+      dq = il_hi >= 0 ? dq_hi : (il_lo >= 0 ? dq_lo : qt);
+      const double s2 = pow2_scale(total);         // exact power-of-two normalisation instead of 1/mass
+      double c1 = fabs(pbr[i0 * RS]) * s2, c2 = fabs(pbr[(i0 + 1) * RS]) * s2;   // (consumes the loads before the buffer is handed back)
+      if (seq + 1 < uses) bar_pair_arrive(6 + 4 * ((seq + 1) & 1) + tw);   // EMPTY: the other producer may park its tile
+      dq *= s2;
+      double mass = total * s2;
+
+      if (total == 0.0) {
+        // zero-mass conditional: uniform in index space (reference tt_irt1_int32.c:116-125)
+        const double u = 1.0 / (double)(n1 - 1);
+        const double sf = 1.0 / ((double)(n1 - 1) * u);
+        int k0 = 0;
+        for (int j = 1; j <= n1 - 2; j++) k0 += (qv > ((double)j * u) * sf) ? 1 : 0;
+        i0 = k0; dq = qv - ((double)k0 * u) * sf; c1 = u * sf; c2 = u * sf; mass = 1.0;
+      }
+      const CellFast o = invert_cell_fast(dq, c1, c2, xg[i0], xg[i0 + 1], ihs[i0]);
+      lp_accumulate(lpN, lpD, lpE, o.dens, mass);
+      if (hf == 0 && row < nv) {
+        a.z[m] = o.xk;
+        if (a.idx_out) a.idx_out[m] = i0;
+        if (!a.last) {
+          a.idx[m] = i0; a.w1[m] = o.w1; a.w2[m] = o.w2;
+          a.lp[m] = lpN; a.lpd[m] = lpD; a.lpe[m] = lpE;
+          atomicAdd(&hist[i0], 1);
+        } else {
+          a.lpz[m] = lp_finish(lpN, lpD, lpE);
+        }
       }
     }
-  };
-  {
-    const int rowC = rows_of(t_begin, nvC);
-    const int idC = load_ids(rowC, nvC);
-    issue_gather(idC, nvC);
-    idN = idC; nvN = nvC;
-    load_scalars_next();
-#pragma unroll
-    for (int i = 0; i < MT; i++) { mrow[i] = mrow_n[i]; w1[i] = w1n[i]; w2[i] = w2n[i]; qv_[i] = qn[i]; lp_[i] = lpn[i]; }
-    const int rowN = rows_of(t_begin + 1, nvN);
-    idN = load_ids(rowN, nvN);
-  }
+  } else {
+    // =========================================== MMA warps ============================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(MMA_REGS));
+    const int g = lane >> 2, t = lane & 3;
+    const int tw = warp & (TAIL_WARPS - 1), prod = warp / TAIL_WARPS;  // tail warp served; first / second producer of its buffer
+    double *ft = ft_all + warp * L::FTILE;
+    double *pbw = pb_all + tw * L::PB;
+    const int ks0 = EXACT ? RT : (r0 + 7) >> 3, rt_act = EXACT ? RT : (r1 + 7) >> 3, nt_act = EXACT ? NT : (n1 + 7) >> 3;
+    const uint32_t row_bytes = (uint32_t)(8 * ks0) * 8u;   // bytes of a left-interface row that the update reads
+    const int64_t slab_cs = (int64_t)r0 * a.n0;
 
-  // optional start offset for a subset of the warps (breaks the lock-step of warps sharing a pipe)
-  if (a.stagger_ns && (warp & a.stagger_mask)) __nanosleep(a.stagger_ns);
-  PT_DECL
-  for (int tile = t_begin; tile < t_end; ++tile) {
-    PT_MARK(7)
-    while (tile >= bts[b + 1]) ++b;
-    if (cur0 == b && cur1 == b + 1) {
-      sl_lo = slab0; sl_hi = slab1;
-    } else if (cur1 == b && cur0 == b + 1) {
-      sl_lo = slab1; sl_hi = slab0;
-    } else {
-      __syncthreads();  // every warp is done with the previous bin's slabs
-      if (cur0 == b) {
-        stage_b(slab1, a.core + (int64_t)(b + 1) * r0, r0, r1, slab_cs, KP, 8 * RT, tid, NTHR); cur1 = b + 1;
-      } else if (cur1 == b) {
-        stage_b(slab0, a.core + (int64_t)(b + 1) * r0, r0, r1, slab_cs, KP, 8 * RT, tid, NTHR); cur0 = b + 1;
-      } else if (cur0 == b + 1) {
-        stage_b(slab1, a.core + (int64_t)b * r0, r0, r1, slab_cs, KP, 8 * RT, tid, NTHR); cur1 = b;
-      } else if (cur1 == b + 1) {
-        stage_b(slab0, a.core + (int64_t)b * r0, r0, r1, slab_cs, KP, 8 * RT, tid, NTHR); cur0 = b;
+    int cur0 = -1, cur1 = -1;  // interval slab held by slab0 / slab1
+    int b = 0;                 // bin of the current tile
+    int bh = 0;                // bin hint of the row look-ahead (monotone)
+    const double *sl_lo = slab0, *sl_hi = slab1;
+
+    // rows of this warp in CTA tile `tile`: first sorted row and number of valid rows (0 past the end)
+    auto rows_of = [&](int tile, int &nv) -> int {
+      if (tile >= t_end) { nv = 0; return 0; }
+      while (tile >= bts[bh + 1]) ++bh;
+      const int row0 = bst[bh] + (tile - bts[bh]) * ROWS_CTA + warp * WROWS;
+      nv = max(0, min(WROWS, bst[bh + 1] - row0));
+      return row0;
+    };
+    // sample ids of a tile: lane l holds the id of row l % WROWS; rows past nv repeat row 0
+    auto load_ids = [&](int row0, int nv) -> int {
+      const int r = lane & (WROWS - 1);
+      return nv > 0 ? a.perm[row0 + (r < nv ? r : 0)] : 0;
+    };
+
+    int nvC = 0, nvN = 0;      // valid rows: current tile / next tile
+    int idC = 0, idN = 0;      // row ids (lane-distributed): current tile / next tile
+    // Gather of the rows whose ids are `ids` into this warp's shared tile: one cp.async (LDGSTS) instruction per row,
+    // 16 bytes per lane, so a row is one coalesced 8*r0-byte segment.
+    auto issue_gather = [&](int ids, int nv) {
+      if (nv > 0) {
+#pragma unroll
+        for (int r = 0; r < WROWS; r++) {
+          const int id = __shfl_sync(FULL, ids, r);
+          if (16u * lane < row_bytes)
+            cp_async16(reinterpret_cast<char *>(ft + r * FP) + 16 * lane, reinterpret_cast<const char *>(a.F + (size_t)id * a.ldf) + 16 * lane);
+        }
+        cp_async_commit();
+      }
+    };
+    // per-row scalars, m-tile i = rows 8i+g: current tile and next tile (in flight)
+    int mrow[MT], mrow_n[MT];
+    double w1[MT], w2[MT], w1n[MT], w2n[MT];
+#pragma unroll
+    for (int i = 0; i < MT; i++) { mrow[i] = mrow_n[i] = 0; w1[i] = w2[i] = w1n[i] = w2n[i] = 0.0; }
+    auto load_scalars_next = [&]() {
+#pragma unroll
+      for (int i = 0; i < MT; i++) mrow_n[i] = __shfl_sync(FULL, idN, 8 * i + g);
+      if (nvN > 0) {
+#pragma unroll
+        for (int i = 0; i < MT; i++) { w1n[i] = a.w1[mrow_n[i]]; w2n[i] = a.w2[mrow_n[i]]; }
+      }
+    };
+    {
+      const int rowC = rows_of(t_begin, nvC);
+      idC = load_ids(rowC, nvC);
+      issue_gather(idC, nvC);
+      idN = idC; nvN = nvC;
+      load_scalars_next();
+#pragma unroll
+      for (int i = 0; i < MT; i++) { mrow[i] = mrow_n[i]; w1[i] = w1n[i]; w2[i] = w2n[i]; }
+      const int rowN = rows_of(t_begin + 1, nvN);
+      idN = load_ids(rowN, nvN);
+    }
+
+    PT_DECL
+    for (int tile = t_begin; tile < t_end; ++tile) {
+      PT_MARK(7)
+      while (tile >= bts[b + 1]) ++b;
+      if (cur0 == b && cur1 == b + 1) {
+        sl_lo = slab0; sl_hi = slab1;
+      } else if (cur1 == b && cur0 == b + 1) {
+        sl_lo = slab1; sl_hi = slab0;
       } else {
-        stage_b(slab0, a.core + (int64_t)b * r0, r0, r1, slab_cs, KP, 8 * RT, tid, NTHR); cur0 = b;
-        stage_b(slab1, a.core + (int64_t)(b + 1) * r0, r0, r1, slab_cs, KP, 8 * RT, tid, NTHR); cur1 = b + 1;
+        bar_mma_warps();  // every MMA warp is done with the previous bin's slabs
+        constexpr int NM = 32 * MMA_WARPS;
+        if (cur0 == b) {
+          stage_b(slab1, a.core + (int64_t)(b + 1) * r0, r0, r1, slab_cs, KP, 8 * RT, tid, NM); cur1 = b + 1;
+        } else if (cur1 == b) {
+          stage_b(slab0, a.core + (int64_t)(b + 1) * r0, r0, r1, slab_cs, KP, 8 * RT, tid, NM); cur0 = b + 1;
+        } else if (cur0 == b + 1) {
+          stage_b(slab1, a.core + (int64_t)b * r0, r0, r1, slab_cs, KP, 8 * RT, tid, NM); cur1 = b;
+        } else if (cur1 == b + 1) {
+          stage_b(slab0, a.core + (int64_t)b * r0, r0, r1, slab_cs, KP, 8 * RT, tid, NM); cur0 = b;
+        } else {
+          stage_b(slab0, a.core + (int64_t)b * r0, r0, r1, slab_cs, KP, 8 * RT, tid, NM); cur0 = b;
+          stage_b(slab1, a.core + (int64_t)(b + 1) * r0, r0, r1, slab_cs, KP, 8 * RT, tid, NM); cur1 = b + 1;
+        }
+        bar_mma_warps();
+        if (cur0 == b) { sl_lo = slab0; sl_hi = slab1; } else { sl_lo = slab1; sl_hi = slab0; }
       }
-      __syncthreads();
-      if (cur0 == b) { sl_lo = slab0; sl_hi = slab1; } else { sl_lo = slab1; sl_hi = slab0; }
-    }
 
-    PT_MARK(0)
-    const int nvalid = nvC;
-    double c[MT][NT + 1][2];
-#pragma unroll
-    for (int i = 0; i < MT; i++)
-#pragma unroll
-      for (int j = 0; j <= NT; j++) c[i][j][0] = c[i][j][1] = 0.0;
-
-    if (nvalid > 0) {
-      // ---- (1) interface update: A fragments from the TMA-staged rows ------------------------------
-      cp_async_wait_all();
-      __syncwarp();
-      PT_MARK(1)
-      double acc[MT][RT][2];
+      PT_MARK(0)
+      const int nvalid = nvC;
+      double c[MT][NT][2];
 #pragma unroll
       for (int i = 0; i < MT; i++)
 #pragma unroll
-        for (int j = 0; j < RT; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < NT; j++) c[i][j][0] = c[i][j][1] = 0.0;
+
+      if (nvalid > 0) {
+        // ---- (1) interface update: A fragments from the staged rows ------------------------------------
+        cp_async_wait_all();
+        __syncwarp();
+        PT_MARK(1)
+        double acc[MT][RT][2];
 #pragma unroll
-      for (int j = 0; j < RT; j++) {
-        if (EXACT || j < ks0) {
-          double a1[MT][2], a2[MT][2];
+        for (int i = 0; i < MT; i++)
 #pragma unroll
-          for (int i = 0; i < MT; i++) {
-            const double2 f = *reinterpret_cast<const double2 *>(ft + (8 * i + g) * FP + 2 * t + 8 * j);
-            a1[i][0] = w1[i] * f.x; a2[i][0] = w2[i] * f.x; a1[i][1] = w1[i] * f.y; a2[i][1] = w2[i] * f.y;
-          }
-          const int sw = ((j ^ (g & 1)) << 3) | (t << 1);
+          for (int j = 0; j < RT; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 #pragma unroll
-          for (int jj = 0; jj < RT; jj++) {
-            if (EXACT || jj < rt_act) {
-              const int off = (8 * jj + g) * KP + sw;
-              const double2 b1 = *reinterpret_cast<const double2 *>(sl_lo + off);
-              const double2 b2 = *reinterpret_cast<const double2 *>(sl_hi + off);
+        for (int j = 0; j < RT; j++) {
+          if (EXACT || j < ks0) {
+            double a1[MT][2], a2[MT][2];
 #pragma unroll
-              for (int i = 0; i < MT; i++) dmma884(acc[i][jj][0], acc[i][jj][1], a1[i][0], b1.x);
+            for (int i = 0; i < MT; i++) {
+              const double2 f = *reinterpret_cast<const double2 *>(ft + (8 * i + g) * FP + 2 * t + 8 * j);
+              a1[i][0] = w1[i] * f.x; a2[i][0] = w2[i] * f.x; a1[i][1] = w1[i] * f.y; a2[i][1] = w2[i] * f.y;
+            }
+            const int sw = ((j ^ (g & 1)) << 3) | (t << 1);
 #pragma unroll
-              for (int i = 0; i < MT; i++) dmma884(acc[i][jj][0], acc[i][jj][1], a2[i][0], b2.x);
+            for (int jj = 0; jj < RT; jj++) {
+              if (EXACT || jj < rt_act) {
+                const int off = (8 * jj + g) * KP + sw;
+                const double2 b1 = *reinterpret_cast<const double2 *>(sl_lo + off);
+                const double2 b2 = *reinterpret_cast<const double2 *>(sl_hi + off);
 #pragma unroll
-              for (int i = 0; i < MT; i++) dmma884(acc[i][jj][0], acc[i][jj][1], a1[i][1], b1.y);
+                for (int i = 0; i < MT; i++) dmma884(acc[i][jj][0], acc[i][jj][1], a1[i][0], b1.x);
 #pragma unroll
-              for (int i = 0; i < MT; i++) dmma884(acc[i][jj][0], acc[i][jj][1], a2[i][1], b2.y);
+                for (int i = 0; i < MT; i++) dmma884(acc[i][jj][0], acc[i][jj][1], a2[i][0], b2.x);
+#pragma unroll
+                for (int i = 0; i < MT; i++) dmma884(acc[i][jj][0], acc[i][jj][1], a1[i][1], b1.y);
+#pragma unroll
+                for (int i = 0; i < MT; i++) dmma884(acc[i][jj][0], acc[i][jj][1], a2[i][1], b2.y);
+              }
             }
           }
         }
-      }
-      PT_MARK(2)
-      // ---- the staged tile is consumed: launch the next tile's gather and scalar loads now ---------
-      __syncwarp();
-      issue_gather(idN, nvN);
-      PT_MARK(7)
-      load_scalars_next();
-      // F' rows go out one 64-byte segment per pdf k-pair (below), so the stores trickle out under the DMMA stream
-      double *Fo[MT];
+        PT_MARK(2)
+        // ---- the staged tile is consumed: launch the next tile's gather and scalar loads now ---------
+        __syncwarp();
+        issue_gather(idN, nvN);
+        load_scalars_next();
+        // F' rows go out one 64-byte segment per pdf k-pair (below), so the stores trickle out under the DMMA stream
+        double *Fo[MT];
 #pragma unroll
-      for (int i = 0; i < MT; i++) Fo[i] = a.F + (size_t)mrow[i] * a.ldf + 2 * t;
-      const bool do_store = !a.last;
-      PT_MARK(3)
-      // ---- (2) conditional pdf on the grid of dimension k+1 ----------------------------------------
-#pragma unroll
-      for (int jj = 0; jj < RT; jj++) {
-        if (EXACT || jj < rt_act) {
-          const int sw = ((jj ^ (g & 1)) << 3) | (t << 1);
-#pragma unroll
-          for (int jn = 0; jn < NTD; jn++) {
-            if (EXACT || jn < nt_act) {
-              const double2 bv = *reinterpret_cast<const double2 *>(Ps + (8 * jn + g) * KP + sw);
-#pragma unroll
-              for (int i = 0; i < MT; i++) dmma884(c[i][jn][0], c[i][jn][1], acc[i][jj][0], bv.x);
-#pragma unroll
-              for (int i = 0; i < MT; i++) dmma884(c[i][jn][0], c[i][jn][1], acc[i][jj][1], bv.y);
-            }
-          }
-          if (do_store) {
-#pragma unroll
-            for (int i = 0; i < MT; i++)
-              if (8 * i + g < nvalid) *reinterpret_cast<double2 *>(Fo[i] + 8 * jj) = make_double2(acc[i][jj][0], acc[i][jj][1]);
-          }
-        }
-      }
-      if (TAIL1) {
-        // last grid column (node 8*(NT-1), even column: no swizzle): quad-distributed dot product
-        double tl[MT];
-#pragma unroll
-        for (int i = 0; i < MT; i++) tl[i] = 0.0;
+        for (int i = 0; i < MT; i++) Fo[i] = a.F + (size_t)mrow[i] * a.ldf + 2 * t;
+        const bool do_store = !a.last;
+        PT_MARK(3)
+        // ---- (2) conditional pdf on the grid of dimension k+1 ----------------------------------------
 #pragma unroll
         for (int jj = 0; jj < RT; jj++) {
-          const double2 pv = *reinterpret_cast<const double2 *>(Ps + (8 * (NT - 1)) * KP + (jj << 3) + (t << 1));
+          if (EXACT || jj < rt_act) {
+            const int sw = ((jj ^ (g & 1)) << 3) | (t << 1);
 #pragma unroll
-          for (int i = 0; i < MT; i++) { tl[i] = fma(acc[i][jj][0], pv.x, tl[i]); tl[i] = fma(acc[i][jj][1], pv.y, tl[i]); }
-        }
+            for (int jn = 0; jn < NTD; jn++) {
+              if (EXACT || jn < nt_act) {
+                const double2 bv = *reinterpret_cast<const double2 *>(Ps + (8 * jn + g) * KP + sw);
 #pragma unroll
-        for (int i = 0; i < MT; i++) {
-          tl[i] += __shfl_xor_sync(FULL, tl[i], 1); tl[i] += __shfl_xor_sync(FULL, tl[i], 2);
-          c[i][NT - 1][0] = (t == 0) ? tl[i] : 0.0;
+                for (int i = 0; i < MT; i++) dmma884(c[i][jn][0], c[i][jn][1], acc[i][jj][0], bv.x);
+#pragma unroll
+                for (int i = 0; i < MT; i++) dmma884(c[i][jn][0], c[i][jn][1], acc[i][jj][1], bv.y);
+              }
+            }
+            if (do_store) {
+#pragma unroll
+              for (int i = 0; i < MT; i++)
+                if (8 * i + g < nvalid) *reinterpret_cast<double2 *>(Fo[i] + 8 * jj) = make_double2(acc[i][jj][0], acc[i][jj][1]);
+            }
+          }
         }
+        if (TAIL1) {
+          // last grid column (node 8*(NT-1), even column: no swizzle): quad-distributed dot product
+          double tl[MT];
+#pragma unroll
+          for (int i = 0; i < MT; i++) tl[i] = 0.0;
+#pragma unroll
+          for (int jj = 0; jj < RT; jj++) {
+            const double2 pv = *reinterpret_cast<const double2 *>(Ps + (8 * (NT - 1)) * KP + (jj << 3) + (t << 1));
+#pragma unroll
+            for (int i = 0; i < MT; i++) { tl[i] = fma(acc[i][jj][0], pv.x, tl[i]); tl[i] = fma(acc[i][jj][1], pv.y, tl[i]); }
+          }
+#pragma unroll
+          for (int i = 0; i < MT; i++) {
+            tl[i] += __shfl_xor_sync(FULL, tl[i], 1); tl[i] += __shfl_xor_sync(FULL, tl[i], 2);
+            c[i][NT - 1][0] = tl[i];
+          }
+        }
+      } else {
+        // this warp has no rows in this tile: keep the pipeline moving
+        issue_gather(idN, nvN);
+        load_scalars_next();
       }
-    } else {
-      // this warp has no rows in this tile: keep the pipeline moving
-      issue_gather(idN, nvN);
-      load_scalars_next();
+      PT_MARK(4)
+      // ids of the tile after next
+      int nvNN = 0;
+      const int rowNN = rows_of(tile + 2, nvNN);
+      const int idNN = load_ids(rowNN, nvNN);
+
+      // ---- (3) park the signed pdf tile for the tail warp (it takes |.|, reference :105); the two producers of a buffer alternate ----
+      {
+        // producer 0 waits for the tail warp to have released producer 1's previous tile, and vice versa
+        if (prod == 1 || tile > t_begin) bar_pair_sync(6 + 4 * prod + tw);
+        PT_MARK(5)
+        if (nvalid > 0) {
+#pragma unroll
+          for (int i = 0; i < MT; i++) {
+#pragma unroll
+            for (int jn = 0; jn < NTD; jn++) {
+              pbw[(8 * jn + 2 * t) * RS + 8 * i + g] = c[i][jn][0];
+              pbw[(8 * jn + 2 * t + 1) * RS + 8 * i + g] = c[i][jn][1];
+            }
+            if (TAIL1 && t == 0) pbw[(8 * (NT - 1)) * RS + 8 * i + g] = c[i][NT - 1][0];
+          }
+          if (lane < WROWS) ids_all[tw * WROWS + lane] = idC;
+        }
+        if (lane == 0) nv_all[tw] = nvalid;
+        bar_pair_arrive(2 + tw);                    // FULL
+      }
+
+      PT_MARK(6)
+      // ---- rotate the row pipeline --------------------------------------------------------------------
+      nvC = nvN; idC = idN;
+#pragma unroll
+      for (int i = 0; i < MT; i++) { mrow[i] = mrow_n[i]; w1[i] = w1n[i]; w2[i] = w2n[i]; }
+      nvN = nvNN; idN = idNN;
     }
-    PT_MARK(4)
-    // ids of the tile after next
-    int nvNN = 0;
-    const int rowNN = rows_of(tile + 2, nvNN);
-    const int idNN = load_ids(rowNN, nvNN);
-
-    if (nvalid > 0) {
-      // ---- (3) CDF, search: all lanes; the MT row tiles are advanced together (independent chains interleave) ----
-      double cdf_lo[MT], c1v[MT], c2v[MT];
-      int i0v[MT];
-      {
-        double S0[MT][NT], S1[MT][NT], carry[MT];
-#pragma unroll
-        for (int i = 0; i < MT; i++) {
-          carry[i] = 0.0;
-#pragma unroll
-          for (int jn = 0; jn < NT; jn++) { c[i][jn][0] = fabs(c[i][jn][0]); c[i][jn][1] = fabs(c[i][jn][1]); S0[i][jn] = 0.0; S1[i][jn] = 0.0; }
-        }
-#pragma unroll
-        for (int jn = 0; jn < NT; jn++) {
-          if (TAIL1 && jn == NT - 1) continue;  // the lone last node starts no cell and is never a search candidate
-          if (EXACT || jn < nt_act) {
-            const double h0 = hh[8 * jn + 2 * t], h1 = hh[8 * jn + 2 * t + 1];
-            double Ta[MT], incl[MT];
-#pragma unroll
-            for (int i = 0; i < MT; i++) {
-              const double p0 = c[i][jn][0], p1 = c[i][jn][1];
-              const double var = (t == 0) ? c[i][jn + 1][0] : p0;
-              const double nxt = __shfl_sync(FULL, var, (t == 3) ? lane - 3 : lane + 1);
-              Ta[i] = h0 * (p0 + p1);
-              incl[i] = Ta[i] + h1 * (p1 + nxt);
-            }
-#pragma unroll
-            for (int i = 0; i < MT; i++) { const double v = __shfl_up_sync(FULL, incl[i], 1, 4); if (t >= 1) incl[i] += v; }
-#pragma unroll
-            for (int i = 0; i < MT; i++) { const double v = __shfl_up_sync(FULL, incl[i], 2, 4); if (t >= 2) incl[i] += v; }
-#pragma unroll
-            for (int i = 0; i < MT; i++) {
-              double excl = __shfl_up_sync(FULL, incl[i], 1, 4);
-              if (t == 0) excl = 0.0;
-              const double tot = __shfl_sync(FULL, incl[i], 3, 4);
-              S0[i][jn] = carry[i] + excl;
-              S1[i][jn] = S0[i][jn] + Ta[i];
-              carry[i] += tot;
-            }
-          }
-        }
-        double sc[MT], qt[MT];
-        int cnt[MT];
-#pragma unroll
-        for (int i = 0; i < MT; i++) { sc[i] = 1.0 / carry[i]; qt[i] = qv_[i] * carry[i]; cnt[i] = 0; }  // q > S/total <=> q*total > S
-#pragma unroll
-        for (int jn = 0; jn < NTD; jn++) {
-          if (EXACT || jn < nt_act) {
-            const int node0 = 8 * jn + 2 * t;
-#pragma unroll
-            for (int i = 0; i < MT; i++) {
-              cnt[i] += (node0 >= 1 && node0 <= n1 - 2 && qt[i] > S0[i][jn]) ? 1 : 0;
-              cnt[i] += (node0 + 1 <= n1 - 2 && qt[i] > S1[i][jn]) ? 1 : 0;
-            }
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < MT; i++) { cnt[i] += __shfl_xor_sync(FULL, cnt[i], 1); }
-#pragma unroll
-        for (int i = 0; i < MT; i++) { cnt[i] += __shfl_xor_sync(FULL, cnt[i], 2); }
-#pragma unroll
-        for (int i = 0; i < MT; i++) {
-          const int i0 = cnt[i], i1 = cnt[i] + 1;
-          const int js = i0 >> 3, ts = (i0 & 7) >> 1, es = i0 & 1;
-          const int jq = i1 >> 3, tq = (i1 & 7) >> 1, eq = i1 & 1;
-          double selS = 0.0, selP = 0.0, selQ = 0.0;
-#pragma unroll
-          for (int jn = 0; jn < NT; jn++) {
-            if (jn == js) { selS = es ? S1[i][jn] : S0[i][jn]; selP = es ? c[i][jn][1] : c[i][jn][0]; }
-            if (jn == jq) { selQ = eq ? c[i][jn][1] : c[i][jn][0]; }
-          }
-          const int base = lane & ~3;
-          selS = __shfl_sync(FULL, selS, base | ts);
-          selP = __shfl_sync(FULL, selP, base | ts);
-          selQ = __shfl_sync(FULL, selQ, base | tq);
-          cdf_lo[i] = selS * sc[i]; c1v[i] = selP * sc[i]; c2v[i] = selQ * sc[i]; i0v[i] = i0;
-          if (carry[i] == 0.0) {
-            // zero-mass conditional: uniform in index space (reference tt_irt1_int32.c:116-125)
-            const double u = 1.0 / (double)(n1 - 1);
-            const double s2 = 1.0 / ((double)(n1 - 1) * u);
-            int k0 = 0;
-            for (int j = 1; j <= n1 - 2; j++) k0 += (qv_[i] > ((double)j * u) * s2) ? 1 : 0;
-            i0v[i] = k0; cdf_lo[i] = ((double)k0 * u) * s2; c1v[i] = u * s2; c2v[i] = u * s2;
-          }
-        }
-      }
-
-      PT_MARK(5)
-      // ---- inversion tail: lane t = i of a quad finishes row 8i + g ---------------------------------
-      {
-        const int sel = (MT == 2) ? (t & 1) : 0;
-        const bool valid = (t < MT) && (8 * sel + g < nvalid);
-        const int m = mrow[sel];
-        const int i0 = i0v[sel];
-        const CellOut o = invert_cell_fast(qv_[sel], cdf_lo[sel], c1v[sel], c2v[sel], xg[i0], xg[i0 + 1], ihs[i0]);
-        if (valid) {
-          a.z[m] = o.xk;
-          if (a.idx_out) a.idx_out[m] = i0;
-          if (!a.last) {
-            a.idx[m] = i0; a.w1[m] = o.w1; a.w2[m] = o.w2;
-            a.lp[m] = lp_[sel] + o.logp;
-            atomicAdd(&hist[i0], 1);
-          } else {
-            a.lpz[m] = lp_[sel] + o.logp;
-          }
-        }
-      }
-    }  // nvalid > 0
-
-    PT_MARK(6)
-    // ---- rotate the row pipeline --------------------------------------------------------------------
-    nvC = nvN;
-#pragma unroll
-    for (int i = 0; i < MT; i++) { mrow[i] = mrow_n[i]; w1[i] = w1n[i]; w2[i] = w2n[i]; qv_[i] = qn[i]; lp_[i] = lpn[i]; }
-    nvN = nvNN; idN = idNN;
+    PT_FLUSH
   }
 
-  PT_FLUSH
   if (!a.last) {
     __syncthreads();
     for (int i = tid; i < n1 - 1; i += NTHR)
@@ -473,44 +509,32 @@ __global__ void __launch_bounds__(WARPS * 32, 1) transition_kernel(const TransAr
   }
 }
 
-template <int RT, int NT, int WARPS, int MT, bool EXACT, bool TAIL1>
+template <int RT, int NT, bool EXACT, bool TAIL1>
 cudaError_t launch_variant(const TransArgs &a, int sm_count, cudaStream_t st) {
-  using L = SmemLayout<RT, NT, WARPS, MT>;
-  static int occ = 0;
-  if (occ == 0) {
-    int o = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, transition_kernel<RT, NT, WARPS, MT, EXACT, TAIL1>, WARPS * 32, L::bytes);
-    if (e != cudaSuccess) return e;
-    occ = o > 0 ? o : 1;
-  }
-  const int rows_cta = WARPS * 8 * MT;
-  int64_t max_tiles = ((int64_t)a.rows + rows_cta - 1) / rows_cta + (a.n0 - 1);
-  int64_t grid = (int64_t)sm_count * occ;
+  using L = SmemLayout<RT, NT, TAIL1>;
+  int64_t max_tiles = ((int64_t)a.rows + ROWS_CTA - 1) / ROWS_CTA + (a.n0 - 1);
+  int64_t grid = sm_count;   // persistent: one CTA per SM (shared memory allows no more)
   if (grid > max_tiles) grid = max_tiles;
   if (grid < 1) grid = 1;
-  transition_kernel<RT, NT, WARPS, MT, EXACT, TAIL1><<<(unsigned)grid, WARPS * 32, L::bytes, st>>>(a);
+  transition_kernel<RT, NT, EXACT, TAIL1><<<(unsigned)grid, NTHR, L::bytes, st>>>(a);
   return cudaGetLastError();
 }
 
-template <int RT, int NT, int WARPS, int MT>
+template <int RT, int NT>
 cudaError_t launch_one(const TransArgs &a, int sm_count, cudaStream_t st) {
   const bool exact = a.r0 == 8 * RT && a.r1 == 8 * RT && (a.n1 + 7) / 8 == NT;
-  if (exact && a.n1 == 8 * (NT - 1) + 1) return launch_variant<RT, NT, WARPS, MT, true, true>(a, sm_count, st);
-  if (exact) return launch_variant<RT, NT, WARPS, MT, true, false>(a, sm_count, st);
-  return launch_variant<RT, NT, WARPS, MT, false, false>(a, sm_count, st);
+  if (exact && a.n1 == 8 * (NT - 1) + 1) return launch_variant<RT, NT, true, true>(a, sm_count, st);
+  if (exact) return launch_variant<RT, NT, true, false>(a, sm_count, st);
+  return launch_variant<RT, NT, false, false>(a, sm_count, st);
 }
 
-template <int RT, int NT, int WARPS, int MT>
+template <int RT, int NT>
 cudaError_t init_one() {
-  using L = SmemLayout<RT, NT, WARPS, MT>;
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(transition_kernel<RT, NT, WARPS, MT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(transition_kernel<RT, NT, WARPS, MT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes)) != cudaSuccess) return e;
-  return cudaFuncSetAttribute(transition_kernel<RT, NT, WARPS, MT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes);
+  if ((e = cudaFuncSetAttribute(transition_kernel<RT, NT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout<RT, NT, true>::bytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(transition_kernel<RT, NT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout<RT, NT, false>::bytes)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(transition_kernel<RT, NT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout<RT, NT, false>::bytes);
 }
-
-constexpr int kWarps = TTIRT_WARPS;
-constexpr int kMT = TTIRT_MT;
 
 }  // namespace
 
@@ -521,21 +545,21 @@ int fast_class_for(int rmax, int nmax) {
   return -1;
 }
 
-int fast_rows_per_cta(int) { return kWarps * 8 * kMT; }
+int fast_rows_per_cta(int) { return ROWS_CTA; }
 
 cudaError_t fast_init(int) {
   cudaError_t e;
-  if ((e = init_one<2, 3, kWarps, kMT>()) != cudaSuccess) return e;
-  if ((e = init_one<4, 5, kWarps, kMT>()) != cudaSuccess) return e;
-  if ((e = init_one<8, 9, kWarps, kMT>()) != cudaSuccess) return e;
+  if ((e = init_one<2, 3>()) != cudaSuccess) return e;
+  if ((e = init_one<4, 5>()) != cudaSuccess) return e;
+  if ((e = init_one<8, 9>()) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
 cudaError_t launch_transition(int cls, const TransArgs &a, int sm_count, cudaStream_t st) {
   switch (cls) {
-    case 0: return launch_one<2, 3, kWarps, kMT>(a, sm_count, st);
-    case 1: return launch_one<4, 5, kWarps, kMT>(a, sm_count, st);
-    case 2: return launch_one<8, 9, kWarps, kMT>(a, sm_count, st);
+    case 0: return launch_one<2, 3>(a, sm_count, st);
+    case 1: return launch_one<4, 5>(a, sm_count, st);
+    case 2: return launch_one<8, 9>(a, sm_count, st);
     default: return cudaErrorInvalidValue;
   }
 }
