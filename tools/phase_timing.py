@@ -31,4 +31,8 @@ ntiles = 31.0 * M / (8 * mt)          # warp-tiles per call (31 transitions)
 for nm, x in zip(names, v):
     print("%-20s %6.2f%%  %8.0f cycles per warp-tile" % (nm, 100 * x / tot, x / ntiles))
 print("total %.0f cycles per warp-tile" % (tot / ntiles))
+tail = np.array(list(out)[24:30], dtype=np.float64)
+uses = 31.0 * M / 16           # parked tiles per call
+for nm, x in zip(["tail: wait FULL", "tail: pass", "tail: search+release", "tail: inversion+out (per pair)", "tail: loop"], tail):
+    print("%-32s %8.0f cycles per parked tile" % (nm, x / uses))
 print("loop time per warp id (mean cycles per launch per CTA):", np.round(per_warp[:warps] / (31.0 * 148)).astype(int).tolist())

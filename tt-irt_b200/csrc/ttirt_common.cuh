@@ -58,20 +58,21 @@ struct CellFast {
   double xk, w1, w2, dens;
 };
 __device__ __forceinline__ CellFast invert_cell_fast(double dq, double c1, double c2, double x1, double x2, double ih) {
+  // reference :146-159 with A2 = 2 Aq:  xk = (-Bq + sqrt((A2 x1 + Bq)^2 + 2 A2 dq)) / A2.  Scalar FP64 instructions
+  // are the scarce resource next to a DMMA stream (see ttirt_fast.cu), so products feed fused multiply-adds here.
   CellFast o;
-  const double Aq = __dmul_rn(__dmul_rn(0.5, __dsub_rn(c2, c1)), ih);
-  const double rA = __drcp_rn(Aq);
-  const double Bq = __dmul_rn(__dsub_rn(__dmul_rn(c1, x2), __dmul_rn(c2, x1)), ih);
-  double Dq = __dadd_rn(__dmul_rn(__dmul_rn(2.0, Aq), x1), Bq);
-  Dq = __dmul_rn(Dq, Dq);
-  Dq = __dadd_rn(Dq, __dmul_rn(__dmul_rn(4.0, Aq), dq));
+  const double A2 = __dmul_rn(__dsub_rn(c2, c1), ih);
+  const double rA = __drcp_rn(A2);
+  const double Bq = __dmul_rn(fma(c1, x2, -__dmul_rn(c2, x1)), ih);
+  const double t = fma(A2, x1, Bq);
+  const double Dq = fma(__dadd_rn(A2, A2), dq, __dmul_rn(t, t));
   const double root = __dsqrt_rn(fabs(Dq));
-  double xk = TTIRT_XK_DIV ? __ddiv_rn(__dmul_rn(0.5, __dadd_rn(-Bq, root)), Aq) : __dmul_rn(__dmul_rn(0.5, __dadd_rn(-Bq, root)), rA);
-  if (Aq == 0.0) xk = __dadd_rn(x1, __ddiv_rn(dq, Bq));
+  double xk = __dmul_rn(__dsub_rn(root, Bq), rA);
+  if ((__double_as_longlong(A2) << 1) == 0) xk = __dadd_rn(x1, __ddiv_rn(dq, Bq));   // Aq == 0.0: linear CDF
   o.xk = xk;
   o.w1 = __dmul_rn(__dsub_rn(x2, xk), ih);
   o.w2 = __dmul_rn(__dsub_rn(xk, x1), ih);
-  o.dens = fabs(__dadd_rn(__dmul_rn(c1, o.w1), __dmul_rn(c2, o.w2)));
+  o.dens = fabs(fma(c1, o.w1, __dmul_rn(c2, o.w2)));
   return o;
 }
 
@@ -79,21 +80,23 @@ __device__ __forceinline__ CellFast invert_cell_fast(double dq, double c1, doubl
 // 161-165) is carried as two running products in split form, Pn * 2^E over the densities and Pd over the masses,
 // both mantissas in [1, 2), and the one logarithm is taken after the last dimension.  Zero, infinite and NaN
 // products stay as they are and give -inf / inf / NaN as a sum of logarithms would.
+static __device__ __noinline__ int split_exponent_subnormal(double &P) {
+  P = __dmul_rn(P, 18014398509481984.0);  // 2^54
+  const int hi = __double2hiint(P);
+  const int ex = (hi >> 20) & 0x7ff;
+  P = __hiloint2double((hi & 0x800fffff) | 0x3ff00000, __double2loint(P));
+  return ex - 1023 - 54;
+}
 __device__ __forceinline__ int split_exponent(double &P) {
-  int e = 0;
-  int hi = __double2hiint(P);
-  int ex = (hi >> 20) & 0x7ff;
-  if (ex == 0 && P != 0.0) {  // subnormal: rescale before splitting
-    P = __dmul_rn(P, 18014398509481984.0);  // 2^54
-    e = -54;
-    hi = __double2hiint(P);
-    ex = (hi >> 20) & 0x7ff;
+  const int hi = __double2hiint(P);
+  const int ex = (hi >> 20) & 0x7ff;
+  if (ex == 0) {  // zero stays zero; a subnormal product is rescaled before splitting (rare: out of line)
+    if (((hi & 0x7fffffff) | __double2loint(P)) == 0) return 0;
+    return split_exponent_subnormal(P);
   }
-  if (ex != 0 && ex != 0x7ff) {
-    e += ex - 1023;
-    P = __hiloint2double((hi & 0x800fffff) | 0x3ff00000, __double2loint(P));
-  }
-  return e;
+  if (ex == 0x7ff) return 0;
+  P = __hiloint2double((hi & 0x800fffff) | 0x3ff00000, __double2loint(P));
+  return ex - 1023;
 }
 __device__ __forceinline__ void lp_accumulate(double &Pn, double &Pd, int &E, double dens, double mass) {
   Pn = __dmul_rn(Pn, dens);

@@ -24,11 +24,19 @@ namespace ttirt {
 __device__ unsigned long long g_phase_cycles[8 + 32];
 #define PT_DECL unsigned long long pt_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pt_t = clock64(); const long long pt_start = pt_t;
 #define PT_MARK(k) { const long long n_ = clock64(); pt_[k] += (unsigned long long)(n_ - pt_t); pt_t = n_; }
-#define PT_FLUSH if (lane == 0) { for (int k_ = 0; k_ < 8; k_++) atomicAdd(&g_phase_cycles[k_], pt_[k_]); atomicAdd(&g_phase_cycles[8 + warp], (unsigned long long)(clock64() - pt_start)); }
+#define PT_FLUSH if (lane == 0) { for (int k_ = 0; k_ < 8; k_++) atomicAdd(&g_phase_cycles[k_], pt_[k_]); atomicAdd(&g_phase_cycles[8 + (warp & 7)], (unsigned long long)(clock64() - pt_start)); }
+// tail warps: phases land in g_phase_cycles[24 + k].  BAR.SYNC defers its blocking to the next dependent
+// instruction, so the time waiting for a parked tile shows up in the phase after the barrier.
+#define TT_DECL unsigned long long tt_[6] = {0, 0, 0, 0, 0, 0}; long long tt_t = clock64();
+#define TT_MARK(k) { const long long n_ = clock64(); tt_[k] += (unsigned long long)(n_ - tt_t); tt_t = n_; }
+#define TT_FLUSH if (lane == 0) { for (int k_ = 0; k_ < 6; k_++) atomicAdd(&g_phase_cycles[24 + k_], tt_[k_]); }
 #else
 #define PT_DECL
 #define PT_MARK(k)
 #define PT_FLUSH
+#define TT_DECL
+#define TT_MARK(k)
+#define TT_FLUSH
 #endif
 
 namespace {
@@ -70,6 +78,28 @@ __device__ void stage_b(double *dst, const double *__restrict__ src, int K, int 
   }
 }
 
+// Trapezoid weight of grid node j (n nodes x[0..n-1]): the CDF of the piecewise-linear density with node values p is
+//   cdf_j = sum_{i<j} w_i p_i + h_{j-1} p_j,   w_i = h_{i-1} + h_i,   h_i = (x_{i+1} - x_i) / 2   (h_{-1} = 0),
+// and cdf_{n-1} (the mass) = sum_{i<n-1} w_i p_i + h_{n-2} p_{n-1}: the last node carries h_{n-2}, nodes beyond it zero.
+__device__ __forceinline__ double node_weight(const double *__restrict__ x, int j, int n) {
+  if (j >= n) return 0.0;
+  const double hl = j >= 1 ? 0.5 * (x[j] - x[j - 1]) : 0.0;
+  const double hr = j + 1 < n ? 0.5 * (x[j + 1] - x[j]) : 0.0;
+  return hl + hr;
+}
+
+// P_{k+1} with column j scaled by node_weight(j): the pdf contraction then delivers w_j p_j directly and the tail's
+// CDF pass is a plain running sum.
+__device__ void stage_p_weighted(double *dst, const double *__restrict__ src, int K, int NC, int KP, int NCP,
+                                 const double *__restrict__ x, int tid, int nthr) {
+  const int total = NCP * KP;
+  for (int e = tid; e < total; e += nthr) {
+    const int c = e / KP, a = e - c * KP;
+    const double v = (a < K && c < NC) ? __ldg(src + a + (int64_t)c * K) * node_weight(x, c, NC) : 0.0;
+    dst[b_phys(c, a, KP)] = v;
+  }
+}
+
 constexpr int MMA_WARPS = 8;    // two per SM sub-partition: they share the FP64 tensor pipe
 constexpr int TAIL_WARPS = 4;   // one per SM sub-partition: CDF, search, inversion of the tiles its two MMA warps produce
 constexpr int MT = 2;           // 8-row MMA tiles per MMA warp
@@ -95,8 +125,8 @@ struct SmemLayout {
   static constexpr int PB = NPD * RS;
   static constexpr int HS = TAIL1 ? 4 * (NT - 1) : 4 * NT;   // cells walked by each of the two lanes of a row
   static constexpr int HB = HS / 4;                // ... as four blocks of HB consecutive cells, walked side by side
-  static constexpr int NHH = 2 * HS + 8;           // half cell widths, zero beyond cell n1-2
-  static constexpr size_t bytes = sizeof(double) * (2 * SLAB + PN + MMA_WARPS * FTILE + TAIL_WARPS * PB + NHH + 2 * 8 * NT) +
+  static constexpr int NHH = 2 * HS + 8;           // entries of the per-node tables rw / hr
+  static constexpr size_t bytes = sizeof(double) * (2 * SLAB + PN + MMA_WARPS * FTILE + TAIL_WARPS * PB + 2 * NHH + 2 * 8 * NT) +
                                   sizeof(int) * (2 * (NBMAX + 1) + NBMAX + TAIL_WARPS * (WROWS + 1));
 };
 
@@ -135,8 +165,9 @@ __global__ void __launch_bounds__(NTHR, 1) transition_kernel(const TransArgs a) 
   double *Ps = slab1 + L::SLAB;
   double *ft_all = Ps + L::PN;                     // per-MMA-warp staged left-interface rows
   double *pb_all = ft_all + MMA_WARPS * L::FTILE;  // per-tail-warp parked |pdf| tile
-  double *hh = pb_all + TAIL_WARPS * L::PB;        // half grid steps of dimension k+1, zero beyond cell n1-2
-  double *xg = hh + L::NHH;                        // grid of dimension k+1
+  double *rw = pb_all + TAIL_WARPS * L::PB;        // 1 / node_weight(j) of dimension k+1's grid (0 beyond node n1-1)
+  double *hr = rw + L::NHH;                        // h_{j-1} / node_weight(j): share of node j's weight left of it
+  double *xg = hr + L::NHH;                        // grid of dimension k+1
   double *ihs = xg + 8 * NT;                       // reciprocal cell widths of dimension k+1
   int *bts = reinterpret_cast<int *>(ihs + 8 * NT);  // bin -> first CTA tile
   int *bst = bts + (L::NBMAX + 1);                    // bin -> first sorted row
@@ -155,107 +186,152 @@ __global__ void __launch_bounds__(NTHR, 1) transition_kernel(const TransArgs a) 
     bts[i] = a.bin_tile_start[i];
     bst[i] = a.bin_start[i];
   }
-  for (int i = tid; i < L::NHH; i += NTHR) hh[i] = (i + 1 < n1) ? 0.5 * (a.xnext[i + 1] - a.xnext[i]) : 0.0;
+  for (int i = tid; i < L::NHH; i += NTHR) {
+    const double w = node_weight(a.xnext, i, n1);
+    const double hl = (i >= 1 && i < n1) ? 0.5 * (a.xnext[i] - a.xnext[i - 1]) : 0.0;
+    rw[i] = w > 0.0 ? 1.0 / w : 0.0;
+    hr[i] = w > 0.0 ? hl / w : 0.0;
+  }
   for (int i = tid; i < 8 * NT; i += NTHR) {
     xg[i] = (i < n1) ? a.xnext[i] : 0.0;
     ihs[i] = (i + 1 < n1) ? 1.0 / (a.xnext[i + 1] - a.xnext[i]) : 0.0;
     if (i < L::NBMAX) hist[i] = 0;
   }
-  stage_b(Ps, a.pnext, r1, n1, r1, KP, 8 * NT, tid, NTHR);
+  stage_p_weighted(Ps, a.pnext, r1, n1, KP, 8 * NT, a.xnext, tid, NTHR);
   __syncthreads();
 
   const int total_tiles = bts[nb0];
   const int t_begin = (int)(((int64_t)blockIdx.x * total_tiles) / gridDim.x);
   const int t_end = (int)(((int64_t)(blockIdx.x + 1) * total_tiles) / gridDim.x);
 
-  if (warp >= MMA_WARPS) {
+  const bool is_tail = warp < TAIL_WARPS;   // warps 0-3: tail, 4-11: MMA (role changes at warpgroup granularity for setmaxnreg)
+  if (is_tail) {
     // =========================================== tail warps ===========================================
-    // Lanes l and l+16 share row l & 15 of the parked tile: each walks HS cells of the trapezoid CDF (reference
-    // tt_irt1_int32.c:107-113), lane l the lower half of the grid and lane l+16 the upper half.
+    // Lanes l and l+16 share row l & 15 of the parked tile, lane l the lower half of the grid and lane l+16 the upper
+    // half (reference tt_irt1_int32.c:105-165 for one sample).
+    //
+    // The MMA warps deliver v_j = w_j p_j (P_{k+1} is staged with its columns scaled by the trapezoid node weights, see
+    // node_weight()), so with R_j = sum_{i<j} |v_i|
+    //   cdf_j = R_j + (h_{j-1} / w_j) |v_j|,   R_j <= cdf_j <= R_{j+1},   mass = R_{n1},
+    // and the CDF pass is a plain running sum.  Next to a DMMA stream every instruction of another warp waits for a
+    // gap between two DMMAs (~20 cycles, whatever its type), so the tail is written for instruction count: one pass,
+    // a two-level search on integer bit patterns, one inversion per pair of tiles.
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TAIL_REGS));
-    const int tw = warp - MMA_WARPS, row = lane & 15, hf = lane >> 4;
+    const int tw = warp, row = lane & 15, hf = lane >> 4;
     const double *pbr = pb_all + tw * L::PB + row;
     const int *ids = ids_all + tw * WROWS;
-    constexpr int HS = L::HS;
+    constexpr int HS = L::HS, HB = L::HB;
     const int c0 = hf * HS, nlast = n1 - 1;
-    auto node = [&](int j) -> int { return TAIL1 ? j : min(j, nlast); };  // TAIL1: 2*HS == n1-1, never out of range
     const int uses = 2 * (t_end - t_begin);
-    constexpr int HB = L::HB;
+    // The inversion runs once per PAIR of tiles: the first tile of a pair waits in registers (st_*), then lanes 0-15
+    // finish its rows while lanes 16-31 finish the second tile's.
+    int st_nv = 0, st_m = 0, st_i0 = 0, st_E = 0;
+    double st_dq = 0.0, st_c1 = 1.0, st_c2 = 1.0, st_mass = 1.0, st_N = 1.0, st_D = 1.0;
+    TT_DECL
     for (int seq = 0; seq < uses; ++seq) {
+      TT_MARK(4)
       bar_pair_sync(2 + tw);                        // FULL: the tile of producer seq & 1 is parked
-      const int nv = nv_all[tw];
+      TT_MARK(0)
+      int nv = nv_all[tw];
+      int m = 0, i0 = 0, lpE = 0;
+      double dq = 0.0, c1 = 1.0, c2 = 1.0, mass = 1.0, lpN = 1.0, lpD = 1.0;
       if (nv == 0) {
         if (seq + 1 < uses) bar_pair_arrive(6 + 4 * ((seq + 1) & 1) + tw);
+      } else {
+        m = ids[row];
+        const double qv = a.q[m];
+        lpN = a.lp[m]; lpD = a.lpd[m];
+        lpE = a.lpe[m];
+        // running sums of this lane's half row: four independent chains (blocks of HB nodes), kept in registers
+        double Rl[4][HB];
+#pragma unroll
+        for (int c = 0; c < HB; ++c) {
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const double v = fabs(pbr[(c0 + k * HB + c) * RS]);   // nodes beyond n1-1 are parked as zeros
+            Rl[k][c] = c ? Rl[k][c - 1] + v : v;
+          }
+        }
+        TT_MARK(1)
+        const double th = (Rl[0][HB - 1] + Rl[1][HB - 1]) + (Rl[2][HB - 1] + Rl[3][HB - 1]);
+        const double ot = __shfl_xor_sync(FULL, th, 16);
+        const double tot0 = hf ? ot : th, tot1 = hf ? th : ot;
+        // mass of the row's conditional (reference :107-113, cdf[n-1]); TAIL1: the last node sits outside the two halves
+        const double total = TAIL1 ? (tot0 + tot1) + fabs(pbr[nlast * RS]) : tot0 + tot1;
+        const double qt = qv * total;                // q > cdf/mass  <=>  q*mass > cdf (unnormalised compare)
+        // search (reference :134-142), first on R: js = last node <= n1-2 with R_js < q*mass.  Two levels: the block of
+        // this lane's half row whose first node is still below, then the node inside it.  Non-negative doubles order
+        // like their bit patterns, so the inner compares are integer ones.
+        double base[4];
+        base[0] = hf ? tot0 : 0.0;
+#pragma unroll
+        for (int k = 1; k < 4; k++) base[k] = base[k - 1] + Rl[k - 1][HB - 1];
+        int ks = 0;
+#pragma unroll
+        for (int k = 1; k < 4; k++) ks += (qt > base[k] && (TAIL1 || c0 + k * HB <= n1 - 2)) ? 1 : 0;
+        const bool k1 = ks & 1, k2 = ks & 2;
+        const double bsel = k2 ? (k1 ? base[3] : base[2]) : (k1 ? base[1] : base[0]);
+        const double qk = qt - bsel;                 // q*mass - R at the block's first node
+        const long long qb = __double_as_longlong(qk);
+        int cs = (qb > 0 && (TAIL1 || c0 + ks * HB <= n1 - 2)) ? 1 : 0;   // the block's first node itself
+        double Rsel = 0.0;
+#pragma unroll
+        for (int c = 1; c < HB; ++c) {
+          const double Rc = k2 ? (k1 ? Rl[3][c - 1] : Rl[2][c - 1]) : (k1 ? Rl[1][c - 1] : Rl[0][c - 1]);   // R - base at node c of the block
+          const bool below = qb > __double_as_longlong(Rc) && (TAIL1 || c0 + ks * HB + c <= n1 - 2);
+          if (below) { cs = c + 1; Rsel = Rc; }
+        }
+        int js = cs > 0 ? c0 + ks * HB + cs - 1 : -1;
+        double dR = qk - Rsel;                       // q*mass - R_js
+        {
+          const int js_o = __shfl_xor_sync(FULL, js, 16);
+          const double dR_o = __shfl_xor_sync(FULL, dR, 16);
+          const int js_hi = hf ? js : js_o, js_lo = hf ? js_o : js;
+          const double dR_hi = hf ? dR : dR_o, dR_lo = hf ? dR_o : dR;
+          js = js_hi >= 0 ? js_hi : js_lo;
+          dR = js_hi >= 0 ? dR_hi : dR_lo;
+        }
+        // nodes before js are below q, nodes after it are not; js itself is decided by its own CDF value
+        if (js < 1) {
+          i0 = 0; dq = qt;                           // cdf_0 = 0
+          c1 = fabs(pbr[0]) * rw[0]; c2 = fabs(pbr[RS]) * rw[1];
+        } else {
+          const double vB = fabs(pbr[(js - 1) * RS]), vA = fabs(pbr[js * RS]), vC = fabs(pbr[(js + 1) * RS]);
+          const double dA = fma(-hr[js], vA, dR);                  // q*mass - cdf_js
+          if (__double_as_longlong(dA) > 0) {
+            i0 = js; dq = dA; c1 = vA * rw[js]; c2 = vC * rw[js + 1];
+          } else {
+            i0 = js - 1; c1 = vB * rw[js - 1]; c2 = vA * rw[js];
+            dq = fma(1.0 - hr[js - 1], vB, dR);                    // q*mass - cdf_{js-1} = dR + (w_{js-1} - h_{js-2}) p_{js-1}
+          }
+        }
+        const double s2 = pow2_scale(total);         // exact power-of-two normalisation instead of 1/mass
+        c1 *= s2; c2 *= s2;                          // (consumes the loads before the buffer is handed back)
+        if (seq + 1 < uses) bar_pair_arrive(6 + 4 * ((seq + 1) & 1) + tw);   // EMPTY: the other producer may park its tile
+        dq *= s2;
+        mass = total * s2;
+        if (total == 0.0) {
+          // zero-mass conditional: uniform in index space (reference tt_irt1_int32.c:116-125)
+          const double u = 1.0 / (double)(n1 - 1);
+          const double sf = 1.0 / ((double)(n1 - 1) * u);
+          int k0 = 0;
+          for (int j = 1; j <= n1 - 2; j++) k0 += (qv > ((double)j * u) * sf) ? 1 : 0;
+          i0 = k0; dq = qv - ((double)k0 * u) * sf; c1 = u * sf; c2 = u * sf; mass = 1.0;
+        }
+      }
+      TT_MARK(2)
+      if ((seq & 1) == 0) {
+        st_nv = nv; st_m = m; st_i0 = i0; st_E = lpE;
+        st_dq = dq; st_c1 = c1; st_c2 = c2; st_mass = mass; st_N = lpN; st_D = lpD;
         continue;
       }
-      const int m = ids[row];
-      const double qv = a.q[m];
-      double lpN = a.lp[m], lpD = a.lpd[m];
-      int lpE = a.lpe[m];
-      // one pass over the parked |pdf|: local trapezoid prefix of each of this lane's four blocks of cells (four
-      // independent chains), kept in registers.  FP64 instructions are what the tail competes with the DMMA
-      // stream for, so everything after this pass that can be done on integer bit patterns is.
-      double Lp[4][HB];
-#pragma unroll
-      for (int c = 0; c < HB; ++c) {
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const int nd = c0 + k * HB + c;
-          const double s2n = fabs(pbr[node(nd) * RS]) + fabs(pbr[node(nd + 1) * RS]);
-          Lp[k][c] = fma(hh[nd], s2n, c ? Lp[k][c - 1] : 0.0);
-        }
-      }
-      const double th = (Lp[0][HB - 1] + Lp[1][HB - 1]) + (Lp[2][HB - 1] + Lp[3][HB - 1]);
-      const double ot = __shfl_xor_sync(FULL, th, 16);
-      const double tot0 = hf ? ot : th, tot1 = hf ? th : ot;
-      const double total = tot0 + tot1;            // mass of the row's conditional (reference :107-113, cdf[n-1])
-      const double qt = qv * total;                // q > cdf/mass  <=>  q*mass > cdf (unnormalised compare)
-      // search (reference :134-142): last node 1 <= nd <= n1-2 whose CDF is below q.  The CDF at node nd of block k is
-      // base_k + Lp[k][c-1]; non-negative doubles order like their bit patterns, so the 64 compares are integer ones.
-      int il = -1;
-      double qsel = qt, Lsel = 0.0;
-      {
-        double base = hf ? tot0 : 0.0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const double qk = qt - base;
-          const long long qb = __double_as_longlong(qk);
-#pragma unroll
-          for (int c = 0; c < HB; ++c) {
-            const int nd = c0 + k * HB + c;
-            const double Lprev = c ? Lp[k][c - 1] : 0.0;
-            bool below = qb > __double_as_longlong(Lprev);
-            if (TAIL1) { if (k == 0 && c == 0) below = below && hf; }   // node 0 is no candidate; 2*HS - 1 == n1 - 2
-            else below = below && nd >= 1 && nd <= n1 - 2;
-            if (below) { il = nd; qsel = qk; Lsel = Lprev; }
-          }
-          base += Lp[k][HB - 1];
-        }
-      }
-      double dq = qsel - Lsel;                     // q*mass - cdf at the chosen node
-      const int il_o = __shfl_xor_sync(FULL, il, 16);
-      const double dq_o = __shfl_xor_sync(FULL, dq, 16);
-      const int il_hi = hf ? il : il_o, il_lo = hf ? il_o : il;
-      const double dq_hi = hf ? dq : dq_o, dq_lo = hf ? dq_o : dq;
-      int i0 = il_hi >= 0 ? il_hi : (il_lo >= 0 ? il_lo : 0);
-      dq = il_hi >= 0 ? dq_hi : (il_lo >= 0 ? dq_lo : qt);
-      const double s2 = pow2_scale(total);         // exact power-of-two normalisation instead of 1/mass
-      double c1 = fabs(pbr[i0 * RS]) * s2, c2 = fabs(pbr[(i0 + 1) * RS]) * s2;   // (consumes the loads before the buffer is handed back)
-      if (seq + 1 < uses) bar_pair_arrive(6 + 4 * ((seq + 1) & 1) + tw);   // EMPTY: the other producer may park its tile
-      dq *= s2;
-      double mass = total * s2;
-
-      if (total == 0.0) {
-        // zero-mass conditional: uniform in index space (reference tt_irt1_int32.c:116-125)
-        const double u = 1.0 / (double)(n1 - 1);
-        const double sf = 1.0 / ((double)(n1 - 1) * u);
-        int k0 = 0;
-        for (int j = 1; j <= n1 - 2; j++) k0 += (qv > ((double)j * u) * sf) ? 1 : 0;
-        i0 = k0; dq = qv - ((double)k0 * u) * sf; c1 = u * sf; c2 = u * sf; mass = 1.0;
+      if (hf == 0) {
+        nv = st_nv; m = st_m; i0 = st_i0; lpE = st_E;
+        dq = st_dq; c1 = st_c1; c2 = st_c2; mass = st_mass; lpN = st_N; lpD = st_D;
       }
       const CellFast o = invert_cell_fast(dq, c1, c2, xg[i0], xg[i0 + 1], ihs[i0]);
       lp_accumulate(lpN, lpD, lpE, o.dens, mass);
-      if (hf == 0 && row < nv) {
+      if (row < nv) {
         a.z[m] = o.xk;
         if (a.idx_out) a.idx_out[m] = i0;
         if (!a.last) {
@@ -266,13 +342,17 @@ __global__ void __launch_bounds__(NTHR, 1) transition_kernel(const TransArgs a) 
           a.lpz[m] = lp_finish(lpN, lpD, lpE);
         }
       }
+      TT_MARK(3)
     }
+    TT_FLUSH
   } else {
     // =========================================== MMA warps ============================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(MMA_REGS));
     const int g = lane >> 2, t = lane & 3;
-    const int tw = warp & (TAIL_WARPS - 1), prod = warp / TAIL_WARPS;  // tail warp served; first / second producer of its buffer
-    double *ft = ft_all + warp * L::FTILE;
+    const int mw = warp - TAIL_WARPS;          // index among the MMA warps
+    const int mtid = 32 * mw + lane;
+    const int tw = mw & (TAIL_WARPS - 1), prod = mw / TAIL_WARPS;  // tail warp served (same SM sub-partition); first / second producer of its buffer
+    double *ft = ft_all + mw * L::FTILE;
     double *pbw = pb_all + tw * L::PB;
     const int ks0 = EXACT ? RT : (r0 + 7) >> 3, rt_act = EXACT ? RT : (r1 + 7) >> 3, nt_act = EXACT ? NT : (n1 + 7) >> 3;
     const uint32_t row_bytes = (uint32_t)(8 * ks0) * 8u;   // bytes of a left-interface row that the update reads
@@ -287,7 +367,7 @@ __global__ void __launch_bounds__(NTHR, 1) transition_kernel(const TransArgs a) 
     auto rows_of = [&](int tile, int &nv) -> int {
       if (tile >= t_end) { nv = 0; return 0; }
       while (tile >= bts[bh + 1]) ++bh;
-      const int row0 = bst[bh] + (tile - bts[bh]) * ROWS_CTA + warp * WROWS;
+      const int row0 = bst[bh] + (tile - bts[bh]) * ROWS_CTA + mw * WROWS;
       nv = max(0, min(WROWS, bst[bh + 1] - row0));
       return row0;
     };
@@ -349,16 +429,16 @@ __global__ void __launch_bounds__(NTHR, 1) transition_kernel(const TransArgs a) 
         bar_mma_warps();  // every MMA warp is done with the previous bin's slabs
         constexpr int NM = 32 * MMA_WARPS;
         if (cur0 == b) {
-          stage_b(slab1, a.core + (int64_t)(b + 1) * r0, r0, r1, slab_cs, KP, 8 * RT, tid, NM); cur1 = b + 1;
+          stage_b(slab1, a.core + (int64_t)(b + 1) * r0, r0, r1, slab_cs, KP, 8 * RT, mtid, NM); cur1 = b + 1;
         } else if (cur1 == b) {
-          stage_b(slab0, a.core + (int64_t)(b + 1) * r0, r0, r1, slab_cs, KP, 8 * RT, tid, NM); cur0 = b + 1;
+          stage_b(slab0, a.core + (int64_t)(b + 1) * r0, r0, r1, slab_cs, KP, 8 * RT, mtid, NM); cur0 = b + 1;
         } else if (cur0 == b + 1) {
-          stage_b(slab1, a.core + (int64_t)b * r0, r0, r1, slab_cs, KP, 8 * RT, tid, NM); cur1 = b;
+          stage_b(slab1, a.core + (int64_t)b * r0, r0, r1, slab_cs, KP, 8 * RT, mtid, NM); cur1 = b;
         } else if (cur1 == b + 1) {
-          stage_b(slab0, a.core + (int64_t)b * r0, r0, r1, slab_cs, KP, 8 * RT, tid, NM); cur0 = b;
+          stage_b(slab0, a.core + (int64_t)b * r0, r0, r1, slab_cs, KP, 8 * RT, mtid, NM); cur0 = b;
         } else {
-          stage_b(slab0, a.core + (int64_t)b * r0, r0, r1, slab_cs, KP, 8 * RT, tid, NM); cur0 = b;
-          stage_b(slab1, a.core + (int64_t)(b + 1) * r0, r0, r1, slab_cs, KP, 8 * RT, tid, NM); cur1 = b + 1;
+          stage_b(slab0, a.core + (int64_t)b * r0, r0, r1, slab_cs, KP, 8 * RT, mtid, NM); cur0 = b;
+          stage_b(slab1, a.core + (int64_t)(b + 1) * r0, r0, r1, slab_cs, KP, 8 * RT, mtid, NM); cur1 = b + 1;
         }
         bar_mma_warps();
         if (cur0 == b) { sl_lo = slab0; sl_hi = slab1; } else { sl_lo = slab1; sl_hi = slab0; }
