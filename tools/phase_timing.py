@@ -36,3 +36,13 @@ uses = 31.0 * M / 16           # parked tiles per call
 for nm, x in zip(["tail: wait FULL", "tail: pass", "tail: search+release", "tail: inversion+out (per pair)", "tail: loop"], tail):
     print("%-32s %8.0f cycles per parked tile" % (nm, x / uses))
 print("loop time per warp id (mean cycles per launch per CTA):", np.round(per_warp[:warps] / (31.0 * 148)).astype(int).tolist())
+
+# timeline of the two MMA warps of sub-partition 0 of CTA 0 (last launch): clock at the end of every phase
+tr = (ctypes.c_longlong * (2 * 24 * 8))()
+lib.ttirt_debug_trace(tr)
+t = np.array(list(tr), dtype=np.int64).reshape(2, 24, 8)
+t0 = t[t > 0].min()
+order = [7, 0, 1, 2, 3, 4, 5, 6]   # loop top, slab/bin done, rows arrived, update done, gather issued, pdf done, buffer free, parked
+print("timeline (cycles since first mark): tile | producer 0: top slab rows upd issue pdf free parked | producer 1: same")
+for i in range(2, 14):
+    print("%2d | %s | %s" % (i, " ".join("%7d" % (t[0, i, k] - t0) for k in order), " ".join("%7d" % (t[1, i, k] - t0) for k in order)))

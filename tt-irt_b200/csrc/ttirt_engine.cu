@@ -741,7 +741,8 @@ extern "C" int ttirt_profile_read(ttirt_model *md, double *ms_total, int64_t *la
 }
 
 #ifdef TTIRT_PHASE_TIMING
-namespace ttirt { void phase_cycles_read(unsigned long long *out); }
+namespace ttirt { void phase_cycles_read(unsigned long long *out); void trace_read(long long *out); }
+extern "C" __attribute__((visibility("default"))) void ttirt_debug_trace(long long *out) { cudaDeviceSynchronize(); ttirt::trace_read(out); }
 extern "C" __attribute__((visibility("default"))) void ttirt_debug_phase_cycles(unsigned long long *out) { cudaDeviceSynchronize(); ttirt::phase_cycles_read(out); }
 #endif
 

@@ -22,8 +22,10 @@ namespace ttirt {
 
 #ifdef TTIRT_PHASE_TIMING
 __device__ unsigned long long g_phase_cycles[8 + 32];
+__device__ long long g_trace[2 * 24 * 8];   // CTA 0, the two MMA warps of sub-partition 0: clock at every PT_MARK of the first 24 tiles
 #define PT_DECL unsigned long long pt_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pt_t = clock64(); const long long pt_start = pt_t;
-#define PT_MARK(k) { const long long n_ = clock64(); pt_[k] += (unsigned long long)(n_ - pt_t); pt_t = n_; }
+#define PT_MARK(k) { const long long n_ = clock64(); pt_[k] += (unsigned long long)(n_ - pt_t); pt_t = n_; \
+  if (blockIdx.x == 0 && lane == 0 && tw == 0 && tile - t_begin < 24) g_trace[(prod * 24 + (tile - t_begin)) * 8 + (k)] = n_; }
 #define PT_FLUSH if (lane == 0) { for (int k_ = 0; k_ < 8; k_++) atomicAdd(&g_phase_cycles[k_], pt_[k_]); atomicAdd(&g_phase_cycles[8 + (warp & 7)], (unsigned long long)(clock64() - pt_start)); }
 // tail warps: phases land in g_phase_cycles[24 + k].  BAR.SYNC defers its blocking to the next dependent
 // instruction, so the time waiting for a parked tile shows up in the phase after the barrier.
@@ -100,12 +102,16 @@ __device__ void stage_p_weighted(double *dst, const double *__restrict__ src, in
   }
 }
 
-constexpr int MMA_WARPS = 8;    // two per SM sub-partition: they share the FP64 tensor pipe
+#ifndef TTIRT_MMA_WARPS
+#define TTIRT_MMA_WARPS 8
+#endif
+constexpr int MMA_WARPS = TTIRT_MMA_WARPS;    // two per SM sub-partition: they share the FP64 tensor pipe (4: experiment, one per sub-partition)
 constexpr int TAIL_WARPS = 4;   // one per SM sub-partition: CDF, search, inversion of the tiles its two MMA warps produce
 constexpr int MT = 2;           // 8-row MMA tiles per MMA warp
 constexpr int WROWS = 8 * MT;   // samples per warp tile
 constexpr int NTHR = 32 * (MMA_WARPS + TAIL_WARPS);
 constexpr int ROWS_CTA = MMA_WARPS * WROWS;
+constexpr int PRODS = MMA_WARPS / TAIL_WARPS;   // producers per tile buffer
 // register file split (setmaxnreg, per warpgroup of four warps): launched at 168 per thread, the tail warpgroup
 // shrinks to TAIL_REGS and the two MMA warpgroups grow to MMA_REGS; 32 * (8 * 192 + 4 * 120) = 32 * 12 * 168: the pool is exactly what the launch allocated
 constexpr int MMA_REGS = 192, TAIL_REGS = 120;
@@ -216,13 +222,13 @@ __global__ void __launch_bounds__(NTHR, 1) transition_kernel(const TransArgs a) 
     // and the CDF pass is a plain running sum.  Next to a DMMA stream every instruction of another warp waits for a
     // gap between two DMMAs (~20 cycles, whatever its type), so the tail is written for instruction count: one pass,
     // a two-level search on integer bit patterns, one inversion per pair of tiles.
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TAIL_REGS));
+    if (NTHR > 256) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TAIL_REGS));
     const int tw = warp, row = lane & 15, hf = lane >> 4;
     const double *pbr = pb_all + tw * L::PB + row;
     const int *ids = ids_all + tw * WROWS;
     constexpr int HS = L::HS, HB = L::HB;
     const int c0 = hf * HS, nlast = n1 - 1;
-    const int uses = 2 * (t_end - t_begin);
+    const int uses = PRODS * (t_end - t_begin);
     // The inversion runs once per PAIR of tiles: the first tile of a pair waits in registers (st_*), then lanes 0-15
     // finish its rows while lanes 16-31 finish the second tile's.
     int st_nv = 0, st_m = 0, st_i0 = 0, st_E = 0;
@@ -236,7 +242,7 @@ __global__ void __launch_bounds__(NTHR, 1) transition_kernel(const TransArgs a) 
       int m = 0, i0 = 0, lpE = 0;
       double dq = 0.0, c1 = 1.0, c2 = 1.0, mass = 1.0, lpN = 1.0, lpD = 1.0;
       if (nv == 0) {
-        if (seq + 1 < uses) bar_pair_arrive(6 + 4 * ((seq + 1) & 1) + tw);
+        if (seq + 1 < uses) bar_pair_arrive(6 + 4 * ((seq + 1) % PRODS) + tw);
       } else {
         m = ids[row];
         const double qv = a.q[m];
@@ -307,7 +313,7 @@ __global__ void __launch_bounds__(NTHR, 1) transition_kernel(const TransArgs a) 
         }
         const double s2 = pow2_scale(total);         // exact power-of-two normalisation instead of 1/mass
         c1 *= s2; c2 *= s2;                          // (consumes the loads before the buffer is handed back)
-        if (seq + 1 < uses) bar_pair_arrive(6 + 4 * ((seq + 1) & 1) + tw);   // EMPTY: the other producer may park its tile
+        if (seq + 1 < uses) bar_pair_arrive(6 + 4 * ((seq + 1) % PRODS) + tw);   // EMPTY: the other producer may park its tile
         dq *= s2;
         mass = total * s2;
         if (total == 0.0) {
@@ -347,7 +353,7 @@ __global__ void __launch_bounds__(NTHR, 1) transition_kernel(const TransArgs a) 
     TT_FLUSH
   } else {
     // =========================================== MMA warps ============================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(MMA_REGS));
+    if (NTHR > 256) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(MMA_REGS));
     const int g = lane >> 2, t = lane & 3;
     const int mw = warp - TAIL_WARPS;          // index among the MMA warps
     const int mtid = 32 * mw + lane;
@@ -554,7 +560,7 @@ __global__ void __launch_bounds__(NTHR, 1) transition_kernel(const TransArgs a) 
       // ---- (3) park the signed pdf tile for the tail warp (it takes |.|, reference :105); the two producers of a buffer alternate ----
       {
         // producer 0 waits for the tail warp to have released producer 1's previous tile, and vice versa
-        if (prod == 1 || tile > t_begin) bar_pair_sync(6 + 4 * prod + tw);
+        if (prod > 0 || tile > t_begin) bar_pair_sync(6 + 4 * prod + tw);
         PT_MARK(5)
         if (nvalid > 0) {
 #pragma unroll
@@ -645,6 +651,7 @@ cudaError_t launch_transition(int cls, const TransArgs &a, int sm_count, cudaStr
 }
 
 #ifdef TTIRT_PHASE_TIMING
+void trace_read(long long *out) { cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * 2 * 24 * 8); }
 void phase_cycles_read(unsigned long long *out) {
   cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(unsigned long long) * 40);
   unsigned long long z[40] = {0};
