@@ -305,7 +305,8 @@ def main():
     peak, peak_src = measured_fp64_peak()
     ach = (k_flops / (k_ms * 1e-3)) / 1e12 if k_ms > 0 else 0.0
     roofline = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
-                "traffic": None, "kernel": "ttirt::transition_kernel<8,9,8> (FP64 DMMA mma.sync.m8n8k4)",
+                "traffic": _ncu_traffic(M), "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                "kernel": "ttirt::transition_kernel<RT,NT,EXACT,TAIL1> (FP64 DMMA mma.sync.m8n8k4; 8 MMA warps + 4 tail warps per CTA)",
                 "kernel_launches_timed": k_launches, "kernel_avg_ms": k_ms / max(1, k_launches),
                 "kernel_share_of_step": k_ms / ms if ms > 0 else None,
                 "flops_per_launch": k_flops / max(1, k_launches),
@@ -323,6 +324,18 @@ def main():
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+def _ncu_traffic(M):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (same chunk size), else None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
+            j = json.load(f)
+        if min(M, 1 << 20) == int(j["rows_per_launch"]):
+            return int(j["dram_bytes_read"]) + int(j["dram_bytes_write"])
+    except Exception:
+        pass
+    return None
 
 
 def _hbm_peak():

@@ -1,0 +1,413 @@
+// The steps either side of tt_irt1, on the device:
+//
+//   seeds      rank-1 lattice with random shift        reference matlab/samplers/qmcnodes.m:6-13
+//              uniform pseudo-random (Philox4x32-10)   reference rand / np.random.random (test_shock_absorber_tt.py:147)
+//              truncated-normal reference map          reference matlab/samplers/randref.m:22-34
+//   consumers  importance weights and their statistics reference matlab/samplers/iw_prune.m:19-29
+//              N / ESS                                 reference matlab/samplers/essinv.m:12-14
+//              Hellinger distance                      reference matlab/samplers/hellinger.m:12-16
+//              independence Metropolis-Hastings prune  reference matlab/samplers/mcmc_prune.m:24-43,
+//                                                                python/test_shock_absorber_tt.py:165-171
+//
+// All of it is HBM-bound streaming or a short sequential chain; none of it is reshaped into tensor-core work.
+// No CPU fallback: without a device every entry point fails.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "../../include/tt_irt1.h"
+#include "ttirt_common.cuh"
+
+namespace ttirt {
+int aux_fail(const char *fmt, ...);   // defined in ttirt_engine.cu: records the thread's last error
+void aux_launched();                  // bumps the library's kernel-launch counter
+}  // namespace ttirt
+using ttirt::aux_fail;
+
+#define CKA(call)                                                                          \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess) return aux_fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// seeds
+// ------------------------------------------------------------------------------------------------
+// qmcnodes.m:6-13:  Y = (0:N-1)/N;  Y = z(1:d) * Y;  Y = Y + Delta;  Y = Y - floor(Y).
+// m/N is exact for N a power of two and z*m/N is exact below 2^53, so the only rounding is the shift's:
+// bit-exact against the reference arithmetic.
+__global__ void lattice_kernel(int d, int64_t M, int64_t m0, double inv_n, const double *__restrict__ z,
+                               const double *__restrict__ shift, double *q, int64_t ldq) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y;
+  if (m >= M || k >= d) return;
+  const double y = __dmul_rn((double)(m0 + m), inv_n);
+  const double t = __dadd_rn(__dmul_rn(z[k], y), shift[k]);
+  q[m + ldq * k] = __dsub_rn(t, floor(t));
+}
+
+// Philox4x32-10 (Salmon, Moraes, Dror, Shaw 2011): counter-based, so any shard of the sample range can be
+// generated independently.  Counter = (sample index lo, hi, dimension, 0), key = seed.
+__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+
+// u = (53 high bits of the first 64 output bits) * 2^-53, in [0, 1)
+__global__ void uniform_kernel(int d, int64_t M, int64_t m0, uint64_t seed, double *q, int64_t ldq) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y;
+  if (m >= M || k >= d) return;
+  const uint64_t idx = (uint64_t)(m0 + m);
+  uint32_t c[4] = {(uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)k, 0u};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const uint64_t bits = ((uint64_t)c[1] << 32) | c[0];
+  q[m + ldq * k] = (double)(bits >> 11) * 1.1102230246251565e-16;  // 2^-53
+}
+
+// randref.m:31-33:  cdf_ifactor = erf(sigma/sqrt(2))/0.5;  y = erfinv((u-0.5)*cdf_ifactor)*sqrt(2)
+__global__ void truncnormal_kernel(int64_t n, double cdf_ifactor, const double *__restrict__ u, double *y) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  y[i] = erfinv((u[i] - 0.5) * cdf_ifactor) * 1.4142135623730951;
+}
+
+// ------------------------------------------------------------------------------------------------
+// consumers: importance-weight statistics
+// ------------------------------------------------------------------------------------------------
+// Deterministic two-level reductions: every block reduces a fixed slice in a fixed tree, a last single block
+// reduces the block partials in index order.  Results do not depend on scheduling.
+constexpr int RB = 256;     // threads per reduction block
+constexpr int RG = 1024;    // reduction blocks
+
+__device__ __forceinline__ double block_sum(double v, double *sh) {
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  for (int s = RB / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  const double r = sh[0];
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ double block_max(double v, double *sh) {
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  for (int s = RB / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + s]);
+    __syncthreads();
+  }
+  const double r = sh[0];
+  __syncthreads();
+  return r;
+}
+
+// pass 1: max of dF = lFex - lFapp  (essinv.m:13, hellinger.m:13)
+__global__ void iw_max_kernel(int64_t M, const double *__restrict__ lfex, const double *__restrict__ lfapp, double *part) {
+  __shared__ double sh[RB];
+  double v = -INFINITY;
+  for (int64_t i = (int64_t)blockIdx.x * RB + threadIdx.x; i < M; i += (int64_t)RG * RB) v = fmax(v, lfex[i] - lfapp[i]);
+  const double r = block_max(v, sh);
+  if (threadIdx.x == 0) part[blockIdx.x] = r;
+}
+__global__ void iw_max_final_kernel(const double *part, double *out) {
+  __shared__ double sh[RB];
+  double v = -INFINITY;
+  for (int i = threadIdx.x; i < RG; i += RB) v = fmax(v, part[i]);
+  const double r = block_max(v, sh);
+  if (threadIdx.x == 0) out[0] = r;
+}
+
+// pass 2: sums of exp(dF) [iw_prune.m:19-20], exp(dF - max), exp(2 (dF - max)) [essinv.m:14], and the max of exp(dF)
+__global__ void iw_sums_kernel(int64_t M, const double *__restrict__ lfex, const double *__restrict__ lfapp,
+                               const double *dmax, double *part) {
+  __shared__ double sh[RB];
+  const double mx = dmax[0];
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * RB + threadIdx.x; i < M; i += (int64_t)RG * RB) {
+    const double dF = lfex[i] - lfapp[i];
+    s0 += exp(dF);
+    const double e = exp(dF - mx);
+    s1 += e;
+    s2 += exp((dF - mx) * 2.0);
+  }
+  const double r0 = block_sum(s0, sh), r1 = block_sum(s1, sh), r2 = block_sum(s2, sh);
+  if (threadIdx.x == 0) { part[blockIdx.x] = r0; part[RG + blockIdx.x] = r1; part[2 * RG + blockIdx.x] = r2; }
+}
+// sums[j] = sum of part[j*RG .. j*RG+RG) for nsum streams
+__global__ void iw_sums_final_kernel(const double *part, int nsum, double *sums) {
+  __shared__ double sh[RB];
+  for (int j = 0; j < nsum; j++) {
+    double v = 0.0;
+    for (int i = threadIdx.x; i < RG; i += RB) v += part[j * RG + i];
+    const double r = block_sum(v, sh);
+    if (threadIdx.x == 0) sums[j] = r;
+  }
+}
+
+// pass 3: with renorm = mean(exp(dF)) and lZex = log(mean(exp(dF - max))) known:
+//   weights w = exp(dF)/renorm                              (iw_prune.m:19-21)
+//   sum (w - 1)^2                                           (iw_prune.m:29)
+//   sum |exp(lFex - log renorm) - exp(lFapp)| / exp(lFapp)  (iw_prune.m:26)
+//   sum (exp(0.5 (dF - max - lZex)) - 1)^2                  (hellinger.m:15)
+__global__ void iw_pass3_kernel(int64_t M, const double *__restrict__ lfex, const double *__restrict__ lfapp, double renorm,
+                                double log_renorm, double mx, double lzex, double *weights, double *part) {
+  __shared__ double sh[RB];
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * RB + threadIdx.x; i < M; i += (int64_t)RG * RB) {
+    const double fe = lfex[i], fa = lfapp[i];
+    const double w = exp(fe - fa) / renorm;
+    if (weights) weights[i] = w;
+    s0 += (w - 1.0) * (w - 1.0);
+    const double ea = exp(fa);
+    s1 += fabs(exp(fe - log_renorm) - ea) / ea;
+    const double h = exp(0.5 * ((fe - fa) - mx - lzex)) - 1.0;
+    s2 += h * h;
+  }
+  const double r0 = block_sum(s0, sh), r1 = block_sum(s1, sh), r2 = block_sum(s2, sh);
+  if (threadIdx.x == 0) { part[blockIdx.x] = r0; part[RG + blockIdx.x] = r1; part[2 * RG + blockIdx.x] = r2; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// consumers: independence Metropolis-Hastings prune (mcmc_prune.m:24-43)
+// ------------------------------------------------------------------------------------------------
+// The chain is sequential in the index of the last ACCEPTED sample c: proposal i+1 is accepted iff
+//   exp(((lFex(i+1) - lFex(c)) - lFapp(i+1)) + lFapp(c)) >= u(i)          (reference rounding order, :25-27)
+// A warp evaluates 32 consecutive proposals against the current c at once; everything before the first accepted
+// lane is a rejection under that same c, so one ballot advances the chain by a whole run.  One warp, one chain:
+// the work is latency, not bandwidth (M = 2^20 takes a few milliseconds; the reference is a scalar interpreter loop).
+// src[i] = index of the sample that occupies position i after pruning.
+__global__ void mcmc_prune_kernel(int64_t M, const double *__restrict__ lfex, const double *__restrict__ lfapp,
+                                  const double *__restrict__ u, int32_t *src, unsigned long long *counters,
+                                  unsigned long long *rej_hist, int rej_hist_len) {
+  const int lane = threadIdx.x;
+  const unsigned FULL = 0xffffffffu;
+  int64_t c = 0;                       // last accepted sample
+  double fe_c = lfex[0], fa_c = lfapp[0];
+  if (lane == 0) src[0] = 0;
+  unsigned long long rejects = 0;
+  int64_t rej_seq = 0;
+  int64_t i = 0;                       // next step: proposal i+1 against u[i]
+  while (i < M - 1) {
+    const int64_t p = i + 1 + lane;    // this lane's proposal
+    bool acc = false;
+    if (p < M) {
+      double al = __dsub_rn(lfex[p], fe_c);
+      al = __dsub_rn(al, lfapp[p]);
+      al = __dadd_rn(al, fa_c);
+      acc = !(exp(al) < u[p - 1]);
+    }
+    const unsigned mask = __ballot_sync(FULL, acc);
+    const int64_t left = M - 1 - i;    // steps still to do
+    const int span = left < 32 ? (int)left : 32;
+    const int first = mask ? __ffs(mask) - 1 : 32;
+    if (first >= span) {
+      // the whole window is rejected: positions i+1 .. i+span carry c
+      if (lane < span) src[i + 1 + lane] = (int32_t)c;
+      rejects += span; rej_seq += span; i += span;
+    } else {
+      if (lane < first) src[i + 1 + lane] = (int32_t)c;
+      rejects += first; rej_seq += first;
+      c = i + 1 + first;
+      if (lane == 0) {
+        src[c] = (int32_t)c;
+        if (rej_seq > 0 && rej_hist_len > 0) {
+          const int64_t b = rej_seq <= rej_hist_len ? rej_seq : rej_hist_len;   // runs beyond the table land in its last bin
+          rej_hist[b - 1] += 1;
+        }
+      }
+      rej_seq = 0;
+      fe_c = lfex[c]; fa_c = lfapp[c];
+      i = c;
+    }
+  }
+  if (lane == 0) { counters[0] = rejects; }
+}
+
+// host-side helpers ---------------------------------------------------------------------------------
+struct DevBuf {
+  void *p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  int alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1) == cudaSuccess ? 0 : -1; }
+  template <class T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+int need_device() {
+  if (ttirt_device_count() <= 0) return aux_fail("no CUDA device available (this library has no CPU fallback)");
+  return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C-ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" int ttirt_seeds_lattice_device(int64_t d, int64_t M, int64_t m0, int64_t N, const double *d_genvec,
+                                          const double *d_shift, double *d_q, int64_t ldq, void *stream) {
+  if (d < 1 || M < 0 || N < 1 || ldq < M || !d_genvec || !d_shift || (M > 0 && !d_q)) return aux_fail("bad arguments to ttirt_seeds_lattice_device");
+  if (M == 0) return 0;
+  const dim3 grid((unsigned)((M + 255) / 256), (unsigned)d);
+  lattice_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((int)d, M, m0, 1.0 / (double)N, d_genvec, d_shift, d_q, ldq);
+  ttirt::aux_launched();
+  CKA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ttirt_seeds_uniform_device(int64_t d, int64_t M, int64_t m0, uint64_t seed, double *d_q, int64_t ldq, void *stream) {
+  if (d < 1 || M < 0 || ldq < M || (M > 0 && !d_q)) return aux_fail("bad arguments to ttirt_seeds_uniform_device");
+  if (M == 0) return 0;
+  const dim3 grid((unsigned)((M + 255) / 256), (unsigned)d);
+  uniform_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((int)d, M, m0, seed, d_q, ldq);
+  ttirt::aux_launched();
+  CKA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ttirt_truncnormal_map_device(int64_t n, double sigma, const double *d_u, double *d_y, void *stream) {
+  if (n < 0 || !(sigma > 0.0) || (n > 0 && (!d_u || !d_y))) return aux_fail("bad arguments to ttirt_truncnormal_map_device");
+  if (n == 0) return 0;
+  const double cdf_ifactor = erf(sigma / sqrt(2.0)) / 0.5;   // randref.m:31
+  truncnormal_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, cdf_ifactor, d_u, d_y);
+  ttirt::aux_launched();
+  CKA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ttirt_iw_stats_device(int64_t M, const double *d_lfex, const double *d_lfapp, double *d_weights,
+                                     double *out, void *stream) {
+  if (M < 1 || !d_lfex || !d_lfapp || !out) return aux_fail("bad arguments to ttirt_iw_stats_device");
+  cudaStream_t st = (cudaStream_t)stream;
+  DevBuf part, scal;
+  if (part.alloc(sizeof(double) * 3 * RG) || scal.alloc(sizeof(double) * 8)) return aux_fail("out of device memory");
+  double *dp = part.as<double>(), *ds = scal.as<double>();
+  iw_max_kernel<<<RG, RB, 0, st>>>(M, d_lfex, d_lfapp, dp);
+  iw_max_final_kernel<<<1, RB, 0, st>>>(dp, ds);
+  iw_sums_kernel<<<RG, RB, 0, st>>>(M, d_lfex, d_lfapp, ds, dp);
+  iw_sums_final_kernel<<<1, RB, 0, st>>>(dp, 3, ds + 1);
+  for (int i = 0; i < 4; i++) ttirt::aux_launched();
+  double h[4];
+  CKA(cudaMemcpyAsync(h, ds, sizeof(double) * 4, cudaMemcpyDeviceToHost, st));
+  CKA(cudaStreamSynchronize(st));
+  const double mx = h[0], s_exp = h[1], s1 = h[2], s2 = h[3];
+  const double renorm = s_exp / (double)M;                  // iw_prune.m:20
+  const double log_renorm = log(renorm);                    // :25
+  const double lzex = log(s1 / (double)M);                  // hellinger.m:14
+  iw_pass3_kernel<<<RG, RB, 0, st>>>(M, d_lfex, d_lfapp, renorm, log_renorm, mx, lzex, d_weights, dp);
+  iw_sums_final_kernel<<<1, RB, 0, st>>>(dp, 3, ds + 4);
+  ttirt::aux_launched(); ttirt::aux_launched();
+  double g[3];
+  CKA(cudaMemcpyAsync(g, ds + 4, sizeof(double) * 3, cudaMemcpyDeviceToHost, st));
+  CKA(cudaStreamSynchronize(st));
+  out[0] = sqrt(g[0] / (double)M);                          // isstd      iw_prune.m:29
+  out[1] = exp(mx) / renorm;                                // max_ratio  iw_prune.m:24 (exp is monotone: max of the ratios)
+  out[2] = g[1] / (double)M;                                // err1       iw_prune.m:26
+  out[3] = (double)M * s2 / (s1 * s1);                      // tau        essinv.m:14
+  out[4] = sqrt(g[2] / (double)M / 2.0);                    // H          hellinger.m:15-16
+  out[5] = log_renorm;                                      // log of the IS normalisation constant
+  return 0;
+}
+
+extern "C" int ttirt_mcmc_prune_device(int64_t M, const double *d_lfex, const double *d_lfapp, const double *d_u,
+                                       int32_t *d_src, int64_t *num_rejects, int64_t *rej_hist, int64_t rej_hist_len, void *stream) {
+  if (M < 1 || M > 2147483647LL || !d_lfex || !d_lfapp || !d_src || (M > 1 && !d_u) || rej_hist_len < 0 || (rej_hist_len > 0 && !rej_hist))
+    return aux_fail("bad arguments to ttirt_mcmc_prune_device");
+  cudaStream_t st = (cudaStream_t)stream;
+  DevBuf cnt, hist;
+  if (cnt.alloc(sizeof(unsigned long long) * 2) || hist.alloc(sizeof(unsigned long long) * (size_t)rej_hist_len)) return aux_fail("out of device memory");
+  CKA(cudaMemsetAsync(cnt.p, 0, sizeof(unsigned long long) * 2, st));
+  if (rej_hist_len > 0) CKA(cudaMemsetAsync(hist.p, 0, sizeof(unsigned long long) * (size_t)rej_hist_len, st));
+  mcmc_prune_kernel<<<1, 32, 0, st>>>(M, d_lfex, d_lfapp, d_u, d_src, cnt.as<unsigned long long>(), hist.as<unsigned long long>(), (int)rej_hist_len);
+  ttirt::aux_launched();
+  CKA(cudaGetLastError());
+  unsigned long long h[2];
+  CKA(cudaMemcpyAsync(h, cnt.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+  if (rej_hist_len > 0) CKA(cudaMemcpyAsync(rej_hist, hist.p, sizeof(int64_t) * (size_t)rej_hist_len, cudaMemcpyDeviceToHost, st));
+  CKA(cudaStreamSynchronize(st));
+  if (num_rejects) *num_rejects = (int64_t)h[0];
+  return 0;
+}
+
+// ---- host-buffer forms (device 0 unless TTIRT_DEVICE says otherwise): allocate, copy, run, copy back ----
+static int pick_device() {
+  const char *e = getenv("TTIRT_DEVICE");
+  const int dev = e ? atoi(e) : 0;
+  return cudaSetDevice(dev) == cudaSuccess ? 0 : aux_fail("cudaSetDevice(%d) failed", dev);
+}
+
+extern "C" int ttirt_seeds_lattice_host(int64_t d, int64_t M, int64_t m0, int64_t N, const int64_t *genvec, const double *shift,
+                                        double *h_q, int64_t ld) {
+  if (need_device() || pick_device()) return -1;
+  if (d < 1 || M < 0 || ld < M || !genvec || !shift || (M > 0 && !h_q)) return aux_fail("bad arguments to ttirt_seeds_lattice_host");
+  if (M == 0) return 0;
+  std::vector<double> z(d);
+  for (int64_t k = 0; k < d; k++) z[k] = (double)genvec[k];
+  DevBuf dz, ds, dq;
+  if (dz.alloc(sizeof(double) * d) || ds.alloc(sizeof(double) * d) || dq.alloc(sizeof(double) * M * d)) return aux_fail("out of device memory");
+  CKA(cudaMemcpy(dz.p, z.data(), sizeof(double) * d, cudaMemcpyHostToDevice));
+  CKA(cudaMemcpy(ds.p, shift, sizeof(double) * d, cudaMemcpyHostToDevice));
+  if (ttirt_seeds_lattice_device(d, M, m0, N, dz.as<double>(), ds.as<double>(), dq.as<double>(), M, nullptr) != 0) return -1;
+  CKA(cudaMemcpy2D(h_q, sizeof(double) * ld, dq.p, sizeof(double) * M, sizeof(double) * M, d, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int ttirt_seeds_uniform_host(int64_t d, int64_t M, int64_t m0, uint64_t seed, double *h_q, int64_t ld) {
+  if (need_device() || pick_device()) return -1;
+  if (d < 1 || M < 0 || ld < M || (M > 0 && !h_q)) return aux_fail("bad arguments to ttirt_seeds_uniform_host");
+  if (M == 0) return 0;
+  DevBuf dq;
+  if (dq.alloc(sizeof(double) * M * d)) return aux_fail("out of device memory");
+  if (ttirt_seeds_uniform_device(d, M, m0, seed, dq.as<double>(), M, nullptr) != 0) return -1;
+  CKA(cudaMemcpy2D(h_q, sizeof(double) * ld, dq.p, sizeof(double) * M, sizeof(double) * M, d, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int ttirt_truncnormal_map_host(int64_t n, double sigma, const double *h_u, double *h_y) {
+  if (need_device() || pick_device()) return -1;
+  if (n < 0 || (n > 0 && (!h_u || !h_y))) return aux_fail("bad arguments to ttirt_truncnormal_map_host");
+  if (n == 0) return 0;
+  DevBuf du, dy;
+  if (du.alloc(sizeof(double) * n) || dy.alloc(sizeof(double) * n)) return aux_fail("out of device memory");
+  CKA(cudaMemcpy(du.p, h_u, sizeof(double) * n, cudaMemcpyHostToDevice));
+  if (ttirt_truncnormal_map_device(n, sigma, du.as<double>(), dy.as<double>(), nullptr) != 0) return -1;
+  CKA(cudaMemcpy(h_y, dy.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int ttirt_iw_stats_host(int64_t M, const double *h_lfex, const double *h_lfapp, double *h_weights, double *out) {
+  if (need_device() || pick_device()) return -1;
+  if (M < 1 || !h_lfex || !h_lfapp || !out) return aux_fail("bad arguments to ttirt_iw_stats_host");
+  DevBuf de, da, dw;
+  if (de.alloc(sizeof(double) * M) || da.alloc(sizeof(double) * M) || (h_weights && dw.alloc(sizeof(double) * M))) return aux_fail("out of device memory");
+  CKA(cudaMemcpy(de.p, h_lfex, sizeof(double) * M, cudaMemcpyHostToDevice));
+  CKA(cudaMemcpy(da.p, h_lfapp, sizeof(double) * M, cudaMemcpyHostToDevice));
+  if (ttirt_iw_stats_device(M, de.as<double>(), da.as<double>(), h_weights ? dw.as<double>() : nullptr, out, nullptr) != 0) return -1;
+  if (h_weights) CKA(cudaMemcpy(h_weights, dw.p, sizeof(double) * M, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int ttirt_mcmc_prune_host(int64_t M, const double *h_lfex, const double *h_lfapp, const double *h_u, int32_t *h_src,
+                                     int64_t *num_rejects, int64_t *rej_hist, int64_t rej_hist_len) {
+  if (need_device() || pick_device()) return -1;
+  if (M < 1 || !h_lfex || !h_lfapp || !h_src || (M > 1 && !h_u)) return aux_fail("bad arguments to ttirt_mcmc_prune_host");
+  DevBuf de, da, du, dsrc;
+  if (de.alloc(sizeof(double) * M) || da.alloc(sizeof(double) * M) || du.alloc(sizeof(double) * M) || dsrc.alloc(sizeof(int32_t) * M))
+    return aux_fail("out of device memory");
+  CKA(cudaMemcpy(de.p, h_lfex, sizeof(double) * M, cudaMemcpyHostToDevice));
+  CKA(cudaMemcpy(da.p, h_lfapp, sizeof(double) * M, cudaMemcpyHostToDevice));
+  if (M > 1) CKA(cudaMemcpy(du.p, h_u, sizeof(double) * (M - 1), cudaMemcpyHostToDevice));
+  if (ttirt_mcmc_prune_device(M, de.as<double>(), da.as<double>(), du.as<double>(), dsrc.as<int32_t>(), num_rejects, rej_hist, rej_hist_len, nullptr) != 0)
+    return -1;
+  CKA(cudaMemcpy(h_src, dsrc.p, sizeof(int32_t) * M, cudaMemcpyDeviceToHost));
+  return 0;
+}
