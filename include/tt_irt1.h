@@ -116,6 +116,59 @@ TTIRT_API void ttirt_set_chunk(int64_t samples);
  * same shape; this releases them.  TTIRT_CACHE=0 in the environment disables the reuse altogether. */
 TTIRT_API void ttirt_cache_clear(void);
 
+/* ------------------------------------------------------------------------------------------
+ * The steps either side of tt_irt1 on the device.  `_device` forms take
+ * device pointers and a cudaStream_t (as void*); `_host` forms take host pointers, run on device TTIRT_DEVICE
+ * (default 0) and block.  All return 0 on success.
+ * ---------------------------------------------------------------------------------------- */
+
+/* Seeds: shifted rank-1 lattice, reference matlab/samplers/qmcnodes.m:6-13:
+ *   q[m + ldq*k] = frac(genvec[k] * ((m0 + m) / N) + shift[k]),  m in [0, M), k in [0, d)
+ * N = 2^l is the size of the whole lattice, [m0, m0 + M) the slice generated here (shards generate their own slice).
+ * Bit-exact against the reference arithmetic.  The device form takes the generating vector as doubles on the device. */
+TTIRT_API int ttirt_seeds_lattice_device(int64_t d, int64_t M, int64_t m0, int64_t N, const double *d_genvec,
+                                         const double *d_shift, double *d_q, int64_t ldq, void *stream);
+TTIRT_API int ttirt_seeds_lattice_host(int64_t d, int64_t M, int64_t m0, int64_t N, const int64_t *genvec,
+                                       const double *shift, double *h_q, int64_t ld);
+
+/* Seeds: uniform pseudo-random numbers in [0, 1) (the reference draws them with rand / np.random.random,
+ * python/test_shock_absorber_tt.py:147; neither is reproducible across hosts).  Philox4x32-10, counter =
+ * (sample index, dimension), key = seed: any slice [m0, m0 + M) can be generated independently. */
+TTIRT_API int ttirt_seeds_uniform_device(int64_t d, int64_t M, int64_t m0, uint64_t seed, double *d_q, int64_t ldq,
+                                         void *stream);
+TTIRT_API int ttirt_seeds_uniform_host(int64_t d, int64_t M, int64_t m0, uint64_t seed, double *h_q, int64_t ld);
+
+/* Uniform -> truncated normal on [-sigma, sigma], reference matlab/samplers/randref.m:31-33:
+ *   y = erfinv((u - 0.5) * erf(sigma / sqrt(2)) / 0.5) * sqrt(2) */
+TTIRT_API int ttirt_truncnormal_map_device(int64_t n, double sigma, const double *d_u, double *d_y, void *stream);
+TTIRT_API int ttirt_truncnormal_map_host(int64_t n, double sigma, const double *h_u, double *h_y);
+
+/* Importance-weight statistics of M samples with log exact density lfex and log sampling density lfapp:
+ *   out[0] isstd      relative standard deviation of the ratio            matlab/samplers/iw_prune.m:19-21,29
+ *   out[1] max_ratio  largest normalised ratio                            iw_prune.m:24
+ *   out[2] err1       empirical L1 error                                  iw_prune.m:25-26
+ *   out[3] tau        N / ESS                                             matlab/samplers/essinv.m:12-14
+ *   out[4] H          Hellinger distance                                  matlab/samplers/hellinger.m:12-16
+ *   out[5] log of the importance-sampling normalisation constant          iw_prune.m:20,25
+ * weights (may be NULL) receives the normalised ratios exp(lfex - lfapp) / mean (iw_prune.m:19-21), the factor the
+ * reference multiplies its quantities of interest with (:28).  Blocks until `out` (host memory) is complete. */
+TTIRT_API int ttirt_iw_stats_device(int64_t M, const double *d_lfex, const double *d_lfapp, double *d_weights, double *out,
+                                    void *stream);
+TTIRT_API int ttirt_iw_stats_host(int64_t M, const double *h_lfex, const double *h_lfapp, double *h_weights, double *out);
+
+/* Independence Metropolis-Hastings prune, reference matlab/samplers/mcmc_prune.m:24-43 (and the loop of
+ * python/test_shock_absorber_tt.py:165-171): proposal i+1 replaces the current sample c iff
+ *   exp(((lfex[i+1] - lfex[c]) - lfapp[i+1]) + lfapp[c]) >= u[i],   i = 0 .. M-2, u pre-drawn uniforms (M-1 of them).
+ * src[i] (int32, M entries) is the index of the sample occupying position i afterwards (the caller gathers y, lfex,
+ * lfapp rows with it); num_rejects the number of rejections; rej_hist[L-1] the number of completed runs of L
+ * consecutive rejections (runs longer than rej_hist_len are counted in the last bin; may be NULL with length 0).
+ * Blocks until the host outputs are complete. */
+TTIRT_API int ttirt_mcmc_prune_device(int64_t M, const double *d_lfex, const double *d_lfapp, const double *d_u,
+                                      int32_t *d_src, int64_t *num_rejects, int64_t *rej_hist, int64_t rej_hist_len,
+                                      void *stream);
+TTIRT_API int ttirt_mcmc_prune_host(int64_t M, const double *h_lfex, const double *h_lfapp, const double *h_u, int32_t *h_src,
+                                    int64_t *num_rejects, int64_t *rej_hist, int64_t rej_hist_len);
+
 #ifdef __cplusplus
 }
 #endif

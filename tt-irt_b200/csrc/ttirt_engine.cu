@@ -42,6 +42,19 @@ static int fail(const char *fmt, ...) {
   return -1;
 }
 
+namespace ttirt {
+// shared with ttirt_aux.cu
+int aux_fail(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  if (getenv("TTIRT_QUIET") == nullptr) fprintf(stderr, "tt_irt1[b200]: %s\n", g_err);
+  return -1;
+}
+void aux_launched() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace ttirt
+
 #define CK(call)                                                                          \
   do {                                                                                    \
     cudaError_t e_ = (call);                                                              \
