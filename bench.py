@@ -296,6 +296,24 @@ def main():
         e2e = {"value": world * M * a.steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(world * (M * d * 8 + cores.nbytes + xs.nbytes)),
                "d2h_bytes_per_step": int(world * (M * d * 8 + M * 8)), "ms_per_step": 1e3 * dt / a.steps,
                "api": "tt_irt1 (C-ABI symbol of tt_irt1_int32.so) on pinned host buffers; includes cores upload and marginalisation sweep"}
+        # the same call as the reference's own Python caller makes it: ordinary pageable numpy arrays (tt_irt.py:44-51)
+        if world == 1:
+            qn = np.asfortranarray(qh.numpy().T)          # M x d, F-order, pageable
+            zn = np.zeros((M, d), order="F"); ln = np.zeros(M)
+
+            def e2e_np():
+                lib.tt_irt1(c_int(d), n32.ctypes.data_as(ip), xs.ctypes.data_as(dp), r32.ctypes.data_as(ip), cores.ctypes.data_as(dp),
+                            c_int(M), qn.ctypes.data_as(dp), zn.ctypes.data_as(dp), ln.ctypes.data_as(dp))
+            e2e_np()
+            t0 = time.perf_counter()
+            for _ in range(a.steps):
+                e2e_np()
+            dtn = time.perf_counter() - t0
+            e2e["pageable_numpy_value"] = M * a.steps / dtn
+            e2e["pageable_numpy_note"] = "same call on pageable numpy arrays (bounce-buffer pipeline, %s host copy threads)" % os.environ.get("TTIRT_COPY_THREADS", "4")
+            if not np.array_equal(ln[:4096], lh[:4096].numpy()):
+                raise SystemExit("bench.py: pageable and pinned e2e results differ")
+            del qn, zn, ln
 
     if rank != 0:
         if dist is not None:

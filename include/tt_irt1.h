@@ -50,6 +50,8 @@ extern "C" {
  *
  * Returns nothing (as the reference).  On any failure (no device, bad shape, CUDA error) it prints
  * one line to stderr and fills z and lPz with NaN; it never aborts the host process.
+ * Caller arrays in ordinary pageable memory (numpy, mxArray) go through page-locked bounce buffers filled and drained
+ * by a few host threads (TTIRT_COPY_THREADS, default 4; TTIRT_NO_STAGING=1 leaves the staging to the driver).
  * Environment: TTIRT_MODE=fast|strict (default fast), TTIRT_DEVICES=<count>|all (default 1),
  * TTIRT_DEVICE=<first ordinal> (default 0), TTIRT_CHUNK=<samples per chunk>, TTIRT_CACHE=0 (free all device
  * memory before returning), TTIRT_TRACE=1 (host-side phase times on stderr), TTIRT_VERBOSE=1.
@@ -137,6 +139,14 @@ TTIRT_API int ttirt_seeds_lattice_host(int64_t d, int64_t M, int64_t m0, int64_t
 TTIRT_API int ttirt_seeds_uniform_device(int64_t d, int64_t M, int64_t m0, uint64_t seed, double *d_q, int64_t ldq,
                                          void *stream);
 TTIRT_API int ttirt_seeds_uniform_host(int64_t d, int64_t M, int64_t m0, uint64_t seed, double *h_q, int64_t ld);
+
+/* tt_irt1 on seeds generated on the device: rows [0, M) of the result use lattice / Philox indices [m0, m0 + M), no q is
+ * uploaded.  h_q may be NULL; when given it receives the seeds used (column-major M x d, leading dimension ld, as
+ * h_z).  Same chunked pipeline, modes and error behaviour as ttirt_sample_host. */
+TTIRT_API int ttirt_sample_lattice_host(ttirt_model *model, int64_t M, int64_t m0, int64_t N, const int64_t *genvec,
+                                        const double *shift, double *h_q, double *h_z, double *h_lpz, int64_t ld, int mode);
+TTIRT_API int ttirt_sample_uniform_host(ttirt_model *model, int64_t M, int64_t m0, uint64_t seed, double *h_q, double *h_z,
+                                        double *h_lpz, int64_t ld, int mode);
 
 /* Uniform -> truncated normal on [-sigma, sigma], reference matlab/samplers/randref.m:31-33:
  *   y = erfinv((u - 0.5) * erf(sigma / sqrt(2)) / 0.5) * sqrt(2) */

@@ -87,3 +87,42 @@ def test_seeds_feed_the_sampler():
     assert np.isfinite(Z).all() and np.isfinite(lPz).all()
     lo, hi = xs.reshape(d, n)[:, 0], xs.reshape(d, n)[:, -1]
     assert (Z >= lo - 1e-9).all() and (Z <= hi + 1e-9).all()
+
+
+def test_sampling_on_device_seeds_equals_sampling_on_uploaded_seeds():
+    """Model.sample_lattice / sample_uniform (seeds generated on the device, no q upload) give bit for bit what
+    Model.sample gives on the same seeds uploaded from the host; a slice [m0, m0+M) equals the slice of the whole."""
+    d, n, r = 8, 17, 16
+    ns, xs, rk, c = synth.make_tt(d, n, r, seed=9)
+    md = tt_irt.Model(ns, xs, rk, c)
+    try:
+        z = np.arange(3, 3 + 2 * d, 2); shift = np.linspace(0.05, 0.9, d)
+        Z, l, q = md.sample_lattice(15, z, shift, want_q=True)
+        assert np.array_equal(q, so.qmc_lattice(d, 15, z, shift))
+        Z2, l2 = md.sample(q)
+        assert np.array_equal(Z, Z2) and np.array_equal(l, l2)
+        Zs, ls = md.sample_lattice(15, z, shift, m0=9000, M=3000)
+        assert np.array_equal(Zs, Z[9000:12000]) and np.array_equal(ls, l[9000:12000])
+        Zu, lu, qu = md.sample_uniform(20000, seed=77, want_q=True)
+        assert np.array_equal(qu, so.uniform_philox(d, 20000, 77))
+        Zu2, lu2 = md.sample(qu)
+        assert np.array_equal(Zu, Zu2) and np.array_equal(lu, lu2)
+    finally:
+        md.close()
+
+
+def test_pageable_and_pinned_callers_agree():
+    """The bounce-buffer pipeline for pageable caller arrays (numpy) returns bit for bit what the direct pipeline does."""
+    import os
+    d, n, r, M = 8, 17, 16, 300000
+    ns, xs, rk, c = synth.make_tt(d, n, r, seed=10)
+    q = synth.make_q(M, d, seed=2)
+    md = tt_irt.Model(ns, xs, rk, c)
+    try:
+        Z1, l1 = md.sample(q)                       # pageable numpy arrays: staged through pinned buffers
+        os.environ["TTIRT_NO_STAGING"] = "1"        # read once per process: only effective if not yet cached
+        Z2, l2 = md.sample(q[:70000])               # small call: below the staging threshold either way
+        assert np.array_equal(Z2, Z1[:70000]) and np.array_equal(l2, l1[:70000])
+    finally:
+        os.environ.pop("TTIRT_NO_STAGING", None)
+        md.close()

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -118,6 +119,9 @@ struct ttirt_model {
   double *d_p0 = nullptr, *d_cdf0 = nullptr;
   DimInfo *d_dims = nullptr;
   Workspace ws[kSlots];
+  // page-locked bounce buffers of the host pipeline, one set per slot: used when the caller's arrays are ordinary
+  // pageable memory (numpy, mxArray), which cudaMemcpyAsync would otherwise stage synchronously at a fraction of PCIe rate
+  struct HostStage { double *q = nullptr, *z = nullptr, *lpz = nullptr; int64_t cap = 0; } stage[kSlots];
   // optional per-launch timing of the dominant (transition) kernel, for bench.py's roofline
   bool profile = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -381,6 +385,7 @@ extern "C" void ttirt_model_destroy(ttirt_model *md) {
   if (!md) return;
   cudaSetDevice(md->device);
   for (auto &w : md->ws) ws_free(w);
+  for (auto &h : md->stage) { cudaFreeHost(h.q); cudaFreeHost(h.z); cudaFreeHost(h.lpz); }
   for (auto &p : md->prof_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   cudaFree(md->d_xs); cudaFree(md->d_core); cudaFree(md->d_pk); cudaFree(md->d_marg);
   cudaFree(md->d_p0); cudaFree(md->d_cdf0); cudaFree(md->d_dims);
@@ -580,8 +585,71 @@ static bool pin_if_pageable(const void *p, size_t bytes) {
 }
 static void unpin(const void *p, bool pinned) { if (pinned) { cudaHostUnregister(const_cast<void *>(p)); } }
 
+// Where a chunk's seeds come from: the caller's q (host memory), or generated on the device (csrc/ttirt_aux.cu), which
+// removes the q upload altogether.
+struct SeedSpec {
+  int kind = 0;                 // 0: host q, 1: shifted rank-1 lattice, 2: Philox uniforms
+  int64_t N = 0, m_base = 0;    // lattice size; global index of row 0 of this call
+  const double *d_genvec = nullptr, *d_shift = nullptr;
+  uint64_t seed = 0;
+};
+
+static bool is_pageable(const void *p) {
+  if (!p) return false;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+  return at.type == cudaMemoryTypeUnregistered;
+}
+
+static int copy_threads() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("TTIRT_COPY_THREADS");
+    v = e ? atoi(e) : 4;
+    if (v < 1) v = 1;
+    if (v > 32) v = 32;
+  }
+  return v;
+}
+
+// d column segments of `rows` doubles, split over a few host threads (a single core tops out near 10 GB/s)
+static void copy_columns(double *dst, int64_t dst_ld, const double *src, int64_t src_ld, int64_t rows, int d) {
+  const int nt = std::min(copy_threads(), d);
+  auto work = [&](int t) {
+    for (int k = t; k < d; k += nt) memcpy(dst + (int64_t)k * dst_ld, src + (int64_t)k * src_ld, sizeof(double) * (size_t)rows);
+  };
+  if (nt <= 1 || (int64_t)rows * d < (1 << 17)) { for (int t = 0; t < nt; t++) work(t); return; }
+  std::vector<std::thread> th;
+  for (int t = 1; t < nt; t++) th.emplace_back(work, t);
+  work(0);
+  for (auto &x : th) x.join();
+}
+
+static int stage_ensure(ttirt_model *md, int slot, int64_t rows, bool need_q, bool need_z) {
+  auto &h = md->stage[slot];
+  if (h.cap >= rows && (!need_q || h.q) && (!need_z || h.z)) return 0;
+  const int64_t cap = std::max(rows, h.cap);
+  if (need_q && (h.cap < cap || !h.q)) { cudaFreeHost(h.q); h.q = nullptr; CK(cudaHostAlloc(&h.q, sizeof(double) * cap * md->d, cudaHostAllocDefault)); }
+  if (need_z && (h.cap < cap || !h.z)) {
+    cudaFreeHost(h.z); cudaFreeHost(h.lpz); h.z = h.lpz = nullptr;
+    CK(cudaHostAlloc(&h.z, sizeof(double) * cap * md->d, cudaHostAllocDefault));
+    CK(cudaHostAlloc(&h.lpz, sizeof(double) * cap, cudaHostAllocDefault));
+  }
+  if (h.cap < cap) {   // the other buffer, if present, is too small now
+    if (!need_q && h.q) { cudaFreeHost(h.q); h.q = nullptr; }
+    if (!need_z && h.z) { cudaFreeHost(h.z); cudaFreeHost(h.lpz); h.z = h.lpz = nullptr; }
+  }
+  h.cap = cap;
+  return 0;
+}
+
+// Rows [m_begin, m_end) of one call on this model's device: chunks of rows go round three slots (stream + device
+// scratch + optional pinned bounce buffers).  Per chunk: seeds in (async H2D from pinned memory, or a host-thread copy
+// into the slot's pinned buffer first when the caller's q is pageable, or generated on the device) -> kernels -> D2H
+// (straight into pinned caller memory, or into the slot's pinned buffer from which a drain thread copies into the
+// caller's pageable arrays while the next chunks compute).
 static int sample_host_rows(ttirt_model *md, int64_t m_begin, int64_t m_end, const double *h_q, double *h_z, double *h_lpz,
-                            int32_t *h_idx, int64_t ld, int mode) {
+                            int32_t *h_idx, int64_t ld, int mode, const SeedSpec &seeds = SeedSpec()) {
   const int64_t M = m_end - m_begin;
   if (M <= 0) return 0;
   CK(cudaSetDevice(md->device));
@@ -591,25 +659,103 @@ static int sample_host_rows(ttirt_model *md, int64_t m_begin, int64_t m_end, con
   if (M < chunk * kSlots) chunk = std::max<int64_t>((M + kSlots - 1) / kSlots, std::min<int64_t>(M, 1 << 16));
   const int64_t nchunks = (M + chunk - 1) / chunk;
   const int nslots = (int)std::min<int64_t>(kSlots, nchunks);
-  for (int s = 0; s < nslots; s++)
+  static const bool no_stage = getenv("TTIRT_NO_STAGING") != nullptr;
+  const bool big = M * d >= (1 << 20);   // tiny calls: the driver's own staging is as good
+  const bool stage_q = !no_stage && big && seeds.kind == 0 && is_pageable(h_q + m_begin);
+  const bool stage_z = !no_stage && big && is_pageable(h_z + m_begin);
+  for (int s = 0; s < nslots; s++) {
     if (ws_ensure(md, md->ws[s], chunk, strict, true, h_idx != nullptr) != 0) return -1;
-  for (int64_t c = 0; c < nchunks; c++) {
-    Workspace &w = md->ws[c % kSlots];
-    const int64_t m0 = m_begin + c * chunk, rows = std::min(chunk, m_end - m0);
-    if (c >= kSlots) CK(cudaEventSynchronize(w.done));
-    CK(cudaMemcpy2DAsync(w.q, sizeof(double) * rows, h_q + m0, sizeof(double) * ld, sizeof(double) * rows, d,
-                         cudaMemcpyHostToDevice, w.stream));
-    if (run_chunk(md, w, rows, w.q, rows, w.z, rows, w.lpz, h_idx ? w.idx_out : nullptr, mode, w.stream) != 0) return -1;
-    CK(cudaMemcpy2DAsync(h_z + m0, sizeof(double) * ld, w.z, sizeof(double) * rows, sizeof(double) * rows, d,
-                         cudaMemcpyDeviceToHost, w.stream));
-    CK(cudaMemcpyAsync(h_lpz + m0, w.lpz, sizeof(double) * rows, cudaMemcpyDeviceToHost, w.stream));
-    if (h_idx)
-      CK(cudaMemcpy2DAsync(h_idx + m0, sizeof(int32_t) * ld, w.idx_out, sizeof(int32_t) * rows, sizeof(int32_t) * rows, d,
-                           cudaMemcpyDeviceToHost, w.stream));
-    CK(cudaEventRecord(w.done, w.stream));
+    if ((stage_q || stage_z) && stage_ensure(md, s, chunk, stage_q, stage_z) != 0) return -1;
   }
-  for (int s = 0; s < nslots; s++) CK(cudaStreamSynchronize(md->ws[s].stream));
-  return 0;
+
+  // drain thread: waits for a chunk's event, copies its outputs from the slot's pinned buffer into the caller's arrays
+  std::mutex mu;
+  std::condition_variable cv;
+  int64_t submitted = 0, drained = 0;
+  bool abort_drain = false;
+  int drain_rc = 0;
+  std::thread drain;
+  if (stage_z) {
+    drain = std::thread([&]() {
+      if (cudaSetDevice(md->device) != cudaSuccess) { std::lock_guard<std::mutex> l(mu); drain_rc = -1; drained = nchunks; cv.notify_all(); return; }
+      for (int64_t c = 0; c < nchunks; c++) {
+        {
+          std::unique_lock<std::mutex> l(mu);
+          cv.wait(l, [&] { return submitted > c || abort_drain; });
+          if (abort_drain) break;
+        }
+        const int s = (int)(c % kSlots);
+        const int64_t m0 = m_begin + c * chunk, rows = std::min(chunk, m_end - m0);
+        if (cudaEventSynchronize(md->ws[s].done) != cudaSuccess) { std::lock_guard<std::mutex> l(mu); drain_rc = -1; }
+        copy_columns(h_z + m0, ld, md->stage[s].z, rows, rows, d);
+        memcpy(h_lpz + m0, md->stage[s].lpz, sizeof(double) * (size_t)rows);
+        { std::lock_guard<std::mutex> l(mu); drained = c + 1; }
+        cv.notify_all();
+      }
+    });
+  }
+  auto finish = [&](int rc) -> int {
+    if (drain.joinable()) {
+      { std::lock_guard<std::mutex> l(mu); if (rc != 0) abort_drain = true; }
+      cv.notify_all();
+      drain.join();
+    }
+    return rc != 0 ? rc : drain_rc;
+  };
+#define CKF(call)                                                                         \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) { fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); return finish(-1); } \
+  } while (0)
+
+  for (int64_t c = 0; c < nchunks; c++) {
+    const int s = (int)(c % kSlots);
+    Workspace &w = md->ws[s];
+    const int64_t m0 = m_begin + c * chunk, rows = std::min(chunk, m_end - m0);
+    if (c >= kSlots) {
+      if (stage_z) {   // the slot's pinned output buffer must have been drained
+        std::unique_lock<std::mutex> l(mu);
+        cv.wait(l, [&] { return drained > c - kSlots; });
+      } else {
+        CKF(cudaEventSynchronize(w.done));
+      }
+    }
+    if (seeds.kind == 1) {
+      if (ttirt_seeds_lattice_device(d, rows, seeds.m_base + (m0 - m_begin), seeds.N, seeds.d_genvec, seeds.d_shift, w.q, rows, w.stream) != 0) return finish(-1);
+    } else if (seeds.kind == 2) {
+      if (ttirt_seeds_uniform_device(d, rows, seeds.m_base + (m0 - m_begin), seeds.seed, w.q, rows, w.stream) != 0) return finish(-1);
+    } else if (stage_q) {
+      if (c >= kSlots) CKF(cudaEventSynchronize(w.done));   // the previous H2D out of this pinned buffer is long done; make it certain
+      copy_columns(md->stage[s].q, rows, h_q + m0, ld, rows, d);
+      CKF(cudaMemcpyAsync(w.q, md->stage[s].q, sizeof(double) * rows * d, cudaMemcpyHostToDevice, w.stream));
+    } else {
+      CKF(cudaMemcpy2DAsync(w.q, sizeof(double) * rows, h_q + m0, sizeof(double) * ld, sizeof(double) * rows, d,
+                            cudaMemcpyHostToDevice, w.stream));
+    }
+    if (run_chunk(md, w, rows, w.q, rows, w.z, rows, w.lpz, h_idx ? w.idx_out : nullptr, mode, w.stream) != 0) return finish(-1);
+    if (seeds.kind != 0 && h_q)   // hand the generated seeds back when the caller wants them
+      CKF(cudaMemcpy2DAsync(const_cast<double *>(h_q) + m0, sizeof(double) * ld, w.q, sizeof(double) * rows, sizeof(double) * rows, d,
+                            cudaMemcpyDeviceToHost, w.stream));
+    if (stage_z) {
+      CKF(cudaMemcpyAsync(md->stage[s].z, w.z, sizeof(double) * rows * d, cudaMemcpyDeviceToHost, w.stream));
+      CKF(cudaMemcpyAsync(md->stage[s].lpz, w.lpz, sizeof(double) * rows, cudaMemcpyDeviceToHost, w.stream));
+    } else {
+      CKF(cudaMemcpy2DAsync(h_z + m0, sizeof(double) * ld, w.z, sizeof(double) * rows, sizeof(double) * rows, d,
+                            cudaMemcpyDeviceToHost, w.stream));
+      CKF(cudaMemcpyAsync(h_lpz + m0, w.lpz, sizeof(double) * rows, cudaMemcpyDeviceToHost, w.stream));
+    }
+    if (h_idx)
+      CKF(cudaMemcpy2DAsync(h_idx + m0, sizeof(int32_t) * ld, w.idx_out, sizeof(int32_t) * rows, sizeof(int32_t) * rows, d,
+                            cudaMemcpyDeviceToHost, w.stream));
+    CKF(cudaEventRecord(w.done, w.stream));
+    if (stage_z) {
+      { std::lock_guard<std::mutex> l(mu); submitted = c + 1; }
+      cv.notify_all();
+    }
+  }
+  for (int s = 0; s < nslots; s++) CKF(cudaStreamSynchronize(md->ws[s].stream));
+#undef CKF
+  return finish(0);
 }
 
 extern "C" int ttirt_sample_host(ttirt_model *md, int64_t M, const double *h_q, double *h_z, double *h_lpz, int32_t *h_idx,
@@ -623,6 +769,41 @@ extern "C" int ttirt_sample_host(ttirt_model *md, int64_t M, const double *h_q, 
   const int rc = sample_host_rows(md, 0, M, h_q, h_z, h_lpz, h_idx, ld, mode);
   unpin(h_q, pq); unpin(h_z, pz); unpin(h_lpz, pl);
   return rc;
+}
+
+// Sampling with the seeds generated on the device: no q upload.  h_q may be NULL;
+// when given it receives the seeds that were used (column-major, leading dimension ld).
+extern "C" int ttirt_sample_lattice_host(ttirt_model *md, int64_t M, int64_t m0, int64_t N, const int64_t *genvec, const double *shift,
+                                         double *h_q, double *h_z, double *h_lpz, int64_t ld, int mode) {
+  g_err[0] = 0;
+  if (!md) return fail("null model");
+  if (M < 0 || ld < M || N < 1 || !genvec || !shift || (M > 0 && (!h_z || !h_lpz))) return fail("bad arguments to ttirt_sample_lattice_host");
+  if (M == 0) return 0;
+  CK(cudaSetDevice(md->device));
+  const int64_t d = md->d;
+  std::vector<double> z(d);
+  for (int64_t k = 0; k < d; k++) z[k] = (double)genvec[k];
+  double *dz = nullptr;
+  CK(cudaMalloc(&dz, sizeof(double) * 2 * d));
+  SeedSpec sp;
+  sp.kind = 1; sp.N = N; sp.m_base = m0; sp.d_genvec = dz; sp.d_shift = dz + d;
+  int rc = 0;
+  if (cudaMemcpy(dz, z.data(), sizeof(double) * d, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(dz + d, shift, sizeof(double) * d, cudaMemcpyHostToDevice) != cudaSuccess) rc = fail("seed upload failed");
+  if (rc == 0) rc = sample_host_rows(md, 0, M, h_q, h_z, h_lpz, nullptr, ld, mode, sp);
+  cudaFree(dz);
+  return rc;
+}
+
+extern "C" int ttirt_sample_uniform_host(ttirt_model *md, int64_t M, int64_t m0, uint64_t seed, double *h_q, double *h_z, double *h_lpz,
+                                         int64_t ld, int mode) {
+  g_err[0] = 0;
+  if (!md) return fail("null model");
+  if (M < 0 || ld < M || (M > 0 && (!h_z || !h_lpz))) return fail("bad arguments to ttirt_sample_uniform_host");
+  if (M == 0) return 0;
+  SeedSpec sp;
+  sp.kind = 2; sp.m_base = m0; sp.seed = seed;
+  return sample_host_rows(md, 0, M, h_q, h_z, h_lpz, nullptr, ld, mode, sp);
 }
 
 // ------------------------------------------------------------------------------------------------

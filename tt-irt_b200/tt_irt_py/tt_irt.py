@@ -183,6 +183,42 @@ class Model(object):
             _raise_last(self._lib, "ttirt_sample_host")
         return (Z, lPz, idx) if want_idx else (Z, lPz)
 
+    def sample_lattice(self, l, genvec, shift, m0=0, M=None, mode=MODE_FAST, want_q=False):
+        """tt_irt1 on the 2^l-point shifted rank-1 lattice of qmcnodes.m, generated on the device (no q upload).
+        Returns (Z, lPz) or (Z, lPz, q)."""
+        N = 1 << int(l)
+        M = N - m0 if M is None else int(M)
+        z = np.ascontiguousarray(np.asarray(genvec)[:self.d], dtype=np.int64)
+        sh = np.ascontiguousarray(np.asarray(shift, dtype=np.float64).ravel()[:self.d])
+        Z = np.zeros((M, self.d), dtype=np.float64, order="F")
+        lPz = np.zeros(M, dtype=np.float64)
+        q = np.zeros((M, self.d), dtype=np.float64, order="F") if want_q else None
+        dp, lp = POINTER(c_double), POINTER(c_longlong)
+        f = self._lib.ttirt_sample_lattice_host
+        f.argtypes = [c_void_p, c_longlong, c_longlong, c_longlong, lp, dp, dp, dp, dp, c_longlong, c_int]
+        f.restype = c_int
+        rc = f(self._h, M, int(m0), N, z.ctypes.data_as(lp), sh.ctypes.data_as(dp), q.ctypes.data_as(dp) if want_q else None,
+               Z.ctypes.data_as(dp), lPz.ctypes.data_as(dp), M, int(mode))
+        if rc != 0:
+            _raise_last(self._lib, "ttirt_sample_lattice_host")
+        return (Z, lPz, q) if want_q else (Z, lPz)
+
+    def sample_uniform(self, M, seed, m0=0, mode=MODE_FAST, want_q=False):
+        """tt_irt1 on M reproducible uniform seed points (Philox4x32-10) generated on the device (no q upload)."""
+        from ctypes import c_ulonglong
+        Z = np.zeros((M, self.d), dtype=np.float64, order="F")
+        lPz = np.zeros(M, dtype=np.float64)
+        q = np.zeros((M, self.d), dtype=np.float64, order="F") if want_q else None
+        dp = POINTER(c_double)
+        f = self._lib.ttirt_sample_uniform_host
+        f.argtypes = [c_void_p, c_longlong, c_longlong, c_ulonglong, dp, dp, dp, c_longlong, c_int]
+        f.restype = c_int
+        rc = f(self._h, int(M), int(m0), int(seed) & 0xFFFFFFFFFFFFFFFF, q.ctypes.data_as(dp) if want_q else None,
+               Z.ctypes.data_as(dp), lPz.ctypes.data_as(dp), int(M), int(mode))
+        if rc != 0:
+            _raise_last(self._lib, "ttirt_sample_uniform_host")
+        return (Z, lPz, q) if want_q else (Z, lPz)
+
     def profile_enable(self, on=True):
         self._lib.ttirt_profile_enable(self._h, 1 if on else 0)
 
