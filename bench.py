@@ -298,7 +298,7 @@ def main():
                "api": "tt_irt1 (C-ABI symbol of tt_irt1_int32.so) on pinned host buffers; includes cores upload and marginalisation sweep"}
         # the same call as the reference's own Python caller makes it: ordinary pageable numpy arrays (tt_irt.py:44-51)
         if world == 1:
-            qn = np.asfortranarray(qh.numpy().T)          # M x d, F-order, pageable
+            qn = np.array(qh.numpy().T, order="F", copy=True)   # M x d, F-order, a pageable copy
             zn = np.zeros((M, d), order="F"); ln = np.zeros(M)
 
             def e2e_np():
