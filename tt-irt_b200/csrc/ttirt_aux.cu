@@ -15,6 +15,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <utility>
 #include <vector>
 
 #include "../../include/tt_irt1.h"
@@ -182,64 +183,169 @@ __global__ void iw_pass3_kernel(int64_t M, const double *__restrict__ lfex, cons
 // ------------------------------------------------------------------------------------------------
 // consumers: independence Metropolis-Hastings prune (mcmc_prune.m:24-43)
 // ------------------------------------------------------------------------------------------------
-// The chain is sequential in the index of the last ACCEPTED sample c: proposal i+1 is accepted iff
-//   exp(((lFex(i+1) - lFex(c)) - lFapp(i+1)) + lFapp(c)) >= u(i)          (reference rounding order, :25-27)
-// A warp evaluates 32 consecutive proposals against the current c at once; everything before the first accepted
-// lane is a rejection under that same c, so one ballot advances the chain by a whole run.  One warp, one chain:
-// the work is latency, not bandwidth (M = 2^20 takes a few milliseconds; the reference is a scalar interpreter loop).
-// src[i] = index of the sample that occupies position i after pruning.
-__global__ void mcmc_prune_kernel(int64_t M, const double *__restrict__ lfex, const double *__restrict__ lfapp,
-                                  const double *__restrict__ u, int32_t *src, unsigned long long *counters,
-                                  unsigned long long *rej_hist, int rej_hist_len) {
-  const int lane = threadIdx.x;
+// The reference chain is sequential in the index c of the last ACCEPTED sample: proposal j replaces c iff
+//   exp(((lFex(j) - lFex(c)) - lFapp(j)) + lFapp(c)) >= u(j-1)            (reference rounding order, :25-27)
+// Parallel formulation with the reference's arithmetic untouched:
+//   1. nxt[c] = first j > c that WOULD be accepted if c were the current sample (M if none): independent per c,
+//      a short forward scan (expected length 1 / acceptance rate; long scans are finished by the whole warp);
+//   2. the chain is the path 0 -> nxt[0] -> nxt[nxt[0]] -> ...; its nodes are marked by pointer doubling
+//      (log2 M rounds of "mark J[c] for every marked c, then J = J o J");
+//   3. src[i] = last marked node <= i (inclusive max-scan); rejections = unmarked positions; a completed run of L
+//      rejections ends at every marked node whose predecessor on the path lies L + 1 back.
+__device__ __forceinline__ bool mh_accept(double fe_j, double fa_j, double u_jm1, double fe_c, double fa_c) {
+  double al = __dsub_rn(fe_j, fe_c);
+  al = __dsub_rn(al, fa_j);
+  al = __dadd_rn(al, fa_c);
+  return !(exp(al) < u_jm1);
+}
+
+__global__ void mh_next_kernel(int M, const double *__restrict__ lfex, const double *__restrict__ lfapp,
+                               const double *__restrict__ u, int *nxt) {
   const unsigned FULL = 0xffffffffu;
-  int64_t c = 0;                       // last accepted sample
-  double fe_c = lfex[0], fa_c = lfapp[0];
-  if (lane == 0) src[0] = 0;
-  unsigned long long rejects = 0;
-  int64_t rej_seq = 0;
-  int64_t i = 0;                       // next step: proposal i+1 against u[i]
-  while (i < M - 1) {
-    const int64_t p = i + 1 + lane;    // this lane's proposal
-    bool acc = false;
-    if (p < M) {
-      double al = __dsub_rn(lfex[p], fe_c);
-      al = __dsub_rn(al, lfapp[p]);
-      al = __dadd_rn(al, fa_c);
-      acc = !(exp(al) < u[p - 1]);
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = c < M;
+  double fe_c = 0.0, fa_c = 0.0;
+  int found = M;
+  if (live) {
+    fe_c = lfex[c]; fa_c = lfapp[c];
+    const int jend = min(c + 32, M - 1);
+    for (int j = c + 1; j <= jend; j++)
+      if (mh_accept(lfex[j], lfapp[j], u[j - 1], fe_c, fa_c)) { found = j; break; }
+  }
+  // scans that did not finish within 32 proposals are completed by the whole warp, 32 proposals per step
+  unsigned pending = __ballot_sync(FULL, live && found == M && c + 32 < M - 1);
+  while (pending) {
+    const int src_lane = __ffs(pending) - 1;
+    pending &= pending - 1;
+    const int cc = __shfl_sync(FULL, c, src_lane);
+    const double fe = __shfl_sync(FULL, fe_c, src_lane), fa = __shfl_sync(FULL, fa_c, src_lane);
+    int res = M;
+    for (int j0 = cc + 33; j0 < M; j0 += 32) {
+      const int j = j0 + lane;
+      const bool acc = j < M && mh_accept(lfex[j], lfapp[j], u[j - 1], fe, fa);
+      const unsigned m = __ballot_sync(FULL, acc);
+      if (m) { res = j0 + __ffs(m) - 1; break; }
     }
-    const unsigned mask = __ballot_sync(FULL, acc);
-    const int64_t left = M - 1 - i;    // steps still to do
-    const int span = left < 32 ? (int)left : 32;
-    const int first = mask ? __ffs(mask) - 1 : 32;
-    if (first >= span) {
-      // the whole window is rejected: positions i+1 .. i+span carry c
-      if (lane < span) src[i + 1 + lane] = (int32_t)c;
-      rejects += span; rej_seq += span; i += span;
-    } else {
-      if (lane < first) src[i + 1 + lane] = (int32_t)c;
-      rejects += first; rej_seq += first;
-      c = i + 1 + first;
-      if (lane == 0) {
-        src[c] = (int32_t)c;
-        if (rej_seq > 0 && rej_hist_len > 0) {
-          const int64_t b = rej_seq <= rej_hist_len ? rej_seq : rej_hist_len;   // runs beyond the table land in its last bin
-          rej_hist[b - 1] += 1;
-        }
-      }
-      rej_seq = 0;
-      fe_c = lfex[c]; fa_c = lfapp[c];
-      i = c;
+    if (lane == src_lane) found = res;
+  }
+  if (live) nxt[c] = found;
+}
+
+__global__ void mh_init_kernel(int M, const int *__restrict__ nxt, int *J, unsigned char *onpath) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < M) { J[c] = nxt[c]; onpath[c] = c == 0; }
+  if (c == M) J[M] = M;
+}
+
+// one doubling round: mark the 2^r-th successor of every marked node, then square the jump table
+__global__ void mh_double_kernel(int M, const int *__restrict__ J, int *Jn, unsigned char *onpath) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > M) return;
+  if (c == M) { Jn[M] = M; return; }
+  const int t = J[c];
+  if (onpath[c] && t < M) onpath[t] = 1;
+  Jn[c] = J[t];
+}
+
+constexpr int SCAN_B = 1024;          // threads per scan block
+constexpr int SCAN_E = 4;             // elements per thread
+constexpr int SCAN_SEG = SCAN_B * SCAN_E;
+
+// inclusive max-scan of v[i] = onpath[i] ? i : 0 (the path starts at 0 and its indices increase)
+__global__ void mh_segmax_kernel(int M, const unsigned char *__restrict__ onpath, int *segmax) {
+  __shared__ int sh[SCAN_B];
+  const int base = blockIdx.x * SCAN_SEG;
+  int v = 0;
+  for (int e = 0; e < SCAN_E; e++) {
+    const int i = base + e * SCAN_B + threadIdx.x;
+    if (i < M && onpath[i]) v = max(v, i);
+  }
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  for (int s = SCAN_B / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sh[threadIdx.x] = max(sh[threadIdx.x], sh[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) segmax[blockIdx.x] = sh[0];
+}
+// exclusive max-scan of the segment maxima, in place, by one block: each thread owns a contiguous slice
+__global__ void mh_segscan_kernel(int nseg, int *segmax) {
+  __shared__ int sh[SCAN_B];
+  const int per = (nseg + SCAN_B - 1) / SCAN_B;
+  const int b0 = threadIdx.x * per, b1 = min(nseg, b0 + per);
+  int run = 0;
+  for (int b = b0; b < b1; b++) run = max(run, segmax[b]);
+  sh[threadIdx.x] = run;
+  __syncthreads();
+  for (int off = 1; off < SCAN_B; off <<= 1) {
+    const int t = (int)threadIdx.x >= off ? sh[threadIdx.x - off] : 0;
+    __syncthreads();
+    sh[threadIdx.x] = max(sh[threadIdx.x], t);
+    __syncthreads();
+  }
+  run = threadIdx.x > 0 ? sh[threadIdx.x - 1] : 0;
+  for (int b = b0; b < b1; b++) { const int v = segmax[b]; segmax[b] = run; run = max(run, v); }
+}
+__global__ void mh_src_kernel(int M, const unsigned char *__restrict__ onpath, const int *__restrict__ segmax, int32_t *src,
+                              unsigned long long *counters, unsigned long long *rej_hist, int rej_hist_len) {
+  __shared__ int sh[SCAN_B];
+  const int base = blockIdx.x * SCAN_SEG + threadIdx.x * SCAN_E;   // each thread owns SCAN_E consecutive positions
+  int v[SCAN_E];
+  int run = 0;
+  for (int e = 0; e < SCAN_E; e++) {
+    const int i = base + e;
+    if (i < M && onpath[i]) run = max(run, i);
+    v[e] = run;
+  }
+  sh[threadIdx.x] = run;
+  __syncthreads();
+  // Hillis-Steele inclusive max-scan over the thread totals
+  for (int off = 1; off < SCAN_B; off <<= 1) {
+    const int t = (int)threadIdx.x >= off ? sh[threadIdx.x - off] : 0;
+    __syncthreads();
+    sh[threadIdx.x] = max(sh[threadIdx.x], t);
+    __syncthreads();
+  }
+  const int before = max(segmax[blockIdx.x], threadIdx.x > 0 ? sh[threadIdx.x - 1] : 0);
+  unsigned long long rejects = 0;
+  for (int e = 0; e < SCAN_E; e++) {
+    const int i = base + e;
+    if (i >= M) break;
+    const int s = max(v[e], before);
+    src[i] = s;
+    if (s != i) {
+      rejects++;
+    } else if (i > 0 && rej_hist_len > 0) {
+      const int prev = e > 0 ? max(v[e - 1], before) : before;   // last path node <= i - 1
+      const int len = i - prev - 1;
+      if (len > 0) atomicAdd(rej_hist + (min(len, rej_hist_len) - 1), 1ULL);
     }
   }
-  if (lane == 0) { counters[0] = rejects; }
+  if (rejects) atomicAdd(counters, rejects);
 }
 
 // host-side helpers ---------------------------------------------------------------------------------
+// scratch from the stream-ordered pool: cudaMalloc / cudaFree per call would cost more than the kernels
 struct DevBuf {
   void *p = nullptr;
-  ~DevBuf() { if (p) cudaFree(p); }
-  int alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1) == cudaSuccess ? 0 : -1; }
+  cudaStream_t st = nullptr;
+  ~DevBuf() { if (p) cudaFreeAsync(p, st); }
+  int alloc(size_t bytes, cudaStream_t stream = nullptr) {
+    static thread_local int pool_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (pool_dev != dev) {   // keep freed scratch in the pool instead of returning it to the driver at every sync
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ULL;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      pool_dev = dev;
+    }
+    st = stream;
+    return cudaMallocAsync(&p, bytes ? bytes : 1, st) == cudaSuccess ? 0 : -1;
+  }
   template <class T> T *as() { return reinterpret_cast<T *>(p); }
 };
 
@@ -289,7 +395,7 @@ extern "C" int ttirt_iw_stats_device(int64_t M, const double *d_lfex, const doub
   if (M < 1 || !d_lfex || !d_lfapp || !out) return aux_fail("bad arguments to ttirt_iw_stats_device");
   cudaStream_t st = (cudaStream_t)stream;
   DevBuf part, scal;
-  if (part.alloc(sizeof(double) * 3 * RG) || scal.alloc(sizeof(double) * 8)) return aux_fail("out of device memory");
+  if (part.alloc(sizeof(double) * 3 * RG, st) || scal.alloc(sizeof(double) * 8, st)) return aux_fail("out of device memory");
   double *dp = part.as<double>(), *ds = scal.as<double>();
   iw_max_kernel<<<RG, RB, 0, st>>>(M, d_lfex, d_lfapp, dp);
   iw_max_final_kernel<<<1, RB, 0, st>>>(dp, ds);
@@ -320,15 +426,33 @@ extern "C" int ttirt_iw_stats_device(int64_t M, const double *d_lfex, const doub
 
 extern "C" int ttirt_mcmc_prune_device(int64_t M, const double *d_lfex, const double *d_lfapp, const double *d_u,
                                        int32_t *d_src, int64_t *num_rejects, int64_t *rej_hist, int64_t rej_hist_len, void *stream) {
-  if (M < 1 || M > 2147483647LL || !d_lfex || !d_lfapp || !d_src || (M > 1 && !d_u) || rej_hist_len < 0 || (rej_hist_len > 0 && !rej_hist))
+  if (M < 1 || M > 2147483000LL || !d_lfex || !d_lfapp || !d_src || (M > 1 && !d_u) || rej_hist_len < 0 || (rej_hist_len > 0 && !rej_hist))
     return aux_fail("bad arguments to ttirt_mcmc_prune_device");
   cudaStream_t st = (cudaStream_t)stream;
-  DevBuf cnt, hist;
-  if (cnt.alloc(sizeof(unsigned long long) * 2) || hist.alloc(sizeof(unsigned long long) * (size_t)rej_hist_len)) return aux_fail("out of device memory");
+  const int m = (int)M;
+  const int nseg = (m + SCAN_SEG - 1) / SCAN_SEG;
+  DevBuf cnt, hist, nxt, j0, j1, onp, seg;
+  if (cnt.alloc(sizeof(unsigned long long) * 2, st) || hist.alloc(sizeof(unsigned long long) * (size_t)rej_hist_len, st) || nxt.alloc(sizeof(int) * (size_t)m, st) ||
+      j0.alloc(sizeof(int) * ((size_t)m + 1), st) || j1.alloc(sizeof(int) * ((size_t)m + 1), st) || onp.alloc((size_t)m, st) || seg.alloc(sizeof(int) * (size_t)nseg, st))
+    return aux_fail("out of device memory");
   CKA(cudaMemsetAsync(cnt.p, 0, sizeof(unsigned long long) * 2, st));
   if (rej_hist_len > 0) CKA(cudaMemsetAsync(hist.p, 0, sizeof(unsigned long long) * (size_t)rej_hist_len, st));
-  mcmc_prune_kernel<<<1, 32, 0, st>>>(M, d_lfex, d_lfapp, d_u, d_src, cnt.as<unsigned long long>(), hist.as<unsigned long long>(), (int)rej_hist_len);
-  ttirt::aux_launched();
+  const unsigned g = (unsigned)((m + 1 + 255) / 256);
+  mh_next_kernel<<<g, 256, 0, st>>>(m, d_lfex, d_lfapp, d_u, nxt.as<int>());
+  mh_init_kernel<<<g, 256, 0, st>>>(m, nxt.as<int>(), j0.as<int>(), onp.as<unsigned char>());
+  int launches = 2;
+  int *ja = j0.as<int>(), *jb = j1.as<int>();
+  for (int64_t reach = 1; reach < M; reach <<= 1) {   // after round r every path node within 2^(r+1) hops of node 0 is marked
+    mh_double_kernel<<<g, 256, 0, st>>>(m, ja, jb, onp.as<unsigned char>());
+    std::swap(ja, jb);
+    launches++;
+  }
+  mh_segmax_kernel<<<nseg, SCAN_B, 0, st>>>(m, onp.as<unsigned char>(), seg.as<int>());
+  mh_segscan_kernel<<<1, SCAN_B, 0, st>>>(nseg, seg.as<int>());
+  mh_src_kernel<<<nseg, SCAN_B, 0, st>>>(m, onp.as<unsigned char>(), seg.as<int>(), d_src, cnt.as<unsigned long long>(),
+                                         hist.as<unsigned long long>(), (int)rej_hist_len);
+  launches += 3;
+  for (int i = 0; i < launches; i++) ttirt::aux_launched();
   CKA(cudaGetLastError());
   unsigned long long h[2];
   CKA(cudaMemcpyAsync(h, cnt.p, sizeof(h), cudaMemcpyDeviceToHost, st));
