@@ -148,6 +148,34 @@ class ClockSampler(object):
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Pin this rank (and, by first touch, its page-locked buffers) to the CPUs next to its GPU: with 8 ranks streaming
+    q / Z through host memory at once, remote-socket traffic is what limits the end-to-end figure."""
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip()
+        bdf = out.splitlines()[0].strip()
+        bdf = bdf.lower()
+        if bdf.startswith("00000000:"):
+            bdf = bdf[4:]
+        path = "/sys/bus/pci/devices/%s/local_cpulist" % bdf
+        with open(path) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                lo, hi = part.split("-"); cpus.update(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "cpus %s (local to GPU %d at %s)" % (spec, gpu_index, bdf)
+    except Exception as e:  # no sysfs / no permission: run unbound
+        return "unbound (%s)" % type(e).__name__
+    return "unbound"
+
+
 def measured_fp64_peak():
     """FP64 roofline denominator: tools/fp64_peak (DMMA/DFMA register loops) run live on this GPU when the
     binary is present, else the figure recorded in profiles/r01_fp64_peak.md."""
@@ -210,6 +238,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (this framework has no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    binding = bind_to_gpu_numa_node(local_rank) if world > 1 else "unbound (single rank)"
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -337,7 +366,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_all / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": config, "roofline": roofline, "cpu_baseline": cb, "e2e": e2e,
-            "gpu_launches": int(launches), "clocks": clocks, "checksum_lpz_1k": checksum}
+            "gpu_launches": int(launches), "clocks": clocks, "checksum_lpz_1k": checksum, "host_binding": binding}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
