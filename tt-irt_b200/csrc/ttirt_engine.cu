@@ -204,6 +204,38 @@ __global__ void sweep_integrate_kernel(const double *__restrict__ P, const doubl
   marg_out[a] = s;
 }
 
+// The whole right-to-left sweep in one launch (one CTA walks the dimensions; the per-element operation order is that
+// of the two kernels above, so the results are bit-identical).  The sweep is ~16 MFLOP even at the metric shape:
+// what it costs is launches, and a call of the drop-in symbol pays for it every time.
+__global__ void sweep_fused_kernel(const DimInfo *__restrict__ dims, int d, const double *__restrict__ core,
+                                   const double *__restrict__ xs, double *pk, double *marg) {
+  for (int k = d - 1; k >= 0; k--) {
+    const DimInfo di = dims[k];
+    const int rows = di.r0 * di.n, rr = di.r1;
+    const double *ck = core + di.off_c, *mg = marg + di.off_m;
+    double *P = pk + di.off_p;
+    for (int i = threadIdx.x; i < rows; i += blockDim.x) {
+      double s = 0.0;
+      for (int l = 0; l < rr; l++) s = __dadd_rn(s, __dmul_rn(mg[l], ck[i + (int64_t)l * rows]));
+      P[i] = s;
+    }
+    __syncthreads();
+    if (k > 0) {
+      const double *x = xs + di.off_x;
+      double *mo = marg + dims[k - 1].off_m;
+      for (int a = threadIdx.x; a < di.r0; a += blockDim.x) {
+        double s = 0.0;
+        for (int j = 0; j + 1 < di.n; j++) {
+          const double h = __dsub_rn(x[j + 1], x[j]);
+          s = __dadd_rn(s, __dmul_rn(__dmul_rn(__dadd_rn(P[a + j * di.r0], P[a + (j + 1) * di.r0]), h), 0.5));
+        }
+        mo[a] = s;
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // One sample's conditional on a grid, strict arithmetic (reference :105-130): abs, trapezoid prefix,
 // zero-mass fallback, reciprocal normalisation.  p and cdf are strided arrays (stride st).
 __device__ void strict_cdf(double *p, double *cdf, const double *x, int nk, int64_t st) {
@@ -400,15 +432,22 @@ static int model_load(ttirt_model *md, const double *xs, const double *core) {
   CK(cudaMemcpy(md->d_core, core, sizeof(double) * md->sum_c, cudaMemcpyHostToDevice));
   const double one = 1.0;
   CK(cudaMemcpy(md->d_marg + md->dims[d - 1].off_m, &one, sizeof(double), cudaMemcpyHostToDevice));
-  for (int64_t k = d - 1; k >= 0; k--) {
-    const DimInfo &di = md->dims[k];
-    const int rows = di.r0 * di.n;
-    sweep_contract_kernel<<<(rows + 127) / 128, 128>>>(md->d_core + di.off_c, md->d_marg + di.off_m, md->d_pk + di.off_p, rows, di.r1);
+  // small TTs (the MH / IW use of the reference: r ~ 8..16, n = 17): one CTA walks the whole sweep in less time than
+  // two launches take; larger cores use one launch per step so that the contraction spreads over the SMs
+  if (md->sum_c <= (1 << 18)) {
+    sweep_fused_kernel<<<1, 1024>>>(md->d_dims, (int)d, md->d_core, md->d_xs, md->d_pk, md->d_marg);
     LAUNCHED();
-    if (k > 0) {
-      sweep_integrate_kernel<<<(di.r0 + 127) / 128, 128>>>(md->d_pk + di.off_p, md->d_xs + di.off_x,
-                                                           md->d_marg + md->dims[k - 1].off_m, di.r0, di.n);
+  } else {
+    for (int64_t k = d - 1; k >= 0; k--) {
+      const DimInfo &di = md->dims[k];
+      const int rows = di.r0 * di.n;
+      sweep_contract_kernel<<<(rows + 127) / 128, 128>>>(md->d_core + di.off_c, md->d_marg + di.off_m, md->d_pk + di.off_p, rows, di.r1);
       LAUNCHED();
+      if (k > 0) {
+        sweep_integrate_kernel<<<(di.r0 + 127) / 128, 128>>>(md->d_pk + di.off_p, md->d_xs + di.off_x,
+                                                             md->d_marg + md->dims[k - 1].off_m, di.r0, di.n);
+        LAUNCHED();
+      }
     }
   }
   stage0_table_kernel<<<1, 32>>>(md->d_pk, md->d_xs, md->d_p0, md->d_cdf0, md->dims[0].n);
