@@ -312,3 +312,28 @@ def test_multi_device_sharding_if_available(oracle_mod):
         assert np.array_equal(Z1, Z2) and np.array_equal(l1, l2)
     with pytest.raises(RuntimeError):
         tt_irt.run_host(ns, xs, rk, c, q, n_devices=ndev + 1)
+
+
+@pytest.mark.parametrize("d,n,r,log2m", [(32, 65, 64, 17), (40, 33, 32, 18), (11, 17, 16, 19)])
+def test_fast_against_strict_at_scale(d, n, r, log2m):
+    """Beyond the sizes the CPU oracle finishes in seconds the strict GPU mode stands in for it (it is bit-exact against
+    the oracle on every shape of this file): the fast path must choose the same grid interval for every sample and
+    dimension and stay within the protocol's relative bar on all but the ill-conditioned entries."""
+    M = 1 << log2m
+    ns, xs, rk, c = synth.make_tt(d, n, r, seed=31 + d)
+    q = synth.make_q(M, d, seed=5)
+    md = tt_irt.Model(ns, xs, rk, c)
+    try:
+        Zs, ls, ixs = md.sample(q, mode=tt_irt.MODE_STRICT, want_idx=True)
+        Zf, lf, ixf = md.sample(q, mode=tt_irt.MODE_FAST, want_idx=True)
+        Zf2, lf2 = md.sample(q, mode=tt_irt.MODE_FAST)
+    finally:
+        md.close()
+    assert np.array_equal(Zf, Zf2) and np.array_equal(lf, lf2)           # deterministic
+    flips = int((ixs != ixf).sum())
+    assert flips <= 2, "%d interval indices differ between the fast and the strict path" % flips
+    dz = np.abs(Zf - Zs) / np.maximum(1.0, np.abs(Zs))
+    dl = np.abs(lf - ls) / np.maximum(1.0, np.abs(ls))
+    assert dz.max() < 1e-7 and dl.max() < 1e-9                            # ill-conditioned entries (oracle/parity.py) stay bounded
+    assert (dz > 1e-12).mean() < 2e-3 and (dl > 1e-12).mean() < 2e-3      # and rare
+    assert np.median(dz) < 1e-15 and np.median(dl) < 1e-14
