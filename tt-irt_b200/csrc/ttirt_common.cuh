@@ -137,8 +137,6 @@ struct TransArgs {
   int32_t *idx_out;          // column k+1 of the exported index array (may be NULL)
   double *lpz;               // final log-density (written when last)
   int *hist_next;            // n1-1 counters for binning dimension k+1 (unused when last)
-  unsigned stagger_ns;       // start offset (ns) of the warps selected by stagger_mask (0: none)
-  unsigned stagger_mask;
 };
 
 // fast-path shape classes: (rank tiles of 8, grid tiles of 8)

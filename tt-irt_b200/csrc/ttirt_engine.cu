@@ -64,18 +64,6 @@ void aux_launched() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 #define LAUNCHED() g_launches.fetch_add(1, std::memory_order_relaxed)
 
-static unsigned stagger_ns() {
-  static int v = -1;
-  if (v < 0) { const char *e = getenv("TTIRT_STAGGER_NS"); v = e ? atoi(e) : 0; }
-  return (unsigned)v;
-}
-
-static unsigned stagger_mask() {
-  static int v = -1;
-  if (v < 0) { const char *e = getenv("TTIRT_STAGGER_MASK"); v = e ? atoi(e) : 4; }
-  return (unsigned)v;
-}
-
 static int64_t default_chunk() {
   int64_t c = g_chunk.load();
   if (c > 0) return c;
@@ -562,7 +550,6 @@ static int run_chunk(ttirt_model *md, Workspace &w, int64_t rows, const double *
     a.q = q + ldq * (k + 1); a.z = z + ldz * (k + 1);
     a.idx_out = idx_out ? idx_out + ldz * (k + 1) : nullptr;
     a.lpz = lpz; a.hist_next = w.hist + (size_t)(k + 1) * nbpad;
-    a.stagger_ns = stagger_ns(); a.stagger_mask = stagger_mask();
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (md->profile) {
       if (md->prof_used == md->prof_events.size()) {

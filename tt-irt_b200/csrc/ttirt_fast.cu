@@ -9,13 +9,13 @@
 //   (2) conditional pdf on the grid of dimension k+1 (reference :103-105): p = |F' P_{k+1}|, a second
 //       DMMA contraction whose A operand is the accumulator of (1) used in place (the contraction
 //       index is permuted identically on both operands, so no register shuffles are needed).
-//   (3) trapezoid CDF as a 4-lane prefix straight from the accumulator registers (:107-113),
-//       normalisation (:116-130), interval search (:134-142), closed-form quadratic inversion
-//       (:146-159), log-density accumulation (:161-165), emission of (interval, w1, w2) and the
+//   (3) trapezoid CDF of the weighted pdf (:107-113), interval search (:134-142), closed-form quadratic
+//       inversion (:146-159), log-density accumulation (:161-165), emission of (interval, w1, w2) and the
 //       histogram that drives the next counting sort.
 //
-// Work decomposition: a warp owns 16 samples end to end (two 8-row MMA tiles); warps never synchronise
-// with each other except when their CTA moves to the next interval bin and restages a slab.
+// Work decomposition: (1) and (2) run in eight MMA warps, each owning 16 samples per tile (two 8-row MMA
+// tiles); (3) runs in four tail warps that receive the pdf tiles through shared memory.  The MMA warps only meet
+// when their CTA moves to the next interval bin and restages a slab.
 #include "ttirt_common.cuh"
 
 namespace ttirt {
