@@ -337,3 +337,32 @@ def test_fast_against_strict_at_scale(d, n, r, log2m):
     assert dz.max() < 1e-7 and dl.max() < 1e-9                            # ill-conditioned entries (oracle/parity.py) stay bounded
     assert (dz > 1e-12).mean() < 2e-3 and (dl > 1e-12).mean() < 2e-3      # and rare
     assert np.median(dz) < 1e-15 and np.median(dl) < 1e-14
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_ragged_shapes(oracle_mod, seed):
+    """Seeded random TTs with a different grid size, grid spacing and rank in every dimension (the reference supports
+    them through its offset tables, tt_irt1_int32.c:41-57), q including exact 0 and 1: strict bit-exact, fast within
+    the protocol.  Shapes straddle the three fast-path classes and the strict-only range."""
+    rng = np.random.default_rng(1000 + seed)
+    d = int(rng.integers(1, 9))
+    rmax = int(rng.choice([3, 8, 16, 24, 32, 50, 64, 70]))
+    nmax = int(rng.choice([2, 9, 17, 24, 33, 40, 65, 72, 90]))
+    ns = rng.integers(2, nmax + 1, size=d)
+    rk = np.concatenate([[1], rng.integers(1, rmax + 1, size=d - 1), [1]]).astype(np.int64)
+    xs = np.concatenate([np.sort(rng.uniform(-2.0, 3.0, size=n)) for n in ns])
+    c = rng.random(int((rk[:-1] * ns * rk[1:]).sum()))
+    M = int(rng.integers(1, 700))
+    q = np.asfortranarray(rng.random((M, d)))
+    q[rng.integers(0, M), rng.integers(0, d)] = 0.0
+    q[rng.integers(0, M), rng.integers(0, d)] = 1.0
+    Zo, lo, io, kap, gap, cond, lsens = _oracle(oracle_mod, ns, xs, rk, c, q)
+    md = tt_irt.Model(ns, xs, rk, c)
+    try:
+        Zs, ls, isx = md.sample(q, mode=tt_irt.MODE_STRICT, want_idx=True)
+        assert np.array_equal(Zs, Zo) and np.array_equal(isx, io), (ns, rk)
+        Zf, lf, ifx = md.sample(q, mode=tt_irt.MODE_FAST, want_idx=True)
+        stats, fails = oracle_mod.parity.compare(Zf, lf, ifx, Zo, lo, io, cond, gap, lsens=lsens)
+        assert not fails, (fails, stats, ns, rk)
+    finally:
+        md.close()
