@@ -32,7 +32,8 @@ def load_library():
         if not hits:
             raise RuntimeError("tt_irt1*.so not found next to %s: run `make -C tt-irt_b200` "
                                "(this package has no CPU fallback)" % __file__)
-        lib = cdll.LoadLibrary(hits[0])
+        # TTIRT_LIBRARY: an alternative build of the same library (kernel experiments); default is the in-tree one
+        lib = cdll.LoadLibrary(os.environ.get("TTIRT_LIBRARY", hits[0]))
         ip, dp, lp = POINTER(c_int), POINTER(c_double), POINTER(c_longlong)
         lib.tt_irt1.restype = None
         lib.tt_irt1.argtypes = [c_int, ip, dp, ip, dp, c_int, dp, dp, dp]
