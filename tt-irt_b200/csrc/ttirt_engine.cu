@@ -93,6 +93,17 @@ struct Workspace {
   int32_t *idx_out = nullptr;
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
+  // CUDA graphs of a chunk's whole kernel sequence (memset, stage 0, per dimension scan / scatter / transition):
+  // small and medium shapes are bound by those ~3d launches, a replayed graph costs one
+  struct ChunkGraph {
+    int64_t rows = 0, ldq = 0, ldz = 0;
+    const double *q = nullptr; double *z = nullptr, *lpz = nullptr; int32_t *idx_out = nullptr;
+    int mode = 0;
+    cudaGraphExec_t exec = nullptr;
+    uint64_t last_use = 0;
+  };
+  std::vector<ChunkGraph> graphs;
+  uint64_t graph_clock = 0;
 };
 
 struct ttirt_model {
@@ -117,7 +128,13 @@ struct ttirt_model {
   double prof_flops = 0.0;
 };
 
+static void ws_drop_graphs(Workspace &w) {
+  for (auto &g : w.graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  w.graphs.clear();
+}
+
 static void ws_free(Workspace &w) {
+  ws_drop_graphs(w);
   cudaFree(w.F); cudaFree(w.idx); cudaFree(w.perm); cudaFree(w.w1); cudaFree(w.w2); cudaFree(w.lp); cudaFree(w.lpd); cudaFree(w.lpe);
   cudaFree(w.hist); cudaFree(w.bin_start); cudaFree(w.bin_tile_start); cudaFree(w.cursor);
   cudaFree(w.left); cudaFree(w.pbuf); cudaFree(w.cbuf);
@@ -133,7 +150,7 @@ static int ws_ensure(ttirt_model *md, Workspace &w, int64_t rows, bool strict, b
   w.stream = nullptr; w.done = nullptr;
   const bool s = strict || w.strict, h = host || w.host, wi = want_idx || w.want_idx;
   const int64_t cap = rows > w.cap ? rows : w.cap;
-  ws_free(w);
+  ws_free(w);   // (drops the chunk graphs: they hold the old pointers)
   w.stream = keep_s; w.done = keep_e;
   w.cap = cap; w.strict = s; w.host = h; w.want_idx = wi;
   const int64_t d = md->d;
@@ -512,8 +529,14 @@ extern "C" int ttirt_model_get_sweep(const ttirt_model *md, double *pk_out, doub
 // ------------------------------------------------------------------------------------------------
 // one chunk, device-resident buffers, enqueued on st
 // ------------------------------------------------------------------------------------------------
-static int run_chunk(ttirt_model *md, Workspace &w, int64_t rows, const double *q, int64_t ldq, double *z, int64_t ldz,
-                     double *lpz, int32_t *idx_out, int mode, cudaStream_t st) {
+// kernels in one chunk's sequence (what a graph replay launches)
+static int64_t g_launches_per_graph(const ttirt_model *md, int mode) {
+  if (mode == TTIRT_MODE_STRICT || md->fast_cls < 0) return 1;
+  return 1 + 3 * (md->d - 1);
+}
+
+static int enqueue_chunk(ttirt_model *md, Workspace &w, int64_t rows, const double *q, int64_t ldq, double *z, int64_t ldz,
+                         double *lpz, int32_t *idx_out, int mode, cudaStream_t st) {
   const int d = (int)md->d;
   if (rows <= 0) return 0;
   if (mode == TTIRT_MODE_STRICT || md->fast_cls < 0) {
@@ -566,6 +589,60 @@ static int run_chunk(ttirt_model *md, Workspace &w, int64_t rows, const double *
     LAUNCHED();
     if (e1) CK(cudaEventRecord(e1, st));
   }
+  return 0;
+}
+
+static bool graphs_enabled() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("TTIRT_GRAPHS"); v = e ? atoi(e) != 0 : 1; }
+  return v != 0;
+}
+
+// One chunk on stream st: replay the chunk's CUDA graph when there is one for exactly these buffers, else capture it
+// while enqueueing (the legacy default stream cannot be captured, and per-launch profiling needs its events outside
+// a graph: both enqueue directly).
+static int run_chunk(ttirt_model *md, Workspace &w, int64_t rows, const double *q, int64_t ldq, double *z, int64_t ldz,
+                     double *lpz, int32_t *idx_out, int mode, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  // large chunks are not launch-bound, and the device-resident API would need one graph per chunk offset
+  if (!graphs_enabled() || st == nullptr || md->profile || rows > (1 << 19)) return enqueue_chunk(md, w, rows, q, ldq, z, ldz, lpz, idx_out, mode, st);
+  for (auto &g : w.graphs) {
+    if (g.rows == rows && g.q == q && g.ldq == ldq && g.z == z && g.ldz == ldz && g.lpz == lpz && g.idx_out == idx_out && g.mode == mode) {
+      g.last_use = ++w.graph_clock;
+      CK(cudaGraphLaunch(g.exec, st));
+      g_launches.fetch_add(g_launches_per_graph(md, mode), std::memory_order_relaxed);
+      return 0;
+    }
+  }
+  cudaGraph_t graph = nullptr;
+  if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    return enqueue_chunk(md, w, rows, q, ldq, z, ldz, lpz, idx_out, mode, st);
+  }
+  const int64_t before = g_launches.load();
+  const int rc = enqueue_chunk(md, w, rows, q, ldq, z, ldz, lpz, idx_out, mode, st);
+  const cudaError_t ec = cudaStreamEndCapture(st, &graph);
+  g_launches.store(before);   // nothing ran yet
+  if (rc != 0 || ec != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    return rc != 0 ? rc : fail("CUDA graph capture of a chunk failed: %s", cudaGetErrorString(ec));
+  }
+  Workspace::ChunkGraph g;
+  g.rows = rows; g.q = q; g.ldq = ldq; g.z = z; g.ldz = ldz; g.lpz = lpz; g.idx_out = idx_out; g.mode = mode;
+  const cudaError_t ei = cudaGraphInstantiate(&g.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ei != cudaSuccess) { cudaGetLastError(); return enqueue_chunk(md, w, rows, q, ldq, z, ldz, lpz, idx_out, mode, st); }
+  if (w.graphs.size() >= 8) {   // least recently used out
+    size_t lru = 0;
+    for (size_t i = 1; i < w.graphs.size(); i++) if (w.graphs[i].last_use < w.graphs[lru].last_use) lru = i;
+    cudaGraphExecDestroy(w.graphs[lru].exec);
+    w.graphs.erase(w.graphs.begin() + lru);
+  }
+  g.last_use = ++w.graph_clock;
+  w.graphs.push_back(g);
+  CK(cudaGraphLaunch(g.exec, st));
+  g_launches.fetch_add(g_launches_per_graph(md, mode), std::memory_order_relaxed);
   return 0;
 }
 
@@ -682,6 +759,10 @@ static int sample_host_rows(ttirt_model *md, int64_t m_begin, int64_t m_end, con
   const int d = (int)md->d;
   const bool strict = (mode == TTIRT_MODE_STRICT) || md->fast_cls < 0;
   int64_t chunk = default_chunk();
+  // light shapes (r <= 16: 2^17 rows, r <= 32: 2^19 rows per chunk): a chunk computes in about a millisecond, so the pipeline is cut finer
+  // (shorter fill and drain, copies and kernels of neighbouring chunks overlap) and every chunk is a graph replay
+  if (g_chunk.load() <= 0 && getenv("TTIRT_CHUNK") == nullptr && !strict && md->fast_cls >= 0 && md->fast_cls <= 1)
+    chunk = md->fast_cls == 0 ? (1 << 17) : (1 << 19);
   if (M < chunk * kSlots) chunk = std::max<int64_t>((M + kSlots - 1) / kSlots, std::min<int64_t>(M, 1 << 16));
   const int64_t nchunks = (M + chunk - 1) / chunk;
   const int nslots = (int)std::min<int64_t>(kSlots, nchunks);
