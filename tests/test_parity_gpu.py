@@ -366,3 +366,25 @@ def test_random_ragged_shapes(oracle_mod, seed):
         assert not fails, (fails, stats, ns, rk)
     finally:
         md.close()
+
+
+@pytest.mark.parametrize("M,extra", [(5000, 7), (400000, 3)])
+def test_host_pipeline_with_padded_leading_dimension(M, extra):
+    """ttirt_sample_host on column-major arrays whose leading dimension exceeds M (a row block of a larger matrix):
+    the direct and the bounce-buffer pipelines must read and write only their own rows."""
+    d, n, r = 8, 17, 8
+    ns, xs, rk, c = synth.make_tt(d, n, r, seed=3)
+    ld = M + extra
+    qbig = np.asfortranarray(np.random.default_rng(0).random((ld, d)))
+    zbig = np.full((ld, d), -7.0, order="F"); lbig = np.full(ld, -7.0)
+    md = tt_irt.Model(ns, xs, rk, c)
+    try:
+        Zref, lref = md.sample(np.asfortranarray(qbig[:M]))
+        lib = tt_irt.load_library()
+        dp = ctypes.POINTER(ctypes.c_double)
+        rc = lib.ttirt_sample_host(md._h, M, qbig.ctypes.data_as(dp), zbig.ctypes.data_as(dp), lbig.ctypes.data_as(dp), None, ld, tt_irt.MODE_FAST)
+        assert rc == 0
+    finally:
+        md.close()
+    assert np.array_equal(zbig[:M], Zref) and np.array_equal(lbig[:M], lref)
+    assert (zbig[M:] == -7.0).all() and (lbig[M:] == -7.0).all()      # rows beyond M untouched
