@@ -8,7 +8,8 @@ from tt_irt_py import synth
 import torch
 lib = ctypes.CDLL(os.path.abspath(sys.argv[1]))
 log2m = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-d, n, r, M = 32, 65, 64, 1 << log2m
+d, n, r = [int(x) for x in os.environ.get("PT_SHAPE", "32,65,64").split(",")]
+M = 1 << log2m
 ns, xs, rk, c = synth.make_tt(d, n, r, seed=2026)
 lp, dp = ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_double)
 lib.ttirt_model_create.restype = ctypes.c_void_p
@@ -27,15 +28,15 @@ per_warp = np.array(list(out)[8:], dtype=np.float64)
 names = ["slab/bin", "wait TMA", "update MMA", "issue+F' store", "pdf MMA+tailcol", "cdf+search", "inversion tail+out", "loop head"]
 tot = v.sum()
 warps = int(os.environ.get("PT_WARPS", "8")); mt = int(os.environ.get("PT_MT", "2"))
-ntiles = 31.0 * M / (8 * mt)          # warp-tiles per call (31 transitions)
+ntiles = (d - 1.0) * M / (8 * mt)      # warp-tiles per call (d-1 transitions)
 for nm, x in zip(names, v):
     print("%-20s %6.2f%%  %8.0f cycles per warp-tile" % (nm, 100 * x / tot, x / ntiles))
 print("total %.0f cycles per warp-tile" % (tot / ntiles))
 tail = np.array(list(out)[24:30], dtype=np.float64)
-uses = 31.0 * M / 16           # parked tiles per call
+uses = (d - 1.0) * M / 16      # parked tiles per call
 for nm, x in zip(["tail: wait FULL", "tail: pass", "tail: search+release", "tail: inversion+out (per pair)", "tail: loop"], tail):
     print("%-32s %8.0f cycles per parked tile" % (nm, x / uses))
-print("loop time per warp id (mean cycles per launch per CTA):", np.round(per_warp[:warps] / (31.0 * 148)).astype(int).tolist())
+print("loop time per warp id (mean cycles per launch per CTA):", np.round(per_warp[:warps] / ((d - 1.0) * 148)).astype(int).tolist())
 
 # timeline of the two MMA warps of sub-partition 0 of CTA 0 (last launch): clock at the end of every phase
 tr = (ctypes.c_longlong * (2 * 24 * 8))()

@@ -106,17 +106,20 @@ __device__ void stage_p_weighted(double *dst, const double *__restrict__ src, in
 #define TTIRT_MMA_WARPS 8
 #endif
 constexpr int MMA_WARPS = TTIRT_MMA_WARPS;    // two per SM sub-partition: they share the FP64 tensor pipe (4: experiment, one per sub-partition)
-constexpr int TAIL_WARPS = 4;   // one per SM sub-partition: CDF, search, inversion of the tiles its two MMA warps produce
+// Tail warps per CTA (template parameter TW): 4 for the r <= 64 class (one per SM sub-partition, each serving two MMA
+// warps: the MMA side is the long one there) and 8 for the lighter classes, where the per-row tail work is as long as
+// the DMMA work and every MMA warp gets a tail warp of its own.
 constexpr int MT = 2;           // 8-row MMA tiles per MMA warp
 constexpr int WROWS = 8 * MT;   // samples per warp tile
-constexpr int NTHR = 32 * (MMA_WARPS + TAIL_WARPS);
 constexpr int ROWS_CTA = MMA_WARPS * WROWS;
-constexpr int PRODS = MMA_WARPS / TAIL_WARPS;   // producers per tile buffer
+__host__ __device__ constexpr int nthr_of(int tw) { return 32 * (MMA_WARPS + tw); }
 // register file split (setmaxnreg, per warpgroup of four warps): launched at 168 per thread, the tail warpgroup
-// shrinks to TAIL_REGS and the two MMA warpgroups grow to MMA_REGS; 32 * (8 * 192 + 4 * 120) = 32 * 12 * 168: the pool is exactly what the launch allocated
-constexpr int MMA_REGS = 192, TAIL_REGS = 120;
+// shrinks to tail_regs and the two MMA warpgroups grow to mma_regs; 32 * (8 * 192 + 4 * 120) = 32 * 12 * 168 and
+// 32 * (8 * 152 + 8 * 104) = 32 * 16 * 128: the pool is exactly what the launch allocated
+__host__ __device__ constexpr int mma_regs_of(int tw) { return tw == 4 ? 192 : 152; }
+__host__ __device__ constexpr int tail_regs_of(int tw) { return tw == 4 ? 120 : 104; }
 
-template <int RT, int NT, bool TAIL1>
+template <int RT, int NT, bool TAIL1, int TW>
 struct SmemLayout {
   static constexpr int KPMAX = (8 * RT + 15) & ~15;
   static constexpr int SLAB = 8 * RT * KPMAX;      // doubles per slab buffer
@@ -132,8 +135,8 @@ struct SmemLayout {
   static constexpr int HS = TAIL1 ? 4 * (NT - 1) : 4 * NT;   // cells walked by each of the two lanes of a row
   static constexpr int HB = HS / 4;                // ... as four blocks of HB consecutive cells, walked side by side
   static constexpr int NHH = 2 * HS + 8;           // entries of the per-node tables rw / hr
-  static constexpr size_t bytes = sizeof(double) * (2 * SLAB + PN + MMA_WARPS * FTILE + TAIL_WARPS * PB + 2 * NHH + 2 * 8 * NT) +
-                                  sizeof(int) * (2 * (NBMAX + 1) + NBMAX + TAIL_WARPS * (WROWS + 1));
+  static constexpr size_t bytes = sizeof(double) * (2 * SLAB + PN + MMA_WARPS * FTILE + TW * PB + 2 * NHH + 2 * 8 * NT) +
+                                  sizeof(int) * (2 * (NBMAX + 1) + NBMAX + TW * (WROWS + 2));
 };
 
 // Named barriers (id 0 is __syncthreads).  Tile hand-over between an MMA warp and its tail warp is a 64-thread
@@ -141,10 +144,15 @@ struct SmemLayout {
 // for the F' stores and the row gather still in flight.
 //   1                 the eight MMA warps (slab restaging at a bin change)
 //   2 + tw            FULL : a producer of buffer tw arrives after parking a tile, tail warp tw waits
-//   6 + 4*p + tw      EMPTY: tail warp tw arrives when producer p (0 / 1) may overwrite the buffer, producer p waits
+//   6 + 4*p + tw      EMPTY (TW == 4): tail warp tw arrives when producer p (0 / 1) may overwrite the buffer, producer p waits.
+//                     With TW == 8 the ids would not fit (2 + 8 + 8 > 16): the single producer of a buffer polls a counter
+//                     in shared memory that its tail warp bumps after its last read of the tile (same warp, same memory pipe:
+//                     the store follows the loads).
 __device__ __forceinline__ void bar_mma_warps() { asm volatile("bar.sync 1, %0;" ::"n"(32 * MMA_WARPS) : "memory"); }
 __device__ __forceinline__ void bar_pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void bar_pair_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ int ld_volatile_s(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
+__device__ __forceinline__ void st_volatile_s(int *p, int v) { *reinterpret_cast<volatile int *>(p) = v; }
 
 // EXACT: r0 == r1 == 8*RT and ceil(n1/8) == NT, so every tile loop runs its full static trip count and no
 // guard branches are compiled in (the steady state of a uniform-rank TT).  TAIL1 (EXACT only): n1 == 8*(NT-1)+1,
@@ -161,10 +169,11 @@ __device__ __forceinline__ void bar_pair_arrive(int id) { asm volatile("bar.arri
 // Row gather: the left-interface rows of an MMA warp's NEXT tile are fetched asynchronously (cp.async / LDGSTS, one
 // coalesced 8*r0-byte row per instruction) into a per-warp shared tile as soon as the current tile's update
 // phase has consumed that tile, i.e. a whole pdf phase ahead of use.
-template <int RT, int NT, bool EXACT, bool TAIL1>
-__global__ void __launch_bounds__(NTHR, 1) transition_kernel(const TransArgs a) {
+template <int RT, int NT, bool EXACT, bool TAIL1, int TW>
+__global__ void __launch_bounds__(nthr_of(TW), 1) transition_kernel(const TransArgs a) {
   static_assert(EXACT || !TAIL1, "TAIL1 needs EXACT");
-  using L = SmemLayout<RT, NT, TAIL1>;
+  using L = SmemLayout<RT, NT, TAIL1, TW>;
+  constexpr int TAIL_WARPS = TW, NTHR = nthr_of(TW), PRODS = MMA_WARPS / TW;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *slab0 = reinterpret_cast<double *>(smem_raw);
   double *slab1 = slab0 + L::SLAB;
@@ -180,6 +189,7 @@ __global__ void __launch_bounds__(NTHR, 1) transition_kernel(const TransArgs a) 
   int *hist = bst + (L::NBMAX + 1);                   // histogram of the intervals chosen in dimension k+1
   int *ids_all = hist + L::NBMAX;                     // per tail warp: sample ids of the parked tile
   int *nv_all = ids_all + TAIL_WARPS * WROWS;         // per tail warp: valid rows of the parked tile
+  int *consumed = nv_all + TAIL_WARPS;                // per tail warp: parked tiles released so far (TW == 8 hand-back)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int FP = L::FPITCH, RS = L::RS;
@@ -203,6 +213,7 @@ __global__ void __launch_bounds__(NTHR, 1) transition_kernel(const TransArgs a) 
     ihs[i] = (i + 1 < n1) ? 1.0 / (a.xnext[i + 1] - a.xnext[i]) : 0.0;
     if (i < L::NBMAX) hist[i] = 0;
   }
+  if (tid < TAIL_WARPS) consumed[tid] = 0;
   stage_p_weighted(Ps, a.pnext, r1, n1, KP, 8 * NT, a.xnext, tid, NTHR);
   __syncthreads();
 
@@ -210,7 +221,7 @@ __global__ void __launch_bounds__(NTHR, 1) transition_kernel(const TransArgs a) 
   const int t_begin = (int)(((int64_t)blockIdx.x * total_tiles) / gridDim.x);
   const int t_end = (int)(((int64_t)(blockIdx.x + 1) * total_tiles) / gridDim.x);
 
-  const bool is_tail = warp < TAIL_WARPS;   // warps 0-3: tail, 4-11: MMA (role changes at warpgroup granularity for setmaxnreg)
+  const bool is_tail = warp < TAIL_WARPS;   // tail warps first, then the MMA warps (role changes at warpgroup granularity for setmaxnreg)
   if (is_tail) {
     // =========================================== tail warps ===========================================
     // Lanes l and l+16 share row l & 15 of the parked tile, lane l the lower half of the grid and lane l+16 the upper
@@ -222,7 +233,7 @@ __global__ void __launch_bounds__(NTHR, 1) transition_kernel(const TransArgs a) 
     // and the CDF pass is a plain running sum.  Next to a DMMA stream every instruction of another warp waits for a
     // gap between two DMMAs (~20 cycles, whatever its type), so the tail is written for instruction count: one pass,
     // a two-level search on integer bit patterns, one inversion per pair of tiles.
-    if (NTHR > 256) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TAIL_REGS));
+    if (NTHR > 256) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(tail_regs_of(TW)));
     const int tw = warp, row = lane & 15, hf = lane >> 4;
     const double *pbr = pb_all + tw * L::PB + row;
     const int *ids = ids_all + tw * WROWS;
@@ -234,15 +245,25 @@ __global__ void __launch_bounds__(NTHR, 1) transition_kernel(const TransArgs a) 
     int st_nv = 0, st_m = 0, st_i0 = 0, st_E = 0;
     double st_dq = 0.0, st_c1 = 1.0, st_c2 = 1.0, st_mass = 1.0, st_N = 1.0, st_D = 1.0;
     TT_DECL
-    for (int seq = 0; seq < uses; ++seq) {
+    // hand the buffer back: to the other producer through its EMPTY barrier (TW == 4), to the only one through the counter
+    auto release = [&](int seq) {
+      if (TW == 4) {
+        if (seq + 1 < uses) bar_pair_arrive(6 + 4 * ((seq + 1) % PRODS) + tw);
+      } else {
+        __syncwarp();
+        if (lane == 0) st_volatile_s(consumed + tw, seq + 1);
+      }
+    };
+    for (int seq = 0; seq < uses + (uses & 1); ++seq) {   // an odd count gets one empty pass that finishes the waiting tile
       TT_MARK(4)
-      bar_pair_sync(2 + tw);                        // FULL: the tile of producer seq & 1 is parked
+      const bool real = seq < uses;
+      if (real) bar_pair_sync(2 + tw);              // FULL: the next tile is parked
       TT_MARK(0)
-      int nv = nv_all[tw];
+      int nv = real ? nv_all[tw] : 0;
       int m = 0, i0 = 0, lpE = 0;
       double dq = 0.0, c1 = 1.0, c2 = 1.0, mass = 1.0, lpN = 1.0, lpD = 1.0;
       if (nv == 0) {
-        if (seq + 1 < uses) bar_pair_arrive(6 + 4 * ((seq + 1) % PRODS) + tw);
+        if (real) release(seq);
       } else {
         m = ids[row];
         const double qv = a.q[m];
@@ -313,7 +334,7 @@ __global__ void __launch_bounds__(NTHR, 1) transition_kernel(const TransArgs a) 
         }
         const double s2 = pow2_scale(total);         // exact power-of-two normalisation instead of 1/mass
         c1 *= s2; c2 *= s2;                          // (consumes the loads before the buffer is handed back)
-        if (seq + 1 < uses) bar_pair_arrive(6 + 4 * ((seq + 1) % PRODS) + tw);   // EMPTY: the other producer may park its tile
+        release(seq);                                // the (other) producer may park its next tile
         dq *= s2;
         mass = total * s2;
         if (total == 0.0) {
@@ -353,7 +374,7 @@ __global__ void __launch_bounds__(NTHR, 1) transition_kernel(const TransArgs a) 
     TT_FLUSH
   } else {
     // =========================================== MMA warps ============================================
-    if (NTHR > 256) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(MMA_REGS));
+    if (NTHR > 256) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(mma_regs_of(TW)));
     const int g = lane >> 2, t = lane & 3;
     const int mw = warp - TAIL_WARPS;          // index among the MMA warps
     const int mtid = 32 * mw + lane;
@@ -560,7 +581,13 @@ __global__ void __launch_bounds__(NTHR, 1) transition_kernel(const TransArgs a) 
       // ---- (3) park the signed pdf tile for the tail warp (it takes |.|, reference :105); the two producers of a buffer alternate ----
       {
         // producer 0 waits for the tail warp to have released producer 1's previous tile, and vice versa
-        if (prod > 0 || tile > t_begin) bar_pair_sync(6 + 4 * prod + tw);
+        if (TW == 4) {
+          if (prod > 0 || tile > t_begin) bar_pair_sync(6 + 4 * prod + tw);
+        } else {
+          if (lane == 0)
+            while (ld_volatile_s(consumed + tw) < tile - t_begin) __nanosleep(20);   // every earlier tile of this warp released
+          __syncwarp();
+        }
         PT_MARK(5)
         if (nvalid > 0) {
 #pragma unroll
@@ -595,32 +622,37 @@ __global__ void __launch_bounds__(NTHR, 1) transition_kernel(const TransArgs a) 
   }
 }
 
-template <int RT, int NT, bool EXACT, bool TAIL1>
+template <int RT, int NT, bool EXACT, bool TAIL1, int TW>
 cudaError_t launch_variant(const TransArgs &a, int sm_count, cudaStream_t st) {
-  using L = SmemLayout<RT, NT, TAIL1>;
+  using L = SmemLayout<RT, NT, TAIL1, TW>;
   int64_t max_tiles = ((int64_t)a.rows + ROWS_CTA - 1) / ROWS_CTA + (a.n0 - 1);
-  int64_t grid = sm_count;   // persistent: one CTA per SM (shared memory allows no more)
+  int64_t grid = sm_count;   // persistent: one CTA per SM (the register file allows no more)
   if (grid > max_tiles) grid = max_tiles;
   if (grid < 1) grid = 1;
-  transition_kernel<RT, NT, EXACT, TAIL1><<<(unsigned)grid, NTHR, L::bytes, st>>>(a);
+  transition_kernel<RT, NT, EXACT, TAIL1, TW><<<(unsigned)grid, nthr_of(TW), L::bytes, st>>>(a);
   return cudaGetLastError();
 }
 
-template <int RT, int NT>
+template <int RT, int NT, int TW>
 cudaError_t launch_one(const TransArgs &a, int sm_count, cudaStream_t st) {
   const bool exact = a.r0 == 8 * RT && a.r1 == 8 * RT && (a.n1 + 7) / 8 == NT;
-  if (exact && a.n1 == 8 * (NT - 1) + 1) return launch_variant<RT, NT, true, true>(a, sm_count, st);
-  if (exact) return launch_variant<RT, NT, true, false>(a, sm_count, st);
-  return launch_variant<RT, NT, false, false>(a, sm_count, st);
+  if (exact && a.n1 == 8 * (NT - 1) + 1) return launch_variant<RT, NT, true, true, TW>(a, sm_count, st);
+  if (exact) return launch_variant<RT, NT, true, false, TW>(a, sm_count, st);
+  return launch_variant<RT, NT, false, false, TW>(a, sm_count, st);
 }
 
-template <int RT, int NT>
+template <int RT, int NT, int TW>
 cudaError_t init_one() {
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(transition_kernel<RT, NT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout<RT, NT, true>::bytes)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(transition_kernel<RT, NT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout<RT, NT, false>::bytes)) != cudaSuccess) return e;
-  return cudaFuncSetAttribute(transition_kernel<RT, NT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout<RT, NT, false>::bytes);
+  if ((e = cudaFuncSetAttribute(transition_kernel<RT, NT, true, true, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout<RT, NT, true, TW>::bytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(transition_kernel<RT, NT, true, false, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout<RT, NT, false, TW>::bytes)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(transition_kernel<RT, NT, false, false, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout<RT, NT, false, TW>::bytes);
 }
+
+#ifndef TTIRT_LIGHT_TW
+#define TTIRT_LIGHT_TW 8    // tail warps of the two lighter classes
+#endif
+constexpr int kLightTW = TTIRT_LIGHT_TW;
 
 }  // namespace
 
@@ -635,17 +667,17 @@ int fast_rows_per_cta(int) { return ROWS_CTA; }
 
 cudaError_t fast_init(int) {
   cudaError_t e;
-  if ((e = init_one<2, 3>()) != cudaSuccess) return e;
-  if ((e = init_one<4, 5>()) != cudaSuccess) return e;
-  if ((e = init_one<8, 9>()) != cudaSuccess) return e;
+  if ((e = init_one<2, 3, kLightTW>()) != cudaSuccess) return e;
+  if ((e = init_one<4, 5, kLightTW>()) != cudaSuccess) return e;
+  if ((e = init_one<8, 9, 4>()) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
 cudaError_t launch_transition(int cls, const TransArgs &a, int sm_count, cudaStream_t st) {
   switch (cls) {
-    case 0: return launch_one<2, 3>(a, sm_count, st);
-    case 1: return launch_one<4, 5>(a, sm_count, st);
-    case 2: return launch_one<8, 9>(a, sm_count, st);
+    case 0: return launch_one<2, 3, kLightTW>(a, sm_count, st);
+    case 1: return launch_one<4, 5, kLightTW>(a, sm_count, st);
+    case 2: return launch_one<8, 9, 4>(a, sm_count, st);
     default: return cudaErrorInvalidValue;
   }
 }
