@@ -13,7 +13,7 @@ cond is the oracle's first-order sensitivity of x_k to O(eps) perturbations of (
 formula's cancellation factor; the cumulative sum carries an ill-conditioned early coordinate into the
 later ones.  lsens_k = |d log p(x_k) / d x_k| of the interpolated conditional carries the same admitted
 perturbation of x_k into the log-density: an entry whose Z is ill-conditioned has an equally ill-conditioned lPz
-(the reference's own two BLAS builds show lPz differences of 0.4 * |dZ| on such entries, tools/lpz_outlier.py).
+(the reference's own two BLAS builds show lPz differences of 0.4 * |dZ| on such entries, tests/devtools/lpz_outlier.py).
 The reference's own OpenBLAS-vs-netlib spread sits below 2 * eps * cumsum(cond) on every
 BASELINE shape (tests/test_oracle.py asserts that), CFAC = 8 leaves a 4x margin.
 """

@@ -1,9 +1,9 @@
 """Measurement of the rows either side of tt_irt1 on one B200: device-resident
 throughput with CUDA events against the HBM roofline (MEASURED_PEAKS.json), the numpy restatement timed beside it.
-usage (under gpurun): python tools/bench_aux.py > gpurun_out/aux_bench.json"""
+usage (under gpurun): python tests/devtools/bench_aux.py > gpurun_out/aux_bench.json"""
 import ctypes, json, os, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "tt-irt_b200")); sys.path.insert(0, ROOT)
 import torch
 from tt_irt_py import synth, tt_irt

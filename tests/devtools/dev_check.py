@@ -1,7 +1,7 @@
 """Development check on a GPU box: sweep, strict and fast paths against the oracle on several shapes."""
 import os, sys, time, json
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "tt-irt_b200")); sys.path.insert(0, ROOT)
 from tt_irt_py import synth, tt_irt
 import oracle

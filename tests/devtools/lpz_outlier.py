@@ -1,7 +1,7 @@
 """Diagnose lPz parity outliers: per-dimension Z error, condition and density slope of the worst samples."""
 import os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "tt-irt_b200")); sys.path.insert(0, ROOT)
 from tt_irt_py import synth, tt_irt
 import oracle

@@ -2,7 +2,7 @@
 # Quick GPU check of a kernel change, every step under its own timeout:
 #   parity on all dev shapes, the GPU test suite, a short bench line, the phase-timing build if present.
 TAG=${1:-q}
-timeout 120 python tools/dev_check.py 2>&1 | python -c "
+timeout 120 python tests/devtools/dev_check.py 2>&1 | python -c "
 import sys,json
 for l in sys.stdin:
     try: j=json.loads(l)
