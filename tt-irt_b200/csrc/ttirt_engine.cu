@@ -75,7 +75,7 @@ static int64_t default_chunk() {
 // ------------------------------------------------------------------------------------------------
 // model
 // ------------------------------------------------------------------------------------------------
-constexpr int kSlots = 3;
+constexpr int kSlots = 4;
 
 struct Workspace {
   int64_t cap = 0;       // samples
