@@ -746,7 +746,7 @@ static int stage_ensure(ttirt_model *md, int slot, int64_t rows, bool need_q, bo
   return 0;
 }
 
-// Rows [m_begin, m_end) of one call on this model's device: chunks of rows go round three slots (stream + device
+// Rows [m_begin, m_end) of one call on this model's device: chunks of rows go round kSlots slots (stream + device
 // scratch + optional pinned bounce buffers).  Per chunk: seeds in (async H2D from pinned memory, or a host-thread copy
 // into the slot's pinned buffer first when the caller's q is pageable, or generated on the device) -> kernels -> D2H
 // (straight into pinned caller memory, or into the slot's pinned buffer from which a drain thread copies into the
