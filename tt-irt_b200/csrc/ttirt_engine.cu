@@ -915,7 +915,7 @@ extern "C" int ttirt_sample_uniform_host(ttirt_model *md, int64_t M, int64_t m0,
 
 // ------------------------------------------------------------------------------------------------
 // The drop-in call.  The reference's tt_irt1 keeps no state between calls and neither does this one as far as
-// the caller can tell, but device allocations (the model's buffers and the three pipeline workspaces, ~3.5 GB at
+// the caller can tell, but device allocations (the model's buffers and the pipeline workspaces, ~4.6 GB at
 // the metric shape) are kept per device and reused by the next call of the same shape: MH / IW drivers call the
 // sampler repeatedly on one TT (reference test_shock_absorber_tt.py:138-153).  Cores and grid are uploaded and
 // the sweep is redone on every call, so results never depend on a previous call.  TTIRT_CACHE=0 disables the
