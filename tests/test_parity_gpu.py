@@ -388,3 +388,30 @@ def test_host_pipeline_with_padded_leading_dimension(M, extra):
         md.close()
     assert np.array_equal(zbig[:M], Zref) and np.array_equal(lbig[:M], lref)
     assert (zbig[M:] == -7.0).all() and (lbig[M:] == -7.0).all()      # rows beyond M untouched
+
+
+def test_repeated_drop_in_calls_are_stable_and_do_not_leak():
+    """The drop-in symbol keeps device allocations, pinned bounce buffers and chunk graphs between calls of the same
+    shape and rebuilds them when the shape changes: alternate shapes and sizes many times, results must repeat bit
+    for bit and device memory must not creep."""
+    import torch
+    shapes = [(8, 17, 8, 1 << 14), (6, 33, 32, 70000), (8, 17, 8, 300000), (4, 65, 64, 20000), (8, 17, 8, 1 << 14)]
+    data, first = [], {}
+    for i, (d, n, r, M) in enumerate(shapes):
+        ns, xs, rk, c = synth.make_tt(d, n, r, seed=50 + i)
+        data.append((tt_irt.TTTensor(ns, rk, c), xs, synth.make_q(M, d, seed=60 + i)))
+    free0 = None
+    for rep in range(12):
+        for i, (f, xs, q) in enumerate(data):
+            Z, l = tt_irt.tt_irt1(q, f, xs)
+            if i not in first:
+                first[i] = (Z.copy(), l.copy())
+                assert np.isfinite(Z).all() and np.isfinite(l).all()
+            else:
+                assert np.array_equal(Z, first[i][0]) and np.array_equal(l, first[i][1]), (rep, i)
+        free = torch.cuda.mem_get_info(0)[0]
+        if rep == 1:
+            free0 = free
+        if rep > 1:
+            assert free >= free0 - (64 << 20), "device memory shrank by %d MB over repeated calls" % ((free0 - free) >> 20)
+    tt_irt.load_library().ttirt_cache_clear()
