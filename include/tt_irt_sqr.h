@@ -1,0 +1,86 @@
+/*
+ * tt_irt_sqr.h -- C-ABI of the B200-native squared-density inverse Rosenblatt transform.
+ *
+ * The reference routine is Matlab-only:
+ *   matlab/samplers/tt_irt_sqr.m:1     function [xq, lFapp] = tt_irt_sqr(xsf, f, q)
+ * with its two helpers
+ *   matlab/utils/tracemult.c:103-112   C(:,:,i) = A(:,:,i) * B(:,:,j(i))   (batched product, used at :77, :109, :205)
+ *   matlab/utils/tracemult.c:131-136   C(i) = A(i, j(i))                    (column pick, used at :139, :146-149)
+ * and is what the DIRT sampler calls per layer (matlab/samplers/tt_dirt_sample.m:46,71).  It has no C entry point, so
+ * the boundary here is new: the same argument meaning as tt_irt1 (include/tt_irt1.h; grid, TT2.0 cores, ranks, seeds in,
+ * samples and log-density out) plus the two things tt_irt_sqr.m adds -- the grid may carry two boundary points per
+ * dimension that the cores lack (:33-36, :53-60) and q may have fewer columns than the TT has dimensions (:9, :105).
+ * INTEGRATION.md shows the MEX gateway a maintainer would put in front of it.
+ *
+ * Both shared libraries of tt-irt_b200/Makefile export these symbols (TTIRT_INT = int / long long for tt_irt_sqr, all
+ * ttirt_sqr_* are width-independent).  Pointers are plain host or device addresses.  There is NO CPU fallback.
+ */
+#ifndef TT_IRT_SQR_H
+#define TT_IRT_SQR_H
+
+#include <stdint.h>
+
+#include "tt_irt1.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/*
+ * [xq, lFapp] = tt_irt_sqr(xsf, f, q)  -- reference matlab/samplers/tt_irt_sqr.m:1-208.
+ *
+ *   d       number of TT cores                                                      (:25)
+ *   n       mode sizes of the cores (d)                                             (:26)
+ *   nxs     number of grid points in xs: sum(n) or sum(n + 2)                       (:33-39)
+ *   xs      grid points of all dimensions stacked, boundaries included              (:30-32)
+ *   ttrank  TT ranks (d+1), ttrank[0] = ttrank[d] = 1                               (:27)
+ *   ttcore  cores of the SQUARE ROOT of the density, core k column-major r_k x n_k x r_{k+1}, stacked
+ *   M, D    q is column-major M x D, 0 < D <= d (D < d samples the marginal of the first D variables, :9, :105)
+ *   z       samples, column-major M x D            (host, caller-allocated, fully overwritten)     (:184)
+ *   lFapp   log of the sampling density, length M  (host, caller-allocated, fully overwritten)     (:194)
+ *
+ * The reference's `keyboard` debugger stops (:17-19, :151-154) have no counterpart: seeds outside [0, 1] are not
+ * checked.  On any failure one line goes to stderr and z / lFapp are NaN-filled; the host process is never aborted.
+ */
+TTIRT_API void tt_irt_sqr(TTIRT_INT d, TTIRT_INT *n, TTIRT_INT nxs, double *xs, TTIRT_INT *ttrank, double *ttcore,
+                          TTIRT_INT M, TTIRT_INT D, double *q, double *z, double *lFapp);
+
+typedef struct ttirt_sqr_model ttirt_sqr_model; /* opaque: extended cores + packed semi-marginal Gram operands on one device */
+
+/* Upload grid and cores, extrapolate the cores to the boundary when the grid has the two extra points (:53-60), run the
+ * right-to-left sweep on the device (:41-82: core x R, Householder QR of the weighted unfolding, Cartesian square) and keep
+ * the per-dimension operands resident.  NULL on failure.  Shapes: r <= 64, extended n <= 72. */
+TTIRT_API ttirt_sqr_model *ttirt_sqr_model_create(int64_t d, const int64_t *n, int64_t nxs, const double *xs,
+                                                  const int64_t *ttrank, const double *ttcore, int device);
+TTIRT_API void ttirt_sqr_model_destroy(ttirt_sqr_model *model);
+
+/* Read back the sweep of dimension k for the parity tests: gram_out (may be NULL) receives P{k} of tt_irt_sqr.m:80,
+ * column-major r_k^2 x n_k (n_k after the boundary extension); rr_out (may be NULL) receives R'R of the factor to the
+ * LEFT of core k (:66-72; r_k x r_k, only defined for k >= 1), the only form in which the factor enters the result. */
+TTIRT_API int ttirt_sqr_model_get_sweep(const ttirt_sqr_model *model, int64_t k, double *gram_out, double *rr_out);
+/* Extended mode size of dimension k (n_k or n_k + 2). */
+TTIRT_API int64_t ttirt_sqr_model_mode_size(const ttirt_sqr_model *model, int64_t k);
+
+/* Sample with everything resident in device memory; d_q / d_z column-major M x D with leading dimensions ldq / ldz,
+ * d_lf length M, d_idx (may be NULL) int32 interval indices i0 (0-based), column-major with leading dimension ldz.
+ * Enqueued on `stream` (cudaStream_t as void*), no synchronisation.  0 on success. */
+TTIRT_API int ttirt_sqr_sample_device(ttirt_sqr_model *model, int64_t M, int64_t D, const double *d_q, int64_t ldq,
+                                      double *d_z, int64_t ldz, double *d_lf, int32_t *d_idx, void *stream);
+/* The same on host buffers (leading dimension ld >= M): chunked copy in, kernels, copy out.  Blocks.  0 on success. */
+TTIRT_API int ttirt_sqr_sample_host(ttirt_sqr_model *model, int64_t M, int64_t D, const double *h_q, double *h_z,
+                                    double *h_lf, int32_t *h_idx, int64_t ld);
+/* Whole call on host buffers (model create, sample, destroy): what tt_irt_sqr() runs. */
+TTIRT_API int ttirt_sqr_run_host(int64_t d, const int64_t *n, int64_t nxs, const double *xs, const int64_t *ttrank,
+                                 const double *ttcore, int64_t M, int64_t D, const double *h_q, double *h_z, double *h_lf,
+                                 int device);
+
+/* Per-launch CUDA-event timing of the dominant kernel (the conditional-pdf contraction, sqr_pdf_kernel):
+ * enable(1) clears and starts; read() synchronises and returns summed kernel time, launches and their algorithmic flops
+ * (rows * (r_k (r_k + 1) n_k + r_k (r_k + 1) / 2) per launch: the symmetric half of :109-112). */
+TTIRT_API void ttirt_sqr_profile_enable(ttirt_sqr_model *model, int on);
+TTIRT_API int ttirt_sqr_profile_read(ttirt_sqr_model *model, double *ms_total, int64_t *launches, double *flops_total);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TT_IRT_SQR_H */

@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include "../../include/tt_irt1.h"
+#include "../../include/tt_irt_sqr.h"
 
 static void nan_fill(double *p, int64_t count) {
   int64_t i;
@@ -60,6 +61,42 @@ void tt_irt1(TTIRT_INT d, TTIRT_INT *n, double *xs, TTIRT_INT *ttrank, double *t
   } else if (getenv("TTIRT_VERBOSE") != NULL) {
     fprintf(stderr, "tt_irt1[b200]: M=%lld d=%lld mode=%s devices=%d launches=%lld\n", (long long)M, (long long)d,
             mode == TTIRT_MODE_STRICT ? "strict" : "fast", ndev, (long long)ttirt_kernel_launches());
+  }
+  free(n64);
+  free(r64);
+}
+
+/*
+ * The squared-density transform, reference matlab/samplers/tt_irt_sqr.m:1 ([xq, lFapp] = tt_irt_sqr(xsf, f, q)).
+ * Matlab-only in the reference; this is the C entry point a MEX gateway binds.
+ */
+void tt_irt_sqr(TTIRT_INT d, TTIRT_INT *n, TTIRT_INT nxs, double *xs, TTIRT_INT *ttrank, double *ttcore, TTIRT_INT M,
+                TTIRT_INT D, double *q, double *z, double *lFapp) {
+  int64_t *n64, *r64, k;
+  int first = 0, rc;
+  const char *e;
+
+  if (d < 1 || M < 0 || D < 1 || D > d || !n || !xs || !ttrank || !ttcore || (M > 0 && (!q || !z || !lFapp))) {
+    fprintf(stderr, "tt_irt_sqr[b200]: invalid arguments\n");
+    if (D >= 1 && M > 0) { nan_fill(z, (int64_t)M * D); nan_fill(lFapp, M); }
+    return;
+  }
+  if (M == 0) return;
+  n64 = (int64_t *)malloc(sizeof(int64_t) * (size_t)d);
+  r64 = (int64_t *)malloc(sizeof(int64_t) * ((size_t)d + 1));
+  if (!n64 || !r64) {
+    fprintf(stderr, "tt_irt_sqr[b200]: out of host memory\n");
+    free(n64); free(r64);
+    nan_fill(z, (int64_t)M * D); nan_fill(lFapp, M);
+    return;
+  }
+  for (k = 0; k < d; k++) n64[k] = (int64_t)n[k];
+  for (k = 0; k <= d; k++) r64[k] = (int64_t)ttrank[k];
+  if ((e = getenv("TTIRT_DEVICE")) != NULL) first = atoi(e);
+  rc = ttirt_sqr_run_host(d, n64, (int64_t)nxs, xs, r64, ttcore, M, D, q, z, lFapp, first);
+  if (rc != 0) {
+    nan_fill(z, (int64_t)M * D);
+    nan_fill(lFapp, M);
   }
   free(n64);
   free(r64);

@@ -1,0 +1,988 @@
+// B200-native squared-density inverse Rosenblatt transform behind include/tt_irt_sqr.h
+// (reference matlab/samplers/tt_irt_sqr.m:1-208 and its MEX helper matlab/utils/tracemult.c).
+//
+//   model_create : extend the cores to the boundary (:53-60), right-to-left sweep (:41-82) on the device:
+//                    core x R (:62-64) -> Householder QR of the weighted unfolding (:66-72) -> Cartesian square (:74-80),
+//                  the square stored as the packed symmetric DMMA operand of the conditional-pdf contraction.
+//   sample       : per chunk and dimension
+//                    sqr_pdf_kernel     (f (x) f)' P_k  (:107-112) as an FP64 tensor-core GEMM whose A operand, the outer
+//                                       product of the left interface with itself, is formed in registers and whose B
+//                                       operand streams from L2 through a TMA-bulk / mbarrier ring
+//                    sqr_tail_kernel    trapezoid CDF, zero-mass fallback, normalise, bisection, quadratic root, clamp,
+//                                       log-density (:113-195), in the reference's operation order
+//                    bin scan / scatter counting sort of the chunk by chosen interval
+//                    sqr_update_kernel  interpolated interface update (:197-207) with the two core slabs of a bin staged
+//                                       in shared memory
+// No CPU fallback anywhere: without a device every entry point fails.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/tt_irt_sqr.h"
+#include "ttirt_common.cuh"
+
+namespace ttirt {
+int aux_fail(const char *fmt, ...);   // ttirt_engine.cu: records the thread's last error, one line on stderr
+void aux_launched();                  // bumps the library's kernel-launch counter
+}  // namespace ttirt
+using ttirt::aux_fail;
+
+#define CKS(call)                                                                          \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess) return aux_fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+#define LAUNCHED() ttirt::aux_launched()
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// ------------------------------------------------------------------------------------------------
+// geometry of the packed Gram operand
+// ------------------------------------------------------------------------------------------------
+// The conditional pdf at node j is  sum_{a,b} f_a f_b G[a,b,j]  (tt_irt_sqr.m:107-112, G = P{k} of :80, symmetric in a, b).
+// The contraction index is walked in DMMA k-steps of four pairs: for every column block c (b = 4c .. 4c+3) and every
+// a <= 4c+3 the k-step (c, a) holds the pairs (a, 4c + t), t = 0..3.  Pairs with a < 4c stand for (a, b) and (b, a) and
+// carry 2 G; the diagonal block 4c <= a <= 4c+3 is walked in full with weight 1.  r (r + 4) / 2 k-rows for r a multiple
+// of 4: 2176 instead of r^2 = 4096 at r = 64 (the exact half is 2080).
+__host__ __device__ inline int sqr_ksteps(int r0) {
+  int ks = 0;
+  for (int c = 0; 4 * c < r0; c++) ks += (4 * c + 4 < r0) ? 4 * c + 4 : r0;
+  return ks;
+}
+
+struct SqrDim {
+  int n;         // grid size of the dimension, boundary points included
+  int n_in;      // mode size of the caller's core (n or n - 2)
+  int r0, r1;    // r_k, r_{k+1}
+  int s1;        // columns of the factor R' to the right of core k (1 for the last core)
+  int s0;        // columns of the factor R' this dimension produces (min(n s1, r0)); unused for k = 0
+  int ksteps;    // DMMA k-steps of the packed operand
+  int pad;
+  int64_t off_x, off_cin, off_c, off_g, off_r;
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers: FP64 MMA, mbarrier, TMA bulk copy
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+  } while (!ok);
+}
+// 1-D TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// sweep kernels (once per model)
+// ------------------------------------------------------------------------------------------------
+// tt_irt_sqr.m:53-60: cores without boundary nodes are extrapolated linearly to the two extra grid points.
+// Operation order as written there (note the right-hand factor (h_n + h_{n-1}) / h_{n-1}: mirrored, not "fixed").
+__global__ void sqr_extend_kernel(const double *__restrict__ cin, const double *__restrict__ x, double *cout, int r0, int n, int r1) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;   // over (a, l)
+  if (e >= r0 * r1) return;
+  const int a = e % r0, l = e / r0;
+  const int nin = n - 2;
+  const double *ci = cin + a + (int64_t)r0 * nin * l;
+  double *co = cout + a + (int64_t)r0 * n * l;
+  for (int j = 0; j < nin; j++) co[(int64_t)r0 * (j + 1)] = ci[(int64_t)r0 * j];
+  const double h1 = __dsub_rn(x[1], x[0]), h2 = __dsub_rn(x[2], x[1]);
+  const double hn = __dsub_rn(x[n - 1], x[n - 2]), hm = __dsub_rn(x[n - 2], x[n - 3]);
+  const double f1 = ci[0], f2 = ci[r0];
+  co[0] = __dsub_rn(f1, __ddiv_rn(__dmul_rn(__dsub_rn(f2, f1), h1), h2));
+  const double g1 = ci[(int64_t)r0 * (nin - 1)], g2 = ci[(int64_t)r0 * (nin - 2)];
+  co[(int64_t)r0 * (n - 1)] = __dadd_rn(g1, __ddiv_rn(__dmul_rn(__dsub_rn(g1, g2), __dadd_rn(hn, hm)), hm));
+}
+
+// h (h[0] = 0) and its running sum, the fallback CDF of :123-127
+__global__ void sqr_grid_kernel(const double *__restrict__ x, double *h, double *hc, int n) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double s = 0.0;
+  h[0] = 0.0; hc[0] = 0.0;
+  for (int j = 1; j < n; j++) {
+    const double hj = __dsub_rn(x[j], x[j - 1]);
+    h[j] = hj;
+    s = __dadd_rn(s, hj);
+    hc[j] = s;
+  }
+}
+
+// :62-64  Pm[(j + n s) + m a] = sum_l core[a, j, l] R'[l, s]   (m = n s1: the unfolding that the QR and the square read)
+__global__ void sqr_contract_kernel(const double *__restrict__ core, const double *__restrict__ Rp, double *Pm, int r0, int n,
+                                    int r1, int s1) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)r0 * n * s1) return;
+  const int a = (int)(e % r0);
+  const int j = (int)((e / r0) % n);
+  const int s = (int)(e / ((int64_t)r0 * n));
+  const double *c = core + a + (int64_t)r0 * j;
+  const double *rr = Rp + (int64_t)r1 * s;
+  double acc = 0.0;
+  for (int l = 0; l < r1; l++) acc = fma(c[(int64_t)r0 * n * l], rr[l], acc);
+  Pm[(int64_t)j + (int64_t)n * s + (int64_t)n * s1 * a] = acc;
+}
+
+// :49-51, :68  A = diag(sqrt(w / 2)) Pm, w the trapezoid node weights
+__global__ void sqr_weight_kernel(const double *__restrict__ Pm, const double *__restrict__ h, double *A, int n, int m, int r0) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)m * r0) return;
+  const int j = (int)((e % m) % n);
+  const double hr = j + 1 < n ? h[j + 1] : 0.0;
+  const double w = sqrt(__dmul_rn(__dadd_rn(h[j], hr), 0.5));
+  A[e] = __dmul_rn(Pm[e], w);
+}
+
+// :70-71  R of the economy QR of A (m x r, column-major, overwritten): Householder reflectors as LAPACK dgeqr2 / dlarfg
+// form them, one CTA, one warp per trailing column.  Rt receives R' (r x rnew column-major, rnew = min(m, r)).
+__global__ void __launch_bounds__(1024) sqr_qr_kernel(double *A, int m, int r, double *Rt, int rnew) {
+  __shared__ double red[32];
+  __shared__ double s_tau, s_scale;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const int steps = m < r ? m : r;
+  for (int c = 0; c < steps; c++) {
+    double *col = A + (size_t)c * m;
+    double ss = 0.0;
+    for (int i = c + 1 + tid; i < m; i += blockDim.x) ss = fma(col[i], col[i], ss);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(FULL, ss, o);
+    if (lane == 0) red[warp] = ss;
+    __syncthreads();
+    if (warp == 0) {
+      double v = lane < nw ? red[lane] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+      if (lane == 0) {
+        const double alpha = col[c];
+        if (v == 0.0) {
+          s_tau = 0.0; s_scale = 0.0;
+        } else {
+          const double beta = -copysign(sqrt(fma(alpha, alpha, v)), alpha);
+          s_tau = (beta - alpha) / beta;
+          s_scale = 1.0 / (alpha - beta);
+          col[c] = beta;
+        }
+      }
+    }
+    __syncthreads();
+    const double tau = s_tau, scale = s_scale;
+    if (tau != 0.0) {
+      for (int i = c + 1 + tid; i < m; i += blockDim.x) col[i] *= scale;
+      __syncthreads();
+      for (int cc = c + 1 + warp; cc < r; cc += nw) {
+        double *cj = A + (size_t)cc * m;
+        double dot = 0.0;
+        for (int i = c + 1 + lane; i < m; i += 32) dot = fma(col[i], cj[i], dot);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(FULL, dot, o);
+        dot += cj[c];
+        const double t = tau * dot;
+        if (lane == 0) cj[c] -= t;
+        for (int i = c + 1 + lane; i < m; i += 32) cj[i] = fma(-t, col[i], cj[i]);
+      }
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < r * rnew; e += blockDim.x) {
+    const int a = e % r, t = e / r;
+    Rt[e] = (t <= a) ? A[(size_t)t + (size_t)m * a] : 0.0;
+  }
+}
+
+// :74-80 as the packed DMMA operand: row 4 ks + t of k-step ks = (c, a) holds w G[a, 4c + t, :], G[a, b, j] = sum_s Pm[a,j,s] Pm[b,j,s]
+__global__ void sqr_gram_pack_kernel(const double *__restrict__ Pm, int n, int s1, int r0, double *gp, int pb, int ksteps) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)ksteps * 4 * n) return;
+  const int j = (int)(e % n);
+  const int kr = (int)(e / n);
+  const int ks = kr >> 2, t = kr & 3;
+  int c = 0, base = 0;
+  for (;;) {
+    const int cnt = (4 * c + 4 < r0) ? 4 * c + 4 : r0;
+    if (ks < base + cnt) break;
+    base += cnt; c++;
+  }
+  const int a = ks - base, b = 4 * c + t;
+  double v = 0.0;
+  if (b < r0) {
+    const int64_t m = (int64_t)n * s1;
+    const double *pa = Pm + j + m * a, *pbp = Pm + j + m * b;
+    for (int s = 0; s < s1; s++) v = fma(pa[(int64_t)n * s], pbp[(int64_t)n * s], v);
+    if (a < 4 * c) v *= 2.0;
+  }
+  gp[(int64_t)kr * pb + j] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-chunk kernels
+// ------------------------------------------------------------------------------------------------
+// fkm1 = ones(1, Mb)  (:103): r_0 = 1, the padding columns of the first 4-block are zero
+__global__ void sqr_init_kernel(double *F, int ldf, int rows) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= rows) return;
+  double *f = F + (size_t)m * ldf;
+  f[0] = 1.0; f[1] = 0.0; f[2] = 0.0; f[3] = 0.0;
+}
+
+constexpr int PDF_WARPS = 8;                  // MMA warps, two per SM sub-partition
+constexpr int PDF_MT = 2;                     // 8-row MMA tiles per warp
+constexpr int PDF_WROWS = 8 * PDF_MT;
+constexpr int PDF_ROWS = PDF_WARPS * PDF_WROWS;   // samples per CTA tile
+constexpr int PDF_KS = 16;                    // k-steps per B slice
+constexpr int PDF_STAGES = 3;
+
+struct PdfArgs {
+  const double *F; int ldf; int rows;
+  const double *gp; int pb; int ksteps; int r0; int n;
+  double *pdf; int64_t ldp;
+};
+
+__host__ __device__ inline size_t pdf_smem_bytes(int ldf, int pb) {
+  return sizeof(double) * ((size_t)PDF_ROWS * ldf + (size_t)PDF_STAGES * PDF_KS * 4 * pb) + 2 * PDF_STAGES * sizeof(uint64_t);
+}
+
+// Conditional pdf of one dimension for a chunk: pdf[j, m] = sum over pairs f_m[a] f_m[b] Gp[(a,b), j].
+//   * persistent CTAs over 128-sample tiles; eight MMA warps of 16 samples each and one producer warp;
+//   * B = Gp (up to 1.3 MB, L2-resident) streams through a three-stage ring of 16-k-step slices, each one TMA bulk copy
+//     signalled on an mbarrier, released by the eight warps on a second mbarrier;
+//   * A is never stored: lane (g, t) multiplies f_g[a] (one broadcast LDS per k-step) with f_g[4c + t] (one LDS per column block);
+//   * pitches: ldf = 4 (mod 8) and pb = 4 (mod 8) doubles make the fragment loads bank-conflict free without a swizzle.
+template <int NT>
+__global__ void __launch_bounds__(32 * (PDF_WARPS + 1), 1) sqr_pdf_kernel(PdfArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *Fs = reinterpret_cast<double *>(smem_raw);
+  double *Bs = Fs + (size_t)PDF_ROWS * a.ldf;
+  const int SB = PDF_KS * 4 * a.pb;           // doubles per stage
+  uint64_t *full = reinterpret_cast<uint64_t *>(Bs + (size_t)PDF_STAGES * SB);
+  uint64_t *empty = full + PDF_STAGES;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ntiles = (a.rows + PDF_ROWS - 1) / PDF_ROWS;
+  const int nslices = (a.ksteps + PDF_KS - 1) / PDF_KS;
+  if (tid == 0) {
+    for (int s = 0; s < PDF_STAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, PDF_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == PDF_WARPS) {                    // producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+        for (int s = 0; s < nslices; s++, it++) {
+          const uint32_t stage = it % PDF_STAGES;
+          if (it >= PDF_STAGES) mbar_wait(empty + stage, ((it / PDF_STAGES) - 1) & 1);
+          const int steps = (a.ksteps - s * PDF_KS) < PDF_KS ? (a.ksteps - s * PDF_KS) : PDF_KS;
+          const uint32_t bytes = (uint32_t)(steps * 4 * a.pb * sizeof(double));
+          mbar_expect_tx(full + stage, bytes);
+          bulk_g2s(Bs + (size_t)stage * SB, a.gp + (size_t)s * SB, bytes, full + stage);
+        }
+    }
+    return;
+  }
+  const int g = lane >> 2, t = lane & 3;
+  const int ldf = a.ldf;
+  double *fw = Fs + (size_t)warp * PDF_WROWS * ldf;        // this warp's 16 staged rows
+  const int nchunk = (a.r0 + 3) >> 2;
+  uint32_t it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int m0 = tile * PDF_ROWS + warp * PDF_WROWS;
+    __syncwarp();
+    for (int row = 0; row < PDF_WROWS; row++) {
+      const int gm = m0 + row;
+      for (int col = lane; col < 4 * nchunk; col += 32) fw[row * ldf + col] = gm < a.rows ? a.F[(size_t)gm * ldf + col] : 0.0;
+    }
+    __syncwarp();
+    double acc[PDF_MT][NT][2];
+#pragma unroll
+    for (int mt = 0; mt < PDF_MT; mt++)
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
+    int ks = 0;
+    uint32_t stage = it % PDF_STAGES, parity = (it / PDF_STAGES) & 1;
+    for (int c = 0; c < nchunk; c++) {
+      double fb[PDF_MT];
+#pragma unroll
+      for (int mt = 0; mt < PDF_MT; mt++) fb[mt] = fw[(mt * 8 + g) * ldf + 4 * c + t];
+      const int amax = (4 * c + 4 < a.r0) ? 4 * c + 4 : a.r0;
+      for (int aa = 0; aa < amax; aa++) {
+        const int kk = ks & (PDF_KS - 1);
+        if (kk == 0) mbar_wait(full + stage, parity);
+        double av[PDF_MT];
+#pragma unroll
+        for (int mt = 0; mt < PDF_MT; mt++) av[mt] = __dmul_rn(fw[(mt * 8 + g) * ldf + aa], fb[mt]);
+        const double *bp = Bs + (size_t)stage * SB + (kk * 4 + t) * a.pb + g;
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) {
+          const double b = bp[nt * 8];
+#pragma unroll
+          for (int mt = 0; mt < PDF_MT; mt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], av[mt], b);
+        }
+        ks++;
+        if ((ks & (PDF_KS - 1)) == 0 || ks == a.ksteps) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(empty + stage);
+          it++;
+          stage = it % PDF_STAGES; parity = (it / PDF_STAGES) & 1;
+        }
+      }
+    }
+#pragma unroll
+    for (int mt = 0; mt < PDF_MT; mt++) {
+      const int row = m0 + mt * 8 + g;
+      if (row < a.rows) {
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) {
+          const int col = nt * 8 + 2 * t;
+          if (col < a.n) a.pdf[(size_t)col * a.ldp + row] = acc[mt][nt][0];
+          if (col + 1 < a.n) a.pdf[(size_t)(col + 1) * a.ldp + row] = acc[mt][nt][1];
+        }
+      }
+    }
+  }
+}
+
+struct TailArgs {
+  const double *pdf; double *cdf; int64_t ldp; int rows; int n;
+  const double *x, *h, *hc;
+  const double *q; double *z; int32_t *idx_out;
+  int *idx; double *w1, *w2; double *lf;
+  int first;        // dimension 0: lFapp starts here (:91)
+  int *hist;        // n - 1 counters for the sort by interval, or NULL when no interface update follows
+};
+
+// :113-195, one thread per sample, every operation in the reference's order (explicit round-to-nearest intrinsics: no
+// FMA contraction).  The unnormalised CDF goes to a scratch column block that the bisection reads back.
+__global__ void __launch_bounds__(256) sqr_tail_kernel(TailArgs a) {
+  extern __shared__ int sh_hist[];
+  const int n = a.n;
+  if (a.hist) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sh_hist[i] = 0;
+    __syncthreads();
+  }
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m < a.rows) {
+    const double *p = a.pdf + m;
+    double *cd = a.cdf + m;
+    double c = 0.0, pprev = p[0];
+    cd[0] = __dmul_rn(__dmul_rn(0.5, pprev), a.h[0]);        // :114-116, h(1) = 0
+    c = cd[0];
+    for (int j = 1; j < n; j++) {
+      const double pj = p[(size_t)j * a.ldp];
+      const double tj = __dmul_rn(__dadd_rn(__dmul_rn(0.5, pprev), __dmul_rn(0.5, pj)), a.h[j]);
+      c = __dadd_rn(c, tj);                                    // :117 cumsum
+      cd[(size_t)j * a.ldp] = c;
+      pprev = pj;
+    }
+    double cmax = c;                                           // :120
+    const bool zero = cmax <= 0.0;                             // :121-127: conditional replaced by h, CDF by cumsum(h)
+    if (zero) cmax = a.hc[n - 1];
+    const double qk = a.q[m];
+    int i0 = 0, i2 = n - 1;                                    // :135-143
+    while (i2 - i0 > 1) {
+      const int i1 = (i0 + i2) >> 1;
+      const double c1 = __ddiv_rn(zero ? a.hc[i1] : cd[(size_t)i1 * a.ldp], cmax);
+      if (qk > c1) i0 = i1; else i2 = i1;
+    }
+    const double C1 = __ddiv_rn(zero ? a.hc[i0] : cd[(size_t)i0 * a.ldp], cmax);                 // :146-149, :129-130
+    const double f1 = __ddiv_rn(zero ? a.h[i0] : p[(size_t)i0 * a.ldp], cmax);
+    const double f2 = __ddiv_rn(zero ? a.h[i0 + 1] : p[(size_t)(i0 + 1) * a.ldp], cmax);
+    const double x1 = a.x[i0], x2 = a.x[i0 + 1];                                                  // :157-159
+    const double h3 = __dsub_rn(x2, x1);
+    const double Aq = __ddiv_rn(__dmul_rn(0.5, __dsub_rn(f2, f1)), h3);                          // :161
+    const double dq = __dsub_rn(qk, C1);
+    const double Dq = __dadd_rn(__dmul_rn(f1, f1), __dmul_rn(__dmul_rn(4.0, Aq), dq));           // :162
+    double xk = __dadd_rn(x1, __ddiv_rn(__dadd_rn(-f1, __dsqrt_rn(fabs(Dq))), __dmul_rn(2.0, Aq)));   // :163
+    if (Aq == 0.0) {                                                                              // :164-170
+      xk = __dadd_rn(x1, __ddiv_rn(dq, f1));
+      if (f1 == 0.0) xk = x1;
+    }
+    if (xk > x2) xk = x2;                                                                         // :173-182
+    if (xk < x1) xk = x1;
+    a.z[m] = xk;                                                                                  // :184
+    const double wa = __ddiv_rn(__dsub_rn(x2, xk), h3), wb = __ddiv_rn(__dsub_rn(xk, x1), h3);    // :187-188
+    const double dens = __dadd_rn(__dmul_rn(f1, wa), __dmul_rn(f2, wb));                          // :193
+    const double lg = log(dens);                                                                  // :194
+    a.lf[m] = a.first ? lg : __dadd_rn(a.lf[m], lg);
+    a.idx[m] = i0; a.w1[m] = wa; a.w2[m] = wb;
+    if (a.idx_out) a.idx_out[m] = i0;
+    if (a.hist) atomicAdd(&sh_hist[i0], 1);
+  }
+  if (a.hist) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < n - 1; i += blockDim.x)
+      if (sh_hist[i]) atomicAdd(a.hist + i, sh_hist[i]);
+  }
+}
+
+constexpr int UPD_TS = 64;        // samples per tile of the interface update
+constexpr int UPD_THREADS = 256;
+
+__global__ void sqr_bin_scan_kernel(const int *__restrict__ hist, int nb, int *bin_start, int *bin_tile_start, int *cursor) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int s = 0, t = 0;
+  for (int b = 0; b < nb; b++) {
+    bin_start[b] = s; bin_tile_start[b] = t; cursor[b] = s;
+    const int c = hist[b];
+    s += c; t += (c + UPD_TS - 1) / UPD_TS;
+  }
+  bin_start[nb] = s; bin_tile_start[nb] = t;
+}
+
+// counting-sort scatter, one atomic per (warp, distinct interval)
+__global__ void sqr_bin_scatter_kernel(const int *__restrict__ idx, int rows, int *cursor, int *perm) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool live = m < rows;
+  const int b = live ? idx[m] : -1;
+  const unsigned peers = __match_any_sync(FULL, b);
+  const int leader = __ffs(peers) - 1;
+  const int rank = __popc(peers & ((1u << lane) - 1));
+  int base = 0;
+  if (live && lane == leader) base = atomicAdd(cursor + b, __popc(peers));
+  base = __shfl_sync(FULL, base, leader);
+  if (live) perm[base + rank] = m;
+}
+
+struct UpdArgs {
+  const double *core; int r0, n, r1;
+  const double *Fin; double *Fout; int ldf;
+  const int *perm, *bin_start, *bin_tile_start; int nb;
+  const double *w1, *w2;
+};
+
+// :197-207  fkm1' = (fkm1 core(:, i0, :)) Aq + (fkm1 core(:, i0 + 1, :)) Bq for 64-sample tiles of one interval; the two
+// slabs are staged in shared memory once per interval and CTA (CTAs own contiguous tile ranges).  FP64 FMA, 4 x 4 outputs
+// per thread for each slab.
+__global__ void __launch_bounds__(UPD_THREADS) sqr_update_kernel(UpdArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  const int r1p = (a.r1 + 3) & ~3;
+  const int SP = r1p + 2;                 // slab pitch: [a][l], l fastest
+  const int FP = UPD_TS + 2;              // staged interface pitch: [a][sample]
+  double *S0 = sm, *S1 = S0 + (size_t)a.r0 * SP, *Ft = S1 + (size_t)a.r0 * SP;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int total = a.bin_tile_start[a.nb];
+  const int t_begin = (int)(((int64_t)total * blockIdx.x) / gridDim.x);
+  const int t_end = (int)(((int64_t)total * (blockIdx.x + 1)) / gridDim.x);
+  int bin = 0, staged = -1;
+  for (int tile = t_begin; tile < t_end; tile++) {
+    while (tile >= a.bin_tile_start[bin + 1]) bin++;
+    const int start = a.bin_start[bin] + (tile - a.bin_tile_start[bin]) * UPD_TS;
+    const int cnt = min(UPD_TS, a.bin_start[bin + 1] - start);
+    __syncthreads();                      // previous tile's reads of Ft (and of the slabs, when they change) are done
+    if (bin != staged) {
+      const int64_t cs = (int64_t)a.r0 * a.n;
+      for (int e = tid; e < a.r0 * r1p; e += UPD_THREADS) {
+        const int aa = e % a.r0, l = e / a.r0;
+        double v0 = 0.0, v1 = 0.0;
+        if (l < a.r1) {
+          v0 = __ldg(a.core + aa + (int64_t)a.r0 * bin + cs * l);
+          v1 = __ldg(a.core + aa + (int64_t)a.r0 * (bin + 1) + cs * l);
+        }
+        S0[aa * SP + l] = v0; S1[aa * SP + l] = v1;
+      }
+      staged = bin;
+    }
+    for (int s = warp; s < UPD_TS; s += UPD_THREADS / 32) {
+      const bool live = s < cnt;
+      const size_t id = live ? (size_t)a.perm[start + s] : 0;
+      for (int aa = lane; aa < a.r0; aa += 32) Ft[aa * FP + s] = live ? a.Fin[id * a.ldf + aa] : 0.0;
+    }
+    __syncthreads();
+    if (4 * tx < r1p) {
+      double acc0[4][4], acc1[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) { acc0[i][j] = 0.0; acc1[i][j] = 0.0; }
+      for (int aa = 0; aa < a.r0; aa++) {
+        const double2 fa = *reinterpret_cast<const double2 *>(Ft + aa * FP + 4 * ty);
+        const double2 fb = *reinterpret_cast<const double2 *>(Ft + aa * FP + 4 * ty + 2);
+        const double2 s0a = *reinterpret_cast<const double2 *>(S0 + aa * SP + 4 * tx);
+        const double2 s0b = *reinterpret_cast<const double2 *>(S0 + aa * SP + 4 * tx + 2);
+        const double2 s1a = *reinterpret_cast<const double2 *>(S1 + aa * SP + 4 * tx);
+        const double2 s1b = *reinterpret_cast<const double2 *>(S1 + aa * SP + 4 * tx + 2);
+        const double f[4] = {fa.x, fa.y, fb.x, fb.y};
+        const double u0[4] = {s0a.x, s0a.y, s0b.x, s0b.y};
+        const double u1[4] = {s1a.x, s1a.y, s1b.x, s1b.y};
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            acc0[i][j] = fma(f[i], u0[j], acc0[i][j]);
+            acc1[i][j] = fma(f[i], u1[j], acc1[i][j]);
+          }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int s = 4 * ty + i;
+        if (s < cnt) {
+          const size_t id = (size_t)a.perm[start + s];
+          const double wa = a.w1[id], wb = a.w2[id];
+          double o[4];
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+            o[j] = (4 * tx + j < a.r1) ? __dadd_rn(__dmul_rn(acc0[i][j], wa), __dmul_rn(acc1[i][j], wb)) : 0.0;   // :205
+          double *dst = a.Fout + id * a.ldf + 4 * tx;
+          *reinterpret_cast<double2 *>(dst) = make_double2(o[0], o[1]);
+          *reinterpret_cast<double2 *>(dst + 2) = make_double2(o[2], o[3]);
+        }
+      }
+    }
+  }
+}
+
+__global__ void sqr_fill_nan_kernel(double *p, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = __longlong_as_double(0x7ff8000000000000LL);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// model
+// ------------------------------------------------------------------------------------------------
+struct ttirt_sqr_model {
+  int device = 0, sm_count = 148;
+  int64_t d = 0;
+  std::vector<SqrDim> dims;
+  int rmax = 1, nmax = 2, ldf = 12, pb = 28, nt = 3, nbpad = 8;
+  int64_t sum_x = 0, sum_cin = 0, sum_c = 0, sum_g = 0, sum_r = 0;
+  bool extended = false;
+  double *d_xs = nullptr, *d_h = nullptr, *d_hc = nullptr, *d_core = nullptr, *d_gp = nullptr, *d_rfac = nullptr;
+  // workspace of one chunk
+  int64_t cap = 0;
+  bool host = false;
+  double *F0 = nullptr, *F1 = nullptr, *pdf = nullptr, *cdf = nullptr, *w1 = nullptr, *w2 = nullptr;
+  int *idx = nullptr, *perm = nullptr, *hist = nullptr, *bin_start = nullptr, *bin_tile_start = nullptr, *cursor = nullptr;
+  double *q = nullptr, *z = nullptr, *lf = nullptr;
+  int32_t *idx_out = nullptr;
+  cudaStream_t stream = nullptr;
+  bool profile = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  size_t prof_used = 0;
+  double prof_flops = 0.0;
+};
+
+static void sqr_ws_free(ttirt_sqr_model *md) {
+  cudaFree(md->F0); cudaFree(md->F1); cudaFree(md->pdf); cudaFree(md->cdf); cudaFree(md->w1); cudaFree(md->w2);
+  cudaFree(md->idx); cudaFree(md->perm); cudaFree(md->hist); cudaFree(md->bin_start); cudaFree(md->bin_tile_start); cudaFree(md->cursor);
+  cudaFree(md->q); cudaFree(md->z); cudaFree(md->lf); cudaFree(md->idx_out);
+  md->F0 = md->F1 = md->pdf = md->cdf = md->w1 = md->w2 = md->q = md->z = md->lf = nullptr;
+  md->idx = md->perm = md->hist = md->bin_start = md->bin_tile_start = md->cursor = nullptr;
+  md->idx_out = nullptr;
+  md->cap = 0; md->host = false;
+}
+
+static int sqr_ws_ensure(ttirt_sqr_model *md, int64_t rows, bool host) {
+  if (md->cap >= rows && (md->host || !host)) return 0;
+  const int64_t cap = std::max(rows, md->cap);
+  const bool h = host || md->host;
+  sqr_ws_free(md);
+  md->cap = cap; md->host = h;
+  const int64_t d = md->d;
+  const size_t fbytes = sizeof(double) * (size_t)cap * md->ldf;
+  CKS(cudaMalloc(&md->F0, fbytes));
+  CKS(cudaMalloc(&md->F1, fbytes));
+  CKS(cudaMemset(md->F0, 0, fbytes));
+  CKS(cudaMemset(md->F1, 0, fbytes));
+  CKS(cudaMalloc(&md->pdf, sizeof(double) * (size_t)cap * md->nmax));
+  CKS(cudaMalloc(&md->cdf, sizeof(double) * (size_t)cap * md->nmax));
+  CKS(cudaMalloc(&md->w1, sizeof(double) * cap));
+  CKS(cudaMalloc(&md->w2, sizeof(double) * cap));
+  CKS(cudaMalloc(&md->idx, sizeof(int) * cap));
+  CKS(cudaMalloc(&md->perm, sizeof(int) * cap));
+  CKS(cudaMalloc(&md->hist, sizeof(int) * d * md->nbpad));
+  CKS(cudaMalloc(&md->bin_start, sizeof(int) * (md->nbpad + 1)));
+  CKS(cudaMalloc(&md->bin_tile_start, sizeof(int) * (md->nbpad + 1)));
+  CKS(cudaMalloc(&md->cursor, sizeof(int) * (md->nbpad + 1)));
+  if (h) {
+    CKS(cudaMalloc(&md->q, sizeof(double) * cap * d));
+    CKS(cudaMalloc(&md->z, sizeof(double) * cap * d));
+    CKS(cudaMalloc(&md->lf, sizeof(double) * cap));
+    CKS(cudaMalloc(&md->idx_out, sizeof(int32_t) * cap * d));
+  }
+  return 0;
+}
+
+extern "C" void ttirt_sqr_model_destroy(ttirt_sqr_model *md) {
+  if (!md) return;
+  cudaSetDevice(md->device);
+  cudaDeviceSynchronize();
+  sqr_ws_free(md);
+  cudaFree(md->d_xs); cudaFree(md->d_h); cudaFree(md->d_hc); cudaFree(md->d_core); cudaFree(md->d_gp); cudaFree(md->d_rfac);
+  if (md->stream) cudaStreamDestroy(md->stream);
+  for (auto &p : md->prof_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+  delete md;
+}
+
+template <int NT>
+static cudaError_t pdf_launch(const PdfArgs &a, int sm_count, cudaStream_t st) {
+  static bool attr_done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const size_t bytes = pdf_smem_bytes(a.ldf, a.pb);
+  if (dev < 64 && !attr_done[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(sqr_pdf_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_done[dev] = true;
+  }
+  const int ntiles = (a.rows + PDF_ROWS - 1) / PDF_ROWS;
+  const int grid = ntiles < sm_count ? ntiles : sm_count;
+  sqr_pdf_kernel<NT><<<grid, 32 * (PDF_WARPS + 1), bytes, st>>>(a);
+  return cudaGetLastError();
+}
+
+static int sqr_model_build(ttirt_sqr_model *md, const int64_t *n, int64_t nxs, const double *xs, const int64_t *rk, const double *core) {
+  const int64_t d = md->d;
+  if (rk[0] != 1 || rk[d] != 1) return aux_fail("tt_irt_sqr: ttrank[0] and ttrank[d] must be 1");
+  int64_t sn = 0;
+  for (int64_t k = 0; k < d; k++) {
+    if (n[k] < 1 || rk[k] < 1 || rk[k + 1] < 1) return aux_fail("tt_irt_sqr: non-positive mode size or rank at dimension %lld", (long long)k);
+    sn += n[k];
+  }
+  // tt_irt_sqr.m:33-39
+  if (nxs == sn + 2 * d) md->extended = true;
+  else if (nxs != sn)
+    return aux_fail("tt_irt_sqr: number of grid points (with or without boundaries) in xsf should be sum of mode sizes in f (got %lld, modes sum to %lld)",
+                    (long long)nxs, (long long)sn);
+  md->dims.resize(d);
+  int64_t ox = 0, oci = 0, oc = 0, og = 0, orr = 0;
+  for (int64_t k = 0; k < d; k++) {
+    SqrDim &di = md->dims[k];
+    di.n_in = (int)n[k];
+    di.n = (int)n[k] + (md->extended ? 2 : 0);
+    if (di.n < 2) return aux_fail("tt_irt_sqr: dimension %lld needs at least 2 grid points", (long long)k);
+    if (md->extended && di.n_in < 2) return aux_fail("tt_irt_sqr: boundary extrapolation needs at least 2 interior points (dimension %lld)", (long long)k);
+    di.r0 = (int)rk[k]; di.r1 = (int)rk[k + 1];
+    di.ksteps = sqr_ksteps(di.r0);
+    di.pad = 0;
+    di.off_x = ox; di.off_cin = oci; di.off_c = oc; di.off_g = og; di.off_r = orr;
+    ox += di.n; oci += (int64_t)di.r0 * di.n_in * di.r1; oc += (int64_t)di.r0 * di.n * di.r1;
+    orr += (int64_t)di.r0 * di.r0;
+    md->rmax = std::max(md->rmax, std::max(di.r0, di.r1));
+    md->nmax = std::max(md->nmax, di.n);
+  }
+  if (md->rmax > 64 || md->nmax > 72)
+    return aux_fail("tt_irt_sqr: shape outside the B200 path (ranks <= 64 and grid sizes <= 72 are supported, got r = %d, n = %d)", md->rmax, md->nmax);
+  md->nt = md->nmax <= 24 ? 3 : (md->nmax <= 40 ? 5 : 9);
+  md->pb = 8 * md->nt + 4;
+  md->ldf = ((md->rmax + 7) & ~7) + 4;
+  md->nbpad = (md->nmax + 7) & ~7;
+  for (int64_t k = 0; k < d; k++) {
+    md->dims[k].off_g = og;
+    og += (int64_t)md->dims[k].ksteps * 4 * md->pb;
+  }
+  // ranks of the factors: s1 of the last core is 1 (:43-44), every QR yields min(rows, columns) rows (:70)
+  int s = 1;
+  for (int64_t k = d - 1; k >= 0; k--) {
+    SqrDim &di = md->dims[k];
+    di.s1 = s;
+    const int64_t m = (int64_t)di.n * s;
+    di.s0 = (int)std::min<int64_t>(m, di.r0);
+    s = di.s0;
+  }
+  md->sum_x = ox; md->sum_cin = oci; md->sum_c = oc; md->sum_g = og; md->sum_r = orr;
+
+  cudaDeviceProp prop;
+  CKS(cudaGetDeviceProperties(&prop, md->device));
+  if (prop.major < 10) return aux_fail("tt_irt_sqr: device %d (%s, sm_%d%d) is not a Blackwell B200-class GPU", md->device, prop.name, prop.major, prop.minor);
+  md->sm_count = prop.multiProcessorCount;
+  CKS(cudaStreamCreateWithFlags(&md->stream, cudaStreamNonBlocking));
+
+  CKS(cudaMalloc(&md->d_xs, sizeof(double) * ox));
+  CKS(cudaMalloc(&md->d_h, sizeof(double) * ox));
+  CKS(cudaMalloc(&md->d_hc, sizeof(double) * ox));
+  CKS(cudaMalloc(&md->d_core, sizeof(double) * oc));
+  CKS(cudaMalloc(&md->d_gp, sizeof(double) * og));
+  CKS(cudaMalloc(&md->d_rfac, sizeof(double) * orr));
+  CKS(cudaMemset(md->d_gp, 0, sizeof(double) * og));
+  CKS(cudaMemset(md->d_rfac, 0, sizeof(double) * orr));
+  CKS(cudaMemcpy(md->d_xs, xs, sizeof(double) * ox, cudaMemcpyHostToDevice));
+
+  double *d_cin = nullptr, *d_pm = nullptr, *d_a = nullptr, *d_one = nullptr;
+  int64_t mmax = 0;
+  for (int64_t k = 0; k < d; k++) mmax = std::max(mmax, (int64_t)md->dims[k].n * md->dims[k].s1 * md->dims[k].r0);
+  auto cleanup = [&]() { if (md->extended) cudaFree(d_cin); cudaFree(d_pm); cudaFree(d_a); cudaFree(d_one); };
+#define CKB(call)                                                                                   \
+  do {                                                                                              \
+    cudaError_t e_ = (call);                                                                        \
+    if (e_ != cudaSuccess) { cleanup(); return aux_fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } \
+  } while (0)
+  CKB(cudaMalloc(&d_pm, sizeof(double) * mmax));
+  CKB(cudaMalloc(&d_a, sizeof(double) * mmax));
+  CKB(cudaMalloc(&d_one, sizeof(double)));
+  const double one = 1.0;
+  CKB(cudaMemcpy(d_one, &one, sizeof(double), cudaMemcpyHostToDevice));
+  if (md->extended) {
+    CKB(cudaMalloc(&d_cin, sizeof(double) * oci));
+    CKB(cudaMemcpy(d_cin, core, sizeof(double) * oci, cudaMemcpyHostToDevice));
+  } else {
+    CKB(cudaMemcpy(md->d_core, core, sizeof(double) * oc, cudaMemcpyHostToDevice));
+  }
+  for (int64_t k = d - 1; k >= 0; k--) {
+    const SqrDim &di = md->dims[k];
+    const double *x = md->d_xs + di.off_x;
+    sqr_grid_kernel<<<1, 32>>>(x, md->d_h + di.off_x, md->d_hc + di.off_x, di.n);
+    LAUNCHED();
+    if (md->extended) {
+      sqr_extend_kernel<<<(di.r0 * di.r1 + 127) / 128, 128>>>(d_cin + di.off_cin, x, md->d_core + di.off_c, di.r0, di.n, di.r1);
+      LAUNCHED();
+    }
+    const double *Rp = (k == d - 1) ? d_one : md->d_rfac + md->dims[k + 1].off_r;
+    const int64_t m = (int64_t)di.n * di.s1;
+    const int64_t tot = m * di.r0;
+    sqr_contract_kernel<<<(unsigned)((tot + 127) / 128), 128>>>(md->d_core + di.off_c, Rp, d_pm, di.r0, di.n, di.r1, di.s1);
+    LAUNCHED();
+    if (k > 0) {
+      sqr_weight_kernel<<<(unsigned)((tot + 255) / 256), 256>>>(d_pm, md->d_h + di.off_x, d_a, di.n, (int)m, di.r0);
+      LAUNCHED();
+      sqr_qr_kernel<<<1, 1024>>>(d_a, (int)m, di.r0, md->d_rfac + di.off_r, di.s0);
+      LAUNCHED();
+    }
+    const int64_t ge = (int64_t)di.ksteps * 4 * di.n;
+    sqr_gram_pack_kernel<<<(unsigned)((ge + 127) / 128), 128>>>(d_pm, di.n, di.s1, di.r0, md->d_gp + di.off_g, md->pb, di.ksteps);
+    LAUNCHED();
+  }
+  CKB(cudaGetLastError());
+  CKB(cudaDeviceSynchronize());
+#undef CKB
+  cleanup();
+  return 0;
+}
+
+extern "C" ttirt_sqr_model *ttirt_sqr_model_create(int64_t d, const int64_t *n, int64_t nxs, const double *xs, const int64_t *ttrank,
+                                                   const double *ttcore, int device) {
+  if (d < 1 || !n || !xs || !ttrank || !ttcore) { aux_fail("bad arguments to ttirt_sqr_model_create"); return nullptr; }
+  const int cnt = ttirt_device_count();
+  if (cnt <= 0) { aux_fail("no CUDA device available (this library has no CPU fallback)"); return nullptr; }
+  if (device < 0 || device >= cnt) { aux_fail("device %d out of range (%d visible)", device, cnt); return nullptr; }
+  if (cudaSetDevice(device) != cudaSuccess) { aux_fail("cudaSetDevice(%d) failed", device); return nullptr; }
+  ttirt_sqr_model *md = new ttirt_sqr_model();
+  md->device = device; md->d = d;
+  if (sqr_model_build(md, n, nxs, xs, ttrank, ttcore) != 0) { ttirt_sqr_model_destroy(md); return nullptr; }
+  return md;
+}
+
+extern "C" int64_t ttirt_sqr_model_mode_size(const ttirt_sqr_model *md, int64_t k) {
+  if (!md || k < 0 || k >= md->d) return -1;
+  return md->dims[k].n;
+}
+
+extern "C" int ttirt_sqr_model_get_sweep(const ttirt_sqr_model *md, int64_t k, double *gram_out, double *rr_out) {
+  if (!md) return aux_fail("null model");
+  if (k < 0 || k >= md->d) return aux_fail("dimension out of range");
+  CKS(cudaSetDevice(md->device));
+  const SqrDim &di = md->dims[k];
+  if (gram_out) {
+    std::vector<double> gp((size_t)di.ksteps * 4 * md->pb);
+    CKS(cudaMemcpy(gp.data(), md->d_gp + di.off_g, sizeof(double) * gp.size(), cudaMemcpyDeviceToHost));
+    // unpack: k-step (c, a) row t holds w G[a, 4c + t, :]; fill both (a, b) and (b, a)
+    int ks = 0;
+    for (int c = 0; 4 * c < di.r0; c++) {
+      const int amax = std::min(4 * c + 4, di.r0);
+      for (int a = 0; a < amax; a++, ks++)
+        for (int t = 0; t < 4; t++) {
+          const int b = 4 * c + t;
+          if (b >= di.r0) continue;
+          const double w = a < 4 * c ? 0.5 : 1.0;
+          for (int j = 0; j < di.n; j++) {
+            const double v = gp[((size_t)ks * 4 + t) * md->pb + j] * w;
+            gram_out[(size_t)a + (size_t)di.r0 * b + (size_t)di.r0 * di.r0 * j] = v;
+            if (a < 4 * c) gram_out[(size_t)b + (size_t)di.r0 * a + (size_t)di.r0 * di.r0 * j] = v;
+          }
+        }
+    }
+  }
+  if (rr_out) {
+    if (k == 0) return aux_fail("no factor to the left of the first core");
+    std::vector<double> rt((size_t)di.r0 * di.s0);
+    CKS(cudaMemcpy(rt.data(), md->d_rfac + di.off_r, sizeof(double) * rt.size(), cudaMemcpyDeviceToHost));
+    for (int a = 0; a < di.r0; a++)
+      for (int b = 0; b < di.r0; b++) {
+        double s = 0.0;
+        for (int t = 0; t < di.s0; t++) s += rt[(size_t)a + (size_t)di.r0 * t] * rt[(size_t)b + (size_t)di.r0 * t];
+        rr_out[(size_t)a + (size_t)di.r0 * b] = s;
+      }
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one chunk, device-resident buffers, enqueued on st
+// ------------------------------------------------------------------------------------------------
+static int sqr_enqueue_chunk(ttirt_sqr_model *md, int64_t rows, int64_t D, const double *q, int64_t ldq, double *z, int64_t ldz,
+                             double *lf, int32_t *idx_out, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  const int d = (int)md->d;
+  CKS(cudaMemsetAsync(md->hist, 0, sizeof(int) * d * md->nbpad, st));
+  sqr_init_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(md->F0, md->ldf, (int)rows);
+  LAUNCHED();
+  double *Fin = md->F0, *Fout = md->F1;
+  for (int k = 0; k < (int)D; k++) {
+    const SqrDim &di = md->dims[k];
+    const bool update = (k + 1 < (int)D);
+    PdfArgs pa;
+    pa.F = Fin; pa.ldf = md->ldf; pa.rows = (int)rows; pa.gp = md->d_gp + di.off_g; pa.pb = md->pb; pa.ksteps = di.ksteps;
+    pa.r0 = di.r0; pa.n = di.n; pa.pdf = md->pdf; pa.ldp = md->cap;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (md->profile) {
+      if (md->prof_used == md->prof_events.size()) {
+        cudaEvent_t x, y;
+        CKS(cudaEventCreate(&x)); CKS(cudaEventCreate(&y));
+        md->prof_events.emplace_back(x, y);
+      }
+      e0 = md->prof_events[md->prof_used].first; e1 = md->prof_events[md->prof_used].second;
+      md->prof_used++;
+      md->prof_flops += (double)rows * ((double)di.r0 * (di.r0 + 1) * di.n + 0.5 * di.r0 * (di.r0 + 1));
+      CKS(cudaEventRecord(e0, st));
+    }
+    cudaError_t pe = md->nt == 3 ? pdf_launch<3>(pa, md->sm_count, st) : (md->nt == 5 ? pdf_launch<5>(pa, md->sm_count, st) : pdf_launch<9>(pa, md->sm_count, st));
+    CKS(pe);
+    LAUNCHED();
+    if (e1) CKS(cudaEventRecord(e1, st));
+    TailArgs ta;
+    ta.pdf = md->pdf; ta.cdf = md->cdf; ta.ldp = md->cap; ta.rows = (int)rows; ta.n = di.n;
+    ta.x = md->d_xs + di.off_x; ta.h = md->d_h + di.off_x; ta.hc = md->d_hc + di.off_x;
+    ta.q = q + ldq * k; ta.z = z + ldz * k; ta.idx_out = idx_out ? idx_out + ldz * k : nullptr;
+    ta.idx = md->idx; ta.w1 = md->w1; ta.w2 = md->w2; ta.lf = lf; ta.first = (k == 0);
+    ta.hist = update ? md->hist + (size_t)k * md->nbpad : nullptr;
+    sqr_tail_kernel<<<(unsigned)((rows + 255) / 256), 256, sizeof(int) * di.n, st>>>(ta);
+    LAUNCHED();
+    CKS(cudaGetLastError());
+    if (update) {
+      const int nb = di.n - 1;
+      sqr_bin_scan_kernel<<<1, 32, 0, st>>>(md->hist + (size_t)k * md->nbpad, nb, md->bin_start, md->bin_tile_start, md->cursor);
+      LAUNCHED();
+      sqr_bin_scatter_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(md->idx, (int)rows, md->cursor, md->perm);
+      LAUNCHED();
+      UpdArgs ua;
+      ua.core = md->d_core + di.off_c; ua.r0 = di.r0; ua.n = di.n; ua.r1 = di.r1;
+      ua.Fin = Fin; ua.Fout = Fout; ua.ldf = md->ldf;
+      ua.perm = md->perm; ua.bin_start = md->bin_start; ua.bin_tile_start = md->bin_tile_start; ua.nb = nb;
+      ua.w1 = md->w1; ua.w2 = md->w2;
+      const int r1p = (di.r1 + 3) & ~3;
+      const size_t sm = sizeof(double) * ((size_t)2 * di.r0 * (r1p + 2) + (size_t)di.r0 * (UPD_TS + 2));
+      static bool attr_done[64] = {};
+      if (md->device < 64 && !attr_done[md->device]) {
+        CKS(cudaFuncSetAttribute(sqr_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_done[md->device] = true;
+      }
+      const int64_t max_tiles = (rows + UPD_TS - 1) / UPD_TS + nb;
+      const int grid = (int)std::min<int64_t>(max_tiles, 2 * md->sm_count);
+      sqr_update_kernel<<<grid, UPD_THREADS, sm, st>>>(ua);
+      LAUNCHED();
+      CKS(cudaGetLastError());
+      std::swap(Fin, Fout);
+    }
+  }
+  return 0;
+}
+
+static int64_t sqr_chunk() {
+  const char *e = getenv("TTIRT_SQR_CHUNK");
+  if (e && atoll(e) > 0) return atoll(e);
+  return (int64_t)1 << 18;
+}
+
+extern "C" int ttirt_sqr_sample_device(ttirt_sqr_model *md, int64_t M, int64_t D, const double *d_q, int64_t ldq, double *d_z,
+                                       int64_t ldz, double *d_lf, int32_t *d_idx, void *stream) {
+  if (!md) return aux_fail("null model");
+  if (M < 0 || ldq < M || ldz < M) return aux_fail("bad M / leading dimensions");
+  if (D < 1 || D > md->d) return aux_fail("tt_irt_sqr: q must have between 1 and d columns (got %lld, d = %lld)", (long long)D, (long long)md->d);
+  if (M == 0) return 0;
+  CKS(cudaSetDevice(md->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t chunk = std::min<int64_t>(M, sqr_chunk());
+  if (md->cap < chunk) {
+    CKS(cudaStreamSynchronize(st));
+    if (sqr_ws_ensure(md, chunk, false) != 0) return -1;
+  }
+  for (int64_t m0 = 0; m0 < M; m0 += chunk) {
+    const int64_t rows = std::min(chunk, M - m0);
+    if (sqr_enqueue_chunk(md, rows, D, d_q + m0, ldq, d_z + m0, ldz, d_lf + m0, d_idx ? d_idx + m0 : nullptr, st) != 0) return -1;
+  }
+  return 0;
+}
+
+extern "C" int ttirt_sqr_sample_host(ttirt_sqr_model *md, int64_t M, int64_t D, const double *h_q, double *h_z, double *h_lf,
+                                     int32_t *h_idx, int64_t ld) {
+  if (!md) return aux_fail("null model");
+  if (M < 0 || ld < M) return aux_fail("bad M / leading dimension");
+  if (D < 1 || D > md->d) return aux_fail("tt_irt_sqr: q must have between 1 and d columns (got %lld, d = %lld)", (long long)D, (long long)md->d);
+  if (M == 0) return 0;
+  if (!h_q || !h_z || !h_lf) return aux_fail("null host buffer");
+  CKS(cudaSetDevice(md->device));
+  const int64_t chunk = std::min<int64_t>(M, sqr_chunk());
+  if (sqr_ws_ensure(md, chunk, true) != 0) return -1;
+  cudaStream_t st = md->stream;
+  const int64_t cap = md->cap;
+  for (int64_t m0 = 0; m0 < M; m0 += chunk) {
+    const int64_t rows = std::min(chunk, M - m0);
+    CKS(cudaMemcpy2DAsync(md->q, sizeof(double) * cap, h_q + m0, sizeof(double) * ld, sizeof(double) * rows, (size_t)D, cudaMemcpyHostToDevice, st));
+    if (sqr_enqueue_chunk(md, rows, D, md->q, cap, md->z, cap, md->lf, h_idx ? md->idx_out : nullptr, st) != 0) return -1;
+    CKS(cudaMemcpy2DAsync(h_z + m0, sizeof(double) * ld, md->z, sizeof(double) * cap, sizeof(double) * rows, (size_t)D, cudaMemcpyDeviceToHost, st));
+    CKS(cudaMemcpyAsync(h_lf + m0, md->lf, sizeof(double) * rows, cudaMemcpyDeviceToHost, st));
+    if (h_idx)
+      CKS(cudaMemcpy2DAsync(h_idx + m0, sizeof(int32_t) * ld, md->idx_out, sizeof(int32_t) * cap, sizeof(int32_t) * rows, (size_t)D, cudaMemcpyDeviceToHost, st));
+    CKS(cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
+extern "C" int ttirt_sqr_run_host(int64_t d, const int64_t *n, int64_t nxs, const double *xs, const int64_t *ttrank, const double *ttcore,
+                                  int64_t M, int64_t D, const double *h_q, double *h_z, double *h_lf, int device) {
+  ttirt_sqr_model *md = ttirt_sqr_model_create(d, n, nxs, xs, ttrank, ttcore, device);
+  if (!md) return -1;
+  const int rc = ttirt_sqr_sample_host(md, M, D, h_q, h_z, h_lf, nullptr, M);
+  ttirt_sqr_model_destroy(md);
+  return rc;
+}
+
+extern "C" void ttirt_sqr_profile_enable(ttirt_sqr_model *md, int on) {
+  if (!md) return;
+  md->profile = on != 0;
+  md->prof_used = 0; md->prof_flops = 0.0;
+}
+
+extern "C" int ttirt_sqr_profile_read(ttirt_sqr_model *md, double *ms_total, int64_t *launches, double *flops_total) {
+  if (!md) return aux_fail("null model");
+  CKS(cudaSetDevice(md->device));
+  CKS(cudaDeviceSynchronize());
+  double ms = 0.0;
+  for (size_t i = 0; i < md->prof_used; i++) {
+    float t = 0.f;
+    CKS(cudaEventElapsedTime(&t, md->prof_events[i].first, md->prof_events[i].second));
+    ms += t;
+  }
+  if (ms_total) *ms_total = ms;
+  if (launches) *launches = (int64_t)md->prof_used;
+  if (flops_total) *flops_total = md->prof_flops;
+  return 0;
+}

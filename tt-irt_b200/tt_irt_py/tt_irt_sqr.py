@@ -1,0 +1,162 @@
+"""Host-side mirror of the reference's squared-density sampler (reference matlab/samplers/tt_irt_sqr.m:1):
+
+    xq, lFapp = tt_irt_sqr(xsf, f, q)
+
+Same argument order and meaning as the Matlab function: `xsf` the grids of all dimensions stacked (with or without the two
+boundary points per dimension that the cores lack, :33-39), `f` the TT of the SQUARE ROOT of the density (a ttpy
+tt.tensor or the TTTensor container of tt_irt.py), `q` seeds in [0,1], M x D with 0 < D <= d (D < d samples the marginal
+of the first D variables, :9, :105).  The work is done by the B200 library next to this file (include/tt_irt_sqr.h);
+there is no CPU fallback: without the library or a CUDA device the call raises.
+
+`SqrModel` keeps the swept model resident on the device for repeated sampling (what tt_dirt_sample.m:46,71 does per layer).
+"""
+from ctypes import c_int, c_double, c_longlong, c_void_p, POINTER, byref
+
+import numpy as np
+
+from .tt_irt import load_library, _packed_cores, _raise_last
+
+_bound = False
+
+
+def _lib():
+    global _bound
+    lib = load_library()
+    if not _bound:
+        ip, dp, lp = POINTER(c_int), POINTER(c_double), POINTER(c_longlong)
+        lib.tt_irt_sqr.restype = None
+        lib.tt_irt_sqr.argtypes = [c_int, ip, c_int, dp, ip, dp, c_int, c_int, dp, dp, dp]
+        lib.ttirt_sqr_model_create.restype = c_void_p
+        lib.ttirt_sqr_model_create.argtypes = [c_longlong, lp, c_longlong, dp, lp, dp, c_int]
+        lib.ttirt_sqr_model_destroy.restype = None
+        lib.ttirt_sqr_model_destroy.argtypes = [c_void_p]
+        lib.ttirt_sqr_model_get_sweep.restype = c_int
+        lib.ttirt_sqr_model_get_sweep.argtypes = [c_void_p, c_longlong, dp, dp]
+        lib.ttirt_sqr_model_mode_size.restype = c_longlong
+        lib.ttirt_sqr_model_mode_size.argtypes = [c_void_p, c_longlong]
+        lib.ttirt_sqr_sample_device.restype = c_int
+        lib.ttirt_sqr_sample_device.argtypes = [c_void_p, c_longlong, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong,
+                                                c_void_p, c_void_p, c_void_p]
+        lib.ttirt_sqr_sample_host.restype = c_int
+        lib.ttirt_sqr_sample_host.argtypes = [c_void_p, c_longlong, c_longlong, dp, dp, dp, c_void_p, c_longlong]
+        lib.ttirt_sqr_profile_enable.restype = None
+        lib.ttirt_sqr_profile_enable.argtypes = [c_void_p, c_int]
+        lib.ttirt_sqr_profile_read.restype = c_int
+        lib.ttirt_sqr_profile_read.argtypes = [c_void_p, dp, lp, dp]
+        _bound = True
+    return lib
+
+
+def tt_irt_sqr(xsf, f, q):
+    """ Inverse CDF (Rosenblatt) transform through the square root of the density (reference tt_irt_sqr.m:1-15)
+        Inputs:
+          xsf: grid points (inc. boundaries) of all dimensions stacked (np.float64, size sum(f.n) or sum(f.n + 2))
+          f: TT of SQRT(PDF) on that grid, with or without the boundary points in each variable
+          q: seed points from [0,1]^D (np.float64 M x D), 0 < D <= d
+        Returns:
+          xq: samples mapped from q by the inverse CDF (M x D, Fortran shaped)
+          lFapp: log(approximate PDF) at xq (M)
+    """
+    lib = _lib()
+    q = np.asfortranarray(q, dtype=np.float64)
+    if q.ndim == 1:
+        q = np.asfortranarray(q[:, None])
+    xsf = np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=np.float64).ravel() for x in xsf])
+                               if isinstance(xsf, (list, tuple)) else np.asarray(xsf, dtype=np.float64).ravel(order="F"))
+    core = _packed_cores(f)
+    n = np.ascontiguousarray(f.n, dtype=np.int32)
+    rf = np.ascontiguousarray(f.r, dtype=np.int32)
+    M, D = q.shape
+    if D < 1 or D > f.d:
+        raise ValueError("q must have between 1 and d columns")
+    if xsf.size not in (int(n.sum()), int((n + 2).sum())):
+        raise ValueError("number of grid points (with or without boundaries) in xsf should be sum of mode sizes in f")
+    xq = np.zeros((M, D), dtype=np.float64, order="F")
+    lFapp = np.zeros(M, dtype=np.float64)
+    dp, ip = POINTER(c_double), POINTER(c_int)
+    lib.tt_irt_sqr(c_int(f.d), n.ctypes.data_as(ip), c_int(xsf.size), xsf.ctypes.data_as(dp), rf.ctypes.data_as(ip),
+                   core.ctypes.data_as(dp), c_int(M), c_int(D), q.ctypes.data_as(dp), xq.ctypes.data_as(dp),
+                   lFapp.ctypes.data_as(dp))
+    return xq, lFapp
+
+
+class SqrModel(object):
+    """TT of sqrt(density) swept once on one B200 (tt_irt_sqr.m:41-82), sampled many times (:85-208)."""
+
+    def __init__(self, n, xs, ranks, cores, device=0):
+        lib = _lib()
+        self._lib = lib
+        self.n = np.ascontiguousarray(n, dtype=np.int64)
+        self.r = np.ascontiguousarray(ranks, dtype=np.int64)
+        self.d = int(self.n.size)
+        xs = np.ascontiguousarray(np.asarray(xs, dtype=np.float64).ravel(order="F"))
+        cores = np.ascontiguousarray(np.asarray(cores, dtype=np.float64).ravel(order="F"))
+        if self.r.size != self.d + 1 or cores.size != int((self.r[:-1] * self.n * self.r[1:]).sum()):
+            raise ValueError("inconsistent TT description")
+        lp, dp = POINTER(c_longlong), POINTER(c_double)
+        self._h = lib.ttirt_sqr_model_create(self.d, self.n.ctypes.data_as(lp), int(xs.size), xs.ctypes.data_as(dp),
+                                             self.r.ctypes.data_as(lp), cores.ctypes.data_as(dp), int(device))
+        if not self._h:
+            _raise_last(lib, "ttirt_sqr_model_create")
+        self.n_ext = np.array([lib.ttirt_sqr_model_mode_size(self._h, k) for k in range(self.d)], dtype=np.int64)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ttirt_sqr_model_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def sweep(self, k):
+        """(P{k} of tt_irt_sqr.m:80 as (r_k^2, n_k) F-order, R'R of the factor left of core k or None for k = 0)."""
+        r0, nk = int(self.r[k]), int(self.n_ext[k])
+        G = np.zeros((r0 * r0, nk), order="F")
+        RR = np.zeros((r0, r0), order="F") if k > 0 else None
+        dp = POINTER(c_double)
+        if self._lib.ttirt_sqr_model_get_sweep(self._h, k, G.ctypes.data_as(dp), RR.ctypes.data_as(dp) if k > 0 else None) != 0:
+            _raise_last(self._lib, "ttirt_sqr_model_get_sweep")
+        return G, RR
+
+    def sample(self, q, want_idx=False):
+        q = np.asfortranarray(q, dtype=np.float64)
+        if q.ndim == 1:
+            q = np.asfortranarray(q[:, None])
+        M, D = q.shape
+        Z = np.zeros((M, D), dtype=np.float64, order="F")
+        lF = np.zeros(M, dtype=np.float64)
+        idx = np.zeros((M, D), dtype=np.int32, order="F") if want_idx else None
+        dp = POINTER(c_double)
+        rc = self._lib.ttirt_sqr_sample_host(self._h, M, D, q.ctypes.data_as(dp), Z.ctypes.data_as(dp), lF.ctypes.data_as(dp),
+                                             idx.ctypes.data_as(c_void_p) if want_idx else None, M)
+        if rc != 0:
+            _raise_last(self._lib, "ttirt_sqr_sample_host")
+        return (Z, lF, idx) if want_idx else (Z, lF)
+
+    def sample_device(self, M, D, q_ptr, ldq, z_ptr, ldz, lf_ptr, idx_ptr=None, stream=None):
+        rc = self._lib.ttirt_sqr_sample_device(self._h, int(M), int(D), c_void_p(q_ptr), int(ldq), c_void_p(z_ptr), int(ldz),
+                                               c_void_p(lf_ptr), c_void_p(idx_ptr) if idx_ptr else None,
+                                               c_void_p(stream) if stream else None)
+        if rc != 0:
+            _raise_last(self._lib, "ttirt_sqr_sample_device")
+
+    def profile_enable(self, on=True):
+        self._lib.ttirt_sqr_profile_enable(self._h, 1 if on else 0)
+
+    def profile_read(self):
+        """(summed pdf-kernel ms, launches timed, algorithmic flops of those launches)."""
+        ms, n, fl = c_double(0), c_longlong(0), c_double(0)
+        if self._lib.ttirt_sqr_profile_read(self._h, byref(ms), byref(n), byref(fl)) != 0:
+            _raise_last(self._lib, "ttirt_sqr_profile_read")
+        return ms.value, n.value, fl.value
+
+
+def flops_per_sample(ns, ranks, D=None):
+    """Algorithmic FP64 flops per sample of the squared-density transform: per sampled dimension the symmetric half of the
+    conditional contraction (:107-112), r_k (r_k + 1) n_k + r_k (r_k + 1) / 2, plus 4 r_k r_{k+1} per interface update (:205)."""
+    ns = np.asarray(ns, dtype=np.int64)
+    ranks = np.asarray(ranks, dtype=np.int64)
+    D = ns.size if D is None else int(D)
+    r0 = ranks[:D]
+    w = (r0 * (r0 + 1) * ns[:D]).sum() + (r0 * (r0 + 1) // 2).sum()
+    w += (4 * ranks[:D - 1] * ranks[1:D]).sum()
+    return int(w)
