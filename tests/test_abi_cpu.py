@@ -1,5 +1,5 @@
 """CPU tests of the C-ABI boundary: both libraries load without a GPU, export every symbol that
-include/tt_irt1.h declares, fail loudly (no CPU fallback) when no device is present, and the host-side
+include/tt_irt1.h and include/tt_irt_sqr.h declare, fail loudly (no CPU fallback) when no device is present, and the host-side
 mirror of the reference wrapper keeps the reference's argument handling."""
 import ctypes
 import os
@@ -14,7 +14,7 @@ LIB64 = os.path.join(ROOT, "tt-irt_b200", "lib", "libtt_irt1_int64.so")
 
 
 def _declared_symbols():
-    src = open(os.path.join(ROOT, "include", "tt_irt1.h")).read()
+    src = open(os.path.join(ROOT, "include", "tt_irt1.h")).read() + open(os.path.join(ROOT, "include", "tt_irt_sqr.h")).read()
     return sorted(set(re.findall(r"^TTIRT_API\s+[\w\s\*]+?\b(\w+)\s*\(", src, flags=re.M)))
 
 
@@ -28,7 +28,7 @@ def libs():
 
 def test_header_declares_the_reference_entry_point():
     syms = _declared_symbols()
-    assert "tt_irt1" in syms and len(syms) >= 12
+    assert "tt_irt1" in syms and "tt_irt_sqr" in syms and len(syms) >= 22
 
 
 def test_both_libraries_export_every_declared_symbol(libs):

@@ -1,0 +1,180 @@
+"""GPU parity tests (-m gpu) of the squared-density inverse Rosenblatt transform (include/tt_irt_sqr.h) against the numpy
+oracle of matlab/samplers/tt_irt_sqr.m and the committed tests/golden/sqr_*.npz.
+
+Bars (the protocol of oracle/parity.py, as for tt_irt1): interval indices equal to the oracle's (a flip is admissible only
+where q sits on a CDF node to 1e-13; none observed), |dZ| <= 1e-12 max(1, |Z|) + 8 eps cumsum(cond) entry by entry,
+lFapp within 1e-12 relative plus the same admitted Z perturbation carried through the density slope.  The sweep operands
+(P{k} of :80 and R'R of :70) agree to 1e-12 relative.  Signed cores make the conditional contraction cancel; there the bar
+is zero index flips and 1e-8 (the reference's own noise floor for such cores).
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from oracle import parity
+from oracle.tt_irt_sqr_oracle import sqr_sweep, tt_irt_sqr_oracle
+from test_sqr_oracle import GOLD, load_sqr_golden, mk
+from tt_irt_py import synth, tt_irt, tt_irt_sqr
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB32 = os.path.join(ROOT, "tt-irt_b200", "tt_irt_py", "tt_irt1_int32.so")
+LIB64 = os.path.join(ROOT, "tt-irt_b200", "lib", "libtt_irt1_int64.so")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    if tt_irt.device_count() < 1:
+        pytest.fail("no CUDA device: the -m gpu tests need a B200 (there is no CPU fallback)")
+
+
+SHAPES = [
+    # d, n, r, M, grid, boundary-less cores, D
+    (1, 9, 1, 500, "uniform", False, None),            # single dimension, r = 1
+    (2, 2, 1, 300, "uniform", False, None),            # smallest grid
+    (3, 5, 3, 400, "uniform", False, None),
+    (4, 9, 4, 1000, "uniform", False, None),
+    (8, 17, 8, 3000, "uniform", False, None),          # BASELINE configs[0] shape
+    (6, 17, 16, 3000, "chebyshev", False, None),       # DIRT layer grid
+    (5, 15, 6, 1500, "uniform", True, None),           # grid carries boundary points the cores lack (:33-36, :53-60)
+    (6, 33, 32, 1500, "uniform", False, 4),            # marginal of the first 4 variables (:9, :105)
+    (5, 12, 40, 1200, "uniform", False, None),         # rank not a multiple of 8, grid not 8 j + 1
+    (4, 65, 64, 1024, "uniform", False, None),         # BASELINE configs[2] class (lone-column kernel variant)
+    (3, 72, 64, 600, "chebyshev", False, None),        # largest supported shape
+    (4, 6, 30, 800, "uniform", False, None),           # n s < r: rank-deficient QR factor
+    (3, 40, 7, 777, "uniform", False, None),           # odd rank, ragged sample count
+]
+
+
+@pytest.mark.parametrize("d,n,r,M,grid,ext,D", SHAPES)
+def test_sweep_and_samples_match_the_oracle(d, n, r, M, grid, ext, D):
+    ns, xs, rk, c = mk.make_case(d, n, r, 300 + d + n + r, -1.0, 1.0, grid, "uniform", ext)
+    D = d if D is None else D
+    q = synth.make_q(M, D, seed=11)
+    sw = sqr_sweep(ns, xs, rk, c)
+    Zo, lo, io, cond, gap, lsens = tt_irt_sqr_oracle(ns, xs, rk, c, q, extras=True)
+    md = tt_irt_sqr.SqrModel(ns, xs, rk, c)
+    try:
+        for k in range(d):
+            G, RR = md.sweep(k)
+            assert np.abs(G - sw["P"][k]).max() <= 1e-12 * np.abs(sw["P"][k]).max()
+            if k > 0:
+                RRo = sw["R"][k] @ sw["R"][k].T
+                assert np.abs(RR - RRo).max() <= 1e-12 * np.abs(RRo).max()
+        Z, lF, idx = md.sample(q, want_idx=True)
+    finally:
+        md.close()
+    st, fails = parity.compare(Z, lF, idx, Zo, lo, io, cond, gap, lsens)
+    assert not fails, (fails, st)
+    assert st["idx_flips"] == 0
+
+
+def test_signed_cores_keep_indices_and_stay_at_the_noise_floor():
+    ns, xs, rk, c = synth.make_tt(5, 20, 12, seed=337, cores="normal")
+    q = synth.make_q(2000, 5, seed=11)
+    Zo, lo, io, cond, gap, lsens = tt_irt_sqr_oracle(ns, xs, rk, c, q, extras=True)
+    md = tt_irt_sqr.SqrModel(ns, xs, rk, c)
+    try:
+        Z, lF, idx = md.sample(q, want_idx=True)
+    finally:
+        md.close()
+    assert (idx != io).sum() == 0
+    assert np.abs(Z - Zo).max() < 1e-8 and np.abs(lF - lo).max() < 1e-8
+
+
+@pytest.mark.parametrize("name", GOLD)
+def test_golden_fixtures(name):
+    g, ns, xs, rk, c, q = load_sqr_golden(name)
+    md = tt_irt_sqr.SqrModel(ns, xs, rk, c)
+    try:
+        Z, lF, idx = md.sample(q, want_idx=True)
+    finally:
+        md.close()
+    st, fails = parity.compare(Z, lF, idx, g["xq"], g["lFapp"], g["idx"], g["cond"], g["gap"], g["lsens"])
+    assert not fails, (fails, st)
+
+
+def _c_call(lib_path, it, ct, ns, xs, rk, c, q):
+    lib = ctypes.CDLL(lib_path)
+    M, D = q.shape
+    Z = np.zeros((M, D), order="F")
+    lF = np.zeros(M)
+    n_ = np.ascontiguousarray(ns, dtype=it)
+    r_ = np.ascontiguousarray(rk, dtype=it)
+    dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ct)
+    lib.tt_irt_sqr.restype = None
+    lib.tt_irt_sqr.argtypes = [ct, ip, ct, dp, ip, dp, ct, ct, dp, dp, dp]
+    lib.tt_irt_sqr(len(ns), n_.ctypes.data_as(ip), xs.size, xs.ctypes.data_as(dp), r_.ctypes.data_as(ip), c.ctypes.data_as(dp), M, D,
+                   q.ctypes.data_as(dp), Z.ctypes.data_as(dp), lF.ctypes.data_as(dp))
+    return Z, lF
+
+
+def test_c_symbol_both_widths_and_python_mirror_agree_bit_for_bit():
+    ns, xs, rk, c = mk.make_case(6, 17, 8, 77, -2.0, 2.0, "uniform", "uniform", True)
+    q = synth.make_q(5000, 6, seed=3)
+    md = tt_irt_sqr.SqrModel(ns, xs, rk, c)
+    try:
+        Z0, l0 = md.sample(q)
+    finally:
+        md.close()
+    Z32, l32 = _c_call(LIB32, np.int32, ctypes.c_int, ns, xs, rk, c, q)
+    Z64, l64 = _c_call(LIB64, np.int64, ctypes.c_longlong, ns, xs, rk, c, q)
+    Zp, lp = tt_irt_sqr.tt_irt_sqr(xs, tt_irt.TTTensor(ns, rk, c), q)
+    for Z, l in ((Z32, l32), (Z64, l64), (Zp, lp)):
+        np.testing.assert_array_equal(Z, Z0)
+        np.testing.assert_array_equal(l, l0)
+
+
+def test_full_size_properties():
+    """At a size the oracle cannot walk in seconds: row-subset invariance against the oracle, marginal = prefix of the full
+    transform, chunk invariance, determinism, samples inside their grid cell, monotone first coordinate."""
+    d, n, r, M = 6, 33, 32, 1 << 17
+    ns, xs, rk, c = synth.make_tt(d, n, r, seed=19, lo=-3.0, hi=3.0)
+    q = synth.make_q(M, d, seed=23)
+    md = tt_irt_sqr.SqrModel(ns, xs, rk, c)
+    try:
+        Z, lF, idx = md.sample(q, want_idx=True)
+        Z2, lF2 = md.sample(q)
+        Zm, lm = md.sample(q[:, :3])
+        os.environ["TTIRT_SQR_CHUNK"] = "10000"
+        try:
+            Zc, lc = md.sample(q)
+        finally:
+            del os.environ["TTIRT_SQR_CHUNK"]
+    finally:
+        md.close()
+    np.testing.assert_array_equal(Z, Z2)
+    np.testing.assert_array_equal(lF, lF2)
+    np.testing.assert_array_equal(Z, Zc)
+    np.testing.assert_array_equal(lF, lc)
+    np.testing.assert_array_equal(Zm, Z[:, :3])
+    rows = np.random.default_rng(1).choice(M, 512, replace=False)
+    Zo, lo, io, cond, gap, lsens = tt_irt_sqr_oracle(ns, xs, rk, c, q[rows], extras=True)
+    st, fails = parity.compare(Z[rows], lF[rows], idx[rows], Zo, lo, io, cond, gap, lsens)
+    assert not fails, (fails, st)
+    for k in range(d):
+        x = xs[k * n:(k + 1) * n]
+        assert (Z[:, k] >= x[idx[:, k]]).all() and (Z[:, k] <= x[idx[:, k] + 1]).all()
+    o = np.argsort(q[:, 0], kind="stable")
+    assert (np.diff(Z[o, 0]) >= 0).all()
+    assert np.isfinite(lF).all()
+
+
+def test_failures_are_loud():
+    ns, xs, rk, c = synth.make_tt(3, 9, 4, seed=1)
+    q = synth.make_q(64, 3, seed=2)
+    Z, l = _c_call(LIB32, np.int32, ctypes.c_int, ns, xs[:-1].copy(), rk, c, q)      # grid size matches neither sum(n) nor sum(n + 2)
+    assert np.isnan(Z).all() and np.isnan(l).all()
+    with pytest.raises(RuntimeError):
+        tt_irt_sqr.SqrModel(*synth.make_tt(3, 9, 70, seed=1))                        # rank beyond the supported shapes
+    with pytest.raises(RuntimeError):
+        tt_irt_sqr.SqrModel(*synth.make_tt(3, 80, 4, seed=1))                        # grid beyond the supported shapes
+    md = tt_irt_sqr.SqrModel(ns, xs, rk, c)
+    try:
+        with pytest.raises(RuntimeError):
+            md.sample(synth.make_q(16, 4, seed=2))                                   # more seed columns than dimensions
+    finally:
+        md.close()

@@ -977,7 +977,10 @@ int run_on_device(int device, int64_t d, const int64_t *n, const double *xs, con
 }
 }  // namespace
 
+namespace ttirt { void sqr_pool_clear(); }   // ttirt_sqr.cu: idle device blocks of the squared-density path
+
 extern "C" void ttirt_cache_clear(void) {
+  ttirt::sqr_pool_clear();
   for (int g = 0; g < kMaxDevices; g++) {
     std::lock_guard<std::mutex> lock(g_slots[g].mu);
     if (g_slots[g].md) { ttirt_model_destroy(g_slots[g].md); g_slots[g].md = nullptr; }

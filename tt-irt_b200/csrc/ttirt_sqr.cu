@@ -15,10 +15,14 @@
 //                                       in shared memory
 // No CPU fallback anywhere: without a device every entry point fails.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/tt_irt_sqr.h"
@@ -40,6 +44,75 @@ using ttirt::aux_fail;
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
+
+// ------------------------------------------------------------------------------------------------
+// device allocations: blocks are handed back to a per-device pool instead of cudaFree (which synchronises the device and,
+// with cudaMalloc, costs more than the kernels of a small call): DIRT calls the transform once per layer with same-shaped
+// TTs (tt_dirt_sample.m:46,71).  No results survive in it; TTIRT_CACHE=0 disables it, ttirt_cache_clear() empties it.
+// ------------------------------------------------------------------------------------------------
+struct DevPool {
+  std::mutex mu;
+  std::multimap<size_t, void *> idle;
+  std::unordered_map<void *, size_t> live;
+};
+DevPool g_pool[64];
+
+bool pool_enabled() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("TTIRT_CACHE"); v = (e && atoi(e) == 0 && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+
+template <typename T>
+cudaError_t sqr_alloc(T **p, size_t bytes) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (bytes == 0) bytes = 8;
+  if (pool_enabled() && dev >= 0 && dev < 64) {
+    DevPool &pl = g_pool[dev];
+    std::lock_guard<std::mutex> lock(pl.mu);
+    auto it = pl.idle.find(bytes);
+    if (it != pl.idle.end()) {
+      *p = static_cast<T *>(it->second);
+      pl.live[it->second] = bytes;
+      pl.idle.erase(it);
+      return cudaSuccess;
+    }
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, bytes);
+    if (e != cudaSuccess) {   // out of memory: give the idle blocks back and retry once
+      cudaGetLastError();
+      for (auto &kv : pl.idle) cudaFree(kv.second);
+      pl.idle.clear();
+      e = cudaMalloc(&q, bytes);
+      if (e != cudaSuccess) return e;
+    }
+    pl.live[q] = bytes;
+    *p = static_cast<T *>(q);
+    return cudaSuccess;
+  }
+  void *q = nullptr;
+  cudaError_t e = cudaMalloc(&q, bytes);
+  *p = static_cast<T *>(q);
+  return e;
+}
+
+void sqr_free(void *p) {
+  if (!p) return;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (pool_enabled() && dev >= 0 && dev < 64) {
+    DevPool &pl = g_pool[dev];
+    std::lock_guard<std::mutex> lock(pl.mu);
+    auto it = pl.live.find(p);
+    if (it != pl.live.end()) {
+      pl.idle.emplace(it->second, p);
+      pl.live.erase(it);
+      return;
+    }
+  }
+  cudaFree(p);
+}
 
 // ------------------------------------------------------------------------------------------------
 // geometry of the packed Gram operand
@@ -159,17 +232,31 @@ __global__ void sqr_weight_kernel(const double *__restrict__ Pm, const double *_
   A[e] = __dmul_rn(Pm[e], w);
 }
 
-// :70-71  R of the economy QR of A (m x r, column-major, overwritten): Householder reflectors as LAPACK dgeqr2 / dlarfg
-// form them, one CTA, one warp per trailing column.  Rt receives R' (r x rnew column-major, rnew = min(m, r)).
-__global__ void __launch_bounds__(1024) sqr_qr_kernel(double *A, int m, int r, double *Rt, int rnew) {
+// :70-71  R of the economy QR of A (m x r): communication-avoiding (TSQR) Householder.  Each CTA factors a block of rows
+// held in shared memory (reflectors as LAPACK dgeqr2 / dlarfg form them, one warp per trailing column) and emits its R;
+// the stacked R factors are factored again until one block is left.  Only R'R enters the result (the factor's row signs and
+// the order of the rows are immaterial), and Householder QR of stacked R factors is as backward stable as the flat one.
+//   in   : column-major, leading dimension lda, rows [b * rb, min(m, (b + 1) * rb)) belong to CTA b
+//   out  : final == 0: stack (column-major (gridDim.x * r) x r), CTA b writes rows [b * r, (b + 1) * r) (zero below the factor)
+//          final == 1: R' (r x rnew column-major, rnew = min(m, r)), single CTA
+__global__ void __launch_bounds__(1024) sqr_qr_block_kernel(const double *__restrict__ in, int m, int lda, int r, int rb, double *out,
+                                                            int ldo, int final, int rnew) {
+  extern __shared__ __align__(16) double As[];     // mb x r, column-major, pitch mb
   __shared__ double red[32];
   __shared__ double s_tau, s_scale;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-  const int steps = m < r ? m : r;
+  const int row0 = blockIdx.x * rb;
+  const int mb = min(rb, m - row0);
+  for (int e = tid; e < mb * r; e += blockDim.x) {
+    const int i = e % mb, c = e / mb;
+    As[e] = in[(size_t)row0 + i + (size_t)lda * c];
+  }
+  __syncthreads();
+  const int steps = mb < r ? mb : r;
   for (int c = 0; c < steps; c++) {
-    double *col = A + (size_t)c * m;
+    double *col = As + (size_t)c * mb;
     double ss = 0.0;
-    for (int i = c + 1 + tid; i < m; i += blockDim.x) ss = fma(col[i], col[i], ss);
+    for (int i = c + 1 + tid; i < mb; i += blockDim.x) ss = fma(col[i], col[i], ss);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(FULL, ss, o);
     if (lane == 0) red[warp] = ss;
@@ -193,25 +280,32 @@ __global__ void __launch_bounds__(1024) sqr_qr_kernel(double *A, int m, int r, d
     __syncthreads();
     const double tau = s_tau, scale = s_scale;
     if (tau != 0.0) {
-      for (int i = c + 1 + tid; i < m; i += blockDim.x) col[i] *= scale;
+      for (int i = c + 1 + tid; i < mb; i += blockDim.x) col[i] *= scale;
       __syncthreads();
       for (int cc = c + 1 + warp; cc < r; cc += nw) {
-        double *cj = A + (size_t)cc * m;
+        double *cj = As + (size_t)cc * mb;
         double dot = 0.0;
-        for (int i = c + 1 + lane; i < m; i += 32) dot = fma(col[i], cj[i], dot);
+        for (int i = c + 1 + lane; i < mb; i += 32) dot = fma(col[i], cj[i], dot);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(FULL, dot, o);
         dot += cj[c];
         const double t = tau * dot;
         if (lane == 0) cj[c] -= t;
-        for (int i = c + 1 + lane; i < m; i += 32) cj[i] = fma(-t, col[i], cj[i]);
+        for (int i = c + 1 + lane; i < mb; i += 32) cj[i] = fma(-t, col[i], cj[i]);
       }
     }
     __syncthreads();
   }
-  for (int e = tid; e < r * rnew; e += blockDim.x) {
-    const int a = e % r, t = e / r;
-    Rt[e] = (t <= a) ? A[(size_t)t + (size_t)m * a] : 0.0;
+  if (final) {
+    for (int e = tid; e < r * rnew; e += blockDim.x) {
+      const int a = e % r, t = e / r;
+      out[e] = (t <= a && t < steps) ? As[(size_t)t + (size_t)mb * a] : 0.0;
+    }
+  } else {
+    for (int e = tid; e < r * r; e += blockDim.x) {
+      const int t = e % r, a = e / r;
+      out[(size_t)blockIdx.x * r + t + (size_t)ldo * a] = (t <= a && t < steps) ? As[(size_t)t + (size_t)mb * a] : 0.0;
+    }
   }
 }
 
@@ -273,7 +367,9 @@ __host__ __device__ inline size_t pdf_smem_bytes(int ldf, int pb) {
 //     signalled on an mbarrier, released by the eight warps on a second mbarrier;
 //   * A is never stored: lane (g, t) multiplies f_g[a] (one broadcast LDS per k-step) with f_g[4c + t] (one LDS per column block);
 //   * pitches: ldf = 4 (mod 8) and pb = 4 (mod 8) doubles make the fragment loads bank-conflict free without a swizzle.
-template <int NT>
+//   * TAIL1 (n = 8 NT + 1, the usual 2^p + 1 grid): the lone last grid column is a DFMA dot product on the A values the lanes
+//     already hold (one broadcast LDS and two DFMA per k-step) instead of a DMMA column tile that is 7/8 padding.
+template <int NT, bool TAIL1>
 __global__ void __launch_bounds__(32 * (PDF_WARPS + 1), 1) sqr_pdf_kernel(PdfArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *Fs = reinterpret_cast<double *>(smem_raw);
@@ -323,6 +419,9 @@ __global__ void __launch_bounds__(32 * (PDF_WARPS + 1), 1) sqr_pdf_kernel(PdfArg
     for (int mt = 0; mt < PDF_MT; mt++)
 #pragma unroll
       for (int nt = 0; nt < NT; nt++) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
+    double tl[PDF_MT];
+#pragma unroll
+    for (int mt = 0; mt < PDF_MT; mt++) tl[mt] = 0.0;
     int ks = 0;
     uint32_t stage = it % PDF_STAGES, parity = (it / PDF_STAGES) & 1;
     for (int c = 0; c < nchunk; c++) {
@@ -343,6 +442,11 @@ __global__ void __launch_bounds__(32 * (PDF_WARPS + 1), 1) sqr_pdf_kernel(PdfArg
 #pragma unroll
           for (int mt = 0; mt < PDF_MT; mt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], av[mt], b);
         }
+        if (TAIL1) {
+          const double bl = bp[8 * NT - g];      // row 4 kk + t, column 8 NT
+#pragma unroll
+          for (int mt = 0; mt < PDF_MT; mt++) tl[mt] = fma(av[mt], bl, tl[mt]);
+        }
         ks++;
         if ((ks & (PDF_KS - 1)) == 0 || ks == a.ksteps) {
           __syncwarp();
@@ -362,6 +466,16 @@ __global__ void __launch_bounds__(32 * (PDF_WARPS + 1), 1) sqr_pdf_kernel(PdfArg
           if (col < a.n) a.pdf[(size_t)col * a.ldp + row] = acc[mt][nt][0];
           if (col + 1 < a.n) a.pdf[(size_t)(col + 1) * a.ldp + row] = acc[mt][nt][1];
         }
+      }
+    }
+    if (TAIL1) {
+#pragma unroll
+      for (int mt = 0; mt < PDF_MT; mt++) {
+        double v = tl[mt];
+        v += __shfl_xor_sync(FULL, v, 1);
+        v += __shfl_xor_sync(FULL, v, 2);
+        const int row = m0 + mt * 8 + g;
+        if (t == 0 && row < a.rows) a.pdf[(size_t)(8 * NT) * a.ldp + row] = v;
       }
     }
   }
@@ -440,8 +554,9 @@ __global__ void __launch_bounds__(256) sqr_tail_kernel(TailArgs a) {
   }
 }
 
-constexpr int UPD_TS = 64;        // samples per tile of the interface update
-constexpr int UPD_THREADS = 256;
+constexpr int UPD_WARPS = 8;
+constexpr int UPD_TS = 16 * UPD_WARPS;   // samples per tile of the interface update (two 8-row MMA tiles per warp)
+constexpr int UPD_THREADS = 32 * UPD_WARPS;
 
 __global__ void sqr_bin_scan_kernel(const int *__restrict__ hist, int nb, int *bin_start, int *bin_tile_start, int *cursor) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -476,86 +591,120 @@ struct UpdArgs {
   const double *w1, *w2;
 };
 
-// :197-207  fkm1' = (fkm1 core(:, i0, :)) Aq + (fkm1 core(:, i0 + 1, :)) Bq for 64-sample tiles of one interval; the two
-// slabs are staged in shared memory once per interval and CTA (CTAs own contiguous tile ranges).  FP64 FMA, 4 x 4 outputs
-// per thread for each slab.
+// :197-207  fkm1' = (fkm1 core(:, i0, :)) Aq + (fkm1 core(:, i0 + 1, :)) Bq for 128-sample tiles of one interval, as two
+// FP64 tensor-core products per tile.  The two core slabs of an interval are staged once per interval and CTA (CTAs own
+// contiguous tile ranges) in the layout they have in global memory ([l][a], a fastest), the gathered interface rows as
+// [sample][a]; both pitches are 4 (mod 8) doubles, which makes every fragment load bank-conflict free without a swizzle.
+// NTU = 8-column output tiles (r_{k+1} <= 8 NTU).
+template <int NTU>
 __global__ void __launch_bounds__(UPD_THREADS) sqr_update_kernel(UpdArgs a) {
   extern __shared__ __align__(16) double sm[];
-  const int r1p = (a.r1 + 3) & ~3;
-  const int SP = r1p + 2;                 // slab pitch: [a][l], l fastest
-  const int FP = UPD_TS + 2;              // staged interface pitch: [a][sample]
-  double *S0 = sm, *S1 = S0 + (size_t)a.r0 * SP, *Ft = S1 + (size_t)a.r0 * SP;
+  const int r0p = (a.r0 + 3) & ~3, r1p = (a.r1 + 3) & ~3;
+  const int P = ((a.r0 + 7) & ~7) + 4;    // pitch of slab rows and of staged interface rows
+  double *S0 = sm, *S1 = S0 + (size_t)8 * NTU * P, *Fs = S1 + (size_t)8 * NTU * P;   // Fs: two buffers of UPD_TS rows
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tx = tid & 15, ty = tid >> 4;
+  const int g = lane >> 2, t = lane & 3;
   const int total = a.bin_tile_start[a.nb];
   const int t_begin = (int)(((int64_t)total * blockIdx.x) / gridDim.x);
   const int t_end = (int)(((int64_t)total * (blockIdx.x + 1)) / gridDim.x);
+  // Each warp gathers and multiplies its own 16 samples: no CTA-wide barrier per tile.  The rows of the NEXT tile are
+  // fetched with cp.async (16 bytes per lane, a whole row per instruction) while the current tile is multiplied.
+  // Rows of the interface buffers are zero in the columns [r, r rounded up to 4), so whole 4-blocks are copied.
+  const int chunks = r0p >> 1;            // 16-byte pieces per row
+  int binp = 0;
+  auto gather = [&](int tile, int buf) {
+    while (tile >= a.bin_tile_start[binp + 1]) binp++;
+    const int start = a.bin_start[binp] + (tile - a.bin_tile_start[binp]) * UPD_TS;
+    const int cnt = min(UPD_TS, a.bin_start[binp + 1] - start);
+    const int mine = warp * 16 + (lane & 15);
+    const int myid = mine < cnt ? a.perm[start + mine] : -1;
+    double *fw = Fs + ((size_t)buf * UPD_TS + warp * 16) * P;
+#pragma unroll 4
+    for (int row = 0; row < 16; row++) {
+      const int id = __shfl_sync(FULL, myid, row);
+      if (id >= 0)
+        for (int ch = lane; ch < chunks; ch += 32)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(fw + row * P + 2 * ch)), "l"(a.Fin + (size_t)id * a.ldf + 2 * ch) : "memory");
+    }
+  };
+  int buf = 0;
+  if (t_begin < t_end) gather(t_begin, 0);
+  asm volatile("cp.async.commit_group;" ::: "memory");
   int bin = 0, staged = -1;
-  for (int tile = t_begin; tile < t_end; tile++) {
+  for (int tile = t_begin; tile < t_end; tile++, buf ^= 1) {
     while (tile >= a.bin_tile_start[bin + 1]) bin++;
     const int start = a.bin_start[bin] + (tile - a.bin_tile_start[bin]) * UPD_TS;
     const int cnt = min(UPD_TS, a.bin_start[bin + 1] - start);
-    __syncthreads();                      // previous tile's reads of Ft (and of the slabs, when they change) are done
+    __syncwarp();                         // this warp's reads of the other buffer (previous tile) are done
+    if (tile + 1 < t_end) gather(tile + 1, buf ^ 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
     if (bin != staged) {
+      __syncthreads();                    // every warp is done with the previous interval's slabs
       const int64_t cs = (int64_t)a.r0 * a.n;
-      for (int e = tid; e < a.r0 * r1p; e += UPD_THREADS) {
-        const int aa = e % a.r0, l = e / a.r0;
+      for (int e = tid; e < 8 * NTU * r0p; e += UPD_THREADS) {
+        const int aa = e % r0p, l = e / r0p;
         double v0 = 0.0, v1 = 0.0;
-        if (l < a.r1) {
+        if (l < a.r1 && aa < a.r0) {
           v0 = __ldg(a.core + aa + (int64_t)a.r0 * bin + cs * l);
           v1 = __ldg(a.core + aa + (int64_t)a.r0 * (bin + 1) + cs * l);
         }
-        S0[aa * SP + l] = v0; S1[aa * SP + l] = v1;
+        S0[l * P + aa] = v0; S1[l * P + aa] = v1;
       }
       staged = bin;
+      __syncthreads();
     }
-    for (int s = warp; s < UPD_TS; s += UPD_THREADS / 32) {
-      const bool live = s < cnt;
-      const size_t id = live ? (size_t)a.perm[start + s] : 0;
-      for (int aa = lane; aa < a.r0; aa += 32) Ft[aa * FP + s] = live ? a.Fin[id * a.ldf + aa] : 0.0;
-    }
-    __syncthreads();
-    if (4 * tx < r1p) {
-      double acc0[4][4], acc1[4][4];
+    asm volatile("cp.async.wait_group 1;" ::: "memory");   // all but the newest group (the next tile's rows) have landed
+    __syncwarp();
+    const double *fw = Fs + ((size_t)buf * UPD_TS + warp * 16) * P;
+    double acc0[2][NTU][2], acc1[2][NTU][2];
 #pragma unroll
-      for (int i = 0; i < 4; i++)
+    for (int mt = 0; mt < 2; mt++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) { acc0[i][j] = 0.0; acc1[i][j] = 0.0; }
-      for (int aa = 0; aa < a.r0; aa++) {
-        const double2 fa = *reinterpret_cast<const double2 *>(Ft + aa * FP + 4 * ty);
-        const double2 fb = *reinterpret_cast<const double2 *>(Ft + aa * FP + 4 * ty + 2);
-        const double2 s0a = *reinterpret_cast<const double2 *>(S0 + aa * SP + 4 * tx);
-        const double2 s0b = *reinterpret_cast<const double2 *>(S0 + aa * SP + 4 * tx + 2);
-        const double2 s1a = *reinterpret_cast<const double2 *>(S1 + aa * SP + 4 * tx);
-        const double2 s1b = *reinterpret_cast<const double2 *>(S1 + aa * SP + 4 * tx + 2);
-        const double f[4] = {fa.x, fa.y, fb.x, fb.y};
-        const double u0[4] = {s0a.x, s0a.y, s0b.x, s0b.y};
-        const double u1[4] = {s1a.x, s1a.y, s1b.x, s1b.y};
+      for (int nt = 0; nt < NTU; nt++) { acc0[mt][nt][0] = acc0[mt][nt][1] = 0.0; acc1[mt][nt][0] = acc1[mt][nt][1] = 0.0; }
+    for (int ks = 0; ks < (r0p >> 2); ks++) {
+      const double a0 = fw[g * P + 4 * ks + t], a1 = fw[(8 + g) * P + 4 * ks + t];
+      const double *b0 = S0 + g * P + 4 * ks + t, *b1 = S1 + g * P + 4 * ks + t;
 #pragma unroll
-        for (int i = 0; i < 4; i++)
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            acc0[i][j] = fma(f[i], u0[j], acc0[i][j]);
-            acc1[i][j] = fma(f[i], u1[j], acc1[i][j]);
-          }
+      for (int nt = 0; nt < NTU; nt++) {
+        const double u0 = b0[nt * 8 * P], u1 = b1[nt * 8 * P];
+        dmma884(acc0[0][nt][0], acc0[0][nt][1], a0, u0);
+        dmma884(acc0[1][nt][0], acc0[1][nt][1], a1, u0);
+        dmma884(acc1[0][nt][0], acc1[0][nt][1], a0, u1);
+        dmma884(acc1[1][nt][0], acc1[1][nt][1], a1, u1);
       }
+    }
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const int s = 4 * ty + i;
-        if (s < cnt) {
-          const size_t id = (size_t)a.perm[start + s];
-          const double wa = a.w1[id], wb = a.w2[id];
-          double o[4];
+    for (int mt = 0; mt < 2; mt++) {
+      const int sidx = warp * 16 + mt * 8 + g;
+      if (sidx < cnt) {
+        const size_t id = (size_t)a.perm[start + sidx];
+        const double wa = a.w1[id], wb = a.w2[id];
+        double *dst = a.Fout + id * a.ldf + 2 * t;
 #pragma unroll
-          for (int j = 0; j < 4; j++)
-            o[j] = (4 * tx + j < a.r1) ? __dadd_rn(__dmul_rn(acc0[i][j], wa), __dmul_rn(acc1[i][j], wb)) : 0.0;   // :205
-          double *dst = a.Fout + id * a.ldf + 4 * tx;
-          *reinterpret_cast<double2 *>(dst) = make_double2(o[0], o[1]);
-          *reinterpret_cast<double2 *>(dst + 2) = make_double2(o[2], o[3]);
+        for (int nt = 0; nt < NTU; nt++) {
+          const double o0 = __dadd_rn(__dmul_rn(acc0[mt][nt][0], wa), __dmul_rn(acc1[mt][nt][0], wb));   // :205
+          const double o1 = __dadd_rn(__dmul_rn(acc0[mt][nt][1], wa), __dmul_rn(acc1[mt][nt][1], wb));
+          if (8 * nt + 2 * t < r1p) *reinterpret_cast<double2 *>(dst + 8 * nt) = make_double2(o0, o1);   // zeros up to the next multiple of 4
         }
       }
     }
   }
+}
+
+template <int NTU>
+static cudaError_t upd_launch(const UpdArgs &a, int grid, cudaStream_t st) {
+  static bool attr_done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !attr_done[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(sqr_update_kernel<NTU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_done[dev] = true;
+  }
+  const int P = ((a.r0 + 7) & ~7) + 4;
+  const size_t sm = sizeof(double) * ((size_t)2 * 8 * NTU * P + (size_t)2 * UPD_TS * P);
+  sqr_update_kernel<NTU><<<grid, UPD_THREADS, sm, st>>>(a);
+  return cudaGetLastError();
 }
 
 __global__ void sqr_fill_nan_kernel(double *p, int64_t n) {
@@ -564,6 +713,23 @@ __global__ void sqr_fill_nan_kernel(double *p, int64_t n) {
 }
 
 }  // namespace
+
+namespace ttirt {
+// called by ttirt_cache_clear() (ttirt_engine.cu)
+void sqr_pool_clear() {
+  int keep = 0;
+  cudaGetDevice(&keep);
+  for (int g = 0; g < 64; g++) {
+    DevPool &pl = g_pool[g];
+    std::lock_guard<std::mutex> lock(pl.mu);
+    if (pl.idle.empty()) continue;
+    cudaSetDevice(g);
+    for (auto &kv : pl.idle) cudaFree(kv.second);
+    pl.idle.clear();
+  }
+  cudaSetDevice(keep);
+}
+}  // namespace ttirt
 
 // ------------------------------------------------------------------------------------------------
 // model
@@ -581,9 +747,11 @@ struct ttirt_sqr_model {
   bool host = false;
   double *F0 = nullptr, *F1 = nullptr, *pdf = nullptr, *cdf = nullptr, *w1 = nullptr, *w2 = nullptr;
   int *idx = nullptr, *perm = nullptr, *hist = nullptr, *bin_start = nullptr, *bin_tile_start = nullptr, *cursor = nullptr;
-  double *q = nullptr, *z = nullptr, *lf = nullptr;
-  int32_t *idx_out = nullptr;
-  cudaStream_t stream = nullptr;
+  // host-buffer mode: two staging slots so that the copies of one chunk overlap the kernels of its neighbours
+  double *q[2] = {nullptr, nullptr}, *z[2] = {nullptr, nullptr}, *lf[2] = {nullptr, nullptr};
+  int32_t *idx_out[2] = {nullptr, nullptr};
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   bool profile = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
   size_t prof_used = 0;
@@ -591,12 +759,14 @@ struct ttirt_sqr_model {
 };
 
 static void sqr_ws_free(ttirt_sqr_model *md) {
-  cudaFree(md->F0); cudaFree(md->F1); cudaFree(md->pdf); cudaFree(md->cdf); cudaFree(md->w1); cudaFree(md->w2);
-  cudaFree(md->idx); cudaFree(md->perm); cudaFree(md->hist); cudaFree(md->bin_start); cudaFree(md->bin_tile_start); cudaFree(md->cursor);
-  cudaFree(md->q); cudaFree(md->z); cudaFree(md->lf); cudaFree(md->idx_out);
-  md->F0 = md->F1 = md->pdf = md->cdf = md->w1 = md->w2 = md->q = md->z = md->lf = nullptr;
+  sqr_free(md->F0); sqr_free(md->F1); sqr_free(md->pdf); sqr_free(md->cdf); sqr_free(md->w1); sqr_free(md->w2);
+  sqr_free(md->idx); sqr_free(md->perm); sqr_free(md->hist); sqr_free(md->bin_start); sqr_free(md->bin_tile_start); sqr_free(md->cursor);
+  for (int s = 0; s < 2; s++) {
+    sqr_free(md->q[s]); sqr_free(md->z[s]); sqr_free(md->lf[s]); sqr_free(md->idx_out[s]);
+    md->q[s] = md->z[s] = md->lf[s] = nullptr; md->idx_out[s] = nullptr;
+  }
+  md->F0 = md->F1 = md->pdf = md->cdf = md->w1 = md->w2 = nullptr;
   md->idx = md->perm = md->hist = md->bin_start = md->bin_tile_start = md->cursor = nullptr;
-  md->idx_out = nullptr;
   md->cap = 0; md->host = false;
 }
 
@@ -608,25 +778,27 @@ static int sqr_ws_ensure(ttirt_sqr_model *md, int64_t rows, bool host) {
   md->cap = cap; md->host = h;
   const int64_t d = md->d;
   const size_t fbytes = sizeof(double) * (size_t)cap * md->ldf;
-  CKS(cudaMalloc(&md->F0, fbytes));
-  CKS(cudaMalloc(&md->F1, fbytes));
+  CKS(sqr_alloc(&md->F0, fbytes));
+  CKS(sqr_alloc(&md->F1, fbytes));
   CKS(cudaMemset(md->F0, 0, fbytes));
   CKS(cudaMemset(md->F1, 0, fbytes));
-  CKS(cudaMalloc(&md->pdf, sizeof(double) * (size_t)cap * md->nmax));
-  CKS(cudaMalloc(&md->cdf, sizeof(double) * (size_t)cap * md->nmax));
-  CKS(cudaMalloc(&md->w1, sizeof(double) * cap));
-  CKS(cudaMalloc(&md->w2, sizeof(double) * cap));
-  CKS(cudaMalloc(&md->idx, sizeof(int) * cap));
-  CKS(cudaMalloc(&md->perm, sizeof(int) * cap));
-  CKS(cudaMalloc(&md->hist, sizeof(int) * d * md->nbpad));
-  CKS(cudaMalloc(&md->bin_start, sizeof(int) * (md->nbpad + 1)));
-  CKS(cudaMalloc(&md->bin_tile_start, sizeof(int) * (md->nbpad + 1)));
-  CKS(cudaMalloc(&md->cursor, sizeof(int) * (md->nbpad + 1)));
+  CKS(sqr_alloc(&md->pdf, sizeof(double) * (size_t)cap * md->nmax));
+  CKS(sqr_alloc(&md->cdf, sizeof(double) * (size_t)cap * md->nmax));
+  CKS(sqr_alloc(&md->w1, sizeof(double) * cap));
+  CKS(sqr_alloc(&md->w2, sizeof(double) * cap));
+  CKS(sqr_alloc(&md->idx, sizeof(int) * cap));
+  CKS(sqr_alloc(&md->perm, sizeof(int) * cap));
+  CKS(sqr_alloc(&md->hist, sizeof(int) * d * md->nbpad));
+  CKS(sqr_alloc(&md->bin_start, sizeof(int) * (md->nbpad + 1)));
+  CKS(sqr_alloc(&md->bin_tile_start, sizeof(int) * (md->nbpad + 1)));
+  CKS(sqr_alloc(&md->cursor, sizeof(int) * (md->nbpad + 1)));
   if (h) {
-    CKS(cudaMalloc(&md->q, sizeof(double) * cap * d));
-    CKS(cudaMalloc(&md->z, sizeof(double) * cap * d));
-    CKS(cudaMalloc(&md->lf, sizeof(double) * cap));
-    CKS(cudaMalloc(&md->idx_out, sizeof(int32_t) * cap * d));
+    for (int s = 0; s < 2; s++) {
+      CKS(sqr_alloc(&md->q[s], sizeof(double) * cap * d));
+      CKS(sqr_alloc(&md->z[s], sizeof(double) * cap * d));
+      CKS(sqr_alloc(&md->lf[s], sizeof(double) * cap));
+      CKS(sqr_alloc(&md->idx_out[s], sizeof(int32_t) * cap * d));
+    }
   }
   return 0;
 }
@@ -636,26 +808,32 @@ extern "C" void ttirt_sqr_model_destroy(ttirt_sqr_model *md) {
   cudaSetDevice(md->device);
   cudaDeviceSynchronize();
   sqr_ws_free(md);
-  cudaFree(md->d_xs); cudaFree(md->d_h); cudaFree(md->d_hc); cudaFree(md->d_core); cudaFree(md->d_gp); cudaFree(md->d_rfac);
+  sqr_free(md->d_xs); sqr_free(md->d_h); sqr_free(md->d_hc); sqr_free(md->d_core); sqr_free(md->d_gp); sqr_free(md->d_rfac);
   if (md->stream) cudaStreamDestroy(md->stream);
+  if (md->copy_stream) cudaStreamDestroy(md->copy_stream);
+  for (int s = 0; s < 2; s++) {
+    if (md->ev_in[s]) cudaEventDestroy(md->ev_in[s]);
+    if (md->ev_done[s]) cudaEventDestroy(md->ev_done[s]);
+    if (md->ev_out[s]) cudaEventDestroy(md->ev_out[s]);
+  }
   for (auto &p : md->prof_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   delete md;
 }
 
-template <int NT>
+template <int NT, bool TAIL1>
 static cudaError_t pdf_launch(const PdfArgs &a, int sm_count, cudaStream_t st) {
   static bool attr_done[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   const size_t bytes = pdf_smem_bytes(a.ldf, a.pb);
   if (dev < 64 && !attr_done[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(sqr_pdf_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(sqr_pdf_kernel<NT, TAIL1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     attr_done[dev] = true;
   }
   const int ntiles = (a.rows + PDF_ROWS - 1) / PDF_ROWS;
   const int grid = ntiles < sm_count ? ntiles : sm_count;
-  sqr_pdf_kernel<NT><<<grid, 32 * (PDF_WARPS + 1), bytes, st>>>(a);
+  sqr_pdf_kernel<NT, TAIL1><<<grid, 32 * (PDF_WARPS + 1), bytes, st>>>(a);
   return cudaGetLastError();
 }
 
@@ -715,33 +893,42 @@ static int sqr_model_build(ttirt_sqr_model *md, const int64_t *n, int64_t nxs, c
   if (prop.major < 10) return aux_fail("tt_irt_sqr: device %d (%s, sm_%d%d) is not a Blackwell B200-class GPU", md->device, prop.name, prop.major, prop.minor);
   md->sm_count = prop.multiProcessorCount;
   CKS(cudaStreamCreateWithFlags(&md->stream, cudaStreamNonBlocking));
+  CKS(cudaStreamCreateWithFlags(&md->copy_stream, cudaStreamNonBlocking));
+  for (int s = 0; s < 2; s++) {
+    CKS(cudaEventCreateWithFlags(&md->ev_in[s], cudaEventDisableTiming));
+    CKS(cudaEventCreateWithFlags(&md->ev_done[s], cudaEventDisableTiming));
+    CKS(cudaEventCreateWithFlags(&md->ev_out[s], cudaEventDisableTiming));
+  }
 
-  CKS(cudaMalloc(&md->d_xs, sizeof(double) * ox));
-  CKS(cudaMalloc(&md->d_h, sizeof(double) * ox));
-  CKS(cudaMalloc(&md->d_hc, sizeof(double) * ox));
-  CKS(cudaMalloc(&md->d_core, sizeof(double) * oc));
-  CKS(cudaMalloc(&md->d_gp, sizeof(double) * og));
-  CKS(cudaMalloc(&md->d_rfac, sizeof(double) * orr));
+  CKS(sqr_alloc(&md->d_xs, sizeof(double) * ox));
+  CKS(sqr_alloc(&md->d_h, sizeof(double) * ox));
+  CKS(sqr_alloc(&md->d_hc, sizeof(double) * ox));
+  CKS(sqr_alloc(&md->d_core, sizeof(double) * oc));
+  CKS(sqr_alloc(&md->d_gp, sizeof(double) * og));
+  CKS(sqr_alloc(&md->d_rfac, sizeof(double) * orr));
   CKS(cudaMemset(md->d_gp, 0, sizeof(double) * og));
   CKS(cudaMemset(md->d_rfac, 0, sizeof(double) * orr));
   CKS(cudaMemcpy(md->d_xs, xs, sizeof(double) * ox, cudaMemcpyHostToDevice));
 
-  double *d_cin = nullptr, *d_pm = nullptr, *d_a = nullptr, *d_one = nullptr;
+  double *d_cin = nullptr, *d_pm = nullptr, *d_a = nullptr, *d_one = nullptr, *d_stack[2] = {nullptr, nullptr};
   int64_t mmax = 0;
   for (int64_t k = 0; k < d; k++) mmax = std::max(mmax, (int64_t)md->dims[k].n * md->dims[k].s1 * md->dims[k].r0);
-  auto cleanup = [&]() { if (md->extended) cudaFree(d_cin); cudaFree(d_pm); cudaFree(d_a); cudaFree(d_one); };
+  auto cleanup = [&]() { if (md->extended) sqr_free(d_cin); sqr_free(d_pm); sqr_free(d_a); sqr_free(d_one); sqr_free(d_stack[0]); sqr_free(d_stack[1]); };
 #define CKB(call)                                                                                   \
   do {                                                                                              \
     cudaError_t e_ = (call);                                                                        \
     if (e_ != cudaSuccess) { cleanup(); return aux_fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } \
   } while (0)
-  CKB(cudaMalloc(&d_pm, sizeof(double) * mmax));
-  CKB(cudaMalloc(&d_a, sizeof(double) * mmax));
-  CKB(cudaMalloc(&d_one, sizeof(double)));
+  CKB(sqr_alloc(&d_pm, sizeof(double) * mmax));
+  CKB(sqr_alloc(&d_a, sizeof(double) * mmax));
+  CKB(sqr_alloc(&d_one, sizeof(double)));
+  CKB(sqr_alloc(&d_stack[0], sizeof(double) * std::max<int64_t>(mmax, 1)));
+  CKB(sqr_alloc(&d_stack[1], sizeof(double) * std::max<int64_t>(mmax, 1)));
+  CKB(cudaFuncSetAttribute(sqr_qr_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
   const double one = 1.0;
   CKB(cudaMemcpy(d_one, &one, sizeof(double), cudaMemcpyHostToDevice));
   if (md->extended) {
-    CKB(cudaMalloc(&d_cin, sizeof(double) * oci));
+    CKB(sqr_alloc(&d_cin, sizeof(double) * oci));
     CKB(cudaMemcpy(d_cin, core, sizeof(double) * oci, cudaMemcpyHostToDevice));
   } else {
     CKB(cudaMemcpy(md->d_core, core, sizeof(double) * oc, cudaMemcpyHostToDevice));
@@ -763,8 +950,27 @@ static int sqr_model_build(ttirt_sqr_model *md, const int64_t *n, int64_t nxs, c
     if (k > 0) {
       sqr_weight_kernel<<<(unsigned)((tot + 255) / 256), 256>>>(d_pm, md->d_h + di.off_x, d_a, di.n, (int)m, di.r0);
       LAUNCHED();
-      sqr_qr_kernel<<<1, 1024>>>(d_a, (int)m, di.r0, md->d_rfac + di.off_r, di.s0);
-      LAUNCHED();
+      // TSQR levels: row blocks that fit shared memory, stacked R factors ping-pong between d_a's tail and d_pm's
+      {
+        const int r = di.r0;
+        int rb = (int)std::min<int64_t>(m, (int64_t)(200 * 1024) / (8 * r));
+        if (rb < 2 * r && m > rb) { cleanup(); return aux_fail("tt_irt_sqr: rank %d too large for the shared-memory QR", r); }
+        const double *src = d_a;
+        int msrc = (int)m, lda = (int)m, level = 0;
+        for (;;) {
+          const int nblk = (msrc + rb - 1) / rb;
+          const size_t smb = sizeof(double) * (size_t)std::min(rb, msrc) * r;
+          if (nblk == 1) {
+            sqr_qr_block_kernel<<<1, 1024, smb>>>(src, msrc, lda, r, rb, md->d_rfac + di.off_r, 0, 1, di.s0);
+            LAUNCHED();
+            break;
+          }
+          double *dst = d_stack[level & 1];
+          sqr_qr_block_kernel<<<nblk, 1024, smb>>>(src, msrc, lda, r, rb, dst, nblk * r, 0, 0);
+          LAUNCHED();
+          src = dst; msrc = nblk * r; lda = nblk * r; level++;
+        }
+      }
     }
     const int64_t ge = (int64_t)di.ksteps * 4 * di.n;
     sqr_gram_pack_kernel<<<(unsigned)((ge + 127) / 128), 128>>>(d_pm, di.n, di.s1, di.r0, md->d_gp + di.off_g, md->pb, di.ksteps);
@@ -863,7 +1069,12 @@ static int sqr_enqueue_chunk(ttirt_sqr_model *md, int64_t rows, int64_t D, const
       md->prof_flops += (double)rows * ((double)di.r0 * (di.r0 + 1) * di.n + 0.5 * di.r0 * (di.r0 + 1));
       CKS(cudaEventRecord(e0, st));
     }
-    cudaError_t pe = md->nt == 3 ? pdf_launch<3>(pa, md->sm_count, st) : (md->nt == 5 ? pdf_launch<5>(pa, md->sm_count, st) : pdf_launch<9>(pa, md->sm_count, st));
+    // the dimension's own grid size picks the variant inside the model's class (pb is the class's pitch)
+    cudaError_t pe;
+    const bool t1 = (di.n == 8 * (md->nt - 1) + 1);
+    if (md->nt == 3) pe = t1 ? pdf_launch<2, true>(pa, md->sm_count, st) : pdf_launch<3, false>(pa, md->sm_count, st);
+    else if (md->nt == 5) pe = t1 ? pdf_launch<4, true>(pa, md->sm_count, st) : pdf_launch<5, false>(pa, md->sm_count, st);
+    else pe = t1 ? pdf_launch<8, true>(pa, md->sm_count, st) : pdf_launch<9, false>(pa, md->sm_count, st);
     CKS(pe);
     LAUNCHED();
     if (e1) CKS(cudaEventRecord(e1, st));
@@ -887,18 +1098,15 @@ static int sqr_enqueue_chunk(ttirt_sqr_model *md, int64_t rows, int64_t D, const
       ua.Fin = Fin; ua.Fout = Fout; ua.ldf = md->ldf;
       ua.perm = md->perm; ua.bin_start = md->bin_start; ua.bin_tile_start = md->bin_tile_start; ua.nb = nb;
       ua.w1 = md->w1; ua.w2 = md->w2;
-      const int r1p = (di.r1 + 3) & ~3;
-      const size_t sm = sizeof(double) * ((size_t)2 * di.r0 * (r1p + 2) + (size_t)di.r0 * (UPD_TS + 2));
-      static bool attr_done[64] = {};
-      if (md->device < 64 && !attr_done[md->device]) {
-        CKS(cudaFuncSetAttribute(sqr_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_done[md->device] = true;
-      }
       const int64_t max_tiles = (rows + UPD_TS - 1) / UPD_TS + nb;
       const int grid = (int)std::min<int64_t>(max_tiles, 2 * md->sm_count);
-      sqr_update_kernel<<<grid, UPD_THREADS, sm, st>>>(ua);
+      cudaError_t ue;
+      if (di.r1 <= 8) ue = upd_launch<1>(ua, grid, st);
+      else if (di.r1 <= 16) ue = upd_launch<2>(ua, grid, st);
+      else if (di.r1 <= 32) ue = upd_launch<4>(ua, grid, st);
+      else ue = upd_launch<8>(ua, grid, st);
+      CKS(ue);
       LAUNCHED();
-      CKS(cudaGetLastError());
       std::swap(Fin, Fout);
     }
   }
@@ -941,27 +1149,54 @@ extern "C" int ttirt_sqr_sample_host(ttirt_sqr_model *md, int64_t M, int64_t D, 
   CKS(cudaSetDevice(md->device));
   const int64_t chunk = std::min<int64_t>(M, sqr_chunk());
   if (sqr_ws_ensure(md, chunk, true) != 0) return -1;
-  cudaStream_t st = md->stream;
+  cudaStream_t st = md->stream, cs = md->copy_stream;
   const int64_t cap = md->cap;
-  for (int64_t m0 = 0; m0 < M; m0 += chunk) {
-    const int64_t rows = std::min(chunk, M - m0);
-    CKS(cudaMemcpy2DAsync(md->q, sizeof(double) * cap, h_q + m0, sizeof(double) * ld, sizeof(double) * rows, (size_t)D, cudaMemcpyHostToDevice, st));
-    if (sqr_enqueue_chunk(md, rows, D, md->q, cap, md->z, cap, md->lf, h_idx ? md->idx_out : nullptr, st) != 0) return -1;
-    CKS(cudaMemcpy2DAsync(h_z + m0, sizeof(double) * ld, md->z, sizeof(double) * cap, sizeof(double) * rows, (size_t)D, cudaMemcpyDeviceToHost, st));
-    CKS(cudaMemcpyAsync(h_lf + m0, md->lf, sizeof(double) * rows, cudaMemcpyDeviceToHost, st));
+  // chunk i: copy in (copy stream) -> kernels (compute stream) -> copy out (copy stream, issued after chunk i + 1 has been
+  // enqueued, so that a host-blocking copy of pageable memory never leaves the compute stream empty)
+  auto copy_out = [&](int64_t j) -> int {
+    const int s = (int)(j & 1);
+    const int64_t m0 = j * chunk, rows = std::min(chunk, M - m0);
+    CKS(cudaStreamWaitEvent(cs, md->ev_done[s], 0));
+    CKS(cudaMemcpy2DAsync(h_z + m0, sizeof(double) * ld, md->z[s], sizeof(double) * cap, sizeof(double) * rows, (size_t)D, cudaMemcpyDeviceToHost, cs));
+    CKS(cudaMemcpyAsync(h_lf + m0, md->lf[s], sizeof(double) * rows, cudaMemcpyDeviceToHost, cs));
     if (h_idx)
-      CKS(cudaMemcpy2DAsync(h_idx + m0, sizeof(int32_t) * ld, md->idx_out, sizeof(int32_t) * cap, sizeof(int32_t) * rows, (size_t)D, cudaMemcpyDeviceToHost, st));
-    CKS(cudaStreamSynchronize(st));
+      CKS(cudaMemcpy2DAsync(h_idx + m0, sizeof(int32_t) * ld, md->idx_out[s], sizeof(int32_t) * cap, sizeof(int32_t) * rows, (size_t)D, cudaMemcpyDeviceToHost, cs));
+    CKS(cudaEventRecord(md->ev_out[s], cs));
+    return 0;
+  };
+  const int64_t nchunks = (M + chunk - 1) / chunk;
+  for (int64_t i = 0; i < nchunks; i++) {
+    const int s = (int)(i & 1);
+    const int64_t m0 = i * chunk, rows = std::min(chunk, M - m0);
+    CKS(cudaMemcpy2DAsync(md->q[s], sizeof(double) * cap, h_q + m0, sizeof(double) * ld, sizeof(double) * rows, (size_t)D, cudaMemcpyHostToDevice, cs));
+    CKS(cudaEventRecord(md->ev_in[s], cs));
+    CKS(cudaStreamWaitEvent(st, md->ev_in[s], 0));
+    if (i >= 2) CKS(cudaStreamWaitEvent(st, md->ev_out[s], 0));
+    if (sqr_enqueue_chunk(md, rows, D, md->q[s], cap, md->z[s], cap, md->lf[s], h_idx ? md->idx_out[s] : nullptr, st) != 0) return -1;
+    CKS(cudaEventRecord(md->ev_done[s], st));
+    if (i >= 1 && copy_out(i - 1) != 0) return -1;
   }
+  if (copy_out(nchunks - 1) != 0) return -1;
+  CKS(cudaStreamSynchronize(cs));
+  CKS(cudaStreamSynchronize(st));
   return 0;
 }
 
 extern "C" int ttirt_sqr_run_host(int64_t d, const int64_t *n, int64_t nxs, const double *xs, const int64_t *ttrank, const double *ttcore,
                                   int64_t M, int64_t D, const double *h_q, double *h_z, double *h_lf, int device) {
+  const bool trace = getenv("TTIRT_TRACE") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
   ttirt_sqr_model *md = ttirt_sqr_model_create(d, n, nxs, xs, ttrank, ttcore, device);
   if (!md) return -1;
+  const auto t1 = std::chrono::steady_clock::now();
   const int rc = ttirt_sqr_sample_host(md, M, D, h_q, h_z, h_lf, nullptr, M);
+  const auto t2 = std::chrono::steady_clock::now();
   ttirt_sqr_model_destroy(md);
+  if (trace) {
+    const auto t3 = std::chrono::steady_clock::now();
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    fprintf(stderr, "tt_irt_sqr[b200]: model %.2f ms, sample %.2f ms, release %.2f ms\n", ms(t0, t1), ms(t1, t2), ms(t2, t3));
+  }
   return rc;
 }
 
