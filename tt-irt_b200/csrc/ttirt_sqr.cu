@@ -409,9 +409,24 @@ __global__ void __launch_bounds__(32 * (PDF_WARPS + 1), 1) sqr_pdf_kernel(PdfArg
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int m0 = tile * PDF_ROWS + warp * PDF_WROWS;
     __syncwarp();
-    for (int row = 0; row < PDF_WROWS; row++) {
-      const int gm = m0 + row;
-      for (int col = lane; col < 4 * nchunk; col += 32) fw[row * ldf + col] = gm < a.rows ? a.F[(size_t)gm * ldf + col] : 0.0;
+    {
+      // the warp's 16 rows are one contiguous block (same pitch in global and shared memory): all loads in flight before
+      // the first store, 16 bytes per lane and instruction; rows past the end of the chunk are zero
+      const int nvec = ldf >> 2;                                   // double2 per lane: 16 ldf / (2 * 32)
+      const int live = a.rows - m0 < PDF_WROWS ? (a.rows - m0 > 0 ? a.rows - m0 : 0) : PDF_WROWS;
+      const int valid = live * (ldf >> 1);                         // double2 holding real rows
+      const double2 *src = reinterpret_cast<const double2 *>(a.F + (size_t)m0 * ldf);
+      double2 *dst = reinterpret_cast<double2 *>(fw);
+      double2 v[17];
+#pragma unroll
+      for (int j = 0; j < 17; j++) {
+        const int e = lane + 32 * j;
+        v[j] = make_double2(0.0, 0.0);
+        if (j < nvec && e < valid) v[j] = src[e];
+      }
+#pragma unroll
+      for (int j = 0; j < 17; j++)
+        if (j < nvec) dst[lane + 32 * j] = v[j];
     }
     __syncwarp();
     double acc[PDF_MT][NT][2];
@@ -429,13 +444,11 @@ __global__ void __launch_bounds__(32 * (PDF_WARPS + 1), 1) sqr_pdf_kernel(PdfArg
 #pragma unroll
       for (int mt = 0; mt < PDF_MT; mt++) fb[mt] = fw[(mt * 8 + g) * ldf + 4 * c + t];
       const int amax = (4 * c + 4 < a.r0) ? 4 * c + 4 : a.r0;
-      for (int aa = 0; aa < amax; aa++) {
-        const int kk = ks & (PDF_KS - 1);
-        if (kk == 0) mbar_wait(full + stage, parity);
+      // one k-step: A = f[a] * f[4c + t] in registers, B fragments from the staged slice
+      auto kstep = [&](const double (&fa)[PDF_MT], const double *bp) {
         double av[PDF_MT];
 #pragma unroll
-        for (int mt = 0; mt < PDF_MT; mt++) av[mt] = __dmul_rn(fw[(mt * 8 + g) * ldf + aa], fb[mt]);
-        const double *bp = Bs + (size_t)stage * SB + (kk * 4 + t) * a.pb + g;
+        for (int mt = 0; mt < PDF_MT; mt++) av[mt] = __dmul_rn(fa[mt], fb[mt]);
 #pragma unroll
         for (int nt = 0; nt < NT; nt++) {
           const double b = bp[nt * 8];
@@ -447,13 +460,47 @@ __global__ void __launch_bounds__(32 * (PDF_WARPS + 1), 1) sqr_pdf_kernel(PdfArg
 #pragma unroll
           for (int mt = 0; mt < PDF_MT; mt++) tl[mt] = fma(av[mt], bl, tl[mt]);
         }
-        ks++;
-        if ((ks & (PDF_KS - 1)) == 0 || ks == a.ksteps) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(empty + stage);
-          it++;
-          stage = it % PDF_STAGES; parity = (it / PDF_STAGES) & 1;
+      };
+      auto release = [&]() {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + stage);
+        it++;
+        stage = it % PDF_STAGES; parity = (it / PDF_STAGES) & 1;
+      };
+      int aa = 0;
+      // groups of four k-steps (every full column block has a multiple of four, slices hold sixteen): one barrier check and
+      // two 32-byte interface loads per group, and the four steps unrolled so that the loads of one run under the MMAs of
+      // the previous
+      for (; aa + 4 <= amax; aa += 4) {
+        const int kk = ks & (PDF_KS - 1);
+        if (kk == 0) mbar_wait(full + stage, parity);
+        double f4[PDF_MT][4];
+#pragma unroll
+        for (int mt = 0; mt < PDF_MT; mt++) {
+          const double2 lo = *reinterpret_cast<const double2 *>(fw + (mt * 8 + g) * ldf + aa);
+          const double2 hi = *reinterpret_cast<const double2 *>(fw + (mt * 8 + g) * ldf + aa + 2);
+          f4[mt][0] = lo.x; f4[mt][1] = lo.y; f4[mt][2] = hi.x; f4[mt][3] = hi.y;
         }
+        const double *bp0 = Bs + (size_t)stage * SB + (kk * 4 + t) * a.pb + g;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          double fa[PDF_MT];
+#pragma unroll
+          for (int mt = 0; mt < PDF_MT; mt++) fa[mt] = f4[mt][u];
+          kstep(fa, bp0 + u * 4 * a.pb);
+        }
+        ks += 4;
+        if ((ks & (PDF_KS - 1)) == 0 || ks == a.ksteps) release();
+      }
+      for (; aa < amax; aa++) {       // a rank that is not a multiple of four: the last column block's remainder
+        const int kk = ks & (PDF_KS - 1);
+        if (kk == 0) mbar_wait(full + stage, parity);
+        double fa[PDF_MT];
+#pragma unroll
+        for (int mt = 0; mt < PDF_MT; mt++) fa[mt] = fw[(mt * 8 + g) * ldf + aa];
+        kstep(fa, Bs + (size_t)stage * SB + (kk * 4 + t) * a.pb + g);
+        ks++;
+        if ((ks & (PDF_KS - 1)) == 0 || ks == a.ksteps) release();
       }
     }
 #pragma unroll
@@ -636,25 +683,28 @@ __global__ void __launch_bounds__(UPD_THREADS) sqr_update_kernel(UpdArgs a) {
     const int start = a.bin_start[bin] + (tile - a.bin_tile_start[bin]) * UPD_TS;
     const int cnt = min(UPD_TS, a.bin_start[bin + 1] - start);
     __syncwarp();                         // this warp's reads of the other buffer (previous tile) are done
-    if (tile + 1 < t_end) gather(tile + 1, buf ^ 1);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    if (bin != staged) {
+    const bool restage = bin != staged;
+    if (restage) {
       __syncthreads();                    // every warp is done with the previous interval's slabs
+      // the two slabs of the interval, 8-byte cp.async per element (core columns are r0 contiguous doubles, any parity)
       const int64_t cs = (int64_t)a.r0 * a.n;
       for (int e = tid; e < 8 * NTU * r0p; e += UPD_THREADS) {
         const int aa = e % r0p, l = e / r0p;
-        double v0 = 0.0, v1 = 0.0;
         if (l < a.r1 && aa < a.r0) {
-          v0 = __ldg(a.core + aa + (int64_t)a.r0 * bin + cs * l);
-          v1 = __ldg(a.core + aa + (int64_t)a.r0 * (bin + 1) + cs * l);
+          const double *src = a.core + aa + (int64_t)a.r0 * bin + cs * l;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(S0 + l * P + aa)), "l"(src) : "memory");
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(S1 + l * P + aa)), "l"(src + a.r0) : "memory");
+        } else {
+          S0[l * P + aa] = 0.0; S1[l * P + aa] = 0.0;
         }
-        S0[l * P + aa] = v0; S1[l * P + aa] = v1;
       }
       staged = bin;
-      __syncthreads();
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (tile + 1 < t_end) gather(tile + 1, buf ^ 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 1;" ::: "memory");   // all but the newest group (the next tile's rows) have landed
-    __syncwarp();
+    if (restage) __syncthreads(); else __syncwarp();
     const double *fw = Fs + ((size_t)buf * UPD_TS + warp * 16) * P;
     double acc0[2][NTU][2], acc1[2][NTU][2];
 #pragma unroll
@@ -692,7 +742,7 @@ __global__ void __launch_bounds__(UPD_THREADS) sqr_update_kernel(UpdArgs a) {
 }
 
 template <int NTU>
-static cudaError_t upd_launch(const UpdArgs &a, int grid, cudaStream_t st) {
+static cudaError_t upd_launch(const UpdArgs &a, int64_t max_tiles, int sm_count, cudaStream_t st) {
   static bool attr_done[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -703,6 +753,11 @@ static cudaError_t upd_launch(const UpdArgs &a, int grid, cudaStream_t st) {
   }
   const int P = ((a.r0 + 7) & ~7) + 4;
   const size_t sm = sizeof(double) * ((size_t)2 * 8 * NTU * P + (size_t)2 * UPD_TS * P);
+  // one wave of CTAs, each walking a contiguous range of tiles (slabs are restaged only when the interval changes):
+  // as many CTAs per SM as the shared memory allows, at most four
+  int per_sm = (int)((size_t)(227 * 1024) / (sm + 1024));
+  per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+  const int grid = (int)std::min<int64_t>(max_tiles, (int64_t)per_sm * sm_count);
   sqr_update_kernel<NTU><<<grid, UPD_THREADS, sm, st>>>(a);
   return cudaGetLastError();
 }
@@ -1099,12 +1154,11 @@ static int sqr_enqueue_chunk(ttirt_sqr_model *md, int64_t rows, int64_t D, const
       ua.perm = md->perm; ua.bin_start = md->bin_start; ua.bin_tile_start = md->bin_tile_start; ua.nb = nb;
       ua.w1 = md->w1; ua.w2 = md->w2;
       const int64_t max_tiles = (rows + UPD_TS - 1) / UPD_TS + nb;
-      const int grid = (int)std::min<int64_t>(max_tiles, 2 * md->sm_count);
       cudaError_t ue;
-      if (di.r1 <= 8) ue = upd_launch<1>(ua, grid, st);
-      else if (di.r1 <= 16) ue = upd_launch<2>(ua, grid, st);
-      else if (di.r1 <= 32) ue = upd_launch<4>(ua, grid, st);
-      else ue = upd_launch<8>(ua, grid, st);
+      if (di.r1 <= 8) ue = upd_launch<1>(ua, max_tiles, md->sm_count, st);
+      else if (di.r1 <= 16) ue = upd_launch<2>(ua, max_tiles, md->sm_count, st);
+      else if (di.r1 <= 32) ue = upd_launch<4>(ua, max_tiles, md->sm_count, st);
+      else ue = upd_launch<8>(ua, max_tiles, md->sm_count, st);
       CKS(ue);
       LAUNCHED();
       std::swap(Fin, Fout);
