@@ -41,6 +41,8 @@ extern "C" {
  *
  * The reference's `keyboard` debugger stops (:17-19, :151-154) have no counterpart: seeds outside [0, 1] are not
  * checked.  On any failure one line goes to stderr and z / lFapp are NaN-filled; the host process is never aborted.
+ * Environment: TTIRT_DEVICE=<first ordinal> (default 0), TTIRT_DEVICES=<count>|all (default 1: rows sharded over that many
+ * GPUs), TTIRT_SQR_CHUNK=<samples per chunk> (default 262144), TTIRT_CACHE=0 (no pooling of device blocks), TTIRT_TRACE=1.
  */
 TTIRT_API void tt_irt_sqr(TTIRT_INT d, TTIRT_INT *n, TTIRT_INT nxs, double *xs, TTIRT_INT *ttrank, double *ttcore,
                           TTIRT_INT M, TTIRT_INT D, double *q, double *z, double *lFapp);
@@ -69,10 +71,12 @@ TTIRT_API int ttirt_sqr_sample_device(ttirt_sqr_model *model, int64_t M, int64_t
 /* The same on host buffers (leading dimension ld >= M): chunked copy in, kernels, copy out.  Blocks.  0 on success. */
 TTIRT_API int ttirt_sqr_sample_host(ttirt_sqr_model *model, int64_t M, int64_t D, const double *h_q, double *h_z,
                                     double *h_lf, int32_t *h_idx, int64_t ld);
-/* Whole call on host buffers (model create, sample, destroy): what tt_irt_sqr() runs. */
+/* Whole call on host buffers (model create, sample, release): what tt_irt_sqr() runs.  The M rows are cut into contiguous
+ * ranges over n_devices devices starting at first_device (cores replicated, sweep redone per device, one host thread per
+ * device, no collective).  0 on success. */
 TTIRT_API int ttirt_sqr_run_host(int64_t d, const int64_t *n, int64_t nxs, const double *xs, const int64_t *ttrank,
                                  const double *ttcore, int64_t M, int64_t D, const double *h_q, double *h_z, double *h_lf,
-                                 int device);
+                                 int first_device, int n_devices);
 
 /* Per-launch CUDA-event timing of the dominant kernel (the conditional-pdf contraction, sqr_pdf_kernel):
  * enable(1) clears and starts; read() synchronises and returns summed kernel time, launches and their algorithmic flops

@@ -178,3 +178,19 @@ def test_failures_are_loud():
             md.sample(synth.make_q(16, 4, seed=2))                                   # more seed columns than dimensions
     finally:
         md.close()
+
+
+def test_device_sharding_does_not_change_a_bit():
+    """ttirt_sqr_run_host over 2 devices (contiguous row ranges, cores replicated) against one device."""
+    if tt_irt.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    ns, xs, rk, c = synth.make_tt(5, 17, 8, seed=4)
+    q = synth.make_q(40000, 5, seed=5)
+    Z1, l1 = _c_call(LIB32, np.int32, ctypes.c_int, ns, xs, rk, c, q)
+    os.environ["TTIRT_DEVICES"] = "2"
+    try:
+        Z2, l2 = _c_call(LIB32, np.int32, ctypes.c_int, ns, xs, rk, c, q)
+    finally:
+        del os.environ["TTIRT_DEVICES"]
+    np.testing.assert_array_equal(Z1, Z2)
+    np.testing.assert_array_equal(l1, l2)

@@ -73,7 +73,7 @@ void tt_irt1(TTIRT_INT d, TTIRT_INT *n, double *xs, TTIRT_INT *ttrank, double *t
 void tt_irt_sqr(TTIRT_INT d, TTIRT_INT *n, TTIRT_INT nxs, double *xs, TTIRT_INT *ttrank, double *ttcore, TTIRT_INT M,
                 TTIRT_INT D, double *q, double *z, double *lFapp) {
   int64_t *n64, *r64, k;
-  int first = 0, rc;
+  int first = 0, ndev = 1, rc;
   const char *e;
 
   if (d < 1 || M < 0 || D < 1 || D > d || !n || !xs || !ttrank || !ttcore || (M > 0 && (!q || !z || !lFapp))) {
@@ -93,7 +93,13 @@ void tt_irt_sqr(TTIRT_INT d, TTIRT_INT *n, TTIRT_INT nxs, double *xs, TTIRT_INT 
   for (k = 0; k < d; k++) n64[k] = (int64_t)n[k];
   for (k = 0; k <= d; k++) r64[k] = (int64_t)ttrank[k];
   if ((e = getenv("TTIRT_DEVICE")) != NULL) first = atoi(e);
-  rc = ttirt_sqr_run_host(d, n64, (int64_t)nxs, xs, r64, ttcore, M, D, q, z, lFapp, first);
+  if ((e = getenv("TTIRT_DEVICES")) != NULL) {
+    if (strcmp(e, "all") == 0) ndev = ttirt_device_count() - first;
+    else ndev = atoi(e);
+    if (ndev < 1) ndev = 1;
+  }
+  while (ndev > 1 && (int64_t)M / ndev < 128) ndev--;   /* never more devices than 128-sample tiles */
+  rc = ttirt_sqr_run_host(d, n64, (int64_t)nxs, xs, r64, ttcore, M, D, q, z, lFapp, first, ndev);
   if (rc != 0) {
     nan_fill(z, (int64_t)M * D);
     nan_fill(lFapp, M);

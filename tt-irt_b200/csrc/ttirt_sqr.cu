@@ -22,6 +22,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -1236,22 +1237,47 @@ extern "C" int ttirt_sqr_sample_host(ttirt_sqr_model *md, int64_t M, int64_t D, 
   return 0;
 }
 
-extern "C" int ttirt_sqr_run_host(int64_t d, const int64_t *n, int64_t nxs, const double *xs, const int64_t *ttrank, const double *ttcore,
-                                  int64_t M, int64_t D, const double *h_q, double *h_z, double *h_lf, int device) {
+// Whole call on host buffers.  Samples are independent (tt_irt_sqr.m:94-208 walks them in blocks), so the M rows are cut
+// into contiguous ranges, one per device; every device gets its own copy of the cores and redoes the (small) sweep; no
+// collective.  One host thread per device, joined before returning.
+static int sqr_run_rows(int device, int64_t d, const int64_t *n, int64_t nxs, const double *xs, const int64_t *ttrank,
+                        const double *ttcore, int64_t rows, int64_t D, const double *h_q, double *h_z, double *h_lf, int64_t ld) {
   const bool trace = getenv("TTIRT_TRACE") != nullptr;
   const auto t0 = std::chrono::steady_clock::now();
   ttirt_sqr_model *md = ttirt_sqr_model_create(d, n, nxs, xs, ttrank, ttcore, device);
   if (!md) return -1;
   const auto t1 = std::chrono::steady_clock::now();
-  const int rc = ttirt_sqr_sample_host(md, M, D, h_q, h_z, h_lf, nullptr, M);
+  const int rc = ttirt_sqr_sample_host(md, rows, D, h_q, h_z, h_lf, nullptr, ld);
   const auto t2 = std::chrono::steady_clock::now();
   ttirt_sqr_model_destroy(md);
   if (trace) {
     const auto t3 = std::chrono::steady_clock::now();
     auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-    fprintf(stderr, "tt_irt_sqr[b200]: model %.2f ms, sample %.2f ms, release %.2f ms\n", ms(t0, t1), ms(t1, t2), ms(t2, t3));
+    fprintf(stderr, "tt_irt_sqr[b200]: device %d rows %lld: model %.2f ms, sample %.2f ms, release %.2f ms\n", device, (long long)rows,
+            ms(t0, t1), ms(t1, t2), ms(t2, t3));
   }
   return rc;
+}
+
+extern "C" int ttirt_sqr_run_host(int64_t d, const int64_t *n, int64_t nxs, const double *xs, const int64_t *ttrank, const double *ttcore,
+                                  int64_t M, int64_t D, const double *h_q, double *h_z, double *h_lf, int first_device, int n_devices) {
+  if (M <= 0) return M == 0 ? 0 : aux_fail("negative M");
+  const int cnt = ttirt_device_count();
+  if (cnt <= 0) return aux_fail("no CUDA device available (this library has no CPU fallback)");
+  if (n_devices < 1) n_devices = 1;
+  if (first_device < 0 || first_device + n_devices > cnt) return aux_fail("devices %d..%d requested, %d visible", first_device, first_device + n_devices - 1, cnt);
+  if (n_devices == 1) return sqr_run_rows(first_device, d, n, nxs, xs, ttrank, ttcore, M, D, h_q, h_z, h_lf, M);
+  std::vector<std::thread> th;
+  std::vector<int> rc((size_t)n_devices, 0);
+  for (int g = 0; g < n_devices; g++) {
+    const int64_t m0 = M * g / n_devices, m1 = M * (g + 1) / n_devices;
+    th.emplace_back([=, &rc]() {
+      rc[(size_t)g] = m1 > m0 ? sqr_run_rows(first_device + g, d, n, nxs, xs, ttrank, ttcore, m1 - m0, D, h_q + m0, h_z + m0, h_lf + m0, M) : 0;
+    });
+  }
+  for (auto &t : th) t.join();
+  for (int g = 0; g < n_devices; g++) if (rc[(size_t)g] != 0) return -1;
+  return 0;
 }
 
 extern "C" void ttirt_sqr_profile_enable(ttirt_sqr_model *md, int on) {
