@@ -84,6 +84,18 @@ TTIRT_API int ttirt_sqr_run_host(int64_t d, const int64_t *n, int64_t nxs, const
 TTIRT_API void ttirt_sqr_profile_enable(ttirt_sqr_model *model, int on);
 TTIRT_API int ttirt_sqr_profile_read(ttirt_sqr_model *model, double *ms_total, int64_t *launches, double *flops_total);
 
+/* tracemult, reference matlab/utils/tracemult.c (real arguments; complex input is not supported), as a standalone operator.
+ * Inside tt_irt_sqr both forms are fused into the path's kernels; these serve callers of the MEX itself.
+ *   d_B != NULL:  C(:,:,i) = A(:,:,i) * B(:,:,j(i))   (:103-112)   A p x m x n, B m x k x s, C p x k x n, all column-major
+ *   d_B == NULL:  C(i) = A(i, j(i))                     (:131-136)   A n x s, C length n (p, m, k ignored)
+ * j holds 1-based indices stored as doubles, exactly what the MEX reads (:106-107).  An index outside 1..s gives NaN in
+ * that slice (device form) or an error before anything is computed (host form); the MEX reads out of bounds there.
+ * `_device`: device pointers, enqueued on `stream`; `_host`: host pointers, device TTIRT_DEVICE, blocks.  0 on success. */
+TTIRT_API int ttirt_tracemult_device(int64_t p, int64_t m, int64_t k, int64_t n, int64_t s, const double *d_A, const double *d_j,
+                                     const double *d_B, double *d_C, void *stream);
+TTIRT_API int ttirt_tracemult_host(int64_t p, int64_t m, int64_t k, int64_t n, int64_t s, const double *h_A, const double *h_j,
+                                   const double *h_B, double *h_C);
+
 #ifdef __cplusplus
 }
 #endif

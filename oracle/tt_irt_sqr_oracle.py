@@ -177,3 +177,19 @@ def tt_irt_sqr_oracle(n, xs, ranks, cores, q, extras=False, block=2 ** 11):
     if extras:
         return xq, lF, idx, cond, gap, lsens
     return xq, lF
+
+
+def tracemult_oracle(A, j, B=None):
+    """matlab/utils/tracemult.c, real case: C(:,:,i) = A(:,:,i) * B(:,:,j(i)) (:103-112) or C(i) = A(i, j(i)) (:131-136);
+    j one-based as the MEX takes it (:106-107)."""
+    j0 = np.asarray(j).astype(np.int64).ravel() - 1
+    A = np.asarray(A, dtype=np.float64)
+    if B is None:
+        return A[np.arange(j0.size), j0].copy()
+    B = np.asarray(B, dtype=np.float64)
+    A = A.reshape(A.shape + (1,) * (3 - A.ndim), order="F")
+    B = B.reshape(B.shape + (1,) * (3 - B.ndim), order="F")
+    C = np.zeros((A.shape[0], B.shape[1], j0.size), order="F")
+    for i in range(j0.size):
+        C[:, :, i] = A[:, :, i] @ B[:, :, j0[i]]
+    return C

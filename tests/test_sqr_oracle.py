@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from oracle.tt_irt_sqr_oracle import sqr_sweep, tt_irt_sqr_oracle, split_cores
+from oracle.tt_irt_sqr_oracle import sqr_sweep, tt_irt_sqr_oracle, split_cores, tracemult_oracle
 from tt_irt_py import synth
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -166,3 +166,23 @@ def test_oracle_reproduces_its_committed_golden_outputs(name):
     tol = 1e-12 * np.maximum(1.0, np.abs(g["xq"])) + 8 * np.finfo(float).eps * np.cumsum(g["cond"], axis=1)
     assert (np.abs(Z - g["xq"]) <= tol).all()
     np.testing.assert_allclose(lF, g["lFapp"], rtol=0, atol=1e-10)
+
+
+def test_tracemult_oracle_matches_the_mex_loops():
+    """matlab/utils/tracemult.c:103-112 (one dgemm per slice, B slice picked by the 1-based j) and :131-136."""
+    rng = np.random.default_rng(3)
+    p, m, k, n, s = 3, 4, 5, 7, 6
+    A = rng.standard_normal((p, m, n))
+    B = rng.standard_normal((m, k, s))
+    j = rng.integers(1, s + 1, n).astype(float)
+    C = tracemult_oracle(A, j, B)
+    for i in range(n):
+        for a in range(p):
+            for b in range(k):
+                assert abs(C[a, b, i] - sum(A[a, l, i] * B[l, b, int(j[i]) - 1] for l in range(m))) < 1e-13
+    A2 = rng.standard_normal((n, s))
+    np.testing.assert_array_equal(tracemult_oracle(A2, j), np.array([A2[i, int(j[i]) - 1] for i in range(n)]))
+    # the two uses inside tt_irt_sqr.m: the Cartesian square of the interface (:109) and the slab product (:205)
+    f = rng.standard_normal((4, 1, n))
+    sq = tracemult_oracle(f, np.arange(1, n + 1), np.transpose(f, (1, 0, 2)))
+    np.testing.assert_allclose(sq, np.einsum("ai,bi->abi", f[:, 0, :], f[:, 0, :]), rtol=0, atol=1e-15)

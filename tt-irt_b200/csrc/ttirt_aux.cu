@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "../../include/tt_irt1.h"
+#include "../../include/tt_irt_sqr.h"
 #include "ttirt_common.cuh"
 
 namespace ttirt {
@@ -327,6 +328,40 @@ __global__ void mh_src_kernel(int M, const unsigned char *__restrict__ onpath, c
 
 // host-side helpers ---------------------------------------------------------------------------------
 // scratch from the stream-ordered pool: cudaMalloc / cudaFree per call would cost more than the kernels
+// ------------------------------------------------------------------------------------------------
+// tracemult (reference matlab/utils/tracemult.c, real case): the indexed batched product and the column pick that
+// tt_irt_sqr.m is written in.  Inside the squared-density path both are fused into its kernels (ttirt_sqr.cu); these are the
+// standalone operators for callers that use the MEX directly (tt_irt_sqr.m:77,109,139,146-149,205, tt_rt_sqr.m, tt_irt_fourier.m).
+// ------------------------------------------------------------------------------------------------
+// C(:,:,i) = A(:,:,i) * B(:,:,j(i))   tracemult.c:103-112;  A p x m x n, B m x k x s, C p x k x n, j 1-based doubles (:106-107).
+// One CTA per group of slices, one thread per output element and slice; a thread walks a contiguous column of B (whole
+// cache lines, reused by the p threads of that column) and a stride-p row of A.  Slices that pick the same j share B in L1 / L2.
+__global__ void tracemult_kernel(int p, int m, int k, int64_t n, int64_t s, const double *__restrict__ A, const double *__restrict__ j,
+                                 const double *__restrict__ B, double *C, int *bad) {
+  const int64_t per = (int64_t)p * k;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= per * n) return;
+  const int64_t i = e / per;
+  const int o = (int)(e - i * per);
+  const int pp = o % p, kk = o / p;
+  const int64_t jj = (int64_t)j[i] - 1;                    // matlab -> C indexing (:107)
+  if (jj < 0 || jj >= s) { if (bad) atomicExch(bad, 1); C[e] = __longlong_as_double(0x7ff8000000000000LL); return; }
+  const double *a = A + pp + (int64_t)p * m * i;
+  const double *b = B + (int64_t)m * kk + (int64_t)m * k * jj;
+  double acc = 0.0;
+  for (int l = 0; l < m; l++) acc = fma(a[(int64_t)p * l], b[l], acc);
+  C[e] = acc;
+}
+
+// C(i) = A(i, j(i))   tracemult.c:131-136;  A n x s
+__global__ void tracepick_kernel(int64_t n, int64_t s, const double *__restrict__ A, const double *__restrict__ j, double *C, int *bad) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t jj = (int64_t)j[i] - 1;
+  if (jj < 0 || jj >= s) { if (bad) atomicExch(bad, 1); C[i] = __longlong_as_double(0x7ff8000000000000LL); return; }
+  C[i] = A[i + jj * n];
+}
+
 struct DevBuf {
   void *p = nullptr;
   cudaStream_t st = nullptr;
@@ -533,5 +568,43 @@ extern "C" int ttirt_mcmc_prune_host(int64_t M, const double *h_lfex, const doub
   if (ttirt_mcmc_prune_device(M, de.as<double>(), da.as<double>(), du.as<double>(), dsrc.as<int32_t>(), num_rejects, rej_hist, rej_hist_len, nullptr) != 0)
     return -1;
   CKA(cudaMemcpy(h_src, dsrc.p, sizeof(int32_t) * M, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int ttirt_tracemult_device(int64_t p, int64_t m, int64_t k, int64_t n, int64_t s, const double *d_A, const double *d_j,
+                                      const double *d_B, double *d_C, void *stream) {
+  if (n < 0 || (n > 0 && (!d_A || !d_j || !d_C))) return aux_fail("bad arguments to ttirt_tracemult_device");
+  if (n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!d_B) {                                               // two-argument form: C(i) = A(i, j(i)), A n x s
+    if (s < 1) return aux_fail("bad arguments to ttirt_tracemult_device");
+    tracepick_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, s, d_A, d_j, d_C, nullptr);
+  } else {
+    if (p < 1 || m < 1 || k < 1 || s < 1 || p > (1 << 20) || k > (1 << 20) || m > (1 << 24)) return aux_fail("bad shapes for ttirt_tracemult_device");
+    const int64_t tot = p * k * n;
+    if ((tot + 255) / 256 > 0x7fffffffLL) return aux_fail("ttirt_tracemult_device: too many output elements");
+    tracemult_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((int)p, (int)m, (int)k, n, s, d_A, d_j, d_B, d_C, nullptr);
+  }
+  ttirt::aux_launched();
+  CKA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ttirt_tracemult_host(int64_t p, int64_t m, int64_t k, int64_t n, int64_t s, const double *h_A, const double *h_j,
+                                    const double *h_B, double *h_C) {
+  if (need_device() || pick_device()) return -1;
+  if (n < 0 || (n > 0 && (!h_A || !h_j || !h_C))) return aux_fail("bad arguments to ttirt_tracemult_host");
+  if (n == 0) return 0;
+  for (int64_t i = 0; i < n; i++)                          // the MEX would read out of bounds here; fail instead
+    if (!(h_j[i] >= 1.0 && h_j[i] <= (double)s)) return aux_fail("tracemult: j(%lld) = %g outside 1..%lld", (long long)(i + 1), h_j[i], (long long)s);
+  const size_t na = h_B ? (size_t)p * m * n : (size_t)n * s, nb = h_B ? (size_t)m * k * s : 0, nc = h_B ? (size_t)p * k * n : (size_t)n;
+  DevBuf da, dj, db, dc;
+  if (da.alloc(sizeof(double) * na) || dj.alloc(sizeof(double) * n) || (h_B && db.alloc(sizeof(double) * nb)) || dc.alloc(sizeof(double) * nc))
+    return aux_fail("out of device memory");
+  CKA(cudaMemcpy(da.p, h_A, sizeof(double) * na, cudaMemcpyHostToDevice));
+  CKA(cudaMemcpy(dj.p, h_j, sizeof(double) * n, cudaMemcpyHostToDevice));
+  if (h_B) CKA(cudaMemcpy(db.p, h_B, sizeof(double) * nb, cudaMemcpyHostToDevice));
+  if (ttirt_tracemult_device(p, m, k, n, s, da.as<double>(), dj.as<double>(), h_B ? db.as<double>() : nullptr, dc.as<double>(), nullptr) != 0) return -1;
+  CKA(cudaMemcpy(h_C, dc.p, sizeof(double) * nc, cudaMemcpyDeviceToHost));
   return 0;
 }

@@ -43,8 +43,41 @@ def _lib():
         lib.ttirt_sqr_profile_enable.argtypes = [c_void_p, c_int]
         lib.ttirt_sqr_profile_read.restype = c_int
         lib.ttirt_sqr_profile_read.argtypes = [c_void_p, dp, lp, dp]
+        lib.ttirt_tracemult_host.restype = c_int
+        lib.ttirt_tracemult_host.argtypes = [c_longlong] * 5 + [dp, dp, dp, dp]
         _bound = True
     return lib
+
+
+def tracemult(A, j, B=None):
+    """ C(:,:,i) = A(:,:,i)*B(:,:,j(i))  or  C(i) = A(i,j(i))  -- reference matlab/utils/tracemult.c:5-8 (real case).
+        A: (p, m, n) [with B] or (n, s) [without]; j: n one-based indices; B: (m, k, s).  Returns (p, k, n) or (n,)."""
+    lib = _lib()
+    dp = POINTER(c_double)
+    jd = np.ascontiguousarray(np.asarray(j, dtype=np.float64).ravel())
+    n = jd.size
+    if B is None:
+        A = np.asfortranarray(A, dtype=np.float64)
+        if A.ndim != 2 or A.shape[0] != n:
+            raise ValueError("size(j,1) differs from size(A)")
+        C = np.zeros(n)
+        rc = lib.ttirt_tracemult_host(0, 0, 0, n, A.shape[1], A.ctypes.data_as(dp), jd.ctypes.data_as(dp), None, C.ctypes.data_as(dp))
+    else:
+        A = np.asfortranarray(A, dtype=np.float64)
+        B = np.asfortranarray(B, dtype=np.float64)
+        A = A.reshape(A.shape + (1,) * (3 - A.ndim), order="F")
+        B = B.reshape(B.shape + (1,) * (3 - B.ndim), order="F")
+        p, m, na = A.shape
+        if na != n:
+            raise ValueError("size(j,1) differs from size(A)")
+        if B.shape[0] != m:
+            raise ValueError("size(A,2) differs from size(B,1)")
+        k, s = B.shape[1], B.shape[2]
+        C = np.zeros((p, k, n), order="F")
+        rc = lib.ttirt_tracemult_host(p, m, k, n, s, A.ctypes.data_as(dp), jd.ctypes.data_as(dp), B.ctypes.data_as(dp), C.ctypes.data_as(dp))
+    if rc != 0:
+        _raise_last(lib, "ttirt_tracemult_host")
+    return C
 
 
 def tt_irt_sqr(xsf, f, q):
