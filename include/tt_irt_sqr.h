@@ -84,6 +84,20 @@ TTIRT_API int ttirt_sqr_run_host(int64_t d, const int64_t *n, int64_t nxs, const
 TTIRT_API void ttirt_sqr_profile_enable(ttirt_sqr_model *model, int on);
 TTIRT_API int ttirt_sqr_profile_read(ttirt_sqr_model *model, double *ms_total, int64_t *launches, double *flops_total);
 
+/* The DIRT sampler loop, reference matlab/samplers/tt_dirt_sample.m:17-73 (spline interpolation, TT cross variants: the
+ * branch that calls tt_irt_sqr at :46 and :71), i.e. the caller of tt_irt_sqr, with the samples resident on the device
+ * between the levels:
+ *   for j = nlvl .. 1:  [z = erf(z / sqrt(2)) cdf_factor + 0.5]  ->  [z, dl] = tt_irt_sqr(x, F{j}, z)  ->  lFapp += dl
+ *                       [ + sum(z.^2, 2) / 2 - log(2 cdf_factor^2 / pi) d / 2 ]            (bracketed: normal reference only)
+ *   level 0:            [same map]  ->  [z, dl] = tt_irt_sqr(x0, F0, z)  ->  lFapp += dl
+ * models[0] is the model of F0 on x0, models[j] of F{j} on x (nlevels = nlvl + 1; all of dimension d on one device);
+ * sigma <= 0: uniform reference, sigma > 0: normal reference truncated to [-sigma, sigma] ('Normal S', :21-30).
+ * q, z column-major M x d.  `_device`: enqueued on `stream`, scratch kept in models[0]; `_host`: blocks.  0 on success. */
+TTIRT_API int ttirt_dirt_sample_device(int64_t nlevels, ttirt_sqr_model *const *models, double sigma, int64_t M, const double *d_q,
+                                       int64_t ldq, double *d_z, int64_t ldz, double *d_lf, void *stream);
+TTIRT_API int ttirt_dirt_sample_host(int64_t nlevels, ttirt_sqr_model *const *models, double sigma, int64_t M, const double *h_q,
+                                     double *h_z, double *h_lf, int64_t ld);
+
 /* tracemult, reference matlab/utils/tracemult.c (real arguments; complex input is not supported), as a standalone operator.
  * Inside tt_irt_sqr both forms are fused into the path's kernels; these serve callers of the MEX itself.
  *   d_B != NULL:  C(:,:,i) = A(:,:,i) * B(:,:,j(i))   (:103-112)   A p x m x n, B m x k x s, C p x k x n, all column-major

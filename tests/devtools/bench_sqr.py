@@ -29,6 +29,57 @@ import bench  # noqa: E402  (ClockSampler, measured_fp64_peak)
 from tt_irt_py import synth, tt_irt, tt_irt_sqr  # noqa: E402
 
 
+def dirt_main(a):
+    """DIRT sampler loop (tt_dirt_sample.m:17-73): nlvl + 1 tt_irt_sqr levels with the reference maps between them, samples
+    resident on the device; synthetic levels of one shape, truncated-normal reference on [-4, 4]."""
+    import torch
+    d, n, r = [int(v) for v in a.shape.split(",")]
+    M = 1 << a.log2m
+    dev = torch.device("cuda", 0)
+    levels = [synth.make_tt(d, n, r, seed=5, lo=-2.0, hi=3.0)] + [synth.make_tt(d, n, r, seed=6 + j, lo=-4.0, hi=4.0) for j in range(a.dirt)]
+    drt = tt_irt_sqr.Dirt(levels, "Normal 4")
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1)
+    q = (torch.rand((d, M), dtype=torch.float64, device=dev, generator=gen) * 2.0 - 1.0) * 3.99
+    z = torch.empty((d, M), dtype=torch.float64, device=dev)
+    lf = torch.empty((M,), dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step():
+        drt.sample_device(M, q.data_ptr(), M, z.data_ptr(), M, lf.data_ptr(), stream.cuda_stream)
+    for _ in range(a.warmup):
+        step()
+    torch.cuda.synchronize()
+    l1 = tt_irt.kernel_launches()
+    sampler = bench.ClockSampler(0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(a.steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.steps
+    clocks = sampler.stop()
+    W = tt_irt_sqr.flops_per_sample(levels[0][0], levels[0][2]) * (a.dirt + 1)
+    out = {"metric": "dirt_samples_per_sec", "value": M / (ms * 1e-3), "unit": "samples/s", "n_gpus": 1, "steps": a.steps, "warmup": a.warmup,
+           "ms_per_step": ms, "higher_is_better": True, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "DIRT sampler loop (tt_dirt_sample.m), %d levels of d=%d n=%d r=%d, truncated-normal reference on [-4,4], M=2^%d"
+                                  % (a.dirt + 1, d, n, r, a.log2m)},
+           "algorithmic_tflops_whole_step": W * M / (ms * 1e-3) / 1e12, "levels": a.dirt + 1,
+           "gpu_launches": int(tt_irt.kernel_launches() - l1), "clocks": clocks,
+           "finite": bool(torch.isfinite(lf).all() and torch.isfinite(z).all())}
+    if not a.no_cpu:
+        from oracle.dirt_oracle import tt_dirt_sample_oracle
+        qs = np.asfortranarray((2.0 * synth.make_q(a.cpu_samples, d, seed=2) - 1.0) * 3.99)
+        t0 = time.perf_counter()
+        tt_dirt_sample_oracle(levels, qs, "Normal 4")
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": a.cpu_samples / dt, "unit": "samples/s", "cores": 1, "kind": "port",
+                               "sample": "%d samples through oracle/dirt_oracle.py (numpy, one thread), %.1f s" % (a.cpu_samples, dt)}
+    drt.close()
+    print(json.dumps(out))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--shape", default="32,65,64")
@@ -38,7 +89,11 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-samples", type=int, default=1 << 12)
+    ap.add_argument("--dirt", type=int, default=-1, help="time the DIRT sampler loop (tt_dirt_sample.m) with this many levels above level 0, "
+                                                         "normal reference on [-4, 4], instead of a single tt_irt_sqr")
     a = ap.parse_args()
+    if a.dirt >= 0:
+        return dirt_main(a)
     d, n, r = [int(v) for v in a.shape.split(",")]
     M = 1 << a.log2m
     import torch

@@ -763,6 +763,28 @@ static cudaError_t upd_launch(const UpdArgs &a, int64_t max_tiles, int sm_count,
   return cudaGetLastError();
 }
 
+// tt_dirt_sample.m:36,60  truncated normal -> uniform:  z = erf(z / sqrt(2)) * cdf_factor + 0.5
+__global__ void dirt_tn2u_kernel(int64_t M, int d, double cdf_factor, const double *__restrict__ in, int64_t ldi, double *out, int64_t ldo) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y;
+  if (m >= M || k >= d) return;
+  out[m + ldo * k] = __dadd_rn(__dmul_rn(erf(__ddiv_rn(in[m + ldi * k], 1.4142135623730951)), cdf_factor), 0.5);
+}
+
+// tt_dirt_sample.m:51-56  lFapp = lFapp + dlFapp;  with a normal reference  lFapp = lFapp + sum(z.^2, 2) / 2 - log(2 cdf_factor^2 / pi) d / 2
+__global__ void dirt_accumulate_kernel(int64_t M, int d, int first, int normal, double logc_half_d, const double *__restrict__ dlf,
+                                       const double *__restrict__ z, int64_t ldz, double *lf) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  double v = first ? dlf[m] : __dadd_rn(lf[m], dlf[m]);
+  if (normal) {
+    double s = 0.0;
+    for (int k = 0; k < d; k++) { const double t = z[m + ldz * k]; s = __dadd_rn(s, __dmul_rn(t, t)); }
+    v = __dsub_rn(__dadd_rn(v, __ddiv_rn(s, 2.0)), logc_half_d);
+  }
+  lf[m] = v;
+}
+
 __global__ void sqr_fill_nan_kernel(double *p, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = __longlong_as_double(0x7ff8000000000000LL);
@@ -812,6 +834,9 @@ struct ttirt_sqr_model {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
   size_t prof_used = 0;
   double prof_flops = 0.0;
+  // scratch of the DIRT layer loop (held by the level-0 model): two M x d seed / sample buffers, one length-M log-density
+  double *dirt_z[2] = {nullptr, nullptr}, *dirt_lf = nullptr;
+  int64_t dirt_cap = 0;
 };
 
 static void sqr_ws_free(ttirt_sqr_model *md) {
@@ -864,6 +889,7 @@ extern "C" void ttirt_sqr_model_destroy(ttirt_sqr_model *md) {
   cudaSetDevice(md->device);
   cudaDeviceSynchronize();
   sqr_ws_free(md);
+  sqr_free(md->dirt_z[0]); sqr_free(md->dirt_z[1]); sqr_free(md->dirt_lf);
   sqr_free(md->d_xs); sqr_free(md->d_h); sqr_free(md->d_hc); sqr_free(md->d_core); sqr_free(md->d_gp); sqr_free(md->d_rfac);
   if (md->stream) cudaStreamDestroy(md->stream);
   if (md->copy_stream) cudaStreamDestroy(md->copy_stream);
@@ -1300,4 +1326,88 @@ extern "C" int ttirt_sqr_profile_read(ttirt_sqr_model *md, double *ms_total, int
   if (launches) *launches = (int64_t)md->prof_used;
   if (flops_total) *flops_total = md->prof_flops;
   return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// DIRT sampler loop (reference matlab/samplers/tt_dirt_sample.m:17-73, spline branch): the caller of tt_irt_sqr
+// ------------------------------------------------------------------------------------------------
+extern "C" int ttirt_dirt_sample_device(int64_t nlevels, ttirt_sqr_model *const *models, double sigma, int64_t M, const double *d_q,
+                                        int64_t ldq, double *d_z, int64_t ldz, double *d_lf, void *stream) {
+  if (nlevels < 1 || !models) return aux_fail("ttirt_dirt_sample: need at least the level-0 model");
+  for (int64_t j = 0; j < nlevels; j++) {
+    if (!models[j]) return aux_fail("ttirt_dirt_sample: null model at level %lld", (long long)j);
+    if (models[j]->d != models[0]->d || models[j]->device != models[0]->device)
+      return aux_fail("ttirt_dirt_sample: all levels must have the same dimension and live on the same device");
+  }
+  if (M < 0 || ldq < M || ldz < M) return aux_fail("bad M / leading dimensions");
+  if (M == 0) return 0;
+  ttirt_sqr_model *m0 = models[0];
+  const int d = (int)m0->d;
+  CKS(cudaSetDevice(m0->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (m0->dirt_cap < M) {
+    CKS(cudaStreamSynchronize(st));
+    sqr_free(m0->dirt_z[0]); sqr_free(m0->dirt_z[1]); sqr_free(m0->dirt_lf);
+    m0->dirt_z[0] = m0->dirt_z[1] = m0->dirt_lf = nullptr; m0->dirt_cap = 0;
+    CKS(sqr_alloc(&m0->dirt_z[0], sizeof(double) * M * d));
+    CKS(sqr_alloc(&m0->dirt_z[1], sizeof(double) * M * d));
+    CKS(sqr_alloc(&m0->dirt_lf, sizeof(double) * M));
+    m0->dirt_cap = M;
+  }
+  const bool normal = sigma > 0.0;
+  const double cdf_factor = normal ? 0.5 / erf(sigma / sqrt(2.0)) : 0.0;                     // :30
+  const double logc_half_d = normal ? log(2.0 * cdf_factor * cdf_factor / 3.14159265358979323846) * d / 2.0 : 0.0;
+  const dim3 g2((unsigned)((M + 255) / 256), (unsigned)d);
+  const double *cur = d_q;
+  int64_t ldc = ldq;
+  int pp = 0;
+  bool first = true;
+  for (int64_t j = nlevels - 1; j >= 0; j--) {                                                // :34 and level 0 (:59-73)
+    if (normal) {
+      dirt_tn2u_kernel<<<g2, 256, 0, st>>>(M, d, cdf_factor, cur, ldc, m0->dirt_z[pp], M);    // :36, :60
+      LAUNCHED();
+      cur = m0->dirt_z[pp]; ldc = M; pp ^= 1;
+    }
+    double *out = j == 0 ? d_z : m0->dirt_z[pp];
+    const int64_t ldo = j == 0 ? ldz : M;
+    if (ttirt_sqr_sample_device(models[j], M, d, cur, ldc, out, ldo, m0->dirt_lf, nullptr, stream) != 0) return -1;   // :46, :71
+    dirt_accumulate_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(M, d, first ? 1 : 0, (normal && j > 0) ? 1 : 0, logc_half_d,
+                                                                       m0->dirt_lf, out, ldo, d_lf);      // :51-56, :73
+    LAUNCHED();
+    first = false;
+    if (j > 0) { cur = out; ldc = M; pp ^= 1; }
+  }
+  CKS(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ttirt_dirt_sample_host(int64_t nlevels, ttirt_sqr_model *const *models, double sigma, int64_t M, const double *h_q,
+                                      double *h_z, double *h_lf, int64_t ld) {
+  if (nlevels < 1 || !models || !models[0]) return aux_fail("ttirt_dirt_sample: need at least the level-0 model");
+  if (M < 0 || ld < M) return aux_fail("bad M / leading dimension");
+  if (M == 0) return 0;
+  if (!h_q || !h_z || !h_lf) return aux_fail("null host buffer");
+  ttirt_sqr_model *m0 = models[0];
+  const int64_t d = m0->d;
+  CKS(cudaSetDevice(m0->device));
+  const int64_t chunk = std::min<int64_t>(M, (int64_t)1 << 20);
+  double *dq = nullptr, *dz = nullptr, *dl = nullptr;
+  CKS(sqr_alloc(&dq, sizeof(double) * chunk * d));
+  CKS(sqr_alloc(&dz, sizeof(double) * chunk * d));
+  CKS(sqr_alloc(&dl, sizeof(double) * chunk));
+  cudaStream_t st = m0->stream;
+  int rc = 0;
+  for (int64_t b = 0; b < M && rc == 0; b += chunk) {
+    const int64_t rows = std::min(chunk, M - b);
+    if (cudaMemcpy2DAsync(dq, sizeof(double) * chunk, h_q + b, sizeof(double) * ld, sizeof(double) * rows, (size_t)d, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = aux_fail("copy in failed"); break; }
+    rc = ttirt_dirt_sample_device(nlevels, models, sigma, rows, dq, chunk, dz, chunk, dl, st);
+    if (rc != 0) break;
+    if (cudaMemcpy2DAsync(h_z + b, sizeof(double) * ld, dz, sizeof(double) * chunk, sizeof(double) * rows, (size_t)d, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaMemcpyAsync(h_lf + b, dl, sizeof(double) * rows, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) rc = aux_fail("copy out failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  cudaStreamSynchronize(st);
+  sqr_free(dq); sqr_free(dz); sqr_free(dl);
+  return rc;
 }

@@ -43,6 +43,11 @@ def _lib():
         lib.ttirt_sqr_profile_enable.argtypes = [c_void_p, c_int]
         lib.ttirt_sqr_profile_read.restype = c_int
         lib.ttirt_sqr_profile_read.argtypes = [c_void_p, dp, lp, dp]
+        lib.ttirt_dirt_sample_host.restype = c_int
+        lib.ttirt_dirt_sample_host.argtypes = [c_longlong, POINTER(c_void_p), c_double, c_longlong, dp, dp, dp, c_longlong]
+        lib.ttirt_dirt_sample_device.restype = c_int
+        lib.ttirt_dirt_sample_device.argtypes = [c_longlong, POINTER(c_void_p), c_double, c_longlong, c_void_p, c_longlong, c_void_p,
+                                                 c_longlong, c_void_p, c_void_p]
         lib.ttirt_tracemult_host.restype = c_int
         lib.ttirt_tracemult_host.argtypes = [c_longlong] * 5 + [dp, dp, dp, dp]
         _bound = True
@@ -193,3 +198,71 @@ def flops_per_sample(ns, ranks, D=None):
     w = (r0 * (r0 + 1) * ns[:D]).sum() + (r0 * (r0 + 1) // 2).sum()
     w += (4 * ranks[:D - 1] * ranks[1:D]).sum()
     return int(w)
+
+
+def _reference_sigma(reference):
+    """tt_dirt_sample.m:21-30: 0 for a uniform reference, else the half-width of the truncated normal ('Normal' -> 4)."""
+    if str(reference)[0].lower() == "u":
+        return 0.0
+    digits = "".join(ch for ch in str(reference) if ch == "." or ch.isdigit())
+    try:
+        return float(digits)
+    except ValueError:
+        return 4.0
+
+
+class Dirt(object):
+    """A Deep Inverse Rosenblatt Transform resident on one B200: IRTstruct.F0 on IRTstruct.x0 and IRTstruct.F{1..nlvl} on
+    IRTstruct.x (reference matlab/samplers/tt_dirt_sample.m, fields of tt_dirt_approx.m:158-162, 257, 321), each swept once.
+    levels[0] = (n, x0, ranks, cores) of F0, levels[j] = (n, x, ranks, cores) of F{j}; spline interpolation only."""
+
+    def __init__(self, levels, reference="uni", device=0):
+        self.sigma = _reference_sigma(reference)
+        self.models = [SqrModel(n, xs, rk, c, device=device) for (n, xs, rk, c) in levels]
+        self.d = self.models[0].d
+        self._lib = self.models[0]._lib
+        self._arr = (c_void_p * len(self.models))(*[m._h for m in self.models])
+
+    def close(self):
+        for m in getattr(self, "models", []):
+            m.close()
+        self.models = []
+
+    def sample(self, q):
+        """[z, lFapp] = tt_dirt_sample(IRTstruct, q): q on [0,1]^d (uniform reference) or [-S,S]^d (truncated normal)."""
+        q = np.asfortranarray(q, dtype=np.float64)
+        M, d = q.shape
+        if d != self.d:
+            raise ValueError("q must be M x d")
+        z = np.zeros((M, d), order="F")
+        lF = np.zeros(M)
+        dp = POINTER(c_double)
+        rc = self._lib.ttirt_dirt_sample_host(len(self.models), self._arr, self.sigma, M, q.ctypes.data_as(dp), z.ctypes.data_as(dp),
+                                              lF.ctypes.data_as(dp), M)
+        if rc != 0:
+            _raise_last(self._lib, "ttirt_dirt_sample_host")
+        return z, lF
+
+    def sample_device(self, M, q_ptr, ldq, z_ptr, ldz, lf_ptr, stream=None):
+        rc = self._lib.ttirt_dirt_sample_device(len(self.models), self._arr, self.sigma, int(M), c_void_p(q_ptr), int(ldq), c_void_p(z_ptr),
+                                                int(ldz), c_void_p(lf_ptr), c_void_p(stream) if stream else None)
+        if rc != 0:
+            _raise_last(self._lib, "ttirt_dirt_sample_device")
+
+
+def tt_dirt_sample(IRTstruct, q):
+    """[z, lFapp] = tt_dirt_sample(IRTstruct, q)  (reference tt_dirt_sample.m:1; the exact-density evaluation of :76-82 stays
+    with the caller).  IRTstruct: mapping with the fields tt_dirt_approx leaves behind -- 'x0', 'F0', 'x', 'F' (list),
+    'reference', and optionally 'interpolation' / 'crossmethod'; F0 / F{j} are ttpy tensors or TTTensor containers."""
+    if str(IRTstruct.get("crossmethod", "amen_cross_s")) == "build_ftt" or str(IRTstruct.get("interpolation", "spline"))[0] != "s":
+        raise NotImplementedError("only the spline / TT-cross branch of tt_dirt_sample (tt_irt_sqr, :46, :71) is built")
+
+    def level(f, x):
+        x = np.concatenate([np.asarray(v, dtype=np.float64).ravel() for v in x]) if isinstance(x, (list, tuple)) else np.asarray(x, dtype=np.float64).ravel()
+        return (np.asarray(f.n, dtype=np.int64), x, np.asarray(f.r, dtype=np.int64), _packed_cores(f))
+    levels = [level(IRTstruct["F0"], IRTstruct["x0"])] + [level(f, IRTstruct["x"]) for f in IRTstruct["F"]]
+    drt = Dirt(levels, IRTstruct.get("reference", "uni"))
+    try:
+        return drt.sample(q)
+    finally:
+        drt.close()
