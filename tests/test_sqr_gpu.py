@@ -212,3 +212,32 @@ def test_tracemult_operator(p, m, k, n, s):
     np.testing.assert_array_equal(tt_irt_sqr.tracemult(A2, j), tracemult_oracle(A2, j))
     with pytest.raises(RuntimeError):
         tt_irt_sqr.tracemult(A2, np.full(n, s + 1.0))          # the MEX would read out of bounds: fail instead
+
+
+def test_edge_seeds_and_zero_mass_fallback():
+    """Seeds exactly 0 and 1 (ties of the bisection go left, :139-142, q >= 1 ends in the last cell) and conditionals without
+    mass (:121-127: the conditional is replaced by h, its CDF by cumsum(h)): same cells, same samples, same -inf pattern."""
+    ns, xs, rk, c = synth.make_tt(3, 9, 4, seed=2)
+    q = synth.make_q(64, 3, seed=3)
+    q[:8, :] = 0.0
+    q[8:16, :] = 1.0
+    q[16:24, 0] = 0.0
+    q[24:32, 2] = 1.0
+    q = np.asfortranarray(q)
+    for cores in (c, None):
+        if cores is None:                       # a vanishing core: every conditional is zero, every dimension falls back
+            cores = c.copy()
+            off = int(rk[0] * ns[0] * rk[1])
+            cores[off:off + int(rk[1] * ns[1] * rk[2])] = 0.0
+        Zo, lo, io, cond, gap, lsens = tt_irt_sqr_oracle(ns, xs, rk, cores, q, extras=True)
+        md = tt_irt_sqr.SqrModel(ns, xs, rk, cores)
+        try:
+            Z, lF, idx = md.sample(q, want_idx=True)
+        finally:
+            md.close()
+        np.testing.assert_array_equal(idx, io)
+        np.testing.assert_allclose(Z, Zo, rtol=0, atol=1e-12)
+        np.testing.assert_array_equal(np.isfinite(lF), np.isfinite(lo))
+        fin = np.isfinite(lo)
+        np.testing.assert_allclose(lF[fin], lo[fin], rtol=0, atol=1e-11)
+        np.testing.assert_array_equal(lF[~fin], lo[~fin])

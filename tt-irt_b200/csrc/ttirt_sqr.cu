@@ -346,9 +346,9 @@ __global__ void sqr_init_kernel(double *F, int ldf, int rows) {
 }
 
 constexpr int PDF_WARPS = 8;                  // MMA warps, two per SM sub-partition
-constexpr int PDF_MT = 2;                     // 8-row MMA tiles per warp
-constexpr int PDF_WROWS = 8 * PDF_MT;
-constexpr int PDF_ROWS = PDF_WARPS * PDF_WROWS;   // samples per CTA tile
+// 8-row MMA tiles per warp (template parameter MT): 2 for the r <= 64 / n <= 72 class (16 column-tile accumulator chains per
+// k-step), 4 for the two lighter classes, whose few column tiles would otherwise leave a k-step too short to hide the
+// operand loads behind its DMMAs
 constexpr int PDF_KS = 16;                    // k-steps per B slice
 constexpr int PDF_STAGES = 3;
 
@@ -358,8 +358,8 @@ struct PdfArgs {
   double *pdf; int64_t ldp;
 };
 
-__host__ __device__ inline size_t pdf_smem_bytes(int ldf, int pb) {
-  return sizeof(double) * ((size_t)PDF_ROWS * ldf + (size_t)PDF_STAGES * PDF_KS * 4 * pb) + 2 * PDF_STAGES * sizeof(uint64_t);
+__host__ __device__ inline size_t pdf_smem_bytes(int rows_cta, int ldf, int pb) {
+  return sizeof(double) * ((size_t)rows_cta * ldf + (size_t)PDF_STAGES * PDF_KS * 4 * pb) + 2 * PDF_STAGES * sizeof(uint64_t);
 }
 
 // Conditional pdf of one dimension for a chunk: pdf[j, m] = sum over pairs f_m[a] f_m[b] Gp[(a,b), j].
@@ -370,8 +370,10 @@ __host__ __device__ inline size_t pdf_smem_bytes(int ldf, int pb) {
 //   * pitches: ldf = 4 (mod 8) and pb = 4 (mod 8) doubles make the fragment loads bank-conflict free without a swizzle.
 //   * TAIL1 (n = 8 NT + 1, the usual 2^p + 1 grid): the lone last grid column is a DFMA dot product on the A values the lanes
 //     already hold (one broadcast LDS and two DFMA per k-step) instead of a DMMA column tile that is 7/8 padding.
-template <int NT, bool TAIL1>
+template <int NT, bool TAIL1, int PDF_MT>
 __global__ void __launch_bounds__(32 * (PDF_WARPS + 1), 1) sqr_pdf_kernel(PdfArgs a) {
+  constexpr int PDF_WROWS = 8 * PDF_MT;               // samples per warp
+  constexpr int PDF_ROWS = PDF_WARPS * PDF_WROWS;     // samples per CTA tile
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *Fs = reinterpret_cast<double *>(smem_raw);
   double *Bs = Fs + (size_t)PDF_ROWS * a.ldf;
@@ -404,7 +406,7 @@ __global__ void __launch_bounds__(32 * (PDF_WARPS + 1), 1) sqr_pdf_kernel(PdfArg
   }
   const int g = lane >> 2, t = lane & 3;
   const int ldf = a.ldf;
-  double *fw = Fs + (size_t)warp * PDF_WROWS * ldf;        // this warp's 16 staged rows
+  double *fw = Fs + (size_t)warp * PDF_WROWS * ldf;        // this warp's staged rows
   const int nchunk = (a.r0 + 3) >> 2;
   uint32_t it = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -413,21 +415,23 @@ __global__ void __launch_bounds__(32 * (PDF_WARPS + 1), 1) sqr_pdf_kernel(PdfArg
     {
       // the warp's 16 rows are one contiguous block (same pitch in global and shared memory): all loads in flight before
       // the first store, 16 bytes per lane and instruction; rows past the end of the chunk are zero
-      const int nvec = ldf >> 2;                                   // double2 per lane: 16 ldf / (2 * 32)
+      const int nvec = (PDF_WROWS * ldf) >> 6;                     // double2 per lane: WROWS ldf / (2 * 32)
       const int live = a.rows - m0 < PDF_WROWS ? (a.rows - m0 > 0 ? a.rows - m0 : 0) : PDF_WROWS;
       const int valid = live * (ldf >> 1);                         // double2 holding real rows
       const double2 *src = reinterpret_cast<const double2 *>(a.F + (size_t)m0 * ldf);
       double2 *dst = reinterpret_cast<double2 *>(fw);
-      double2 v[17];
+      for (int base = 0; base < nvec; base += 17) {
+        double2 v[17];
 #pragma unroll
-      for (int j = 0; j < 17; j++) {
-        const int e = lane + 32 * j;
-        v[j] = make_double2(0.0, 0.0);
-        if (j < nvec && e < valid) v[j] = src[e];
+        for (int j = 0; j < 17; j++) {
+          const int e = lane + 32 * (base + j);
+          v[j] = make_double2(0.0, 0.0);
+          if (base + j < nvec && e < valid) v[j] = src[e];
+        }
+#pragma unroll
+        for (int j = 0; j < 17; j++)
+          if (base + j < nvec) dst[lane + 32 * (base + j)] = v[j];
       }
-#pragma unroll
-      for (int j = 0; j < 17; j++)
-        if (j < nvec) dst[lane + 32 * j] = v[j];
     }
     __syncwarp();
     double acc[PDF_MT][NT][2];
@@ -902,20 +906,21 @@ extern "C" void ttirt_sqr_model_destroy(ttirt_sqr_model *md) {
   delete md;
 }
 
-template <int NT, bool TAIL1>
+template <int NT, bool TAIL1, int MT>
 static cudaError_t pdf_launch(const PdfArgs &a, int sm_count, cudaStream_t st) {
+  constexpr int PDF_ROWS = PDF_WARPS * 8 * MT;
   static bool attr_done[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
-  const size_t bytes = pdf_smem_bytes(a.ldf, a.pb);
+  const size_t bytes = pdf_smem_bytes(PDF_ROWS, a.ldf, a.pb);
   if (dev < 64 && !attr_done[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(sqr_pdf_kernel<NT, TAIL1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(sqr_pdf_kernel<NT, TAIL1, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     attr_done[dev] = true;
   }
   const int ntiles = (a.rows + PDF_ROWS - 1) / PDF_ROWS;
   const int grid = ntiles < sm_count ? ntiles : sm_count;
-  sqr_pdf_kernel<NT, TAIL1><<<grid, 32 * (PDF_WARPS + 1), bytes, st>>>(a);
+  sqr_pdf_kernel<NT, TAIL1, MT><<<grid, 32 * (PDF_WARPS + 1), bytes, st>>>(a);
   return cudaGetLastError();
 }
 
@@ -1154,9 +1159,9 @@ static int sqr_enqueue_chunk(ttirt_sqr_model *md, int64_t rows, int64_t D, const
     // the dimension's own grid size picks the variant inside the model's class (pb is the class's pitch)
     cudaError_t pe;
     const bool t1 = (di.n == 8 * (md->nt - 1) + 1);
-    if (md->nt == 3) pe = t1 ? pdf_launch<2, true>(pa, md->sm_count, st) : pdf_launch<3, false>(pa, md->sm_count, st);
-    else if (md->nt == 5) pe = t1 ? pdf_launch<4, true>(pa, md->sm_count, st) : pdf_launch<5, false>(pa, md->sm_count, st);
-    else pe = t1 ? pdf_launch<8, true>(pa, md->sm_count, st) : pdf_launch<9, false>(pa, md->sm_count, st);
+    if (md->nt == 3) pe = t1 ? pdf_launch<2, true, 4>(pa, md->sm_count, st) : pdf_launch<3, false, 4>(pa, md->sm_count, st);
+    else if (md->nt == 5) pe = t1 ? pdf_launch<4, true, 4>(pa, md->sm_count, st) : pdf_launch<5, false, 4>(pa, md->sm_count, st);
+    else pe = t1 ? pdf_launch<8, true, 2>(pa, md->sm_count, st) : pdf_launch<9, false, 2>(pa, md->sm_count, st);
     CKS(pe);
     LAUNCHED();
     if (e1) CKS(cudaEventRecord(e1, st));
