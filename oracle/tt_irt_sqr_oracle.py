@@ -4,11 +4,15 @@ Follows /root/reference/matlab/samplers/tt_irt_sqr.m:1-208 statement by statemen
 matlab/utils/tracemult.c:103-112 for the batched product and :131-136 for the column pick).  Nothing under
 tt-irt_b200/ imports this file; only tests/, __graft_entry__.smoke() and the bench scripts' checker legs do.
 
-PARITY UNPINNED against a live reference: the routine is Matlab-only (no Matlab / Octave in this image, no golden
-vectors in the reference).  It is pinned instead by closed forms (tests/test_sqr_oracle.py):
-rank-1 separable densities against an independent scalar 1-D inverse CDF, the identity
-sum_j trapezoid(pdf) = 1 after normalisation, exactness of Z -> CDF(Z) = q, and invariance of the conditionals
-under the sign / rotation freedom of the QR factor.
+PARITY PARTLY PINNED.  The routine itself is Matlab-only (no Matlab / Octave in this image, no golden vectors in the
+reference), so it cannot be run here.  It is pinned against the UNMODIFIED reference C routine
+tt_irt1 (oracle/_ref) wherever the two transforms are the same map (tests/test_sqr_oracle.py): on separable (rank-1)
+sqrt-densities every output (Z and the log-density), and for general ranks the first coordinate, which exercises the whole
+backward sweep (core x R, weighted QR, Cartesian square) against tt_irt1's marginalisation of the Kronecker-squared TT.
+What the reference C cannot pin -- the squared LINEAR interpolant of the interface between grid nodes for ranks > 1 -- is
+pinned by closed forms: CDF(x_k) = q_k for every sample and dimension with the conditionals rebuilt independently, the
+first semi-marginal against the explicitly marginalised squared TT, marginal sampling = prefix of the full transform,
+boundary extension = explicitly extended cores, the zero-mass fallback.
 Third-party arithmetic: `qr` (LAPACK dgeqrf behind Matlab, tt_irt_sqr.m:69) is numpy.linalg.qr here, i.e. the
 wheel-bundled OpenBLAS 0.3.30 dgeqrf; only R'R enters the result, so the factor's row signs do not matter.
 """

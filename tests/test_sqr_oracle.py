@@ -186,3 +186,54 @@ def test_tracemult_oracle_matches_the_mex_loops():
     f = rng.standard_normal((4, 1, n))
     sq = tracemult_oracle(f, np.arange(1, n + 1), np.transpose(f, (1, 0, 2)))
     np.testing.assert_allclose(sq, np.einsum("ai,bi->abi", f[:, 0, :], f[:, 0, :]), rtol=0, atol=1e-15)
+
+
+def _squared_tt(ns, rk, c):
+    """TT of the elementwise square p = f o f: cores are the Kronecker squares of f's cores, ranks r^2."""
+    cores = split_cores(ns, rk, c)
+    out = []
+    for G in cores:
+        r0, n, r1 = G.shape
+        K = np.einsum("ajb,cjd->acjbd", G, G).reshape((r0 * r0, n, r1 * r1), order="C")
+        out.append(K.ravel(order="F"))
+    return np.concatenate(out), np.asarray(rk, dtype=np.int64) ** 2
+
+
+def _reference_tt_irt1(ns, xs, rk, c, q):
+    """The unmodified reference C tt_irt1 (oracle/_ref) when it is built, else its bit-exact C restatement."""
+    import oracle
+    if oracle.have_ref(32, "shim"):
+        return oracle.ref_run(ns, xs, rk, c, q, width=32, blas="shim")
+    if not os.path.exists(os.path.join(oracle.ORACLE_DIR, "liboracle_tt_irt1.so")):
+        oracle.build()
+    return oracle.oracle_run(ns, xs, rk, c, q)
+
+
+def test_pinned_by_the_reference_c_routine_on_separable_densities():
+    """For a rank-1 sqrt-density the squared-density transform and the reference's linear-spline tt_irt1 on the squared node
+    values are the same map (the scalar left interface normalises away): Z and the log-density agree with the live reference."""
+    d, n = 4, 17
+    rng = np.random.default_rng(11)
+    f = [rng.random(n) + 0.2 for _ in range(d)]
+    xs = np.concatenate([np.sort(rng.random(n)) * 3 - 1 for _ in range(d)])
+    ns, rk = np.full(d, n), np.ones(d + 1, dtype=np.int64)
+    q = synth.make_q(500, d, seed=12)
+    Zs, ls = tt_irt_sqr_oracle(ns, xs, rk, np.concatenate(f), q)
+    Zr, lr = _reference_tt_irt1(ns, xs, rk, np.concatenate([v ** 2 for v in f]), q)
+    np.testing.assert_allclose(Zs, Zr, rtol=0, atol=2e-10)       # the reference's own root formula cancels in absolute coordinates
+    assert np.median(np.abs(Zs - Zr)) < 1e-14
+    np.testing.assert_allclose(ls, lr, rtol=0, atol=1e-9)
+
+
+def test_sweep_pinned_by_the_reference_c_routine_through_the_first_coordinate():
+    """General ranks: the first coordinate only sees the backward sweep.  tt_irt1 on the Kronecker-squared TT (rank r^2)
+    integrates the same squared interpolant with the same trapezoid weights that tt_irt_sqr folds into its QR factors
+    (:49-51, :66-72), so the first column of Z must agree with the live reference."""
+    d, n, r = 4, 9, 3
+    ns, xs, rk, c = synth.make_tt(d, n, r, seed=14, cores="normal")
+    c2, rk2 = _squared_tt(ns, rk, c)
+    q = synth.make_q(400, d, seed=15)
+    Zs, ls = tt_irt_sqr_oracle(ns, xs, rk, c, q)
+    Zr, lr = _reference_tt_irt1(ns, xs, rk2, c2, q)
+    np.testing.assert_allclose(Zs[:, 0], Zr[:, 0], rtol=0, atol=1e-10)
+    assert np.median(np.abs(Zs[:, 0] - Zr[:, 0])) < 1e-13
