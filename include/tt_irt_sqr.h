@@ -47,6 +47,15 @@ extern "C" {
 TTIRT_API void tt_irt_sqr(TTIRT_INT d, TTIRT_INT *n, TTIRT_INT nxs, double *xs, TTIRT_INT *ttrank, double *ttcore,
                           TTIRT_INT M, TTIRT_INT D, double *q, double *z, double *lFapp);
 
+/*
+ * [q, lFapp] = tt_rt_sqr(xsf, f, x)  -- the forward (Rosenblatt) transform, reference matlab/samplers/tt_rt_sqr.m:1-178:
+ * same arguments and sweep as tt_irt_sqr, x (column-major M x D) in, q = CDF values in [0,1] and the log-density at x out.
+ * The per-dimension tail is the reference's (:129-166): cell found on the grid, quadratic-spline CDF evaluated at x_k,
+ * nothing clamped.  What tt_dirt_inverse.m:39,52 calls.  Same failure behaviour and environment as tt_irt_sqr.
+ */
+TTIRT_API void tt_rt_sqr(TTIRT_INT d, TTIRT_INT *n, TTIRT_INT nxs, double *xs, TTIRT_INT *ttrank, double *ttcore,
+                         TTIRT_INT M, TTIRT_INT D, double *x, double *q, double *lFapp);
+
 typedef struct ttirt_sqr_model ttirt_sqr_model; /* opaque: extended cores + packed semi-marginal Gram operands on one device */
 
 /* Upload grid and cores, extrapolate the cores to the boundary when the grid has the two extra points (:53-60), run the
@@ -71,12 +80,22 @@ TTIRT_API int ttirt_sqr_sample_device(ttirt_sqr_model *model, int64_t M, int64_t
 /* The same on host buffers (leading dimension ld >= M): chunked copy in, kernels, copy out.  Blocks.  0 on success. */
 TTIRT_API int ttirt_sqr_sample_host(ttirt_sqr_model *model, int64_t M, int64_t D, const double *h_q, double *h_z,
                                     double *h_lf, int32_t *h_idx, int64_t ld);
+/* The forward transform tt_rt_sqr on a resident model: points x in, CDF values q and log-density out (same layouts). */
+TTIRT_API int ttirt_sqr_forward_device(ttirt_sqr_model *model, int64_t M, int64_t D, const double *d_x, int64_t ldx,
+                                       double *d_q, int64_t ldq, double *d_lf, int32_t *d_idx, void *stream);
+TTIRT_API int ttirt_sqr_forward_host(ttirt_sqr_model *model, int64_t M, int64_t D, const double *h_x, double *h_q,
+                                     double *h_lf, int32_t *h_idx, int64_t ld);
 /* Whole call on host buffers (model create, sample, release): what tt_irt_sqr() runs.  The M rows are cut into contiguous
  * ranges over n_devices devices starting at first_device (cores replicated, sweep redone per device, one host thread per
  * device, no collective).  0 on success. */
 TTIRT_API int ttirt_sqr_run_host(int64_t d, const int64_t *n, int64_t nxs, const double *xs, const int64_t *ttrank,
                                  const double *ttcore, int64_t M, int64_t D, const double *h_q, double *h_z, double *h_lf,
                                  int first_device, int n_devices);
+
+/* ... and what tt_rt_sqr() runs. */
+TTIRT_API int ttirt_sqr_run_forward_host(int64_t d, const int64_t *n, int64_t nxs, const double *xs, const int64_t *ttrank,
+                                         const double *ttcore, int64_t M, int64_t D, const double *h_x, double *h_q, double *h_lf,
+                                         int first_device, int n_devices);
 
 /* Per-launch CUDA-event timing of the dominant kernel (the conditional-pdf contraction, sqr_pdf_kernel):
  * enable(1) clears and starts; read() synchronises and returns summed kernel time, launches and their algorithmic flops
@@ -97,6 +116,16 @@ TTIRT_API int ttirt_dirt_sample_device(int64_t nlevels, ttirt_sqr_model *const *
                                        int64_t ldq, double *d_z, int64_t ldz, double *d_lf, void *stream);
 TTIRT_API int ttirt_dirt_sample_host(int64_t nlevels, ttirt_sqr_model *const *models, double sigma, int64_t M, const double *h_q,
                                      double *h_z, double *h_lf, int64_t ld);
+
+/* The inverse of the DIRT, reference matlab/samplers/tt_dirt_inverse.m:24-59: level 0 first, then levels 1..nlvl, each
+ *   [lFapp += sum(q.^2, 2) / 2]  ->  [q, dl] = tt_rt_sqr(x, F{j}, q)  ->  [q = erfinv((q - 0.5) / cdf_factor) sqrt(2)]  ->  lFapp += dl
+ * (bracketed: normal reference only; the reference drops the additive constant of the normal density here, :49, mirrored).
+ * Same model array and sigma as ttirt_dirt_sample_*; x (M x d, points in the target space) in, reference-space q and the
+ * log-density at x out. */
+TTIRT_API int ttirt_dirt_inverse_device(int64_t nlevels, ttirt_sqr_model *const *models, double sigma, int64_t M, const double *d_x,
+                                        int64_t ldx, double *d_q, int64_t ldq, double *d_lf, void *stream);
+TTIRT_API int ttirt_dirt_inverse_host(int64_t nlevels, ttirt_sqr_model *const *models, double sigma, int64_t M, const double *h_x,
+                                      double *h_q, double *h_lf, int64_t ld);
 
 /* tracemult, reference matlab/utils/tracemult.c (real arguments; complex input is not supported), as a standalone operator.
  * Inside tt_irt_sqr both forms are fused into the path's kernels; these serve callers of the MEX itself.

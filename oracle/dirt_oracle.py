@@ -7,9 +7,9 @@ import math
 import re
 
 import numpy as np
-from scipy.special import erf
+from scipy.special import erf, erfinv
 
-from .tt_irt_sqr_oracle import tt_irt_sqr_oracle
+from .tt_irt_sqr_oracle import tt_irt_sqr_oracle, tt_rt_sqr_oracle
 
 
 def parse_reference(reference):
@@ -47,3 +47,25 @@ def tt_dirt_sample_oracle(levels, q, reference="uni"):
     z, dl = tt_irt_sqr_oracle(n, xs, rk, c, z)                               # :71
     lF = lF + dl                                                             # :73
     return z, lF
+
+
+def tt_dirt_inverse_oracle(levels, x, reference="uni"):
+    """[q, lFapp] = tt_dirt_inverse(IRTstruct, x), /root/reference/matlab/samplers/tt_dirt_inverse.m:1-60: the levels walked
+    from level 0 upwards with the forward transform tt_rt_sqr."""
+    sigma = parse_reference(reference)
+    if sigma is not None:
+        cdf_factor = 0.5 / erf(sigma / math.sqrt(2.0))                      # :33
+    n, xs, rk, c = levels[0]
+    q, dl = tt_rt_sqr_oracle(n, xs, rk, c, np.asarray(x, dtype=np.float64))  # :39
+    if sigma is not None:
+        q = erfinv((q - 0.5) / cdf_factor) * math.sqrt(2.0)                 # :42
+    lF = np.zeros(q.shape[0]) + dl                                           # :44
+    for j in range(1, len(levels)):                                          # :47
+        if sigma is not None:
+            lF = lF + np.sum(q ** 2, axis=1) / 2                             # :50
+        n, xs, rk, c = levels[j]
+        q, dl = tt_rt_sqr_oracle(n, xs, rk, c, q)                            # :52
+        if sigma is not None:
+            q = erfinv((q - 0.5) / cdf_factor) * math.sqrt(2.0)             # :55
+        lF = lF + dl                                                         # :57
+    return q, lF

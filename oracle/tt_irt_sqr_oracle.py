@@ -183,6 +183,71 @@ def tt_irt_sqr_oracle(n, xs, ranks, cores, q, extras=False, block=2 ** 11):
     return xq, lF
 
 
+def tt_rt_sqr_oracle(n, xs, ranks, cores, x):
+    """[q, lFapp] = tt_rt_sqr(xsf, f, x): the forward (Rosenblatt) transform, /root/reference/matlab/samplers/tt_rt_sqr.m:1-178.
+    Its sweep (:41-78) and conditional (:100-127) are those of tt_irt_sqr.m; the per-dimension tail differs (:129-166):
+    the cell is found on the grid, the CDF is the quadratic spline evaluated at x_k, nothing is clamped.  x is (M, D)."""
+    sw = sqr_sweep(n, xs, ranks, cores)
+    nn, f, h, P, pos, xsv, rf = sw["n"], sw["f"], sw["h"], sw["P"], sw["pos"], sw["xs"], sw["rf"]
+    d = len(f)
+    x = np.asarray(x, dtype=np.float64)
+    if x.ndim == 1:
+        x = x[:, None]
+    M, D = x.shape
+    D = min(d, D)
+    q = np.zeros((M, D), order="F")
+    lF = np.zeros(M)
+    block = 2 ** 11
+    for start in range(0, M, block):
+        Mb = min(block, M - start)
+        fkm1 = np.ones((1, Mb))
+        for k in range(D):
+            nk = int(nn[k])
+            r0 = int(rf[k])
+            fk = (fkm1[:, None, :] * fkm1[None, :, :]).reshape((r0 * r0, Mb), order="F")      # :103-105
+            fk = fk.T @ P[k]                                                                   # :107
+            Ck = np.zeros_like(fk)
+            Ck[:, 1:] = 0.5 * fk[:, :-1] + 0.5 * fk[:, 1:]                                     # :109-110
+            Ck[:, 0] = 0.5 * fk[:, 0]
+            Ck = np.cumsum(Ck * h[k][None, :], axis=1)                                         # :111-112
+            Cmax = Ck[:, nk - 1].copy()                                                        # :115
+            iz = np.nonzero(Cmax <= 0)[0]
+            if iz.size:                                                                        # :118-122
+                fk[iz, :] = h[k][None, :]
+                Ck[iz, :] = np.cumsum(h[k])[None, :]
+                Cmax[iz] = Ck[iz, nk - 1]
+            Ck = Ck / Cmax[:, None]                                                            # :124-125
+            fk = fk / Cmax[:, None]
+            xk = x[start:start + Mb, k]                                                        # :129
+            grid = xsv[pos[k]:pos[k] + nk]
+            i0 = np.zeros(Mb, dtype=np.int64)
+            i2 = np.full(Mb, nk - 1, dtype=np.int64)
+            while np.any(i2 - i0 > 1):                                                         # :132-138
+                i1 = (i0 + i2) // 2
+                left = xk > grid[i1]
+                i0 = np.where(left, i1, i0)
+                i2 = np.where(~left, i1, i2)
+            ar = np.arange(Mb)
+            C1 = Ck[ar, i0]                                                                    # :141-143
+            f1 = fk[ar, i0]
+            f2 = fk[ar, i0 + 1]
+            x1 = grid[i0]                                                                      # :145-147
+            x2 = grid[i0 + 1]
+            h3 = x2 - x1
+            Aq = 0.5 * (f2 - f1) / h3                                                          # :150
+            q[start:start + Mb, k] = Aq * (xk - x1) ** 2 + f1 * (xk - x1) + C1                 # :151
+            wA = (x2 - xk) / h3                                                                # :156-157
+            wB = (xk - x1) / h3
+            with np.errstate(divide="ignore", invalid="ignore"):
+                lF[start:start + Mb] += np.log(f1 * wA + f2 * wB)                              # :162-163
+            if k < d - 1:                                                                      # :166-177
+                core = f[k]
+                t0 = np.einsum("am,amb->bm", fkm1, core[:, i0, :])
+                t1 = np.einsum("am,amb->bm", fkm1, core[:, i0 + 1, :])
+                fkm1 = t0 * wA[None, :] + t1 * wB[None, :]
+    return q, lF
+
+
 def tracemult_oracle(A, j, B=None):
     """matlab/utils/tracemult.c, real case: C(:,:,i) = A(:,:,i) * B(:,:,j(i)) (:103-112) or C(i) = A(i, j(i)) (:131-136);
     j one-based as the MEX takes it (:106-107)."""

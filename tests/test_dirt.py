@@ -7,7 +7,7 @@ amplified by the next level's inverse-CDF slope 1 / p (up to ~1e3 in the tails).
 import numpy as np
 import pytest
 
-from oracle.dirt_oracle import parse_reference, tt_dirt_sample_oracle
+from oracle.dirt_oracle import parse_reference, tt_dirt_inverse_oracle, tt_dirt_sample_oracle
 from oracle.tt_irt_sqr_oracle import tt_irt_sqr_oracle
 from tt_irt_py import synth, tt_irt
 
@@ -98,3 +98,54 @@ def test_device_loop_matches_the_oracle(d, n, r, nlvl, reference, M):
     z3, lF3 = tt_irt_sqr.tt_dirt_sample(st, q)
     np.testing.assert_array_equal(z3, z)
     np.testing.assert_array_equal(lF3, lF)
+
+
+@pytest.mark.parametrize("reference", ["uni", "Normal 3"])
+def test_oracle_inverse_undoes_the_sampler(reference):
+    """tt_dirt_inverse(tt_dirt_sample(q)) = q; the log-densities agree up to the additive constant the reference drops
+    (tt_dirt_inverse.m:49: nlvl d log(2 cdf_factor^2 / pi) / 2)."""
+    import math
+    from scipy.special import erf
+    d, nlvl = 4, 2
+    lv = make_levels(d, 17, 5, nlvl, reference, seed=7)
+    q = make_seeds(500, d, reference)
+    z, lf = tt_dirt_sample_oracle(lv, q, reference)
+    qb, lb = tt_dirt_inverse_oracle(lv, z, reference)
+    assert np.median(np.abs(qb - q)) < 1e-11 and np.abs(qb - q).max() < 1e-6
+    sigma = parse_reference(reference)
+    const = 0.0 if sigma is None else nlvl * math.log(2 * (0.5 / erf(sigma / math.sqrt(2))) ** 2 / math.pi) * d / 2
+    assert np.median(np.abs((lb - lf) - const)) < 1e-10
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("d,n,r,nlvl,reference,M", [(4, 17, 6, 0, "uni", 3000), (4, 17, 6, 2, "uni", 3000), (6, 17, 8, 3, "Normal 4", 4000),
+                                                     (3, 33, 12, 1, "Normal 2.5", 2500)])
+def test_device_inverse_matches_the_oracle_and_round_trips(d, n, r, nlvl, reference, M):
+    from tt_irt_py import tt_irt_sqr
+    if tt_irt.device_count() < 1:
+        pytest.fail("no CUDA device: the -m gpu tests need a B200 (there is no CPU fallback)")
+    lv = make_levels(d, n, r, nlvl, reference, seed=20 + d)
+    q = make_seeds(M, d, reference)
+    zo, lo = tt_dirt_sample_oracle(lv, q, reference)
+    qo, lbo = tt_dirt_inverse_oracle(lv, zo, reference)
+    drt = tt_irt_sqr.Dirt(lv, reference)
+    try:
+        qb, lb = drt.inverse(zo)                      # same input as the oracle
+        z, lf = drt.sample(q)
+        qr, lr = drt.inverse(z)                       # device round trip
+    finally:
+        drt.close()
+    # Conditioning: with a normal reference every level ends in erfinv (slope 1 / phi(q), 10^3 at |q| = 3.6) and these synthetic
+    # levels are not the near-identity maps of a fitted DIRT, so the composition amplifies rounding by many orders of
+    # magnitude.  The yardstick is the oracle's own response to a one-ulp-class relative perturbation of its input.
+    rng = np.random.default_rng(0)
+    qp, lp = tt_dirt_inverse_oracle(lv, zo * (1.0 + 1e-15 * rng.standard_normal(zo.shape)), reference)
+    sq, sl = np.abs(qp - qo), np.abs(lp - lbo)
+    dq, dl = np.abs(qb - qo), np.abs(lb - lbo)
+    for (e, s_) in ((dq, sq), (dl, sl)):
+        assert np.median(e) <= 10 * np.median(s_) + 1e-12, (np.median(e), np.median(s_))
+        assert np.quantile(e, 0.9) <= 10 * np.quantile(s_, 0.9) + 1e-10
+        assert e.max() <= 100 * s_.max() + 1e-8
+    dr = np.abs(qr - q)
+    so = np.abs(qo - q)                                   # the oracle's own round-trip error
+    assert np.median(dr) <= 10 * np.median(so) + 1e-12 and dr.max() <= 100 * so.max() + 1e-8, (np.median(dr), dr.max())

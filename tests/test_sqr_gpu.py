@@ -14,7 +14,7 @@ import numpy as np
 import pytest
 
 from oracle import parity
-from oracle.tt_irt_sqr_oracle import sqr_sweep, tt_irt_sqr_oracle, tracemult_oracle
+from oracle.tt_irt_sqr_oracle import sqr_sweep, tt_irt_sqr_oracle, tt_rt_sqr_oracle, tracemult_oracle
 from test_sqr_oracle import GOLD, load_sqr_golden, mk
 from tt_irt_py import synth, tt_irt, tt_irt_sqr
 
@@ -241,3 +241,43 @@ def test_edge_seeds_and_zero_mass_fallback():
         fin = np.isfinite(lo)
         np.testing.assert_allclose(lF[fin], lo[fin], rtol=0, atol=1e-11)
         np.testing.assert_array_equal(lF[~fin], lo[~fin])
+
+
+@pytest.mark.parametrize("d,n,r,M,ext,D", [(4, 9, 4, 1000, False, None), (8, 17, 8, 3000, False, None), (5, 15, 6, 1500, True, None),
+                                           (6, 33, 32, 1500, False, 4), (4, 65, 64, 1024, False, None), (5, 12, 40, 1200, False, None)])
+def test_forward_transform_matches_the_oracle(d, n, r, M, ext, D):
+    """tt_rt_sqr (reference matlab/samplers/tt_rt_sqr.m): CDF values to 1e-12 absolute (they live in [0, 1] and are sums of
+    the same conditionals), cells equal, log-density to 1e-12 relative + the conditional's own conditioning."""
+    ns, xs, rk, c = mk.make_case(d, n, r, 300 + d + n + r, -1.0, 1.0, "uniform", "uniform", ext)
+    D = d if D is None else D
+    q = synth.make_q(M, D, seed=11)
+    X, _ = tt_irt_sqr_oracle(ns, xs, rk, c, q)           # points inside the support
+    Qo, lo = tt_rt_sqr_oracle(ns, xs, rk, c, X)
+    md = tt_irt_sqr.SqrModel(ns, xs, rk, c)
+    try:
+        Q, lF, idx = md.forward(X, want_idx=True)
+        Z, lz = md.sample(q)
+        Q2, l2 = md.forward(Z)                          # device round trip
+    finally:
+        md.close()
+    assert np.abs(Q - Qo).max() <= 1e-12, np.abs(Q - Qo).max()
+    assert np.abs(lF - lo).max() <= 1e-11 * max(1.0, np.abs(lo).max())
+    assert np.abs(Q2 - q).max() <= 1e-11 and np.abs(l2 - lz).max() <= 1e-11 * max(1.0, np.abs(lz).max())
+    Qc, lc = tt_irt_sqr.tt_rt_sqr(xs, tt_irt.TTTensor(ns, rk, c), X)      # the C symbol through the Python mirror
+    np.testing.assert_array_equal(Qc, Q)
+    np.testing.assert_array_equal(lc, lF)
+
+
+def test_round_trip_at_full_size():
+    """Encode -> decode at a size the oracle cannot walk: tt_rt_sqr(tt_irt_sqr(q)) = q for 2^17 seeds."""
+    d, n, r, M = 6, 33, 32, 1 << 17
+    ns, xs, rk, c = synth.make_tt(d, n, r, seed=19, lo=-3.0, hi=3.0)
+    q = synth.make_q(M, d, seed=23)
+    md = tt_irt_sqr.SqrModel(ns, xs, rk, c)
+    try:
+        Z, lF = md.sample(q)
+        Q, l2 = md.forward(Z)
+    finally:
+        md.close()
+    assert np.abs(Q - q).max() <= 1e-10 and np.median(np.abs(Q - q)) <= 1e-14
+    assert np.abs(l2 - lF).max() <= 1e-10 * max(1.0, np.abs(lF).max())

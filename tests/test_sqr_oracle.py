@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from oracle.tt_irt_sqr_oracle import sqr_sweep, tt_irt_sqr_oracle, split_cores, tracemult_oracle
+from oracle.tt_irt_sqr_oracle import sqr_sweep, tt_irt_sqr_oracle, tt_rt_sqr_oracle, split_cores, tracemult_oracle
 from tt_irt_py import synth
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -237,3 +237,36 @@ def test_sweep_pinned_by_the_reference_c_routine_through_the_first_coordinate():
     Zr, lr = _reference_tt_irt1(ns, xs, rk2, c2, q)
     np.testing.assert_allclose(Zs[:, 0], Zr[:, 0], rtol=0, atol=1e-10)
     assert np.median(np.abs(Zs[:, 0] - Zr[:, 0])) < 1e-13
+
+
+def test_forward_transform_inverts_the_inverse_transform():
+    """tt_rt_sqr(tt_irt_sqr(q)) = q with the same log-density (the two reference routines share sweep and conditionals)."""
+    for (d, n, r, cores, grid) in [(5, 17, 6, "uniform", "uniform"), (4, 12, 5, "normal", "chebyshev")]:
+        ns, xs, rk, c = synth.make_tt(d, n, r, seed=3, cores=cores, grid=grid)
+        q = synth.make_q(800, d, seed=4)
+        Z, l = tt_irt_sqr_oracle(ns, xs, rk, c, q)
+        q2, l2 = tt_rt_sqr_oracle(ns, xs, rk, c, Z)
+        assert np.abs(q2 - q).max() < (1e-12 if cores == "uniform" else 1e-9)
+        assert np.abs(l2 - l).max() < (1e-12 if cores == "uniform" else 1e-8)
+    # marginal and boundary-less cores go through the same code path
+    ns, xs, rk, c = mk.make_case(4, 8, 3, 21, -1.0, 1.0, "uniform", "uniform", True)
+    q = synth.make_q(200, 2, seed=6)
+    Z, l = tt_irt_sqr_oracle(ns, xs, rk, c, q)
+    q2, l2 = tt_rt_sqr_oracle(ns, xs, rk, c, Z)
+    assert q2.shape == (200, 2) and np.abs(q2 - q).max() < 1e-12 and np.abs(l2 - l).max() < 1e-12
+
+
+def test_forward_transform_pinned_by_the_reference_c_routine_at_grid_nodes():
+    """At a grid node x_j the forward transform returns the conditional CDF node value; for a separable density that is
+    the normalised trapezoid sum the reference C tt_irt1 inverts, so feeding those q to the live reference returns x_j."""
+    d, n = 3, 9
+    rng = np.random.default_rng(5)
+    f = [rng.random(n) + 0.2 for _ in range(d)]
+    grids = [np.sort(rng.random(n)) * 2 - 1 for _ in range(d)]
+    xs = np.concatenate(grids)
+    ns, rk = np.full(d, n), np.ones(d + 1, dtype=np.int64)
+    pts = np.asfortranarray(np.stack([g[rng.integers(1, n - 1, 300)] for g in grids], axis=1))
+    qn, ln = tt_rt_sqr_oracle(ns, xs, rk, np.concatenate(f), pts)
+    Zr, lr = _reference_tt_irt1(ns, xs, rk, np.concatenate([v ** 2 for v in f]), qn)
+    np.testing.assert_allclose(Zr, pts, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(lr, ln, rtol=0, atol=1e-8)

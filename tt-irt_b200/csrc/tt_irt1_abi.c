@@ -67,27 +67,28 @@ void tt_irt1(TTIRT_INT d, TTIRT_INT *n, double *xs, TTIRT_INT *ttrank, double *t
 }
 
 /*
- * The squared-density transform, reference matlab/samplers/tt_irt_sqr.m:1 ([xq, lFapp] = tt_irt_sqr(xsf, f, q)).
- * Matlab-only in the reference; this is the C entry point a MEX gateway binds.
+ * The squared-density transforms, reference matlab/samplers/tt_irt_sqr.m:1 ([xq, lFapp] = tt_irt_sqr(xsf, f, q)) and
+ * matlab/samplers/tt_rt_sqr.m:1 ([q, lFapp] = tt_rt_sqr(xsf, f, x)).  Matlab-only in the reference; these are the C entry
+ * points a MEX gateway binds.
  */
-void tt_irt_sqr(TTIRT_INT d, TTIRT_INT *n, TTIRT_INT nxs, double *xs, TTIRT_INT *ttrank, double *ttcore, TTIRT_INT M,
-                TTIRT_INT D, double *q, double *z, double *lFapp) {
+static void sqr_entry(const char *name, int forward, TTIRT_INT d, TTIRT_INT *n, TTIRT_INT nxs, double *xs, TTIRT_INT *ttrank,
+                      double *ttcore, TTIRT_INT M, TTIRT_INT D, double *in, double *out, double *lFapp) {
   int64_t *n64, *r64, k;
   int first = 0, ndev = 1, rc;
   const char *e;
 
-  if (d < 1 || M < 0 || D < 1 || D > d || !n || !xs || !ttrank || !ttcore || (M > 0 && (!q || !z || !lFapp))) {
-    fprintf(stderr, "tt_irt_sqr[b200]: invalid arguments\n");
-    if (D >= 1 && M > 0) { nan_fill(z, (int64_t)M * D); nan_fill(lFapp, M); }
+  if (d < 1 || M < 0 || D < 1 || D > d || !n || !xs || !ttrank || !ttcore || (M > 0 && (!in || !out || !lFapp))) {
+    fprintf(stderr, "%s[b200]: invalid arguments\n", name);
+    if (D >= 1 && M > 0) { nan_fill(out, (int64_t)M * D); nan_fill(lFapp, M); }
     return;
   }
   if (M == 0) return;
   n64 = (int64_t *)malloc(sizeof(int64_t) * (size_t)d);
   r64 = (int64_t *)malloc(sizeof(int64_t) * ((size_t)d + 1));
   if (!n64 || !r64) {
-    fprintf(stderr, "tt_irt_sqr[b200]: out of host memory\n");
+    fprintf(stderr, "%s[b200]: out of host memory\n", name);
     free(n64); free(r64);
-    nan_fill(z, (int64_t)M * D); nan_fill(lFapp, M);
+    nan_fill(out, (int64_t)M * D); nan_fill(lFapp, M);
     return;
   }
   for (k = 0; k < d; k++) n64[k] = (int64_t)n[k];
@@ -99,11 +100,22 @@ void tt_irt_sqr(TTIRT_INT d, TTIRT_INT *n, TTIRT_INT nxs, double *xs, TTIRT_INT 
     if (ndev < 1) ndev = 1;
   }
   while (ndev > 1 && (int64_t)M / ndev < 128) ndev--;   /* never more devices than 128-sample tiles */
-  rc = ttirt_sqr_run_host(d, n64, (int64_t)nxs, xs, r64, ttcore, M, D, q, z, lFapp, first, ndev);
+  rc = forward ? ttirt_sqr_run_forward_host(d, n64, (int64_t)nxs, xs, r64, ttcore, M, D, in, out, lFapp, first, ndev)
+               : ttirt_sqr_run_host(d, n64, (int64_t)nxs, xs, r64, ttcore, M, D, in, out, lFapp, first, ndev);
   if (rc != 0) {
-    nan_fill(z, (int64_t)M * D);
+    nan_fill(out, (int64_t)M * D);
     nan_fill(lFapp, M);
   }
   free(n64);
   free(r64);
+}
+
+void tt_irt_sqr(TTIRT_INT d, TTIRT_INT *n, TTIRT_INT nxs, double *xs, TTIRT_INT *ttrank, double *ttcore, TTIRT_INT M,
+                TTIRT_INT D, double *q, double *z, double *lFapp) {
+  sqr_entry("tt_irt_sqr", 0, d, n, nxs, xs, ttrank, ttcore, M, D, q, z, lFapp);
+}
+
+void tt_rt_sqr(TTIRT_INT d, TTIRT_INT *n, TTIRT_INT nxs, double *xs, TTIRT_INT *ttrank, double *ttcore, TTIRT_INT M,
+               TTIRT_INT D, double *x, double *q, double *lFapp) {
+  sqr_entry("tt_rt_sqr", 1, d, n, nxs, xs, ttrank, ttcore, M, D, x, q, lFapp);
 }

@@ -539,6 +539,7 @@ struct TailArgs {
   const double *q; double *z; int32_t *idx_out;
   int *idx; double *w1, *w2; double *lf;
   int first;        // dimension 0: lFapp starts here (:91)
+  int forward;      // 0: inverse transform (tt_irt_sqr.m: q -> x), 1: forward transform (tt_rt_sqr.m: x -> q)
   int *hist;        // n - 1 counters for the sort by interval, or NULL when no interface update follows
 };
 
@@ -568,12 +569,19 @@ __global__ void __launch_bounds__(256) sqr_tail_kernel(TailArgs a) {
     double cmax = c;                                           // :120
     const bool zero = cmax <= 0.0;                             // :121-127: conditional replaced by h, CDF by cumsum(h)
     if (zero) cmax = a.hc[n - 1];
-    const double qk = a.q[m];
+    const double qk = a.q[m];                                  // the seed (inverse) or the point (forward, tt_rt_sqr.m:129)
     int i0 = 0, i2 = n - 1;                                    // :135-143
-    while (i2 - i0 > 1) {
-      const int i1 = (i0 + i2) >> 1;
-      const double c1 = __ddiv_rn(zero ? a.hc[i1] : cd[(size_t)i1 * a.ldp], cmax);
-      if (qk > c1) i0 = i1; else i2 = i1;
+    if (a.forward) {
+      while (i2 - i0 > 1) {                                    // tt_rt_sqr.m:132-138: the cell is found on the grid
+        const int i1 = (i0 + i2) >> 1;
+        if (qk > a.x[i1]) i0 = i1; else i2 = i1;
+      }
+    } else {
+      while (i2 - i0 > 1) {
+        const int i1 = (i0 + i2) >> 1;
+        const double c1 = __ddiv_rn(zero ? a.hc[i1] : cd[(size_t)i1 * a.ldp], cmax);
+        if (qk > c1) i0 = i1; else i2 = i1;
+      }
     }
     const double C1 = __ddiv_rn(zero ? a.hc[i0] : cd[(size_t)i0 * a.ldp], cmax);                 // :146-149, :129-130
     const double f1 = __ddiv_rn(zero ? a.h[i0] : p[(size_t)i0 * a.ldp], cmax);
@@ -581,16 +589,24 @@ __global__ void __launch_bounds__(256) sqr_tail_kernel(TailArgs a) {
     const double x1 = a.x[i0], x2 = a.x[i0 + 1];                                                  // :157-159
     const double h3 = __dsub_rn(x2, x1);
     const double Aq = __ddiv_rn(__dmul_rn(0.5, __dsub_rn(f2, f1)), h3);                          // :161
-    const double dq = __dsub_rn(qk, C1);
-    const double Dq = __dadd_rn(__dmul_rn(f1, f1), __dmul_rn(__dmul_rn(4.0, Aq), dq));           // :162
-    double xk = __dadd_rn(x1, __ddiv_rn(__dadd_rn(-f1, __dsqrt_rn(fabs(Dq))), __dmul_rn(2.0, Aq)));   // :163
-    if (Aq == 0.0) {                                                                              // :164-170
-      xk = __dadd_rn(x1, __ddiv_rn(dq, f1));
-      if (f1 == 0.0) xk = x1;
+    double xk, out;
+    if (a.forward) {
+      xk = qk;
+      const double dx = __dsub_rn(xk, x1);
+      out = __dadd_rn(__dadd_rn(__dmul_rn(Aq, __dmul_rn(dx, dx)), __dmul_rn(f1, dx)), C1);       // tt_rt_sqr.m:151
+    } else {
+      const double dq = __dsub_rn(qk, C1);
+      const double Dq = __dadd_rn(__dmul_rn(f1, f1), __dmul_rn(__dmul_rn(4.0, Aq), dq));         // :162
+      xk = __dadd_rn(x1, __ddiv_rn(__dadd_rn(-f1, __dsqrt_rn(fabs(Dq))), __dmul_rn(2.0, Aq)));   // :163
+      if (Aq == 0.0) {                                                                            // :164-170
+        xk = __dadd_rn(x1, __ddiv_rn(dq, f1));
+        if (f1 == 0.0) xk = x1;
+      }
+      if (xk > x2) xk = x2;                                                                       // :173-182
+      if (xk < x1) xk = x1;
+      out = xk;
     }
-    if (xk > x2) xk = x2;                                                                         // :173-182
-    if (xk < x1) xk = x1;
-    a.z[m] = xk;                                                                                  // :184
+    a.z[m] = out;                                                                                 // :184 / tt_rt_sqr.m:153
     const double wa = __ddiv_rn(__dsub_rn(x2, xk), h3), wb = __ddiv_rn(__dsub_rn(xk, x1), h3);    // :187-188
     const double dens = __dadd_rn(__dmul_rn(f1, wa), __dmul_rn(f2, wb));                          // :193
     const double lg = log(dens);                                                                  // :194
@@ -787,6 +803,28 @@ __global__ void dirt_accumulate_kernel(int64_t M, int d, int first, int normal, 
     v = __dsub_rn(__dadd_rn(v, __ddiv_rn(s, 2.0)), logc_half_d);
   }
   lf[m] = v;
+}
+
+// tt_dirt_inverse.m:42,55  uniform -> truncated normal:  q = erfinv((q - 0.5) / cdf_factor) * sqrt(2)   (in place)
+__global__ void dirt_u2tn_kernel(int64_t M, int d, double cdf_factor, double *q, int64_t ldq) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y;
+  if (m >= M || k >= d) return;
+  q[m + ldq * k] = __dmul_rn(erfinv(__ddiv_rn(__dsub_rn(q[m + ldq * k], 0.5), cdf_factor)), 1.4142135623730951);
+}
+
+// tt_dirt_inverse.m:44,50,57  lFapp = lFapp [+ sum(q.^2, 2) / 2 of the level's input] + dlFapp
+__global__ void dirt_inverse_accumulate_kernel(int64_t M, int d, int first, int normal, const double *__restrict__ dlf,
+                                               const double *__restrict__ qin, int64_t ldq, double *lf) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  double v = first ? 0.0 : lf[m];
+  if (normal) {
+    double s = 0.0;
+    for (int k = 0; k < d; k++) { const double t = qin[m + ldq * k]; s = __dadd_rn(s, __dmul_rn(t, t)); }
+    v = __dadd_rn(v, __ddiv_rn(s, 2.0));
+  }
+  lf[m] = __dadd_rn(v, dlf[m]);
 }
 
 __global__ void sqr_fill_nan_kernel(double *p, int64_t n) {
@@ -1131,7 +1169,7 @@ extern "C" int ttirt_sqr_model_get_sweep(const ttirt_sqr_model *md, int64_t k, d
 // one chunk, device-resident buffers, enqueued on st
 // ------------------------------------------------------------------------------------------------
 static int sqr_enqueue_chunk(ttirt_sqr_model *md, int64_t rows, int64_t D, const double *q, int64_t ldq, double *z, int64_t ldz,
-                             double *lf, int32_t *idx_out, cudaStream_t st) {
+                             double *lf, int32_t *idx_out, cudaStream_t st, int forward = 0) {
   if (rows <= 0) return 0;
   const int d = (int)md->d;
   CKS(cudaMemsetAsync(md->hist, 0, sizeof(int) * d * md->nbpad, st));
@@ -1169,7 +1207,7 @@ static int sqr_enqueue_chunk(ttirt_sqr_model *md, int64_t rows, int64_t D, const
     ta.pdf = md->pdf; ta.cdf = md->cdf; ta.ldp = md->cap; ta.rows = (int)rows; ta.n = di.n;
     ta.x = md->d_xs + di.off_x; ta.h = md->d_h + di.off_x; ta.hc = md->d_hc + di.off_x;
     ta.q = q + ldq * k; ta.z = z + ldz * k; ta.idx_out = idx_out ? idx_out + ldz * k : nullptr;
-    ta.idx = md->idx; ta.w1 = md->w1; ta.w2 = md->w2; ta.lf = lf; ta.first = (k == 0);
+    ta.idx = md->idx; ta.w1 = md->w1; ta.w2 = md->w2; ta.lf = lf; ta.first = (k == 0); ta.forward = forward;
     ta.hist = update ? md->hist + (size_t)k * md->nbpad : nullptr;
     sqr_tail_kernel<<<(unsigned)((rows + 255) / 256), 256, sizeof(int) * di.n, st>>>(ta);
     LAUNCHED();
@@ -1205,8 +1243,8 @@ static int64_t sqr_chunk() {
   return (int64_t)1 << 18;
 }
 
-extern "C" int ttirt_sqr_sample_device(ttirt_sqr_model *md, int64_t M, int64_t D, const double *d_q, int64_t ldq, double *d_z,
-                                       int64_t ldz, double *d_lf, int32_t *d_idx, void *stream) {
+static int sqr_transform_device(ttirt_sqr_model *md, int64_t M, int64_t D, const double *d_q, int64_t ldq, double *d_z,
+                                int64_t ldz, double *d_lf, int32_t *d_idx, void *stream, int forward) {
   if (!md) return aux_fail("null model");
   if (M < 0 || ldq < M || ldz < M) return aux_fail("bad M / leading dimensions");
   if (D < 1 || D > md->d) return aux_fail("tt_irt_sqr: q must have between 1 and d columns (got %lld, d = %lld)", (long long)D, (long long)md->d);
@@ -1220,13 +1258,23 @@ extern "C" int ttirt_sqr_sample_device(ttirt_sqr_model *md, int64_t M, int64_t D
   }
   for (int64_t m0 = 0; m0 < M; m0 += chunk) {
     const int64_t rows = std::min(chunk, M - m0);
-    if (sqr_enqueue_chunk(md, rows, D, d_q + m0, ldq, d_z + m0, ldz, d_lf + m0, d_idx ? d_idx + m0 : nullptr, st) != 0) return -1;
+    if (sqr_enqueue_chunk(md, rows, D, d_q + m0, ldq, d_z + m0, ldz, d_lf + m0, d_idx ? d_idx + m0 : nullptr, st, forward) != 0) return -1;
   }
   return 0;
 }
 
-extern "C" int ttirt_sqr_sample_host(ttirt_sqr_model *md, int64_t M, int64_t D, const double *h_q, double *h_z, double *h_lf,
-                                     int32_t *h_idx, int64_t ld) {
+extern "C" int ttirt_sqr_sample_device(ttirt_sqr_model *md, int64_t M, int64_t D, const double *d_q, int64_t ldq, double *d_z,
+                                       int64_t ldz, double *d_lf, int32_t *d_idx, void *stream) {
+  return sqr_transform_device(md, M, D, d_q, ldq, d_z, ldz, d_lf, d_idx, stream, 0);
+}
+
+extern "C" int ttirt_sqr_forward_device(ttirt_sqr_model *md, int64_t M, int64_t D, const double *d_x, int64_t ldx, double *d_q,
+                                        int64_t ldq, double *d_lf, int32_t *d_idx, void *stream) {
+  return sqr_transform_device(md, M, D, d_x, ldx, d_q, ldq, d_lf, d_idx, stream, 1);
+}
+
+static int sqr_transform_host(ttirt_sqr_model *md, int64_t M, int64_t D, const double *h_q, double *h_z, double *h_lf,
+                              int32_t *h_idx, int64_t ld, int forward) {
   if (!md) return aux_fail("null model");
   if (M < 0 || ld < M) return aux_fail("bad M / leading dimension");
   if (D < 1 || D > md->d) return aux_fail("tt_irt_sqr: q must have between 1 and d columns (got %lld, d = %lld)", (long long)D, (long long)md->d);
@@ -1258,7 +1306,7 @@ extern "C" int ttirt_sqr_sample_host(ttirt_sqr_model *md, int64_t M, int64_t D, 
     CKS(cudaEventRecord(md->ev_in[s], cs));
     CKS(cudaStreamWaitEvent(st, md->ev_in[s], 0));
     if (i >= 2) CKS(cudaStreamWaitEvent(st, md->ev_out[s], 0));
-    if (sqr_enqueue_chunk(md, rows, D, md->q[s], cap, md->z[s], cap, md->lf[s], h_idx ? md->idx_out[s] : nullptr, st) != 0) return -1;
+    if (sqr_enqueue_chunk(md, rows, D, md->q[s], cap, md->z[s], cap, md->lf[s], h_idx ? md->idx_out[s] : nullptr, st, forward) != 0) return -1;
     CKS(cudaEventRecord(md->ev_done[s], st));
     if (i >= 1 && copy_out(i - 1) != 0) return -1;
   }
@@ -1268,17 +1316,27 @@ extern "C" int ttirt_sqr_sample_host(ttirt_sqr_model *md, int64_t M, int64_t D, 
   return 0;
 }
 
+extern "C" int ttirt_sqr_sample_host(ttirt_sqr_model *md, int64_t M, int64_t D, const double *h_q, double *h_z, double *h_lf,
+                                     int32_t *h_idx, int64_t ld) {
+  return sqr_transform_host(md, M, D, h_q, h_z, h_lf, h_idx, ld, 0);
+}
+
+extern "C" int ttirt_sqr_forward_host(ttirt_sqr_model *md, int64_t M, int64_t D, const double *h_x, double *h_q, double *h_lf,
+                                      int32_t *h_idx, int64_t ld) {
+  return sqr_transform_host(md, M, D, h_x, h_q, h_lf, h_idx, ld, 1);
+}
+
 // Whole call on host buffers.  Samples are independent (tt_irt_sqr.m:94-208 walks them in blocks), so the M rows are cut
 // into contiguous ranges, one per device; every device gets its own copy of the cores and redoes the (small) sweep; no
 // collective.  One host thread per device, joined before returning.
 static int sqr_run_rows(int device, int64_t d, const int64_t *n, int64_t nxs, const double *xs, const int64_t *ttrank,
-                        const double *ttcore, int64_t rows, int64_t D, const double *h_q, double *h_z, double *h_lf, int64_t ld) {
+                        const double *ttcore, int64_t rows, int64_t D, const double *h_q, double *h_z, double *h_lf, int64_t ld, int forward) {
   const bool trace = getenv("TTIRT_TRACE") != nullptr;
   const auto t0 = std::chrono::steady_clock::now();
   ttirt_sqr_model *md = ttirt_sqr_model_create(d, n, nxs, xs, ttrank, ttcore, device);
   if (!md) return -1;
   const auto t1 = std::chrono::steady_clock::now();
-  const int rc = ttirt_sqr_sample_host(md, rows, D, h_q, h_z, h_lf, nullptr, ld);
+  const int rc = sqr_transform_host(md, rows, D, h_q, h_z, h_lf, nullptr, ld, forward);
   const auto t2 = std::chrono::steady_clock::now();
   ttirt_sqr_model_destroy(md);
   if (trace) {
@@ -1290,25 +1348,36 @@ static int sqr_run_rows(int device, int64_t d, const int64_t *n, int64_t nxs, co
   return rc;
 }
 
-extern "C" int ttirt_sqr_run_host(int64_t d, const int64_t *n, int64_t nxs, const double *xs, const int64_t *ttrank, const double *ttcore,
-                                  int64_t M, int64_t D, const double *h_q, double *h_z, double *h_lf, int first_device, int n_devices) {
+static int sqr_run_host(int64_t d, const int64_t *n, int64_t nxs, const double *xs, const int64_t *ttrank, const double *ttcore,
+                        int64_t M, int64_t D, const double *h_q, double *h_z, double *h_lf, int first_device, int n_devices, int forward) {
   if (M <= 0) return M == 0 ? 0 : aux_fail("negative M");
   const int cnt = ttirt_device_count();
   if (cnt <= 0) return aux_fail("no CUDA device available (this library has no CPU fallback)");
   if (n_devices < 1) n_devices = 1;
   if (first_device < 0 || first_device + n_devices > cnt) return aux_fail("devices %d..%d requested, %d visible", first_device, first_device + n_devices - 1, cnt);
-  if (n_devices == 1) return sqr_run_rows(first_device, d, n, nxs, xs, ttrank, ttcore, M, D, h_q, h_z, h_lf, M);
+  if (n_devices == 1) return sqr_run_rows(first_device, d, n, nxs, xs, ttrank, ttcore, M, D, h_q, h_z, h_lf, M, forward);
   std::vector<std::thread> th;
   std::vector<int> rc((size_t)n_devices, 0);
   for (int g = 0; g < n_devices; g++) {
     const int64_t m0 = M * g / n_devices, m1 = M * (g + 1) / n_devices;
     th.emplace_back([=, &rc]() {
-      rc[(size_t)g] = m1 > m0 ? sqr_run_rows(first_device + g, d, n, nxs, xs, ttrank, ttcore, m1 - m0, D, h_q + m0, h_z + m0, h_lf + m0, M) : 0;
+      rc[(size_t)g] = m1 > m0 ? sqr_run_rows(first_device + g, d, n, nxs, xs, ttrank, ttcore, m1 - m0, D, h_q + m0, h_z + m0, h_lf + m0, M, forward) : 0;
     });
   }
   for (auto &t : th) t.join();
   for (int g = 0; g < n_devices; g++) if (rc[(size_t)g] != 0) return -1;
   return 0;
+}
+
+extern "C" int ttirt_sqr_run_host(int64_t d, const int64_t *n, int64_t nxs, const double *xs, const int64_t *ttrank, const double *ttcore,
+                                  int64_t M, int64_t D, const double *h_q, double *h_z, double *h_lf, int first_device, int n_devices) {
+  return sqr_run_host(d, n, nxs, xs, ttrank, ttcore, M, D, h_q, h_z, h_lf, first_device, n_devices, 0);
+}
+
+extern "C" int ttirt_sqr_run_forward_host(int64_t d, const int64_t *n, int64_t nxs, const double *xs, const int64_t *ttrank,
+                                          const double *ttcore, int64_t M, int64_t D, const double *h_x, double *h_q, double *h_lf,
+                                          int first_device, int n_devices) {
+  return sqr_run_host(d, n, nxs, xs, ttrank, ttcore, M, D, h_x, h_q, h_lf, first_device, n_devices, 1);
 }
 
 extern "C" void ttirt_sqr_profile_enable(ttirt_sqr_model *md, int on) {
@@ -1414,5 +1483,84 @@ extern "C" int ttirt_dirt_sample_host(int64_t nlevels, ttirt_sqr_model *const *m
   }
   cudaStreamSynchronize(st);
   sqr_free(dq); sqr_free(dz); sqr_free(dl);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// inverse of the DIRT (reference matlab/samplers/tt_dirt_inverse.m:24-59): the levels from 0 upwards with tt_rt_sqr
+// ------------------------------------------------------------------------------------------------
+extern "C" int ttirt_dirt_inverse_device(int64_t nlevels, ttirt_sqr_model *const *models, double sigma, int64_t M, const double *d_x,
+                                         int64_t ldx, double *d_q, int64_t ldq, double *d_lf, void *stream) {
+  if (nlevels < 1 || !models) return aux_fail("ttirt_dirt_inverse: need at least the level-0 model");
+  for (int64_t j = 0; j < nlevels; j++) {
+    if (!models[j]) return aux_fail("ttirt_dirt_inverse: null model at level %lld", (long long)j);
+    if (models[j]->d != models[0]->d || models[j]->device != models[0]->device)
+      return aux_fail("ttirt_dirt_inverse: all levels must have the same dimension and live on the same device");
+  }
+  if (M < 0 || ldx < M || ldq < M) return aux_fail("bad M / leading dimensions");
+  if (M == 0) return 0;
+  ttirt_sqr_model *m0 = models[0];
+  const int d = (int)m0->d;
+  CKS(cudaSetDevice(m0->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (m0->dirt_cap < M) {
+    CKS(cudaStreamSynchronize(st));
+    sqr_free(m0->dirt_z[0]); sqr_free(m0->dirt_z[1]); sqr_free(m0->dirt_lf);
+    m0->dirt_z[0] = m0->dirt_z[1] = m0->dirt_lf = nullptr; m0->dirt_cap = 0;
+    CKS(sqr_alloc(&m0->dirt_z[0], sizeof(double) * M * d));
+    CKS(sqr_alloc(&m0->dirt_z[1], sizeof(double) * M * d));
+    CKS(sqr_alloc(&m0->dirt_lf, sizeof(double) * M));
+    m0->dirt_cap = M;
+  }
+  const bool normal = sigma > 0.0;
+  const double cdf_factor = normal ? 0.5 / erf(sigma / sqrt(2.0)) : 0.0;                      // :33
+  const dim3 g2((unsigned)((M + 255) / 256), (unsigned)d);
+  const double *cur = d_x;
+  int64_t ldc = ldx;
+  int pp = 0;
+  for (int64_t j = 0; j < nlevels; j++) {                                                      // :39 (level 0), :47-58
+    double *out = j == nlevels - 1 ? d_q : m0->dirt_z[pp];
+    const int64_t ldo = j == nlevels - 1 ? ldq : M;
+    if (ttirt_sqr_forward_device(models[j], M, d, cur, ldc, out, ldo, m0->dirt_lf, nullptr, stream) != 0) return -1;   // :39, :52
+    dirt_inverse_accumulate_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(M, d, j == 0 ? 1 : 0, (normal && j > 0) ? 1 : 0,
+                                                                               m0->dirt_lf, cur, ldc, d_lf);              // :44, :50, :57
+    LAUNCHED();
+    if (normal) {
+      dirt_u2tn_kernel<<<g2, 256, 0, st>>>(M, d, cdf_factor, out, ldo);                        // :42, :55
+      LAUNCHED();
+    }
+    cur = out; ldc = ldo; pp ^= 1;
+  }
+  CKS(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ttirt_dirt_inverse_host(int64_t nlevels, ttirt_sqr_model *const *models, double sigma, int64_t M, const double *h_x,
+                                       double *h_q, double *h_lf, int64_t ld) {
+  if (nlevels < 1 || !models || !models[0]) return aux_fail("ttirt_dirt_inverse: need at least the level-0 model");
+  if (M < 0 || ld < M) return aux_fail("bad M / leading dimension");
+  if (M == 0) return 0;
+  if (!h_x || !h_q || !h_lf) return aux_fail("null host buffer");
+  ttirt_sqr_model *m0 = models[0];
+  const int64_t d = m0->d;
+  CKS(cudaSetDevice(m0->device));
+  const int64_t chunk = std::min<int64_t>(M, (int64_t)1 << 20);
+  double *dx = nullptr, *dq = nullptr, *dl = nullptr;
+  CKS(sqr_alloc(&dx, sizeof(double) * chunk * d));
+  CKS(sqr_alloc(&dq, sizeof(double) * chunk * d));
+  CKS(sqr_alloc(&dl, sizeof(double) * chunk));
+  cudaStream_t st = m0->stream;
+  int rc = 0;
+  for (int64_t b = 0; b < M && rc == 0; b += chunk) {
+    const int64_t rows = std::min(chunk, M - b);
+    if (cudaMemcpy2DAsync(dx, sizeof(double) * chunk, h_x + b, sizeof(double) * ld, sizeof(double) * rows, (size_t)d, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = aux_fail("copy in failed"); break; }
+    rc = ttirt_dirt_inverse_device(nlevels, models, sigma, rows, dx, chunk, dq, chunk, dl, st);
+    if (rc != 0) break;
+    if (cudaMemcpy2DAsync(h_q + b, sizeof(double) * ld, dq, sizeof(double) * chunk, sizeof(double) * rows, (size_t)d, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaMemcpyAsync(h_lf + b, dl, sizeof(double) * rows, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) rc = aux_fail("copy out failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  cudaStreamSynchronize(st);
+  sqr_free(dx); sqr_free(dq); sqr_free(dl);
   return rc;
 }

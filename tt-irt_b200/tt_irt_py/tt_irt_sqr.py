@@ -43,6 +43,18 @@ def _lib():
         lib.ttirt_sqr_profile_enable.argtypes = [c_void_p, c_int]
         lib.ttirt_sqr_profile_read.restype = c_int
         lib.ttirt_sqr_profile_read.argtypes = [c_void_p, dp, lp, dp]
+        lib.tt_rt_sqr.restype = None
+        lib.tt_rt_sqr.argtypes = [c_int, ip, c_int, dp, ip, dp, c_int, c_int, dp, dp, dp]
+        lib.ttirt_sqr_forward_host.restype = c_int
+        lib.ttirt_sqr_forward_host.argtypes = [c_void_p, c_longlong, c_longlong, dp, dp, dp, c_void_p, c_longlong]
+        lib.ttirt_sqr_forward_device.restype = c_int
+        lib.ttirt_sqr_forward_device.argtypes = [c_void_p, c_longlong, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong,
+                                                 c_void_p, c_void_p, c_void_p]
+        lib.ttirt_dirt_inverse_host.restype = c_int
+        lib.ttirt_dirt_inverse_host.argtypes = [c_longlong, POINTER(c_void_p), c_double, c_longlong, dp, dp, dp, c_longlong]
+        lib.ttirt_dirt_inverse_device.restype = c_int
+        lib.ttirt_dirt_inverse_device.argtypes = [c_longlong, POINTER(c_void_p), c_double, c_longlong, c_void_p, c_longlong, c_void_p,
+                                                  c_longlong, c_void_p, c_void_p]
         lib.ttirt_dirt_sample_host.restype = c_int
         lib.ttirt_dirt_sample_host.argtypes = [c_longlong, POINTER(c_void_p), c_double, c_longlong, dp, dp, dp, c_longlong]
         lib.ttirt_dirt_sample_device.restype = c_int
@@ -85,6 +97,12 @@ def tracemult(A, j, B=None):
     return C
 
 
+def tt_rt_sqr(xsf, f, x):
+    """ Forward (Rosenblatt) transform through the square root of the density (reference tt_rt_sqr.m:1-15): same inputs as
+        tt_irt_sqr with points x (M x D) instead of seeds; returns (q, lFapp), q the CDF values in [0,1]."""
+    return _sqr_call("tt_rt_sqr", xsf, f, x)
+
+
 def tt_irt_sqr(xsf, f, q):
     """ Inverse CDF (Rosenblatt) transform through the square root of the density (reference tt_irt_sqr.m:1-15)
         Inputs:
@@ -95,6 +113,10 @@ def tt_irt_sqr(xsf, f, q):
           xq: samples mapped from q by the inverse CDF (M x D, Fortran shaped)
           lFapp: log(approximate PDF) at xq (M)
     """
+    return _sqr_call("tt_irt_sqr", xsf, f, q)
+
+
+def _sqr_call(symbol, xsf, f, q):
     lib = _lib()
     q = np.asfortranarray(q, dtype=np.float64)
     if q.ndim == 1:
@@ -112,9 +134,9 @@ def tt_irt_sqr(xsf, f, q):
     xq = np.zeros((M, D), dtype=np.float64, order="F")
     lFapp = np.zeros(M, dtype=np.float64)
     dp, ip = POINTER(c_double), POINTER(c_int)
-    lib.tt_irt_sqr(c_int(f.d), n.ctypes.data_as(ip), c_int(xsf.size), xsf.ctypes.data_as(dp), rf.ctypes.data_as(ip),
-                   core.ctypes.data_as(dp), c_int(M), c_int(D), q.ctypes.data_as(dp), xq.ctypes.data_as(dp),
-                   lFapp.ctypes.data_as(dp))
+    getattr(lib, symbol)(c_int(f.d), n.ctypes.data_as(ip), c_int(xsf.size), xsf.ctypes.data_as(dp), rf.ctypes.data_as(ip),
+                         core.ctypes.data_as(dp), c_int(M), c_int(D), q.ctypes.data_as(dp), xq.ctypes.data_as(dp),
+                         lFapp.ctypes.data_as(dp))
     return xq, lFapp
 
 
@@ -169,6 +191,22 @@ class SqrModel(object):
         if rc != 0:
             _raise_last(self._lib, "ttirt_sqr_sample_host")
         return (Z, lF, idx) if want_idx else (Z, lF)
+
+    def forward(self, x, want_idx=False):
+        """tt_rt_sqr on the resident model: points x (M x D) -> (q, lFapp[, idx])."""
+        x = np.asfortranarray(x, dtype=np.float64)
+        if x.ndim == 1:
+            x = np.asfortranarray(x[:, None])
+        M, D = x.shape
+        Q = np.zeros((M, D), dtype=np.float64, order="F")
+        lF = np.zeros(M, dtype=np.float64)
+        idx = np.zeros((M, D), dtype=np.int32, order="F") if want_idx else None
+        dp = POINTER(c_double)
+        rc = self._lib.ttirt_sqr_forward_host(self._h, M, D, x.ctypes.data_as(dp), Q.ctypes.data_as(dp), lF.ctypes.data_as(dp),
+                                              idx.ctypes.data_as(c_void_p) if want_idx else None, M)
+        if rc != 0:
+            _raise_last(self._lib, "ttirt_sqr_forward_host")
+        return (Q, lF, idx) if want_idx else (Q, lF)
 
     def sample_device(self, M, D, q_ptr, ldq, z_ptr, ldz, lf_ptr, idx_ptr=None, stream=None):
         rc = self._lib.ttirt_sqr_sample_device(self._h, int(M), int(D), c_void_p(q_ptr), int(ldq), c_void_p(z_ptr), int(ldz),
@@ -243,6 +281,21 @@ class Dirt(object):
             _raise_last(self._lib, "ttirt_dirt_sample_host")
         return z, lF
 
+    def inverse(self, x):
+        """[q, lFapp] = tt_dirt_inverse(IRTstruct, x): points of the target space back to the reference space."""
+        x = np.asfortranarray(x, dtype=np.float64)
+        M, d = x.shape
+        if d != self.d:
+            raise ValueError("x must be M x d")
+        q = np.zeros((M, d), order="F")
+        lF = np.zeros(M)
+        dp = POINTER(c_double)
+        rc = self._lib.ttirt_dirt_inverse_host(len(self.models), self._arr, self.sigma, M, x.ctypes.data_as(dp), q.ctypes.data_as(dp),
+                                               lF.ctypes.data_as(dp), M)
+        if rc != 0:
+            _raise_last(self._lib, "ttirt_dirt_inverse_host")
+        return q, lF
+
     def sample_device(self, M, q_ptr, ldq, z_ptr, ldz, lf_ptr, stream=None):
         rc = self._lib.ttirt_dirt_sample_device(len(self.models), self._arr, self.sigma, int(M), c_void_p(q_ptr), int(ldq), c_void_p(z_ptr),
                                                 int(ldz), c_void_p(lf_ptr), c_void_p(stream) if stream else None)
@@ -250,10 +303,27 @@ class Dirt(object):
             _raise_last(self._lib, "ttirt_dirt_sample_device")
 
 
+def tt_dirt_inverse(IRTstruct, x):
+    """[q, lFapp] = tt_dirt_inverse(IRTstruct, x)  (reference tt_dirt_inverse.m:1); IRTstruct as for tt_dirt_sample."""
+    drt = _dirt_from_struct(IRTstruct)
+    try:
+        return drt.inverse(x)
+    finally:
+        drt.close()
+
+
 def tt_dirt_sample(IRTstruct, q):
     """[z, lFapp] = tt_dirt_sample(IRTstruct, q)  (reference tt_dirt_sample.m:1; the exact-density evaluation of :76-82 stays
     with the caller).  IRTstruct: mapping with the fields tt_dirt_approx leaves behind -- 'x0', 'F0', 'x', 'F' (list),
     'reference', and optionally 'interpolation' / 'crossmethod'; F0 / F{j} are ttpy tensors or TTTensor containers."""
+    drt = _dirt_from_struct(IRTstruct)
+    try:
+        return drt.sample(q)
+    finally:
+        drt.close()
+
+
+def _dirt_from_struct(IRTstruct):
     if str(IRTstruct.get("crossmethod", "amen_cross_s")) == "build_ftt" or str(IRTstruct.get("interpolation", "spline"))[0] != "s":
         raise NotImplementedError("only the spline / TT-cross branch of tt_dirt_sample (tt_irt_sqr, :46, :71) is built")
 
@@ -261,8 +331,4 @@ def tt_dirt_sample(IRTstruct, q):
         x = np.concatenate([np.asarray(v, dtype=np.float64).ravel() for v in x]) if isinstance(x, (list, tuple)) else np.asarray(x, dtype=np.float64).ravel()
         return (np.asarray(f.n, dtype=np.int64), x, np.asarray(f.r, dtype=np.int64), _packed_cores(f))
     levels = [level(IRTstruct["F0"], IRTstruct["x0"])] + [level(f, IRTstruct["x"]) for f in IRTstruct["F"]]
-    drt = Dirt(levels, IRTstruct.get("reference", "uni"))
-    try:
-        return drt.sample(q)
-    finally:
-        drt.close()
+    return Dirt(levels, IRTstruct.get("reference", "uni"))
