@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--shape", default="32,65,64", help="d,n,r (default: the metric configuration)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-next-rows", action="store_true", help="skip the informational tt_irt_sqr figure appended at N=1")
     ap.add_argument("--cpu-samples-per-core", type=int, default=1 << 14)
     return ap.parse_args()
 
@@ -367,10 +368,27 @@ def main():
             "ms_per_step": ms_all / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": config, "roofline": roofline, "cpu_baseline": cb, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks, "checksum_lpz_1k": checksum, "host_binding": binding}
+    if world == 1 and not a.no_next_rows:
+        line["next_rows"] = _next_rows()
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+def _next_rows():
+    """Information only (not part of the metric): the SURVEY section 8(f) rank-4 row, the squared-density transform
+    tt_irt_sqr, measured by its own script at its metric shape in a child process (device-resident, no CPU leg, so
+    nothing under oracle/ runs).  A failure here never touches the headline line."""
+    try:
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "devtools", "bench_sqr.py"), "--no-cpu", "--no-e2e",
+                              "--steps", "2", "--warmup", "2"], capture_output=True, text=True, timeout=180)
+        j = json.loads(out.stdout.strip().splitlines()[-1])
+        return {"tt_irt_sqr": {"metric": j["metric"], "value": j["value"], "unit": j["unit"], "workload": j["config"]["workload"],
+                               "roofline": {k: j["roofline"][k] for k in ("bound", "achieved", "peak", "unit", "frac", "kernel", "kernel_share_of_step")},
+                               "algorithmic_tflops_whole_step": j["algorithmic_tflops_whole_step"], "gpu_launches": j["gpu_launches"]}}
+    except Exception as e:   # noqa: BLE001
+        return {"tt_irt_sqr": {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}}
 
 
 def _ncu_traffic(M):
