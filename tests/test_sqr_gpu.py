@@ -281,3 +281,31 @@ def test_round_trip_at_full_size():
         md.close()
     assert np.abs(Q - q).max() <= 1e-10 and np.median(np.abs(Q - q)) <= 1e-14
     assert np.abs(l2 - lF).max() <= 1e-10 * max(1.0, np.abs(lF).max())
+
+
+def test_repeated_calls_with_changing_shapes_are_stable_and_bounded():
+    """tt_irt_sqr keeps no state the caller can see; its device blocks go back to a per-device pool (bounded by TTIRT_POOL_MB).
+    Alternating shapes and sizes must repeat bit for bit, and device memory must not creep once every shape has been seen."""
+    import torch
+    shapes = [(6, 17, 8, 1 << 14), (5, 33, 32, 70000), (6, 17, 8, 300000), (4, 65, 64, 20000), (3, 9, 4, 1000)]
+    data, first = [], {}
+    for i, (d, n, r, M) in enumerate(shapes):
+        ns, xs, rk, c = synth.make_tt(d, n, r, seed=50 + i)
+        data.append((tt_irt.TTTensor(ns, rk, c), xs, synth.make_q(M, d, seed=60 + i)))
+    free0 = None
+    for rep in range(8):
+        for i, (f, xs, q) in enumerate(data):
+            Z, l = tt_irt_sqr.tt_irt_sqr(xs, f, q)
+            if i not in first:
+                first[i] = (Z.copy(), l.copy())
+                assert np.isfinite(Z).all() and np.isfinite(l).all()
+            else:
+                assert np.array_equal(Z, first[i][0]) and np.array_equal(l, first[i][1]), (rep, i)
+        free = torch.cuda.mem_get_info(0)[0]
+        if rep == 1:
+            free0 = free
+        if rep > 1:
+            assert free >= free0 - (64 << 20), "device memory shrank by %d MB over repeated calls" % ((free0 - free) >> 20)
+    before = torch.cuda.mem_get_info(0)[0]
+    tt_irt.load_library().ttirt_cache_clear()
+    assert torch.cuda.mem_get_info(0)[0] >= before          # the pool's idle blocks went back to the driver

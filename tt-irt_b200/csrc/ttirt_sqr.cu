@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <iterator>
 #include <map>
 #include <mutex>
 #include <thread>
@@ -55,7 +56,16 @@ struct DevPool {
   std::mutex mu;
   std::multimap<size_t, void *> idle;
   std::unordered_map<void *, size_t> live;
+  size_t idle_bytes = 0;
 };
+
+// idle blocks a device may hold back (TTIRT_POOL_MB, default 8192): callers that keep changing shapes would otherwise
+// accumulate one set of blocks per shape
+size_t pool_limit() {
+  static size_t v = 0;
+  if (v == 0) { const char *e = getenv("TTIRT_POOL_MB"); v = ((e && atoll(e) > 0) ? (size_t)atoll(e) : (size_t)8192) << 20; }
+  return v;
+}
 DevPool g_pool[64];
 
 bool pool_enabled() {
@@ -77,6 +87,7 @@ cudaError_t sqr_alloc(T **p, size_t bytes) {
       *p = static_cast<T *>(it->second);
       pl.live[it->second] = bytes;
       pl.idle.erase(it);
+      pl.idle_bytes -= bytes;
       return cudaSuccess;
     }
     void *q = nullptr;
@@ -85,6 +96,7 @@ cudaError_t sqr_alloc(T **p, size_t bytes) {
       cudaGetLastError();
       for (auto &kv : pl.idle) cudaFree(kv.second);
       pl.idle.clear();
+      pl.idle_bytes = 0;
       e = cudaMalloc(&q, bytes);
       if (e != cudaSuccess) return e;
     }
@@ -107,8 +119,18 @@ void sqr_free(void *p) {
     std::lock_guard<std::mutex> lock(pl.mu);
     auto it = pl.live.find(p);
     if (it != pl.live.end()) {
-      pl.idle.emplace(it->second, p);
+      const size_t bytes = it->second;
       pl.live.erase(it);
+      // over the limit: the largest idle blocks go back to the driver first (callers of sqr_free have synchronised)
+      while (!pl.idle.empty() && pl.idle_bytes + bytes > pool_limit()) {
+        auto big = std::prev(pl.idle.end());
+        cudaFree(big->second);
+        pl.idle_bytes -= big->first;
+        pl.idle.erase(big);
+      }
+      if (bytes > pool_limit()) { cudaFree(p); return; }
+      pl.idle.emplace(bytes, p);
+      pl.idle_bytes += bytes;
       return;
     }
   }
@@ -670,22 +692,30 @@ __global__ void __launch_bounds__(UPD_THREADS) sqr_update_kernel(UpdArgs a) {
   const int r0p = (a.r0 + 3) & ~3, r1p = (a.r1 + 3) & ~3;
   const int P = ((a.r0 + 7) & ~7) + 4;    // pitch of slab rows and of staged interface rows
   double *S0 = sm, *S1 = S0 + (size_t)8 * NTU * P, *Fs = S1 + (size_t)8 * NTU * P;   // Fs: two buffers of UPD_TS rows
+  double *Wsm = Fs + (size_t)2 * UPD_TS * P;                                          // [2][UPD_TS][2] interpolation weights
+  int *Ids = reinterpret_cast<int *>(Wsm + 4 * UPD_TS);                               // [2][UPD_TS] sample ids
+  int *Bts = Ids + 2 * UPD_TS, *Bst = Bts + (a.nb + 1);                               // the two bin tables
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int total = a.bin_tile_start[a.nb];
+  for (int i = tid; i <= a.nb; i += UPD_THREADS) { Bts[i] = a.bin_tile_start[i]; Bst[i] = a.bin_start[i]; }
+  __syncthreads();
+  const int total = Bts[a.nb];
   const int t_begin = (int)(((int64_t)total * blockIdx.x) / gridDim.x);
   const int t_end = (int)(((int64_t)total * (blockIdx.x + 1)) / gridDim.x);
-  // Each warp gathers and multiplies its own 16 samples: no CTA-wide barrier per tile.  The rows of the NEXT tile are
-  // fetched with cp.async (16 bytes per lane, a whole row per instruction) while the current tile is multiplied.
+  // Each warp gathers and multiplies its own 16 samples: no CTA-wide barrier per tile.  Everything a tile needs from global
+  // memory arrives asynchronously while earlier tiles are multiplied: the sample ids two tiles ahead (a register), the rows
+  // and the interpolation weights one tile ahead (cp.async: a whole row per instruction, 8 bytes per weight).
   // Rows of the interface buffers are zero in the columns [r, r rounded up to 4), so whole 4-blocks are copied.
   const int chunks = r0p >> 1;            // 16-byte pieces per row
-  int binp = 0;
-  auto gather = [&](int tile, int buf) {
-    while (tile >= a.bin_tile_start[binp + 1]) binp++;
-    const int start = a.bin_start[binp] + (tile - a.bin_tile_start[binp]) * UPD_TS;
-    const int cnt = min(UPD_TS, a.bin_start[binp + 1] - start);
-    const int mine = warp * 16 + (lane & 15);
-    const int myid = mine < cnt ? a.perm[start + mine] : -1;
+  const int mine = warp * 16 + (lane & 15);
+  int cur_p = 0;
+  auto load_id = [&](int tile) -> int {
+    while (tile >= Bts[cur_p + 1]) cur_p++;
+    const int start = Bst[cur_p] + (tile - Bts[cur_p]) * UPD_TS;
+    const int cnt = min(UPD_TS, Bst[cur_p + 1] - start);
+    return mine < cnt ? a.perm[start + mine] : -1;
+  };
+  auto issue = [&](int buf, int myid) {
     double *fw = Fs + ((size_t)buf * UPD_TS + warp * 16) * P;
 #pragma unroll 4
     for (int row = 0; row < 16; row++) {
@@ -694,15 +724,22 @@ __global__ void __launch_bounds__(UPD_THREADS) sqr_update_kernel(UpdArgs a) {
         for (int ch = lane; ch < chunks; ch += 32)
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(fw + row * P + 2 * ch)), "l"(a.Fin + (size_t)id * a.ldf + 2 * ch) : "memory");
     }
+    if (lane < 16) {
+      Ids[buf * UPD_TS + mine] = myid;
+      if (myid >= 0) {
+        double *w = Wsm + ((size_t)buf * UPD_TS + mine) * 2;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(w)), "l"(a.w1 + myid) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(w + 1)), "l"(a.w2 + myid) : "memory");
+      }
+    }
   };
   int buf = 0;
-  if (t_begin < t_end) gather(t_begin, 0);
+  if (t_begin < t_end) issue(0, load_id(t_begin));
   asm volatile("cp.async.commit_group;" ::: "memory");
+  int id_after = t_begin + 1 < t_end ? load_id(t_begin + 1) : -1;
   int bin = 0, staged = -1;
   for (int tile = t_begin; tile < t_end; tile++, buf ^= 1) {
-    while (tile >= a.bin_tile_start[bin + 1]) bin++;
-    const int start = a.bin_start[bin] + (tile - a.bin_tile_start[bin]) * UPD_TS;
-    const int cnt = min(UPD_TS, a.bin_start[bin + 1] - start);
+    while (tile >= Bts[bin + 1]) bin++;
     __syncwarp();                         // this warp's reads of the other buffer (previous tile) are done
     const bool restage = bin != staged;
     if (restage) {
@@ -722,8 +759,9 @@ __global__ void __launch_bounds__(UPD_THREADS) sqr_update_kernel(UpdArgs a) {
       staged = bin;
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
-    if (tile + 1 < t_end) gather(tile + 1, buf ^ 1);
+    if (tile + 1 < t_end) issue(buf ^ 1, id_after);
     asm volatile("cp.async.commit_group;" ::: "memory");
+    id_after = tile + 2 < t_end ? load_id(tile + 2) : -1;    // in flight while this tile is multiplied
     asm volatile("cp.async.wait_group 1;" ::: "memory");   // all but the newest group (the next tile's rows) have landed
     if (restage) __syncthreads(); else __syncwarp();
     const double *fw = Fs + ((size_t)buf * UPD_TS + warp * 16) * P;
@@ -747,9 +785,10 @@ __global__ void __launch_bounds__(UPD_THREADS) sqr_update_kernel(UpdArgs a) {
 #pragma unroll
     for (int mt = 0; mt < 2; mt++) {
       const int sidx = warp * 16 + mt * 8 + g;
-      if (sidx < cnt) {
-        const size_t id = (size_t)a.perm[start + sidx];
-        const double wa = a.w1[id], wb = a.w2[id];
+      const int sid = Ids[buf * UPD_TS + sidx];
+      if (sid >= 0) {
+        const size_t id = (size_t)sid;
+        const double wa = Wsm[((size_t)buf * UPD_TS + sidx) * 2], wb = Wsm[((size_t)buf * UPD_TS + sidx) * 2 + 1];
         double *dst = a.Fout + id * a.ldf + 2 * t;
 #pragma unroll
         for (int nt = 0; nt < NTU; nt++) {
@@ -773,7 +812,7 @@ static cudaError_t upd_launch(const UpdArgs &a, int64_t max_tiles, int sm_count,
     attr_done[dev] = true;
   }
   const int P = ((a.r0 + 7) & ~7) + 4;
-  const size_t sm = sizeof(double) * ((size_t)2 * 8 * NTU * P + (size_t)2 * UPD_TS * P);
+  const size_t sm = sizeof(double) * ((size_t)2 * 8 * NTU * P + (size_t)2 * UPD_TS * P + 4 * UPD_TS) + sizeof(int) * (2 * UPD_TS + 2 * (a.nb + 1));
   // one wave of CTAs, each walking a contiguous range of tiles (slabs are restaged only when the interval changes):
   // as many CTAs per SM as the shared memory allows, at most four
   int per_sm = (int)((size_t)(227 * 1024) / (sm + 1024));
@@ -846,6 +885,7 @@ void sqr_pool_clear() {
     cudaSetDevice(g);
     for (auto &kv : pl.idle) cudaFree(kv.second);
     pl.idle.clear();
+    pl.idle_bytes = 0;
   }
   cudaSetDevice(keep);
 }
