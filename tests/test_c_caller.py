@@ -1,5 +1,6 @@
-"""A plain-C program calling the drop-in symbol (examples/call_tt_irt1.c): compiles and links against both libraries
-here (CPU); on a B200 it runs and must agree with the Python path on the same xorshift-generated inputs."""
+"""Plain-C programs calling the drop-in symbol (examples/call_tt_irt1.c) and the squared-density transforms
+(examples/call_tt_irt_sqr.c): they compile and link against both libraries here (CPU); on a B200 they run and must agree with
+the Python path on the same xorshift-generated inputs."""
 import os
 import re
 import subprocess
@@ -13,7 +14,21 @@ SO32 = os.path.join(ROOT, "tt-irt_b200", "tt_irt_py", "tt_irt1_int32.so")
 LIB64 = os.path.join(ROOT, "tt-irt_b200", "lib")
 
 
-def _build(tmp_path, width):
+SRC_SQR = os.path.join(ROOT, "examples", "call_tt_irt_sqr.c")
+
+
+def _build(tmp_path, width, src=None):
+    global SRC
+    keep = SRC
+    if src is not None:
+        SRC = src
+    try:
+        return _build_one(tmp_path, width)
+    finally:
+        SRC = keep
+
+
+def _build_one(tmp_path, width):
     exe = str(tmp_path / ("call%d" % width))
     if width == 32:
         cmd = ["gcc", "-O2", "-DTTIRT_INT=int", SRC, "-I" + os.path.join(ROOT, "include"), SO32, "-lm", "-o", exe]
@@ -70,4 +85,39 @@ def test_c_caller_agrees_with_the_python_path(tmp_path, width):
     finally:
         md.close()
     # same library, same inputs: the column-wise sums agree to summation-order rounding
+    assert abs(Z.sum() - sz) <= 1e-9 * max(1.0, abs(sz)) and abs(l.sum() - sl) <= 1e-9 * max(1.0, abs(sl))
+
+
+@pytest.mark.parametrize("width", [32, 64])
+def test_sqr_c_caller_compiles_and_links(tmp_path, width):
+    exe = _build(tmp_path, width, SRC_SQR)
+    from tt_irt_py import tt_irt
+    if tt_irt.device_count() < 1:
+        env = dict(os.environ, LD_LIBRARY_PATH=os.path.dirname(SO32))
+        env.pop("TTIRT_QUIET", None)
+        out = subprocess.run([exe, "64"], capture_output=True, text=True, env=env)
+        assert out.returncode == 1 and "sumZ=nan" in out.stdout and "no CUDA device" in out.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("width", [32, 64])
+def test_sqr_c_caller_round_trips_and_agrees_with_the_python_path(tmp_path, width):
+    from tt_irt_py import tt_irt_sqr
+    exe = _build(tmp_path, width, SRC_SQR)
+    M, d, nn, r = 2048, 5, 17, 8
+    out = subprocess.run([exe, str(M)], capture_output=True, text=True, env=dict(os.environ, LD_LIBRARY_PATH=os.path.dirname(SO32)))
+    assert out.returncode == 0, out.stdout + out.stderr
+    m = re.search(r"sumZ=(\S+) sumlF=(\S+) outside=(\d+) roundtrip=(\S+) dlF=(\S+) launches=(\d+)", out.stdout)
+    sz, sl, outside, rt, dl, launches = float(m.group(1)), float(m.group(2)), int(m.group(3)), float(m.group(4)), float(m.group(5)), int(m.group(6))
+    assert outside == 0 and launches > 0 and rt < 1e-11 and dl < 1e-10
+    rk = np.array([1] + [r] * (d - 1) + [1]); ns = np.full(d, nn)
+    ncore = int((rk[:-1] * ns * rk[1:]).sum())
+    core, qf = _xorshift_inputs(ncore, M * d)
+    xs = np.tile(-1.0 + 2.0 * np.arange(nn) / (nn - 1), d)
+    q = qf.reshape((M, d), order="F")
+    md = tt_irt_sqr.SqrModel(ns, xs, rk, core)
+    try:
+        Z, l = md.sample(q)
+    finally:
+        md.close()
     assert abs(Z.sum() - sz) <= 1e-9 * max(1.0, abs(sz)) and abs(l.sum() - sl) <= 1e-9 * max(1.0, abs(sl))

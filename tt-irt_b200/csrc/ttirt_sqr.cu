@@ -11,8 +11,10 @@
 //                    sqr_tail_kernel    trapezoid CDF, zero-mass fallback, normalise, bisection, quadratic root, clamp,
 //                                       log-density (:113-195), in the reference's operation order
 //                    bin scan / scatter counting sort of the chunk by chosen interval
-//                    sqr_update_kernel  interpolated interface update (:197-207) with the two core slabs of a bin staged
-//                                       in shared memory
+//                    sqr_update_kernel  interpolated interface update (:197-207): two FP64 tensor-core products per tile with
+//                                       the two core slabs of a bin staged in shared memory
+//   forward      : tt_rt_sqr.m (x -> q): the same kernels with the tail's other branch (tt_rt_sqr.m:129-166)
+//   DIRT loops   : tt_dirt_sample.m:17-73 and tt_dirt_inverse.m:24-59 over resident level models
 // No CPU fallback anywhere: without a device every entry point fails.
 #include <algorithm>
 #include <chrono>
@@ -864,11 +866,6 @@ __global__ void dirt_inverse_accumulate_kernel(int64_t M, int d, int first, int 
     v = __dadd_rn(v, __ddiv_rn(s, 2.0));
   }
   lf[m] = __dadd_rn(v, dlf[m]);
-}
-
-__global__ void sqr_fill_nan_kernel(double *p, int64_t n) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = __longlong_as_double(0x7ff8000000000000LL);
 }
 
 }  // namespace
