@@ -309,3 +309,35 @@ def test_repeated_calls_with_changing_shapes_are_stable_and_bounded():
     before = torch.cuda.mem_get_info(0)[0]
     tt_irt.load_library().ttirt_cache_clear()
     assert torch.cuda.mem_get_info(0)[0] >= before          # the pool's idle blocks went back to the driver
+
+
+@pytest.mark.parametrize("d,n,r,M,cores", [(4, 65, 64, 3000, "uniform"), (6, 33, 32, 5000, "uniform"), (8, 17, 16, 20000, "uniform"),
+                                           (5, 20, 12, 4000, "normal"), (5, 12, 40, 1200, "uniform"), (4, 40, 7, 999, "uniform")])
+def test_fused_and_separate_tail_agree_bit_for_bit(d, n, r, M, cores):
+    """The tail fused into the conditional-pdf kernel (no CDF scratch: mass, then a guarded count against q * mass, the
+    reference bisection only when the count is ambiguous or the CDF is not monotone) and the separate tail kernel
+    (TTIRT_SQR_FUSED=0) must give identical bits, in both directions; seeds on CDF nodes and at 0 / 1 included."""
+    ns, xs, rk, c = synth.make_tt(d, n, r, seed=70 + d, cores=cores)
+    q = synth.make_q(M, d, seed=71)
+    q[:16, :] = 0.0
+    q[16:32, :] = 1.0
+    q[32:48, 0] = 0.5
+    q = np.asfortranarray(q)
+    md = tt_irt_sqr.SqrModel(ns, xs, rk, c)
+    try:
+        os.environ["TTIRT_SQR_FUSED"] = "2"          # fused in every class (the default leaves the r <= 64 class unfused)
+        try:
+            Zf, lf, idf = md.sample(q, want_idx=True)
+            Qf, l2f = md.forward(Zf)
+            os.environ["TTIRT_SQR_FUSED"] = "0"
+            Zs, ls, ids = md.sample(q, want_idx=True)
+            Qs, l2s = md.forward(Zf)
+        finally:
+            del os.environ["TTIRT_SQR_FUSED"]
+    finally:
+        md.close()
+    np.testing.assert_array_equal(idf, ids)
+    np.testing.assert_array_equal(Zf, Zs)
+    np.testing.assert_array_equal(lf, ls)
+    np.testing.assert_array_equal(Qf, Qs)
+    np.testing.assert_array_equal(l2f, l2s)

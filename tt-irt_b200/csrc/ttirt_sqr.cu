@@ -376,15 +376,183 @@ constexpr int PDF_WARPS = 8;                  // MMA warps, two per SM sub-parti
 constexpr int PDF_KS = 16;                    // k-steps per B slice
 constexpr int PDF_STAGES = 3;
 
+struct TailArgs {
+  const double *pdf; double *cdf; int64_t ldp; int rows; int n;
+  const double *x, *h, *hc;
+  const double *q; double *z; int32_t *idx_out;
+  int *idx; double *w1, *w2; double *lf;
+  int first;        // dimension 0: lFapp starts here (:91)
+  int forward;      // 0: inverse transform (tt_irt_sqr.m: q -> x), 1: forward transform (tt_rt_sqr.m: x -> q)
+  int *hist;        // n - 1 counters for the sort by interval, or NULL when no interface update follows
+};
+
+// One increment of the trapezoid CDF, :114-117:  ((0.5 p_{j-1} + 0.5 p_j) h_j), no FMA contraction
+__device__ __forceinline__ double cdf_step(double pprev, double pj, double hj) {
+  return __dmul_rn(__dadd_rn(__dmul_rn(0.5, pprev), __dmul_rn(0.5, pj)), hj);
+}
+
+// Everything after the cell i0 is known, :129-130, :146-195 (inverse) / tt_rt_sqr.m:141-163 (forward), in the reference's
+// operation order.  c1raw, p1raw, p2raw: unnormalised CDF and conditional at the cell's nodes; cmax the normalisation.
+__device__ __forceinline__ void tail_finish(const TailArgs &a, int m, int i0, double qk, double c1raw, double p1raw, double p2raw,
+                                            double cmax, int *sh_hist) {
+  const double C1 = __ddiv_rn(c1raw, cmax);                                                       // :146-149, :129-130
+  const double f1 = __ddiv_rn(p1raw, cmax);
+  const double f2 = __ddiv_rn(p2raw, cmax);
+  const double x1 = a.x[i0], x2 = a.x[i0 + 1];                                                    // :157-159
+  const double h3 = __dsub_rn(x2, x1);
+  const double Aq = __ddiv_rn(__dmul_rn(0.5, __dsub_rn(f2, f1)), h3);                            // :161
+  double xk, out;
+  if (a.forward) {
+    xk = qk;
+    const double dx = __dsub_rn(xk, x1);
+    out = __dadd_rn(__dadd_rn(__dmul_rn(Aq, __dmul_rn(dx, dx)), __dmul_rn(f1, dx)), C1);         // tt_rt_sqr.m:151
+  } else {
+    const double dq = __dsub_rn(qk, C1);
+    const double Dq = __dadd_rn(__dmul_rn(f1, f1), __dmul_rn(__dmul_rn(4.0, Aq), dq));           // :162
+    xk = __dadd_rn(x1, __ddiv_rn(__dadd_rn(-f1, __dsqrt_rn(fabs(Dq))), __dmul_rn(2.0, Aq)));     // :163
+    if (Aq == 0.0) {                                                                              // :164-170
+      xk = __dadd_rn(x1, __ddiv_rn(dq, f1));
+      if (f1 == 0.0) xk = x1;
+    }
+    if (xk > x2) xk = x2;                                                                         // :173-182
+    if (xk < x1) xk = x1;
+    out = xk;
+  }
+  a.z[m] = out;                                                                                   // :184 / tt_rt_sqr.m:153
+  const double wa = __ddiv_rn(__dsub_rn(x2, xk), h3), wb = __ddiv_rn(__dsub_rn(xk, x1), h3);      // :187-188
+  const double dens = __dadd_rn(__dmul_rn(f1, wa), __dmul_rn(f2, wb));                            // :193
+  const double lg = log(dens);                                                                    // :194
+  a.lf[m] = a.first ? lg : __dadd_rn(a.lf[m], lg);
+  a.idx[m] = i0; a.w1[m] = wa; a.w2[m] = wb;
+  if (a.idx_out) a.idx_out[m] = i0;
+  if (sh_hist) atomicAdd(&sh_hist[i0], 1);
+}
+
+// :113-195, one thread per sample, every operation in the reference's order (explicit round-to-nearest intrinsics: no
+// FMA contraction).  The unnormalised CDF goes to a scratch column block that the bisection reads back.
+// (The path of shapes whose pdf tile cannot be parked in shared memory; otherwise the tail runs inside sqr_pdf_kernel.)
+__global__ void __launch_bounds__(256) sqr_tail_kernel(TailArgs a) {
+  extern __shared__ int sh_hist[];
+  const int n = a.n;
+  if (a.hist) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sh_hist[i] = 0;
+    __syncthreads();
+  }
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m < a.rows) {
+    const double *p = a.pdf + m;
+    double *cd = a.cdf + m;
+    double pprev = p[0];
+    double c = __dmul_rn(__dmul_rn(0.5, pprev), a.h[0]);       // :114-116, h(1) = 0
+    cd[0] = c;
+    for (int j = 1; j < n; j++) {
+      const double pj = p[(size_t)j * a.ldp];
+      c = __dadd_rn(c, cdf_step(pprev, pj, a.h[j]));           // :117 cumsum
+      cd[(size_t)j * a.ldp] = c;
+      pprev = pj;
+    }
+    double cmax = c;                                           // :120
+    const bool zero = cmax <= 0.0;                             // :121-127: conditional replaced by h, CDF by cumsum(h)
+    if (zero) cmax = a.hc[n - 1];
+    const double qk = a.q[m];                                  // the seed (inverse) or the point (forward, tt_rt_sqr.m:129)
+    int i0 = 0, i2 = n - 1;                                    // :135-143
+    if (a.forward) {
+      while (i2 - i0 > 1) {                                    // tt_rt_sqr.m:132-138: the cell is found on the grid
+        const int i1 = (i0 + i2) >> 1;
+        if (qk > a.x[i1]) i0 = i1; else i2 = i1;
+      }
+    } else {
+      while (i2 - i0 > 1) {
+        const int i1 = (i0 + i2) >> 1;
+        const double c1 = __ddiv_rn(zero ? a.hc[i1] : cd[(size_t)i1 * a.ldp], cmax);
+        if (qk > c1) i0 = i1; else i2 = i1;
+      }
+    }
+    tail_finish(a, m, i0, qk, zero ? a.hc[i0] : cd[(size_t)i0 * a.ldp], zero ? a.h[i0] : p[(size_t)i0 * a.ldp],
+                zero ? a.h[i0 + 1] : p[(size_t)(i0 + 1) * a.ldp], cmax, a.hist ? sh_hist : nullptr);
+  }
+  if (a.hist) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < n - 1; i += blockDim.x)
+      if (sh_hist[i]) atomicAdd(a.hist + i, sh_hist[i]);
+  }
+}
+
+// The same tail for one row whose conditional sits in shared memory (pr[0..n)), run by one lane inside sqr_pdf_kernel:
+// no scratch in global memory.  The CDF is never stored: pass 1 yields the mass; when every increment is non-negative the
+// CDF is monotone and the reference's bisection (:135-143) returns the number of interior nodes below q, which pass 2
+// counts against q * mass with a 4-ulp guard band on either side (no division); if the two counts differ, or an increment
+// was negative, the bisection itself runs with the prefix sums recomputed in the same order.  Bit-identical to
+// sqr_tail_kernel on the same conditional.
+__device__ void fused_tail_row(const TailArgs &a, int m, const double *pr, const double *sx, const double *sh, const double *shc,
+                               int *sh_hist) {
+  const int n = a.n;
+  double pprev = pr[0];
+  const double c0 = __dmul_rn(__dmul_rn(0.5, pprev), sh[0]);
+  double c = c0;
+  bool mono = true;
+  for (int j = 1; j < n; j++) {
+    const double pj = pr[j];
+    const double tj = cdf_step(pprev, pj, sh[j]);
+    mono = mono && !(tj < 0.0);
+    c = __dadd_rn(c, tj);
+    pprev = pj;
+  }
+  double cmax = c;
+  const bool zero = cmax <= 0.0;
+  if (zero) cmax = shc[n - 1];
+  auto prefix = [&](int i) -> double {       // C_i, the rounding sequence of pass 1
+    double pp = pr[0], cc = c0;
+    for (int j = 1; j <= i; j++) { const double pj = pr[j]; cc = __dadd_rn(cc, cdf_step(pp, pj, sh[j])); pp = pj; }
+    return cc;
+  };
+  const double qk = a.q[m];
+  int i0 = 0, i2 = n - 1;
+  double c1raw;
+  if (a.forward) {
+    while (i2 - i0 > 1) { const int i1 = (i0 + i2) >> 1; if (qk > sx[i1]) i0 = i1; else i2 = i1; }
+    c1raw = zero ? shc[i0] : prefix(i0);
+  } else if (zero) {
+    while (i2 - i0 > 1) { const int i1 = (i0 + i2) >> 1; if (qk > __ddiv_rn(shc[i1], cmax)) i0 = i1; else i2 = i1; }
+    c1raw = shc[i0];
+  } else {
+    bool done = false;
+    if (mono && c0 == 0.0) {
+      const double qc = __dmul_rn(qk, cmax);
+      const double lo = __dmul_rn(qc, 1.0 - 8.8817841970012523e-16), hi = __dmul_rn(qc, 1.0 + 8.8817841970012523e-16);
+      int L = 0, U = 0;
+      double cc = c0, clast = c0, pp = pr[0];
+      for (int j = 1; j < n - 1; j++) {
+        const double pj = pr[j];
+        cc = __dadd_rn(cc, cdf_step(pp, pj, sh[j]));
+        pp = pj;
+        if (cc < lo) { L++; clast = cc; }
+        if (cc < hi) U++;
+      }
+      if (L == U && qc > 0.0) { i0 = L; c1raw = clast; done = true; }
+    }
+    if (!done) {
+      while (i2 - i0 > 1) { const int i1 = (i0 + i2) >> 1; if (qk > __ddiv_rn(prefix(i1), cmax)) i0 = i1; else i2 = i1; }
+      c1raw = prefix(i0);
+    }
+  }
+  tail_finish(a, m, i0, qk, c1raw, zero ? sh[i0] : pr[i0], zero ? sh[i0 + 1] : pr[i0 + 1], cmax, sh_hist);
+}
+
 struct PdfArgs {
   const double *F; int ldf; int rows;
   const double *gp; int pb; int ksteps; int r0; int n;
   double *pdf; int64_t ldp;
+  // fused tail (FUSE): the warp parks its pdf tile in shared memory (row pitch pp doubles, warp w at doubles
+  // park_off + w * park_stride from the start of dynamic shared memory) and one lane per row finishes the dimension
+  TailArgs tail; int pp; int park_off; int park_stride;
 };
 
 __host__ __device__ inline size_t pdf_smem_bytes(int rows_cta, int ldf, int pb) {
   return sizeof(double) * ((size_t)rows_cta * ldf + (size_t)PDF_STAGES * PDF_KS * 4 * pb) + 2 * PDF_STAGES * sizeof(uint64_t);
 }
+// with the fused tail: + grid tables and histogram, + the parked tiles unless they alias the interface rows
+__host__ inline size_t pdf_fused_tables_bytes(int n) { return sizeof(double) * 3 * (size_t)n + sizeof(int) * (((size_t)n + 1) & ~(size_t)1); }
 
 // Conditional pdf of one dimension for a chunk: pdf[j, m] = sum over pairs f_m[a] f_m[b] Gp[(a,b), j].
 //   * persistent CTAs over 128-sample tiles; eight MMA warps of 16 samples each and one producer warp;
@@ -394,7 +562,9 @@ __host__ __device__ inline size_t pdf_smem_bytes(int rows_cta, int ldf, int pb) 
 //   * pitches: ldf = 4 (mod 8) and pb = 4 (mod 8) doubles make the fragment loads bank-conflict free without a swizzle.
 //   * TAIL1 (n = 8 NT + 1, the usual 2^p + 1 grid): the lone last grid column is a DFMA dot product on the A values the lanes
 //     already hold (one broadcast LDS and two DFMA per k-step) instead of a DMMA column tile that is 7/8 padding.
-template <int NT, bool TAIL1, int PDF_MT>
+//   * FUSE: the tail of the dimension (:113-195) runs here too: the warp parks its finished pdf tile in shared memory and one
+//     lane per row walks it (fused_tail_row), so the conditional never goes to global memory and sqr_tail_kernel is not launched.
+template <int NT, bool TAIL1, int PDF_MT, bool FUSE>
 __global__ void __launch_bounds__(32 * (PDF_WARPS + 1), 1) sqr_pdf_kernel(PdfArgs a) {
   constexpr int PDF_WROWS = 8 * PDF_MT;               // samples per warp
   constexpr int PDF_ROWS = PDF_WARPS * PDF_WROWS;     // samples per CTA tile
@@ -404,7 +574,13 @@ __global__ void __launch_bounds__(32 * (PDF_WARPS + 1), 1) sqr_pdf_kernel(PdfArg
   const int SB = PDF_KS * 4 * a.pb;           // doubles per stage
   uint64_t *full = reinterpret_cast<uint64_t *>(Bs + (size_t)PDF_STAGES * SB);
   uint64_t *empty = full + PDF_STAGES;
+  // FUSE: grid, intervals and their running sum (3 n doubles), the interval histogram (n ints), then the parked tiles
+  double *sx = reinterpret_cast<double *>(empty + PDF_STAGES), *sh = sx + a.n, *shc = sh + a.n;
+  int *sh_hist = reinterpret_cast<int *>(shc + a.n);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (FUSE) {
+    for (int i = tid; i < a.n; i += blockDim.x) { sx[i] = a.tail.x[i]; sh[i] = a.tail.h[i]; shc[i] = a.tail.hc[i]; sh_hist[i] = 0; }
+  }
   const int ntiles = (a.rows + PDF_ROWS - 1) / PDF_ROWS;
   const int nslices = (a.ksteps + PDF_KS - 1) / PDF_KS;
   if (tid == 0) {
@@ -532,117 +708,59 @@ __global__ void __launch_bounds__(32 * (PDF_WARPS + 1), 1) sqr_pdf_kernel(PdfArg
         if ((ks & (PDF_KS - 1)) == 0 || ks == a.ksteps) release();
       }
     }
+    if (FUSE) {
+      // park the tile [row][node] (odd pitch: the row-per-lane reads of the tail are conflict free), then one lane per row
+      double *park = reinterpret_cast<double *>(smem_raw) + a.park_off + (size_t)warp * a.park_stride;
+      __syncwarp();                          // (when the park aliases this warp's interface rows: every lane is done with them)
 #pragma unroll
-    for (int mt = 0; mt < PDF_MT; mt++) {
-      const int row = m0 + mt * 8 + g;
-      if (row < a.rows) {
+      for (int mt = 0; mt < PDF_MT; mt++) {
+        double *pr = park + (mt * 8 + g) * a.pp;
 #pragma unroll
         for (int nt = 0; nt < NT; nt++) {
           const int col = nt * 8 + 2 * t;
-          if (col < a.n) a.pdf[(size_t)col * a.ldp + row] = acc[mt][nt][0];
-          if (col + 1 < a.n) a.pdf[(size_t)(col + 1) * a.ldp + row] = acc[mt][nt][1];
+          if (col < a.n) pr[col] = acc[mt][nt][0];
+          if (col + 1 < a.n) pr[col + 1] = acc[mt][nt][1];
+        }
+        if (TAIL1) {
+          double v = tl[mt];
+          v += __shfl_xor_sync(FULL, v, 1);
+          v += __shfl_xor_sync(FULL, v, 2);
+          if (t == 0) pr[8 * NT] = v;
+        }
+      }
+      __syncwarp();
+      for (int row = lane; row < PDF_WROWS; row += 32)
+        if (m0 + row < a.rows) fused_tail_row(a.tail, m0 + row, park + row * a.pp, sx, sh, shc, a.tail.hist ? sh_hist : nullptr);
+      __syncwarp();
+    } else {
+#pragma unroll
+      for (int mt = 0; mt < PDF_MT; mt++) {
+        const int row = m0 + mt * 8 + g;
+        if (row < a.rows) {
+#pragma unroll
+          for (int nt = 0; nt < NT; nt++) {
+            const int col = nt * 8 + 2 * t;
+            if (col < a.n) a.pdf[(size_t)col * a.ldp + row] = acc[mt][nt][0];
+            if (col + 1 < a.n) a.pdf[(size_t)(col + 1) * a.ldp + row] = acc[mt][nt][1];
+          }
+        }
+      }
+      if (TAIL1) {
+#pragma unroll
+        for (int mt = 0; mt < PDF_MT; mt++) {
+          double v = tl[mt];
+          v += __shfl_xor_sync(FULL, v, 1);
+          v += __shfl_xor_sync(FULL, v, 2);
+          const int row = m0 + mt * 8 + g;
+          if (t == 0 && row < a.rows) a.pdf[(size_t)(8 * NT) * a.ldp + row] = v;
         }
       }
     }
-    if (TAIL1) {
-#pragma unroll
-      for (int mt = 0; mt < PDF_MT; mt++) {
-        double v = tl[mt];
-        v += __shfl_xor_sync(FULL, v, 1);
-        v += __shfl_xor_sync(FULL, v, 2);
-        const int row = m0 + mt * 8 + g;
-        if (t == 0 && row < a.rows) a.pdf[(size_t)(8 * NT) * a.ldp + row] = v;
-      }
-    }
   }
-}
-
-struct TailArgs {
-  const double *pdf; double *cdf; int64_t ldp; int rows; int n;
-  const double *x, *h, *hc;
-  const double *q; double *z; int32_t *idx_out;
-  int *idx; double *w1, *w2; double *lf;
-  int first;        // dimension 0: lFapp starts here (:91)
-  int forward;      // 0: inverse transform (tt_irt_sqr.m: q -> x), 1: forward transform (tt_rt_sqr.m: x -> q)
-  int *hist;        // n - 1 counters for the sort by interval, or NULL when no interface update follows
-};
-
-// :113-195, one thread per sample, every operation in the reference's order (explicit round-to-nearest intrinsics: no
-// FMA contraction).  The unnormalised CDF goes to a scratch column block that the bisection reads back.
-__global__ void __launch_bounds__(256) sqr_tail_kernel(TailArgs a) {
-  extern __shared__ int sh_hist[];
-  const int n = a.n;
-  if (a.hist) {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) sh_hist[i] = 0;
-    __syncthreads();
-  }
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m < a.rows) {
-    const double *p = a.pdf + m;
-    double *cd = a.cdf + m;
-    double c = 0.0, pprev = p[0];
-    cd[0] = __dmul_rn(__dmul_rn(0.5, pprev), a.h[0]);        // :114-116, h(1) = 0
-    c = cd[0];
-    for (int j = 1; j < n; j++) {
-      const double pj = p[(size_t)j * a.ldp];
-      const double tj = __dmul_rn(__dadd_rn(__dmul_rn(0.5, pprev), __dmul_rn(0.5, pj)), a.h[j]);
-      c = __dadd_rn(c, tj);                                    // :117 cumsum
-      cd[(size_t)j * a.ldp] = c;
-      pprev = pj;
-    }
-    double cmax = c;                                           // :120
-    const bool zero = cmax <= 0.0;                             // :121-127: conditional replaced by h, CDF by cumsum(h)
-    if (zero) cmax = a.hc[n - 1];
-    const double qk = a.q[m];                                  // the seed (inverse) or the point (forward, tt_rt_sqr.m:129)
-    int i0 = 0, i2 = n - 1;                                    // :135-143
-    if (a.forward) {
-      while (i2 - i0 > 1) {                                    // tt_rt_sqr.m:132-138: the cell is found on the grid
-        const int i1 = (i0 + i2) >> 1;
-        if (qk > a.x[i1]) i0 = i1; else i2 = i1;
-      }
-    } else {
-      while (i2 - i0 > 1) {
-        const int i1 = (i0 + i2) >> 1;
-        const double c1 = __ddiv_rn(zero ? a.hc[i1] : cd[(size_t)i1 * a.ldp], cmax);
-        if (qk > c1) i0 = i1; else i2 = i1;
-      }
-    }
-    const double C1 = __ddiv_rn(zero ? a.hc[i0] : cd[(size_t)i0 * a.ldp], cmax);                 // :146-149, :129-130
-    const double f1 = __ddiv_rn(zero ? a.h[i0] : p[(size_t)i0 * a.ldp], cmax);
-    const double f2 = __ddiv_rn(zero ? a.h[i0 + 1] : p[(size_t)(i0 + 1) * a.ldp], cmax);
-    const double x1 = a.x[i0], x2 = a.x[i0 + 1];                                                  // :157-159
-    const double h3 = __dsub_rn(x2, x1);
-    const double Aq = __ddiv_rn(__dmul_rn(0.5, __dsub_rn(f2, f1)), h3);                          // :161
-    double xk, out;
-    if (a.forward) {
-      xk = qk;
-      const double dx = __dsub_rn(xk, x1);
-      out = __dadd_rn(__dadd_rn(__dmul_rn(Aq, __dmul_rn(dx, dx)), __dmul_rn(f1, dx)), C1);       // tt_rt_sqr.m:151
-    } else {
-      const double dq = __dsub_rn(qk, C1);
-      const double Dq = __dadd_rn(__dmul_rn(f1, f1), __dmul_rn(__dmul_rn(4.0, Aq), dq));         // :162
-      xk = __dadd_rn(x1, __ddiv_rn(__dadd_rn(-f1, __dsqrt_rn(fabs(Dq))), __dmul_rn(2.0, Aq)));   // :163
-      if (Aq == 0.0) {                                                                            // :164-170
-        xk = __dadd_rn(x1, __ddiv_rn(dq, f1));
-        if (f1 == 0.0) xk = x1;
-      }
-      if (xk > x2) xk = x2;                                                                       // :173-182
-      if (xk < x1) xk = x1;
-      out = xk;
-    }
-    a.z[m] = out;                                                                                 // :184 / tt_rt_sqr.m:153
-    const double wa = __ddiv_rn(__dsub_rn(x2, xk), h3), wb = __ddiv_rn(__dsub_rn(xk, x1), h3);    // :187-188
-    const double dens = __dadd_rn(__dmul_rn(f1, wa), __dmul_rn(f2, wb));                          // :193
-    const double lg = log(dens);                                                                  // :194
-    a.lf[m] = a.first ? lg : __dadd_rn(a.lf[m], lg);
-    a.idx[m] = i0; a.w1[m] = wa; a.w2[m] = wb;
-    if (a.idx_out) a.idx_out[m] = i0;
-    if (a.hist) atomicAdd(&sh_hist[i0], 1);
-  }
-  if (a.hist) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < n - 1; i += blockDim.x)
-      if (sh_hist[i]) atomicAdd(a.hist + i, sh_hist[i]);
+  if (FUSE && a.tail.hist) {                 // the eight MMA warps (the producer warp has left): flush the CTA's histogram
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * PDF_WARPS) : "memory");
+    for (int i = tid; i < a.n - 1; i += 32 * PDF_WARPS)
+      if (sh_hist[i]) atomicAdd(a.tail.hist + i, sh_hist[i]);
   }
 }
 
@@ -981,22 +1099,57 @@ extern "C" void ttirt_sqr_model_destroy(ttirt_sqr_model *md) {
   delete md;
 }
 
-template <int NT, bool TAIL1, int MT>
-static cudaError_t pdf_launch(const PdfArgs &a, int sm_count, cudaStream_t st) {
+// TTIRT_SQR_FUSED=0 keeps the tail in its own kernel (read at every launch: the tests compare the two paths bit for bit)
+static bool sqr_fuse_enabled() {
+  const char *e = getenv("TTIRT_SQR_FUSED");
+  return e ? atoi(e) != 0 : true;
+}
+
+template <int NT, bool TAIL1, int MT, bool FUSE>
+static cudaError_t pdf_launch_impl(const PdfArgs &a, size_t bytes, int sm_count, cudaStream_t st) {
   constexpr int PDF_ROWS = PDF_WARPS * 8 * MT;
   static bool attr_done[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
-  const size_t bytes = pdf_smem_bytes(PDF_ROWS, a.ldf, a.pb);
   if (dev < 64 && !attr_done[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(sqr_pdf_kernel<NT, TAIL1, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(sqr_pdf_kernel<NT, TAIL1, MT, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     attr_done[dev] = true;
   }
   const int ntiles = (a.rows + PDF_ROWS - 1) / PDF_ROWS;
   const int grid = ntiles < sm_count ? ntiles : sm_count;
-  sqr_pdf_kernel<NT, TAIL1, MT><<<grid, 32 * (PDF_WARPS + 1), bytes, st>>>(a);
+  sqr_pdf_kernel<NT, TAIL1, MT, FUSE><<<grid, 32 * (PDF_WARPS + 1), bytes, st>>>(a);
   return cudaGetLastError();
+}
+
+// Launches the conditional-pdf kernel; *fused tells the caller whether the tail ran inside it (else sqr_tail_kernel follows).
+template <int NT, bool TAIL1, int MT>
+static cudaError_t pdf_launch(PdfArgs a, int sm_count, cudaStream_t st, bool *fused) {
+  constexpr int PDF_ROWS = PDF_WARPS * 8 * MT, WROWS = 8 * MT;
+  const size_t base = pdf_smem_bytes(PDF_ROWS, a.ldf, a.pb);
+  *fused = false;
+  // Measured on B200: in the two lighter classes (32 rows per warp: every lane walks a row) the fused tail beats the
+  // separate kernel by 8 % (r = 32, n = 33) to 14 % (r = 16, n = 17) of the step; in the r <= 64 / n <= 72 class (16 rows
+  // per warp, half the lanes idle, its FP64 instructions contending with a saturated DMMA pipe) it loses 2.5 %: not fused
+  // there unless TTIRT_SQR_FUSED=2 asks for it.
+  const char *fe = getenv("TTIRT_SQR_FUSED");
+  const bool want = sqr_fuse_enabled() && (MT >= 4 || (fe && atoi(fe) >= 2));
+  if (want) {
+    const int pp = (a.n + 1) | 1;                                   // odd pitch >= n + 1
+    const size_t tables = pdf_fused_tables_bytes(a.n);
+    const size_t park = sizeof(double) * (size_t)PDF_ROWS * pp;
+    if (base + tables + park <= (size_t)227 * 1024) {               // a park of its own behind the tables
+      a.pp = pp; a.park_off = (int)((base + tables) / sizeof(double)); a.park_stride = WROWS * pp;
+      *fused = true;
+      return pdf_launch_impl<NT, TAIL1, MT, true>(a, base + tables + park, sm_count, st);
+    }
+    if (pp <= a.ldf && base + tables <= (size_t)227 * 1024) {       // alias the warp's interface rows (dead after the k loop)
+      a.pp = pp; a.park_off = 0; a.park_stride = WROWS * a.ldf;
+      *fused = true;
+      return pdf_launch_impl<NT, TAIL1, MT, true>(a, base + tables, sm_count, st);
+    }
+  }
+  return pdf_launch_impl<NT, TAIL1, MT, false>(a, base, sm_count, st);
 }
 
 static int sqr_model_build(ttirt_sqr_model *md, const int64_t *n, int64_t nxs, const double *xs, const int64_t *rk, const double *core) {
@@ -1219,6 +1372,13 @@ static int sqr_enqueue_chunk(ttirt_sqr_model *md, int64_t rows, int64_t D, const
     PdfArgs pa;
     pa.F = Fin; pa.ldf = md->ldf; pa.rows = (int)rows; pa.gp = md->d_gp + di.off_g; pa.pb = md->pb; pa.ksteps = di.ksteps;
     pa.r0 = di.r0; pa.n = di.n; pa.pdf = md->pdf; pa.ldp = md->cap;
+    TailArgs ta;
+    ta.pdf = md->pdf; ta.cdf = md->cdf; ta.ldp = md->cap; ta.rows = (int)rows; ta.n = di.n;
+    ta.x = md->d_xs + di.off_x; ta.h = md->d_h + di.off_x; ta.hc = md->d_hc + di.off_x;
+    ta.q = q + ldq * k; ta.z = z + ldz * k; ta.idx_out = idx_out ? idx_out + ldz * k : nullptr;
+    ta.idx = md->idx; ta.w1 = md->w1; ta.w2 = md->w2; ta.lf = lf; ta.first = (k == 0); ta.forward = forward;
+    ta.hist = update ? md->hist + (size_t)k * md->nbpad : nullptr;
+    pa.tail = ta; pa.pp = 0; pa.park_off = 0; pa.park_stride = 0;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (md->profile) {
       if (md->prof_used == md->prof_events.size()) {
@@ -1233,22 +1393,19 @@ static int sqr_enqueue_chunk(ttirt_sqr_model *md, int64_t rows, int64_t D, const
     }
     // the dimension's own grid size picks the variant inside the model's class (pb is the class's pitch)
     cudaError_t pe;
+    bool fused = false;
     const bool t1 = (di.n == 8 * (md->nt - 1) + 1);
-    if (md->nt == 3) pe = t1 ? pdf_launch<2, true, 4>(pa, md->sm_count, st) : pdf_launch<3, false, 4>(pa, md->sm_count, st);
-    else if (md->nt == 5) pe = t1 ? pdf_launch<4, true, 4>(pa, md->sm_count, st) : pdf_launch<5, false, 4>(pa, md->sm_count, st);
-    else pe = t1 ? pdf_launch<8, true, 2>(pa, md->sm_count, st) : pdf_launch<9, false, 2>(pa, md->sm_count, st);
+    if (md->nt == 3) pe = t1 ? pdf_launch<2, true, 4>(pa, md->sm_count, st, &fused) : pdf_launch<3, false, 4>(pa, md->sm_count, st, &fused);
+    else if (md->nt == 5) pe = t1 ? pdf_launch<4, true, 4>(pa, md->sm_count, st, &fused) : pdf_launch<5, false, 4>(pa, md->sm_count, st, &fused);
+    else pe = t1 ? pdf_launch<8, true, 2>(pa, md->sm_count, st, &fused) : pdf_launch<9, false, 2>(pa, md->sm_count, st, &fused);
     CKS(pe);
     LAUNCHED();
     if (e1) CKS(cudaEventRecord(e1, st));
-    TailArgs ta;
-    ta.pdf = md->pdf; ta.cdf = md->cdf; ta.ldp = md->cap; ta.rows = (int)rows; ta.n = di.n;
-    ta.x = md->d_xs + di.off_x; ta.h = md->d_h + di.off_x; ta.hc = md->d_hc + di.off_x;
-    ta.q = q + ldq * k; ta.z = z + ldz * k; ta.idx_out = idx_out ? idx_out + ldz * k : nullptr;
-    ta.idx = md->idx; ta.w1 = md->w1; ta.w2 = md->w2; ta.lf = lf; ta.first = (k == 0); ta.forward = forward;
-    ta.hist = update ? md->hist + (size_t)k * md->nbpad : nullptr;
-    sqr_tail_kernel<<<(unsigned)((rows + 255) / 256), 256, sizeof(int) * di.n, st>>>(ta);
-    LAUNCHED();
-    CKS(cudaGetLastError());
+    if (!fused) {
+      sqr_tail_kernel<<<(unsigned)((rows + 255) / 256), 256, sizeof(int) * di.n, st>>>(ta);
+      LAUNCHED();
+      CKS(cudaGetLastError());
+    }
     if (update) {
       const int nb = di.n - 1;
       sqr_bin_scan_kernel<<<1, 32, 0, st>>>(md->hist + (size_t)k * md->nbpad, nb, md->bin_start, md->bin_tile_start, md->cursor);
