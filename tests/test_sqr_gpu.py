@@ -325,7 +325,9 @@ def test_fused_and_separate_tail_agree_bit_for_bit(d, n, r, M, cores):
     q = np.asfortranarray(q)
     md = tt_irt_sqr.SqrModel(ns, xs, rk, c)
     try:
-        os.environ["TTIRT_SQR_FUSED"] = "2"          # fused in every class (the default leaves the r <= 64 class unfused)
+        # "2": fused tail in every class (the default leaves the r <= 64 class unfused); "1": fused tail without the fused
+        # interface update of small cores (a different summation order, so not bit-comparable with the sorted DMMA update)
+        os.environ["TTIRT_SQR_FUSED"] = "2" if n > 40 else "1"
         try:
             Zf, lf, idf = md.sample(q, want_idx=True)
             Qf, l2f = md.forward(Zf)
@@ -341,3 +343,31 @@ def test_fused_and_separate_tail_agree_bit_for_bit(d, n, r, M, cores):
     np.testing.assert_array_equal(lf, ls)
     np.testing.assert_array_equal(Qf, Qs)
     np.testing.assert_array_equal(l2f, l2s)
+
+
+@pytest.mark.parametrize("d,n,r,M", [(8, 17, 16, 20000), (11, 17, 16, 5000), (8, 17, 8, 7000), (6, 20, 12, 3000), (5, 9, 5, 999)])
+def test_fully_fused_step_of_small_cores_matches_the_oracle_and_the_sorted_path(d, n, r, M):
+    """Small cores (the whole core fits in shared memory next to the tiles): contraction, tail and interface update of a
+    dimension run in one kernel, without the sort.  Against the oracle inside the protocol; against the sorted DMMA update
+    (TTIRT_SQR_FUSED=1) inside the same protocol (the two differ by summation order only) with identical cells."""
+    ns, xs, rk, c = synth.make_tt(d, n, r, seed=80 + d)
+    q = synth.make_q(M, d, seed=81)
+    Zo, lo, io, cond, gap, lsens = tt_irt_sqr_oracle(ns, xs, rk, c, q, extras=True)
+    md = tt_irt_sqr.SqrModel(ns, xs, rk, c)
+    try:
+        l0 = tt_irt.kernel_launches()
+        Z, lF, idx = md.sample(q, want_idx=True)
+        launches = tt_irt.kernel_launches() - l0
+        os.environ["TTIRT_SQR_FUSED"] = "1"
+        try:
+            Z1, l1, i1 = md.sample(q, want_idx=True)
+        finally:
+            del os.environ["TTIRT_SQR_FUSED"]
+    finally:
+        md.close()
+    assert launches == d + 1                        # init + one kernel per dimension
+    st, fails = parity.compare(Z, lF, idx, Zo, lo, io, cond, gap, lsens)
+    assert not fails, (fails, st)
+    st1, fails1 = parity.compare(Z, lF, idx, Z1, l1, i1, cond, gap, lsens)      # the two update arithmetics: same protocol
+    assert not fails1 and st1["idx_flips"] == 0, (fails1, st1)
+    assert np.median(np.abs(Z - Z1)) <= 1e-15

@@ -393,8 +393,9 @@ __device__ __forceinline__ double cdf_step(double pprev, double pj, double hj) {
 
 // Everything after the cell i0 is known, :129-130, :146-195 (inverse) / tt_rt_sqr.m:141-163 (forward), in the reference's
 // operation order.  c1raw, p1raw, p2raw: unnormalised CDF and conditional at the cell's nodes; cmax the normalisation.
-__device__ __forceinline__ void tail_finish(const TailArgs &a, int m, int i0, double qk, double c1raw, double p1raw, double p2raw,
-                                            double cmax, int *sh_hist) {
+struct TailOut { int i0; double wa, wb; };
+__device__ __forceinline__ TailOut tail_finish(const TailArgs &a, int m, int i0, double qk, double c1raw, double p1raw, double p2raw,
+                                               double cmax, int *sh_hist) {
   const double C1 = __ddiv_rn(c1raw, cmax);                                                       // :146-149, :129-130
   const double f1 = __ddiv_rn(p1raw, cmax);
   const double f2 = __ddiv_rn(p2raw, cmax);
@@ -426,6 +427,8 @@ __device__ __forceinline__ void tail_finish(const TailArgs &a, int m, int i0, do
   a.idx[m] = i0; a.w1[m] = wa; a.w2[m] = wb;
   if (a.idx_out) a.idx_out[m] = i0;
   if (sh_hist) atomicAdd(&sh_hist[i0], 1);
+  TailOut o; o.i0 = i0; o.wa = wa; o.wb = wb;
+  return o;
 }
 
 // :113-195, one thread per sample, every operation in the reference's order (explicit round-to-nearest intrinsics: no
@@ -484,8 +487,8 @@ __global__ void __launch_bounds__(256) sqr_tail_kernel(TailArgs a) {
 // counts against q * mass with a 4-ulp guard band on either side (no division); if the two counts differ, or an increment
 // was negative, the bisection itself runs with the prefix sums recomputed in the same order.  Bit-identical to
 // sqr_tail_kernel on the same conditional.
-__device__ void fused_tail_row(const TailArgs &a, int m, const double *pr, const double *sx, const double *sh, const double *shc,
-                               int *sh_hist) {
+__device__ TailOut fused_tail_row(const TailArgs &a, int m, const double *pr, const double *sx, const double *sh, const double *shc,
+                                  int *sh_hist) {
   const int n = a.n;
   double pprev = pr[0];
   const double c0 = __dmul_rn(__dmul_rn(0.5, pprev), sh[0]);
@@ -536,7 +539,7 @@ __device__ void fused_tail_row(const TailArgs &a, int m, const double *pr, const
       c1raw = prefix(i0);
     }
   }
-  tail_finish(a, m, i0, qk, c1raw, zero ? sh[i0] : pr[i0], zero ? sh[i0 + 1] : pr[i0 + 1], cmax, sh_hist);
+  return tail_finish(a, m, i0, qk, c1raw, zero ? sh[i0] : pr[i0], zero ? sh[i0 + 1] : pr[i0 + 1], cmax, sh_hist);
 }
 
 struct PdfArgs {
@@ -546,6 +549,9 @@ struct PdfArgs {
   // fused tail (FUSE): the warp parks its pdf tile in shared memory (row pitch pp doubles, warp w at doubles
   // park_off + w * park_stride from the start of dynamic shared memory) and one lane per row finishes the dimension
   TailArgs tail; int pp; int park_off; int park_stride;
+  // fused interface update (small cores only: the whole core k sits in shared memory at core_off, [node][a][l], l fastest):
+  // after the tail every row multiplies its own two slabs (:197-207), no sort, no further kernel in this dimension
+  int upd; const double *core; double *Fout; int r1; int core_off;
 };
 
 __host__ __device__ inline size_t pdf_smem_bytes(int rows_cta, int ldf, int pb) {
@@ -580,6 +586,15 @@ __global__ void __launch_bounds__(32 * (PDF_WARPS + 1), 1) sqr_pdf_kernel(PdfArg
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (FUSE) {
     for (int i = tid; i < a.n; i += blockDim.x) { sx[i] = a.tail.x[i]; sh[i] = a.tail.h[i]; shc[i] = a.tail.hc[i]; sh_hist[i] = 0; }
+    if (a.upd) {
+      // [node][a][l] with a padded to a multiple of 4 (zero rows) and l to a multiple of 4 (zero columns)
+      double *Cs = reinterpret_cast<double *>(smem_raw) + a.core_off;
+      const int r1p = (a.r1 + 3) & ~3, r0p = (a.r0 + 3) & ~3;
+      for (int e = tid; e < r0p * a.n * r1p; e += blockDim.x) {
+        const int aa = e % r0p, j = (e / r0p) % a.n, l = e / (r0p * a.n);
+        Cs[((size_t)j * r0p + aa) * r1p + l] = (l < a.r1 && aa < a.r0) ? a.core[aa + (size_t)a.r0 * (j + (size_t)a.n * l)] : 0.0;
+      }
+    }
   }
   const int ntiles = (a.rows + PDF_ROWS - 1) / PDF_ROWS;
   const int nslices = (a.ksteps + PDF_KS - 1) / PDF_KS;
@@ -729,9 +744,40 @@ __global__ void __launch_bounds__(32 * (PDF_WARPS + 1), 1) sqr_pdf_kernel(PdfArg
         }
       }
       __syncwarp();
+      TailOut mine;
+      mine.i0 = 0; mine.wa = 0.0; mine.wb = 0.0;
       for (int row = lane; row < PDF_WROWS; row += 32)
-        if (m0 + row < a.rows) fused_tail_row(a.tail, m0 + row, park + row * a.pp, sx, sh, shc, a.tail.hist ? sh_hist : nullptr);
+        if (m0 + row < a.rows) mine = fused_tail_row(a.tail, m0 + row, park + row * a.pp, sx, sh, shc, a.tail.hist ? sh_hist : nullptr);
       __syncwarp();
+      if (a.upd) {
+        // (host side guarantees one row per lane, a park of its own -- the interface rows are intact -- and r_{k+1} <= 32)
+        const double *Cs = reinterpret_cast<const double *>(smem_raw) + a.core_off;
+        const int r1p = (a.r1 + 3) & ~3, r0p = (a.r0 + 3) & ~3;
+        const int LPR = r1p <= 16 ? 16 : 32;          // lanes per row: two rows at a time when the rank allows
+        const int l = lane & (LPR - 1), sub = lane / LPR;
+        const size_t slab = (size_t)r0p * r1p;
+        for (int rb = 0; rb < PDF_WROWS; rb += 32 / LPR) {
+          const int rr = rb + sub;
+          const int j0 = __shfl_sync(FULL, mine.i0, rr);
+          const double wa = __shfl_sync(FULL, mine.wa, rr), wb = __shfl_sync(FULL, mine.wb, rr);
+          if (l < r1p && m0 + rr < a.rows) {
+            const double *f = fw + rr * ldf;          // (32-byte aligned rows; columns [r0, r0p) are zero)
+            const double *s0 = Cs + (size_t)j0 * slab + l, *s1 = s0 + slab;
+            double u0a = 0.0, u0b = 0.0, u1a = 0.0, u1b = 0.0;
+            for (int aa = 0; aa < r0p; aa += 4) {
+              const double2 fl = *reinterpret_cast<const double2 *>(f + aa), fh = *reinterpret_cast<const double2 *>(f + aa + 2);
+              u0a = fma(fl.x, s0[0], u0a);       u1a = fma(fl.x, s1[0], u1a);
+              u0b = fma(fl.y, s0[r1p], u0b);     u1b = fma(fl.y, s1[r1p], u1b);
+              u0a = fma(fh.x, s0[2 * r1p], u0a); u1a = fma(fh.x, s1[2 * r1p], u1a);
+              u0b = fma(fh.y, s0[3 * r1p], u0b); u1b = fma(fh.y, s1[3 * r1p], u1b);
+              s0 += 4 * r1p; s1 += 4 * r1p;
+            }
+            const double u0 = __dadd_rn(u0a, u0b), u1 = __dadd_rn(u1a, u1b);
+            a.Fout[(size_t)(m0 + rr) * ldf + l] = l < a.r1 ? __dadd_rn(__dmul_rn(u0, wa), __dmul_rn(u1, wb)) : 0.0;   // :205
+          }
+        }
+        __syncwarp();
+      }
     } else {
 #pragma unroll
       for (int mt = 0; mt < PDF_MT; mt++) {
@@ -1122,9 +1168,10 @@ static cudaError_t pdf_launch_impl(const PdfArgs &a, size_t bytes, int sm_count,
   return cudaGetLastError();
 }
 
-// Launches the conditional-pdf kernel; *fused tells the caller whether the tail ran inside it (else sqr_tail_kernel follows).
+// Launches the conditional-pdf kernel; *fused tells the caller whether the tail ran inside it (else sqr_tail_kernel follows),
+// *fused_upd whether the interface update did too (the caller asks for it by filling a.core / a.Fout / a.r1 and a.upd = 1).
 template <int NT, bool TAIL1, int MT>
-static cudaError_t pdf_launch(PdfArgs a, int sm_count, cudaStream_t st, bool *fused) {
+static cudaError_t pdf_launch(PdfArgs a, int sm_count, cudaStream_t st, bool *fused, bool *fused_upd) {
   constexpr int PDF_ROWS = PDF_WARPS * 8 * MT, WROWS = 8 * MT;
   const size_t base = pdf_smem_bytes(PDF_ROWS, a.ldf, a.pb);
   *fused = false;
@@ -1134,6 +1181,9 @@ static cudaError_t pdf_launch(PdfArgs a, int sm_count, cudaStream_t st, bool *fu
   // there unless TTIRT_SQR_FUSED=2 asks for it.
   const char *fe = getenv("TTIRT_SQR_FUSED");
   const bool want = sqr_fuse_enabled() && (MT >= 4 || (fe && atoi(fe) >= 2));
+  const bool want_upd = a.upd != 0;
+  a.upd = 0;
+  *fused_upd = false;
   if (want) {
     const int pp = (a.n + 1) | 1;                                   // odd pitch >= n + 1
     const size_t tables = pdf_fused_tables_bytes(a.n);
@@ -1141,6 +1191,13 @@ static cudaError_t pdf_launch(PdfArgs a, int sm_count, cudaStream_t st, bool *fu
     if (base + tables + park <= (size_t)227 * 1024) {               // a park of its own behind the tables
       a.pp = pp; a.park_off = (int)((base + tables) / sizeof(double)); a.park_stride = WROWS * pp;
       *fused = true;
+      const int r1p = (a.r1 + 3) & ~3;
+      const size_t corebytes = sizeof(double) * (size_t)((a.r0 + 3) & ~3) * a.n * r1p;
+      if (want_upd && WROWS == 32 && r1p <= 32 && base + tables + park + corebytes <= (size_t)227 * 1024 && !(fe && atoi(fe) == 1)) {
+        a.upd = 1; a.core_off = (int)((base + tables + park) / sizeof(double));
+        *fused_upd = true;
+        return pdf_launch_impl<NT, TAIL1, MT, true>(a, base + tables + park + corebytes, sm_count, st);
+      }
       return pdf_launch_impl<NT, TAIL1, MT, true>(a, base + tables + park, sm_count, st);
     }
     if (pp <= a.ldf && base + tables <= (size_t)227 * 1024) {       // alias the warp's interface rows (dead after the k loop)
@@ -1379,6 +1436,8 @@ static int sqr_enqueue_chunk(ttirt_sqr_model *md, int64_t rows, int64_t D, const
     ta.idx = md->idx; ta.w1 = md->w1; ta.w2 = md->w2; ta.lf = lf; ta.first = (k == 0); ta.forward = forward;
     ta.hist = update ? md->hist + (size_t)k * md->nbpad : nullptr;
     pa.tail = ta; pa.pp = 0; pa.park_off = 0; pa.park_stride = 0;
+    // ask for the fused interface update too; the launcher grants it when the whole core fits next to the tiles
+    pa.upd = update ? 1 : 0; pa.core = md->d_core + di.off_c; pa.Fout = Fout; pa.r1 = di.r1; pa.core_off = 0;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (md->profile) {
       if (md->prof_used == md->prof_events.size()) {
@@ -1393,11 +1452,11 @@ static int sqr_enqueue_chunk(ttirt_sqr_model *md, int64_t rows, int64_t D, const
     }
     // the dimension's own grid size picks the variant inside the model's class (pb is the class's pitch)
     cudaError_t pe;
-    bool fused = false;
+    bool fused = false, fused_upd = false;
     const bool t1 = (di.n == 8 * (md->nt - 1) + 1);
-    if (md->nt == 3) pe = t1 ? pdf_launch<2, true, 4>(pa, md->sm_count, st, &fused) : pdf_launch<3, false, 4>(pa, md->sm_count, st, &fused);
-    else if (md->nt == 5) pe = t1 ? pdf_launch<4, true, 4>(pa, md->sm_count, st, &fused) : pdf_launch<5, false, 4>(pa, md->sm_count, st, &fused);
-    else pe = t1 ? pdf_launch<8, true, 2>(pa, md->sm_count, st, &fused) : pdf_launch<9, false, 2>(pa, md->sm_count, st, &fused);
+    if (md->nt == 3) pe = t1 ? pdf_launch<2, true, 4>(pa, md->sm_count, st, &fused, &fused_upd) : pdf_launch<3, false, 4>(pa, md->sm_count, st, &fused, &fused_upd);
+    else if (md->nt == 5) pe = t1 ? pdf_launch<4, true, 4>(pa, md->sm_count, st, &fused, &fused_upd) : pdf_launch<5, false, 4>(pa, md->sm_count, st, &fused, &fused_upd);
+    else pe = t1 ? pdf_launch<8, true, 2>(pa, md->sm_count, st, &fused, &fused_upd) : pdf_launch<9, false, 2>(pa, md->sm_count, st, &fused, &fused_upd);
     CKS(pe);
     LAUNCHED();
     if (e1) CKS(cudaEventRecord(e1, st));
@@ -1406,7 +1465,9 @@ static int sqr_enqueue_chunk(ttirt_sqr_model *md, int64_t rows, int64_t D, const
       LAUNCHED();
       CKS(cudaGetLastError());
     }
-    if (update) {
+    if (update && fused_upd) {
+      std::swap(Fin, Fout);
+    } else if (update) {
       const int nb = di.n - 1;
       sqr_bin_scan_kernel<<<1, 32, 0, st>>>(md->hist + (size_t)k * md->nbpad, nb, md->bin_start, md->bin_tile_start, md->cursor);
       LAUNCHED();
