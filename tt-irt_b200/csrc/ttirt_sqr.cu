@@ -374,7 +374,7 @@ constexpr int PDF_WARPS = 8;                  // MMA warps, two per SM sub-parti
 // k-step), 4 for the two lighter classes, whose few column tiles would otherwise leave a k-step too short to hide the
 // operand loads behind its DMMAs
 constexpr int PDF_KS = 16;                    // k-steps per B slice
-constexpr int PDF_STAGES = 3;
+// ring depth (template parameter PDF_STAGES): three slices, two in the light two-CTAs-per-SM configuration
 
 struct TailArgs {
   const double *pdf; double *cdf; int64_t ldp; int rows; int n;
@@ -554,8 +554,8 @@ struct PdfArgs {
   int upd; const double *core; double *Fout; int r1; int core_off;
 };
 
-__host__ __device__ inline size_t pdf_smem_bytes(int rows_cta, int ldf, int pb) {
-  return sizeof(double) * ((size_t)rows_cta * ldf + (size_t)PDF_STAGES * PDF_KS * 4 * pb) + 2 * PDF_STAGES * sizeof(uint64_t);
+__host__ __device__ inline size_t pdf_smem_bytes(int rows_cta, int ldf, int pb, int stages) {
+  return sizeof(double) * ((size_t)rows_cta * ldf + (size_t)stages * PDF_KS * 4 * pb) + 2 * stages * sizeof(uint64_t);
 }
 // with the fused tail: + grid tables and histogram, + the parked tiles unless they alias the interface rows
 __host__ inline size_t pdf_fused_tables_bytes(int n) { return sizeof(double) * 3 * (size_t)n + sizeof(int) * (((size_t)n + 1) & ~(size_t)1); }
@@ -570,8 +570,10 @@ __host__ inline size_t pdf_fused_tables_bytes(int n) { return sizeof(double) * 3
 //     already hold (one broadcast LDS and two DFMA per k-step) instead of a DMMA column tile that is 7/8 padding.
 //   * FUSE: the tail of the dimension (:113-195) runs here too: the warp parks its finished pdf tile in shared memory and one
 //     lane per row walks it (fused_tail_row), so the conditional never goes to global memory and sqr_tail_kernel is not launched.
-template <int NT, bool TAIL1, int PDF_MT, bool FUSE>
-__global__ void __launch_bounds__(32 * (PDF_WARPS + 1), 1) sqr_pdf_kernel(PdfArgs a) {
+//   * MINB = 2 (with two ring stages and 16 rows per warp): two CTAs per SM for the small-core class, whose warps walk
+//     contraction, tail and update one after the other and need neighbours to overlap them with.
+template <int NT, bool TAIL1, int PDF_MT, bool FUSE, int PDF_STAGES, int MINB>
+__global__ void __launch_bounds__(32 * (PDF_WARPS + 1), MINB) sqr_pdf_kernel(PdfArgs a) {
   constexpr int PDF_WROWS = 8 * PDF_MT;               // samples per warp
   constexpr int PDF_ROWS = PDF_WARPS * PDF_WROWS;     // samples per CTA tile
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1151,20 +1153,21 @@ static bool sqr_fuse_enabled() {
   return e ? atoi(e) != 0 : true;
 }
 
-template <int NT, bool TAIL1, int MT, bool FUSE>
+template <int NT, bool TAIL1, int MT, bool FUSE, int STG = 3, int MINB = 1>
 static cudaError_t pdf_launch_impl(const PdfArgs &a, size_t bytes, int sm_count, cudaStream_t st) {
   constexpr int PDF_ROWS = PDF_WARPS * 8 * MT;
   static bool attr_done[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 64 && !attr_done[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(sqr_pdf_kernel<NT, TAIL1, MT, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(sqr_pdf_kernel<NT, TAIL1, MT, FUSE, STG, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024 / MINB);
     if (e != cudaSuccess) return e;
     attr_done[dev] = true;
   }
   const int ntiles = (a.rows + PDF_ROWS - 1) / PDF_ROWS;
-  const int grid = ntiles < sm_count ? ntiles : sm_count;
-  sqr_pdf_kernel<NT, TAIL1, MT, FUSE><<<grid, 32 * (PDF_WARPS + 1), bytes, st>>>(a);
+  const int grid = ntiles < MINB * sm_count ? ntiles : MINB * sm_count;
+  sqr_pdf_kernel<NT, TAIL1, MT, FUSE, STG, MINB><<<grid, 32 * (PDF_WARPS + 1), bytes, st>>>(a);
   return cudaGetLastError();
 }
 
@@ -1173,7 +1176,7 @@ static cudaError_t pdf_launch_impl(const PdfArgs &a, size_t bytes, int sm_count,
 template <int NT, bool TAIL1, int MT>
 static cudaError_t pdf_launch(PdfArgs a, int sm_count, cudaStream_t st, bool *fused, bool *fused_upd) {
   constexpr int PDF_ROWS = PDF_WARPS * 8 * MT, WROWS = 8 * MT;
-  const size_t base = pdf_smem_bytes(PDF_ROWS, a.ldf, a.pb);
+  const size_t base = pdf_smem_bytes(PDF_ROWS, a.ldf, a.pb, 3);
   *fused = false;
   // Measured on B200: in the two lighter classes (32 rows per warp: every lane walks a row) the fused tail beats the
   // separate kernel by 8 % (r = 32, n = 33) to 14 % (r = 16, n = 17) of the step; in the r <= 64 / n <= 72 class (16 rows
@@ -1194,8 +1197,19 @@ static cudaError_t pdf_launch(PdfArgs a, int sm_count, cudaStream_t st, bool *fu
       const int r1p = (a.r1 + 3) & ~3;
       const size_t corebytes = sizeof(double) * (size_t)((a.r0 + 3) & ~3) * a.n * r1p;
       if (want_upd && WROWS == 32 && r1p <= 32 && base + tables + park + corebytes <= (size_t)227 * 1024 && !(fe && atoi(fe) == 1)) {
-        a.upd = 1; a.core_off = (int)((base + tables + park) / sizeof(double));
         *fused_upd = true;
+        a.upd = 1;
+        // two CTAs per SM when half-size tiles (16 rows per warp) and a two-stage ring fit twice (and TTIRT_SQR_LIGHT != 0)
+        const char *le = getenv("TTIRT_SQR_LIGHT");
+        const size_t lbase = pdf_smem_bytes(PDF_WARPS * 16, a.ldf, a.pb, 2), lpark = sizeof(double) * (size_t)PDF_WARPS * 16 * pp;
+        if constexpr (NT <= 3) {
+          if (lbase + tables + lpark + corebytes <= (size_t)113 * 1024 && !(le && atoi(le) == 0)) {
+            a.park_off = (int)((lbase + tables) / sizeof(double)); a.park_stride = 16 * pp;
+            a.core_off = (int)((lbase + tables + lpark) / sizeof(double));
+            return pdf_launch_impl<NT, TAIL1, 2, true, 2, 2>(a, lbase + tables + lpark + corebytes, sm_count, st);
+          }
+        }
+        a.core_off = (int)((base + tables + park) / sizeof(double));
         return pdf_launch_impl<NT, TAIL1, MT, true>(a, base + tables + park + corebytes, sm_count, st);
       }
       return pdf_launch_impl<NT, TAIL1, MT, true>(a, base + tables + park, sm_count, st);
