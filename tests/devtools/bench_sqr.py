@@ -29,6 +29,18 @@ import bench  # noqa: E402  (ClockSampler, measured_fp64_peak)
 from tt_irt_py import synth, tt_irt, tt_irt_sqr  # noqa: E402
 
 
+def _ncu_traffic(d, n, r, M):
+    """DRAM bytes per launch of sqr_pdf_kernel from the committed ncu capture, when this run has the same shape and chunk."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_sqr_ncu_traffic.json")) as f:
+            j = json.load(f)
+        if j["shape"] == "d=%d n=%d r=%d" % (d, n, r) and min(M, 1 << 18) == int(j["rows_per_launch"]):
+            return int(j["dram_bytes_read"]) + int(j["dram_bytes_write"])
+    except Exception:
+        pass
+    return None
+
+
 def dirt_main(a):
     """DIRT sampler loop (tt_dirt_sample.m:17-73): nlvl + 1 tt_irt_sqr levels with the reference maps between them, samples
     resident on the device; synthetic levels of one shape, truncated-normal reference on [-4, 4]."""
@@ -142,7 +154,7 @@ def main():
            "config": {"workload": "squared-density IRT (tt_irt_sqr.m), synthetic random TT of sqrt(density) d=%d n=%d r=%d, M=2^%d uniform seeds; "
                                   "inputs larger than L2 (q+Z %.1f GB)" % (d, n, r, a.log2m, 16.0 * M * d / 1e9)},
            "roofline": {"bound": "tensor", "achieved": kfl / kms / 1e9 if kms > 0 else None, "peak": peak, "unit": "TFLOP/s",
-                        "frac": (kfl / kms / 1e9) / peak if kms > 0 else None, "traffic": None, "kernel": "sqr_pdf_kernel",
+                        "frac": (kfl / kms / 1e9) / peak if kms > 0 else None, "traffic": _ncu_traffic(d, n, r, M), "kernel": "sqr_pdf_kernel",
                         "kernel_avg_ms": kms / max(kn, 1), "kernel_share_of_step": kms / (ms * a.steps), "peak_source": peak_src,
                         "algorithmic_flops_per_sample": W},
            "algorithmic_tflops_whole_step": W * M / (ms * 1e-3) / 1e12,

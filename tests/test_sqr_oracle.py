@@ -270,3 +270,25 @@ def test_forward_transform_pinned_by_the_reference_c_routine_at_grid_nodes():
     Zr, lr = _reference_tt_irt1(ns, xs, rk, np.concatenate([v ** 2 for v in f]), qn)
     np.testing.assert_allclose(Zr, pts, rtol=0, atol=1e-9)
     np.testing.assert_allclose(lr, ln, rtol=0, atol=1e-8)
+
+
+def test_python_mirror_checks_its_arguments_before_touching_the_library():
+    """tt_irt_sqr.py mirrors the Matlab function's own checks (tt_irt_sqr.m:37-39 grid size; q columns <= d) and the MEX's
+    (tracemult.c:83, :87 shape messages); they fire on the host, without a device."""
+    from tt_irt_py import tt_irt, tt_irt_sqr
+    ns, xs, rk, c = synth.make_tt(3, 5, 2, seed=1)
+    f = tt_irt.TTTensor(ns, rk, c)
+    q = synth.make_q(8, 3, seed=2)
+    with pytest.raises(ValueError):
+        tt_irt_sqr.tt_irt_sqr(xs[:-1], f, q)
+    with pytest.raises(ValueError):
+        tt_irt_sqr.tt_irt_sqr(xs, f, synth.make_q(8, 4, seed=2))
+    with pytest.raises(ValueError):
+        tt_irt_sqr.tt_rt_sqr(xs[:-2], f, q)
+    with pytest.raises(NotImplementedError):
+        tt_irt_sqr.tt_dirt_sample({"x0": xs, "F0": f, "x": xs, "F": [], "reference": "uni", "interpolation": "fourier"}, q)
+    with pytest.raises(NotImplementedError):
+        tt_irt_sqr.tt_dirt_inverse({"x0": xs, "F0": f, "x": xs, "F": [], "reference": "uni", "crossmethod": "build_ftt"}, q)
+    assert tt_irt_sqr._reference_sigma("uni") == 0.0 and tt_irt_sqr._reference_sigma("Normal") == 4.0
+    assert tt_irt_sqr._reference_sigma("normal 2.5") == 2.5
+    assert tt_irt_sqr.flops_per_sample(np.full(32, 65), np.array([1] + [64] * 31 + [1])) == 8938787

@@ -561,10 +561,11 @@ __host__ __device__ inline size_t pdf_smem_bytes(int rows_cta, int ldf, int pb, 
 __host__ inline size_t pdf_fused_tables_bytes(int n) { return sizeof(double) * 3 * (size_t)n + sizeof(int) * (((size_t)n + 1) & ~(size_t)1); }
 
 // Conditional pdf of one dimension for a chunk: pdf[j, m] = sum over pairs f_m[a] f_m[b] Gp[(a,b), j].
-//   * persistent CTAs over 128-sample tiles; eight MMA warps of 16 samples each and one producer warp;
-//   * B = Gp (up to 1.3 MB, L2-resident) streams through a three-stage ring of 16-k-step slices, each one TMA bulk copy
+//   * persistent CTAs over tiles of 8 * 8 PDF_MT samples; eight MMA warps of 8 PDF_MT samples each and one producer warp;
+//   * B = Gp (up to 1.3 MB, L2-resident) streams through a ring of PDF_STAGES 16-k-step slices, each one TMA bulk copy
 //     signalled on an mbarrier, released by the eight warps on a second mbarrier;
-//   * A is never stored: lane (g, t) multiplies f_g[a] (one broadcast LDS per k-step) with f_g[4c + t] (one LDS per column block);
+//   * A is never stored: lane (g, t) multiplies f_g[a] (32-byte loads, four k-steps at a time) with f_g[4c + t] (one LDS per
+//     column block);
 //   * pitches: ldf = 4 (mod 8) and pb = 4 (mod 8) doubles make the fragment loads bank-conflict free without a swizzle.
 //   * TAIL1 (n = 8 NT + 1, the usual 2^p + 1 grid): the lone last grid column is a DFMA dot product on the A values the lanes
 //     already hold (one broadcast LDS and two DFMA per k-step) instead of a DMMA column tile that is 7/8 padding.
