@@ -143,14 +143,38 @@ void sqr_free(void *p) {
 // geometry of the packed Gram operand
 // ------------------------------------------------------------------------------------------------
 // The conditional pdf at node j is  sum_{a,b} f_a f_b G[a,b,j]  (tt_irt_sqr.m:107-112, G = P{k} of :80, symmetric in a, b).
-// The contraction index is walked in DMMA k-steps of four pairs: for every column block c (b = 4c .. 4c+3) and every
-// a <= 4c+3 the k-step (c, a) holds the pairs (a, 4c + t), t = 0..3.  Pairs with a < 4c stand for (a, b) and (b, a) and
-// carry 2 G; the diagonal block 4c <= a <= 4c+3 is walked in full with weight 1.  r (r + 4) / 2 k-rows for r a multiple
-// of 4: 2176 instead of r^2 = 4096 at r = 64 (the exact half is 2080).
+// The contraction index is walked in DMMA k-steps of four pairs (a, b), a <= b, each pair once:
+//   off-diagonal part   for every column block c >= 1 (b = 4c .. 4c+3) and every a < 4c the k-step (c, a) holds the pairs
+//                       (a, 4c + t), t = 0..3, with 2 G (they stand for (a, b) and (b, a));  2 nc (nc - 1) k-steps, nc = ceil(r / 4)
+//   diagonal part       the ten pairs 4c <= a <= b <= 4c+3 of every block, packed four to a k-step in block order, with G on
+//                       the diagonal and 2 G off it;  ceil(10 nc / 4) k-steps
+// r (r + 1) / 2 k-rows for r a multiple of 4: 2080 instead of r^2 = 4096 at r = 64.  Pairs that reach past r carry zeros.
+__host__ __device__ inline int sqr_offdiag_ksteps(int r0) {
+  const int nc = (r0 + 3) >> 2;
+  return 2 * nc * (nc - 1);
+}
 __host__ __device__ inline int sqr_ksteps(int r0) {
-  int ks = 0;
-  for (int c = 0; 4 * c < r0; c++) ks += (4 * c + 4 < r0) ? 4 * c + 4 : r0;
-  return ks;
+  const int nc = (r0 + 3) >> 2;
+  return 2 * nc * (nc - 1) + ((10 * nc + 3) >> 2);
+}
+// pair p of the diagonal part -> (a, b): block p / 10, position in the block's upper triangle p % 10
+__host__ __device__ inline void sqr_diag_pair(int p, int &a, int &b) {
+  const int cc = p / 10, q = p - 10 * cc;
+  a = 4 * cc + (int)((0x3221110000ULL >> (4 * q)) & 15);
+  b = 4 * cc + (int)((0x3323213210ULL >> (4 * q)) & 15);
+}
+// k-row kr = 4 ks + t of the packed operand -> (a, b, weight); weight 0: padding
+__host__ __device__ inline void sqr_krow_pair(int kr, int r0, int &a, int &b, double &w) {
+  const int ks = kr >> 2, t = kr & 3, noff = sqr_offdiag_ksteps(r0);
+  if (ks < noff) {
+    int c = 1;
+    while (ks >= 2 * (c + 1) * c) c++;        // block c owns the k-steps [2 c (c - 1), 2 (c + 1) c)
+    a = ks - 2 * c * (c - 1); b = 4 * c + t; w = 2.0;
+  } else {
+    sqr_diag_pair(4 * (ks - noff) + t, a, b);
+    w = a == b ? 1.0 : 2.0;
+  }
+  if (b >= r0 || a >= r0) w = 0.0;
 }
 
 struct SqrDim {
@@ -334,26 +358,21 @@ __global__ void __launch_bounds__(1024) sqr_qr_block_kernel(const double *__rest
   }
 }
 
-// :74-80 as the packed DMMA operand: row 4 ks + t of k-step ks = (c, a) holds w G[a, 4c + t, :], G[a, b, j] = sum_s Pm[a,j,s] Pm[b,j,s]
+// :74-80 as the packed DMMA operand: k-row kr holds w G[a, b, :] for its pair (sqr_krow_pair), G[a, b, j] = sum_s Pm[a,j,s] Pm[b,j,s]
 __global__ void sqr_gram_pack_kernel(const double *__restrict__ Pm, int n, int s1, int r0, double *gp, int pb, int ksteps) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (int64_t)ksteps * 4 * n) return;
   const int j = (int)(e % n);
   const int kr = (int)(e / n);
-  const int ks = kr >> 2, t = kr & 3;
-  int c = 0, base = 0;
-  for (;;) {
-    const int cnt = (4 * c + 4 < r0) ? 4 * c + 4 : r0;
-    if (ks < base + cnt) break;
-    base += cnt; c++;
-  }
-  const int a = ks - base, b = 4 * c + t;
+  int a, b;
+  double w;
+  sqr_krow_pair(kr, r0, a, b, w);
   double v = 0.0;
-  if (b < r0) {
+  if (w != 0.0) {
     const int64_t m = (int64_t)n * s1;
     const double *pa = Pm + j + m * a, *pbp = Pm + j + m * b;
     for (int s = 0; s < s1; s++) v = fma(pa[(int64_t)n * s], pbp[(int64_t)n * s], v);
-    if (a < 4 * c) v *= 2.0;
+    v *= w;
   }
   gp[(int64_t)kr * pb + j] = v;
 }
@@ -662,39 +681,34 @@ __global__ void __launch_bounds__(32 * (PDF_WARPS + 1), MINB) sqr_pdf_kernel(Pdf
     for (int mt = 0; mt < PDF_MT; mt++) tl[mt] = 0.0;
     int ks = 0;
     uint32_t stage = it % PDF_STAGES, parity = (it / PDF_STAGES) & 1;
-    for (int c = 0; c < nchunk; c++) {
+    // one k-step: A values av (the products f[a] f[b] of the lane's pair) against the B fragments of the staged slice
+    auto kstep = [&](const double (&av)[PDF_MT], const double *bp) {
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++) {
+        const double b = bp[nt * 8];
+#pragma unroll
+        for (int mt = 0; mt < PDF_MT; mt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], av[mt], b);
+      }
+      if (TAIL1) {
+        const double bl = bp[8 * NT - g];      // row 4 kk + t, column 8 NT
+#pragma unroll
+        for (int mt = 0; mt < PDF_MT; mt++) tl[mt] = fma(av[mt], bl, tl[mt]);
+      }
+    };
+    auto release = [&]() {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + stage);
+      it++;
+      stage = it % PDF_STAGES; parity = (it / PDF_STAGES) & 1;
+    };
+    // off-diagonal part: pairs (a, 4c + t), a < 4c, in groups of four k-steps (4c is a multiple of four, slices hold
+    // sixteen): one barrier check and two 32-byte interface loads per group, the four steps unrolled so that the loads of
+    // one run under the MMAs of the previous
+    for (int c = 1; c < nchunk; c++) {
       double fb[PDF_MT];
 #pragma unroll
       for (int mt = 0; mt < PDF_MT; mt++) fb[mt] = fw[(mt * 8 + g) * ldf + 4 * c + t];
-      const int amax = (4 * c + 4 < a.r0) ? 4 * c + 4 : a.r0;
-      // one k-step: A = f[a] * f[4c + t] in registers, B fragments from the staged slice
-      auto kstep = [&](const double (&fa)[PDF_MT], const double *bp) {
-        double av[PDF_MT];
-#pragma unroll
-        for (int mt = 0; mt < PDF_MT; mt++) av[mt] = __dmul_rn(fa[mt], fb[mt]);
-#pragma unroll
-        for (int nt = 0; nt < NT; nt++) {
-          const double b = bp[nt * 8];
-#pragma unroll
-          for (int mt = 0; mt < PDF_MT; mt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], av[mt], b);
-        }
-        if (TAIL1) {
-          const double bl = bp[8 * NT - g];      // row 4 kk + t, column 8 NT
-#pragma unroll
-          for (int mt = 0; mt < PDF_MT; mt++) tl[mt] = fma(av[mt], bl, tl[mt]);
-        }
-      };
-      auto release = [&]() {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty + stage);
-        it++;
-        stage = it % PDF_STAGES; parity = (it / PDF_STAGES) & 1;
-      };
-      int aa = 0;
-      // groups of four k-steps (every full column block has a multiple of four, slices hold sixteen): one barrier check and
-      // two 32-byte interface loads per group, and the four steps unrolled so that the loads of one run under the MMAs of
-      // the previous
-      for (; aa + 4 <= amax; aa += 4) {
+      for (int aa = 0; aa < 4 * c; aa += 4) {
         const int kk = ks & (PDF_KS - 1);
         if (kk == 0) mbar_wait(full + stage, parity);
         double f4[PDF_MT][4];
@@ -707,24 +721,28 @@ __global__ void __launch_bounds__(32 * (PDF_WARPS + 1), MINB) sqr_pdf_kernel(Pdf
         const double *bp0 = Bs + (size_t)stage * SB + (kk * 4 + t) * a.pb + g;
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-          double fa[PDF_MT];
+          double av[PDF_MT];
 #pragma unroll
-          for (int mt = 0; mt < PDF_MT; mt++) fa[mt] = f4[mt][u];
-          kstep(fa, bp0 + u * 4 * a.pb);
+          for (int mt = 0; mt < PDF_MT; mt++) av[mt] = __dmul_rn(f4[mt][u], fb[mt]);
+          kstep(av, bp0 + u * 4 * a.pb);
         }
         ks += 4;
         if ((ks & (PDF_KS - 1)) == 0 || ks == a.ksteps) release();
       }
-      for (; aa < amax; aa++) {       // a rank that is not a multiple of four: the last column block's remainder
-        const int kk = ks & (PDF_KS - 1);
-        if (kk == 0) mbar_wait(full + stage, parity);
-        double fa[PDF_MT];
+    }
+    // diagonal part: lane t of k-step ds holds pair 4 ds + t of the blocks' upper triangles (both factors by its own index)
+    for (int ds = 0; ds < ((10 * nchunk + 3) >> 2); ds++) {
+      const int kk = ks & (PDF_KS - 1);
+      if (kk == 0) mbar_wait(full + stage, parity);
+      int pa, pb_;
+      sqr_diag_pair(4 * ds + t, pa, pb_);
+      if (pb_ >= 4 * nchunk) { pa = 0; pb_ = 0; }          // padding pairs of the last k-step (their k-rows are zero)
+      double av[PDF_MT];
 #pragma unroll
-        for (int mt = 0; mt < PDF_MT; mt++) fa[mt] = fw[(mt * 8 + g) * ldf + aa];
-        kstep(fa, Bs + (size_t)stage * SB + (kk * 4 + t) * a.pb + g);
-        ks++;
-        if ((ks & (PDF_KS - 1)) == 0 || ks == a.ksteps) release();
-      }
+      for (int mt = 0; mt < PDF_MT; mt++) av[mt] = __dmul_rn(fw[(mt * 8 + g) * ldf + pa], fw[(mt * 8 + g) * ldf + pb_]);
+      kstep(av, Bs + (size_t)stage * SB + (kk * 4 + t) * a.pb + g);
+      ks++;
+      if ((ks & (PDF_KS - 1)) == 0 || ks == a.ksteps) release();
     }
     if (FUSE) {
       // park the tile [row][node] (odd pitch: the row-per-lane reads of the tail are conflict free), then one lane per row
@@ -1396,21 +1414,17 @@ extern "C" int ttirt_sqr_model_get_sweep(const ttirt_sqr_model *md, int64_t k, d
   if (gram_out) {
     std::vector<double> gp((size_t)di.ksteps * 4 * md->pb);
     CKS(cudaMemcpy(gp.data(), md->d_gp + di.off_g, sizeof(double) * gp.size(), cudaMemcpyDeviceToHost));
-    // unpack: k-step (c, a) row t holds w G[a, 4c + t, :]; fill both (a, b) and (b, a)
-    int ks = 0;
-    for (int c = 0; 4 * c < di.r0; c++) {
-      const int amax = std::min(4 * c + 4, di.r0);
-      for (int a = 0; a < amax; a++, ks++)
-        for (int t = 0; t < 4; t++) {
-          const int b = 4 * c + t;
-          if (b >= di.r0) continue;
-          const double w = a < 4 * c ? 0.5 : 1.0;
-          for (int j = 0; j < di.n; j++) {
-            const double v = gp[((size_t)ks * 4 + t) * md->pb + j] * w;
-            gram_out[(size_t)a + (size_t)di.r0 * b + (size_t)di.r0 * di.r0 * j] = v;
-            if (a < 4 * c) gram_out[(size_t)b + (size_t)di.r0 * a + (size_t)di.r0 * di.r0 * j] = v;
-          }
-        }
+    // unpack: k-row kr holds w G[a, b, :] for its pair; fill both (a, b) and (b, a)
+    for (int kr = 0; kr < 4 * di.ksteps; kr++) {
+      int a, b;
+      double w;
+      sqr_krow_pair(kr, di.r0, a, b, w);
+      if (w == 0.0) continue;
+      for (int j = 0; j < di.n; j++) {
+        const double v = gp[(size_t)kr * md->pb + j] / w;
+        gram_out[(size_t)a + (size_t)di.r0 * b + (size_t)di.r0 * di.r0 * j] = v;
+        gram_out[(size_t)b + (size_t)di.r0 * a + (size_t)di.r0 * di.r0 * j] = v;
+      }
     }
   }
   if (rr_out) {
