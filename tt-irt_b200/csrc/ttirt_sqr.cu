@@ -1521,10 +1521,12 @@ static int sqr_enqueue_chunk(ttirt_sqr_model *md, int64_t rows, int64_t D, const
   return 0;
 }
 
-static int64_t sqr_chunk() {
+// samples per chunk: TTIRT_SQR_CHUNK, else 2^19 in the r <= 64 / n <= 72 class (measured 3.28 / 3.36 / 3.42 M samples/s at
+// 2^17 / 2^18 / 2^19: fewer partial waves of the persistent kernels) and 2^18 in the lighter classes (finer copy / compute overlap)
+static int64_t sqr_chunk(const ttirt_sqr_model *md) {
   const char *e = getenv("TTIRT_SQR_CHUNK");
   if (e && atoll(e) > 0) return atoll(e);
-  return (int64_t)1 << 18;
+  return (int64_t)1 << (md->nt == 9 ? 19 : 18);
 }
 
 static int sqr_transform_device(ttirt_sqr_model *md, int64_t M, int64_t D, const double *d_q, int64_t ldq, double *d_z,
@@ -1535,7 +1537,7 @@ static int sqr_transform_device(ttirt_sqr_model *md, int64_t M, int64_t D, const
   if (M == 0) return 0;
   CKS(cudaSetDevice(md->device));
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t chunk = std::min<int64_t>(M, sqr_chunk());
+  const int64_t chunk = std::min<int64_t>(M, sqr_chunk(md));
   if (md->cap < chunk) {
     CKS(cudaStreamSynchronize(st));
     if (sqr_ws_ensure(md, chunk, false) != 0) return -1;
@@ -1565,7 +1567,7 @@ static int sqr_transform_host(ttirt_sqr_model *md, int64_t M, int64_t D, const d
   if (M == 0) return 0;
   if (!h_q || !h_z || !h_lf) return aux_fail("null host buffer");
   CKS(cudaSetDevice(md->device));
-  const int64_t chunk = std::min<int64_t>(M, sqr_chunk());
+  const int64_t chunk = std::min<int64_t>(M, sqr_chunk(md));
   if (sqr_ws_ensure(md, chunk, true) != 0) return -1;
   cudaStream_t st = md->stream, cs = md->copy_stream;
   const int64_t cap = md->cap;
