@@ -30,12 +30,16 @@ from tt_irt_py import synth, tt_irt, tt_irt_sqr  # noqa: E402
 
 
 def _ncu_traffic(d, n, r, M):
-    """DRAM bytes per launch of sqr_pdf_kernel from the committed ncu capture, when this run has the same shape and chunk."""
+    """DRAM bytes per launch of sqr_pdf_kernel from the committed ncu capture of the same shape, scaled by the rows per launch
+    (the capture ran one 2^18-row chunk; traffic is per row: interface row in, conditional out; the default chunk of this
+    shape class is 2^19)."""
     try:
         with open(os.path.join(ROOT, "profiles", "r01_sqr_ncu_traffic.json")) as f:
             j = json.load(f)
-        if j["shape"] == "d=%d n=%d r=%d" % (d, n, r) and min(M, 1 << 18) == int(j["rows_per_launch"]):
-            return int(j["dram_bytes_read"]) + int(j["dram_bytes_write"])
+        if j["shape"] == "d=%d n=%d r=%d" % (d, n, r):
+            chunk = int(os.environ.get("TTIRT_SQR_CHUNK", 0)) or (1 << (19 if n > 40 else 18))
+            rows = min(M, chunk)
+            return int((int(j["dram_bytes_read"]) + int(j["dram_bytes_write"])) * rows / int(j["rows_per_launch"]))
     except Exception:
         pass
     return None
