@@ -5,13 +5,27 @@
     python bench.py --impl reference [...]                        the reference's own CPU path, host cores
 
 A "step" is one pass of the hot path (all d dimensions) over one batch of M synthetic seed points.
-Workload: BASELINE.json configs[2], synthetic random TT density d=32, n=65, r=64, M=2^24 uniform points
-per GPU (weak scaling: N=4 is configs[4]'s M=2^26).  `value` times the device-resident entry point
-(ttirt_sample_device, inputs already in HBM) with CUDA events on the launching stream; `e2e` times the
-reference's own C-ABI symbol `tt_irt1` on pinned HOST buffers (cores upload, marginalisation sweep, H2D of q,
-kernels, D2H of Z and lPz all inside the timed region).  One JSON line on stdout (rank 0).
+
+`value`  BASELINE.json configs[2] (synthetic random TT density d=32, n=65, r=64, M=2^24 uniform points) per GPU, through
+         the device-resident entry point (ttirt_sample_device, inputs already in HBM), CUDA events on the launching
+         stream, max over ranks.  At N>1 these are N replicas of the one-GPU job ("scaling": "weak"): samples are
+         independent (tt_irt1_int32.c:88-181), there is no collective, so this line only shows that the GPUs do not
+         disturb each other.
+`e2e`    the reference's own C-ABI symbol `tt_irt1` on pinned HOST buffers, everything inside the timed region (cores
+         upload, marginalisation sweep, H2D of q, kernels, D2H of Z and lPz).
+           N=1 : configs[2], M=2^24, one GPU.
+           N>1 : configs[4], ONE call of tt_irt1 by rank 0 on M=2^26 seed points with TTIRT_DEVICES=N -- the product's own
+                 multi-GPU path (ttirt_run_host: one host thread per device, contiguous row shards, cores fanned out
+                 by peer copies); the other ranks wait on a host-side (gloo) barrier.  Beside it: the same call with the
+                 seeds generated on the devices (ttirt_run_uniform_host, no q upload) and the box's host-copy ceiling
+                 measured with plain pinned copies on the same buffers.
+`roofline` the dominant kernel (transition_kernel) timed launch by launch with CUDA events in a serialised pass of the
+         same workload right after the timed region (the timed region itself overlaps chunks on two streams, where
+         per-launch events would also measure the overlap), against the live FP64 DMMA probe.
+One JSON line on stdout (rank 0).
 """
 import argparse
+import glob
 import json
 import os
 import subprocess
@@ -39,10 +53,12 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log2m", type=int, default=24, help="log2 of samples per GPU per step (default: configs[2], 2^24)")
+    ap.add_argument("--log2m-sharded", type=int, default=26, help="log2 of the samples of the one sharded call at N>1 (configs[4], 2^26)")
     ap.add_argument("--shape", default="32,65,64", help="d,n,r (default: the metric configuration)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-next-rows", action="store_true", help="skip the informational tt_irt_sqr figure appended at N=1")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the other BASELINE shapes appended at N=1")
     ap.add_argument("--cpu-samples-per-core", type=int, default=1 << 14)
     return ap.parse_args()
 
@@ -90,19 +106,32 @@ def cpu_baseline(ns, xs, rk, cores, d, samples_per_core, repeats=1):
     else:
         kind, blas = "port", ""
         oracle.build()
+    # The library is loaded (and run once) in THIS process before the workers fork: they inherit the mapping, and the
+    # driver's loaded-library record of this process shows oracle/_ref/... (the workers themselves end with the pool).
+    qw = synth.make_q(64, d, seed=999)
+    if kind == "reference":
+        oracle.ref_run(ns, xs, rk, cores, qw, width=32, blas=blas)
+        loaded = os.path.relpath(oracle.ref_lib_path(32, blas), ROOT)
+    else:
+        oracle.oracle_run(ns, xs, rk, cores, qw)
+        loaded = "oracle/liboracle_tt_irt1.so"
     _CPU_CTX["args"] = (kind, 32, blas, ns, xs, rk, cores)
     _CPU_CTX["qs"] = [synth.make_q(samples_per_core, d, seed=1000 + i) for i in range(ncores)]
     ctx = mp.get_context("fork")
     best = None
-    with ctx.Pool(ncores) as pool:
-        pool.map(_cpu_worker_warm, range(ncores))  # library load + first touch outside the timed region
+    pool = ctx.Pool(ncores)
+    try:
+        pool.map(_cpu_worker_warm, range(ncores))  # first touch outside the timed region
         for _ in range(repeats):
             t0 = time.perf_counter()
             pool.map(_cpu_worker, range(ncores), chunksize=1)
             dt = time.perf_counter() - t0
             best = dt if best is None else min(best, dt)
+    finally:
+        pool.close()
+        pool.join()
     total = samples_per_core * ncores
-    return {"value": total / best, "unit": UNIT, "cores": ncores, "kind": kind,
+    return {"value": total / best, "unit": UNIT, "cores": ncores, "kind": kind, "library": loaded,
             "sample": "%d samples (%d per core x %d processes, OPENBLAS_NUM_THREADS=1%s), %.1f s wall" %
                       (total, samples_per_core, ncores, ", BLAS=" + blas if blas else "", best)}, best
 
@@ -149,34 +178,6 @@ class ClockSampler(object):
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def bind_to_gpu_numa_node(gpu_index):
-    """Pin this rank (and, by first touch, its page-locked buffers) to the CPUs next to its GPU: with 8 ranks streaming
-    q / Z through host memory at once, remote-socket traffic is what limits the end-to-end figure."""
-    try:
-        out = subprocess.run(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
-                             capture_output=True, text=True, timeout=20).stdout.strip()
-        bdf = out.splitlines()[0].strip()
-        bdf = bdf.lower()
-        if bdf.startswith("00000000:"):
-            bdf = bdf[4:]
-        path = "/sys/bus/pci/devices/%s/local_cpulist" % bdf
-        with open(path) as f:
-            spec = f.read().strip()
-        cpus = set()
-        for part in spec.split(","):
-            if "-" in part:
-                lo, hi = part.split("-"); cpus.update(range(int(lo), int(hi) + 1))
-            elif part:
-                cpus.add(int(part))
-        cpus &= set(os.sched_getaffinity(0))
-        if cpus:
-            os.sched_setaffinity(0, cpus)
-            return "cpus %s (local to GPU %d at %s)" % (spec, gpu_index, bdf)
-    except Exception as e:  # no sysfs / no permission: run unbound
-        return "unbound (%s)" % type(e).__name__
-    return "unbound"
-
-
 def measured_fp64_peak():
     """FP64 roofline denominator: tools/fp64_peak (DMMA/DFMA register loops) run live on this GPU when the
     binary is present, else the figure recorded in profiles/r01_fp64_peak.md."""
@@ -194,6 +195,16 @@ def measured_fp64_peak():
     return FP64_PEAK_FALLBACK_TFLOPS, "recorded DMMA peak of profiles/r01_fp64_peak.md (fallback); MEASURED_PEAKS.json has no FP64 entry"
 
 
+def _c_symbol(lib, width):
+    """(callable, int numpy type) of the reference's entry point in the library of the given integer width."""
+    import ctypes as C
+    ct = C.c_int if width == 32 else C.c_longlong
+    dp, ip = C.POINTER(C.c_double), C.POINTER(ct)
+    lib.tt_irt1.restype = None
+    lib.tt_irt1.argtypes = [ct, ip, dp, ip, dp, ct, dp, dp, dp]
+    return lib.tt_irt1, (np.int32 if width == 32 else np.int64), ip, dp
+
+
 def main():
     a = parse()
     d, n, r = [int(x) for x in a.shape.split(",")]
@@ -207,6 +218,8 @@ def main():
         d, n, r, a.log2m, "; inputs >> L2" if M * d * 8 > (1 << 28) else "")
     config = {"workload": workload, "d": d, "n": n, "r": r, "M_per_gpu": M, "flops_per_sample": W,
               "bytes_per_sample": 8 * (2 * d + 1), "l2_policy": "inputs (%.1f GB of q and Z per step) far exceed the 126 MB L2" % (2 * M * d * 8 / 1e9)}
+    if world > 1:
+        config["value_is"] = "%d independent replicas of the one-GPU job (no data-path collective exists); the product's sharded call is e2e" % world
 
     # ---------------------------------------------------------------- reference arm (CPU) ----
     if a.impl == "reference":
@@ -239,11 +252,12 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (this framework has no CPU fallback)")
     torch.cuda.set_device(local_rank)
-    binding = bind_to_gpu_numa_node(local_rank) if world > 1 else "unbound (single rank)"
     dist = None
+    host_group = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        host_group = dist.new_group(backend="gloo")   # host-side waits: an NCCL barrier would spin ON the GPUs rank 0 is timing
     dev = torch.device("cuda", local_rank)
 
     def barrier():
@@ -266,7 +280,6 @@ def main():
     for _ in range(a.warmup):
         step()
     barrier()
-    md.profile_enable(True)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     l0 = tt_irt.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -279,6 +292,15 @@ def main():
     ms = e0.elapsed_time(e1)
     launches = tt_irt.kernel_launches() - l0
     clocks = sampler.stop() if sampler else None
+    # serialised pass of the same workload for the per-launch kernel time (see the module docstring)
+    md.profile_enable(True)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record(stream)
+    for _ in range(a.steps):
+        step()
+    p1.record(stream)
+    torch.cuda.synchronize()
+    ms_serial = p0.elapsed_time(p1)
     k_ms, k_launches, k_flops = md.profile_read()
     md.profile_enable(False)
     tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -288,62 +310,19 @@ def main():
     value = world * M * a.steps / (ms_all * 1e-3)
     checksum = float(lpz[: 1 << 10].sum().item())  # D2H read of a result so nothing is elided
 
-    # ---- e2e: the reference's own symbol tt_irt1 on pinned host buffers ---------------------------
     e2e = None
     if not a.no_e2e:
-        from ctypes import POINTER, c_double, c_int, cast
         del z, lpz
-        qh = torch.empty((d, M), dtype=torch.float64, pin_memory=True)
-        qh.copy_(q)
-        del q
-        torch.cuda.empty_cache()
-        zh = torch.empty((d, M), dtype=torch.float64, pin_memory=True)
-        lh = torch.empty((M,), dtype=torch.float64, pin_memory=True)
-        n32 = np.ascontiguousarray(ns, dtype=np.int32)
-        r32 = np.ascontiguousarray(rk, dtype=np.int32)
-        dp, ip = POINTER(c_double), POINTER(c_int)
-        os.environ["TTIRT_DEVICE"] = str(local_rank)
-        os.environ["TTIRT_DEVICES"] = "1"
-
-        def e2e_step():
-            lib.tt_irt1(c_int(d), n32.ctypes.data_as(ip), xs.ctypes.data_as(dp), r32.ctypes.data_as(ip), cores.ctypes.data_as(dp),
-                        c_int(M), cast(qh.data_ptr(), dp), cast(zh.data_ptr(), dp), cast(lh.data_ptr(), dp))
-
-        for _ in range(min(a.warmup, 2)):
-            e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(a.steps):
-            e2e_step()
-        barrier()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if dist is not None:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        if not bool(torch.isfinite(lh[: 1 << 12]).all()):
-            raise SystemExit("bench.py: e2e produced non-finite lPz")
-        e2e = {"value": world * M * a.steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(world * (M * d * 8 + cores.nbytes + xs.nbytes)),
-               "d2h_bytes_per_step": int(world * (M * d * 8 + M * 8)), "ms_per_step": 1e3 * dt / a.steps,
-               "api": "tt_irt1 (C-ABI symbol of tt_irt1_int32.so) on pinned host buffers; includes cores upload and marginalisation sweep"}
-        # the same call as the reference's own Python caller makes it: ordinary pageable numpy arrays (tt_irt.py:44-51)
         if world == 1:
-            qn = np.array(qh.numpy().T, order="F", copy=True)   # M x d, F-order, a pageable copy
-            zn = np.zeros((M, d), order="F"); ln = np.zeros(M)
-
-            def e2e_np():
-                lib.tt_irt1(c_int(d), n32.ctypes.data_as(ip), xs.ctypes.data_as(dp), r32.ctypes.data_as(ip), cores.ctypes.data_as(dp),
-                            c_int(M), qn.ctypes.data_as(dp), zn.ctypes.data_as(dp), ln.ctypes.data_as(dp))
-            e2e_np()
-            t0 = time.perf_counter()
-            for _ in range(a.steps):
-                e2e_np()
-            dtn = time.perf_counter() - t0
-            e2e["pageable_numpy_value"] = M * a.steps / dtn
-            e2e["pageable_numpy_note"] = "same call on pageable numpy arrays (bounce-buffer pipeline, %s host copy threads)" % os.environ.get("TTIRT_COPY_THREADS", "4")
-            if not np.array_equal(ln[:4096], lh[:4096].numpy()):
-                raise SystemExit("bench.py: pageable and pinned e2e results differ")
-            del qn, zn, ln
+            e2e = e2e_single(a, lib, torch, ns, xs, rk, cores, d, M, q, local_rank)
+            del q
+        else:
+            del q
+            torch.cuda.empty_cache()
+            dist.barrier(group=host_group)
+            if rank == 0:
+                e2e = e2e_sharded(a, lib, torch, ns, xs, rk, cores, d, world)
+            dist.barrier(group=host_group)   # ranks != 0 sleep here on the host while rank 0 drives all the GPUs
 
     if rank != 0:
         if dist is not None:
@@ -352,11 +331,15 @@ def main():
 
     peak, peak_src = measured_fp64_peak()
     ach = (k_flops / (k_ms * 1e-3)) / 1e12 if k_ms > 0 else 0.0
+    traffic, traffic_src = _ncu_traffic(M)
     roofline = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
-                "traffic": _ncu_traffic(M), "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                "traffic_source": traffic_src,
                 "kernel": "ttirt::transition_kernel<RT,NT,EXACT,TAIL1> (FP64 DMMA mma.sync.m8n8k4; 8 MMA warps + 4 tail warps per CTA)",
                 "kernel_launches_timed": k_launches, "kernel_avg_ms": k_ms / max(1, k_launches),
-                "kernel_share_of_step": k_ms / ms if ms > 0 else None,
+                "kernel_timing": "CUDA events around every launch in a serialised pass of the same %d steps right after the timed region" % a.steps,
+                "kernel_share_of_serial_step": k_ms / ms_serial if ms_serial > 0 else None,
+                "serial_ms_per_step": ms_serial / a.steps,
                 "flops_per_launch": k_flops / max(1, k_launches),
                 "peak_source": peak_src,
                 "whole_step_frac": (value / world * W / 1e12) / peak,
@@ -367,13 +350,288 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_all / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": config, "roofline": roofline, "cpu_baseline": cb, "e2e": e2e,
-            "gpu_launches": int(launches), "clocks": clocks, "checksum_lpz_1k": checksum, "host_binding": binding}
+            "gpu_launches": int(launches), "clocks": clocks, "checksum_lpz_1k": checksum}
+    if world == 1 and not a.no_other_configs and a.shape == "32,65,64":
+        md.close()
+        torch.cuda.empty_cache()
+        lib.ttirt_cache_clear()
+        line["other_configs"] = other_configs(torch, peak)
     if world == 1 and not a.no_next_rows:
         line["next_rows"] = _next_rows()
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# e2e, one GPU: the drop-in symbol on pinned host buffers (and on pageable numpy arrays, for information)
+# ------------------------------------------------------------------------------------------------
+def e2e_single(a, lib, torch, ns, xs, rk, cores, d, M, q_dev, local_rank):
+    from ctypes import c_int, cast
+    fn, it, ip, dp = _c_symbol(lib, 32)
+    qh = torch.empty((d, M), dtype=torch.float64, pin_memory=True)
+    qh.copy_(q_dev)
+    del q_dev
+    torch.cuda.empty_cache()
+    zh = torch.empty((d, M), dtype=torch.float64, pin_memory=True)
+    lh = torch.empty((M,), dtype=torch.float64, pin_memory=True)
+    n32 = np.ascontiguousarray(ns, dtype=it)
+    r32 = np.ascontiguousarray(rk, dtype=it)
+    os.environ["TTIRT_DEVICE"] = str(local_rank)
+    os.environ["TTIRT_DEVICES"] = "1"
+
+    def e2e_step():
+        fn(c_int(d), n32.ctypes.data_as(ip), xs.ctypes.data_as(dp), r32.ctypes.data_as(ip), cores.ctypes.data_as(dp),
+           c_int(M), cast(qh.data_ptr(), dp), cast(zh.data_ptr(), dp), cast(lh.data_ptr(), dp))
+
+    for _ in range(min(a.warmup, 2)):
+        e2e_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if not bool(torch.isfinite(lh[: 1 << 12]).all()):
+        raise SystemExit("bench.py: e2e produced non-finite lPz")
+    e2e = {"value": M * a.steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(M * d * 8 + cores.nbytes + xs.nbytes),
+           "d2h_bytes_per_step": int(M * d * 8 + M * 8), "ms_per_step": 1e3 * dt / a.steps,
+           "workload": "BASELINE.json configs[2]: M=2^%d, one GPU" % a.log2m,
+           "api": "tt_irt1 (C-ABI symbol of tt_irt1_int32.so) on pinned host buffers; includes cores upload and marginalisation sweep"}
+    # the same call as the reference's own Python caller makes it: ordinary pageable numpy arrays (tt_irt.py:44-51)
+    qn = np.array(qh.numpy().T, order="F", copy=True)   # M x d, F-order, a pageable copy
+    zn = np.zeros((M, d), order="F"); ln = np.zeros(M)
+
+    def e2e_np():
+        fn(c_int(d), n32.ctypes.data_as(ip), xs.ctypes.data_as(dp), r32.ctypes.data_as(ip), cores.ctypes.data_as(dp),
+           c_int(M), qn.ctypes.data_as(dp), zn.ctypes.data_as(dp), ln.ctypes.data_as(dp))
+    e2e_np()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        e2e_np()
+    dtn = time.perf_counter() - t0
+    e2e["pageable_numpy_value"] = M * a.steps / dtn
+    e2e["pageable_numpy_note"] = "same call on pageable numpy arrays (bounce-buffer pipeline, %s host copy threads)" % os.environ.get("TTIRT_COPY_THREADS", "4")
+    if not np.array_equal(ln[:4096], lh[:4096].numpy()):
+        raise SystemExit("bench.py: pageable and pinned e2e results differ")
+    return e2e
+
+
+# ------------------------------------------------------------------------------------------------
+# e2e, N GPUs: ONE call of the drop-in symbol, sharded over the N devices by the library (BASELINE configs[4])
+# ------------------------------------------------------------------------------------------------
+def e2e_sharded(a, lib, torch, ns, xs, rk, cores, d, ndev):
+    import ctypes as C
+    fn, it, ip, dp = _c_symbol(lib, 32)
+    log2m = a.log2m_sharded
+    qh = zh = lh = None
+    while log2m >= 22:   # the host may not have 2 x 17 GB to page-lock: halve (and say so) rather than fail
+        try:
+            Ms = 1 << log2m
+            qh = torch.empty((d, Ms), dtype=torch.float64, pin_memory=True)
+            zh = torch.empty((d, Ms), dtype=torch.float64, pin_memory=True)
+            lh = torch.empty((Ms,), dtype=torch.float64, pin_memory=True)
+            break
+        except RuntimeError:
+            qh = zh = lh = None
+            log2m -= 1
+    if qh is None:
+        return {"unavailable": "could not page-lock host buffers for the sharded call"}
+    Ms = 1 << log2m
+    gen = torch.Generator(device="cuda:0")
+    gen.manual_seed(4321)
+    step_rows = 1 << 22
+    for m0 in range(0, Ms, step_rows):   # seeds made on GPU 0, parked in the pinned array
+        blk = torch.rand((d, min(step_rows, Ms - m0)), dtype=torch.float64, device="cuda:0", generator=gen)
+        qh[:, m0:m0 + blk.shape[1]].copy_(blk)
+    del blk
+    torch.cuda.empty_cache()
+    n32 = np.ascontiguousarray(ns, dtype=it)
+    r32 = np.ascontiguousarray(rk, dtype=it)
+    os.environ["TTIRT_DEVICE"] = "0"
+    os.environ["TTIRT_DEVICES"] = str(ndev)
+    qp, zp, lp_ = C.cast(qh.data_ptr(), dp), C.cast(zh.data_ptr(), dp), C.cast(lh.data_ptr(), dp)
+
+    def call():
+        fn(C.c_int(d), n32.ctypes.data_as(ip), xs.ctypes.data_as(dp), r32.ctypes.data_as(ip), cores.ctypes.data_as(dp),
+           C.c_int(Ms), qp, zp, lp_)
+
+    def timed(f, steps, warm):
+        for _ in range(warm):
+            f()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            f()
+        return (time.perf_counter() - t0) / steps
+
+    dt = timed(call, a.steps, min(a.warmup, 2))
+    if not bool(torch.isfinite(lh[:: max(1, Ms // 4096)]).all()):
+        raise SystemExit("bench.py: sharded e2e produced non-finite lPz")
+    chk_rows = slice(Ms - 4096, Ms)    # rows of the last device's shard, compared with a one-device call on the same seeds below
+    last = lh[chk_rows].clone()
+    e2e = {"value": Ms / dt, "unit": UNIT, "h2d_bytes_per_step": int(Ms * d * 8 + cores.nbytes + xs.nbytes),
+           "d2h_bytes_per_step": int(Ms * d * 8 + Ms * 8), "ms_per_step": 1e3 * dt,
+           "workload": "BASELINE.json configs[4]: ONE tt_irt1 call, M=2^%d seed points sharded over %d B200 by the library (TTIRT_DEVICES=%d)" % (log2m, ndev, ndev),
+           "api": "tt_irt1 (C-ABI symbol of tt_irt1_int32.so) called once by rank 0 on pinned host buffers; ttirt_run_host underneath: one host "
+                  "thread per device, contiguous row shards, cores uploaded to device 0 and fanned out by peer copies, no collective",
+           "devices": ndev}
+    if log2m != a.log2m_sharded:
+        e2e["note"] = "host memory allowed only 2^%d seed points to be page-locked (asked for 2^%d)" % (log2m, a.log2m_sharded)
+    # same seeds, last 2^20 rows on ONE device: the shard boundaries must not change a bit
+    os.environ["TTIRT_DEVICES"] = "1"
+    sub = 1 << 20
+    q1 = qh[:, Ms - sub:].contiguous().pin_memory()
+    z1 = torch.empty((d, sub), dtype=torch.float64, pin_memory=True); l1 = torch.empty((sub,), dtype=torch.float64, pin_memory=True)
+    fn(C.c_int(d), n32.ctypes.data_as(ip), xs.ctypes.data_as(dp), r32.ctypes.data_as(ip), cores.ctypes.data_as(dp),
+       C.c_int(sub), C.cast(q1.data_ptr(), dp), C.cast(z1.data_ptr(), dp), C.cast(l1.data_ptr(), dp))
+    e2e["same_bits_as_one_device_on_last_rows"] = bool(torch.equal(l1[-4096:], last)) and bool(torch.equal(z1[:, -4096:], zh[:, chk_rows]))
+    del q1, z1, l1
+    os.environ["TTIRT_DEVICES"] = str(ndev)
+
+    # ---- the same call without the q upload: seeds generated on the devices ----
+    n64 = np.ascontiguousarray(ns, dtype=np.int64)
+    r64 = np.ascontiguousarray(rk, dtype=np.int64)
+    lp64 = C.POINTER(C.c_longlong)
+    ru = lib.ttirt_run_uniform_host
+    ru.restype = C.c_int
+    ru.argtypes = [C.c_longlong, lp64, dp, lp64, dp, C.c_longlong, C.c_longlong, C.c_ulonglong, dp, dp, dp, C.c_int, C.c_int, C.c_int]
+
+    def call_nu():
+        rc = ru(d, n64.ctypes.data_as(lp64), xs.ctypes.data_as(dp), r64.ctypes.data_as(lp64), cores.ctypes.data_as(dp), Ms, 0, 2026,
+                None, zp, lp_, 0, 0, ndev)
+        if rc != 0:
+            raise SystemExit("bench.py: ttirt_run_uniform_host failed")
+
+    dtn = timed(call_nu, a.steps, 1)
+    e2e["no_upload"] = {"value": Ms / dtn, "unit": UNIT, "ms_per_step": 1e3 * dtn, "h2d_bytes_per_step": int(cores.nbytes + xs.nbytes),
+                        "d2h_bytes_per_step": int(Ms * d * 8 + Ms * 8),
+                        "api": "ttirt_run_uniform_host: same sharded call, Philox seeds generated on the devices (no q upload), Z and lPz to pinned host buffers"}
+    lib.ttirt_cache_clear()
+    torch.cuda.empty_cache()
+
+    # ---- the box's host-copy ceiling: plain pinned copies of the same shards on all devices at once ----
+    try:
+        e2e["host_copy_ceiling"] = host_copy_ceiling(torch, qh, zh, d, Ms, ndev)
+        cg = e2e["host_copy_ceiling"]["duplex_GBps"]
+        bps = 8 * (2 * d + 1)
+        e2e["host_copy_ceiling"]["samples_per_s_at_ceiling"] = cg * 1e9 / bps
+        e2e["frac_of_host_copy_ceiling"] = e2e["value"] * bps / (cg * 1e9)
+        e2e["no_upload"]["frac_of_d2h_ceiling"] = e2e["no_upload"]["value"] * (8 * (d + 1)) / (e2e["host_copy_ceiling"]["d2h_only_GBps"] * 1e9)
+    except Exception as ex:   # noqa: BLE001
+        e2e["host_copy_ceiling"] = {"unavailable": "%s: %s" % (type(ex).__name__, str(ex)[:200])}
+    return e2e
+
+
+def host_copy_ceiling(torch, qh, zh, d, Ms, ndev):
+    """GB/s of plain cudaMemcpyAsync between the pinned arrays of the sharded call and device buffers, every device at once,
+    each copying its own row shard (d column segments per chunk of 2^20 rows, as the pipeline does): H2D alone, D2H alone
+    and both directions together.  This is the ceiling of any end-to-end figure that streams q in and Z out on this box."""
+    rows = Ms // ndev
+    chunk = 1 << 20
+    bufs = []
+    for g in range(ndev):
+        with torch.cuda.device(g):
+            bufs.append((torch.empty((d, chunk), dtype=torch.float64, device="cuda:%d" % g),
+                         torch.empty((d, chunk), dtype=torch.float64, device="cuda:%d" % g),
+                         torch.cuda.Stream(device=g), torch.cuda.Stream(device=g)))
+
+    def run(h2d, d2h):
+        for g in range(ndev):
+            torch.cuda.synchronize(g)
+        t0 = time.perf_counter()
+        for c0 in range(0, rows, chunk):
+            for g in range(ndev):
+                di, do, s1, s2 = bufs[g]
+                m0 = g * rows + c0
+                w = min(chunk, rows - c0)
+                if h2d:
+                    with torch.cuda.stream(s1):
+                        di[:, :w].copy_(qh[:, m0:m0 + w], non_blocking=True)
+                if d2h:
+                    with torch.cuda.stream(s2):
+                        zh[:, m0:m0 + w].copy_(do[:, :w], non_blocking=True)
+        for g in range(ndev):
+            torch.cuda.synchronize(g)
+        dt = time.perf_counter() - t0
+        return (int(h2d) + int(d2h)) * rows * ndev * d * 8 / dt / 1e9
+
+    run(True, True)
+    out = {"h2d_only_GBps": run(True, False), "d2h_only_GBps": run(False, True), "duplex_GBps": run(True, True),
+           "how": "pinned host arrays of the sharded call <-> device buffers, %d devices at once, chunks of 2^20 rows x %d column segments, both copy engines" % (ndev, d)}
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# the other BASELINE shapes (N=1 only): device-resident and through the C symbol, a few steps each
+# ------------------------------------------------------------------------------------------------
+def other_configs(torch, peak_tflops):
+    """BASELINE.json configs[3], [1] and [0] (parity-test shapes, not the metric): samples/s device-resident
+    (ttirt_sample_device, CUDA events) and through the drop-in C symbol on pinned host buffers, with the two rooflines that
+    could bound them (FP64 pipe: flops per sample x rate / measured DMMA peak; HBM: 8(2d+1) bytes per sample x rate /
+    measured copy bandwidth).  Information for the record; failures here never touch the headline line."""
+    import ctypes as C
+    from tt_irt_py import tt_irt
+    out = {}
+    cases = [("configs[3] lorenz-40 shape, int64 ABI", 40, 33, 32, 22, 64, (-3.0, 3.0), 3, 3),
+             ("configs[1] inverse-diffusion shape", 11, 17, 16, 20, 32, (-3.0 ** 0.5, 3.0 ** 0.5), 10, 3),
+             ("configs[0] shock-absorber shape", 8, 17, 8, 14, 32, (0.0, 1.0), 50, 5)]
+    for name, d, n, r, log2m, width, (lo, hi), steps, warm in cases:
+        try:
+            M = 1 << log2m
+            ns, xs, rk, cores = synth.make_tt(d, n, r, seed=77, lo=lo, hi=hi)
+            Wf = synth.flops_per_sample(ns, rk)
+            md = tt_irt.Model(ns, xs, rk, cores, device=0)
+            q = torch.rand((d, M), dtype=torch.float64, device="cuda:0")
+            z = torch.empty_like(q); l = torch.empty((M,), dtype=torch.float64, device="cuda:0")
+            st = torch.cuda.current_stream()
+
+            def step():
+                md.sample_device(M, q.data_ptr(), M, z.data_ptr(), M, l.data_ptr(), None, tt_irt.MODE_FAST, st.cuda_stream)
+            for _ in range(warm):
+                step()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            l0 = tt_irt.kernel_launches()
+            e0.record(st)
+            for _ in range(steps):
+                step()
+            e1.record(st)
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            launches = (tt_irt.kernel_launches() - l0) // steps
+            val = M / (ms * 1e-3)
+            so = os.path.join(ROOT, "tt-irt_b200", "tt_irt_py", "tt_irt1_int32.so") if width == 32 else os.path.join(ROOT, "tt-irt_b200", "lib", "libtt_irt1_int64.so")
+            lw = tt_irt.load_library() if width == 32 else C.CDLL(so)
+            fn, it, ip, dp = _c_symbol(lw, width)
+            ct = C.c_int if width == 32 else C.c_longlong
+            qh = torch.empty((d, M), dtype=torch.float64, pin_memory=True); qh.copy_(q)
+            zh = torch.empty((d, M), dtype=torch.float64, pin_memory=True); lh = torch.empty((M,), dtype=torch.float64, pin_memory=True)
+            nn, rr = np.ascontiguousarray(ns, dtype=it), np.ascontiguousarray(rk, dtype=it)
+            os.environ["TTIRT_DEVICE"] = "0"; os.environ["TTIRT_DEVICES"] = "1"
+
+            def call():
+                fn(ct(d), nn.ctypes.data_as(ip), xs.ctypes.data_as(dp), rr.ctypes.data_as(ip), cores.ctypes.data_as(dp), ct(M),
+                   C.cast(qh.data_ptr(), dp), C.cast(zh.data_ptr(), dp), C.cast(lh.data_ptr(), dp))
+            for _ in range(warm):
+                call()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                call()
+            dt = (time.perf_counter() - t0) / steps
+            ok = bool(torch.isfinite(lh).all()) and bool(torch.equal(lh, l.cpu()))
+            out[name] = {"d": d, "n": n, "r": r, "M": M, "abi_width": width, "value": val, "ms_per_step": ms, "launches_per_step": int(launches),
+                         "e2e_value": M / dt, "e2e_ms_per_call": 1e3 * dt, "e2e_matches_device_resident_bit_for_bit": ok,
+                         "flops_per_sample": Wf, "frac_of_fp64_peak": val * Wf / 1e12 / peak_tflops,
+                         "frac_of_hbm_stream_bound": val * 8 * (2 * d + 1) / 1e9 / _hbm_peak(),
+                         "binding_roofline": "fp64" if Wf / (8.0 * (2 * d + 1)) > peak_tflops * 1e3 / _hbm_peak() else "hbm"}
+            md.close()
+            del q, z, l, qh, zh, lh
+            lw.ttirt_cache_clear()
+            torch.cuda.empty_cache()
+        except Exception as ex:   # noqa: BLE001
+            out[name] = {"unavailable": "%s: %s" % (type(ex).__name__, str(ex)[:200])}
+    return out
 
 
 def _next_rows():
@@ -392,15 +650,18 @@ def _next_rows():
 
 
 def _ncu_traffic(M):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (same chunk size), else None."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
-            j = json.load(f)
-        if min(M, 1 << 20) == int(j["rows_per_launch"]):
-            return int(j["dram_bytes_read"]) + int(j["dram_bytes_write"])
-    except Exception:
-        pass
-    return None
+    """DRAM bytes per launch of the dominant kernel from the newest committed `ncu --set full` capture of this kernel
+    (profiles/rNN_ncu_traffic.json, written from the round's own capture by tools/ncu_traffic.py; same rows per launch), else None."""
+    best = (None, None)
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_traffic.json"))):
+        try:
+            with open(f) as fh:
+                j = json.load(fh)
+            if "transition_kernel" in j.get("kernel", "") and min(M, 1 << 20) == int(j["rows_per_launch"]):
+                best = (int(j["dram_bytes_read"]) + int(j["dram_bytes_write"]), os.path.relpath(f, ROOT))
+        except Exception:
+            continue
+    return best
 
 
 def _hbm_peak():

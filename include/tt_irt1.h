@@ -52,8 +52,9 @@ extern "C" {
  * one line to stderr and fills z and lPz with NaN; it never aborts the host process.
  * Caller arrays in ordinary pageable memory (numpy, mxArray) go through page-locked bounce buffers filled and drained
  * by a few host threads (TTIRT_COPY_THREADS, default 4; TTIRT_NO_STAGING=1 leaves the staging to the driver).
- * Environment: TTIRT_MODE=fast|strict (default fast), TTIRT_DEVICES=<count>|all (default 1),
- * TTIRT_DEVICE=<first ordinal> (default 0), TTIRT_CHUNK=<samples per chunk>, TTIRT_CACHE=0 (free all device
+ * Environment: TTIRT_MODE=fast|strict (default fast), TTIRT_DEVICES=<count>|all|auto (default auto: one device per
+ * 2^22 seed points, at most all visible ones from TTIRT_DEVICE on -- a batch of M >= 2^22 * N is sharded over N GPUs,
+ * a small one stays on one), TTIRT_DEVICE=<first ordinal> (default 0), TTIRT_CHUNK=<samples per chunk>, TTIRT_CACHE=0 (free all device
  * memory before returning), TTIRT_TRACE=1 (host-side phase times on stderr), TTIRT_VERBOSE=1.
  */
 TTIRT_API void tt_irt1(TTIRT_INT d, TTIRT_INT *n, double *xs, TTIRT_INT *ttrank, double *ttcore, TTIRT_INT M,
@@ -92,12 +93,20 @@ TTIRT_API int ttirt_sample_host(ttirt_model *model, int64_t M, const double *h_q
                       int32_t *h_idx, int64_t ld, int mode);
 
 /* Whole call on host buffers: create models on n_devices devices starting at first_device, shard the
- * M rows contiguously across them (one host thread per device, no collective).  Grid and cores are uploaded and
+ * M rows contiguously across them (one host thread per device, no collective).  Grid and cores are uploaded (to the
+ * first device from the host, to the others from there by peer copies; TTIRT_FANOUT=0: every device from the host) and
  * the sweep is run on every call; only device allocations are reused between calls (see ttirt_cache_clear).
  * This is what tt_irt1() runs.  0 on success. */
 TTIRT_API int ttirt_run_host(int64_t d, const int64_t *n, const double *xs, const int64_t *ttrank,
                    const double *ttcore, int64_t M, const double *h_q, double *h_z, double *h_lpz,
                    int32_t *h_idx, int mode, int first_device, int n_devices);
+
+/* Host-side arithmetic of the multi-device decomposition (no device needed): the contiguous row range [*m0, *m1) of
+ * shard `shard` out of `n_shards` for a batch of M samples (what ttirt_run_host gives device first_device + shard; ranks
+ * of a multi-process job use the same split), and the device count the drop-in call picks when TTIRT_DEVICES is unset
+ * (one device per 2^22 seed points, at most `visible`).  ttirt_shard_rows returns 0, or -1 on bad arguments. */
+TTIRT_API int ttirt_shard_rows(int64_t M, int n_shards, int shard, int64_t *m0, int64_t *m1);
+TTIRT_API int ttirt_auto_devices(int64_t M, int visible);
 
 /* Per-launch CUDA-event timing of the dominant kernel (the fused transition kernel) for calls to
  * ttirt_sample_device on this model: enable(1) clears and starts, read() synchronises and returns the summed
@@ -147,6 +156,12 @@ TTIRT_API int ttirt_sample_lattice_host(ttirt_model *model, int64_t M, int64_t m
                                         const double *shift, double *h_q, double *h_z, double *h_lpz, int64_t ld, int mode);
 TTIRT_API int ttirt_sample_uniform_host(ttirt_model *model, int64_t M, int64_t m0, uint64_t seed, double *h_q, double *h_z,
                                         double *h_lpz, int64_t ld, int mode);
+
+/* The whole call (as ttirt_run_host: models on n_devices devices, contiguous row shards) with the seeds generated on the
+ * devices: Philox indices [m0, m0 + M), identical results for every device count, no q upload.  h_q may be NULL. */
+TTIRT_API int ttirt_run_uniform_host(int64_t d, const int64_t *n, const double *xs, const int64_t *ttrank,
+                                     const double *ttcore, int64_t M, int64_t m0, uint64_t seed, double *h_q, double *h_z,
+                                     double *h_lpz, int mode, int first_device, int n_devices);
 
 /* Uniform -> truncated normal on [-sigma, sigma], reference matlab/samplers/randref.m:31-33:
  *   y = erfinv((u - 0.5) * erf(sigma / sqrt(2)) / 0.5) * sqrt(2) */

@@ -90,6 +90,17 @@ def test_python_mirror_raises_without_device(libs):
         tt_irt.Model(ns, xs, rk, c)
     with pytest.raises(RuntimeError):
         tt_irt.run_host(ns, xs, rk, c, synth.make_q(8, 3))
+    with pytest.raises(RuntimeError):
+        tt_irt.run_uniform_host(ns, xs, rk, c, 8, seed=1)
+    # the void entry points NaN-fill; their Python mirrors turn that into an exception with the library's message
+    f = tt_irt.TTTensor(ns, rk, c)
+    with pytest.raises(RuntimeError, match="no CUDA device|failed"):
+        tt_irt.tt_irt1(synth.make_q(8, 3), f, xs)
+    from tt_irt_py import tt_irt_sqr
+    with pytest.raises(RuntimeError):
+        tt_irt_sqr.tt_irt_sqr(xs, f, synth.make_q(8, 3))
+    with pytest.raises(RuntimeError):
+        tt_irt_sqr.tt_rt_sqr(xs, f, np.zeros((8, 3), order="F"))
 
 
 def test_wrapper_repacks_discontiguous_cores():

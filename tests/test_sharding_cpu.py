@@ -1,6 +1,9 @@
 """Multi-process (gloo, world_size 2) test of the sample-sharding logic used at N > 1 GPUs: ranks own
 contiguous row ranges, there is no data-path collective, and the union of the shards equals the
-single-process result.  Runs the CPU oracle in place of the GPU kernels (test infrastructure only)."""
+single-process result.  The row split and the device policy are the PRODUCT's own host code (ttirt_shard_rows,
+ttirt_auto_devices, exported by the C-ABI library and used by ttirt_run_host / tt_irt1 themselves; they need no device);
+the CPU oracle stands in for the GPU kernels on each shard (test infrastructure only)."""
+import ctypes
 import os
 import socket
 import sys
@@ -27,7 +30,12 @@ def _worker(rank, world, port, out_dir):
     M, d = 1000, 5
     ns, xs, rk, c = synth.make_tt(d, 9, 4, seed=3)
     q = synth.make_q(M, d, seed=4)                     # every rank regenerates the same seeds
-    m0, m1 = M * rank // world, M * (rank + 1) // world  # the contiguous split of ttirt_run_host
+    from tt_irt_py import tt_irt
+    lib = tt_irt.load_library()
+    a, b = ctypes.c_longlong(-1), ctypes.c_longlong(-1)
+    lib.ttirt_shard_rows.argtypes = [ctypes.c_longlong, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong)]
+    assert lib.ttirt_shard_rows(M, world, rank, ctypes.byref(a), ctypes.byref(b)) == 0   # the split ttirt_run_host uses
+    m0, m1 = a.value, b.value
     Z, l = oracle.oracle_run(ns, xs, rk, c, q[m0:m1])
     # the only communication of the bench: barrier + max-over-ranks of the timing scalar
     t = torch.tensor([float(rank + 1)])
@@ -52,3 +60,28 @@ def test_row_shards_reassemble_to_the_full_result(tmp_path, oracle_mod):
         s = np.load(os.path.join(str(tmp_path), "shard%d.npz" % r))
         assert np.array_equal(s["Z"], Z[int(s["m0"]):int(s["m1"])])
         assert np.array_equal(s["l"], l[int(s["m0"]):int(s["m1"])])
+
+
+def test_product_shard_arithmetic_and_device_policy():
+    """ttirt_shard_rows / ttirt_auto_devices (host code of the product library, no device needed): shards are contiguous,
+    ordered, cover [0, M) exactly and differ by at most one row, up to the int32 ABI's largest batch; the default
+    device policy shards a batch over N GPUs once it holds 2^22 seed points per GPU."""
+    from tt_irt_py import tt_irt
+    lib = tt_irt.load_library()
+    LL = ctypes.c_longlong
+    lib.ttirt_shard_rows.argtypes = [LL, ctypes.c_int, ctypes.c_int, ctypes.POINTER(LL), ctypes.POINTER(LL)]
+    lib.ttirt_auto_devices.argtypes = [LL, ctypes.c_int]
+    for M in (0, 1, 7, 1000, 10001, (1 << 26), (1 << 31) - 1, (1 << 40) + 3):
+        for G in (1, 2, 3, 4, 8):
+            prev, sizes = 0, []
+            for g in range(G):
+                a, b = LL(-1), LL(-1)
+                assert lib.ttirt_shard_rows(M, G, g, ctypes.byref(a), ctypes.byref(b)) == 0
+                assert a.value == prev and b.value >= a.value
+                sizes.append(b.value - a.value); prev = b.value
+            assert prev == M and max(sizes) - min(sizes) <= 1
+    a, b = LL(0), LL(0)
+    assert lib.ttirt_shard_rows(10, 2, 2, ctypes.byref(a), ctypes.byref(b)) != 0
+    assert lib.ttirt_shard_rows(-1, 2, 0, ctypes.byref(a), ctypes.byref(b)) != 0
+    pol = lib.ttirt_auto_devices
+    assert [pol(1 << 14, 8), pol(1 << 22, 8), pol(1 << 24, 8), pol(1 << 25, 8), pol(1 << 26, 8), pol(1 << 26, 2), pol(1 << 26, 0)] == [1, 1, 4, 8, 8, 2, 1]

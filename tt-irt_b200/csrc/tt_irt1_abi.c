@@ -21,6 +21,29 @@ static void nan_fill(double *p, int64_t count) {
   for (i = 0; i < count; i++) p[i] = NAN;
 }
 
+/*
+ * How many devices a call uses.  TTIRT_DEVICES=<count> or "all" is taken as given; unset or "auto": the samples are
+ * independent (reference tt_irt1_int32.c:88-181), so a batch large enough to keep a full pipeline busy on each device
+ * (2^22 seed points: four chunks of 2^20) is sharded over all visible GPUs from `first` on, a smaller one over fewer,
+ * down to one.  Never more devices than `min_rows`-row blocks.
+ */
+static int device_policy(const char *e, int first, int64_t M, int64_t min_rows) {
+  int ndev = 1, visible;
+  if (e != NULL && strcmp(e, "all") != 0 && strcmp(e, "auto") != 0) {
+    ndev = atoi(e);
+  } else {
+    visible = ttirt_device_count() - first;
+    if (e != NULL && strcmp(e, "all") == 0) {
+      ndev = visible;
+    } else {
+      ndev = ttirt_auto_devices(M, visible);
+    }
+  }
+  if (ndev < 1) ndev = 1;
+  while (ndev > 1 && M / ndev < min_rows) ndev--;
+  return ndev;
+}
+
 void tt_irt1(TTIRT_INT d, TTIRT_INT *n, double *xs, TTIRT_INT *ttrank, double *ttcore, TTIRT_INT M,
              double *q, double *z, double *lPz) {
   int64_t *n64, *r64, k;
@@ -46,13 +69,7 @@ void tt_irt1(TTIRT_INT d, TTIRT_INT *n, double *xs, TTIRT_INT *ttrank, double *t
 
   if ((e = getenv("TTIRT_MODE")) != NULL && strcmp(e, "strict") == 0) mode = TTIRT_MODE_STRICT;
   if ((e = getenv("TTIRT_DEVICE")) != NULL) first = atoi(e);
-  if ((e = getenv("TTIRT_DEVICES")) != NULL) {
-    if (strcmp(e, "all") == 0) ndev = ttirt_device_count() - first;
-    else ndev = atoi(e);
-    if (ndev < 1) ndev = 1;
-  }
-  /* never more devices than 64-sample blocks */
-  while (ndev > 1 && (int64_t)M / ndev < 64) ndev--;
+  ndev = device_policy(getenv("TTIRT_DEVICES"), first, (int64_t)M, 64);
 
   rc = ttirt_run_host(d, n64, xs, r64, ttcore, M, q, z, lPz, NULL, mode, first, ndev);
   if (rc != 0) {
@@ -94,12 +111,7 @@ static void sqr_entry(const char *name, int forward, TTIRT_INT d, TTIRT_INT *n, 
   for (k = 0; k < d; k++) n64[k] = (int64_t)n[k];
   for (k = 0; k <= d; k++) r64[k] = (int64_t)ttrank[k];
   if ((e = getenv("TTIRT_DEVICE")) != NULL) first = atoi(e);
-  if ((e = getenv("TTIRT_DEVICES")) != NULL) {
-    if (strcmp(e, "all") == 0) ndev = ttirt_device_count() - first;
-    else ndev = atoi(e);
-    if (ndev < 1) ndev = 1;
-  }
-  while (ndev > 1 && (int64_t)M / ndev < 128) ndev--;   /* never more devices than 128-sample tiles */
+  ndev = device_policy(getenv("TTIRT_DEVICES"), first, (int64_t)M, 128);   /* never more devices than 128-sample tiles */
   rc = forward ? ttirt_sqr_run_forward_host(d, n64, (int64_t)nxs, xs, r64, ttcore, M, D, in, out, lFapp, first, ndev)
                : ttirt_sqr_run_host(d, n64, (int64_t)nxs, xs, r64, ttcore, M, D, in, out, lFapp, first, ndev);
   if (rc != 0) {

@@ -14,6 +14,7 @@ struct DimInfo {
   int64_t off_c;    // start of core k in ttcore    (reference pstt, :55-57)
   int64_t off_p;    // start of P_k (r_k x n_k)     in the stacked product buffer
   int64_t off_m;    // start of C_k (r_{k+1})       in the stacked marginal buffer
+  int64_t off_pw;   // start of the node-weighted copy of P_k (fast path; 16-byte aligned: even offsets)
 };
 
 struct CellOut {
@@ -113,20 +114,51 @@ __device__ __forceinline__ double pow2_scale(double x) {
   return (ex != 0 && ex != 0x7ff) ? __hiloint2double((2046 - ex) << 20, 0) : 1.0;
 }
 
+// Trapezoid weight of grid node j (n nodes x[0..n-1]): the CDF of the piecewise-linear density with node values p is
+//   cdf_j = sum_{i<j} w_i p_i + h_{j-1} p_j,   w_i = h_{i-1} + h_i,   h_i = (x_{i+1} - x_i) / 2   (h_{-1} = 0),
+// and cdf_{n-1} (the mass) = sum_{i<n-1} w_i p_i + h_{n-2} p_{n-1}: the last node carries h_{n-2}, nodes beyond it zero.
+__device__ __forceinline__ double node_weight(const double *__restrict__ x, int j, int n) {
+  if (j >= n) return 0.0;
+  const double hl = j >= 1 ? 0.5 * (x[j] - x[j - 1]) : 0.0;
+  const double hr = j + 1 < n ? 0.5 * (x[j + 1] - x[j]) : 0.0;
+  return hl + hr;
+}
+
+// Exclusive scans of an interval histogram (nb <= 96 bins) by ONE warp: bst[b] = first sorted row of bin b, bts[b] = first
+// CTA tile of bin b (tiles never straddle bins), entry nb = totals.  Every CTA of the scatter and the transition kernel
+// recomputes them from the global histogram; that is cheaper than a launch of its own.  bts may be null.
+__device__ __forceinline__ void bin_offsets_warp(const int *__restrict__ hist, int nb, int rows_per_tile, int *bst, int *bts, int lane) {
+  int cs = 0, ct = 0;
+  for (int b0 = 0; b0 < nb; b0 += 32) {
+    const int b = b0 + lane;
+    const int c = b < nb ? hist[b] : 0;
+    const int t = (c + rows_per_tile - 1) / rows_per_tile;
+    int is = c, it = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int us = __shfl_up_sync(0xffffffffu, is, o), ut = __shfl_up_sync(0xffffffffu, it, o);
+      if (lane >= o) { is += us; it += ut; }
+    }
+    if (b < nb) { bst[b] = cs + is - c; if (bts) bts[b] = ct + it - t; }
+    cs += __shfl_sync(0xffffffffu, is, 31); ct += __shfl_sync(0xffffffffu, it, 31);
+  }
+  if (lane == 0) { bst[nb] = cs; if (bts) bts[nb] = ct; }
+}
+
 // Arguments of one fused "transition" launch of the fast path: interface update through dimension k
 // (binned by the interval chosen there) followed by the whole conditional step of dimension k+1.
 struct TransArgs {
   const double *core;        // core_k, column-major r0 x n0 x r1
-  const double *pnext;       // P_{k+1}, column-major r1 x n1
+  const double *pnext;       // P_{k+1} with column j scaled by node_weight(j), column-major r1 x n1, 16-byte aligned
   const double *xnext;       // grid of dimension k+1 (n1)
   int r0, n0, r1, n1;
+  int async_ok;              // core is 16-byte aligned: slabs may be staged by cp.async when r0 is even
   int last;                  // k+1 == d-1: no further interface update
   int rows;                  // samples in this chunk
   double *F;                 // left-interface rows, rows x ldf, updated in place
   int ldf;
   const int *perm;           // samples ordered by the interval chosen in dimension k
-  const int *bin_start;      // n0 entries (+1)
-  const int *bin_tile_start; // n0 entries (+1), prefix of ceil(count / rows per CTA tile)
+  const int *hist_cur;       // n0-1 counters: samples per interval chosen in dimension k (every CTA scans them itself)
   int *idx;                  // per sample: interval index (out: dimension k+1)
   double *w1, *w2;           // per sample: interpolation weights (in: dimension k, out: k+1)
   double *lp;                // per sample: running product of the scaled densities, mantissa (see lp_accumulate)

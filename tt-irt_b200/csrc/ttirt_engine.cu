@@ -33,6 +33,8 @@ using namespace ttirt;
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
 static std::atomic<int64_t> g_chunk{0};
+// launches enqueued while a chunk graph is being captured do not run: they are counted when the graph is launched
+static thread_local bool t_capturing = false;
 
 static int fail(const char *fmt, ...) {
   va_list ap;
@@ -53,7 +55,7 @@ int aux_fail(const char *fmt, ...) {
   if (getenv("TTIRT_QUIET") == nullptr) fprintf(stderr, "tt_irt1[b200]: %s\n", g_err);
   return -1;
 }
-void aux_launched() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+void aux_launched() { if (!t_capturing) g_launches.fetch_add(1, std::memory_order_relaxed); }
 }  // namespace ttirt
 
 #define CK(call)                                                                          \
@@ -62,7 +64,7 @@ void aux_launched() { g_launches.fetch_add(1, std::memory_order_relaxed); }
     if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
 
-#define LAUNCHED() g_launches.fetch_add(1, std::memory_order_relaxed)
+#define LAUNCHED() do { if (!t_capturing) g_launches.fetch_add(1, std::memory_order_relaxed); } while (0)
 
 static int64_t default_chunk() {
   int64_t c = g_chunk.load();
@@ -85,7 +87,6 @@ struct Workspace {
   double *w1 = nullptr, *w2 = nullptr, *lp = nullptr, *lpd = nullptr;
   int *lpe = nullptr;
   int *hist = nullptr;   // d x nbpad
-  int *bin_start = nullptr, *bin_tile_start = nullptr, *cursor = nullptr;
   // strict scratch
   double *left = nullptr, *pbuf = nullptr, *cbuf = nullptr;
   // host-mode staging
@@ -114,10 +115,18 @@ struct ttirt_model {
   int64_t rmax = 1, nmax = 2, nbpad = 0, sum_pk = 0, sum_mg = 0, sum_x = 0, sum_c = 0;
   int ldf = 8;
   int fast_cls = -1;
-  double *d_xs = nullptr, *d_core = nullptr, *d_pk = nullptr, *d_marg = nullptr;
+  double *d_xs = nullptr, *d_core = nullptr, *d_pk = nullptr, *d_pkw = nullptr, *d_marg = nullptr;
+  int64_t sum_pkw = 0;
   double *d_p0 = nullptr, *d_cdf0 = nullptr;
   DimInfo *d_dims = nullptr;
-  Workspace ws[kSlots];
+  Workspace ws[kSlots];      // host pipeline slots (own streams)
+  // device-pointer API: two workspaces of its own.  A call of several chunks alternates them on two internal streams
+  // forked from / joined into the caller's stream, so that one chunk's sort, kernel prologues and drains run under the
+  // other chunk's transition kernel; a one-chunk call runs on the caller's stream directly.  `done` of each workspace is
+  // recorded after its last use and waited for before its next one, whichever stream that is on.
+  Workspace dws[2];
+  bool dws_used[2] = {false, false};
+  cudaEvent_t fork_ev = nullptr;
   // page-locked bounce buffers of the host pipeline, one set per slot: used when the caller's arrays are ordinary
   // pageable memory (numpy, mxArray), which cudaMemcpyAsync would otherwise stage synchronously at a fraction of PCIe rate
   struct HostStage { double *q = nullptr, *z = nullptr, *lpz = nullptr; int64_t cap = 0; } stage[kSlots];
@@ -136,7 +145,7 @@ static void ws_drop_graphs(Workspace &w) {
 static void ws_free(Workspace &w) {
   ws_drop_graphs(w);
   cudaFree(w.F); cudaFree(w.idx); cudaFree(w.perm); cudaFree(w.w1); cudaFree(w.w2); cudaFree(w.lp); cudaFree(w.lpd); cudaFree(w.lpe);
-  cudaFree(w.hist); cudaFree(w.bin_start); cudaFree(w.bin_tile_start); cudaFree(w.cursor);
+  cudaFree(w.hist);
   cudaFree(w.left); cudaFree(w.pbuf); cudaFree(w.cbuf);
   cudaFree(w.q); cudaFree(w.z); cudaFree(w.lpz); cudaFree(w.idx_out);
   if (w.stream) cudaStreamDestroy(w.stream);
@@ -144,15 +153,7 @@ static void ws_free(Workspace &w) {
   w = Workspace();
 }
 
-static int ws_ensure(ttirt_model *md, Workspace &w, int64_t rows, bool strict, bool host, bool want_idx) {
-  if (w.cap >= rows && (w.strict || !strict) && (w.host || !host) && (w.want_idx || !(host && want_idx))) return 0;
-  cudaStream_t keep_s = w.stream; cudaEvent_t keep_e = w.done;
-  w.stream = nullptr; w.done = nullptr;
-  const bool s = strict || w.strict, h = host || w.host, wi = want_idx || w.want_idx;
-  const int64_t cap = rows > w.cap ? rows : w.cap;
-  ws_free(w);   // (drops the chunk graphs: they hold the old pointers)
-  w.stream = keep_s; w.done = keep_e;
-  w.cap = cap; w.strict = s; w.host = h; w.want_idx = wi;
+static int ws_alloc(ttirt_model *md, Workspace &w, int64_t cap, bool s, bool h, bool wi) {
   const int64_t d = md->d;
   CK(cudaMalloc(&w.F, sizeof(double) * cap * md->ldf));
   CK(cudaMalloc(&w.idx, sizeof(int) * cap));
@@ -162,10 +163,7 @@ static int ws_ensure(ttirt_model *md, Workspace &w, int64_t rows, bool strict, b
   CK(cudaMalloc(&w.lp, sizeof(double) * cap));
   CK(cudaMalloc(&w.lpd, sizeof(double) * cap));
   CK(cudaMalloc(&w.lpe, sizeof(int) * cap));
-  CK(cudaMalloc(&w.hist, sizeof(int) * d * md->nbpad));
-  CK(cudaMalloc(&w.bin_start, sizeof(int) * (md->nbpad + 1)));
-  CK(cudaMalloc(&w.bin_tile_start, sizeof(int) * (md->nbpad + 1)));
-  CK(cudaMalloc(&w.cursor, sizeof(int) * (md->nbpad + 1)));
+  CK(cudaMalloc(&w.hist, sizeof(int) * 2 * d * md->nbpad));   // d interval histograms, then d sets of scatter cursors
   if (s) {
     CK(cudaMalloc(&w.left, sizeof(double) * 2 * md->rmax * cap));
     CK(cudaMalloc(&w.pbuf, sizeof(double) * md->nmax * cap));
@@ -179,6 +177,30 @@ static int ws_ensure(ttirt_model *md, Workspace &w, int64_t rows, bool strict, b
   }
   if (!w.stream) CK(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
   if (!w.done) CK(cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming));
+  return 0;
+}
+
+// Grow a workspace.  The capacity and the mode flags are recorded only once every allocation has succeeded: after a
+// failed cudaMalloc the workspace is empty again (cap 0), so a later, smaller call on a caller-held model allocates
+// afresh instead of launching kernels on null scratch pointers.
+static int ws_ensure(ttirt_model *md, Workspace &w, int64_t rows, bool strict, bool host, bool want_idx) {
+  if (w.cap >= rows && (w.strict || !strict) && (w.host || !host) && (w.want_idx || !(host && want_idx))) return 0;
+  cudaStream_t keep_s = w.stream; cudaEvent_t keep_e = w.done;
+  w.stream = nullptr; w.done = nullptr;
+  const bool s = strict || w.strict, h = host || w.host, wi = want_idx || w.want_idx;
+  const int64_t cap = rows > w.cap ? rows : w.cap;
+  if (keep_s) cudaStreamSynchronize(keep_s);   // work still using the old scratch
+  ws_free(w);   // (drops the chunk graphs: they hold the old pointers)
+  w.stream = keep_s; w.done = keep_e;
+  if (ws_alloc(md, w, cap, s, h, wi) != 0) {
+    keep_s = w.stream; keep_e = w.done;
+    w.stream = nullptr; w.done = nullptr;
+    ws_free(w);                                // cap = 0, every pointer null
+    w.stream = keep_s; w.done = keep_e;
+    cudaGetLastError();                        // an out-of-memory error is not sticky: clear it
+    return -1;
+  }
+  w.cap = cap; w.strict = s; w.host = h; w.want_idx = wi;
   return 0;
 }
 
@@ -268,6 +290,20 @@ __device__ __forceinline__ int strict_search(const double *cdf, int nk, int64_t 
     if (qk > cdf[mid * st]) lo = mid; else hi = mid;
   }
   return lo;
+}
+
+// Fast path: P_k with column j scaled by the trapezoid node weight of grid node j (ttirt_common.cuh node_weight), laid out
+// per dimension at 16-byte aligned offsets so that the transition kernel stages it with cp.async.
+__global__ void weight_p_kernel(const DimInfo *__restrict__ dims, int d, const double *__restrict__ xs, const double *__restrict__ pk,
+                                double *pkw) {
+  const int k = blockIdx.y;
+  if (k >= d) return;
+  const DimInfo di = dims[k];
+  const int total = di.r0 * di.n;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int c = e / di.r0;
+    pkw[di.off_pw + e] = pk[di.off_p + e] * node_weight(xs + di.off_x, c, di.n);
+  }
 }
 
 // Stage-0 tables: the first conditional is the same for every sample (r_0 = 1, left interface {1}).
@@ -366,24 +402,13 @@ __global__ void stage0_kernel(const double *__restrict__ p0, const double *__res
   }
 }
 
-// exclusive scans of the interval histogram: sorted-row offsets and CTA-tile offsets per bin
-__global__ void bin_scan_kernel(const int *__restrict__ hist, int nb, int rows_per_tile, int *bin_start,
-                                int *bin_tile_start, int *cursor) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  int s = 0, t = 0;
-  for (int b = 0; b < nb; b++) {
-    bin_start[b] = s; bin_tile_start[b] = t; cursor[b] = s;
-    const int c = hist[b];
-    s += c; t += (c + rows_per_tile - 1) / rows_per_tile;
-  }
-  bin_start[nb] = s; bin_tile_start[nb] = t;
-}
-
-// counting-sort scatter: perm[position] = sample, positions grouped by interval
-__global__ void bin_scatter_kernel(const int *__restrict__ idx, int rows, int nb, int *cursor, int *perm) {
-  extern __shared__ int sh[];  // nb counts, then nb bases
-  int *cnt = sh, *base = sh + nb;
+// counting-sort scatter: perm[position] = sample, positions grouped by interval.  The bin offsets are scanned from the
+// histogram by every CTA (no scan launch); cursor[] starts at zero and hands out ranges inside a bin.
+__global__ void bin_scatter_kernel(const int *__restrict__ idx, int rows, int nb, const int *__restrict__ hist, int *cursor, int *perm) {
+  extern __shared__ int sh[];  // nb counts, nb bases, nb + 1 bin starts
+  int *cnt = sh, *base = sh + nb, *bst = sh + 2 * nb;
   for (int i = threadIdx.x; i < nb; i += blockDim.x) cnt[i] = 0;
+  if (threadIdx.x < 32) bin_offsets_warp(hist, nb, 1, bst, nullptr, threadIdx.x);
   __syncthreads();
   constexpr int PER = 4;
   int myb[PER], myr[PER];
@@ -395,7 +420,7 @@ __global__ void bin_scatter_kernel(const int *__restrict__ idx, int rows, int nb
     if (m < rows) { myb[u] = idx[m]; myr[u] = atomicAdd(&cnt[myb[u]], 1); }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < nb; i += blockDim.x) base[i] = cnt[i] ? atomicAdd(cursor + i, cnt[i]) : 0;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) base[i] = cnt[i] ? bst[i] + atomicAdd(cursor + i, cnt[i]) : 0;
   __syncthreads();
 #pragma unroll
   for (int u = 0; u < PER; u++) {
@@ -412,29 +437,130 @@ __global__ void fill_nan_kernel(double *p, int64_t n) {
 // ------------------------------------------------------------------------------------------------
 // model create / destroy
 // ------------------------------------------------------------------------------------------------
-extern "C" int ttirt_device_count(void) {
+static int physical_device_count() {
   int c = 0;
   if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); return 0; }
   return c;
+}
+// Test hook: TTIRT_VIRTUAL_DEVICES=K lets one physical GPU stand in for K devices of a multi-device call (logical device g
+// runs on physical device g mod count, with its own engine slot, host thread and row shard), so that the sharding, the
+// fan-out of the cores and the per-device pipelines are exercised on a one-GPU box.  Never set in production.
+static int virtual_devices() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("TTIRT_VIRTUAL_DEVICES"); v = e ? atoi(e) : 0; if (v < 0) v = 0; }
+  return v;
+}
+static int physical_of(int logical) {
+  const int c = physical_device_count();
+  return (virtual_devices() > 0 && c > 0) ? logical % c : logical;
+}
+extern "C" int ttirt_device_count(void) {
+  const int c = physical_device_count();
+  return (c > 0 && virtual_devices() > c) ? virtual_devices() : c;
+}
+
+// Row range of shard `shard` out of `n_shards` for a batch of M samples: contiguous, balanced to one row, in order.
+// (Samples are independent, reference tt_irt1_int32.c:88-181; this is the whole multi-GPU decomposition.)
+extern "C" int ttirt_shard_rows(int64_t M, int n_shards, int shard, int64_t *m0, int64_t *m1) {
+  if (M < 0 || n_shards < 1 || shard < 0 || shard >= n_shards || !m0 || !m1) return -1;
+  *m0 = (int64_t)(((__int128)M * shard) / n_shards);
+  *m1 = (int64_t)(((__int128)M * (shard + 1)) / n_shards);
+  return 0;
+}
+
+// Default device count of the drop-in call (TTIRT_DEVICES unset / "auto"): one device per 2^22 seed points (a full
+// four-chunk pipeline each), at most `visible`, at least one.
+extern "C" int ttirt_auto_devices(int64_t M, int visible) {
+  const int64_t want = M >> 22;
+  if (visible < 1 || want < 1) return 1;
+  return (int)(want > visible ? visible : want);
 }
 
 extern "C" void ttirt_model_destroy(ttirt_model *md) {
   if (!md) return;
   cudaSetDevice(md->device);
   for (auto &w : md->ws) ws_free(w);
+  for (auto &w : md->dws) ws_free(w);
+  if (md->fork_ev) cudaEventDestroy(md->fork_ev);
   for (auto &h : md->stage) { cudaFreeHost(h.q); cudaFreeHost(h.z); cudaFreeHost(h.lpz); }
   for (auto &p : md->prof_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
-  cudaFree(md->d_xs); cudaFree(md->d_core); cudaFree(md->d_pk); cudaFree(md->d_marg);
+  cudaFree(md->d_xs); cudaFree(md->d_core); cudaFree(md->d_pk); cudaFree(md->d_pkw); cudaFree(md->d_marg);
   cudaFree(md->d_p0); cudaFree(md->d_cdf0); cudaFree(md->d_dims);
   delete md;
 }
 
+// Replication of grid + cores in a multi-device call ("one H2D + cudaMemcpyPeerAsync fan-out over
+// NVSwitch"): the first device (root) uploads from the host and publishes its device copy; the other devices pull it over
+// NVLink instead of reading the caller's pageable arrays eight times, and fall back to the host upload if that fails.
+// Plain copies, no collective.  The root keeps its buffers untouched until every peer has reported (pending == 0).
+struct Fanout {
+  std::mutex mu;
+  std::condition_variable cv;
+  int state = 0;                 // 0 pending, 1 root copy resident, -1 root failed (peers upload from the host)
+  int src_device = 0;
+  const double *d_xs = nullptr, *d_core = nullptr;
+  int pending = 0;               // peers that have not finished with the root's copy yet
+  bool reported[64] = {false};   // per peer: peer_done() counts once
+  void publish(int st, int dev, const double *x, const double *c) {
+    { std::lock_guard<std::mutex> l(mu); if (state == 0) { state = st; src_device = dev; d_xs = x; d_core = c; } }
+    cv.notify_all();
+  }
+  void peer_done(int peer) {
+    { std::lock_guard<std::mutex> l(mu); if (!reported[peer & 63]) { reported[peer & 63] = true; --pending; } }
+    cv.notify_all();
+  }
+  void wait_peers() {
+    std::unique_lock<std::mutex> l(mu);
+    cv.wait(l, [&] { return pending <= 0; });
+  }
+};
+struct CoreSource {
+  const double *xs = nullptr, *core = nullptr;   // host arrays (always valid)
+  Fanout *fan = nullptr;
+  bool root = false;
+  int peer = 0;                                  // index among the devices of the call
+};
+
+static bool fanout_enabled() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("TTIRT_FANOUT"); v = e ? atoi(e) != 0 : 1; }
+  return v != 0;
+}
+
 // Upload grid and cores into an allocated model of matching shape and run the right-to-left sweep:
 // C_{d-1} = {1}; P_k = core_k x_3 C_k; C_{k-1} = trapezoid(P_k)   (reference tt_irt1_int32.c:59-82)
-static int model_load(ttirt_model *md, const double *xs, const double *core) {
+static int model_load_body(ttirt_model *md, const CoreSource &src);
+static int model_load(ttirt_model *md, const CoreSource &src) {
+  const int rc = model_load_body(md, src);
+  // a root that fails after publishing its copy must not let the caller free it under the peers' copies
+  if (rc != 0 && src.fan && src.root) { src.fan->publish(-1, 0, nullptr, nullptr); src.fan->wait_peers(); }
+  return rc;
+}
+static int model_load_body(ttirt_model *md, const CoreSource &src) {
   const int64_t d = md->d;
-  CK(cudaMemcpy(md->d_xs, xs, sizeof(double) * md->sum_x, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(md->d_core, core, sizeof(double) * md->sum_c, cudaMemcpyHostToDevice));
+  const double *xs = src.xs, *core = src.core;
+  bool have = false;
+  if (src.fan && !src.root) {
+    Fanout &f = *src.fan;
+    {
+      std::unique_lock<std::mutex> l(f.mu);
+      f.cv.wait(l, [&] { return f.state != 0; });
+    }
+    if (f.state == 1) {
+      cudaError_t e = cudaDeviceEnablePeerAccess(f.src_device, 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+      if (e == cudaSuccess) e = cudaMemcpyPeer(md->d_xs, md->device, f.d_xs, f.src_device, sizeof(double) * md->sum_x);
+      if (e == cudaSuccess) e = cudaMemcpyPeer(md->d_core, md->device, f.d_core, f.src_device, sizeof(double) * md->sum_c);
+      if (e == cudaSuccess) have = true; else cudaGetLastError();
+    }
+    f.peer_done(src.peer);
+  }
+  if (!have) {
+    cudaError_t e = cudaMemcpy(md->d_xs, xs, sizeof(double) * md->sum_x, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(md->d_core, core, sizeof(double) * md->sum_c, cudaMemcpyHostToDevice);
+    if (src.fan && src.root) src.fan->publish(e == cudaSuccess ? 1 : -1, md->device, md->d_xs, md->d_core);
+    CK(e);
+  }
   const double one = 1.0;
   CK(cudaMemcpy(md->d_marg + md->dims[d - 1].off_m, &one, sizeof(double), cudaMemcpyHostToDevice));
   // small TTs (the MH / IW use of the reference: r ~ 8..16, n = 17): one CTA walks the whole sweep in less time than
@@ -457,30 +583,35 @@ static int model_load(ttirt_model *md, const double *xs, const double *core) {
   }
   stage0_table_kernel<<<1, 32>>>(md->d_pk, md->d_xs, md->d_p0, md->d_cdf0, md->dims[0].n);
   LAUNCHED();
+  if (md->fast_cls >= 0 && d > 1) {
+    weight_p_kernel<<<dim3(8, (unsigned)d), 256>>>(md->d_dims, (int)d, md->d_xs, md->d_pk, md->d_pkw);
+    LAUNCHED();
+  }
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   return 0;
 }
 
-static int model_build(ttirt_model *md, const int64_t *n, const double *xs, const int64_t *rk, const double *core) {
+static int model_build(ttirt_model *md, const int64_t *n, const int64_t *rk, const CoreSource &src) {
   const int64_t d = md->d;
   if (rk[0] != 1 || rk[d] != 1) return fail("ttrank[0] and ttrank[d] must be 1 (got %lld, %lld)", (long long)rk[0], (long long)rk[d]);
   md->n.assign(n, n + d);
   md->r.assign(rk, rk + d + 1);
   md->dims.resize(d);
-  int64_t ox = 0, oc = 0, op = 0, om = 0;
+  int64_t ox = 0, oc = 0, op = 0, om = 0, opw = 0;
   for (int64_t k = 0; k < d; k++) {
     if (n[k] < 2) return fail("n[%lld] = %lld: every grid needs at least 2 points", (long long)k, (long long)n[k]);
     if (rk[k] < 1 || rk[k + 1] < 1) return fail("non-positive TT rank at %lld", (long long)k);
     if (n[k] > (1 << 20) || rk[k] > (1 << 14)) return fail("shape too large at dimension %lld", (long long)k);
     DimInfo &di = md->dims[k];
     di.n = (int)n[k]; di.r0 = (int)rk[k]; di.r1 = (int)rk[k + 1]; di.pad = 0;
-    di.off_x = ox; di.off_c = oc; di.off_p = op; di.off_m = om;
+    di.off_x = ox; di.off_c = oc; di.off_p = op; di.off_m = om; di.off_pw = opw;
     ox += n[k]; oc += rk[k] * n[k] * rk[k + 1]; op += rk[k] * n[k]; om += rk[k + 1];
+    opw += (rk[k] * n[k] + 1) & ~(int64_t)1;
     if (rk[k + 1] > md->rmax) md->rmax = rk[k + 1];
     if (n[k] > md->nmax) md->nmax = n[k];
   }
-  md->sum_pk = op; md->sum_mg = om;
+  md->sum_pk = op; md->sum_mg = om; md->sum_pkw = opw;
   md->nbpad = (md->nmax + 7) & ~(int64_t)7;
   md->fast_cls = fast_class_for((int)md->rmax, (int)md->nmax);
   md->ldf = (int)((md->rmax + 7) & ~(int64_t)7);
@@ -495,27 +626,34 @@ static int model_build(ttirt_model *md, const int64_t *n, const double *xs, cons
   CK(cudaMalloc(&md->d_xs, sizeof(double) * ox));
   CK(cudaMalloc(&md->d_core, sizeof(double) * oc));
   CK(cudaMalloc(&md->d_pk, sizeof(double) * op));
+  CK(cudaMalloc(&md->d_pkw, sizeof(double) * opw));
   CK(cudaMalloc(&md->d_marg, sizeof(double) * om));
   CK(cudaMalloc(&md->d_p0, sizeof(double) * n[0]));
   CK(cudaMalloc(&md->d_cdf0, sizeof(double) * n[0]));
   CK(cudaMalloc(&md->d_dims, sizeof(DimInfo) * d));
   CK(cudaMemcpy(md->d_dims, md->dims.data(), sizeof(DimInfo) * d, cudaMemcpyHostToDevice));
   md->sum_x = ox; md->sum_c = oc;
-  return model_load(md, xs, core);
+  return model_load(md, src);
+}
+
+static ttirt_model *model_create_from(int64_t d, const int64_t *n, const int64_t *ttrank, const CoreSource &src, int device) {
+  int cnt = physical_device_count();
+  if (cnt <= 0) { fail("no CUDA device available (this library has no CPU fallback)"); return nullptr; }
+  if (device < 0 || device >= cnt) { fail("device %d out of range (%d visible)", device, cnt); return nullptr; }
+  if (cudaSetDevice(device) != cudaSuccess) { fail("cudaSetDevice(%d) failed", device); return nullptr; }
+  ttirt_model *md = new ttirt_model();
+  md->device = device; md->d = d;
+  if (model_build(md, n, ttrank, src) != 0) { ttirt_model_destroy(md); return nullptr; }
+  return md;
 }
 
 extern "C" ttirt_model *ttirt_model_create(int64_t d, const int64_t *n, const double *xs, const int64_t *ttrank,
                                            const double *ttcore, int device) {
   g_err[0] = 0;
   if (d < 1 || !n || !xs || !ttrank || !ttcore) { fail("bad arguments to ttirt_model_create"); return nullptr; }
-  int cnt = ttirt_device_count();
-  if (cnt <= 0) { fail("no CUDA device available (this library has no CPU fallback)"); return nullptr; }
-  if (device < 0 || device >= cnt) { fail("device %d out of range (%d visible)", device, cnt); return nullptr; }
-  if (cudaSetDevice(device) != cudaSuccess) { fail("cudaSetDevice(%d) failed", device); return nullptr; }
-  ttirt_model *md = new ttirt_model();
-  md->device = device; md->d = d;
-  if (model_build(md, n, xs, ttrank, ttcore) != 0) { ttirt_model_destroy(md); return nullptr; }
-  return md;
+  CoreSource src;
+  src.xs = xs; src.core = ttcore;
+  return model_create_from(d, n, ttrank, src, device);
 }
 
 extern "C" int ttirt_model_get_sweep(const ttirt_model *md, double *pk_out, double *marg_out) {
@@ -532,7 +670,7 @@ extern "C" int ttirt_model_get_sweep(const ttirt_model *md, double *pk_out, doub
 // kernels in one chunk's sequence (what a graph replay launches)
 static int64_t g_launches_per_graph(const ttirt_model *md, int mode) {
   if (mode == TTIRT_MODE_STRICT || md->fast_cls < 0) return 1;
-  return 1 + 3 * (md->d - 1);
+  return 1 + 2 * (md->d - 1);
 }
 
 static int enqueue_chunk(ttirt_model *md, Workspace &w, int64_t rows, const double *q, int64_t ldq, double *z, int64_t ldz,
@@ -546,9 +684,8 @@ static int enqueue_chunk(ttirt_model *md, Workspace &w, int64_t rows, const doub
     CK(cudaGetLastError());
     return 0;
   }
-  const int rows_tile = fast_rows_per_cta(md->fast_cls);
   const int nbpad = (int)md->nbpad;
-  if (d > 1) CK(cudaMemsetAsync(w.hist, 0, sizeof(int) * d * nbpad, st));
+  if (d > 1) CK(cudaMemsetAsync(w.hist, 0, sizeof(int) * 2 * d * nbpad, st));   // histograms and scatter cursors
   {
     const DimInfo &d0 = md->dims[0];
     const size_t sm = sizeof(double) * 3 * d0.n + sizeof(int) * d0.n;
@@ -560,15 +697,15 @@ static int enqueue_chunk(ttirt_model *md, Workspace &w, int64_t rows, const doub
   for (int k = 0; k + 1 < d; k++) {
     const DimInfo &dk = md->dims[k], &dn = md->dims[k + 1];
     const int nb = dk.n - 1;
-    bin_scan_kernel<<<1, 32, 0, st>>>(w.hist + (size_t)k * nbpad, nb, rows_tile, w.bin_start, w.bin_tile_start, w.cursor);
-    LAUNCHED();
-    bin_scatter_kernel<<<(unsigned)((rows + 1023) / 1024), 256, sizeof(int) * 2 * nb, st>>>(w.idx, (int)rows, nb, w.cursor, w.perm);
+    bin_scatter_kernel<<<(unsigned)((rows + 1023) / 1024), 256, sizeof(int) * (3 * nb + 1), st>>>(
+        w.idx, (int)rows, nb, w.hist + (size_t)k * nbpad, w.hist + (size_t)(d + k) * nbpad, w.perm);
     LAUNCHED();
     TransArgs a;
-    a.core = md->d_core + dk.off_c; a.pnext = md->d_pk + dn.off_p; a.xnext = md->d_xs + dn.off_x;
+    a.core = md->d_core + dk.off_c; a.pnext = md->d_pkw + dn.off_pw; a.xnext = md->d_xs + dn.off_x;
     a.r0 = dk.r0; a.n0 = dk.n; a.r1 = dk.r1; a.n1 = dn.n;
+    a.async_ok = (reinterpret_cast<uintptr_t>(a.core) & 15) == 0;
     a.last = (k + 1 == d - 1); a.rows = (int)rows; a.F = w.F; a.ldf = md->ldf;
-    a.perm = w.perm; a.bin_start = w.bin_start; a.bin_tile_start = w.bin_tile_start;
+    a.perm = w.perm; a.hist_cur = w.hist + (size_t)k * nbpad;
     a.idx = w.idx; a.w1 = w.w1; a.w2 = w.w2; a.lp = w.lp; a.lpd = w.lpd; a.lpe = w.lpe;
     a.q = q + ldq * (k + 1); a.z = z + ldz * (k + 1);
     a.idx_out = idx_out ? idx_out + ldz * (k + 1) : nullptr;
@@ -619,10 +756,10 @@ static int run_chunk(ttirt_model *md, Workspace &w, int64_t rows, const double *
     cudaGetLastError();
     return enqueue_chunk(md, w, rows, q, ldq, z, ldz, lpz, idx_out, mode, st);
   }
-  const int64_t before = g_launches.load();
+  t_capturing = true;    // nothing runs yet: this thread's launches are counted at cudaGraphLaunch
   const int rc = enqueue_chunk(md, w, rows, q, ldq, z, ldz, lpz, idx_out, mode, st);
+  t_capturing = false;
   const cudaError_t ec = cudaStreamEndCapture(st, &graph);
-  g_launches.store(before);   // nothing ran yet
   if (rc != 0 || ec != cudaSuccess || !graph) {
     if (graph) cudaGraphDestroy(graph);
     cudaGetLastError();
@@ -656,14 +793,45 @@ extern "C" int ttirt_sample_device(ttirt_model *md, int64_t M, const double *d_q
   cudaStream_t st = (cudaStream_t)stream;
   const bool strict = (mode == TTIRT_MODE_STRICT) || md->fast_cls < 0;
   const int64_t chunk = std::min<int64_t>(M, default_chunk());
-  Workspace &w = md->ws[0];
-  if (w.cap < chunk || (strict && !w.strict)) {
-    CK(cudaStreamSynchronize(st));  // a previous call on this stream may still use the old scratch
-    if (ws_ensure(md, w, chunk, strict, false, false) != 0) return -1;
+  const int64_t nchunks = (M + chunk - 1) / chunk;
+  static const bool two_streams = !(getenv("TTIRT_DEVICE_STREAMS") && atoi(getenv("TTIRT_DEVICE_STREAMS")) < 2);
+  // per-launch profiling needs the kernels serialised (events around overlapping kernels measure the overlap too)
+  const int nws = (nchunks >= 2 && !strict && !md->profile && two_streams) ? 2 : 1;
+  for (int i = 0; i < nws; i++) {
+    Workspace &w = md->dws[i];
+    if (w.cap < chunk || (strict && !w.strict)) {
+      CK(cudaStreamSynchronize(st));  // a previous call on this stream may still use the old scratch (ws_ensure syncs w.stream)
+      if (md->dws_used[i]) CK(cudaEventSynchronize(w.done));
+      if (ws_ensure(md, w, chunk, strict, false, false) != 0) return -1;
+    }
   }
-  for (int64_t m0 = 0; m0 < M; m0 += chunk) {
+  if (nws == 1) {
+    Workspace &w = md->dws[0];
+    if (md->dws_used[0]) CK(cudaStreamWaitEvent(st, w.done, 0));
+    for (int64_t m0 = 0; m0 < M; m0 += chunk) {
+      const int64_t rows = std::min(chunk, M - m0);
+      if (run_chunk(md, w, rows, d_q + m0, ldq, d_z + m0, ldz, d_lpz + m0, d_idx ? d_idx + m0 : nullptr, mode, st) != 0) return -1;
+    }
+    CK(cudaEventRecord(w.done, st));
+    md->dws_used[0] = true;
+    return 0;
+  }
+  if (!md->fork_ev) CK(cudaEventCreateWithFlags(&md->fork_ev, cudaEventDisableTiming));
+  CK(cudaEventRecord(md->fork_ev, st));
+  for (int i = 0; i < 2; i++) {
+    CK(cudaStreamWaitEvent(md->dws[i].stream, md->fork_ev, 0));
+    if (md->dws_used[i]) CK(cudaStreamWaitEvent(md->dws[i].stream, md->dws[i].done, 0));
+  }
+  int64_t c = 0;
+  for (int64_t m0 = 0; m0 < M; m0 += chunk, ++c) {
     const int64_t rows = std::min(chunk, M - m0);
-    if (run_chunk(md, w, rows, d_q + m0, ldq, d_z + m0, ldz, d_lpz + m0, d_idx ? d_idx + m0 : nullptr, mode, st) != 0) return -1;
+    Workspace &w = md->dws[c & 1];
+    if (run_chunk(md, w, rows, d_q + m0, ldq, d_z + m0, ldz, d_lpz + m0, d_idx ? d_idx + m0 : nullptr, mode, w.stream) != 0) return -1;
+  }
+  for (int i = 0; i < 2; i++) {
+    CK(cudaEventRecord(md->dws[i].done, md->dws[i].stream));
+    md->dws_used[i] = true;
+    CK(cudaStreamWaitEvent(st, md->dws[i].done, 0));
   }
   return 0;
 }
@@ -952,23 +1120,40 @@ bool same_shape(const ttirt_model *md, int64_t d, const int64_t *n, const int64_
 }
 
 // rows [m0, m1) of one call on one device, through that device's cached engine
-int run_on_device(int device, int64_t d, const int64_t *n, const double *xs, const int64_t *rk, const double *core,
-                  int64_t m0, int64_t m1, const double *h_q, double *h_z, double *h_lpz, int32_t *h_idx, int64_t ld, int mode) {
+int run_on_device(int device, int64_t d, const int64_t *n, const int64_t *rk, const CoreSource &src,
+                  int64_t m0, int64_t m1, const double *h_q, double *h_z, double *h_lpz, int32_t *h_idx, int64_t ld, int mode,
+                  const SeedSpec &seeds) {
+  // whatever happens below, a root must publish (so that peers never wait for ever) and a peer must report (so that the
+  // root never does); both are idempotent
+  struct FanGuard {
+    const CoreSource &s;
+    ~FanGuard() {
+      if (!s.fan) return;
+      if (s.root) { s.fan->publish(-1, 0, nullptr, nullptr); s.fan->wait_peers(); }
+      else s.fan->peer_done(s.peer);
+    }
+  } guard{src};
   if (device < 0 || device >= kMaxDevices) return fail("device %d out of range", device);
-  EngineSlot &sl = g_slots[device];
+  EngineSlot &sl = g_slots[device];   // per LOGICAL device (equal to the physical one outside the virtual-device test hook)
   std::lock_guard<std::mutex> lock(sl.mu);
   const double t0 = now_s();
+  device = physical_of(device);
   if (same_shape(sl.md, d, n, rk)) {
     if (cudaSetDevice(device) != cudaSuccess) return fail("cudaSetDevice(%d) failed", device);
-    if (model_load(sl.md, xs, core) != 0) { ttirt_model_destroy(sl.md); sl.md = nullptr; return -1; }
+    if (model_load(sl.md, src) != 0) {
+      if (src.fan && src.root) src.fan->wait_peers();
+      ttirt_model_destroy(sl.md); sl.md = nullptr;
+      return -1;
+    }
   } else {
     ttirt_model_destroy(sl.md);
-    sl.md = ttirt_model_create(d, n, xs, rk, core, device);
+    sl.md = model_create_from(d, n, rk, src, device);
     if (!sl.md) return -1;
   }
   const double t1 = now_s();
-  const int rc = sample_host_rows(sl.md, m0, m1, h_q, h_z, h_lpz, h_idx, ld, mode);
+  const int rc = sample_host_rows(sl.md, m0, m1, h_q, h_z, h_lpz, h_idx, ld, mode, seeds);
   const double t2 = now_s();
+  if (src.fan && src.root) src.fan->wait_peers();   // peers copy from this model's buffers
   if (!cache_enabled() || rc != 0) { ttirt_model_destroy(sl.md); sl.md = nullptr; }
   if (trace_on())
     fprintf(stderr, "tt_irt1[b200] trace: device %d rows %lld: model %.1f ms, pipeline %.1f ms, release %.1f ms\n", device,
@@ -987,9 +1172,9 @@ extern "C" void ttirt_cache_clear(void) {
   }
 }
 
-extern "C" int ttirt_run_host(int64_t d, const int64_t *n, const double *xs, const int64_t *ttrank, const double *ttcore,
-                              int64_t M, const double *h_q, double *h_z, double *h_lpz, int32_t *h_idx, int mode,
-                              int first_device, int n_devices) {
+static int run_host_impl(int64_t d, const int64_t *n, const double *xs, const int64_t *ttrank, const double *ttcore,
+                         int64_t M, const double *h_q, double *h_z, double *h_lpz, int32_t *h_idx, int mode,
+                         int first_device, int n_devices, const SeedSpec &seeds) {
   g_err[0] = 0;
   if (M < 0) return fail("negative M");
   if (d < 1 || !n || !xs || !ttrank || !ttcore) return fail("bad arguments to ttirt_run_host");
@@ -998,22 +1183,35 @@ extern "C" int ttirt_run_host(int64_t d, const int64_t *n, const double *xs, con
   if (n_devices <= 0 || first_device < 0 || first_device + n_devices > cnt)
     return fail("device range [%d, %d) not available (%d visible)", first_device, first_device + n_devices, cnt);
   if (M == 0) return 0;
-  if (cudaSetDevice(first_device) != cudaSuccess) return fail("cudaSetDevice(%d) failed", first_device);
+  if (cudaSetDevice(physical_of(first_device)) != cudaSuccess) return fail("cudaSetDevice(%d) failed", first_device);
   const bool pq = pin_if_pageable(h_q, sizeof(double) * M * d), pz = pin_if_pageable(h_z, sizeof(double) * M * d),
              pl = pin_if_pageable(h_lpz, sizeof(double) * M);
   struct Unpin {
     const void *q, *z, *l; bool pq, pz, pl;
     ~Unpin() { unpin(q, pq); unpin(z, pz); unpin(l, pl); }
   } unpin_guard{h_q, h_z, h_lpz, pq, pz, pl};
-  if (n_devices == 1) return run_on_device(first_device, d, n, xs, ttrank, ttcore, 0, M, h_q, h_z, h_lpz, h_idx, M, mode);
-  // samples are independent: contiguous row shards, one host thread per device, no collective
+  CoreSource src;
+  src.xs = xs; src.core = ttcore;
+  if (n_devices == 1) return run_on_device(first_device, d, n, ttrank, src, 0, M, h_q, h_z, h_lpz, h_idx, M, mode, seeds);
+  // samples are independent: contiguous row shards, one host thread per device, no collective.  Grid and cores reach the
+  // first device from the host and the others from there (Fanout); the tiny sweep is redone on every device.
+  Fanout fan;
+  fan.pending = n_devices - 1;
+  int64_t core_elems = 0;
+  for (int64_t k = 0; k < d; k++) core_elems += ttrank[k] * n[k] * ttrank[k + 1];
+  const bool use_fan = fanout_enabled() && n_devices <= 64 && core_elems >= (1 << 16);   // small cores: eight host uploads are as quick
   std::vector<int> rcs(n_devices, 0);
   std::vector<std::string> errs(n_devices);
   std::vector<std::thread> th;
   for (int g = 0; g < n_devices; g++) {
     th.emplace_back([&, g]() {
-      const int64_t m0 = M * g / n_devices, m1 = M * (g + 1) / n_devices;
-      rcs[g] = run_on_device(first_device + g, d, n, xs, ttrank, ttcore, m0, m1, h_q, h_z, h_lpz, h_idx, M, mode);
+      int64_t m0 = 0, m1 = 0;
+      ttirt_shard_rows(M, n_devices, g, &m0, &m1);
+      CoreSource s = src;
+      if (use_fan) { s.fan = &fan; s.root = g == 0; s.peer = g; }
+      SeedSpec sp = seeds;
+      sp.m_base = seeds.m_base + m0;
+      rcs[g] = run_on_device(first_device + g, d, n, ttrank, s, m0, m1, h_q, h_z, h_lpz, h_idx, M, mode, sp);
       if (rcs[g] != 0) errs[g] = g_err;
     });
   }
@@ -1021,6 +1219,24 @@ extern "C" int ttirt_run_host(int64_t d, const int64_t *n, const double *xs, con
   for (int g = 0; g < n_devices; g++)
     if (rcs[g] != 0) return fail("device %d: %s", first_device + g, errs[g].c_str());
   return 0;
+}
+
+extern "C" int ttirt_run_host(int64_t d, const int64_t *n, const double *xs, const int64_t *ttrank, const double *ttcore,
+                              int64_t M, const double *h_q, double *h_z, double *h_lpz, int32_t *h_idx, int mode,
+                              int first_device, int n_devices) {
+  if (M > 0 && (!h_q || !h_z || !h_lpz)) return fail("bad arguments to ttirt_run_host");
+  return run_host_impl(d, n, xs, ttrank, ttcore, M, h_q, h_z, h_lpz, h_idx, mode, first_device, n_devices, SeedSpec());
+}
+
+// The whole call with the seeds generated on the devices (Philox4x32-10, counter = global sample index, so the result does
+// not depend on the number of devices): no q upload at all.  h_q may be NULL; when given it receives the seeds.
+extern "C" int ttirt_run_uniform_host(int64_t d, const int64_t *n, const double *xs, const int64_t *ttrank, const double *ttcore,
+                                      int64_t M, int64_t m0, uint64_t seed, double *h_q, double *h_z, double *h_lpz, int mode,
+                                      int first_device, int n_devices) {
+  if (M > 0 && (!h_z || !h_lpz)) return fail("bad arguments to ttirt_run_uniform_host");
+  SeedSpec sp;
+  sp.kind = 2; sp.m_base = m0; sp.seed = seed;
+  return run_host_impl(d, n, xs, ttrank, ttcore, M, h_q, h_z, h_lpz, nullptr, mode, first_device, n_devices, sp);
 }
 
 extern "C" void ttirt_profile_enable(ttirt_model *md, int on) {

@@ -73,33 +73,43 @@ __device__ __forceinline__ int b_phys(int c, int a, int KP) { return c * KP + ((
 __device__ void stage_b(double *dst, const double *__restrict__ src, int K, int NC, int64_t cs, int KP, int NCP,
                         int tid, int nthr) {
   const int total = NCP * KP;
-  for (int e = tid; e < total; e += nthr) {
-    const int c = e / KP, a = e - c * KP;
-    const double v = (a < K && c < NC) ? __ldg(src + a + (int64_t)c * cs) : 0.0;
-    dst[b_phys(c, a, KP)] = v;
+  // four independent loads in flight per thread and pass (a dependent load-store loop pays one L2 latency per element)
+  for (int e0 = tid; e0 < total; e0 += 4 * nthr) {
+    double v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int e = e0 + u * nthr;
+      const int c = e / KP, a = e - c * KP;
+      v[u] = (e < total && a < K && c < NC) ? __ldg(src + a + (int64_t)c * cs) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int e = e0 + u * nthr;
+      if (e < total) { const int c = e / KP, a = e - c * KP; dst[b_phys(c, a, KP)] = v[u]; }
+    }
   }
 }
 
-// Trapezoid weight of grid node j (n nodes x[0..n-1]): the CDF of the piecewise-linear density with node values p is
-//   cdf_j = sum_{i<j} w_i p_i + h_{j-1} p_j,   w_i = h_{i-1} + h_i,   h_i = (x_{i+1} - x_i) / 2   (h_{-1} = 0),
-// and cdf_{n-1} (the mass) = sum_{i<n-1} w_i p_i + h_{n-2} p_{n-1}: the last node carries h_{n-2}, nodes beyond it zero.
-__device__ __forceinline__ double node_weight(const double *__restrict__ x, int j, int n) {
-  if (j >= n) return 0.0;
-  const double hl = j >= 1 ? 0.5 * (x[j] - x[j - 1]) : 0.0;
-  const double hr = j + 1 < n ? 0.5 * (x[j + 1] - x[j]) : 0.0;
-  return hl + hr;
+// The same image, written by cp.async (LDGSTS) in 16-byte pieces: nothing passes through registers and every piece of
+// the slab is in flight at once, so a restage costs one L2 round trip instead of one per element.  Needs K even, cs even
+// and a 16-byte aligned src (rows 2i, 2i+1 of a column are one piece and stay adjacent under the swizzle); pieces outside
+// K x NC are zero-filled (src-size 0).  The caller commits / waits.
+__device__ __forceinline__ void cp_async16_zfill(void *dst, const void *src, bool valid) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(valid ? 16 : 0) : "memory");
 }
-
-// P_{k+1} with column j scaled by node_weight(j): the pdf contraction then delivers w_j p_j directly and the tail's
-// CDF pass is a plain running sum.
-__device__ void stage_p_weighted(double *dst, const double *__restrict__ src, int K, int NC, int KP, int NCP,
-                                 const double *__restrict__ x, int tid, int nthr) {
-  const int total = NCP * KP;
+__device__ void stage_b_async(double *dst, const double *__restrict__ src, int K, int NC, int64_t cs, int KP, int NCP,
+                              int tid, int nthr) {
+  const int hp = KP >> 1, total = NCP * hp;
   for (int e = tid; e < total; e += nthr) {
-    const int c = e / KP, a = e - c * KP;
-    const double v = (a < K && c < NC) ? __ldg(src + a + (int64_t)c * K) * node_weight(x, c, NC) : 0.0;
-    dst[b_phys(c, a, KP)] = v;
+    const int c = e / hp, a = (e - c * hp) << 1;
+    const bool valid = a < K && c < NC;
+    cp_async16_zfill(dst + b_phys(c, a, KP), valid ? src + a + (int64_t)c * cs : src, valid);
   }
+}
+__device__ __forceinline__ void stage_slab(bool async_ok, double *dst, const double *__restrict__ src, int K, int NC, int64_t cs,
+                                           int KP, int NCP, int tid, int nthr) {
+  if (async_ok) stage_b_async(dst, src, K, NC, cs, KP, NCP, tid, nthr);
+  else stage_b(dst, src, K, NC, cs, KP, NCP, tid, nthr);
 }
 
 #ifndef TTIRT_MMA_WARPS
@@ -198,10 +208,12 @@ __global__ void __launch_bounds__(nthr_of(TW), 1) transition_kernel(const TransA
   constexpr int KP = L::KPMAX;                   // compile-time column pitch: B-fragment offsets fold into immediates
   constexpr int NTD = TAIL1 ? NT - 1 : NT;       // grid column tiles computed by DMMA
 
-  for (int i = tid; i <= nb0; i += NTHR) {
-    bts[i] = a.bin_tile_start[i];
-    bst[i] = a.bin_start[i];
-  }
+  // ---- prologue: everything the CTA needs is requested at once (cp.async), the small tables are computed underneath ----
+  // 16-byte pieces need even leading dimensions and aligned bases (the host checks the bases: TransArgs::async_ok)
+  const bool p_async = !(r1 & 1);                    // pnext itself is aligned by construction (DimInfo::off_pw)
+  const bool slab_async = a.async_ok && !(r0 & 1);   // slab b starts at core + b * r0, column stride r0 * n0
+  stage_slab(p_async, Ps, a.pnext, r1, n1, r1, KP, 8 * NT, tid, NTHR);
+  if (warp == 0) bin_offsets_warp(a.hist_cur, nb0, ROWS_CTA, bst, bts, lane);
   for (int i = tid; i < L::NHH; i += NTHR) {
     const double w = node_weight(a.xnext, i, n1);
     const double hl = (i >= 1 && i < n1) ? 0.5 * (a.xnext[i] - a.xnext[i - 1]) : 0.0;
@@ -214,12 +226,23 @@ __global__ void __launch_bounds__(nthr_of(TW), 1) transition_kernel(const TransA
     if (i < L::NBMAX) hist[i] = 0;
   }
   if (tid < TAIL_WARPS) consumed[tid] = 0;
-  stage_p_weighted(Ps, a.pnext, r1, n1, KP, 8 * NT, a.xnext, tid, NTHR);
   __syncthreads();
 
   const int total_tiles = bts[nb0];
   const int t_begin = (int)(((int64_t)blockIdx.x * total_tiles) / gridDim.x);
   const int t_end = (int)(((int64_t)(blockIdx.x + 1) * total_tiles) / gridDim.x);
+  // the two slabs of the first tile's interval, by all threads
+  int b_first = -1;
+  if (t_begin < t_end) {
+    b_first = 0;
+    while (t_begin >= bts[b_first + 1]) ++b_first;
+    const int64_t slab_cs0 = (int64_t)r0 * a.n0;
+    stage_slab(slab_async, slab0, a.core + (int64_t)b_first * r0, r0, r1, slab_cs0, KP, 8 * RT, tid, NTHR);
+    stage_slab(slab_async, slab1, a.core + (int64_t)(b_first + 1) * r0, r0, r1, slab_cs0, KP, 8 * RT, tid, NTHR);
+  }
+  cp_async_commit();
+  cp_async_wait_all();
+  __syncthreads();
 
   const bool is_tail = warp < TAIL_WARPS;   // tail warps first, then the MMA warps (role changes at warpgroup granularity for setmaxnreg)
   if (is_tail) {
@@ -385,8 +408,8 @@ __global__ void __launch_bounds__(nthr_of(TW), 1) transition_kernel(const TransA
     const uint32_t row_bytes = (uint32_t)(8 * ks0) * 8u;   // bytes of a left-interface row that the update reads
     const int64_t slab_cs = (int64_t)r0 * a.n0;
 
-    int cur0 = -1, cur1 = -1;  // interval slab held by slab0 / slab1
-    int b = 0;                 // bin of the current tile
+    int cur0 = b_first, cur1 = b_first < 0 ? -1 : b_first + 1;  // interval slab held by slab0 / slab1 (the prologue staged the first pair)
+    int b = b_first < 0 ? 0 : b_first;   // bin of the current tile
     int bh = 0;                // bin hint of the row look-ahead (monotone)
     const double *sl_lo = slab0, *sl_hi = slab1;
 
@@ -456,17 +479,19 @@ __global__ void __launch_bounds__(nthr_of(TW), 1) transition_kernel(const TransA
         bar_mma_warps();  // every MMA warp is done with the previous bin's slabs
         constexpr int NM = 32 * MMA_WARPS;
         if (cur0 == b) {
-          stage_b(slab1, a.core + (int64_t)(b + 1) * r0, r0, r1, slab_cs, KP, 8 * RT, mtid, NM); cur1 = b + 1;
+          stage_slab(slab_async, slab1, a.core + (int64_t)(b + 1) * r0, r0, r1, slab_cs, KP, 8 * RT, mtid, NM); cur1 = b + 1;
         } else if (cur1 == b) {
-          stage_b(slab0, a.core + (int64_t)(b + 1) * r0, r0, r1, slab_cs, KP, 8 * RT, mtid, NM); cur0 = b + 1;
+          stage_slab(slab_async, slab0, a.core + (int64_t)(b + 1) * r0, r0, r1, slab_cs, KP, 8 * RT, mtid, NM); cur0 = b + 1;
         } else if (cur0 == b + 1) {
-          stage_b(slab1, a.core + (int64_t)b * r0, r0, r1, slab_cs, KP, 8 * RT, mtid, NM); cur1 = b;
+          stage_slab(slab_async, slab1, a.core + (int64_t)b * r0, r0, r1, slab_cs, KP, 8 * RT, mtid, NM); cur1 = b;
         } else if (cur1 == b + 1) {
-          stage_b(slab0, a.core + (int64_t)b * r0, r0, r1, slab_cs, KP, 8 * RT, mtid, NM); cur0 = b;
+          stage_slab(slab_async, slab0, a.core + (int64_t)b * r0, r0, r1, slab_cs, KP, 8 * RT, mtid, NM); cur0 = b;
         } else {
-          stage_b(slab0, a.core + (int64_t)b * r0, r0, r1, slab_cs, KP, 8 * RT, mtid, NM); cur0 = b;
-          stage_b(slab1, a.core + (int64_t)(b + 1) * r0, r0, r1, slab_cs, KP, 8 * RT, mtid, NM); cur1 = b + 1;
+          stage_slab(slab_async, slab0, a.core + (int64_t)b * r0, r0, r1, slab_cs, KP, 8 * RT, mtid, NM); cur0 = b;
+          stage_slab(slab_async, slab1, a.core + (int64_t)(b + 1) * r0, r0, r1, slab_cs, KP, 8 * RT, mtid, NM); cur1 = b + 1;
         }
+        cp_async_commit();
+        cp_async_wait_all();   // (also the row gather in flight: it is needed right after anyway)
         bar_mma_warps();
         if (cur0 == b) { sl_lo = slab0; sl_hi = slab1; } else { sl_lo = slab1; sl_hi = slab0; }
       }

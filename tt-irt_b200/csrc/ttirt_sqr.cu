@@ -1115,12 +1115,7 @@ static void sqr_ws_free(ttirt_sqr_model *md) {
   md->cap = 0; md->host = false;
 }
 
-static int sqr_ws_ensure(ttirt_sqr_model *md, int64_t rows, bool host) {
-  if (md->cap >= rows && (md->host || !host)) return 0;
-  const int64_t cap = std::max(rows, md->cap);
-  const bool h = host || md->host;
-  sqr_ws_free(md);
-  md->cap = cap; md->host = h;
+static int sqr_ws_alloc(ttirt_sqr_model *md, int64_t cap, bool h) {
   const int64_t d = md->d;
   const size_t fbytes = sizeof(double) * (size_t)cap * md->ldf;
   CKS(sqr_alloc(&md->F0, fbytes));
@@ -1145,6 +1140,25 @@ static int sqr_ws_ensure(ttirt_sqr_model *md, int64_t rows, bool host) {
       CKS(sqr_alloc(&md->idx_out[s], sizeof(int32_t) * cap * d));
     }
   }
+  return 0;
+}
+
+// Capacity and mode are recorded only after every allocation has succeeded; a failed allocation leaves the workspace
+// empty (cap 0), so a later smaller call on a caller-held model allocates afresh instead of running on null scratch.
+// Blocks go back to the per-device pool here: work of an earlier device-API call may still be using them on the
+// caller's stream, so the device is synchronised first (growing the workspace is rare).
+static int sqr_ws_ensure(ttirt_sqr_model *md, int64_t rows, bool host) {
+  if (md->cap >= rows && (md->host || !host)) return 0;
+  const int64_t cap = std::max(rows, md->cap);
+  const bool h = host || md->host;
+  if (md->cap > 0) cudaDeviceSynchronize();
+  sqr_ws_free(md);
+  if (sqr_ws_alloc(md, cap, h) != 0) {
+    sqr_ws_free(md);
+    cudaGetLastError();
+    return -1;
+  }
+  md->cap = cap; md->host = h;
   return 0;
 }
 
@@ -1753,9 +1767,12 @@ extern "C" int ttirt_dirt_sample_host(int64_t nlevels, ttirt_sqr_model *const *m
   CKS(cudaSetDevice(m0->device));
   const int64_t chunk = std::min<int64_t>(M, (int64_t)1 << 20);
   double *dq = nullptr, *dz = nullptr, *dl = nullptr;
-  CKS(sqr_alloc(&dq, sizeof(double) * chunk * d));
-  CKS(sqr_alloc(&dz, sizeof(double) * chunk * d));
-  CKS(sqr_alloc(&dl, sizeof(double) * chunk));
+  if (sqr_alloc(&dq, sizeof(double) * chunk * d) != cudaSuccess || sqr_alloc(&dz, sizeof(double) * chunk * d) != cudaSuccess ||
+      sqr_alloc(&dl, sizeof(double) * chunk) != cudaSuccess) {
+    cudaGetLastError();
+    sqr_free(dq); sqr_free(dz); sqr_free(dl);   // the blocks that did come through go back to the pool
+    return aux_fail("out of device memory for %lld x %lld staging blocks", (long long)chunk, (long long)d);
+  }
   cudaStream_t st = m0->stream;
   int rc = 0;
   for (int64_t b = 0; b < M && rc == 0; b += chunk) {
@@ -1832,9 +1849,12 @@ extern "C" int ttirt_dirt_inverse_host(int64_t nlevels, ttirt_sqr_model *const *
   CKS(cudaSetDevice(m0->device));
   const int64_t chunk = std::min<int64_t>(M, (int64_t)1 << 20);
   double *dx = nullptr, *dq = nullptr, *dl = nullptr;
-  CKS(sqr_alloc(&dx, sizeof(double) * chunk * d));
-  CKS(sqr_alloc(&dq, sizeof(double) * chunk * d));
-  CKS(sqr_alloc(&dl, sizeof(double) * chunk));
+  if (sqr_alloc(&dx, sizeof(double) * chunk * d) != cudaSuccess || sqr_alloc(&dq, sizeof(double) * chunk * d) != cudaSuccess ||
+      sqr_alloc(&dl, sizeof(double) * chunk) != cudaSuccess) {
+    cudaGetLastError();
+    sqr_free(dx); sqr_free(dq); sqr_free(dl);
+    return aux_fail("out of device memory for %lld x %lld staging blocks", (long long)chunk, (long long)d);
+  }
   cudaStream_t st = m0->stream;
   int rc = 0;
   for (int64_t b = 0; b < M && rc == 0; b += chunk) {

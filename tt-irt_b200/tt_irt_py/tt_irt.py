@@ -94,6 +94,14 @@ def _raise_last(lib, what):
     raise RuntimeError("%s failed: %s" % (what, msg.decode() if msg else "unknown error"))
 
 
+def _check_void_call(lib, what, M, lPz):
+    """The reference's entry points return nothing; the B200 library reports failure (no device, unsupported shape, CUDA
+    error) by NaN-filling its outputs and keeping a message.  The Python mirror turns that into an exception."""
+    if M > 0 and np.isnan(lPz[0]) and np.isnan(lPz).all():
+        msg = lib.ttirt_last_error()
+        raise RuntimeError("%s failed: %s" % (what, msg.decode() if msg else "outputs are NaN (see stderr)"))
+
+
 def tt_irt1(q, f, xsf):
     """ Inverse Rosenblatt sampler, linear splines (reference tt_irt.py:13-53)
         Inputs:
@@ -121,6 +129,7 @@ def tt_irt1(q, f, xsf):
     lib.tt_irt1(c_int(f.d), n.ctypes.data_as(ip), xsf.ctypes.data_as(dp), rf.ctypes.data_as(ip),
                 core.ctypes.data_as(dp), c_int(q.shape[0]), q.ctypes.data_as(dp), Z.ctypes.data_as(dp),
                 lPz.ctypes.data_as(dp))
+    _check_void_call(lib, "tt_irt1", q.shape[0], lPz)
     return (Z, lPz)
 
 
@@ -259,6 +268,31 @@ def run_host(n, xs, ranks, cores, q, mode=MODE_FAST, first_device=0, n_devices=1
     if rc != 0:
         _raise_last(lib, "ttirt_run_host")
     return (Z, lPz, idx) if want_idx else (Z, lPz)
+
+
+def run_uniform_host(n, xs, ranks, cores, M, seed, m0=0, mode=MODE_FAST, first_device=0, n_devices=1, want_q=False):
+    """One-shot call with the seeds generated on the devices (Philox indices [m0, m0 + M)), rows sharded over n_devices
+    GPUs: no q upload; the result does not depend on the device count."""
+    from ctypes import c_ulonglong
+    lib = load_library()
+    n = np.ascontiguousarray(n, dtype=np.int64)
+    r = np.ascontiguousarray(ranks, dtype=np.int64)
+    xs = np.ascontiguousarray(np.asarray(xs, dtype=np.float64).ravel(order="F"))
+    cores = np.ascontiguousarray(np.asarray(cores, dtype=np.float64).ravel(order="F"))
+    d = int(n.size)
+    Z = np.zeros((M, d), dtype=np.float64, order="F")
+    lPz = np.zeros(M, dtype=np.float64)
+    q = np.zeros((M, d), dtype=np.float64, order="F") if want_q else None
+    lp, dp = POINTER(c_longlong), POINTER(c_double)
+    f = lib.ttirt_run_uniform_host
+    f.restype = c_int
+    f.argtypes = [c_longlong, lp, dp, lp, dp, c_longlong, c_longlong, c_ulonglong, dp, dp, dp, c_int, c_int, c_int]
+    rc = f(d, n.ctypes.data_as(lp), xs.ctypes.data_as(dp), r.ctypes.data_as(lp), cores.ctypes.data_as(dp), int(M), int(m0),
+           int(seed) & 0xFFFFFFFFFFFFFFFF, q.ctypes.data_as(dp) if want_q else None, Z.ctypes.data_as(dp), lPz.ctypes.data_as(dp),
+           int(mode), int(first_device), int(n_devices))
+    if rc != 0:
+        _raise_last(lib, "ttirt_run_uniform_host")
+    return (Z, lPz, q) if want_q else (Z, lPz)
 
 
 def kernel_launches():

@@ -137,6 +137,8 @@ def _sqr_call(symbol, xsf, f, q):
     getattr(lib, symbol)(c_int(f.d), n.ctypes.data_as(ip), c_int(xsf.size), xsf.ctypes.data_as(dp), rf.ctypes.data_as(ip),
                          core.ctypes.data_as(dp), c_int(M), c_int(D), q.ctypes.data_as(dp), xq.ctypes.data_as(dp),
                          lFapp.ctypes.data_as(dp))
+    from .tt_irt import _check_void_call
+    _check_void_call(lib, symbol, M, lFapp)
     return xq, lFapp
 
 
