@@ -524,9 +524,26 @@ def e2e_sharded(a, lib, torch, ns, xs, rk, cores, d, ndev):
 
 
 def host_copy_ceiling(torch, qh, zh, d, Ms, ndev):
-    """GB/s of plain cudaMemcpyAsync between the pinned arrays of the sharded call and device buffers, every device at once,
-    each copying its own row shard (d column segments per chunk of 2^20 rows, as the pipeline does): H2D alone, D2H alone
-    and both directions together.  This is the ceiling of any end-to-end figure that streams q in and Z out on this box."""
+    """GB/s of plain cudaMemcpy2DAsync between the pinned arrays of the sharded call and device buffers, every device at
+    once, each copying its own row shard in chunks of 2^20 rows (d column segments per chunk, exactly the copies the
+    pipeline issues): H2D alone, D2H alone and both directions together.  This is the ceiling of any end-to-end figure
+    that streams q in and Z out on this box."""
+    import ctypes as C
+    rt = None
+    for nm in ("libcudart.so.12", "libcudart.so"):
+        try:
+            rt = C.CDLL(nm)
+            break
+        except OSError:
+            continue
+    if rt is None:
+        import glob as _g
+        hits = _g.glob(os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "cuda_runtime", "lib", "libcudart.so*"))
+        rt = C.CDLL(hits[0])
+    cp2d = rt.cudaMemcpy2DAsync
+    cp2d.restype = C.c_int
+    cp2d.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p]
+    H2D, D2H = 1, 2
     rows = Ms // ndev
     chunk = 1 << 20
     bufs = []
@@ -545,12 +562,11 @@ def host_copy_ceiling(torch, qh, zh, d, Ms, ndev):
                 di, do, s1, s2 = bufs[g]
                 m0 = g * rows + c0
                 w = min(chunk, rows - c0)
-                if h2d:
-                    with torch.cuda.stream(s1):
-                        di[:, :w].copy_(qh[:, m0:m0 + w], non_blocking=True)
-                if d2h:
-                    with torch.cuda.stream(s2):
-                        zh[:, m0:m0 + w].copy_(do[:, :w], non_blocking=True)
+                with torch.cuda.device(g):
+                    if h2d and cp2d(di.data_ptr(), 8 * chunk, qh.data_ptr() + 8 * m0, 8 * Ms, 8 * w, d, H2D, s1.cuda_stream) != 0:
+                        raise RuntimeError("cudaMemcpy2DAsync H2D failed")
+                    if d2h and cp2d(zh.data_ptr() + 8 * m0, 8 * Ms, do.data_ptr(), 8 * chunk, 8 * w, d, D2H, s2.cuda_stream) != 0:
+                        raise RuntimeError("cudaMemcpy2DAsync D2H failed")
         for g in range(ndev):
             torch.cuda.synchronize(g)
         dt = time.perf_counter() - t0
@@ -558,7 +574,7 @@ def host_copy_ceiling(torch, qh, zh, d, Ms, ndev):
 
     run(True, True)
     out = {"h2d_only_GBps": run(True, False), "d2h_only_GBps": run(False, True), "duplex_GBps": run(True, True),
-           "how": "pinned host arrays of the sharded call <-> device buffers, %d devices at once, chunks of 2^20 rows x %d column segments, both copy engines" % (ndev, d)}
+           "how": "cudaMemcpy2DAsync, pinned host arrays of the sharded call <-> device buffers, %d devices at once, chunks of 2^20 rows x %d column segments, one stream per direction and device" % (ndev, d)}
     return out
 
 

@@ -392,7 +392,9 @@ import oracle
 import test_parity_gpu as T
 from tt_irt_py import tt_irt, synth
 assert tt_irt.device_count() == 3, tt_irt.device_count()
+print("three logical devices", flush=True)
 T._check_sharded_call(oracle, 3)
+print("sharded call ok", flush=True)
 # the drop-in symbol with TTIRT_DEVICES=3
 ns, xs, rk, c = synth.make_tt(5, 17, 16, seed=3)
 q = synth.make_q(20000, 5, seed=4)
@@ -415,15 +417,22 @@ def test_virtual_devices_exercise_the_sharded_path_on_one_gpu(tmp_path):
     script.write_text(_VIRTUAL_SCRIPT)
     env = dict(os.environ, TTIRT_VIRTUAL_DEVICES="3")
     env.pop("TTIRT_DEVICES", None)
-    out = subprocess.run([sys.executable, str(script), ROOT], env=env, capture_output=True, text=True, timeout=600)
+    out = subprocess.run([sys.executable, "-u", "-X", "faulthandler", str(script), ROOT], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "virtual devices ok" in out.stdout, (out.stdout[-2000:], out.stderr[-4000:])
 
 
+# the reference's own share of Z entries beyond 1e-12 relative when only its BLAS is swapped, per shape
+# (tests/golden/*_2p14.npz: ref_blas_swap_z_frac_gt_1e-12, measured on the unmodified reference at M = 2^14)
+_REF_FRAC = {(32, 65, 64): "roofline_d32_n65_r64", (40, 33, 32): "lorenz_d40_n33_r32_i64", (11, 17, 16): "diffusion_d11_n17_r16"}
+
+
 @pytest.mark.parametrize("d,n,r,log2m", [(32, 65, 64, 17), (40, 33, 32, 18), (11, 17, 16, 19)])
-def test_fast_against_strict_at_scale(d, n, r, log2m):
+def test_fast_against_strict_at_scale(oracle_mod, golden_dir, d, n, r, log2m):
     """Beyond the sizes the CPU oracle finishes in seconds the strict GPU mode stands in for it (it is bit-exact against
-    the oracle on every shape of this file): the fast path must choose the same grid interval for every sample and
-    dimension and stay within the protocol's relative bar on all but the ill-conditioned entries."""
+    the oracle on every shape of this file and against the reference's complete output at 2^14, test_parity_2p14.py).
+    The fast path must choose the same grid interval for every sample and dimension -- a differing index is admitted only
+    where the ORACLE, run on that row, reports q within 1e-13 of a CDF node -- and its share of Z entries beyond 1e-12
+    relative must not exceed 1.5x the share the reference itself shows under a BLAS swap on this shape."""
     M = 1 << log2m
     ns, xs, rk, c = synth.make_tt(d, n, r, seed=31 + d)
     q = synth.make_q(M, d, seed=5)
@@ -435,13 +444,72 @@ def test_fast_against_strict_at_scale(d, n, r, log2m):
     finally:
         md.close()
     assert np.array_equal(Zf, Zf2) and np.array_equal(lf, lf2)           # deterministic
-    flips = int((ixs != ixf).sum())
-    assert flips <= 2, "%d interval indices differ between the fast and the strict path" % flips
-    dz = np.abs(Zf - Zs) / np.maximum(1.0, np.abs(Zs))
-    dl = np.abs(lf - ls) / np.maximum(1.0, np.abs(ls))
+    flipped = np.argwhere(ixs != ixf)
+    ok_rows = np.ones(M, dtype=bool)
+    if flipped.size:
+        rows = np.unique(flipped[:, 0])
+        assert rows.size <= 4, "%d rows with differing interval indices" % rows.size
+        Zo, lo, io, kap, gap, cond, lsens = _oracle(oracle_mod, ns, xs, rk, c, q[rows])
+        assert np.array_equal(io, ixs[rows])                               # strict == oracle on these rows
+        pos = {int(m): i for i, m in enumerate(rows)}
+        for m, k in flipped:
+            first = int(np.nonzero(ixs[m] != ixf[m])[0][0])                # later dimensions follow from the first flip
+            assert gap[pos[int(m)], first] < 1e-13, "row %d dim %d: interval differs although q is %.2e away from the CDF node" % (m, first, gap[pos[int(m)], first])
+        ok_rows[rows] = False
+    dz = np.abs(Zf - Zs)[ok_rows] / np.maximum(1.0, np.abs(Zs[ok_rows]))
+    dl = np.abs(lf - ls)[ok_rows] / np.maximum(1.0, np.abs(ls[ok_rows]))
     assert dz.max() < 1e-7 and dl.max() < 1e-9                            # ill-conditioned entries (oracle/parity.py) stay bounded
-    assert (dz > 1e-12).mean() < 2e-3 and (dl > 1e-12).mean() < 2e-3      # and rare
+    ref_frac = float(np.load(os.path.join(golden_dir, _REF_FRAC[(d, n, r)] + "_2p14.npz"))["ref_blas_swap_z_frac_gt_1e-12"])
+    assert (dz > 1e-12).mean() <= 1.5 * ref_frac, ((dz > 1e-12).mean(), ref_frac)
+    assert (dl > 1e-12).mean() <= 1e-5
     assert np.median(dz) < 1e-15 and np.median(dl) < 1e-14
+
+
+def test_int32_abi_edge_largest_batch(oracle_mod):
+    """The largest batch the int32 ABI can address: M = 2^26, d = 32, last element index 2^31 - 1 (the reference computes
+    m + i + M * k in `int`, tt_irt1_int32.c:135,159).  A rank-1 density keeps the arithmetic trivial; what is tested is
+    that every row and column of the 16 GiB arrays is read and written at the right place (first / last rows, rows either
+    side of every 2^31-byte boundary of the column-major arrays, random rows), through the int32 symbol."""
+    avail = 0
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable"):
+                    avail = int(line.split()[1]) >> 20
+    except OSError:
+        pass
+    if avail < 48:
+        pytest.skip("needs 2 x 16 GiB host arrays, %d GiB available" % avail)
+    d, n, M = 32, 5, 1 << 26
+    ns = np.full(d, n, dtype=np.int64); rk = np.ones(d + 1, dtype=np.int64)
+    rng = np.random.default_rng(5)
+    xs = np.concatenate([np.sort(rng.uniform(-1.0, 2.0, n)) for _ in range(d)])
+    c = rng.random(d * n) + 0.1
+    block = np.asfortranarray(rng.random((1 << 16, d)))
+    q = np.empty((M, d), order="F")
+    for k in range(d):                      # cheap fill: a 2^16-row random block, rolled differently in every column
+        col = np.roll(block[:, k], 977 * k)
+        q[:, k].reshape(-1, 1 << 16)[:] = col[None, :]
+    rows = np.unique(np.concatenate([np.arange(0, 200), np.arange(M - 200, M), np.arange(M // 2 - 100, M // 2 + 100),
+                                     (np.arange(1, 8) * (M // 8))[:, None].repeat(3, 1).ravel() + np.tile([-1, 0, 1], 7),
+                                     rng.integers(0, M, 3000)]))
+    q[rows] = rng.random((rows.size, d))    # distinct seeds on the checked rows
+    f = tt_irt.TTTensor(ns, rk, c)
+    os.environ["TTIRT_DEVICES"] = "1"
+    try:
+        Z, l = tt_irt.tt_irt1(q, f, xs)
+    finally:
+        os.environ.pop("TTIRT_DEVICES", None)
+    Zo, lo, io, kap, gap, cond, lsens = _oracle(oracle_mod, ns, xs, rk, c, q[rows])
+    stats, fails = oracle_mod.parity.compare(Z[rows], l[rows], None, Zo, lo, None, cond, gap, lsens=lsens)
+    assert not fails, (fails, stats)
+    # the tiled rows repeat with period 2^16: so must the results (a misplaced chunk or column would break the period)
+    probe = np.setdiff1d(np.arange(5000, 5064), rows % (1 << 16))
+    for m in probe[:16]:
+        same = np.arange(m, M, 1 << 16)
+        same = same[~np.isin(same, rows)]
+        assert (Z[same] == Z[same[0]]).all() and (l[same] == l[same[0]]).all()
+    assert np.isfinite(l).all()
 
 
 @pytest.mark.parametrize("seed", range(12))

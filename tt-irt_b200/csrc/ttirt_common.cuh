@@ -171,6 +171,24 @@ struct TransArgs {
   int *hist_next;            // n1-1 counters for binning dimension k+1 (unused when last)
 };
 
+// Arguments of the all-dimensions "walk" kernel (ttirt_walk.cu): small uniform-rank TTs, one launch per chunk.
+struct WalkArgs {
+  const double *pack;        // per-dimension operand blocks (walk_pack), 16-byte aligned
+  int d, rows;
+  const double *q;           // column-major rows x d, leading dimension ldq
+  int64_t ldq;
+  double *z;                 // column-major, leading dimension ldz
+  int64_t ldz;
+  double *lpz;
+  int32_t *idx_out;          // may be NULL; leading dimension ldz
+};
+int walk_class_for(int r, int n);                    // -1: shape not served by the walk kernel
+int64_t walk_pack_doubles(int cls, int d);
+cudaError_t walk_init(int device);
+cudaError_t walk_pack(int cls, const DimInfo *d_dims, int d, const double *xs, const double *core, const double *pk,
+                      const double *p0, const double *cdf0, double *pack, cudaStream_t st);
+cudaError_t launch_walk(int cls, const WalkArgs &a, int sm_count, cudaStream_t st);
+
 // fast-path shape classes: (rank tiles of 8, grid tiles of 8)
 int fast_class_for(int rmax, int nmax);             // -1: shape outside the fast path
 int fast_rows_per_cta(int cls);

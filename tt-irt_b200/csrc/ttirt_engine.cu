@@ -119,6 +119,8 @@ struct ttirt_model {
   int64_t sum_pkw = 0;
   double *d_p0 = nullptr, *d_cdf0 = nullptr;
   DimInfo *d_dims = nullptr;
+  int walk_cls = -1;             // >= 0: the all-dimensions walk kernel serves this model's fast path (ttirt_walk.cu)
+  double *d_walk = nullptr;      // its packed per-dimension operand blocks
   Workspace ws[kSlots];      // host pipeline slots (own streams)
   // device-pointer API: two workspaces of its own.  A call of several chunks alternates them on two internal streams
   // forked from / joined into the caller's stream, so that one chunk's sort, kernel prologues and drains run under the
@@ -485,7 +487,7 @@ extern "C" void ttirt_model_destroy(ttirt_model *md) {
   for (auto &h : md->stage) { cudaFreeHost(h.q); cudaFreeHost(h.z); cudaFreeHost(h.lpz); }
   for (auto &p : md->prof_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   cudaFree(md->d_xs); cudaFree(md->d_core); cudaFree(md->d_pk); cudaFree(md->d_pkw); cudaFree(md->d_marg);
-  cudaFree(md->d_p0); cudaFree(md->d_cdf0); cudaFree(md->d_dims);
+  cudaFree(md->d_p0); cudaFree(md->d_cdf0); cudaFree(md->d_dims); cudaFree(md->d_walk);
   delete md;
 }
 
@@ -583,6 +585,10 @@ static int model_load_body(ttirt_model *md, const CoreSource &src) {
   }
   stage0_table_kernel<<<1, 32>>>(md->d_pk, md->d_xs, md->d_p0, md->d_cdf0, md->dims[0].n);
   LAUNCHED();
+  if (md->walk_cls >= 0) {
+    CK(walk_pack(md->walk_cls, md->d_dims, (int)d, md->d_xs, md->d_core, md->d_pk, md->d_p0, md->d_cdf0, md->d_walk, nullptr));
+    LAUNCHED();
+  }
   if (md->fast_cls >= 0 && d > 1) {
     weight_p_kernel<<<dim3(8, (unsigned)d), 256>>>(md->d_dims, (int)d, md->d_xs, md->d_pk, md->d_pkw);
     LAUNCHED();
@@ -622,6 +628,18 @@ static int model_build(ttirt_model *md, const int64_t *n, const int64_t *rk, con
   if (prop.major < 10) return fail("device %d (%s, sm_%d%d) is not a Blackwell B200-class GPU", md->device, prop.name, prop.major, prop.minor);
   md->sm_count = prop.multiProcessorCount;
   CK(fast_init(md->device));
+  // small uniform-rank TTs: one persistent kernel for the whole walk (TTIRT_WALK=0: per-dimension path, for comparison)
+  {
+    static const bool walk_on = !(getenv("TTIRT_WALK") && atoi(getenv("TTIRT_WALK")) == 0);
+    bool uniform = d >= 2;
+    for (int64_t k = 0; k < d && uniform; k++) uniform = n[k] == n[0];
+    for (int64_t k = 1; k < d && uniform; k++) uniform = rk[k] == rk[1];
+    md->walk_cls = (walk_on && uniform) ? walk_class_for((int)rk[1], (int)n[0]) : -1;
+    if (md->walk_cls >= 0) {
+      CK(walk_init(md->device));
+      CK(cudaMalloc(&md->d_walk, sizeof(double) * walk_pack_doubles(md->walk_cls, (int)d)));
+    }
+  }
 
   CK(cudaMalloc(&md->d_xs, sizeof(double) * ox));
   CK(cudaMalloc(&md->d_core, sizeof(double) * oc));
@@ -669,7 +687,7 @@ extern "C" int ttirt_model_get_sweep(const ttirt_model *md, double *pk_out, doub
 // ------------------------------------------------------------------------------------------------
 // kernels in one chunk's sequence (what a graph replay launches)
 static int64_t g_launches_per_graph(const ttirt_model *md, int mode) {
-  if (mode == TTIRT_MODE_STRICT || md->fast_cls < 0) return 1;
+  if (mode == TTIRT_MODE_STRICT || md->fast_cls < 0 || md->walk_cls >= 0) return 1;
   return 1 + 2 * (md->d - 1);
 }
 
@@ -682,6 +700,13 @@ static int enqueue_chunk(ttirt_model *md, Workspace &w, int64_t rows, const doub
                                                                   z, ldz, lpz, idx_out, w.left, w.pbuf, w.cbuf, (int)md->rmax);
     LAUNCHED();
     CK(cudaGetLastError());
+    return 0;
+  }
+  if (md->walk_cls >= 0) {
+    WalkArgs wa;
+    wa.pack = md->d_walk; wa.d = d; wa.rows = (int)rows; wa.q = q; wa.ldq = ldq; wa.z = z; wa.ldz = ldz; wa.lpz = lpz; wa.idx_out = idx_out;
+    CK(launch_walk(md->walk_cls, wa, md->sm_count, st));
+    LAUNCHED();
     return 0;
   }
   const int nbpad = (int)md->nbpad;

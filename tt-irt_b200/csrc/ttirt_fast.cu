@@ -112,6 +112,9 @@ __device__ __forceinline__ void stage_slab(bool async_ok, double *dst, const dou
   else stage_b(dst, src, K, NC, cs, KP, NCP, tid, nthr);
 }
 
+#ifndef TTIRT_SWPIPE
+#define TTIRT_SWPIPE 0
+#endif
 #ifndef TTIRT_MMA_WARPS
 #define TTIRT_MMA_WARPS 8
 #endif
@@ -514,6 +517,54 @@ __global__ void __launch_bounds__(nthr_of(TW), 1) transition_kernel(const TransA
         for (int i = 0; i < MT; i++)
 #pragma unroll
           for (int j = 0; j < RT; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+#if TTIRT_SWPIPE
+        if (EXACT) {
+          // Software-pipelined operand loads: the fragments of step (j, jj + 1) are requested before the DMMAs of step
+          // (j, jj) issue, so a warp that has the sub-partition to itself (its partner is between tiles) does not wait
+          // for shared memory in front of every group of DMMAs.
+          double2 fq[2][MT], bl[2], bh[2];
+#pragma unroll
+          for (int i = 0; i < MT; i++) fq[0][i] = *reinterpret_cast<const double2 *>(ft + (8 * i + g) * FP + 2 * t);
+          {
+            const int off0 = g * KP + (((0 ^ (g & 1)) << 3) | (t << 1));
+            bl[0] = *reinterpret_cast<const double2 *>(sl_lo + off0);
+            bh[0] = *reinterpret_cast<const double2 *>(sl_hi + off0);
+          }
+#pragma unroll
+          for (int j = 0; j < RT; j++) {
+            double a1[MT][2], a2[MT][2];
+#pragma unroll
+            for (int i = 0; i < MT; i++) {
+              const double2 f = fq[j & 1][i];
+              a1[i][0] = w1[i] * f.x; a2[i][0] = w2[i] * f.x; a1[i][1] = w1[i] * f.y; a2[i][1] = w2[i] * f.y;
+            }
+            if (j + 1 < RT) {
+#pragma unroll
+              for (int i = 0; i < MT; i++) fq[(j + 1) & 1][i] = *reinterpret_cast<const double2 *>(ft + (8 * i + g) * FP + 2 * t + 8 * (j + 1));
+            }
+#pragma unroll
+            for (int jj = 0; jj < RT; jj++) {
+              const int cur = (j * RT + jj) & 1;
+              if (jj + 1 < RT || j + 1 < RT) {
+                const int jn = jj + 1 < RT ? j : j + 1, jjn = jj + 1 < RT ? jj + 1 : 0;
+                const int offn = (8 * jjn + g) * KP + (((jn ^ (g & 1)) << 3) | (t << 1));
+                bl[cur ^ 1] = *reinterpret_cast<const double2 *>(sl_lo + offn);
+                bh[cur ^ 1] = *reinterpret_cast<const double2 *>(sl_hi + offn);
+              }
+              const double2 b1 = bl[cur], b2 = bh[cur];
+#pragma unroll
+              for (int i = 0; i < MT; i++) dmma884(acc[i][jj][0], acc[i][jj][1], a1[i][0], b1.x);
+#pragma unroll
+              for (int i = 0; i < MT; i++) dmma884(acc[i][jj][0], acc[i][jj][1], a2[i][0], b2.x);
+#pragma unroll
+              for (int i = 0; i < MT; i++) dmma884(acc[i][jj][0], acc[i][jj][1], a1[i][1], b1.y);
+#pragma unroll
+              for (int i = 0; i < MT; i++) dmma884(acc[i][jj][0], acc[i][jj][1], a2[i][1], b2.y);
+            }
+          }
+        } else
+#endif
+        {
 #pragma unroll
         for (int j = 0; j < RT; j++) {
           if (EXACT || j < ks0) {
@@ -542,6 +593,7 @@ __global__ void __launch_bounds__(nthr_of(TW), 1) transition_kernel(const TransA
             }
           }
         }
+        }
         PT_MARK(2)
         // ---- the staged tile is consumed: launch the next tile's gather and scalar loads now ---------
         __syncwarp();
@@ -554,6 +606,34 @@ __global__ void __launch_bounds__(nthr_of(TW), 1) transition_kernel(const TransA
         const bool do_store = !a.last;
         PT_MARK(3)
         // ---- (2) conditional pdf on the grid of dimension k+1 ----------------------------------------
+#if TTIRT_SWPIPE
+        if (EXACT) {
+          double2 bq[2];
+          bq[0] = *reinterpret_cast<const double2 *>(Ps + g * KP + (((0 ^ (g & 1)) << 3) | (t << 1)));
+#pragma unroll
+          for (int jj = 0; jj < RT; jj++) {
+#pragma unroll
+            for (int jn = 0; jn < NTD; jn++) {
+              const int cur = (jj * NTD + jn) & 1;
+              if (jn + 1 < NTD || jj + 1 < RT) {
+                const int jjn = jn + 1 < NTD ? jj : jj + 1, jnn = jn + 1 < NTD ? jn + 1 : 0;
+                bq[cur ^ 1] = *reinterpret_cast<const double2 *>(Ps + (8 * jnn + g) * KP + (((jjn ^ (g & 1)) << 3) | (t << 1)));
+              }
+              const double2 bv = bq[cur];
+#pragma unroll
+              for (int i = 0; i < MT; i++) dmma884(c[i][jn][0], c[i][jn][1], acc[i][jj][0], bv.x);
+#pragma unroll
+              for (int i = 0; i < MT; i++) dmma884(c[i][jn][0], c[i][jn][1], acc[i][jj][1], bv.y);
+            }
+            if (do_store) {
+#pragma unroll
+              for (int i = 0; i < MT; i++)
+                if (8 * i + g < nvalid) *reinterpret_cast<double2 *>(Fo[i] + 8 * jj) = make_double2(acc[i][jj][0], acc[i][jj][1]);
+            }
+          }
+        } else
+#endif
+        {
 #pragma unroll
         for (int jj = 0; jj < RT; jj++) {
           if (EXACT || jj < rt_act) {
@@ -574,6 +654,7 @@ __global__ void __launch_bounds__(nthr_of(TW), 1) transition_kernel(const TransA
                 if (8 * i + g < nvalid) *reinterpret_cast<double2 *>(Fo[i] + 8 * jj) = make_double2(acc[i][jj][0], acc[i][jj][1]);
             }
           }
+        }
         }
         if (TAIL1) {
           // last grid column (node 8*(NT-1), even column: no swizzle): quad-distributed dot product
