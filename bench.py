@@ -626,18 +626,30 @@ def other_configs(torch, peak_tflops):
             nn, rr = np.ascontiguousarray(ns, dtype=it), np.ascontiguousarray(rk, dtype=it)
             os.environ["TTIRT_DEVICE"] = "0"; os.environ["TTIRT_DEVICES"] = "1"
 
-            def call():
-                fn(ct(d), nn.ctypes.data_as(ip), xs.ctypes.data_as(dp), rr.ctypes.data_as(ip), cores.ctypes.data_as(dp), ct(M),
+            cores_b = cores.copy()
+            cores_b[-1] = np.nextafter(cores_b[-1], 2.0)   # a second TT, one ulp away in one entry: forces upload + sweep
+
+            def call(cc=cores):
+                fn(ct(d), nn.ctypes.data_as(ip), xs.ctypes.data_as(dp), rr.ctypes.data_as(ip), cc.ctypes.data_as(dp), ct(M),
                    C.cast(qh.data_ptr(), dp), C.cast(zh.data_ptr(), dp), C.cast(lh.data_ptr(), dp))
-            for _ in range(warm):
-                call()
+            # (a) a different TT on every call: grid + cores upload, sweep and operand packing inside every call
+            for i in range(warm):
+                call(cores_b if i & 1 else cores)
+            t0 = time.perf_counter()
+            for i in range(steps):
+                call(cores_b if i & 1 else cores)
+            dt = (time.perf_counter() - t0) / steps
+            # (b) the same TT again and again (the MH / IW drivers' pattern): models up to 512 KB are recognised by an exact
+            #     byte comparison and stay resident
+            call(); call()
             t0 = time.perf_counter()
             for _ in range(steps):
                 call()
-            dt = (time.perf_counter() - t0) / steps
+            dts = (time.perf_counter() - t0) / steps
             ok = bool(torch.isfinite(lh).all()) and bool(torch.equal(lh, l.cpu()))
             out[name] = {"d": d, "n": n, "r": r, "M": M, "abi_width": width, "value": val, "ms_per_step": ms, "launches_per_step": int(launches),
-                         "e2e_value": M / dt, "e2e_ms_per_call": 1e3 * dt, "e2e_matches_device_resident_bit_for_bit": ok,
+                         "e2e_value": M / dt, "e2e_ms_per_call": 1e3 * dt, "e2e_ms_per_call_same_tt_again": 1e3 * dts,
+                         "e2e_matches_device_resident_bit_for_bit": ok,
                          "flops_per_sample": Wf, "frac_of_fp64_peak": val * Wf / 1e12 / peak_tflops,
                          "frac_of_hbm_stream_bound": val * 8 * (2 * d + 1) / 1e9 / _hbm_peak(),
                          "binding_roofline": "fp64" if Wf / (8.0 * (2 * d + 1)) > peak_tflops * 1e3 / _hbm_peak() else "hbm"}
@@ -673,7 +685,7 @@ def _ncu_traffic(M):
         try:
             with open(f) as fh:
                 j = json.load(fh)
-            if "transition_kernel" in j.get("kernel", "") and min(M, 1 << 20) == int(j["rows_per_launch"]):
+            if "transition_kernel" in j.get("kernel", "") and min(M, 1 << 22) == int(j["rows_per_launch"]):
                 best = (int(j["dram_bytes_read"]) + int(j["dram_bytes_write"]), os.path.relpath(f, ROOT))
         except Exception:
             continue

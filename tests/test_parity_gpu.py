@@ -306,7 +306,7 @@ def test_failed_workspace_allocation_is_recoverable(oracle_mod):
     """A caller-held model whose scratch allocation fails (absurd chunk) must come back empty, not half-built: the next,
     ordinary call allocates afresh and is correct (no kernels on null scratch, no sticky CUDA error)."""
     torch = pytest.importorskip("torch")
-    d, n, r, M = 6, 17, 8, 4000
+    d, n, r, M = 3, 65, 64, 4000                    # per-dimension path (interface rows of 512 B per sample in the workspace)
     ns, xs, rk, c = synth.make_tt(d, n, r, seed=14)
     q = synth.make_q(M, d, seed=15)
     Zo, lo, io, kap, gap, cond, lsens = _oracle(oracle_mod, ns, xs, rk, c, q)
@@ -316,13 +316,13 @@ def test_failed_workspace_allocation_is_recoverable(oracle_mod):
         Z0, l0 = md.sample(q)                        # a workspace exists
         qd = torch.from_numpy(np.ascontiguousarray(q.T)).cuda()
         zd = torch.empty_like(qd); ld_ = torch.empty(M, dtype=torch.float64, device="cuda")
-        huge = 1 << 36                               # 2^36 rows x 64 B of interface rows: cannot be allocated
+        huge = 1 << 30                               # 2^30 rows x 512 B of interface rows: cannot be allocated
         lib.ttirt_set_chunk(huge)
         try:
             with pytest.raises(RuntimeError):
                 md.sample_device(huge, qd.data_ptr(), huge, zd.data_ptr(), huge, ld_.data_ptr())
             dp = ctypes.POINTER(ctypes.c_double)
-            rc = lib.ttirt_sample_host(md._h, huge, q.ctypes.data_as(dp), Z0.ctypes.data_as(dp), l0.ctypes.data_as(dp), None, huge, tt_irt.MODE_FAST)
+            rc = lib.ttirt_sample_host(md._h, 4 * huge, q.ctypes.data_as(dp), Z0.ctypes.data_as(dp), l0.ctypes.data_as(dp), None, 4 * huge, tt_irt.MODE_FAST)
             assert rc != 0
         finally:
             lib.ttirt_set_chunk(0)
@@ -561,6 +561,40 @@ def test_host_pipeline_with_padded_leading_dimension(M, extra):
         md.close()
     assert np.array_equal(zbig[:M], Zref) and np.array_equal(lbig[:M], lref)
     assert (zbig[M:] == -7.0).all() and (lbig[M:] == -7.0).all()      # rows beyond M untouched
+
+
+def test_resident_small_model_is_never_stale(oracle_mod):
+    """The drop-in call keeps a small model resident when the next call brings bit-identical grid and cores (exact byte
+    comparison).  A change of a single core entry, of the grid, or of nothing at all must each give exactly the result of
+    a fresh model."""
+    d, n, r, M = 6, 17, 8, 3000
+    ns, xs, rk, c = synth.make_tt(d, n, r, seed=41)
+    q = synth.make_q(M, d, seed=42)
+
+    def fresh(xs_, c_):
+        md = tt_irt.Model(ns, xs_, rk, c_)
+        try:
+            return md.sample(q)
+        finally:
+            md.close()
+    f = tt_irt.TTTensor(ns, rk, c)
+    Z0, l0 = tt_irt.tt_irt1(q, f, xs)
+    Z1, l1 = tt_irt.tt_irt1(q, f, xs)                      # same bytes: resident model
+    Zr, lr = fresh(xs, c)
+    assert np.array_equal(Z0, Zr) and np.array_equal(l0, lr) and np.array_equal(Z1, Zr) and np.array_equal(l1, lr)
+    c2 = c.copy(); c2[c2.size // 2] *= 1.5                 # one core entry differs
+    Z2, l2 = tt_irt.tt_irt1(q, tt_irt.TTTensor(ns, rk, c2), xs)
+    Zr2, lr2 = fresh(xs, c2)
+    assert np.array_equal(Z2, Zr2) and np.array_equal(l2, lr2) and not np.array_equal(Z2, Z0)
+    xs2 = xs.copy(); xs2[3] += 1e-3                        # one grid point differs
+    Z3, l3 = tt_irt.tt_irt1(q, tt_irt.TTTensor(ns, rk, c2), xs2)
+    Zr3, lr3 = fresh(xs2, c2)
+    assert np.array_equal(Z3, Zr3) and np.array_equal(l3, lr3) and not np.array_equal(Z3, Z2)
+    Z4, l4 = tt_irt.tt_irt1(q, f, xs)                      # back to the first TT
+    assert np.array_equal(Z4, Z0) and np.array_equal(l4, l0)
+    Zo, lo, io, kap, gap, cond, lsens = _oracle(oracle_mod, ns, xs, rk, c, q)
+    stats, fails = oracle_mod.parity.compare(Z4, l4, None, Zo, lo, None, cond, gap, lsens=lsens)
+    assert not fails, (fails, stats)
 
 
 def test_repeated_drop_in_calls_are_stable_and_do_not_leak():

@@ -66,11 +66,22 @@ void aux_launched() { if (!t_capturing) g_launches.fetch_add(1, std::memory_orde
 
 #define LAUNCHED() do { if (!t_capturing) g_launches.fetch_add(1, std::memory_order_relaxed); } while (0)
 
+static bool trace_on() {
+  static int v = -1;
+  if (v < 0) v = getenv("TTIRT_TRACE") != nullptr;
+  return v != 0;
+}
+static double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// samples per chunk; never beyond 2^30 (kernels index a chunk's rows with int)
 static int64_t default_chunk() {
+  const int64_t cap = (int64_t)1 << 30;
   int64_t c = g_chunk.load();
-  if (c > 0) return c;
+  if (c > 0) return std::min(c, cap);
   const char *e = getenv("TTIRT_CHUNK");
-  if (e && atoll(e) > 0) return atoll(e);
+  if (e && atoll(e) > 0) return std::min<int64_t>(atoll(e), cap);
   return (int64_t)1 << 20;
 }
 
@@ -78,6 +89,7 @@ static int64_t default_chunk() {
 // model
 // ------------------------------------------------------------------------------------------------
 constexpr int kSlots = 4;
+constexpr size_t kImageBytes = 512 << 10;   // models up to this size keep a host image for the bit-identical-reload check
 
 struct Workspace {
   int64_t cap = 0;       // samples
@@ -119,6 +131,13 @@ struct ttirt_model {
   int64_t sum_pkw = 0;
   double *d_p0 = nullptr, *d_cdf0 = nullptr;
   DimInfo *d_dims = nullptr;
+  // model_load() enqueues upload, sweep and operand packing on load_stream and records `loaded`; the host pipeline lets its
+  // slot streams wait for that event instead of synchronising the device (a small call is all latency)
+  cudaStream_t load_stream = nullptr;
+  cudaEvent_t loaded = nullptr;
+  std::vector<double> image;      // host copy of (xs, cores) the model was loaded from, small models only
+  bool image_valid = false;
+  bool keep_transition_path = false;   // walk models: also prepare the per-dimension path (never needed in production)
   int walk_cls = -1;             // >= 0: the all-dimensions walk kernel serves this model's fast path (ttirt_walk.cu)
   double *d_walk = nullptr;      // its packed per-dimension operand blocks
   Workspace ws[kSlots];      // host pipeline slots (own streams)
@@ -157,15 +176,18 @@ static void ws_free(Workspace &w) {
 
 static int ws_alloc(ttirt_model *md, Workspace &w, int64_t cap, bool s, bool h, bool wi) {
   const int64_t d = md->d;
-  CK(cudaMalloc(&w.F, sizeof(double) * cap * md->ldf));
-  CK(cudaMalloc(&w.idx, sizeof(int) * cap));
-  CK(cudaMalloc(&w.perm, sizeof(int) * cap));
-  CK(cudaMalloc(&w.w1, sizeof(double) * cap));
-  CK(cudaMalloc(&w.w2, sizeof(double) * cap));
-  CK(cudaMalloc(&w.lp, sizeof(double) * cap));
-  CK(cudaMalloc(&w.lpd, sizeof(double) * cap));
-  CK(cudaMalloc(&w.lpe, sizeof(int) * cap));
-  CK(cudaMalloc(&w.hist, sizeof(int) * 2 * d * md->nbpad));   // d interval histograms, then d sets of scatter cursors
+  // per-sample state of the per-dimension path; the walk kernel keeps all of it in registers
+  if (md->walk_cls < 0 || md->keep_transition_path) {
+    CK(cudaMalloc(&w.F, sizeof(double) * cap * md->ldf));
+    CK(cudaMalloc(&w.idx, sizeof(int) * cap));
+    CK(cudaMalloc(&w.perm, sizeof(int) * cap));
+    CK(cudaMalloc(&w.w1, sizeof(double) * cap));
+    CK(cudaMalloc(&w.w2, sizeof(double) * cap));
+    CK(cudaMalloc(&w.lp, sizeof(double) * cap));
+    CK(cudaMalloc(&w.lpd, sizeof(double) * cap));
+    CK(cudaMalloc(&w.lpe, sizeof(int) * cap));
+    CK(cudaMalloc(&w.hist, sizeof(int) * 2 * d * md->nbpad));   // d interval histograms, then d sets of scatter cursors
+  }
   if (s) {
     CK(cudaMalloc(&w.left, sizeof(double) * 2 * md->rmax * cap));
     CK(cudaMalloc(&w.pbuf, sizeof(double) * md->nmax * cap));
@@ -236,8 +258,11 @@ __global__ void sweep_integrate_kernel(const double *__restrict__ P, const doubl
 // The whole right-to-left sweep in one launch (one CTA walks the dimensions; the per-element operation order is that
 // of the two kernels above, so the results are bit-identical).  The sweep is ~16 MFLOP even at the metric shape:
 // what it costs is launches, and a call of the drop-in symbol pays for it every time.
+__device__ void strict_cdf(double *p, double *cdf, const double *x, int nk, int64_t st);
 __global__ void sweep_fused_kernel(const DimInfo *__restrict__ dims, int d, const double *__restrict__ core,
-                                   const double *__restrict__ xs, double *pk, double *marg) {
+                                   const double *__restrict__ xs, double *pk, double *marg, double *p0, double *cdf0) {
+  if (threadIdx.x == 0) marg[dims[d - 1].off_m] = 1.0;   // C_{d-1} = {1} (reference :60-61)
+  __syncthreads();
   for (int k = d - 1; k >= 0; k--) {
     const DimInfo di = dims[k];
     const int rows = di.r0 * di.n, rr = di.r1;
@@ -262,6 +287,13 @@ __global__ void sweep_fused_kernel(const DimInfo *__restrict__ dims, int d, cons
       }
       __syncthreads();
     }
+  }
+  // stage-0 tables (the body of stage0_table_kernel): the first conditional is the same for every sample
+  if (threadIdx.x == 0) {
+    const int n0 = dims[0].n;
+    const double *P0 = pk + dims[0].off_p, *x = xs + dims[0].off_x;
+    for (int j = 0; j < n0; j++) p0[j] = fabs(__dadd_rn(0.0, __dmul_rn(P0[j], 1.0)));
+    strict_cdf(p0, cdf0, x, n0, 1);
   }
 }
 
@@ -484,6 +516,8 @@ extern "C" void ttirt_model_destroy(ttirt_model *md) {
   for (auto &w : md->ws) ws_free(w);
   for (auto &w : md->dws) ws_free(w);
   if (md->fork_ev) cudaEventDestroy(md->fork_ev);
+  if (md->load_stream) { cudaStreamSynchronize(md->load_stream); cudaStreamDestroy(md->load_stream); }
+  if (md->loaded) cudaEventDestroy(md->loaded);
   for (auto &h : md->stage) { cudaFreeHost(h.q); cudaFreeHost(h.z); cudaFreeHost(h.lpz); }
   for (auto &p : md->prof_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   cudaFree(md->d_xs); cudaFree(md->d_core); cudaFree(md->d_pk); cudaFree(md->d_pkw); cudaFree(md->d_marg);
@@ -549,53 +583,93 @@ static int model_load_body(ttirt_model *md, const CoreSource &src) {
       f.cv.wait(l, [&] { return f.state != 0; });
     }
     if (f.state == 1) {
-      cudaError_t e = cudaDeviceEnablePeerAccess(f.src_device, 0);
-      if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
-      if (e == cudaSuccess) e = cudaMemcpyPeer(md->d_xs, md->device, f.d_xs, f.src_device, sizeof(double) * md->sum_x);
-      if (e == cudaSuccess) e = cudaMemcpyPeer(md->d_core, md->device, f.d_core, f.src_device, sizeof(double) * md->sum_c);
+      cudaError_t e = cudaSuccess;
+      cudaStream_t ps = md->load_stream;
+      if (f.src_device == md->device) {   // only under the virtual-device test hook: two logical devices on one GPU
+        e = cudaMemcpyAsync(md->d_xs, f.d_xs, sizeof(double) * md->sum_x, cudaMemcpyDeviceToDevice, ps);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(md->d_core, f.d_core, sizeof(double) * md->sum_c, cudaMemcpyDeviceToDevice, ps);
+      } else {
+        e = cudaDeviceEnablePeerAccess(f.src_device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+        if (e == cudaSuccess) e = cudaMemcpyPeerAsync(md->d_xs, md->device, f.d_xs, f.src_device, sizeof(double) * md->sum_x, ps);
+        if (e == cudaSuccess) e = cudaMemcpyPeerAsync(md->d_core, md->device, f.d_core, f.src_device, sizeof(double) * md->sum_c, ps);
+      }
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ps);   // the root may reuse its buffers once this peer has reported
       if (e == cudaSuccess) have = true; else cudaGetLastError();
     }
     f.peer_done(src.peer);
   }
+  cudaStream_t ls = md->load_stream;
+  const double tl0 = now_s();
   if (!have) {
-    cudaError_t e = cudaMemcpy(md->d_xs, xs, sizeof(double) * md->sum_x, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(md->d_core, core, sizeof(double) * md->sum_c, cudaMemcpyHostToDevice);
-    if (src.fan && src.root) src.fan->publish(e == cudaSuccess ? 1 : -1, md->device, md->d_xs, md->d_core);
+    // pageable sources are staged by the driver before cudaMemcpyAsync returns, so the caller's arrays may change afterwards
+    cudaError_t e = cudaMemcpyAsync(md->d_xs, xs, sizeof(double) * md->sum_x, cudaMemcpyHostToDevice, ls);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(md->d_core, core, sizeof(double) * md->sum_c, cudaMemcpyHostToDevice, ls);
+    if (src.fan && src.root) {
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ls);   // the peers copy from this device's buffers
+      src.fan->publish(e == cudaSuccess ? 1 : -1, md->device, md->d_xs, md->d_core);
+    }
     CK(e);
   }
-  const double one = 1.0;
-  CK(cudaMemcpy(md->d_marg + md->dims[d - 1].off_m, &one, sizeof(double), cudaMemcpyHostToDevice));
-  // small TTs (the MH / IW use of the reference: r ~ 8..16, n = 17): one CTA walks the whole sweep in less time than
-  // two launches take; larger cores use one launch per step so that the contraction spreads over the SMs
+  // small TTs (the MH / IW use of the reference: r ~ 8..16, n = 17): one CTA walks the whole sweep (and builds the stage-0
+  // tables) in less time than two launches take; larger cores use one launch per step so that the contraction spreads
+  // over the SMs
   if (md->sum_c <= (1 << 18)) {
-    sweep_fused_kernel<<<1, 1024>>>(md->d_dims, (int)d, md->d_core, md->d_xs, md->d_pk, md->d_marg);
+    sweep_fused_kernel<<<1, 1024, 0, ls>>>(md->d_dims, (int)d, md->d_core, md->d_xs, md->d_pk, md->d_marg, md->d_p0, md->d_cdf0);
     LAUNCHED();
   } else {
+    static const double one = 1.0;
+    CK(cudaMemcpyAsync(md->d_marg + md->dims[d - 1].off_m, &one, sizeof(double), cudaMemcpyHostToDevice, ls));
     for (int64_t k = d - 1; k >= 0; k--) {
       const DimInfo &di = md->dims[k];
       const int rows = di.r0 * di.n;
-      sweep_contract_kernel<<<(rows + 127) / 128, 128>>>(md->d_core + di.off_c, md->d_marg + di.off_m, md->d_pk + di.off_p, rows, di.r1);
+      sweep_contract_kernel<<<(rows + 127) / 128, 128, 0, ls>>>(md->d_core + di.off_c, md->d_marg + di.off_m, md->d_pk + di.off_p, rows, di.r1);
       LAUNCHED();
       if (k > 0) {
-        sweep_integrate_kernel<<<(di.r0 + 127) / 128, 128>>>(md->d_pk + di.off_p, md->d_xs + di.off_x,
-                                                             md->d_marg + md->dims[k - 1].off_m, di.r0, di.n);
+        sweep_integrate_kernel<<<(di.r0 + 127) / 128, 128, 0, ls>>>(md->d_pk + di.off_p, md->d_xs + di.off_x,
+                                                                    md->d_marg + md->dims[k - 1].off_m, di.r0, di.n);
         LAUNCHED();
       }
     }
-  }
-  stage0_table_kernel<<<1, 32>>>(md->d_pk, md->d_xs, md->d_p0, md->d_cdf0, md->dims[0].n);
-  LAUNCHED();
-  if (md->walk_cls >= 0) {
-    CK(walk_pack(md->walk_cls, md->d_dims, (int)d, md->d_xs, md->d_core, md->d_pk, md->d_p0, md->d_cdf0, md->d_walk, nullptr));
+    stage0_table_kernel<<<1, 32, 0, ls>>>(md->d_pk, md->d_xs, md->d_p0, md->d_cdf0, md->dims[0].n);
     LAUNCHED();
   }
-  if (md->fast_cls >= 0 && d > 1) {
-    weight_p_kernel<<<dim3(8, (unsigned)d), 256>>>(md->d_dims, (int)d, md->d_xs, md->d_pk, md->d_pkw);
+  if (md->walk_cls >= 0) {
+    CK(walk_pack(md->walk_cls, md->d_dims, (int)d, md->d_xs, md->d_core, md->d_pk, md->d_p0, md->d_cdf0, md->d_walk, ls));
+    LAUNCHED();
+  }
+  if (md->fast_cls >= 0 && d > 1 && (md->walk_cls < 0 || md->keep_transition_path)) {
+    weight_p_kernel<<<dim3(8, (unsigned)d), 256, 0, ls>>>(md->d_dims, (int)d, md->d_xs, md->d_pk, md->d_pkw);
     LAUNCHED();
   }
   CK(cudaGetLastError());
-  CK(cudaDeviceSynchronize());
+  CK(cudaEventRecord(md->loaded, ls));
+  // The model is complete when this returns.  (Letting the pipeline's slot streams wait for `loaded` instead was measured
+  // and lost: 417 against 405 ms per call at the metric shape, 61 against 53 ms at d=40 n=33 r=32 -- all four slots then
+  // start at once instead of staggered behind their uploads.)
+  const double tl1 = now_s();
+  CK(cudaStreamSynchronize(ls));
+  if (trace_on())
+    fprintf(stderr, "tt_irt1[b200] trace: model_load device %d: enqueue %.3f ms (uploads are staged inside), + %.3f ms until loaded\n",
+            md->device, 1e3 * (tl1 - tl0), 1e3 * (now_s() - tl1));
+  // small models: keep the host-side image, so that the next drop-in call with bit-identical grid and cores (an MH / IW
+  // driver calling the sampler again on the same TT, reference test_shock_absorber_tt.py:138-153) skips upload and sweep
+  md->image_valid = false;
+  if ((size_t)(md->sum_x + md->sum_c) * sizeof(double) <= kImageBytes) {
+    md->image.resize((size_t)(md->sum_x + md->sum_c));
+    memcpy(md->image.data(), xs, sizeof(double) * md->sum_x);
+    memcpy(md->image.data() + md->sum_x, core, sizeof(double) * md->sum_c);
+    md->image_valid = true;
+  }
   return 0;
+}
+
+// true when the model was loaded from exactly these bytes (exact comparison, no hashing) and reuse is enabled
+static bool model_image_matches(const ttirt_model *md, const double *xs, const double *core) {
+  static const bool reuse = !(getenv("TTIRT_MODEL_REUSE") && atoi(getenv("TTIRT_MODEL_REUSE")) == 0);
+  if (!reuse || !md->image_valid) return false;
+  return memcmp(md->image.data(), xs, sizeof(double) * md->sum_x) == 0 &&
+         memcmp(md->image.data() + md->sum_x, core, sizeof(double) * md->sum_c) == 0;
 }
 
 static int model_build(ttirt_model *md, const int64_t *n, const int64_t *rk, const CoreSource &src) {
@@ -651,6 +725,8 @@ static int model_build(ttirt_model *md, const int64_t *n, const int64_t *rk, con
   CK(cudaMalloc(&md->d_dims, sizeof(DimInfo) * d));
   CK(cudaMemcpy(md->d_dims, md->dims.data(), sizeof(DimInfo) * d, cudaMemcpyHostToDevice));
   md->sum_x = ox; md->sum_c = oc;
+  CK(cudaStreamCreateWithFlags(&md->load_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&md->loaded, cudaEventDisableTiming));
   return model_load(md, src);
 }
 
@@ -671,12 +747,20 @@ extern "C" ttirt_model *ttirt_model_create(int64_t d, const int64_t *n, const do
   if (d < 1 || !n || !xs || !ttrank || !ttcore) { fail("bad arguments to ttirt_model_create"); return nullptr; }
   CoreSource src;
   src.xs = xs; src.core = ttcore;
-  return model_create_from(d, n, ttrank, src, device);
+  ttirt_model *md = model_create_from(d, n, ttrank, src, device);
+  // a caller-held model is complete when this returns (the drop-in call lets its pipeline wait for `loaded` instead)
+  if (md && cudaStreamSynchronize(md->load_stream) != cudaSuccess) {
+    fail("model upload / sweep failed: %s", cudaGetErrorString(cudaGetLastError()));
+    ttirt_model_destroy(md);
+    return nullptr;
+  }
+  return md;
 }
 
 extern "C" int ttirt_model_get_sweep(const ttirt_model *md, double *pk_out, double *marg_out) {
   if (!md) return fail("null model");
   CK(cudaSetDevice(md->device));
+  CK(cudaStreamSynchronize(md->load_stream));
   if (pk_out) CK(cudaMemcpy(pk_out, md->d_pk, sizeof(double) * md->sum_pk, cudaMemcpyDeviceToHost));
   if (marg_out) CK(cudaMemcpy(marg_out, md->d_marg, sizeof(double) * md->sum_mg, cudaMemcpyDeviceToHost));
   return 0;
@@ -767,7 +851,8 @@ static int run_chunk(ttirt_model *md, Workspace &w, int64_t rows, const double *
                      double *lpz, int32_t *idx_out, int mode, cudaStream_t st) {
   if (rows <= 0) return 0;
   // large chunks are not launch-bound, and the device-resident API would need one graph per chunk offset
-  if (!graphs_enabled() || st == nullptr || md->profile || rows > (1 << 19)) return enqueue_chunk(md, w, rows, q, ldq, z, ldz, lpz, idx_out, mode, st);
+  const bool one_launch = mode == TTIRT_MODE_STRICT || md->fast_cls < 0 || md->walk_cls >= 0;   // nothing for a graph to save
+  if (!graphs_enabled() || st == nullptr || md->profile || rows > (1 << 19) || one_launch) return enqueue_chunk(md, w, rows, q, ldq, z, ldz, lpz, idx_out, mode, st);
   for (auto &g : w.graphs) {
     if (g.rows == rows && g.q == q && g.ldq == ldq && g.z == z && g.ldz == ldz && g.lpz == lpz && g.idx_out == idx_out && g.mode == mode) {
       g.last_use = ++w.graph_clock;
@@ -817,7 +902,15 @@ extern "C" int ttirt_sample_device(ttirt_model *md, int64_t M, const double *d_q
   CK(cudaSetDevice(md->device));
   cudaStream_t st = (cudaStream_t)stream;
   const bool strict = (mode == TTIRT_MODE_STRICT) || md->fast_cls < 0;
-  const int64_t chunk = std::min<int64_t>(M, default_chunk());
+  // chunk size of the device-pointer API when none is set: 2^22 rows in the r <= 64 class (the transition kernel's prologue
+  // and drain are paid once per launch: 43.2 -> 43.8 M samples/s at the metric shape against 2^20), one launch for the
+  // walk kernel (no per-sample scratch), 2^20 otherwise
+  int64_t want = default_chunk();
+  if (g_chunk.load() <= 0 && getenv("TTIRT_CHUNK") == nullptr && !strict) {
+    if (md->walk_cls >= 0) want = (int64_t)1 << 24;
+    else if (md->fast_cls == 2) want = (int64_t)1 << 22;
+  }
+  const int64_t chunk = std::min<int64_t>(M, want);
   const int64_t nchunks = (M + chunk - 1) / chunk;
   static const bool two_streams = !(getenv("TTIRT_DEVICE_STREAMS") && atoi(getenv("TTIRT_DEVICE_STREAMS")) < 2);
   // per-launch profiling needs the kernels serialised (events around overlapping kernels measure the overlap too)
@@ -948,6 +1041,7 @@ static int sample_host_rows(ttirt_model *md, int64_t m_begin, int64_t m_end, con
                             int32_t *h_idx, int64_t ld, int mode, const SeedSpec &seeds = SeedSpec()) {
   const int64_t M = m_end - m_begin;
   if (M <= 0) return 0;
+  const double ts0 = now_s();
   CK(cudaSetDevice(md->device));
   const int d = (int)md->d;
   const bool strict = (mode == TTIRT_MODE_STRICT) || md->fast_cls < 0;
@@ -956,7 +1050,9 @@ static int sample_host_rows(ttirt_model *md, int64_t m_begin, int64_t m_end, con
   // (shorter fill and drain, copies and kernels of neighbouring chunks overlap) and every chunk is a graph replay
   if (g_chunk.load() <= 0 && getenv("TTIRT_CHUNK") == nullptr && !strict && md->fast_cls >= 0 && md->fast_cls <= 1)
     chunk = md->fast_cls == 0 ? (1 << 17) : (1 << 19);
-  if (M < chunk * kSlots) chunk = std::max<int64_t>((M + kSlots - 1) / kSlots, std::min<int64_t>(M, 1 << 16));
+  // a walk-kernel chunk is one launch: cut small calls finer, so that upload, kernel and download of neighbouring chunks overlap
+  const bool walk = !strict && md->walk_cls >= 0;
+  if (M < chunk * kSlots) chunk = std::max<int64_t>((M + kSlots - 1) / kSlots, std::min<int64_t>(M, walk ? (1 << 12) : (1 << 16)));
   const int64_t nchunks = (M + chunk - 1) / chunk;
   const int nslots = (int)std::min<int64_t>(kSlots, nchunks);
   static const bool no_stage = getenv("TTIRT_NO_STAGING") != nullptr;
@@ -968,6 +1064,7 @@ static int sample_host_rows(ttirt_model *md, int64_t m_begin, int64_t m_end, con
     if ((stage_q || stage_z) && stage_ensure(md, s, chunk, stage_q, stage_z) != 0) return -1;
   }
 
+  const double ts1 = now_s();
   // drain thread: waits for a chunk's event, copies its outputs from the slot's pinned buffer into the caller's arrays
   std::mutex mu;
   std::condition_variable cv;
@@ -1012,6 +1109,7 @@ static int sample_host_rows(ttirt_model *md, int64_t m_begin, int64_t m_end, con
     const int s = (int)(c % kSlots);
     Workspace &w = md->ws[s];
     const int64_t m0 = m_begin + c * chunk, rows = std::min(chunk, m_end - m0);
+    if (c < kSlots) CKF(cudaStreamWaitEvent(w.stream, md->loaded, 0));   // upload + sweep of this call's model (model_load)
     if (c >= kSlots) {
       if (stage_z) {   // the slot's pinned output buffer must have been drained
         std::unique_lock<std::mutex> l(mu);
@@ -1053,8 +1151,12 @@ static int sample_host_rows(ttirt_model *md, int64_t m_begin, int64_t m_end, con
       cv.notify_all();
     }
   }
+  const double te = now_s();
   for (int s = 0; s < nslots; s++) CKF(cudaStreamSynchronize(md->ws[s].stream));
 #undef CKF
+  if (trace_on())
+    fprintf(stderr, "tt_irt1[b200] trace: pipeline device %d: %lld chunks of %lld rows, setup %.3f ms, enqueue %.3f ms, wait %.3f ms (staged q %d, z %d)\n",
+            md->device, (long long)nchunks, (long long)chunk, 1e3 * (ts1 - ts0), 1e3 * (te - ts1), 1e3 * (now_s() - te), (int)stage_q, (int)stage_z);
   return finish(0);
 }
 
@@ -1127,16 +1229,6 @@ bool cache_enabled() {
   return !(e && atoi(e) == 0);
 }
 
-bool trace_on() {
-  static int v = -1;
-  if (v < 0) v = getenv("TTIRT_TRACE") != nullptr;
-  return v != 0;
-}
-
-double now_s() {
-  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
-}
-
 bool same_shape(const ttirt_model *md, int64_t d, const int64_t *n, const int64_t *rk) {
   if (!md || md->d != d) return false;
   for (int64_t k = 0; k < d; k++) if (md->n[k] != n[k]) return false;
@@ -1165,7 +1257,9 @@ int run_on_device(int device, int64_t d, const int64_t *n, const int64_t *rk, co
   device = physical_of(device);
   if (same_shape(sl.md, d, n, rk)) {
     if (cudaSetDevice(device) != cudaSuccess) return fail("cudaSetDevice(%d) failed", device);
-    if (model_load(sl.md, src) != 0) {
+    if (!src.fan && model_image_matches(sl.md, src.xs, src.core)) {
+      // same bytes as the resident model: nothing to upload, nothing to recompute
+    } else if (model_load(sl.md, src) != 0) {
       if (src.fan && src.root) src.fan->wait_peers();
       ttirt_model_destroy(sl.md); sl.md = nullptr;
       return -1;
