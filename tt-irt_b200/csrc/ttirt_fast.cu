@@ -132,7 +132,11 @@ __host__ __device__ constexpr int nthr_of(int tw) { return 32 * (MMA_WARPS + tw)
 __host__ __device__ constexpr int mma_regs_of(int tw) { return tw == 4 ? 192 : 152; }
 __host__ __device__ constexpr int tail_regs_of(int tw) { return tw == 4 ? 120 : 104; }
 
-template <int RT, int NT, bool TAIL1, int TW>
+// GD: depth of the row gather.  1: the rows of tile t+1 are requested once tile t's update phase has consumed the staged
+// tile (a whole pdf phase ahead: enough at r = 64, where that phase lasts ~2 us).  2 (the two lighter classes, where the pdf
+// phase is a quarter of that and a request would still be in flight when it is needed): two staged tiles per MMA warp,
+// the rows of tile t+2 are requested at that point.
+template <int RT, int NT, bool TAIL1, int TW, int GD>
 struct SmemLayout {
   static constexpr int KPMAX = (8 * RT + 15) & ~15;
   static constexpr int SLAB = 8 * RT * KPMAX;      // doubles per slab buffer
@@ -148,7 +152,7 @@ struct SmemLayout {
   static constexpr int HS = TAIL1 ? 4 * (NT - 1) : 4 * NT;   // cells walked by each of the two lanes of a row
   static constexpr int HB = HS / 4;                // ... as four blocks of HB consecutive cells, walked side by side
   static constexpr int NHH = 2 * HS + 8;           // entries of the per-node tables rw / hr
-  static constexpr size_t bytes = sizeof(double) * (2 * SLAB + PN + MMA_WARPS * FTILE + TW * PB + 2 * NHH + 2 * 8 * NT) +
+  static constexpr size_t bytes = sizeof(double) * (2 * SLAB + PN + MMA_WARPS * GD * FTILE + TW * PB + 2 * NHH + 2 * 8 * NT) +
                                   sizeof(int) * (2 * (NBMAX + 1) + NBMAX + TW * (WROWS + 2));
 };
 
@@ -182,17 +186,18 @@ __device__ __forceinline__ void st_volatile_s(int *p, int v) { *reinterpret_cast
 // Row gather: the left-interface rows of an MMA warp's NEXT tile are fetched asynchronously (cp.async / LDGSTS, one
 // coalesced 8*r0-byte row per instruction) into a per-warp shared tile as soon as the current tile's update
 // phase has consumed that tile, i.e. a whole pdf phase ahead of use.
-template <int RT, int NT, bool EXACT, bool TAIL1, int TW>
+template <int RT, int NT, bool EXACT, bool TAIL1, int TW, int GD>
 __global__ void __launch_bounds__(nthr_of(TW), 1) transition_kernel(const TransArgs a) {
   static_assert(EXACT || !TAIL1, "TAIL1 needs EXACT");
-  using L = SmemLayout<RT, NT, TAIL1, TW>;
+  static_assert(GD == 1 || GD == 2, "gather depth 1 or 2");
+  using L = SmemLayout<RT, NT, TAIL1, TW, GD>;
   constexpr int TAIL_WARPS = TW, NTHR = nthr_of(TW), PRODS = MMA_WARPS / TW;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *slab0 = reinterpret_cast<double *>(smem_raw);
   double *slab1 = slab0 + L::SLAB;
   double *Ps = slab1 + L::SLAB;
   double *ft_all = Ps + L::PN;                     // per-MMA-warp staged left-interface rows
-  double *pb_all = ft_all + MMA_WARPS * L::FTILE;  // per-tail-warp parked |pdf| tile
+  double *pb_all = ft_all + MMA_WARPS * GD * L::FTILE;  // per-tail-warp parked |pdf| tile
   double *rw = pb_all + TAIL_WARPS * L::PB;        // 1 / node_weight(j) of dimension k+1's grid (0 beyond node n1-1)
   double *hr = rw + L::NHH;                        // h_{j-1} / node_weight(j): share of node j's weight left of it
   double *xg = hr + L::NHH;                        // grid of dimension k+1
@@ -405,7 +410,7 @@ __global__ void __launch_bounds__(nthr_of(TW), 1) transition_kernel(const TransA
     const int mw = warp - TAIL_WARPS;          // index among the MMA warps
     const int mtid = 32 * mw + lane;
     const int tw = mw & (TAIL_WARPS - 1), prod = mw / TAIL_WARPS;  // tail warp served (same SM sub-partition); first / second producer of its buffer
-    double *ft = ft_all + mw * L::FTILE;
+    double *ft_base = ft_all + mw * GD * L::FTILE;
     double *pbw = pb_all + tw * L::PB;
     const int ks0 = EXACT ? RT : (r0 + 7) >> 3, rt_act = EXACT ? RT : (r1 + 7) >> 3, nt_act = EXACT ? NT : (n1 + 7) >> 3;
     const uint32_t row_bytes = (uint32_t)(8 * ks0) * 8u;   // bytes of a left-interface row that the update reads
@@ -430,11 +435,14 @@ __global__ void __launch_bounds__(nthr_of(TW), 1) transition_kernel(const TransA
       return nv > 0 ? a.perm[row0 + (r < nv ? r : 0)] : 0;
     };
 
-    int nvC = 0, nvN = 0;      // valid rows: current tile / next tile
-    int idC = 0, idN = 0;      // row ids (lane-distributed): current tile / next tile
-    // Gather of the rows whose ids are `ids` into this warp's shared tile: one cp.async (LDGSTS) instruction per row,
-    // 16 bytes per lane, so a row is one coalesced 8*r0-byte segment.
-    auto issue_gather = [&](int ids, int nv) {
+    // Row pipeline of this warp.  Stage 0 is the current tile, stage j the tile j ahead; ids are known GD + 1 tiles ahead,
+    // rows and per-row scalars are requested GD tiles ahead.
+    int nvC = 0, idC = 0;            // current tile: valid rows, row ids (lane-distributed)
+    int nvQ[GD + 1], idQ[GD + 1];    // [j]: tile j ahead, j = 1 .. GD
+    // Gather of the rows whose ids are `ids` into a staged tile of this warp: one cp.async (LDGSTS) instruction per row,
+    // 16 bytes per lane, so a row is one coalesced 8*r0-byte segment.  Always commits (an empty group when there are no
+    // rows), so that "all but the latest GD - 1 groups" below always means "the current tile's rows".
+    auto issue_gather = [&](int ids, int nv, double *ft) {
       if (nv > 0) {
 #pragma unroll
         for (int r = 0; r < WROWS; r++) {
@@ -442,36 +450,45 @@ __global__ void __launch_bounds__(nthr_of(TW), 1) transition_kernel(const TransA
           if (16u * lane < row_bytes)
             cp_async16(reinterpret_cast<char *>(ft + r * FP) + 16 * lane, reinterpret_cast<const char *>(a.F + (size_t)id * a.ldf) + 16 * lane);
         }
-        cp_async_commit();
       }
+      cp_async_commit();
     };
-    // per-row scalars, m-tile i = rows 8i+g: current tile and next tile (in flight)
-    int mrow[MT], mrow_n[MT];
-    double w1[MT], w2[MT], w1n[MT], w2n[MT];
+    // per-row scalars, m-tile i = rows 8i+g: [0] current tile, [j] the tile j ahead (in flight)
+    int mrow[GD + 1][MT];
+    double w1s[GD + 1][MT], w2s[GD + 1][MT];
 #pragma unroll
-    for (int i = 0; i < MT; i++) { mrow[i] = mrow_n[i] = 0; w1[i] = w2[i] = w1n[i] = w2n[i] = 0.0; }
-    auto load_scalars_next = [&]() {
+    for (int j = 0; j <= GD; j++)
 #pragma unroll
-      for (int i = 0; i < MT; i++) mrow_n[i] = __shfl_sync(FULL, idN, 8 * i + g);
-      if (nvN > 0) {
+      for (int i = 0; i < MT; i++) { mrow[j][i] = 0; w1s[j][i] = w2s[j][i] = 0.0; }
+    auto load_scalars = [&](int j, int ids, int nv) {
 #pragma unroll
-        for (int i = 0; i < MT; i++) { w1n[i] = a.w1[mrow_n[i]]; w2n[i] = a.w2[mrow_n[i]]; }
+      for (int i = 0; i < MT; i++) mrow[j][i] = __shfl_sync(FULL, ids, 8 * i + g);
+      if (nv > 0) {
+#pragma unroll
+        for (int i = 0; i < MT; i++) { w1s[j][i] = a.w1[mrow[j][i]]; w2s[j][i] = a.w2[mrow[j][i]]; }
       }
     };
     {
       const int rowC = rows_of(t_begin, nvC);
       idC = load_ids(rowC, nvC);
-      issue_gather(idC, nvC);
-      idN = idC; nvN = nvC;
-      load_scalars_next();
 #pragma unroll
-      for (int i = 0; i < MT; i++) { mrow[i] = mrow_n[i]; w1[i] = w1n[i]; w2[i] = w2n[i]; }
-      const int rowN = rows_of(t_begin + 1, nvN);
-      idN = load_ids(rowN, nvN);
+      for (int j = 1; j <= GD; j++) {
+        const int rowj = rows_of(t_begin + j, nvQ[j]);
+        idQ[j] = load_ids(rowj, nvQ[j]);
+      }
+      issue_gather(idC, nvC, ft_base);
+      load_scalars(0, idC, nvC);
+      if (GD == 2) {
+        issue_gather(idQ[1], nvQ[1], ft_base + L::FTILE);
+        load_scalars(1, idQ[1], nvQ[1]);
+      }
     }
+    double (&w1)[MT] = w1s[0];
+    double (&w2)[MT] = w2s[0];
 
     PT_DECL
     for (int tile = t_begin; tile < t_end; ++tile) {
+      double *ft = ft_base + (GD == 2 ? ((tile - t_begin) & 1) * L::FTILE : 0);   // this tile's staged rows
       PT_MARK(7)
       while (tile >= bts[b + 1]) ++b;
       if (cur0 == b && cur1 == b + 1) {
@@ -509,7 +526,7 @@ __global__ void __launch_bounds__(nthr_of(TW), 1) transition_kernel(const TransA
 
       if (nvalid > 0) {
         // ---- (1) interface update: A fragments from the staged rows ------------------------------------
-        cp_async_wait_all();
+        if (GD == 1) cp_async_wait_all(); else asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncwarp();
         PT_MARK(1)
         double acc[MT][RT][2];
@@ -597,12 +614,12 @@ __global__ void __launch_bounds__(nthr_of(TW), 1) transition_kernel(const TransA
         PT_MARK(2)
         // ---- the staged tile is consumed: launch the next tile's gather and scalar loads now ---------
         __syncwarp();
-        issue_gather(idN, nvN);
-        load_scalars_next();
+        issue_gather(idQ[GD], nvQ[GD], ft);
+        load_scalars(GD, idQ[GD], nvQ[GD]);
         // F' rows go out one 64-byte segment per pdf k-pair (below), so the stores trickle out under the DMMA stream
         double *Fo[MT];
 #pragma unroll
-        for (int i = 0; i < MT; i++) Fo[i] = a.F + (size_t)mrow[i] * a.ldf + 2 * t;
+        for (int i = 0; i < MT; i++) Fo[i] = a.F + (size_t)mrow[0][i] * a.ldf + 2 * t;
         const bool do_store = !a.last;
         PT_MARK(3)
         // ---- (2) conditional pdf on the grid of dimension k+1 ----------------------------------------
@@ -675,14 +692,14 @@ __global__ void __launch_bounds__(nthr_of(TW), 1) transition_kernel(const TransA
         }
       } else {
         // this warp has no rows in this tile: keep the pipeline moving
-        issue_gather(idN, nvN);
-        load_scalars_next();
+        issue_gather(idQ[GD], nvQ[GD], ft);
+        load_scalars(GD, idQ[GD], nvQ[GD]);
       }
       PT_MARK(4)
-      // ids of the tile after next
-      int nvNN = 0;
-      const int rowNN = rows_of(tile + 2, nvNN);
-      const int idNN = load_ids(rowNN, nvNN);
+      // ids of the tile GD + 1 ahead
+      int nvNew = 0;
+      const int rowNew = rows_of(tile + GD + 1, nvNew);
+      const int idNew = load_ids(rowNew, nvNew);
 
       // ---- (3) park the signed pdf tile for the tail warp (it takes |.|, reference :105); the two producers of a buffer alternate ----
       {
@@ -713,10 +730,14 @@ __global__ void __launch_bounds__(nthr_of(TW), 1) transition_kernel(const TransA
 
       PT_MARK(6)
       // ---- rotate the row pipeline --------------------------------------------------------------------
-      nvC = nvN; idC = idN;
+      nvC = nvQ[1]; idC = idQ[1];
 #pragma unroll
-      for (int i = 0; i < MT; i++) { mrow[i] = mrow_n[i]; w1[i] = w1n[i]; w2[i] = w2n[i]; }
-      nvN = nvNN; idN = idNN;
+      for (int j = 1; j < GD; j++) { nvQ[j] = nvQ[j + 1]; idQ[j] = idQ[j + 1]; }
+      nvQ[GD] = nvNew; idQ[GD] = idNew;
+#pragma unroll
+      for (int j = 0; j < GD; j++)
+#pragma unroll
+        for (int i = 0; i < MT; i++) { mrow[j][i] = mrow[j + 1][i]; w1s[j][i] = w1s[j + 1][i]; w2s[j][i] = w2s[j + 1][i]; }
     }
     PT_FLUSH
   }
@@ -728,37 +749,41 @@ __global__ void __launch_bounds__(nthr_of(TW), 1) transition_kernel(const TransA
   }
 }
 
-template <int RT, int NT, bool EXACT, bool TAIL1, int TW>
+template <int RT, int NT, bool EXACT, bool TAIL1, int TW, int GD>
 cudaError_t launch_variant(const TransArgs &a, int sm_count, cudaStream_t st) {
-  using L = SmemLayout<RT, NT, TAIL1, TW>;
+  using L = SmemLayout<RT, NT, TAIL1, TW, GD>;
   int64_t max_tiles = ((int64_t)a.rows + ROWS_CTA - 1) / ROWS_CTA + (a.n0 - 1);
   int64_t grid = sm_count;   // persistent: one CTA per SM (the register file allows no more)
   if (grid > max_tiles) grid = max_tiles;
   if (grid < 1) grid = 1;
-  transition_kernel<RT, NT, EXACT, TAIL1, TW><<<(unsigned)grid, nthr_of(TW), L::bytes, st>>>(a);
+  transition_kernel<RT, NT, EXACT, TAIL1, TW, GD><<<(unsigned)grid, nthr_of(TW), L::bytes, st>>>(a);
   return cudaGetLastError();
 }
 
-template <int RT, int NT, int TW>
+template <int RT, int NT, int TW, int GD>
 cudaError_t launch_one(const TransArgs &a, int sm_count, cudaStream_t st) {
   const bool exact = a.r0 == 8 * RT && a.r1 == 8 * RT && (a.n1 + 7) / 8 == NT;
-  if (exact && a.n1 == 8 * (NT - 1) + 1) return launch_variant<RT, NT, true, true, TW>(a, sm_count, st);
-  if (exact) return launch_variant<RT, NT, true, false, TW>(a, sm_count, st);
-  return launch_variant<RT, NT, false, false, TW>(a, sm_count, st);
+  if (exact && a.n1 == 8 * (NT - 1) + 1) return launch_variant<RT, NT, true, true, TW, GD>(a, sm_count, st);
+  if (exact) return launch_variant<RT, NT, true, false, TW, GD>(a, sm_count, st);
+  return launch_variant<RT, NT, false, false, TW, GD>(a, sm_count, st);
 }
 
-template <int RT, int NT, int TW>
+template <int RT, int NT, int TW, int GD>
 cudaError_t init_one() {
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(transition_kernel<RT, NT, true, true, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout<RT, NT, true, TW>::bytes)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(transition_kernel<RT, NT, true, false, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout<RT, NT, false, TW>::bytes)) != cudaSuccess) return e;
-  return cudaFuncSetAttribute(transition_kernel<RT, NT, false, false, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout<RT, NT, false, TW>::bytes);
+  if ((e = cudaFuncSetAttribute(transition_kernel<RT, NT, true, true, TW, GD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout<RT, NT, true, TW, GD>::bytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(transition_kernel<RT, NT, true, false, TW, GD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout<RT, NT, false, TW, GD>::bytes)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(transition_kernel<RT, NT, false, false, TW, GD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout<RT, NT, false, TW, GD>::bytes);
 }
 
 #ifndef TTIRT_LIGHT_TW
 #define TTIRT_LIGHT_TW 8    // tail warps of the two lighter classes
 #endif
 constexpr int kLightTW = TTIRT_LIGHT_TW;
+#ifndef TTIRT_LIGHT_GD
+#define TTIRT_LIGHT_GD 2    // gather depth of the two lighter classes
+#endif
+constexpr int kLightGD = TTIRT_LIGHT_GD;
 
 }  // namespace
 
@@ -773,17 +798,17 @@ int fast_rows_per_cta(int) { return ROWS_CTA; }
 
 cudaError_t fast_init(int) {
   cudaError_t e;
-  if ((e = init_one<2, 3, kLightTW>()) != cudaSuccess) return e;
-  if ((e = init_one<4, 5, kLightTW>()) != cudaSuccess) return e;
-  if ((e = init_one<8, 9, 4>()) != cudaSuccess) return e;
+  if ((e = init_one<2, 3, kLightTW, kLightGD>()) != cudaSuccess) return e;
+  if ((e = init_one<4, 5, kLightTW, kLightGD>()) != cudaSuccess) return e;
+  if ((e = init_one<8, 9, 4, 1>()) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
 cudaError_t launch_transition(int cls, const TransArgs &a, int sm_count, cudaStream_t st) {
   switch (cls) {
-    case 0: return launch_one<2, 3, kLightTW>(a, sm_count, st);
-    case 1: return launch_one<4, 5, kLightTW>(a, sm_count, st);
-    case 2: return launch_one<8, 9, 4>(a, sm_count, st);
+    case 0: return launch_one<2, 3, kLightTW, kLightGD>(a, sm_count, st);
+    case 1: return launch_one<4, 5, kLightTW, kLightGD>(a, sm_count, st);
+    case 2: return launch_one<8, 9, 4, 1>(a, sm_count, st);
     default: return cudaErrorInvalidValue;
   }
 }
