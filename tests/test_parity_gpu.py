@@ -337,9 +337,9 @@ def test_failed_workspace_allocation_is_recoverable(oracle_mod):
 
 
 def _check_sharded_call(oracle_mod, ndev):
-    """One ttirt_run_host call sharded over ndev devices: parity against the oracle on every row (so every shard and
-    every shard boundary), bit-identical to the one-device call, seeded variant independent of the device count."""
-    d, n, r, M = 6, 17, 8, 30011                                     # odd M: uneven shards
+    """One ttirt_run_host call spread over ndev devices: parity against the oracle on every row (so every chunk and every
+    boundary between devices), bit-identical to the one-device call, seeded variant independent of the device count."""
+    d, n, r, M = 6, 17, 8, 300011                                    # odd M, several chunks per device
     ns, xs, rk, c = synth.make_tt(d, n, r, seed=6)
     q = synth.make_q(M, d, seed=7)
     Zo, lo, io, kap, gap, cond, lsens = _oracle(oracle_mod, ns, xs, rk, c, q)
@@ -391,7 +391,7 @@ import numpy as np
 import oracle
 import test_parity_gpu as T
 from tt_irt_py import tt_irt, synth
-assert tt_irt.device_count() == 3, tt_irt.device_count()
+assert tt_irt.device_count() == 3, tt_irt.device_count()   # one physical GPU visible (CUDA_VISIBLE_DEVICES=0), three logical
 print("three logical devices", flush=True)
 T._check_sharded_call(oracle, 3)
 print("sharded call ok", flush=True)
@@ -407,15 +407,17 @@ print("virtual devices ok")
 """
 
 
-def test_virtual_devices_exercise_the_sharded_path_on_one_gpu(tmp_path):
-    """TTIRT_VIRTUAL_DEVICES=3 (test hook of the library): three logical devices -- own engine slot, host thread, row shard,
-    fan-out of the cores -- on however many physical GPUs there are.  Runs the same checks as the real multi-GPU test, in
-    a child process because the hook is read once per process."""
+@pytest.mark.parametrize("balance", ["queue", "static"])
+def test_virtual_devices_exercise_the_sharded_path_on_one_gpu(tmp_path, balance):
+    """TTIRT_VIRTUAL_DEVICES=3 (test hook of the library): three logical devices -- own engine slot, host thread, pipeline,
+    fan-out of the cores -- on one physical GPU.  Runs the same checks as the real multi-GPU test (every row against the
+    oracle, bit-identical to the one-device call) for both ways of dealing out the rows: chunk by chunk from the shared queue
+    (default) and as contiguous equal shards (TTIRT_BALANCE=static).  In a child process because the hooks are read once."""
     import subprocess
     import sys
     script = tmp_path / "virtual_devices.py"
     script.write_text(_VIRTUAL_SCRIPT)
-    env = dict(os.environ, TTIRT_VIRTUAL_DEVICES="3")
+    env = dict(os.environ, TTIRT_VIRTUAL_DEVICES="3", CUDA_VISIBLE_DEVICES="0", TTIRT_BALANCE=balance)
     env.pop("TTIRT_DEVICES", None)
     out = subprocess.run([sys.executable, "-u", "-X", "faulthandler", str(script), ROOT], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "virtual devices ok" in out.stdout, (out.stdout[-2000:], out.stderr[-4000:])

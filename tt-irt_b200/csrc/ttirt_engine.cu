@@ -974,6 +974,22 @@ static bool pin_if_pageable(const void *p, size_t bytes) {
 }
 static void unpin(const void *p, bool pinned) { if (pinned) { cudaHostUnregister(const_cast<void *>(p)); } }
 
+// Work queue of one call: chunks of `chunk` rows of [base, end), handed out in order to whoever asks next.  A one-device call
+// walks a private queue; a multi-device call shares one between its device threads, so that a device that moves its data
+// faster takes more chunks (on the 8-GPU boxes of this pool four of the GPUs reach host memory ~25 % slower than the
+// other four).  Chunk boundaries are fixed by the queue, never by who takes a chunk: results do not depend on the assignment.
+struct ChunkQueue {
+  std::atomic<int64_t> next{0};
+  int64_t base = 0, end = 0, chunk = 1;
+  bool claim(int64_t &m0, int64_t &rows) {
+    const int64_t i = next.fetch_add(1, std::memory_order_relaxed);
+    m0 = base + i * chunk;
+    if (m0 >= end) return false;
+    rows = std::min(chunk, end - m0);
+    return true;
+  }
+};
+
 // Where a chunk's seeds come from: the caller's q (host memory), or generated on the device (csrc/ttirt_aux.cu), which
 // removes the q upload altogether.
 struct SeedSpec {
@@ -1037,23 +1053,33 @@ static int stage_ensure(ttirt_model *md, int slot, int64_t rows, bool need_q, bo
 // into the slot's pinned buffer first when the caller's q is pageable, or generated on the device) -> kernels -> D2H
 // (straight into pinned caller memory, or into the slot's pinned buffer from which a drain thread copies into the
 // caller's pageable arrays while the next chunks compute).
+// chunk size of the host pipeline for a model of fast-path class `cls` and `rows` rows per device
+static int64_t host_chunk_for(int cls, bool strict, bool walk, int64_t rows) {
+  int64_t chunk = default_chunk();
+  // light shapes (r <= 16: 2^17 rows, r <= 32: 2^19 rows per chunk): a chunk computes in about a millisecond, so the pipeline is cut finer
+  // (shorter fill and drain, copies and kernels of neighbouring chunks overlap) and every chunk is a graph replay
+  if (g_chunk.load() <= 0 && getenv("TTIRT_CHUNK") == nullptr && !strict && cls >= 0 && cls <= 1)
+    chunk = cls == 0 ? (1 << 17) : (1 << 19);
+  // a walk-kernel chunk is one launch: cut small calls finer, so that upload, kernel and download of neighbouring chunks overlap
+  if (rows < chunk * kSlots) chunk = std::max<int64_t>((rows + kSlots - 1) / kSlots, std::min<int64_t>(rows, walk ? (1 << 12) : (1 << 16)));
+  return chunk;
+}
+
 static int sample_host_rows(ttirt_model *md, int64_t m_begin, int64_t m_end, const double *h_q, double *h_z, double *h_lpz,
-                            int32_t *h_idx, int64_t ld, int mode, const SeedSpec &seeds = SeedSpec()) {
+                            int32_t *h_idx, int64_t ld, int mode, const SeedSpec &seeds = SeedSpec(), ChunkQueue *shared = nullptr) {
   const int64_t M = m_end - m_begin;
   if (M <= 0) return 0;
   const double ts0 = now_s();
   CK(cudaSetDevice(md->device));
   const int d = (int)md->d;
   const bool strict = (mode == TTIRT_MODE_STRICT) || md->fast_cls < 0;
-  int64_t chunk = default_chunk();
-  // light shapes (r <= 16: 2^17 rows, r <= 32: 2^19 rows per chunk): a chunk computes in about a millisecond, so the pipeline is cut finer
-  // (shorter fill and drain, copies and kernels of neighbouring chunks overlap) and every chunk is a graph replay
-  if (g_chunk.load() <= 0 && getenv("TTIRT_CHUNK") == nullptr && !strict && md->fast_cls >= 0 && md->fast_cls <= 1)
-    chunk = md->fast_cls == 0 ? (1 << 17) : (1 << 19);
-  // a walk-kernel chunk is one launch: cut small calls finer, so that upload, kernel and download of neighbouring chunks overlap
   const bool walk = !strict && md->walk_cls >= 0;
-  if (M < chunk * kSlots) chunk = std::max<int64_t>((M + kSlots - 1) / kSlots, std::min<int64_t>(M, walk ? (1 << 12) : (1 << 16)));
-  const int64_t nchunks = (M + chunk - 1) / chunk;
+  // the chunks of this call: a private queue over [m_begin, m_end), or the queue shared by the devices of the call
+  ChunkQueue own;
+  own.base = m_begin; own.end = m_end; own.chunk = host_chunk_for(md->fast_cls, strict, walk, M);
+  ChunkQueue &queue = shared ? *shared : own;
+  const int64_t chunk = queue.chunk;
+  const int64_t nchunks = shared ? (int64_t)kSlots : (M + chunk - 1) / chunk;   // (shared: unknown in advance)
   const int nslots = (int)std::min<int64_t>(kSlots, nchunks);
   static const bool no_stage = getenv("TTIRT_NO_STAGING") != nullptr;
   const bool big = M * d >= (1 << 20);   // tiny calls: the driver's own staging is as good
@@ -1069,20 +1095,22 @@ static int sample_host_rows(ttirt_model *md, int64_t m_begin, int64_t m_end, con
   std::mutex mu;
   std::condition_variable cv;
   int64_t submitted = 0, drained = 0;
-  bool abort_drain = false;
+  std::vector<std::pair<int64_t, int64_t>> claimed;   // (first row, rows) of this device's chunks, in submission order
+  bool abort_drain = false, all_submitted = false;
   int drain_rc = 0;
   std::thread drain;
   if (stage_z) {
     drain = std::thread([&]() {
-      if (cudaSetDevice(md->device) != cudaSuccess) { std::lock_guard<std::mutex> l(mu); drain_rc = -1; drained = nchunks; cv.notify_all(); return; }
-      for (int64_t c = 0; c < nchunks; c++) {
+      if (cudaSetDevice(md->device) != cudaSuccess) { std::lock_guard<std::mutex> l(mu); drain_rc = -1; drained = INT64_MAX / 2; cv.notify_all(); return; }
+      for (int64_t c = 0;; c++) {
+        int64_t m0, rows;
         {
           std::unique_lock<std::mutex> l(mu);
-          cv.wait(l, [&] { return submitted > c || abort_drain; });
-          if (abort_drain) break;
+          cv.wait(l, [&] { return submitted > c || all_submitted || abort_drain; });
+          if (abort_drain || submitted <= c) break;
+          m0 = claimed[(size_t)c].first; rows = claimed[(size_t)c].second;
         }
         const int s = (int)(c % kSlots);
-        const int64_t m0 = m_begin + c * chunk, rows = std::min(chunk, m_end - m0);
         if (cudaEventSynchronize(md->ws[s].done) != cudaSuccess) { std::lock_guard<std::mutex> l(mu); drain_rc = -1; }
         copy_columns(h_z + m0, ld, md->stage[s].z, rows, rows, d);
         memcpy(h_lpz + m0, md->stage[s].lpz, sizeof(double) * (size_t)rows);
@@ -1093,7 +1121,7 @@ static int sample_host_rows(ttirt_model *md, int64_t m_begin, int64_t m_end, con
   }
   auto finish = [&](int rc) -> int {
     if (drain.joinable()) {
-      { std::lock_guard<std::mutex> l(mu); if (rc != 0) abort_drain = true; }
+      { std::lock_guard<std::mutex> l(mu); if (rc != 0) abort_drain = true; all_submitted = true; }
       cv.notify_all();
       drain.join();
     }
@@ -1105,11 +1133,12 @@ static int sample_host_rows(ttirt_model *md, int64_t m_begin, int64_t m_end, con
     if (e_ != cudaSuccess) { fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); return finish(-1); } \
   } while (0)
 
-  for (int64_t c = 0; c < nchunks; c++) {
+  int64_t taken = 0;
+  for (int64_t c = 0;; c++) {
     const int s = (int)(c % kSlots);
     Workspace &w = md->ws[s];
-    const int64_t m0 = m_begin + c * chunk, rows = std::min(chunk, m_end - m0);
     if (c < kSlots) CKF(cudaStreamWaitEvent(w.stream, md->loaded, 0));   // upload + sweep of this call's model (model_load)
+    // first a free slot, then a chunk: a device that is waiting for its own pipeline does not sit on work another could do
     if (c >= kSlots) {
       if (stage_z) {   // the slot's pinned output buffer must have been drained
         std::unique_lock<std::mutex> l(mu);
@@ -1118,6 +1147,9 @@ static int sample_host_rows(ttirt_model *md, int64_t m_begin, int64_t m_end, con
         CKF(cudaEventSynchronize(w.done));
       }
     }
+    int64_t m0 = 0, rows = 0;
+    if (!queue.claim(m0, rows)) break;
+    taken++;
     if (seeds.kind == 1) {
       if (ttirt_seeds_lattice_device(d, rows, seeds.m_base + (m0 - m_begin), seeds.N, seeds.d_genvec, seeds.d_shift, w.q, rows, w.stream) != 0) return finish(-1);
     } else if (seeds.kind == 2) {
@@ -1147,7 +1179,7 @@ static int sample_host_rows(ttirt_model *md, int64_t m_begin, int64_t m_end, con
                             cudaMemcpyDeviceToHost, w.stream));
     CKF(cudaEventRecord(w.done, w.stream));
     if (stage_z) {
-      { std::lock_guard<std::mutex> l(mu); submitted = c + 1; }
+      { std::lock_guard<std::mutex> l(mu); claimed.emplace_back(m0, rows); submitted = c + 1; }
       cv.notify_all();
     }
   }
@@ -1156,7 +1188,7 @@ static int sample_host_rows(ttirt_model *md, int64_t m_begin, int64_t m_end, con
 #undef CKF
   if (trace_on())
     fprintf(stderr, "tt_irt1[b200] trace: pipeline device %d: %lld chunks of %lld rows, setup %.3f ms, enqueue %.3f ms, wait %.3f ms (staged q %d, z %d)\n",
-            md->device, (long long)nchunks, (long long)chunk, 1e3 * (ts1 - ts0), 1e3 * (te - ts1), 1e3 * (now_s() - te), (int)stage_q, (int)stage_z);
+            md->device, (long long)taken, (long long)chunk, 1e3 * (ts1 - ts0), 1e3 * (te - ts1), 1e3 * (now_s() - te), (int)stage_q, (int)stage_z);
   return finish(0);
 }
 
@@ -1239,7 +1271,7 @@ bool same_shape(const ttirt_model *md, int64_t d, const int64_t *n, const int64_
 // rows [m0, m1) of one call on one device, through that device's cached engine
 int run_on_device(int device, int64_t d, const int64_t *n, const int64_t *rk, const CoreSource &src,
                   int64_t m0, int64_t m1, const double *h_q, double *h_z, double *h_lpz, int32_t *h_idx, int64_t ld, int mode,
-                  const SeedSpec &seeds) {
+                  const SeedSpec &seeds, ChunkQueue *queue = nullptr) {
   // whatever happens below, a root must publish (so that peers never wait for ever) and a peer must report (so that the
   // root never does); both are idempotent
   struct FanGuard {
@@ -1270,7 +1302,7 @@ int run_on_device(int device, int64_t d, const int64_t *n, const int64_t *rk, co
     if (!sl.md) return -1;
   }
   const double t1 = now_s();
-  const int rc = sample_host_rows(sl.md, m0, m1, h_q, h_z, h_lpz, h_idx, ld, mode, seeds);
+  const int rc = sample_host_rows(sl.md, m0, m1, h_q, h_z, h_lpz, h_idx, ld, mode, seeds, queue);
   const double t2 = now_s();
   if (src.fan && src.root) src.fan->wait_peers();   // peers copy from this model's buffers
   if (!cache_enabled() || rc != 0) { ttirt_model_destroy(sl.md); sl.md = nullptr; }
@@ -1312,25 +1344,37 @@ static int run_host_impl(int64_t d, const int64_t *n, const double *xs, const in
   CoreSource src;
   src.xs = xs; src.core = ttcore;
   if (n_devices == 1) return run_on_device(first_device, d, n, ttrank, src, 0, M, h_q, h_z, h_lpz, h_idx, M, mode, seeds);
-  // samples are independent: contiguous row shards, one host thread per device, no collective.  Grid and cores reach the
-  // first device from the host and the others from there (Fanout); the tiny sweep is redone on every device.
+  // Samples are independent (reference tt_irt1_int32.c:88-181): one host thread and one pipeline per device, no collective.
+  // The rows go to the devices chunk by chunk from a shared queue (default), or as contiguous equal shards
+  // (TTIRT_BALANCE=static: ttirt_shard_rows).  Grid and cores reach the first device from the host and the others from
+  // there (Fanout); the tiny sweep is redone on every device.
+  static const bool balance = !(getenv("TTIRT_BALANCE") && strcmp(getenv("TTIRT_BALANCE"), "static") == 0);
   Fanout fan;
   fan.pending = n_devices - 1;
-  int64_t core_elems = 0;
-  for (int64_t k = 0; k < d; k++) core_elems += ttrank[k] * n[k] * ttrank[k + 1];
+  int64_t core_elems = 0, rmax = 1, nmax = 2;
+  for (int64_t k = 0; k < d; k++) {
+    core_elems += ttrank[k] * n[k] * ttrank[k + 1];
+    rmax = std::max(rmax, ttrank[k + 1]); nmax = std::max(nmax, n[k]);
+  }
   const bool use_fan = fanout_enabled() && n_devices <= 64 && core_elems >= (1 << 16);   // small cores: eight host uploads are as quick
+  ChunkQueue queue;
+  queue.base = 0; queue.end = M;
+  {
+    const int cls = fast_class_for((int)rmax, (int)nmax);
+    queue.chunk = host_chunk_for(cls, mode == TTIRT_MODE_STRICT || cls < 0, false, M / n_devices);
+  }
   std::vector<int> rcs(n_devices, 0);
   std::vector<std::string> errs(n_devices);
   std::vector<std::thread> th;
   for (int g = 0; g < n_devices; g++) {
     th.emplace_back([&, g]() {
-      int64_t m0 = 0, m1 = 0;
-      ttirt_shard_rows(M, n_devices, g, &m0, &m1);
+      int64_t m0 = 0, m1 = M;
+      if (!balance) ttirt_shard_rows(M, n_devices, g, &m0, &m1);
       CoreSource s = src;
       if (use_fan) { s.fan = &fan; s.root = g == 0; s.peer = g; }
       SeedSpec sp = seeds;
       sp.m_base = seeds.m_base + m0;
-      rcs[g] = run_on_device(first_device + g, d, n, ttrank, s, m0, m1, h_q, h_z, h_lpz, h_idx, M, mode, sp);
+      rcs[g] = run_on_device(first_device + g, d, n, ttrank, s, m0, m1, h_q, h_z, h_lpz, h_idx, M, mode, sp, balance ? &queue : nullptr);
       if (rcs[g] != 0) errs[g] = g_err;
     });
   }
