@@ -550,7 +550,7 @@ def host_copy_ceiling(torch, qh, zh, d, Ms, ndev):
         with torch.cuda.device(g):
             bufs.append((torch.empty((d, chunk), dtype=torch.float64, device="cuda:%d" % g),
                          torch.empty((d, chunk), dtype=torch.float64, device="cuda:%d" % g),
-                         torch.cuda.Stream(device=g), torch.cuda.Stream(device=g)))
+                         [torch.cuda.Stream(device=g) for _ in range(2)], [torch.cuda.Stream(device=g) for _ in range(2)]))
 
     import itertools
     import threading
@@ -569,8 +569,13 @@ def host_copy_ceiling(torch, qh, zh, d, Ms, ndev):
 
         def worker(g):
             rt.cudaSetDevice(g)
-            di, do, s1, s2 = bufs[g]
+            di, do, sa, sb = bufs[g]
+            k = 0
             while True:
+                # two chunks in flight per direction and device; a new chunk is claimed when the one before last is done
+                s1, s2 = sa[k & 1], sb[k & 1]
+                rt.cudaStreamSynchronize(s1.cuda_stream)
+                rt.cudaStreamSynchronize(s2.cuda_stream)
                 with lock:
                     i = next(counter)
                 if i >= nchunks:
@@ -581,9 +586,9 @@ def host_copy_ceiling(torch, qh, zh, d, Ms, ndev):
                     err.append("H2D")
                 if d2h and cp2d(zh.data_ptr() + 8 * m0, 8 * Ms, do.data_ptr(), 8 * chunk, 8 * w, d, D2H, s2.cuda_stream) != 0:
                     err.append("D2H")
-                # one chunk in flight per direction and device: the next claim waits for this one (copies within a stream serialise anyway)
-                rt.cudaStreamSynchronize(s1.cuda_stream)
-                rt.cudaStreamSynchronize(s2.cuda_stream)
+                k += 1
+            for st in sa + sb:
+                rt.cudaStreamSynchronize(st.cuda_stream)
         t0 = time.perf_counter()
         th = [threading.Thread(target=worker, args=(g,)) for g in range(ndev)]
         for t in th:

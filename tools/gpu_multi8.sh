@@ -4,7 +4,7 @@ set -u
 TAG=${1:-r02m8}; OUT=gpurun_out; mkdir -p $OUT
 { nvidia-smi -L; nproc; free -g; nvidia-smi topo -m; } > $OUT/${TAG}_env.log 2>&1
 TTIRT_EXPECT_GPUS=8 timeout 600 python -m pytest tests/test_parity_gpu.py tests/test_sqr_gpu.py -m gpu -x -q -k "multi_device or virtual_devices or sharding" -rs > $OUT/${TAG}_pytest_multi.log 2>&1; echo "pytest multi rc=$?"; tail -4 $OUT/${TAG}_pytest_multi.log
-for N in 8 4; do
+for N in 8; do
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N bench.py --gpus $N --steps 3 --warmup 3 > $OUT/${TAG}_bench_n$N.json 2> $OUT/${TAG}_bench_n$N.err; echo "bench N=$N rc=$?"
 python - <<P
 import json
@@ -14,4 +14,4 @@ P
 done
 PROBE_DEVICES=8 TTIRT_TRACE=1 timeout 300 python tools/multi_device_probe.py 26 > $OUT/${TAG}_probe_chunk20.json 2> $OUT/${TAG}_probe_chunk20.err; cat $OUT/${TAG}_probe_chunk20.json; tail -12 $OUT/${TAG}_probe_chunk20.err
 PROBE_DEVICES=8 TTIRT_CHUNK=524288 timeout 300 python tools/multi_device_probe.py 26 > $OUT/${TAG}_probe_chunk19.json 2>/dev/null; cat $OUT/${TAG}_probe_chunk19.json
-PROBE_DEVICES=8 TTIRT_FANOUT=0 timeout 300 python tools/multi_device_probe.py 26 > $OUT/${TAG}_probe_nofan.json 2>/dev/null; cat $OUT/${TAG}_probe_nofan.json
+PROBE_DEVICES=8 TTIRT_BALANCE=static timeout 300 python tools/multi_device_probe.py 26 > $OUT/${TAG}_probe_static.json 2>/dev/null; cat $OUT/${TAG}_probe_static.json
