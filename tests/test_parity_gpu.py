@@ -95,6 +95,36 @@ def test_ragged_modes_and_ranks(oracle_mod):
         md.close()
 
 
+@pytest.mark.parametrize("ranks", [(1, 8, 11, 13, 9, 5, 1), (1, 3, 8, 2, 1), (1, 16, 4, 16, 16, 1), (1, 2, 1)])
+def test_walk_kernel_with_ragged_ranks_on_17_point_grids(oracle_mod, ranks):
+    """TT-cross ranks as the reference's shock-absorber driver produces them (start rank 8, tolerance 0.05: 8 ... 16,
+    different in every dimension) on its 17-point grids: served by the one-launch walk kernel with zero-padded ranks.
+    Strict bit-exact, fast within the protocol, one kernel launch per call."""
+    rk = np.array(ranks, dtype=np.int64)
+    d = rk.size - 1
+    ns = np.full(d, 17, dtype=np.int64)
+    rng = np.random.default_rng(int(rk.sum()))
+    xs = np.concatenate([np.sort(rng.uniform(-1.0, 2.0, size=17)) for _ in range(d)])
+    c = rng.random(int((rk[:-1] * ns * rk[1:]).sum()))
+    M = 5000
+    q = synth.make_q(M, d, seed=3)
+    q[0, :] = 0.0; q[1, :] = 1.0
+    Zo, lo, io, kap, gap, cond, lsens = _oracle(oracle_mod, ns, xs, rk, c, q)
+    md = tt_irt.Model(ns, xs, rk, c)
+    try:
+        Zs, ls, isx = md.sample(q, mode=tt_irt.MODE_STRICT, want_idx=True)
+        assert np.array_equal(Zs, Zo) and np.array_equal(isx, io)
+        l0 = tt_irt.kernel_launches()
+        Zf, lf, ifx = md.sample(q, mode=tt_irt.MODE_FAST, want_idx=True)
+        launches = tt_irt.kernel_launches() - l0
+        stats, fails = oracle_mod.parity.compare(Zf, lf, ifx, Zo, lo, io, cond, gap, lsens=lsens)
+        assert not fails, (fails, stats)
+        assert stats["idx_flips"] == 0
+        assert launches <= 4, "expected one walk-kernel launch per chunk (four chunks at most), saw %d launches" % launches
+    finally:
+        md.close()
+
+
 @pytest.mark.parametrize("name", GOLDEN)
 def test_against_golden_reference_outputs(oracle_mod, golden_dir, name):
     """Committed outputs of the unmodified reference (netlib-order BLAS build): strict mode reproduces Z bit

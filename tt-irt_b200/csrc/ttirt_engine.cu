@@ -705,10 +705,9 @@ static int model_build(ttirt_model *md, const int64_t *n, const int64_t *rk, con
   // small uniform-rank TTs: one persistent kernel for the whole walk (TTIRT_WALK=0: per-dimension path, for comparison)
   {
     static const bool walk_on = !(getenv("TTIRT_WALK") && atoi(getenv("TTIRT_WALK")) == 0);
-    bool uniform = d >= 2;
+    bool uniform = d >= 2;                                    // one grid size throughout; ranks may differ (zero-padded)
     for (int64_t k = 0; k < d && uniform; k++) uniform = n[k] == n[0];
-    for (int64_t k = 1; k < d && uniform; k++) uniform = rk[k] == rk[1];
-    md->walk_cls = (walk_on && uniform) ? walk_class_for((int)rk[1], (int)n[0]) : -1;
+    md->walk_cls = (walk_on && uniform) ? walk_class_for((int)md->rmax, (int)n[0]) : -1;
     if (md->walk_cls >= 0) {
       CK(walk_init(md->device));
       CK(cudaMalloc(&md->d_walk, sizeof(double) * walk_pack_doubles(md->walk_cls, (int)d)));

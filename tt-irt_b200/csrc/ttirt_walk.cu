@@ -18,7 +18,8 @@
 //     formulation as the transition kernel's tail (weighted running sums, unnormalised compare, power-of-two scaling,
 //     split-product log-density), one row per lane.
 // Dimension 0 (left rank 1) is the shared table of the stage-0 kernel, in the reference's operation order.
-// Shapes outside (r in {8, 16}, every n = 17, uniform inner ranks, d >= 2) use the per-dimension path.
+// Served: every n = 17, every inner rank <= 16 (interface width 8 or 16, smaller ranks zero-padded), d >= 2; everything else
+// uses the per-dimension path.
 #include "ttirt_common.cuh"
 
 namespace ttirt {
@@ -100,17 +101,20 @@ __global__ void walk_pack_kernel(const DimInfo *__restrict__ dims, int d, const 
   const DimInfo di = dims[k];
   double *blk = pack + (size_t)k * L::STAGE;
   const double *x = xs + di.off_x, *ck = core + di.off_c;
+  // ranks below R are padded with zeros: the padded interface entries stay exactly zero through every update and add
+  // exact zeros to every sum, so results do not depend on the padding
+  const int r0 = di.r0, r1 = di.r1;
   if (k == 0) {
     for (int i = threadIdx.x; i < N; i += blockDim.x) { blk[L::P0 + i] = p0[i]; blk[L::C0 + i] = cdf0[i]; blk[L::X0 + i] = x[i]; }
     for (int e = threadIdx.x; e < N * R; e += blockDim.x) {
       const int i = e / R, b = e - i * R;
-      blk[L::CORE0 + e] = ck[i + (int64_t)b * N];          // core_0[0, i, b], r_0 = 1
+      blk[L::CORE0 + e] = b < r1 ? ck[i + (int64_t)b * N] : 0.0;          // core_0[0, i, b], r_0 = 1
     }
     return;
   }
   for (int e = threadIdx.x; e < N * R; e += blockDim.x) {
     const int j = e / R, a = e - j * R;
-    blk[L::PW + e] = pk[di.off_p + a + j * R] * node_weight(x, j, N);
+    blk[L::PW + e] = a < r0 ? pk[di.off_p + a + j * r0] * node_weight(x, j, N) : 0.0;
   }
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
     const double w = node_weight(x, i, N);
@@ -124,7 +128,10 @@ __global__ void walk_pack_kernel(const DimInfo *__restrict__ dims, int d, const 
     for (int e = threadIdx.x; e < N * L::NS; e += blockDim.x) {
       const int i = e / L::NS, ab = e - i * L::NS;
       double v = 0.0;
-      if (ab < R * R) { const int a = ab / R, b = ab - a * R; v = ck[a + i * R + (int64_t)b * R * N]; }
+      if (ab < R * R) {
+        const int a = ab / R, b = ab - a * R;
+        if (a < r0 && b < r1) v = ck[a + i * r0 + (int64_t)b * r0 * N];
+      }
       blk[L::CORE + e] = v;
     }
   }
@@ -280,11 +287,12 @@ cudaError_t walk_launch_one(const WalkArgs &a, int sm_count, cudaStream_t st) {
 
 }  // namespace
 
-// 0 / 1: walk class for uniform inner rank r on n-point grids, -1: not served by the walk kernel
-int walk_class_for(int r, int n) {
+// 0 / 1: walk class (interface width 8 / 16) for a TT whose inner ranks are all <= rmax on n-point grids in every dimension;
+// -1: not served by the walk kernel.  Ranks below the class width are zero-padded by walk_pack.
+int walk_class_for(int rmax, int n) {
   if (n != 17) return -1;
-  if (r == 8) return 0;
-  if (r == 16) return 1;
+  if (rmax <= 8) return 0;
+  if (rmax <= 16) return 1;
   return -1;
 }
 
