@@ -6,11 +6,12 @@ mkdir -p $OUT
 timeout 1500 python -m pytest tests -m gpu -x -q -rs > $OUT/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -6 $OUT/${TAG}_pytest_gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 $OUT/${TAG}_smoke.log
 timeout 600 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"
-python - <<'P'
-import json
-j=json.load(open('gpurun_out/r02d_bench.json')); r=j['roofline']
+python - $TAG <<'P'
+import json,sys
+TAG=sys.argv[1]
+j=json.load(open('gpurun_out/'+TAG+'_bench.json')); r=j['roofline']
 print('value %.2f M/s' % (j['value']/1e6), 'kernel frac %.4f' % r['frac'], 'avg ms %.4f' % r['kernel_avg_ms'], 'whole %.4f' % r['whole_step_frac'], 'e2e %.2f' % (j['e2e']['value']/1e6), 'pageable %.2f' % (j['e2e']['pageable_numpy_value']/1e6))
-for k,v in (j.get('other_configs') or {}).items(): print('   ', k, {a:(round(b,4) if isinstance(b,float) else b) for a,b in v.items() if a in ('value','ms_per_step','launches_per_step','e2e_value','e2e_ms_per_call','frac_of_fp64_peak','e2e_matches_device_resident_bit_for_bit','unavailable')})
+for k,v in (j.get('other_configs') or {}).items(): print('   ', k, {a:(round(b,4) if isinstance(b,float) else b) for a,b in v.items() if a in ('value','ms_per_step','launches_per_step','e2e_value','e2e_ms_per_call','e2e_ms_per_call_same_tt_again','frac_of_fp64_peak','e2e_matches_device_resident_bit_for_bit','unavailable')})
 print(j['cpu_baseline'])
 P
 timeout 600 python bench.py --impl reference --steps 1 --warmup 1 > $OUT/${TAG}_bench_reference.json 2>> $OUT/${TAG}_bench.err; echo "ref rc=$?"
