@@ -412,7 +412,7 @@ def e2e_single(a, lib, torch, ns, xs, rk, cores, d, M, q_dev, local_rank):
         e2e_np()
     dtn = time.perf_counter() - t0
     e2e["pageable_numpy_value"] = M * a.steps / dtn
-    e2e["pageable_numpy_note"] = "same call on pageable numpy arrays (bounce-buffer pipeline, %s host copy threads)" % os.environ.get("TTIRT_COPY_THREADS", "4")
+    e2e["pageable_numpy_note"] = "same call on pageable numpy arrays (bounce-buffer pipeline, %s host copy threads)" % os.environ.get("TTIRT_COPY_THREADS", "default")
     if not np.array_equal(ln[:4096], lh[:4096].numpy()):
         raise SystemExit("bench.py: pageable and pinned e2e results differ")
     return e2e

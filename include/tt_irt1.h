@@ -51,7 +51,7 @@ extern "C" {
  * Returns nothing (as the reference).  On any failure (no device, bad shape, CUDA error) it prints
  * one line to stderr and fills z and lPz with NaN; it never aborts the host process.
  * Caller arrays in ordinary pageable memory (numpy, mxArray) go through page-locked bounce buffers filled and drained
- * by a few host threads (TTIRT_COPY_THREADS, default 4; TTIRT_NO_STAGING=1 leaves the staging to the driver).
+ * by a few host threads (TTIRT_COPY_THREADS, default min(8, cores / 2); TTIRT_NO_STAGING=1 leaves the staging to the driver).
  * Environment: TTIRT_MODE=fast|strict (default fast), TTIRT_DEVICES=<count>|all|auto (default auto: one device per
  * 2^22 seed points, at most all visible ones from TTIRT_DEVICE on -- a batch of M >= 2^22 * N is sharded over N GPUs,
  * a small one stays on one), TTIRT_DEVICE=<first ordinal> (default 0), TTIRT_CHUNK=<samples per chunk>, TTIRT_CACHE=0 (free all device

@@ -125,6 +125,49 @@ def test_walk_kernel_with_ragged_ranks_on_17_point_grids(oracle_mod, ranks):
         md.close()
 
 
+def test_walk_kernel_known_answers(oracle_mod):
+    """The walk kernel's own branches on 17-point grids: zero-mass conditional (index-space fallback, reference :116-125),
+    sign flip of a core (the fabs at :105), seeds exactly 0 and 1, a single row, and signed (cancelling) cores."""
+    # zero-mass conditional in dimension 1: second core all zero
+    ns = np.array([17, 17, 17]); rk = np.array([1, 2, 3, 1])
+    rng = np.random.default_rng(3)
+    xs = np.concatenate([np.sort(rng.uniform(0.0, 3.0, 17)) for _ in range(3)])
+    c = np.concatenate([rng.random(17 * 2), np.zeros(2 * 17 * 3), rng.random(3 * 17)])
+    q = synth.make_q(700, 3, seed=2)
+    Zo, lo, io, _, gap, cond, lsens = _oracle(oracle_mod, ns, xs, rk, c, q)
+    md = tt_irt.Model(ns, xs, rk, c)
+    Z, l, idx = md.sample(q, want_idx=True)
+    md.close()
+    assert np.array_equal(idx, io)
+    np.testing.assert_allclose(Z, Zo, rtol=0, atol=1e-12)
+    assert np.array_equal(np.isfinite(l), np.isfinite(lo))
+    # sign flip of the first core changes nothing; seeds 0 / 1; one row
+    ns, xs, rk, c = synth.make_tt(5, 17, 8, seed=12)
+    q = synth.make_q(300, 5, seed=13)
+    q[0, :] = 0.0; q[1, :] = 1.0; q[2, 0] = 0.0; q[2, 1] = 1.0
+    md = tt_irt.Model(ns, xs, rk, c); Z1, l1, i1 = md.sample(q, want_idx=True); Zr, lr = md.sample(np.asfortranarray(q[7:8])); md.close()
+    c2 = c.copy(); c2[:17 * 8] *= -1.0
+    md = tt_irt.Model(ns, xs, rk, c2); Z2, l2 = md.sample(q); md.close()
+    assert np.array_equal(Z1, Z2) and np.array_equal(l1, l2)
+    assert np.array_equal(Zr[0], Z1[7]) and lr[0] == l1[7]
+    Zo, lo, io, _, gap, cond, lsens = _oracle(oracle_mod, ns, xs, rk, c, q)
+    assert np.array_equal(i1, io)
+    assert i1[0].tolist() == [0] * 5 and i1[1].tolist() == [15] * 5
+    stats, fails = oracle_mod.parity.compare(Z1, l1, i1, Zo, lo, io, cond, gap, lsens=lsens)
+    assert not fails, (fails, stats)
+    # signed cores: the contraction cancels and the reference's own two BLAS builds disagree by ~1e-7 (tests/test_oracle.py);
+    # the bar is the strict GPU mode (bit-exact against the oracle) to that spread, with the same intervals almost everywhere
+    ns, xs, rk, c = synth.make_tt(6, 17, 8, seed=5, cores="normal")
+    q = synth.make_q(4000, 6, seed=6)
+    md = tt_irt.Model(ns, xs, rk, c)
+    Zs, ls, ixs = md.sample(q, mode=tt_irt.MODE_STRICT, want_idx=True)
+    Zf, lf, ixf = md.sample(q, mode=tt_irt.MODE_FAST, want_idx=True)
+    md.close()
+    same = (ixs == ixf).all(axis=1)
+    assert same.mean() > 0.999
+    assert np.abs(Zf - Zs)[same].max() < 1e-6 and np.median(np.abs(Zf - Zs)[same]) < 1e-13
+
+
 @pytest.mark.parametrize("name", GOLDEN)
 def test_against_golden_reference_outputs(oracle_mod, golden_dir, name):
     """Committed outputs of the unmodified reference (netlib-order BLAS build): strict mode reproduces Z bit

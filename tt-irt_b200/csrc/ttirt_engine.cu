@@ -1009,7 +1009,8 @@ static int copy_threads() {
   static int v = -1;
   if (v < 0) {
     const char *e = getenv("TTIRT_COPY_THREADS");
-    v = e ? atoi(e) : 4;
+    const int hw = (int)std::thread::hardware_concurrency();
+    v = e ? atoi(e) : std::min(8, std::max(2, hw / 2));   // 8 on the 16-core boxes: 38.6 -> 39.6 M samples/s on pageable arrays
     if (v < 1) v = 1;
     if (v > 32) v = 32;
   }
