@@ -92,10 +92,13 @@ TTIRT_API int ttirt_sample_device(ttirt_model *model, int64_t M, const double *d
 TTIRT_API int ttirt_sample_host(ttirt_model *model, int64_t M, const double *h_q, double *h_z, double *h_lpz,
                       int32_t *h_idx, int64_t ld, int mode);
 
-/* Whole call on host buffers: create models on n_devices devices starting at first_device, shard the
- * M rows contiguously across them (one host thread per device, no collective).  Grid and cores are uploaded (to the
- * first device from the host, to the others from there by peer copies; TTIRT_FANOUT=0: every device from the host) and
- * the sweep is run on every call; only device allocations are reused between calls (see ttirt_cache_clear).
+/* Whole call on host buffers: models on n_devices devices starting at first_device, one host thread and one copy /
+ * compute pipeline per device, no collective.  The M rows are dealt out to the devices chunk by chunk from a shared queue
+ * (a device with a faster path to host memory takes more; TTIRT_BALANCE=static: contiguous equal shards as given by
+ * ttirt_shard_rows); chunk boundaries belong to the queue, so the result is bit-identical for every device count.  Grid
+ * and cores are uploaded (to the first device from the host, to the others from there by peer copies; TTIRT_FANOUT=0: every
+ * device from the host) and the sweep is run on every call; only device allocations -- and, for models up to 512 KB whose
+ * grid and cores arrive byte-identical, the resident model -- are reused between calls (see ttirt_cache_clear).
  * This is what tt_irt1() runs.  0 on success. */
 TTIRT_API int ttirt_run_host(int64_t d, const int64_t *n, const double *xs, const int64_t *ttrank,
                    const double *ttcore, int64_t M, const double *h_q, double *h_z, double *h_lpz,
