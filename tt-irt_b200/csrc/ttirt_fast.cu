@@ -25,7 +25,7 @@ __device__ unsigned long long g_phase_cycles[8 + 32];
 __device__ long long g_trace[2 * 24 * 8];   // CTA 0, the two MMA warps of sub-partition 0: clock at every PT_MARK of the first 24 tiles
 #define PT_DECL unsigned long long pt_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pt_t = clock64(); const long long pt_start = pt_t;
 #define PT_MARK(k) { const long long n_ = clock64(); pt_[k] += (unsigned long long)(n_ - pt_t); pt_t = n_; \
-  if (blockIdx.x == 0 && lane == 0 && tw == 0 && tile - t_begin < 24) g_trace[(prod * 24 + (tile - t_begin)) * 8 + (k)] = n_; }
+  if (blockIdx.x == 0 && lane == 0 && (mw & 3) == 0 && tile - t_begin < 24) g_trace[((mw >> 2) * 24 + (tile - t_begin)) * 8 + (k)] = n_; }
 #define PT_FLUSH if (lane == 0) { for (int k_ = 0; k_ < 8; k_++) atomicAdd(&g_phase_cycles[k_], pt_[k_]); atomicAdd(&g_phase_cycles[8 + (warp & 7)], (unsigned long long)(clock64() - pt_start)); }
 // tail warps: phases land in g_phase_cycles[24 + k].  BAR.SYNC defers its blocking to the next dependent
 // instruction, so the time waiting for a parked tile shows up in the phase after the barrier.
@@ -112,6 +112,9 @@ __device__ __forceinline__ void stage_slab(bool async_ok, double *dst, const dou
   else stage_b(dst, src, K, NC, cs, KP, NCP, tid, nthr);
 }
 
+#ifndef TTIRT_ALT
+#define TTIRT_ALT 1     // partner alternation of the update phases: 0 off, 1 the r <= 32 class (+2 % there; -2 % at r <= 16 and r <= 64), 2 every class
+#endif
 #ifndef TTIRT_SWPIPE
 #define TTIRT_SWPIPE 0
 #endif
@@ -153,7 +156,7 @@ struct SmemLayout {
   static constexpr int HB = HS / 4;                // ... as four blocks of HB consecutive cells, walked side by side
   static constexpr int NHH = 2 * HS + 8;           // entries of the per-node tables rw / hr
   static constexpr size_t bytes = sizeof(double) * (2 * SLAB + PN + MMA_WARPS * GD * FTILE + TW * PB + 2 * NHH + 2 * 8 * NT) +
-                                  sizeof(int) * (2 * (NBMAX + 1) + NBMAX + TW * (WROWS + 2));
+                                  sizeof(int) * (2 * (NBMAX + 1) + NBMAX + TW * (WROWS + 2) + MMA_WARPS);
 };
 
 // Named barriers (id 0 is __syncthreads).  Tile hand-over between an MMA warp and its tail warp is a 64-thread
@@ -190,6 +193,8 @@ template <int RT, int NT, bool EXACT, bool TAIL1, int TW, int GD>
 __global__ void __launch_bounds__(nthr_of(TW), 1) transition_kernel(const TransArgs a) {
   static_assert(EXACT || !TAIL1, "TAIL1 needs EXACT");
   static_assert(GD == 1 || GD == 2, "gather depth 1 or 2");
+  static_assert(MMA_WARPS == 8, "partner alternation pairs MMA warps mw and mw ^ 4");
+  constexpr bool ALT = (TTIRT_ALT == 2) || (TTIRT_ALT == 1 && TW == 8 && RT == 4);
   using L = SmemLayout<RT, NT, TAIL1, TW, GD>;
   constexpr int TAIL_WARPS = TW, NTHR = nthr_of(TW), PRODS = MMA_WARPS / TW;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -208,6 +213,7 @@ __global__ void __launch_bounds__(nthr_of(TW), 1) transition_kernel(const TransA
   int *ids_all = hist + L::NBMAX;                     // per tail warp: sample ids of the parked tile
   int *nv_all = ids_all + TAIL_WARPS * WROWS;         // per tail warp: valid rows of the parked tile
   int *consumed = nv_all + TAIL_WARPS;                // per tail warp: parked tiles released so far (TW == 8 hand-back)
+  int *upd_done = consumed + TAIL_WARPS;              // per MMA warp: tiles whose update phase is finished (partner alternation)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int FP = L::FPITCH, RS = L::RS;
@@ -234,6 +240,7 @@ __global__ void __launch_bounds__(nthr_of(TW), 1) transition_kernel(const TransA
     if (i < L::NBMAX) hist[i] = 0;
   }
   if (tid < TAIL_WARPS) consumed[tid] = 0;
+  if (tid < MMA_WARPS) upd_done[tid] = 0;
   __syncthreads();
 
   const int total_tiles = bts[nb0];
@@ -524,6 +531,18 @@ __global__ void __launch_bounds__(nthr_of(TW), 1) transition_kernel(const TransA
 #pragma unroll
         for (int j = 0; j < NT; j++) c[i][j][0] = c[i][j][1] = 0.0;
 
+      // Partner alternation.  The two MMA warps of an SM sub-partition (mw, mw ^ 4) run the same instruction stream on the one
+      // FP64 pipe they share; left alone they fall into lock-step in the lighter classes (timeline in
+      // profiles/r02_phase_timing_r32.log: both leave their DMMA loops at the same time and the pipe idles for a quarter of
+      // every tile).  So their update phases take turns: the first warp of a pair starts tile i's update when its partner has
+      // finished tile i-1's, the second when the first has finished tile i's.  Each warp's pdf phase, parking and
+      // bookkeeping then run under the partner's update phase.
+      if (ALT) {
+        const int need = (mw & 4) ? (tile - t_begin) + 1 : (tile - t_begin);
+        if (lane == 0)
+          while (ld_volatile_s(upd_done + (mw ^ 4)) < need) __nanosleep(64);
+        __syncwarp();
+      }
       if (nvalid > 0) {
         // ---- (1) interface update: A fragments from the staged rows ------------------------------------
         if (GD == 1) cp_async_wait_all(); else asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -614,6 +633,7 @@ __global__ void __launch_bounds__(nthr_of(TW), 1) transition_kernel(const TransA
         PT_MARK(2)
         // ---- the staged tile is consumed: launch the next tile's gather and scalar loads now ---------
         __syncwarp();
+        if (ALT && lane == 0) st_volatile_s(upd_done + mw, (tile - t_begin) + 1);
         issue_gather(idQ[GD], nvQ[GD], ft);
         load_scalars(GD, idQ[GD], nvQ[GD]);
         // F' rows go out one 64-byte segment per pdf k-pair (below), so the stores trickle out under the DMMA stream
@@ -692,6 +712,7 @@ __global__ void __launch_bounds__(nthr_of(TW), 1) transition_kernel(const TransA
         }
       } else {
         // this warp has no rows in this tile: keep the pipeline moving
+        if (ALT && lane == 0) st_volatile_s(upd_done + mw, (tile - t_begin) + 1);
         issue_gather(idQ[GD], nvQ[GD], ft);
         load_scalars(GD, idQ[GD], nvQ[GD]);
       }
