@@ -118,28 +118,26 @@ __device__ __forceinline__ void stage_slab(bool async_ok, double *dst, const dou
 #ifndef TTIRT_SWPIPE
 #define TTIRT_SWPIPE 0
 #endif
-#ifndef TTIRT_MMA_WARPS
-#define TTIRT_MMA_WARPS 8
-#endif
-constexpr int MMA_WARPS = TTIRT_MMA_WARPS;    // two per SM sub-partition: they share the FP64 tensor pipe (4: experiment, one per sub-partition)
-// Tail warps per CTA (template parameter TW): 4 for the r <= 64 class (one per SM sub-partition, each serving two MMA
-// warps: the MMA side is the long one there) and 8 for the lighter classes, where the per-row tail work is as long as
-// the DMMA work and every MMA warp gets a tail warp of its own.
+// Warps per CTA (template parameters MW, TW): MMA warps and tail warps, in multiples of the four SM sub-partitions.
+//   MW = 8, TW = 4   the r <= 64 class: two MMA warps per sub-partition share its FP64 tensor pipe, one tail warp serves both
+//                    (the MMA side is the long one there; a third MMA warp fits neither the registers nor shared memory)
+//   MW = 8, TW = 8   lighter classes, round-1 layout: every MMA warp has a tail warp of its own
+//   MW = 12, TW = 4  lighter classes: three MMA warps per sub-partition (their accumulators are small enough for 128
+//                    registers), so that two are inside their DMMA loops while the third gathers, parks and waits
 constexpr int MT = 2;           // 8-row MMA tiles per MMA warp
 constexpr int WROWS = 8 * MT;   // samples per warp tile
-constexpr int ROWS_CTA = MMA_WARPS * WROWS;
-__host__ __device__ constexpr int nthr_of(int tw) { return 32 * (MMA_WARPS + tw); }
-// register file split (setmaxnreg, per warpgroup of four warps): launched at 168 per thread, the tail warpgroup
-// shrinks to tail_regs and the two MMA warpgroups grow to mma_regs; 32 * (8 * 192 + 4 * 120) = 32 * 12 * 168 and
-// 32 * (8 * 152 + 8 * 104) = 32 * 16 * 128: the pool is exactly what the launch allocated
-__host__ __device__ constexpr int mma_regs_of(int tw) { return tw == 4 ? 192 : 152; }
-__host__ __device__ constexpr int tail_regs_of(int tw) { return tw == 4 ? 120 : 104; }
+__host__ __device__ constexpr int nthr_of(int mw, int tw) { return 32 * (mw + tw); }
+// register file split (setmaxnreg, per warpgroup of four warps): the launch allocates 65536 / threads registers per thread
+// (168 for 12 warps, 128 for 16), the tail warpgroup(s) shrink to tail_regs and the MMA warpgroups grow to mma_regs;
+// 8 * 192 + 4 * 120 = 12 * 168, 8 * 152 + 8 * 104 = 16 * 128, 12 * 128 + 4 * 128 = 16 * 128: exactly the pool of the launch
+__host__ __device__ constexpr int mma_regs_of(int mw, int tw) { return mw == 12 ? 128 : (tw == 4 ? 192 : 152); }
+__host__ __device__ constexpr int tail_regs_of(int mw, int tw) { return mw == 12 ? 128 : (tw == 4 ? 120 : 104); }
 
 // GD: depth of the row gather.  1: the rows of tile t+1 are requested once tile t's update phase has consumed the staged
 // tile (a whole pdf phase ahead: enough at r = 64, where that phase lasts ~2 us).  2 (the two lighter classes, where the pdf
 // phase is a quarter of that and a request would still be in flight when it is needed): two staged tiles per MMA warp,
 // the rows of tile t+2 are requested at that point.
-template <int RT, int NT, bool TAIL1, int TW, int GD>
+template <int RT, int NT, bool TAIL1, int MW, int TW, int GD>
 struct SmemLayout {
   static constexpr int KPMAX = (8 * RT + 15) & ~15;
   static constexpr int SLAB = 8 * RT * KPMAX;      // doubles per slab buffer
@@ -155,8 +153,8 @@ struct SmemLayout {
   static constexpr int HS = TAIL1 ? 4 * (NT - 1) : 4 * NT;   // cells walked by each of the two lanes of a row
   static constexpr int HB = HS / 4;                // ... as four blocks of HB consecutive cells, walked side by side
   static constexpr int NHH = 2 * HS + 8;           // entries of the per-node tables rw / hr
-  static constexpr size_t bytes = sizeof(double) * (2 * SLAB + PN + MMA_WARPS * GD * FTILE + TW * PB + 2 * NHH + 2 * 8 * NT) +
-                                  sizeof(int) * (2 * (NBMAX + 1) + NBMAX + TW * (WROWS + 2) + MMA_WARPS);
+  static constexpr size_t bytes = sizeof(double) * (2 * SLAB + PN + MW * GD * FTILE + TW * PB + 2 * NHH + 2 * 8 * NT) +
+                                  sizeof(int) * (2 * (NBMAX + 1) + NBMAX + TW * (WROWS + 2) + MW);
 };
 
 // Named barriers (id 0 is __syncthreads).  Tile hand-over between an MMA warp and its tail warp is a 64-thread
@@ -164,11 +162,13 @@ struct SmemLayout {
 // for the F' stores and the row gather still in flight.
 //   1                 the eight MMA warps (slab restaging at a bin change)
 //   2 + tw            FULL : a producer of buffer tw arrives after parking a tile, tail warp tw waits
-//   6 + 4*p + tw      EMPTY (TW == 4): tail warp tw arrives when producer p (0 / 1) may overwrite the buffer, producer p waits.
-//                     With TW == 8 the ids would not fit (2 + 8 + 8 > 16): the single producer of a buffer polls a counter
-//                     in shared memory that its tail warp bumps after its last read of the tile (same warp, same memory pipe:
-//                     the store follows the loads).
-__device__ __forceinline__ void bar_mma_warps() { asm volatile("bar.sync 1, %0;" ::"n"(32 * MMA_WARPS) : "memory"); }
+//   6 + 4*p + tw      EMPTY (MW = 8, TW = 4): tail warp tw arrives when producer p (0 / 1) may overwrite the buffer, producer p waits.
+//                     With eight tail warps or three producers per buffer the ids would not fit (16 in all): there the
+//                     producers of a buffer poll a counter in shared memory that the tail warp bumps after its last read of
+//                     a tile (same warp, same memory pipe: the store follows the loads); use number PRODS * i + p of the
+//                     buffer belongs to producer p's tile i, so the counter also keeps the producers in turn.
+template <int MW>
+__device__ __forceinline__ void bar_mma_warps() { asm volatile("bar.sync 1, %0;" ::"n"(32 * MW) : "memory"); }
 __device__ __forceinline__ void bar_pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void bar_pair_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ int ld_volatile_s(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
@@ -189,14 +189,17 @@ __device__ __forceinline__ void st_volatile_s(int *p, int v) { *reinterpret_cast
 // Row gather: the left-interface rows of an MMA warp's NEXT tile are fetched asynchronously (cp.async / LDGSTS, one
 // coalesced 8*r0-byte row per instruction) into a per-warp shared tile as soon as the current tile's update
 // phase has consumed that tile, i.e. a whole pdf phase ahead of use.
-template <int RT, int NT, bool EXACT, bool TAIL1, int TW, int GD>
-__global__ void __launch_bounds__(nthr_of(TW), 1) transition_kernel(const TransArgs a) {
+template <int RT, int NT, bool EXACT, bool TAIL1, int MW, int TW, int GD>
+__global__ void __launch_bounds__(nthr_of(MW, TW), 1) transition_kernel(const TransArgs a) {
   static_assert(EXACT || !TAIL1, "TAIL1 needs EXACT");
   static_assert(GD == 1 || GD == 2, "gather depth 1 or 2");
-  static_assert(MMA_WARPS == 8, "partner alternation pairs MMA warps mw and mw ^ 4");
-  constexpr bool ALT = (TTIRT_ALT == 2) || (TTIRT_ALT == 1 && TW == 8 && RT == 4);
-  using L = SmemLayout<RT, NT, TAIL1, TW, GD>;
-  constexpr int TAIL_WARPS = TW, NTHR = nthr_of(TW), PRODS = MMA_WARPS / TW;
+  static_assert(MW % TW == 0 && (TW == 4 || TW == 8), "tail warp tw serves the MMA warps mw with mw % TW == tw (same sub-partition)");
+  constexpr bool ALT = MW == 8 && ((TTIRT_ALT == 2) || (TTIRT_ALT == 1 && TW == 8 && RT == 4));   // pairs mw, mw ^ 4
+  using L = SmemLayout<RT, NT, TAIL1, MW, TW, GD>;
+  constexpr int MMA_WARPS = MW, ROWS_CTA = MW * WROWS;
+  constexpr int TAIL_WARPS = TW, NTHR = nthr_of(MW, TW), PRODS = MMA_WARPS / TW;
+  constexpr bool EMPTY_BARS = MW == 8 && TW == 4;   // hand-back by named barriers (ids 6 .. 13); else by the polled counter
+  constexpr int LAUNCH_REGS = (65536 / NTHR) & ~7;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *slab0 = reinterpret_cast<double *>(smem_raw);
   double *slab1 = slab0 + L::SLAB;
@@ -271,7 +274,7 @@ __global__ void __launch_bounds__(nthr_of(TW), 1) transition_kernel(const TransA
     // and the CDF pass is a plain running sum.  Next to a DMMA stream every instruction of another warp waits for a
     // gap between two DMMAs (~20 cycles, whatever its type), so the tail is written for instruction count: one pass,
     // a two-level search on integer bit patterns, one inversion per pair of tiles.
-    if (NTHR > 256) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(tail_regs_of(TW)));
+    if (tail_regs_of(MW, TW) < LAUNCH_REGS) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(tail_regs_of(MW, TW)));
     const int tw = warp, row = lane & 15, hf = lane >> 4;
     const double *pbr = pb_all + tw * L::PB + row;
     const int *ids = ids_all + tw * WROWS;
@@ -283,9 +286,9 @@ __global__ void __launch_bounds__(nthr_of(TW), 1) transition_kernel(const TransA
     int st_nv = 0, st_m = 0, st_i0 = 0, st_E = 0;
     double st_dq = 0.0, st_c1 = 1.0, st_c2 = 1.0, st_mass = 1.0, st_N = 1.0, st_D = 1.0;
     TT_DECL
-    // hand the buffer back: to the other producer through its EMPTY barrier (TW == 4), to the only one through the counter
+    // hand the buffer back: to the other producer through its EMPTY barrier, or to whoever is next through the counter
     auto release = [&](int seq) {
-      if (TW == 4) {
+      if (EMPTY_BARS) {
         if (seq + 1 < uses) bar_pair_arrive(6 + 4 * ((seq + 1) % PRODS) + tw);
       } else {
         __syncwarp();
@@ -412,7 +415,7 @@ __global__ void __launch_bounds__(nthr_of(TW), 1) transition_kernel(const TransA
     TT_FLUSH
   } else {
     // =========================================== MMA warps ============================================
-    if (NTHR > 256) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(mma_regs_of(TW)));
+    if (mma_regs_of(MW, TW) > LAUNCH_REGS) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(mma_regs_of(MW, TW)));
     const int g = lane >> 2, t = lane & 3;
     const int mw = warp - TAIL_WARPS;          // index among the MMA warps
     const int mtid = 32 * mw + lane;
@@ -503,7 +506,7 @@ __global__ void __launch_bounds__(nthr_of(TW), 1) transition_kernel(const TransA
       } else if (cur1 == b && cur0 == b + 1) {
         sl_lo = slab1; sl_hi = slab0;
       } else {
-        bar_mma_warps();  // every MMA warp is done with the previous bin's slabs
+        bar_mma_warps<MW>();  // every MMA warp is done with the previous bin's slabs
         constexpr int NM = 32 * MMA_WARPS;
         if (cur0 == b) {
           stage_slab(slab_async, slab1, a.core + (int64_t)(b + 1) * r0, r0, r1, slab_cs, KP, 8 * RT, mtid, NM); cur1 = b + 1;
@@ -519,7 +522,7 @@ __global__ void __launch_bounds__(nthr_of(TW), 1) transition_kernel(const TransA
         }
         cp_async_commit();
         cp_async_wait_all();   // (also the row gather in flight: it is needed right after anyway)
-        bar_mma_warps();
+        bar_mma_warps<MW>();
         if (cur0 == b) { sl_lo = slab0; sl_hi = slab1; } else { sl_lo = slab1; sl_hi = slab0; }
       }
 
@@ -725,11 +728,11 @@ __global__ void __launch_bounds__(nthr_of(TW), 1) transition_kernel(const TransA
       // ---- (3) park the signed pdf tile for the tail warp (it takes |.|, reference :105); the two producers of a buffer alternate ----
       {
         // producer 0 waits for the tail warp to have released producer 1's previous tile, and vice versa
-        if (TW == 4) {
+        if (EMPTY_BARS) {
           if (prod > 0 || tile > t_begin) bar_pair_sync(6 + 4 * prod + tw);
         } else {
           if (lane == 0)
-            while (ld_volatile_s(consumed + tw) < tile - t_begin) __nanosleep(20);   // every earlier tile of this warp released
+            while (ld_volatile_s(consumed + tw) < PRODS * (tile - t_begin) + prod) __nanosleep(20);   // every earlier use of the buffer released
           __syncwarp();
         }
         PT_MARK(5)
@@ -770,37 +773,41 @@ __global__ void __launch_bounds__(nthr_of(TW), 1) transition_kernel(const TransA
   }
 }
 
-template <int RT, int NT, bool EXACT, bool TAIL1, int TW, int GD>
+template <int RT, int NT, bool EXACT, bool TAIL1, int MW, int TW, int GD>
 cudaError_t launch_variant(const TransArgs &a, int sm_count, cudaStream_t st) {
-  using L = SmemLayout<RT, NT, TAIL1, TW, GD>;
+  using L = SmemLayout<RT, NT, TAIL1, MW, TW, GD>;
+  constexpr int ROWS_CTA = MW * WROWS;
   int64_t max_tiles = ((int64_t)a.rows + ROWS_CTA - 1) / ROWS_CTA + (a.n0 - 1);
   int64_t grid = sm_count;   // persistent: one CTA per SM (the register file allows no more)
   if (grid > max_tiles) grid = max_tiles;
   if (grid < 1) grid = 1;
-  transition_kernel<RT, NT, EXACT, TAIL1, TW, GD><<<(unsigned)grid, nthr_of(TW), L::bytes, st>>>(a);
+  transition_kernel<RT, NT, EXACT, TAIL1, MW, TW, GD><<<(unsigned)grid, nthr_of(MW, TW), L::bytes, st>>>(a);
   return cudaGetLastError();
 }
 
-template <int RT, int NT, int TW, int GD>
+template <int RT, int NT, int MW, int TW, int GD>
 cudaError_t launch_one(const TransArgs &a, int sm_count, cudaStream_t st) {
   const bool exact = a.r0 == 8 * RT && a.r1 == 8 * RT && (a.n1 + 7) / 8 == NT;
-  if (exact && a.n1 == 8 * (NT - 1) + 1) return launch_variant<RT, NT, true, true, TW, GD>(a, sm_count, st);
-  if (exact) return launch_variant<RT, NT, true, false, TW, GD>(a, sm_count, st);
-  return launch_variant<RT, NT, false, false, TW, GD>(a, sm_count, st);
+  if (exact && a.n1 == 8 * (NT - 1) + 1) return launch_variant<RT, NT, true, true, MW, TW, GD>(a, sm_count, st);
+  if (exact) return launch_variant<RT, NT, true, false, MW, TW, GD>(a, sm_count, st);
+  return launch_variant<RT, NT, false, false, MW, TW, GD>(a, sm_count, st);
 }
 
-template <int RT, int NT, int TW, int GD>
+template <int RT, int NT, int MW, int TW, int GD>
 cudaError_t init_one() {
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(transition_kernel<RT, NT, true, true, TW, GD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout<RT, NT, true, TW, GD>::bytes)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(transition_kernel<RT, NT, true, false, TW, GD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout<RT, NT, false, TW, GD>::bytes)) != cudaSuccess) return e;
-  return cudaFuncSetAttribute(transition_kernel<RT, NT, false, false, TW, GD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout<RT, NT, false, TW, GD>::bytes);
+  if ((e = cudaFuncSetAttribute(transition_kernel<RT, NT, true, true, MW, TW, GD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout<RT, NT, true, MW, TW, GD>::bytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(transition_kernel<RT, NT, true, false, MW, TW, GD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout<RT, NT, false, MW, TW, GD>::bytes)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(transition_kernel<RT, NT, false, false, MW, TW, GD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout<RT, NT, false, MW, TW, GD>::bytes);
 }
 
-#ifndef TTIRT_LIGHT_TW
-#define TTIRT_LIGHT_TW 8    // tail warps of the two lighter classes
+#ifndef TTIRT_LIGHT_MW
+#define TTIRT_LIGHT_MW 8    // MMA warps of the two lighter classes: 8 with eight tail warps; 12 with four (measured: the one tail warp per sub-partition cannot keep up with three MMA warps, 65 against 101 M samples/s at d=40 n=33 r=32)
 #endif
-constexpr int kLightTW = TTIRT_LIGHT_TW;
+#ifndef TTIRT_LIGHT_TW
+#define TTIRT_LIGHT_TW (TTIRT_LIGHT_MW == 12 ? 4 : 8)    // tail warps of the two lighter classes
+#endif
+constexpr int kLightMW = TTIRT_LIGHT_MW, kLightTW = TTIRT_LIGHT_TW;
 #ifndef TTIRT_LIGHT_GD
 #define TTIRT_LIGHT_GD 2    // gather depth of the two lighter classes
 #endif
@@ -815,21 +822,21 @@ int fast_class_for(int rmax, int nmax) {
   return -1;
 }
 
-int fast_rows_per_cta(int) { return ROWS_CTA; }
+int fast_rows_per_cta(int cls) { return (cls == 2 ? 8 : kLightMW) * WROWS; }
 
 cudaError_t fast_init(int) {
   cudaError_t e;
-  if ((e = init_one<2, 3, kLightTW, kLightGD>()) != cudaSuccess) return e;
-  if ((e = init_one<4, 5, kLightTW, kLightGD>()) != cudaSuccess) return e;
-  if ((e = init_one<8, 9, 4, 1>()) != cudaSuccess) return e;
+  if ((e = init_one<2, 3, kLightMW, kLightTW, kLightGD>()) != cudaSuccess) return e;
+  if ((e = init_one<4, 5, kLightMW, kLightTW, kLightGD>()) != cudaSuccess) return e;
+  if ((e = init_one<8, 9, 8, 4, 1>()) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
 cudaError_t launch_transition(int cls, const TransArgs &a, int sm_count, cudaStream_t st) {
   switch (cls) {
-    case 0: return launch_one<2, 3, kLightTW, kLightGD>(a, sm_count, st);
-    case 1: return launch_one<4, 5, kLightTW, kLightGD>(a, sm_count, st);
-    case 2: return launch_one<8, 9, 4, 1>(a, sm_count, st);
+    case 0: return launch_one<2, 3, kLightMW, kLightTW, kLightGD>(a, sm_count, st);
+    case 1: return launch_one<4, 5, kLightMW, kLightTW, kLightGD>(a, sm_count, st);
+    case 2: return launch_one<8, 9, 8, 4, 1>(a, sm_count, st);
     default: return cudaErrorInvalidValue;
   }
 }
