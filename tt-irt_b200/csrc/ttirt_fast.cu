@@ -130,8 +130,11 @@ __host__ __device__ constexpr int nthr_of(int mw, int tw) { return 32 * (mw + tw
 // register file split (setmaxnreg, per warpgroup of four warps): the launch allocates 65536 / threads registers per thread
 // (168 for 12 warps, 128 for 16), the tail warpgroup(s) shrink to tail_regs and the MMA warpgroups grow to mma_regs;
 // 8 * 192 + 4 * 120 = 12 * 168, 8 * 152 + 8 * 104 = 16 * 128, 12 * 128 + 4 * 128 = 16 * 128: exactly the pool of the launch
-__host__ __device__ constexpr int mma_regs_of(int mw, int tw) { return mw == 12 ? 128 : (tw == 4 ? 192 : 152); }
-__host__ __device__ constexpr int tail_regs_of(int mw, int tw) { return mw == 12 ? 128 : (tw == 4 ? 120 : 104); }
+#ifndef TTIRT_LIGHT_TAIL_REGS
+#define TTIRT_LIGHT_TAIL_REGS 104   // 120 (MMA warps at 136) measured: no difference
+#endif
+__host__ __device__ constexpr int tail_regs_of(int mw, int tw) { return mw == 12 ? 128 : (tw == 4 ? 120 : TTIRT_LIGHT_TAIL_REGS); }
+__host__ __device__ constexpr int mma_regs_of(int mw, int tw) { return mw == 12 ? 128 : (tw == 4 ? 192 : 256 - tail_regs_of(mw, tw)); }
 
 // GD: depth of the row gather.  1: the rows of tile t+1 are requested once tile t's update phase has consumed the staged
 // tile (a whole pdf phase ahead: enough at r = 64, where that phase lasts ~2 us).  2 (the two lighter classes, where the pdf
