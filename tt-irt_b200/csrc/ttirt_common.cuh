@@ -191,7 +191,6 @@ cudaError_t launch_walk(int cls, const WalkArgs &a, int sm_count, cudaStream_t s
 
 // fast-path shape classes: (rank tiles of 8, grid tiles of 8)
 int fast_class_for(int rmax, int nmax);             // -1: shape outside the fast path
-int fast_rows_per_cta(int cls);
 cudaError_t launch_transition(int cls, const TransArgs &a, int sm_count, cudaStream_t st);
 cudaError_t fast_init(int device);                  // opt in to large dynamic shared memory
 

@@ -137,7 +137,6 @@ struct ttirt_model {
   cudaEvent_t loaded = nullptr;
   std::vector<double> image;      // host copy of (xs, cores) the model was loaded from, small models only
   bool image_valid = false;
-  bool keep_transition_path = false;   // walk models: also prepare the per-dimension path (never needed in production)
   int walk_cls = -1;             // >= 0: the all-dimensions walk kernel serves this model's fast path (ttirt_walk.cu)
   double *d_walk = nullptr;      // its packed per-dimension operand blocks
   Workspace ws[kSlots];      // host pipeline slots (own streams)
@@ -177,7 +176,7 @@ static void ws_free(Workspace &w) {
 static int ws_alloc(ttirt_model *md, Workspace &w, int64_t cap, bool s, bool h, bool wi) {
   const int64_t d = md->d;
   // per-sample state of the per-dimension path; the walk kernel keeps all of it in registers
-  if (md->walk_cls < 0 || md->keep_transition_path) {
+  if (md->walk_cls < 0) {
     CK(cudaMalloc(&w.F, sizeof(double) * cap * md->ldf));
     CK(cudaMalloc(&w.idx, sizeof(int) * cap));
     CK(cudaMalloc(&w.perm, sizeof(int) * cap));
@@ -638,7 +637,7 @@ static int model_load_body(ttirt_model *md, const CoreSource &src) {
     CK(walk_pack(md->walk_cls, md->d_dims, (int)d, md->d_xs, md->d_core, md->d_pk, md->d_p0, md->d_cdf0, md->d_walk, ls));
     LAUNCHED();
   }
-  if (md->fast_cls >= 0 && d > 1 && (md->walk_cls < 0 || md->keep_transition_path)) {
+  if (md->fast_cls >= 0 && d > 1 && md->walk_cls < 0) {
     weight_p_kernel<<<dim3(8, (unsigned)d), 256, 0, ls>>>(md->d_dims, (int)d, md->d_xs, md->d_pk, md->d_pkw);
     LAUNCHED();
   }

@@ -825,7 +825,6 @@ int fast_class_for(int rmax, int nmax) {
   return -1;
 }
 
-int fast_rows_per_cta(int cls) { return (cls == 2 ? 8 : kLightMW) * WROWS; }
 
 cudaError_t fast_init(int) {
   cudaError_t e;
