@@ -979,8 +979,26 @@ static void unpin(const void *p, bool pinned) { if (pinned) { cudaHostUnregister
 struct ChunkQueue {
   std::atomic<int64_t> next{0};
   int64_t base = 0, end = 0, chunk = 1;
+  // ramp (one-device calls of many chunks): the first and the last `levels` chunks are 1 / 2^levels ... 1 / 2 of the regular
+  // size, so that the first upload and the last download -- which nothing can overlap -- are short
+  std::vector<int64_t> starts;   // empty: uniform chunks
+  void ramp(int levels) {
+    const int64_t M = end - base;
+    if (levels < 1 || (chunk >> levels) < 1024 || M < 8 * chunk) return;
+    int64_t m = base, tail_rows = 0;
+    for (int l = levels; l >= 1; l--) { starts.push_back(m); m += chunk >> l; tail_rows += chunk >> l; }
+    while (end - m - tail_rows >= chunk) { starts.push_back(m); m += chunk; }
+    if (end - m > tail_rows) { starts.push_back(m); m = end - tail_rows; }   // a shorter regular chunk takes up the remainder
+    for (int l = 1; l <= levels; l++) { starts.push_back(m); m += chunk >> l; }
+    starts.push_back(end);
+  }
   bool claim(int64_t &m0, int64_t &rows) {
     const int64_t i = next.fetch_add(1, std::memory_order_relaxed);
+    if (!starts.empty()) {
+      if (i + 1 >= (int64_t)starts.size()) return false;
+      m0 = starts[(size_t)i]; rows = starts[(size_t)i + 1] - m0;
+      return true;
+    }
     m0 = base + i * chunk;
     if (m0 >= end) return false;
     rows = std::min(chunk, end - m0);
@@ -1076,6 +1094,9 @@ static int sample_host_rows(ttirt_model *md, int64_t m_begin, int64_t m_end, con
   // the chunks of this call: a private queue over [m_begin, m_end), or the queue shared by the devices of the call
   ChunkQueue own;
   own.base = m_begin; own.end = m_end; own.chunk = host_chunk_for(md->fast_cls, strict, walk, M);
+  // (metric shape, pinned arrays: 41.35 -> 42.05 M samples/s with two levels; TTIRT_RAMP=<levels>, 0 turns it off)
+  static const int ramp_levels = getenv("TTIRT_RAMP") ? atoi(getenv("TTIRT_RAMP")) : 2;
+  if (!shared && !strict && md->fast_cls == 2) own.ramp(ramp_levels);   // (r <= 32 class measured: 52.6 against 50.8 ms per call, left uniform)
   ChunkQueue &queue = shared ? *shared : own;
   const int64_t chunk = queue.chunk;
   const int64_t nchunks = shared ? (int64_t)kSlots : (M + chunk - 1) / chunk;   // (shared: unknown in advance)
