@@ -638,6 +638,32 @@ def test_host_pipeline_with_padded_leading_dimension(M, extra):
     assert (zbig[M:] == -7.0).all() and (lbig[M:] == -7.0).all()      # rows beyond M untouched
 
 
+def test_chunk_ramp_and_chunk_size_do_not_change_a_bit(oracle_mod):
+    """One-device calls of many chunks in the r <= 64 class ramp their chunk sizes (quarter, half, full ... half, quarter).
+    Results must not depend on how the rows are cut: uniform small chunks with the ramp, one big chunk, and the oracle."""
+    d, n, r = 3, 65, 64
+    ns, xs, rk, c = synth.make_tt(d, n, r, seed=71)
+    lib = tt_irt.load_library()
+    M = 9 * (1 << 13) + 333                       # more than eight chunks of 2^13 rows: the ramp is on
+    q = synth.make_q(M, d, seed=72)
+    md = tt_irt.Model(ns, xs, rk, c)
+    try:
+        lib.ttirt_set_chunk(1 << 13)
+        try:
+            Za, la, ia = md.sample(q, want_idx=True)
+        finally:
+            lib.ttirt_set_chunk(0)
+        Zb, lb, ib = md.sample(q, want_idx=True)   # default chunk: one chunk
+    finally:
+        md.close()
+    assert np.array_equal(Za, Zb) and np.array_equal(la, lb) and np.array_equal(ia, ib)
+    rows = np.concatenate([np.arange(0, 300), np.arange((1 << 11) - 50, (1 << 11) + 50), np.arange(3 * (1 << 11) - 50, 3 * (1 << 11) + 50),
+                           np.arange(M - 300, M)])
+    Zo, lo, io, kap, gap, cond, lsens = _oracle(oracle_mod, ns, xs, rk, c, q[rows])
+    stats, fails = oracle_mod.parity.compare(Za[rows], la[rows], ia[rows], Zo, lo, io, cond, gap, lsens=lsens)
+    assert not fails, (fails, stats)
+
+
 def test_resident_small_model_is_never_stale(oracle_mod):
     """The drop-in call keeps a small model resident when the next call brings bit-identical grid and cores (exact byte
     comparison).  A change of a single core entry, of the grid, or of nothing at all must each give exactly the result of

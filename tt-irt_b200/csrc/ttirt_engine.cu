@@ -135,6 +135,8 @@ struct ttirt_model {
   // slot streams wait for that event instead of synchronising the device (a small call is all latency)
   cudaStream_t load_stream = nullptr;
   cudaEvent_t loaded = nullptr;
+  double *core_stage = nullptr;   // page-locked staging buffer for large cores arriving in pageable memory
+  int64_t core_stage_cap = 0;
   std::vector<double> image;      // host copy of (xs, cores) the model was loaded from, small models only
   bool image_valid = false;
   int walk_cls = -1;             // >= 0: the all-dimensions walk kernel serves this model's fast path (ttirt_walk.cu)
@@ -518,6 +520,7 @@ extern "C" void ttirt_model_destroy(ttirt_model *md) {
   if (md->load_stream) { cudaStreamSynchronize(md->load_stream); cudaStreamDestroy(md->load_stream); }
   if (md->loaded) cudaEventDestroy(md->loaded);
   for (auto &h : md->stage) { cudaFreeHost(h.q); cudaFreeHost(h.z); cudaFreeHost(h.lpz); }
+  cudaFreeHost(md->core_stage);
   for (auto &p : md->prof_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   cudaFree(md->d_xs); cudaFree(md->d_core); cudaFree(md->d_pk); cudaFree(md->d_pkw); cudaFree(md->d_marg);
   cudaFree(md->d_p0); cudaFree(md->d_cdf0); cudaFree(md->d_dims); cudaFree(md->d_walk);
@@ -562,6 +565,44 @@ static bool fanout_enabled() {
   return v != 0;
 }
 
+static bool is_pageable(const void *p);
+// Cores from the caller's array to the device.  Large cores in ordinary pageable memory (numpy, mxArray: 64 MB at the metric
+// shape) go through a page-locked staging buffer of the model in eight pieces: host threads copy the pieces, each piece is
+// sent as soon as it is there (the driver's own staging of pageable memory runs at ~10 GB/s: 6 ms against ~3).
+static cudaError_t upload_cores(ttirt_model *md, const double *core, cudaStream_t ls) {
+  const size_t bytes = sizeof(double) * (size_t)md->sum_c;
+  static const bool no_stage = getenv("TTIRT_NO_STAGING") != nullptr;
+  if (no_stage || bytes < ((size_t)8 << 20) || !is_pageable(core)) return cudaMemcpyAsync(md->d_core, core, bytes, cudaMemcpyHostToDevice, ls);
+  if (md->core_stage_cap < md->sum_c) {
+    cudaFreeHost(md->core_stage); md->core_stage = nullptr; md->core_stage_cap = 0;
+    if (cudaHostAlloc(&md->core_stage, bytes, cudaHostAllocDefault) != cudaSuccess) {
+      cudaGetLastError();
+      return cudaMemcpyAsync(md->d_core, core, bytes, cudaMemcpyHostToDevice, ls);
+    }
+    md->core_stage_cap = md->sum_c;
+  }
+  constexpr int kPieces = 8;
+  std::atomic<int> ready[kPieces];
+  for (auto &r : ready) r.store(0);
+  const int64_t per = (md->sum_c + kPieces - 1) / kPieces;
+  std::vector<std::thread> th;
+  for (int p = 0; p < kPieces; p++)
+    th.emplace_back([&, p]() {
+      const int64_t a = p * per, b = std::min<int64_t>(md->sum_c, a + per);
+      if (b > a) memcpy(md->core_stage + a, core + a, sizeof(double) * (size_t)(b - a));
+      ready[p].store(1, std::memory_order_release);
+    });
+  cudaError_t e = cudaSuccess;
+  for (int p = 0; p < kPieces; p++) {
+    while (!ready[p].load(std::memory_order_acquire)) std::this_thread::yield();
+    const int64_t a = p * per, b = std::min<int64_t>(md->sum_c, a + per);
+    if (b > a && e == cudaSuccess)
+      e = cudaMemcpyAsync(md->d_core + a, md->core_stage + a, sizeof(double) * (size_t)(b - a), cudaMemcpyHostToDevice, ls);
+  }
+  for (auto &t : th) t.join();
+  return e;
+}
+
 // Upload grid and cores into an allocated model of matching shape and run the right-to-left sweep:
 // C_{d-1} = {1}; P_k = core_k x_3 C_k; C_{k-1} = trapezoid(P_k)   (reference tt_irt1_int32.c:59-82)
 static int model_load_body(ttirt_model *md, const CoreSource &src);
@@ -603,7 +644,7 @@ static int model_load_body(ttirt_model *md, const CoreSource &src) {
   if (!have) {
     // pageable sources are staged by the driver before cudaMemcpyAsync returns, so the caller's arrays may change afterwards
     cudaError_t e = cudaMemcpyAsync(md->d_xs, xs, sizeof(double) * md->sum_x, cudaMemcpyHostToDevice, ls);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(md->d_core, core, sizeof(double) * md->sum_c, cudaMemcpyHostToDevice, ls);
+    if (e == cudaSuccess) e = upload_cores(md, core, ls);
     if (src.fan && src.root) {
       if (e == cudaSuccess) e = cudaStreamSynchronize(ls);   // the peers copy from this device's buffers
       src.fan->publish(e == cudaSuccess ? 1 : -1, md->device, md->d_xs, md->d_core);
