@@ -375,6 +375,43 @@ def test_device_resident_entry_point_matches_host_path():
         md.close()
 
 
+def test_device_api_two_stream_chunks_match_host_path():
+    """ttirt_sample_device on a call of several chunks: the chunks alternate two workspaces on two internal streams forked
+    from / joined into the caller's stream.  Results equal the host pipeline's bit for bit, work issued on the caller's
+    stream afterwards sees them (the join), and a second call on ANOTHER stream reuses the workspaces safely."""
+    torch = pytest.importorskip("torch")
+    d, n, r = 3, 65, 64
+    ns, xs, rk, c = synth.make_tt(d, n, r, seed=81)
+    M = 5 * (1 << 12) + 7
+    q = synth.make_q(M, d, seed=82)
+    lib = tt_irt.load_library()
+    md = tt_irt.Model(ns, xs, rk, c)
+    try:
+        Zh, lh, ih = md.sample(q, want_idx=True)
+        qd = torch.from_numpy(np.ascontiguousarray(q.T)).cuda()
+        lib.ttirt_set_chunk(1 << 12)
+        try:
+            outs = []
+            for _ in range(2):
+                st = torch.cuda.Stream()
+                zd = torch.full((d, M), float("nan"), dtype=torch.float64, device="cuda")
+                ld_ = torch.full((M,), float("nan"), dtype=torch.float64, device="cuda")
+                idd = torch.full((d, M), -1, dtype=torch.int32, device="cuda")
+                with torch.cuda.stream(st):
+                    md.sample_device(M, qd.data_ptr(), M, zd.data_ptr(), M, ld_.data_ptr(), idd.data_ptr(), tt_irt.MODE_FAST, st.cuda_stream)
+                    zsum = zd.sum()            # enqueued on the caller's stream right behind the call: must see every chunk
+                outs.append((st, zd, ld_, idd, zsum))
+            for st, zd, ld_, idd, zsum in outs:
+                st.synchronize()
+                assert np.array_equal(zd.cpu().numpy().T, Zh) and np.array_equal(ld_.cpu().numpy(), lh)
+                assert np.array_equal(idd.cpu().numpy().T, ih)
+                assert float(zsum.item()) == float(torch.from_numpy(np.ascontiguousarray(Zh.T)).cuda().sum().item())
+        finally:
+            lib.ttirt_set_chunk(0)
+    finally:
+        md.close()
+
+
 def test_failed_workspace_allocation_is_recoverable(oracle_mod):
     """A caller-held model whose scratch allocation fails (absurd chunk) must come back empty, not half-built: the next,
     ordinary call allocates afresh and is correct (no kernels on null scratch, no sticky CUDA error)."""
