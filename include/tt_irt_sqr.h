@@ -41,8 +41,8 @@ extern "C" {
  *
  * The reference's `keyboard` debugger stops (:17-19, :151-154) have no counterpart: seeds outside [0, 1] are not
  * checked.  On any failure one line goes to stderr and z / lFapp are NaN-filled; the host process is never aborted.
- * Environment: TTIRT_DEVICE=<first ordinal> (default 0), TTIRT_DEVICES=<count>|all (default 1: rows sharded over that many
- * GPUs), TTIRT_SQR_CHUNK=<samples per chunk> (default 2^19 / 2^18 by shape class), TTIRT_CACHE=0 (no pooling of device blocks), TTIRT_TRACE=1.
+ * Environment: TTIRT_DEVICE=<first ordinal> (default 0), TTIRT_DEVICES=<count>|all|auto (default auto, as for tt_irt1: one
+ * device per 2^22 seed points; rows sharded contiguously over that many GPUs), TTIRT_SQR_CHUNK=<samples per chunk> (default 2^19 / 2^18 by shape class), TTIRT_CACHE=0 (no pooling of device blocks), TTIRT_TRACE=1.
  */
 TTIRT_API void tt_irt_sqr(TTIRT_INT d, TTIRT_INT *n, TTIRT_INT nxs, double *xs, TTIRT_INT *ttrank, double *ttcore,
                           TTIRT_INT M, TTIRT_INT D, double *q, double *z, double *lFapp);
