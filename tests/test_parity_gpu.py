@@ -653,6 +653,74 @@ def test_random_ragged_shapes(oracle_mod, seed):
         md.close()
 
 
+WIDE_SHAPES = [
+    # ranks (d + 1), grid sizes (d), M, cores
+    ((1, 96, 96, 96, 1), (129, 129, 129, 129), 3000, "uniform"),        # r > 64 and n > 72: several 64-row tiles per interval
+    ((1, 128, 128, 1), (33, 33, 33), 2500, "uniform"),                  # wide ranks on a small grid (two column tiles)
+    ((1, 6, 6, 6, 1), (80, 300, 80, 80), 4000, "uniform"),              # small ranks on wide grids (five column tiles of the pdf)
+    ((1, 70, 130, 9, 1), (12, 90, 75, 5), 2000, "uniform"),             # ragged: ranks and grids not multiples of 8, K not a multiple of 16
+    ((1, 65, 67, 1), (73, 2, 74), 1500, "normal"),                      # signed cores (the fabs of :105), a two-point grid in the middle
+]
+
+
+@pytest.mark.parametrize("ranks,ns,M,cores", WIDE_SHAPES)
+def test_wide_shapes_strict_bitexact_and_fast_within_protocol(oracle_mod, ranks, ns, M, cores):
+    """Shapes beyond the fused transition kernel (r > 64 or n > 72; the reference serves any shape on one path,
+    tt_irt1_int32.c:41-53) run the unfused DMMA path of csrc/ttirt_wide.cu in fast mode: interval indices equal to the
+    oracle's, Z and lPz inside the protocol; strict mode stays bit-exact; seeds 0 and 1 included."""
+    rk = np.array(ranks, dtype=np.int64)
+    ns = np.array(ns, dtype=np.int64)
+    d = ns.size
+    rng = np.random.default_rng(int(rk.sum() + ns.sum()))
+    xs = np.concatenate([np.sort(rng.uniform(-1.5, 2.5, size=n)) for n in ns])
+    size = int((rk[:-1] * ns * rk[1:]).sum())
+    c = rng.random(size) if cores == "uniform" else rng.standard_normal(size)
+    q = synth.make_q(M, d, seed=5)
+    q[0, :] = 0.0; q[1, :] = 1.0
+    Zo, lo, io, kap, gap, cond, lsens = _oracle(oracle_mod, ns, xs, rk, c, q)
+    md = tt_irt.Model(ns, xs, rk, c)
+    try:
+        Zs, ls, isx = md.sample(q, mode=tt_irt.MODE_STRICT, want_idx=True)
+        assert np.array_equal(Zs, Zo) and np.array_equal(isx, io)
+        l0 = tt_irt.kernel_launches()
+        Zf, lf, ifx = md.sample(q, mode=tt_irt.MODE_FAST, want_idx=True)
+        launches = tt_irt.kernel_launches() - l0
+        stats, fails = oracle_mod.parity.compare(Zf, lf, ifx, Zo, lo, io, cond, gap, lsens=lsens)
+        assert not fails, (fails, stats)
+        if cores == "uniform":
+            assert stats["idx_flips"] == 0, stats
+        # stage 0, then scatter + update + pdf + tail per further dimension, per chunk: the wide path ran, not the strict kernel
+        assert launches % (1 + 4 * (d - 1)) == 0 and launches >= 1 + 4 * (d - 1), launches
+        # a second call gives the same bits (no state carried between calls, scratch reuse is clean)
+        Zf2, lf2, ifx2 = md.sample(q, mode=tt_irt.MODE_FAST, want_idx=True)
+        assert np.array_equal(Zf, Zf2) and np.array_equal(lf, lf2) and np.array_equal(ifx, ifx2)
+    finally:
+        md.close()
+
+
+def test_wide_path_rows_and_chunks_do_not_change_a_bit(oracle_mod):
+    """Wide path through the drop-in symbol: the result of a row does not depend on the batch it arrives in (samples are
+    independent, tt_irt1_int32.c:88-181) nor on the chunking of the host pipeline."""
+    ns, xs, rk, c = synth.make_tt(4, 90, 80, seed=31)
+    M = 70000
+    q = synth.make_q(M, 4, seed=32)
+    f = tt_irt.TTTensor(ns, rk, c)
+    Z, l = tt_irt.tt_irt1(q, f, xs)
+    assert np.isfinite(l).all()
+    rows = np.concatenate([np.arange(0, 200), np.arange(M - 77, M)])
+    Zr, lr = tt_irt.tt_irt1(np.asfortranarray(q[rows]), f, xs)
+    assert np.array_equal(Zr, Z[rows]) and np.array_equal(lr, l[rows])
+    Zo, lo, io, kap, gap, cond, lsens = _oracle(oracle_mod, ns, xs, rk, c, np.asfortranarray(q[rows]))
+    stats, fails = oracle_mod.parity.compare(Zr, lr, None, Zo, lo, None, cond, gap, lsens=lsens)
+    assert not fails, (fails, stats)
+    tt_irt.load_library().ttirt_set_chunk(1 << 14)
+    try:
+        Zc, lc = tt_irt.tt_irt1(q, f, xs)
+    finally:
+        tt_irt.load_library().ttirt_set_chunk(0)
+    assert np.array_equal(Zc, Z) and np.array_equal(lc, l)
+
+
 @pytest.mark.parametrize("M,extra", [(5000, 7), (400000, 3)])
 def test_host_pipeline_with_padded_leading_dimension(M, extra):
     """ttirt_sample_host on column-major arrays whose leading dimension exceeds M (a row block of a larger matrix):

@@ -189,7 +189,33 @@ cudaError_t walk_pack(int cls, const DimInfo *d_dims, int d, const double *xs, c
                       const double *p0, const double *cdf0, double *pack, cudaStream_t st);
 cudaError_t launch_walk(int cls, const WalkArgs &a, int sm_count, cudaStream_t st);
 
-// fast-path shape classes: (rank tiles of 8, grid tiles of 8)
+// One dimension step k -> k+1 of the wide path (ttirt_wide.cu: ranks / grids beyond the fused transition kernel): grouped
+// DMMA GEMM for the interface update, DMMA GEMM for the weighted conditional pdf, one-thread-per-sample tail.
+struct WideArgs {
+  const double *core;        // core_k, column-major r0 x n0 x r1
+  const double *pnext;       // P_{k+1} with column j scaled by node_weight(j), column-major r1 x n1
+  const double *xnext, *ihnext, *rwnext, *hrnext;   // grid of dimension k+1 and its tables (wide_tables)
+  int r0, n0, r1, n1;
+  int last, rows;
+  const double *Fin;         // left-interface rows of dimension k (rows x ldf, zero-padded to r0 rounded to 8)
+  double *Fout;              // ... of dimension k+1 (a different buffer)
+  int ldf;
+  double *pb;                // n1 x rows scratch: weighted signed pdf, node-major
+  const int *perm, *hist_cur;
+  int *idx;
+  double *w1, *w2, *lp, *lpd;
+  int *lpe;
+  const double *q;           // column k+1 of q for this chunk
+  double *z;
+  int32_t *idx_out;
+  double *lpz;
+  int *hist_next;
+};
+cudaError_t launch_wide_step(const WideArgs &a, cudaStream_t st);   // three launches
+cudaError_t wide_tables(const DimInfo *d_dims, int d, const double *xs, double *ih, double *rw, double *hr, cudaStream_t st);
+constexpr int kWideClass = 3;
+
+// fast-path shape classes: 0 - 2 the fused transition kernel (rank tiles of 8, grid tiles of 8), 3 the wide path
 int fast_class_for(int rmax, int nmax);             // -1: shape outside the fast path
 cudaError_t launch_transition(int cls, const TransArgs &a, int sm_count, cudaStream_t st);
 cudaError_t fast_init(int device);                  // opt in to large dynamic shared memory

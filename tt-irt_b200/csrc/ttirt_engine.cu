@@ -85,6 +85,15 @@ static int64_t default_chunk() {
   return (int64_t)1 << 20;
 }
 
+// wide path: per-sample scratch is two interface rows and one pdf column (16 r + 8 n bytes and change): chunks of at most
+// ~1.5 GB of it, at least 2^14 rows (the GEMMs bound this path, not launches)
+static int64_t wide_chunk_for(int64_t rmax, int64_t nmax) {
+  const int64_t per_row = 16 * ((rmax + 7) & ~(int64_t)7) + 8 * nmax + 64;
+  int64_t c = (int64_t)1 << 20;
+  while (c > ((int64_t)1 << 14) && c * per_row > ((int64_t)3 << 29)) c >>= 1;
+  return c;
+}
+
 // ------------------------------------------------------------------------------------------------
 // model
 // ------------------------------------------------------------------------------------------------
@@ -99,6 +108,8 @@ struct Workspace {
   double *w1 = nullptr, *w2 = nullptr, *lp = nullptr, *lpd = nullptr;
   int *lpe = nullptr;
   int *hist = nullptr;   // d x nbpad
+  double *F2 = nullptr;  // wide path: second interface buffer (cap x ldf), weighted pdf (nmax x cap)
+  double *pw = nullptr;
   // strict scratch
   double *left = nullptr, *pbuf = nullptr, *cbuf = nullptr;
   // host-mode staging
@@ -130,6 +141,7 @@ struct ttirt_model {
   double *d_xs = nullptr, *d_core = nullptr, *d_pk = nullptr, *d_pkw = nullptr, *d_marg = nullptr;
   int64_t sum_pkw = 0;
   double *d_p0 = nullptr, *d_cdf0 = nullptr;
+  double *d_wtab = nullptr;      // wide path: 1 / cell width, 1 / node weight, h_{j-1} / node weight (3 x sum_x, the layout of xs)
   DimInfo *d_dims = nullptr;
   // model_load() enqueues upload, sweep and operand packing on load_stream and records `loaded`; the host pipeline lets its
   // slot streams wait for that event instead of synchronising the device (a small call is all latency)
@@ -167,7 +179,7 @@ static void ws_drop_graphs(Workspace &w) {
 static void ws_free(Workspace &w) {
   ws_drop_graphs(w);
   cudaFree(w.F); cudaFree(w.idx); cudaFree(w.perm); cudaFree(w.w1); cudaFree(w.w2); cudaFree(w.lp); cudaFree(w.lpd); cudaFree(w.lpe);
-  cudaFree(w.hist);
+  cudaFree(w.hist); cudaFree(w.F2); cudaFree(w.pw);
   cudaFree(w.left); cudaFree(w.pbuf); cudaFree(w.cbuf);
   cudaFree(w.q); cudaFree(w.z); cudaFree(w.lpz); cudaFree(w.idx_out);
   if (w.stream) cudaStreamDestroy(w.stream);
@@ -188,6 +200,10 @@ static int ws_alloc(ttirt_model *md, Workspace &w, int64_t cap, bool s, bool h, 
     CK(cudaMalloc(&w.lpd, sizeof(double) * cap));
     CK(cudaMalloc(&w.lpe, sizeof(int) * cap));
     CK(cudaMalloc(&w.hist, sizeof(int) * 2 * d * md->nbpad));   // d interval histograms, then d sets of scatter cursors
+    if (md->fast_cls == kWideClass) {
+      CK(cudaMalloc(&w.F2, sizeof(double) * cap * md->ldf));
+      CK(cudaMalloc(&w.pw, sizeof(double) * cap * md->nmax));
+    }
   }
   if (s) {
     CK(cudaMalloc(&w.left, sizeof(double) * 2 * md->rmax * cap));
@@ -523,7 +539,7 @@ extern "C" void ttirt_model_destroy(ttirt_model *md) {
   cudaFreeHost(md->core_stage);
   for (auto &p : md->prof_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   cudaFree(md->d_xs); cudaFree(md->d_core); cudaFree(md->d_pk); cudaFree(md->d_pkw); cudaFree(md->d_marg);
-  cudaFree(md->d_p0); cudaFree(md->d_cdf0); cudaFree(md->d_dims); cudaFree(md->d_walk);
+  cudaFree(md->d_p0); cudaFree(md->d_cdf0); cudaFree(md->d_dims); cudaFree(md->d_walk); cudaFree(md->d_wtab);
   delete md;
 }
 
@@ -682,6 +698,10 @@ static int model_load_body(ttirt_model *md, const CoreSource &src) {
     weight_p_kernel<<<dim3(8, (unsigned)d), 256, 0, ls>>>(md->d_dims, (int)d, md->d_xs, md->d_pk, md->d_pkw);
     LAUNCHED();
   }
+  if (md->fast_cls == kWideClass && d > 1) {
+    CK(wide_tables(md->d_dims, (int)d, md->d_xs, md->d_wtab, md->d_wtab + md->sum_x, md->d_wtab + 2 * md->sum_x, ls));
+    LAUNCHED();
+  }
   CK(cudaGetLastError());
   CK(cudaEventRecord(md->loaded, ls));
   // The model is complete when this returns.  (Letting the pipeline's slot streams wait for `loaded` instead was measured
@@ -762,6 +782,7 @@ static int model_build(ttirt_model *md, const int64_t *n, const int64_t *rk, con
   CK(cudaMalloc(&md->d_p0, sizeof(double) * n[0]));
   CK(cudaMalloc(&md->d_cdf0, sizeof(double) * n[0]));
   CK(cudaMalloc(&md->d_dims, sizeof(DimInfo) * d));
+  if (md->fast_cls == kWideClass) CK(cudaMalloc(&md->d_wtab, sizeof(double) * 3 * ox));
   CK(cudaMemcpy(md->d_dims, md->dims.data(), sizeof(DimInfo) * d, cudaMemcpyHostToDevice));
   md->sum_x = ox; md->sum_c = oc;
   CK(cudaStreamCreateWithFlags(&md->load_stream, cudaStreamNonBlocking));
@@ -811,7 +832,7 @@ extern "C" int ttirt_model_get_sweep(const ttirt_model *md, double *pk_out, doub
 // kernels in one chunk's sequence (what a graph replay launches)
 static int64_t g_launches_per_graph(const ttirt_model *md, int mode) {
   if (mode == TTIRT_MODE_STRICT || md->fast_cls < 0 || md->walk_cls >= 0) return 1;
-  return 1 + 2 * (md->d - 1);
+  return 1 + (md->fast_cls == kWideClass ? 4 : 2) * (md->d - 1);
 }
 
 static int enqueue_chunk(ttirt_model *md, Workspace &w, int64_t rows, const double *q, int64_t ldq, double *z, int64_t ldz,
@@ -848,16 +869,6 @@ static int enqueue_chunk(ttirt_model *md, Workspace &w, int64_t rows, const doub
     bin_scatter_kernel<<<(unsigned)((rows + 1023) / 1024), 256, sizeof(int) * (3 * nb + 1), st>>>(
         w.idx, (int)rows, nb, w.hist + (size_t)k * nbpad, w.hist + (size_t)(d + k) * nbpad, w.perm);
     LAUNCHED();
-    TransArgs a;
-    a.core = md->d_core + dk.off_c; a.pnext = md->d_pkw + dn.off_pw; a.xnext = md->d_xs + dn.off_x;
-    a.r0 = dk.r0; a.n0 = dk.n; a.r1 = dk.r1; a.n1 = dn.n;
-    a.async_ok = (reinterpret_cast<uintptr_t>(a.core) & 15) == 0;
-    a.last = (k + 1 == d - 1); a.rows = (int)rows; a.F = w.F; a.ldf = md->ldf;
-    a.perm = w.perm; a.hist_cur = w.hist + (size_t)k * nbpad;
-    a.idx = w.idx; a.w1 = w.w1; a.w2 = w.w2; a.lp = w.lp; a.lpd = w.lpd; a.lpe = w.lpe;
-    a.q = q + ldq * (k + 1); a.z = z + ldz * (k + 1);
-    a.idx_out = idx_out ? idx_out + ldz * (k + 1) : nullptr;
-    a.lpz = lpz; a.hist_next = w.hist + (size_t)(k + 1) * nbpad;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (md->profile) {
       if (md->prof_used == md->prof_events.size()) {
@@ -870,6 +881,35 @@ static int enqueue_chunk(ttirt_model *md, Workspace &w, int64_t rows, const doub
       md->prof_flops += (double)rows * (4.0 * dk.r0 * dk.r1 + 2.0 * dk.r1 * dn.n);
       CK(cudaEventRecord(e0, st));
     }
+    if (md->fast_cls == kWideClass) {
+      // wide shapes: update GEMM (F -> F2 or back), pdf GEMM, tail (ttirt_wide.cu); stage 0 left the first rows in w.F
+      WideArgs wa;
+      wa.core = md->d_core + dk.off_c; wa.pnext = md->d_pkw + dn.off_pw;
+      wa.xnext = md->d_xs + dn.off_x; wa.ihnext = md->d_wtab + dn.off_x; wa.rwnext = md->d_wtab + md->sum_x + dn.off_x;
+      wa.hrnext = md->d_wtab + 2 * md->sum_x + dn.off_x;
+      wa.r0 = dk.r0; wa.n0 = dk.n; wa.r1 = dk.r1; wa.n1 = dn.n;
+      wa.last = (k + 1 == d - 1); wa.rows = (int)rows;
+      wa.Fin = (k & 1) ? w.F2 : w.F; wa.Fout = (k & 1) ? w.F : w.F2; wa.ldf = md->ldf;
+      wa.pb = w.pw; wa.perm = w.perm; wa.hist_cur = w.hist + (size_t)k * nbpad;
+      wa.idx = w.idx; wa.w1 = w.w1; wa.w2 = w.w2; wa.lp = w.lp; wa.lpd = w.lpd; wa.lpe = w.lpe;
+      wa.q = q + ldq * (k + 1); wa.z = z + ldz * (k + 1);
+      wa.idx_out = idx_out ? idx_out + ldz * (k + 1) : nullptr;
+      wa.lpz = lpz; wa.hist_next = w.hist + (size_t)(k + 1) * nbpad;
+      CK(launch_wide_step(wa, st));
+      LAUNCHED(); LAUNCHED(); LAUNCHED();
+      if (e1) CK(cudaEventRecord(e1, st));
+      continue;
+    }
+    TransArgs a;
+    a.core = md->d_core + dk.off_c; a.pnext = md->d_pkw + dn.off_pw; a.xnext = md->d_xs + dn.off_x;
+    a.r0 = dk.r0; a.n0 = dk.n; a.r1 = dk.r1; a.n1 = dn.n;
+    a.async_ok = (reinterpret_cast<uintptr_t>(a.core) & 15) == 0;
+    a.last = (k + 1 == d - 1); a.rows = (int)rows; a.F = w.F; a.ldf = md->ldf;
+    a.perm = w.perm; a.hist_cur = w.hist + (size_t)k * nbpad;
+    a.idx = w.idx; a.w1 = w.w1; a.w2 = w.w2; a.lp = w.lp; a.lpd = w.lpd; a.lpe = w.lpe;
+    a.q = q + ldq * (k + 1); a.z = z + ldz * (k + 1);
+    a.idx_out = idx_out ? idx_out + ldz * (k + 1) : nullptr;
+    a.lpz = lpz; a.hist_next = w.hist + (size_t)(k + 1) * nbpad;
     CK(launch_transition(md->fast_cls, a, md->sm_count, st));
     LAUNCHED();
     if (e1) CK(cudaEventRecord(e1, st));
@@ -948,6 +988,7 @@ extern "C" int ttirt_sample_device(ttirt_model *md, int64_t M, const double *d_q
   if (g_chunk.load() <= 0 && getenv("TTIRT_CHUNK") == nullptr && !strict) {
     if (md->walk_cls >= 0) want = (int64_t)1 << 24;
     else if (md->fast_cls == 2) want = (int64_t)1 << 22;
+    else if (md->fast_cls == kWideClass) want = wide_chunk_for(md->rmax, md->nmax);
   }
   const int64_t chunk = std::min<int64_t>(M, want);
   const int64_t nchunks = (M + chunk - 1) / chunk;
@@ -1112,8 +1153,9 @@ static int stage_ensure(ttirt_model *md, int slot, int64_t rows, bool need_q, bo
 // (straight into pinned caller memory, or into the slot's pinned buffer from which a drain thread copies into the
 // caller's pageable arrays while the next chunks compute).
 // chunk size of the host pipeline for a model of fast-path class `cls` and `rows` rows per device
-static int64_t host_chunk_for(int cls, bool strict, bool walk, int64_t rows) {
+static int64_t host_chunk_for(int cls, bool strict, bool walk, int64_t rows, int64_t rmax, int64_t nmax) {
   int64_t chunk = default_chunk();
+  if (g_chunk.load() <= 0 && getenv("TTIRT_CHUNK") == nullptr && !strict && cls == kWideClass) chunk = wide_chunk_for(rmax, nmax);
   // light shapes (r <= 16: 2^17 rows, r <= 32: 2^19 rows per chunk): a chunk computes in about a millisecond, so the pipeline is cut finer
   // (shorter fill and drain, copies and kernels of neighbouring chunks overlap) and every chunk is a graph replay
   if (g_chunk.load() <= 0 && getenv("TTIRT_CHUNK") == nullptr && !strict && cls >= 0 && cls <= 1)
@@ -1134,7 +1176,7 @@ static int sample_host_rows(ttirt_model *md, int64_t m_begin, int64_t m_end, con
   const bool walk = !strict && md->walk_cls >= 0;
   // the chunks of this call: a private queue over [m_begin, m_end), or the queue shared by the devices of the call
   ChunkQueue own;
-  own.base = m_begin; own.end = m_end; own.chunk = host_chunk_for(md->fast_cls, strict, walk, M);
+  own.base = m_begin; own.end = m_end; own.chunk = host_chunk_for(md->fast_cls, strict, walk, M, md->rmax, md->nmax);
   // (metric shape, pinned arrays: 41.35 -> 42.05 M samples/s with two levels; TTIRT_RAMP=<levels>, 0 turns it off)
   static const int ramp_levels = getenv("TTIRT_RAMP") ? atoi(getenv("TTIRT_RAMP")) : 2;
   if (!shared && !strict && md->fast_cls == 2) own.ramp(ramp_levels);   // (r <= 32 class measured: 52.6 against 50.8 ms per call, left uniform)
@@ -1422,7 +1464,7 @@ static int run_host_impl(int64_t d, const int64_t *n, const double *xs, const in
   queue.base = 0; queue.end = M;
   {
     const int cls = fast_class_for((int)rmax, (int)nmax);
-    queue.chunk = host_chunk_for(cls, mode == TTIRT_MODE_STRICT || cls < 0, false, M / n_devices);
+    queue.chunk = host_chunk_for(cls, mode == TTIRT_MODE_STRICT || cls < 0, false, M / n_devices, rmax, nmax);
     // four or more devices share the host's memory path: finer chunks even out what the faster and the slower devices
     // take and shorten the tail (8 x B200, M = 2^26: 237 -> 246 M samples/s)
     if (balance && n_devices >= 4 && cls == 2 && mode != TTIRT_MODE_STRICT && g_chunk.load() <= 0 && getenv("TTIRT_CHUNK") == nullptr &&

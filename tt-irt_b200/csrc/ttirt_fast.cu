@@ -16,6 +16,8 @@
 // Work decomposition: (1) and (2) run in eight MMA warps, each owning 16 samples per tile (two 8-row MMA
 // tiles); (3) runs in four tail warps that receive the pdf tiles through shared memory.  The MMA warps only meet
 // when their CTA moves to the next interval bin and restages a slab.
+#include <cstdlib>
+
 #include "ttirt_common.cuh"
 
 namespace ttirt {
@@ -822,6 +824,9 @@ int fast_class_for(int rmax, int nmax) {
   if (rmax <= 16 && nmax <= 24) return 0;
   if (rmax <= 32 && nmax <= 40) return 1;
   if (rmax <= 64 && nmax <= 72) return 2;
+  // anything larger: the unfused DMMA path of ttirt_wide.cu (TTIRT_WIDE=0: the strict kernel serves these shapes, as before)
+  static const bool wide_on = !(getenv("TTIRT_WIDE") && atoi(getenv("TTIRT_WIDE")) == 0);
+  if (wide_on && rmax <= 1024 && nmax <= 1024) return kWideClass;
   return -1;
 }
 
