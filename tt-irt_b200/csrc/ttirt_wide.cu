@@ -133,18 +133,19 @@ __global__ void __launch_bounds__(W_THREADS, 3) wide_gemm_kernel(const WideGemmA
   const bool bcol_ok = bcol < a.N;
   const int nks = (a.K + W_KS - 1) / W_KS;
   const int nsl = (UPDATE ? 2 : 1) * nks;
+  // The loaded values stay untouched in registers until they are stored (the interpolation weight is applied there): an
+  // instruction that consumes them here would make the warp wait for the loads before its DMMA loop instead of after it.
   double2 ra[4], rb[4];
   auto load_slice = [&](int s) {
     const int p = (UPDATE && s >= nks) ? 1 : 0;
     const int k0 = (s - p * nks) * W_KS + 8 * h;
-    const double scale = sc[p][srow];
     const double *bp = a.B + (UPDATE ? (int64_t)(bin + p) * a.K : 0) + (int64_t)bcol * a.ldb;
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       const int kk = k0 + 2 * ((u + srow) & 3);
       double2 v = make_double2(0.0, 0.0);
       if (arow != nullptr && kk < K8) v = *reinterpret_cast<const double2 *>(arow + kk);
-      ra[u] = make_double2(v.x * scale, v.y * scale);
+      ra[u] = v;
       double bx = 0.0, by = 0.0;
       if (bcol_ok) {
         if (kk < a.K) bx = __ldg(bp + kk);
@@ -153,17 +154,21 @@ __global__ void __launch_bounds__(W_THREADS, 3) wide_gemm_kernel(const WideGemmA
       rb[u] = make_double2(bx, by);
     }
   };
-  auto store_slice = [&]() {
+  auto store_slice = [&](int s) {
+    const double scale = UPDATE ? sc[s >= nks ? 1 : 0][srow] : 1.0;
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       const int off = srow * W_PITCH + 8 * h + 2 * ((u + srow) & 3);
-      *reinterpret_cast<double2 *>(As + off) = ra[u];
+      *reinterpret_cast<double2 *>(As + off) = UPDATE ? make_double2(ra[u].x * scale, ra[u].y * scale) : ra[u];
       *reinterpret_cast<double2 *>(Bs + off) = rb[u];
     }
   };
 
   const int g = lane >> 2, t = lane & 3, wr = warp >> 1, wc = warp & 1;
-  const bool warp_has_rows = 32 * wr < nv;
+  bool warp_has_rows = 32 * wr < nv;
+  // 8-column groups of this warp that hold output columns at all (the last column tile of a 2^p + 1 grid holds one column)
+  const int jmax = min(4, max(0, ((UPDATE ? ((a.N + 7) & ~7) : a.N) - (c0 + 32 * wc) + 7) >> 3));
+  if (jmax == 0) warp_has_rows = false;
   double acc[4][4][2];
 #pragma unroll
   for (int i = 0; i < 4; i++)
@@ -173,7 +178,7 @@ __global__ void __launch_bounds__(W_THREADS, 3) wide_gemm_kernel(const WideGemmA
   load_slice(0);
   for (int s = 0; s < nsl; s++) {
     __syncthreads();          // every warp is done with the previous slice
-    store_slice();
+    store_slice(s);
     __syncthreads();
     if (s + 1 < nsl) load_slice(s + 1);
     if (warp_has_rows) {
@@ -184,14 +189,26 @@ __global__ void __launch_bounds__(W_THREADS, 3) wide_gemm_kernel(const WideGemmA
         for (int i = 0; i < 4; i++) av[i] = *reinterpret_cast<const double2 *>(As + (32 * wr + 8 * i + g) * W_PITCH + 8 * jb + 2 * t);
 #pragma unroll
         for (int j = 0; j < 4; j++) bv[j] = *reinterpret_cast<const double2 *>(Bs + (32 * wc + 8 * j + g) * W_PITCH + 8 * jb + 2 * t);
+        if (jmax == 4) {
 #pragma unroll
-        for (int i = 0; i < 4; i++)
+          for (int i = 0; i < 4; i++)
 #pragma unroll
-          for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], av[i].x, bv[j].x);
+            for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], av[i].x, bv[j].x);
 #pragma unroll
-        for (int i = 0; i < 4; i++)
+          for (int i = 0; i < 4; i++)
 #pragma unroll
-          for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], av[i].y, bv[j].y);
+            for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], av[i].y, bv[j].y);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 3; j++) {
+            if (j < jmax) {
+#pragma unroll
+              for (int i = 0; i < 4; i++) dmma884(acc[i][j][0], acc[i][j][1], av[i].x, bv[j].x);
+#pragma unroll
+              for (int i = 0; i < 4; i++) dmma884(acc[i][j][0], acc[i][j][1], av[i].y, bv[j].y);
+            }
+          }
+        }
       }
     }
   }
