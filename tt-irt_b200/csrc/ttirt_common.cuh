@@ -212,6 +212,7 @@ struct WideArgs {
   int *hist_next;
 };
 cudaError_t launch_wide_step(const WideArgs &a, cudaStream_t st);   // three launches
+cudaError_t wide_init(int device);                  // opt in to the GEMM's dynamic shared memory
 cudaError_t wide_tables(const DimInfo *d_dims, int d, const double *xs, double *ih, double *rw, double *hr, cudaStream_t st);
 constexpr int kWideClass = 3;
 

@@ -762,6 +762,7 @@ static int model_build(ttirt_model *md, const int64_t *n, const int64_t *rk, con
   if (prop.major < 10) return fail("device %d (%s, sm_%d%d) is not a Blackwell B200-class GPU", md->device, prop.name, prop.major, prop.minor);
   md->sm_count = prop.multiProcessorCount;
   CK(fast_init(md->device));
+  if (md->fast_cls == kWideClass) CK(wide_init(md->device));
   // small uniform-rank TTs: one persistent kernel for the whole walk (TTIRT_WALK=0: per-dimension path, for comparison)
   {
     static const bool walk_on = !(getenv("TTIRT_WALK") && atoi(getenv("TTIRT_WALK")) == 0);

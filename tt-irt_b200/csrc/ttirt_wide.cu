@@ -19,6 +19,8 @@
 //                                (ttirt_walk.cu), the nodes streamed from HBM instead of held in registers.
 // HBM traffic per sample and dimension: F in (once per column tile) + F' out + V out + V in twice ~ 8 (3 r + 3 n) bytes
 // against 4 r^2 + 2 r n flops: FP64 tensor pipe bound from r ~ 48 on.
+#include <type_traits>
+
 #include "ttirt_common.cuh"
 
 namespace ttirt {
@@ -40,6 +42,24 @@ constexpr int W_TM = 64, W_TN = 64, W_KS = 16, W_THREADS = 128;
 // row pitch of the staged operands in doubles: 24 = 8 (mod 16), so the LDS.128 fragment loads of a quarter warp (rows g, g+1,
 // k pairs 2t) fall into eight different 16-byte slots of the 128-byte bank window: conflict-free without a swizzle
 constexpr int W_PITCH = W_KS + 8;
+#ifndef TTIRT_WIDE_CTAS
+#define TTIRT_WIDE_CTAS 3
+#endif
+#ifndef TTIRT_WIDE_STAGES
+#define TTIRT_WIDE_STAGES 2
+#endif
+constexpr int W_STAGES = TTIRT_WIDE_STAGES, W_CTAS = TTIRT_WIDE_CTAS;
+constexpr size_t W_SMEM = sizeof(double) * W_STAGES * (W_TM + W_TN) * W_PITCH;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// cp.async (LDGSTS) of BYTES (8 or 16) global -> shared; !valid: zero-fill (src-size 0, src still a mapped address)
+template <int BYTES>
+__device__ __forceinline__ void cp_async_zfill(void *dst, const void *src, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(smem_u32(dst)), "l"(src), "n"(BYTES), "r"(valid ? BYTES : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 struct WideGemmArgs {
   const double *A;        // rows of the A operand: A + id * lda, valid and zero-padded up to K rounded to 8
@@ -52,6 +72,7 @@ struct WideGemmArgs {
   const double *B;        // B(kk, c) = B[kk + c * ldb]; UPDATE: phase p of interval b starts at B + (b + p) * K
   int64_t ldb;
   int K, N;               // contraction length per phase, output columns
+  int ncol;               // column tiles (grid = row tiles x ncol, column tile fastest)
   double *C;              // UPDATE: C[id * ldc + c] for c < N rounded to 8; else C[c * ldc + position] for c < N
   int64_t ldc;
 };
@@ -59,15 +80,17 @@ struct WideGemmArgs {
 // The contraction index is consumed in a permuted order on BOTH operands (lane t of a quad takes k = 8j + 2t and 8j + 2t + 1
 // for the two k-steps of an 8-block), so one LDS.128 per operand feeds two DMMAs.
 template <bool UPDATE>
-__global__ void __launch_bounds__(W_THREADS, 3) wide_gemm_kernel(const WideGemmArgs a) {
-  __shared__ __align__(16) double As[W_TM * W_PITCH];
-  __shared__ __align__(16) double Bs[W_TN * W_PITCH];
+__global__ void __launch_bounds__(W_THREADS, W_CTAS) wide_gemm_kernel(const WideGemmArgs a) {
+  extern __shared__ __align__(16) unsigned char wide_smem[];
+  double *As = reinterpret_cast<double *>(wide_smem);          // W_STAGES stages of the A tile, then of the B tile
+  double *Bs = As + W_STAGES * W_TM * W_PITCH;
   __shared__ double sc[2][W_TM];
   __shared__ int ids[W_TM];
   __shared__ int tile_info[3];   // interval, first (sorted) row, valid rows (0: no such tile)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int T = blockIdx.x, c0 = blockIdx.y * W_TN;
+  // column tiles of one row tile are neighbours in the grid: they run at the same time and share the tile's A rows in L2
+  const int T = (int)(blockIdx.x / (unsigned)a.ncol), c0 = (int)(blockIdx.x % (unsigned)a.ncol) * W_TN;
 
   // ---- which rows: tile T of the chunk.  UPDATE: tiles are numbered interval by interval (none straddles two), the warp
   //      scans the histogram for the interval that holds tile T ----
@@ -122,96 +145,119 @@ __global__ void __launch_bounds__(W_THREADS, 3) wide_gemm_kernel(const WideGemmA
   }
   __syncthreads();
 
-  // ---- staging: thread (srow, h) moves 8 consecutive k of row srow of the A tile and of column srow of the B tile, as four
-  //      16-byte pieces in the rotated order (u + srow) & 3, which makes the shared-memory stores of a quarter warp
-  //      conflict-free as well ----
+  // ---- staging by cp.async (LDGSTS) into a ring of W_STAGES shared-memory stages, one slice ahead of the DMMA loop.
+  //      Written for instruction count: next to a DMMA stream every other instruction of the sub-partition waits for a gap
+  //      (ttirt_fast.cu), so the per-slice address arithmetic is a handful of adds on bases prepared here.
+  //      A: thread (srow, h) moves 8 consecutive k of row srow as four 16-byte pieces (rows are 64-byte aligned);
+  //      B: 8-byte pieces (a slab column may start at an odd element), lanes along k, so that a warp instruction reads two
+  //         128-byte runs; a thread's eight columns are a constant byte stride apart.
+  //      Pieces outside the operands are zero-filled (src-size 0, any mapped address). ----
   const int srow = tid >> 1, h = tid & 1;
   const int my_id = ids[srow];
-  const double *arow = my_id >= 0 ? a.A + (size_t)my_id * a.lda : nullptr;
   const int K8 = (a.K + 7) & ~7;
-  const int bcol = c0 + srow;
-  const bool bcol_ok = bcol < a.N;
+  const double *a_src = a.A + (size_t)(my_id >= 0 ? my_id : 0) * a.lda + 8 * h;     // + k0 per slice
+  const int a_lim = my_id >= 0 ? K8 - 8 * h : 0;                                    // pieces are valid while k0 < a_lim (K8, k0: multiples of 8)
+  const uint32_t a_dst = smem_u32(As + srow * W_PITCH + 8 * h);
+  const int bk = tid & 15, bc = tid >> 4;                                           // B: element k0 + bk of columns c0 + bc + 8 e
+  const double *b_src = a.B + (UPDATE ? (int64_t)bin * a.K : 0) + bk + (int64_t)min(c0 + bc, a.N - 1) * a.ldb;   // + phase * K + k0 per slice
+  const uint32_t b_stride = (uint32_t)(8 * a.ldb * sizeof(double));                 // bytes between a thread's columns (< 2^32: ldb <= 2^20)
+  const uint32_t b_dst = smem_u32(Bs + bc * W_PITCH + bk);
+  int b_cols = 0;                                                                   // how many of the thread's eight columns exist
+#pragma unroll
+  for (int e = 0; e < 8; e++) b_cols += (c0 + bc + 8 * e < a.N) ? 1 : 0;
+  const int b_lim = a.K - bk;                                                       // element valid while k0 < b_lim
   const int nks = (a.K + W_KS - 1) / W_KS;
   const int nsl = (UPDATE ? 2 : 1) * nks;
-  // The loaded values stay untouched in registers until they are stored (the interpolation weight is applied there): an
-  // instruction that consumes them here would make the warp wait for the loads before its DMMA loop instead of after it.
-  double2 ra[4], rb[4];
-  auto load_slice = [&](int s) {
-    const int p = (UPDATE && s >= nks) ? 1 : 0;
-    const int k0 = (s - p * nks) * W_KS + 8 * h;
-    const double *bp = a.B + (UPDATE ? (int64_t)(bin + p) * a.K : 0) + (int64_t)bcol * a.ldb;
+  auto issue_slice = [&](int s) {
+    if (s < nsl) {
+      const int p = (UPDATE && s >= nks) ? 1 : 0;
+      const int k0 = (s - p * nks) * W_KS;
+      const uint32_t st_off = (uint32_t)((s % W_STAGES) * (W_TM * W_PITCH) * sizeof(double));   // W_TM == W_TN: same for both tiles
+      {
+        const int sz = k0 < a_lim ? 16 : 0;
+        const char *src = reinterpret_cast<const char *>(a_src + k0);
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const int kk = k0 + 2 * ((u + srow) & 3);
-      double2 v = make_double2(0.0, 0.0);
-      if (arow != nullptr && kk < K8) v = *reinterpret_cast<const double2 *>(arow + kk);
-      ra[u] = v;
-      double bx = 0.0, by = 0.0;
-      if (bcol_ok) {
-        if (kk < a.K) bx = __ldg(bp + kk);
-        if (kk + 1 < a.K) by = __ldg(bp + kk + 1);
+        for (int u = 0; u < 4; u++)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(a_dst + st_off + 16 * u), "l"(src + 16 * u), "r"(sz) : "memory");
       }
-      rb[u] = make_double2(bx, by);
-    }
-  };
-  auto store_slice = [&](int s) {
-    const double scale = UPDATE ? sc[s >= nks ? 1 : 0][srow] : 1.0;
+      {
+        const int live = k0 < b_lim ? b_cols : 0;
+        const char *src = reinterpret_cast<const char *>(b_src + (UPDATE ? p * a.K : 0) + k0);
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const int off = srow * W_PITCH + 8 * h + 2 * ((u + srow) & 3);
-      *reinterpret_cast<double2 *>(As + off) = UPDATE ? make_double2(ra[u].x * scale, ra[u].y * scale) : ra[u];
-      *reinterpret_cast<double2 *>(Bs + off) = rb[u];
+        for (int e = 0; e < 8; e++)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(b_dst + st_off + (uint32_t)(8 * e * W_PITCH * sizeof(double))),
+                       "l"(e < live ? src + (size_t)e * b_stride : src), "r"(e < live ? 8 : 0) : "memory");
+      }
     }
+    cp_async_commit();   // (an empty group past the last slice keeps the group count in step)
   };
 
   const int g = lane >> 2, t = lane & 3, wr = warp >> 1, wc = warp & 1;
-  bool warp_has_rows = 32 * wr < nv;
   // 8-column groups of this warp that hold output columns at all (the last column tile of a 2^p + 1 grid holds one column)
   const int jmax = min(4, max(0, ((UPDATE ? ((a.N + 7) & ~7) : a.N) - (c0 + 32 * wc) + 7) >> 3));
-  if (jmax == 0) warp_has_rows = false;
+  const bool warp_has_rows = 32 * wr < nv && jmax > 0;
   double acc[4][4][2];
 #pragma unroll
   for (int i = 0; i < 4; i++)
 #pragma unroll
     for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  load_slice(0);
-  for (int s = 0; s < nsl; s++) {
-    __syncthreads();          // every warp is done with the previous slice
-    store_slice(s);
-    __syncthreads();
-    if (s + 1 < nsl) load_slice(s + 1);
-    if (warp_has_rows) {
+  // per-row interpolation weights of this lane's four row tiles (UPDATE): applied to the A fragments
+  double wsc[2][4];
 #pragma unroll
-      for (int jb = 0; jb < W_KS / 8; jb++) {
-        double2 av[4], bv[4];
+  for (int i = 0; i < 4; i++) { wsc[0][i] = sc[0][32 * wr + 8 * i + g]; wsc[1][i] = sc[1][32 * wr + 8 * i + g]; }
+  const double *a_frag = As + (32 * wr + g) * W_PITCH + 2 * t, *b_frag = Bs + (32 * wc + g) * W_PITCH + 2 * t;
+
+  // one slice of the contraction from ring stage `stage`; MODE 0: warp without work, 1: all four column groups, 2: jmax < 4
+  auto compute = [&](auto mode_tag, int stage, int ph) {
+    constexpr int MODE = decltype(mode_tag)::value;
+    if (MODE == 0) return;
+    const double *as = a_frag + stage * (W_TM * W_PITCH), *bs = b_frag + stage * (W_TN * W_PITCH);
 #pragma unroll
-        for (int i = 0; i < 4; i++) av[i] = *reinterpret_cast<const double2 *>(As + (32 * wr + 8 * i + g) * W_PITCH + 8 * jb + 2 * t);
+    for (int jb = 0; jb < W_KS / 8; jb++) {
+      double2 av[4], bv[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) bv[j] = *reinterpret_cast<const double2 *>(Bs + (32 * wc + 8 * j + g) * W_PITCH + 8 * jb + 2 * t);
-        if (jmax == 4) {
+      for (int i = 0; i < 4; i++) {
+        av[i] = *reinterpret_cast<const double2 *>(as + 8 * i * W_PITCH + 8 * jb);
+        if (UPDATE) { const double w = ph ? wsc[1][i] : wsc[0][i]; av[i].x *= w; av[i].y *= w; }
+      }
 #pragma unroll
-          for (int i = 0; i < 4; i++)
+      for (int j = 0; j < 4; j++) bv[j] = *reinterpret_cast<const double2 *>(bs + 8 * j * W_PITCH + 8 * jb);
+      if (MODE == 1) {
 #pragma unroll
-            for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], av[i].x, bv[j].x);
+        for (int i = 0; i < 4; i++)
 #pragma unroll
-          for (int i = 0; i < 4; i++)
+          for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], av[i].x, bv[j].x);
 #pragma unroll
-            for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], av[i].y, bv[j].y);
-        } else {
+        for (int i = 0; i < 4; i++)
 #pragma unroll
-          for (int j = 0; j < 3; j++) {
-            if (j < jmax) {
+          for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], av[i].y, bv[j].y);
+      } else {
 #pragma unroll
-              for (int i = 0; i < 4; i++) dmma884(acc[i][j][0], acc[i][j][1], av[i].x, bv[j].x);
+        for (int j = 0; j < 3; j++) {
+          if (j < jmax) {
 #pragma unroll
-              for (int i = 0; i < 4; i++) dmma884(acc[i][j][0], acc[i][j][1], av[i].y, bv[j].y);
-            }
+            for (int i = 0; i < 4; i++) dmma884(acc[i][j][0], acc[i][j][1], av[i].x, bv[j].x);
+#pragma unroll
+            for (int i = 0; i < 4; i++) dmma884(acc[i][j][0], acc[i][j][1], av[i].y, bv[j].y);
           }
         }
       }
     }
-  }
+  };
+  auto mainloop = [&](auto mode_tag) {
+#pragma unroll
+    for (int s = 0; s < W_STAGES - 1; s++) issue_slice(s);
+    for (int s = 0; s < nsl; s++) {
+      cp_async_wait<W_STAGES - 2>();   // this thread's pieces of slice s have landed
+      __syncthreads();                 // ... everybody's have, and every warp is done with slice s - 1 (whose stage is refilled next)
+      issue_slice(s + W_STAGES - 1);
+      compute(mode_tag, s % W_STAGES, (UPDATE && s >= nks) ? 1 : 0);
+    }
+  };
+  if (!warp_has_rows) mainloop(std::integral_constant<int, 0>());
+  else if (jmax == 4) mainloop(std::integral_constant<int, 1>());
+  else mainloop(std::integral_constant<int, 2>());
 
   // ---- epilogue: lane (g, t) holds C[8i + g][8j + 2t], C[8i + g][8j + 2t + 1] ----
   if (!warp_has_rows) return;
@@ -331,6 +377,12 @@ __global__ void wide_tables_kernel(const DimInfo *__restrict__ dims, const doubl
 
 }  // namespace
 
+cudaError_t wide_init(int) {
+  cudaError_t e = cudaFuncSetAttribute(wide_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W_SMEM);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(wide_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W_SMEM);
+}
+
 cudaError_t wide_tables(const DimInfo *d_dims, int d, const double *xs, double *ih, double *rw, double *hr, cudaStream_t st) {
   wide_tables_kernel<<<d, 128, 0, st>>>(d_dims, xs, ih, rw, hr);
   return cudaGetLastError();
@@ -345,8 +397,9 @@ cudaError_t launch_wide_step(const WideArgs &w, cudaStream_t st) {
     g.B = w.core; g.ldb = (int64_t)w.r0 * w.n0; g.K = w.r0; g.N = w.r1;
     g.C = w.Fout; g.ldc = w.ldf;
     const int n8 = (w.r1 + 7) & ~7;
-    const dim3 grid((unsigned)(row_tiles + (w.n0 - 1)), (unsigned)((n8 + W_TN - 1) / W_TN));   // at most rows / 64 + one ragged tile per interval
-    wide_gemm_kernel<true><<<grid, W_THREADS, 0, st>>>(g);
+    g.ncol = (n8 + W_TN - 1) / W_TN;
+    const unsigned grid = (unsigned)(row_tiles + (w.n0 - 1)) * (unsigned)g.ncol;   // at most rows / 64 + one ragged tile per interval
+    wide_gemm_kernel<true><<<grid, W_THREADS, W_SMEM, st>>>(g);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
@@ -355,8 +408,9 @@ cudaError_t launch_wide_step(const WideArgs &w, cudaStream_t st) {
     g.A = w.Fout; g.lda = w.ldf; g.perm = nullptr; g.hist = nullptr; g.nb = 0; g.w1 = g.w2 = nullptr; g.rows = w.rows;
     g.B = w.pnext; g.ldb = w.r1; g.K = w.r1; g.N = w.n1;
     g.C = w.pb; g.ldc = w.rows;
-    const dim3 grid((unsigned)row_tiles, (unsigned)((w.n1 + W_TN - 1) / W_TN));
-    wide_gemm_kernel<false><<<grid, W_THREADS, 0, st>>>(g);
+    g.ncol = (w.n1 + W_TN - 1) / W_TN;
+    const unsigned grid = (unsigned)row_tiles * (unsigned)g.ncol;
+    wide_gemm_kernel<false><<<grid, W_THREADS, W_SMEM, st>>>(g);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
