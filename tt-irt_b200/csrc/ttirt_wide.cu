@@ -38,7 +38,8 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 // CTA tile 64 rows x 64 columns, K in slices of 16; four warps, each 32 x 32 (4 x 4 DMMA tiles: 16 independent
 // accumulator chains).  One shared-memory stage; the next slice's global loads are in flight (registers) while the current
 // slice is multiplied, and three CTAs per SM cover each other's barriers.
-constexpr int W_TM = 64, W_TN = 64, W_KS = 16, W_THREADS = 128;
+constexpr int W_TM = 64, W_KS = 16, W_THREADS = 128;
+constexpr int W_NJ_UPDATE = 4, W_NJ_PDF = 5;
 // row pitch of the staged operands in doubles: 24 = 8 (mod 16), so the LDS.128 fragment loads of a quarter warp (rows g, g+1,
 // k pairs 2t) fall into eight different 16-byte slots of the 128-byte bank window: conflict-free without a swizzle
 constexpr int W_PITCH = W_KS + 8;
@@ -49,7 +50,7 @@ constexpr int W_PITCH = W_KS + 8;
 #define TTIRT_WIDE_STAGES 2
 #endif
 constexpr int W_STAGES = TTIRT_WIDE_STAGES, W_CTAS = TTIRT_WIDE_CTAS;
-constexpr size_t W_SMEM = sizeof(double) * W_STAGES * (W_TM + W_TN) * W_PITCH;
+constexpr size_t wide_smem_bytes(int nj) { return sizeof(double) * W_STAGES * (W_TM + 16 * nj) * W_PITCH; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 // cp.async (LDGSTS) of BYTES (8 or 16) global -> shared; !valid: zero-fill (src-size 0, src still a mapped address)
@@ -73,24 +74,31 @@ struct WideGemmArgs {
   int64_t ldb;
   int K, N;               // contraction length per phase, output columns
   int ncol;               // column tiles (grid = row tiles x ncol, column tile fastest)
+  int gpt;                // 8-column groups per column tile (<= 2 NJ; the last tile may hold fewer)
   double *C;              // UPDATE: C[id * ldc + c] for c < N rounded to 8; else C[c * ldc + position] for c < N
   int64_t ldc;
 };
 
 // The contraction index is consumed in a permuted order on BOTH operands (lane t of a quad takes k = 8j + 2t and 8j + 2t + 1
 // for the two k-steps of an 8-block), so one LDS.128 per operand feeds two DMMAs.
-template <bool UPDATE>
+// NJ: 8-column groups per warp at most (a column tile is up to 16 NJ columns wide).  The column groups of a launch are
+// spread evenly over its column tiles and the groups of a tile over its two warp columns, so a 2^p + 1 grid costs one
+// extra group in one tile (NJ = 5: 129 nodes are tiles of 9 and 8 groups) instead of a column tile of its own.
+template <bool UPDATE, int NJ>
 __global__ void __launch_bounds__(W_THREADS, W_CTAS) wide_gemm_kernel(const WideGemmArgs a) {
   extern __shared__ __align__(16) unsigned char wide_smem[];
   double *As = reinterpret_cast<double *>(wide_smem);          // W_STAGES stages of the A tile, then of the B tile
   double *Bs = As + W_STAGES * W_TM * W_PITCH;
+  constexpr int TN = 16 * NJ;                                  // columns of the B tile
   __shared__ double sc[2][W_TM];
   __shared__ int ids[W_TM];
   __shared__ int tile_info[3];   // interval, first (sorted) row, valid rows (0: no such tile)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // column tiles of one row tile are neighbours in the grid: they run at the same time and share the tile's A rows in L2
-  const int T = (int)(blockIdx.x / (unsigned)a.ncol), c0 = (int)(blockIdx.x % (unsigned)a.ncol) * W_TN;
+  const int T = (int)(blockIdx.x / (unsigned)a.ncol), c0 = (int)(blockIdx.x % (unsigned)a.ncol) * a.gpt * 8;
+  const int Nout = UPDATE ? ((a.N + 7) & ~7) : a.N;            // output columns (UPDATE writes the zero padding too)
+  const int gt = min(a.gpt, (Nout - c0 + 7) >> 3);             // column groups of this tile
 
   // ---- which rows: tile T of the chunk.  UPDATE: tiles are numbered interval by interval (none straddles two), the warp
   //      scans the histogram for the interval that holds tile T ----
@@ -162,9 +170,9 @@ __global__ void __launch_bounds__(W_THREADS, W_CTAS) wide_gemm_kernel(const Wide
   const double *b_src = a.B + (UPDATE ? (int64_t)bin * a.K : 0) + bk + (int64_t)min(c0 + bc, a.N - 1) * a.ldb;   // + phase * K + k0 per slice
   const uint32_t b_stride = (uint32_t)(8 * a.ldb * sizeof(double));                 // bytes between a thread's columns (< 2^32: ldb <= 2^20)
   const uint32_t b_dst = smem_u32(Bs + bc * W_PITCH + bk);
-  int b_cols = 0;                                                                   // how many of the thread's eight columns exist
+  int b_cols = 0;                                                                   // how many of the thread's columns bc + 8 e exist in this tile
 #pragma unroll
-  for (int e = 0; e < 8; e++) b_cols += (c0 + bc + 8 * e < a.N) ? 1 : 0;
+  for (int e = 0; e < 2 * NJ; e++) b_cols += (e < gt && c0 + bc + 8 * e < a.N) ? 1 : 0;
   const int b_lim = a.K - bk;                                                       // element valid while k0 < b_lim
   const int nks = (a.K + W_KS - 1) / W_KS;
   const int nsl = (UPDATE ? 2 : 1) * nks;
@@ -172,20 +180,20 @@ __global__ void __launch_bounds__(W_THREADS, W_CTAS) wide_gemm_kernel(const Wide
     if (s < nsl) {
       const int p = (UPDATE && s >= nks) ? 1 : 0;
       const int k0 = (s - p * nks) * W_KS;
-      const uint32_t st_off = (uint32_t)((s % W_STAGES) * (W_TM * W_PITCH) * sizeof(double));   // W_TM == W_TN: same for both tiles
+      const uint32_t st_a = (uint32_t)((s % W_STAGES) * (W_TM * W_PITCH) * sizeof(double)), st_b = (uint32_t)((s % W_STAGES) * (TN * W_PITCH) * sizeof(double));
       {
         const int sz = k0 < a_lim ? 16 : 0;
         const char *src = reinterpret_cast<const char *>(a_src + k0);
 #pragma unroll
         for (int u = 0; u < 4; u++)
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(a_dst + st_off + 16 * u), "l"(src + 16 * u), "r"(sz) : "memory");
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(a_dst + st_a + 16 * u), "l"(src + 16 * u), "r"(sz) : "memory");
       }
       {
         const int live = k0 < b_lim ? b_cols : 0;
         const char *src = reinterpret_cast<const char *>(b_src + (UPDATE ? p * a.K : 0) + k0);
 #pragma unroll
-        for (int e = 0; e < 8; e++)
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(b_dst + st_off + (uint32_t)(8 * e * W_PITCH * sizeof(double))),
+        for (int e = 0; e < 2 * NJ; e++)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(b_dst + st_b + (uint32_t)(8 * e * W_PITCH * sizeof(double))),
                        "l"(e < live ? src + (size_t)e * b_stride : src), "r"(e < live ? 8 : 0) : "memory");
       }
     }
@@ -193,48 +201,50 @@ __global__ void __launch_bounds__(W_THREADS, W_CTAS) wide_gemm_kernel(const Wide
   };
 
   const int g = lane >> 2, t = lane & 3, wr = warp >> 1, wc = warp & 1;
-  // 8-column groups of this warp that hold output columns at all (the last column tile of a 2^p + 1 grid holds one column)
-  const int jmax = min(4, max(0, ((UPDATE ? ((a.N + 7) & ~7) : a.N) - (c0 + 32 * wc) + 7) >> 3));
+  // the tile's column groups are split between the two warp columns: the first takes the larger half
+  const int j_first = wc ? (gt + 1) >> 1 : 0, jmax = wc ? gt >> 1 : (gt + 1) >> 1;
   const bool warp_has_rows = 32 * wr < nv && jmax > 0;
-  double acc[4][4][2];
+  double acc[4][NJ][2];
 #pragma unroll
   for (int i = 0; i < 4; i++)
 #pragma unroll
-    for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < NJ; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   // per-row interpolation weights of this lane's four row tiles (UPDATE): applied to the A fragments
   double wsc[2][4];
 #pragma unroll
   for (int i = 0; i < 4; i++) { wsc[0][i] = sc[0][32 * wr + 8 * i + g]; wsc[1][i] = sc[1][32 * wr + 8 * i + g]; }
-  const double *a_frag = As + (32 * wr + g) * W_PITCH + 2 * t, *b_frag = Bs + (32 * wc + g) * W_PITCH + 2 * t;
+  const double *a_frag = As + (32 * wr + g) * W_PITCH + 2 * t, *b_frag = Bs + (8 * j_first + g) * W_PITCH + 2 * t;
 
-  // one slice of the contraction from ring stage `stage`; MODE 0: warp without work, 1: all four column groups, 2: jmax < 4
-  auto compute = [&](auto mode_tag, int stage, int ph) {
-    constexpr int MODE = decltype(mode_tag)::value;
-    if (MODE == 0) return;
-    const double *as = a_frag + stage * (W_TM * W_PITCH), *bs = b_frag + stage * (W_TN * W_PITCH);
+  // one slice of the contraction from ring stage `stage` for a warp with JM column groups (compile time); JM = 0: nothing
+  // to do; JM = -1: jmax groups, decided at run time
+  auto compute = [&](auto jm_tag, int stage, int ph) {
+    constexpr int JM = decltype(jm_tag)::value;
+    if (JM == 0) return;
+    constexpr int JN = JM <= 0 ? NJ : JM;
+    const double *as = a_frag + stage * (W_TM * W_PITCH), *bs = b_frag + stage * (TN * W_PITCH);
 #pragma unroll
     for (int jb = 0; jb < W_KS / 8; jb++) {
-      double2 av[4], bv[4];
+      double2 av[4], bv[JN];
 #pragma unroll
       for (int i = 0; i < 4; i++) {
         av[i] = *reinterpret_cast<const double2 *>(as + 8 * i * W_PITCH + 8 * jb);
         if (UPDATE) { const double w = ph ? wsc[1][i] : wsc[0][i]; av[i].x *= w; av[i].y *= w; }
       }
 #pragma unroll
-      for (int j = 0; j < 4; j++) bv[j] = *reinterpret_cast<const double2 *>(bs + 8 * j * W_PITCH + 8 * jb);
-      if (MODE == 1) {
+      for (int j = 0; j < JN; j++) bv[j] = *reinterpret_cast<const double2 *>(bs + 8 * j * W_PITCH + 8 * jb);
+      if (JM > 0) {
 #pragma unroll
         for (int i = 0; i < 4; i++)
 #pragma unroll
-          for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], av[i].x, bv[j].x);
+          for (int j = 0; j < JN; j++) dmma884(acc[i][j][0], acc[i][j][1], av[i].x, bv[j].x);
 #pragma unroll
         for (int i = 0; i < 4; i++)
 #pragma unroll
-          for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], av[i].y, bv[j].y);
+          for (int j = 0; j < JN; j++) dmma884(acc[i][j][0], acc[i][j][1], av[i].y, bv[j].y);
       } else {
 #pragma unroll
-        for (int j = 0; j < 3; j++) {
+        for (int j = 0; j < JN; j++) {
           if (j < jmax) {
 #pragma unroll
             for (int i = 0; i < 4; i++) dmma884(acc[i][j][0], acc[i][j][1], av[i].x, bv[j].x);
@@ -245,23 +255,23 @@ __global__ void __launch_bounds__(W_THREADS, W_CTAS) wide_gemm_kernel(const Wide
       }
     }
   };
-  auto mainloop = [&](auto mode_tag) {
+  auto mainloop = [&](auto jm_tag) {
 #pragma unroll
     for (int s = 0; s < W_STAGES - 1; s++) issue_slice(s);
     for (int s = 0; s < nsl; s++) {
       cp_async_wait<W_STAGES - 2>();   // this thread's pieces of slice s have landed
       __syncthreads();                 // ... everybody's have, and every warp is done with slice s - 1 (whose stage is refilled next)
       issue_slice(s + W_STAGES - 1);
-      compute(mode_tag, s % W_STAGES, (UPDATE && s >= nks) ? 1 : 0);
+      compute(jm_tag, s % W_STAGES, (UPDATE && s >= nks) ? 1 : 0);
     }
   };
   if (!warp_has_rows) mainloop(std::integral_constant<int, 0>());
-  else if (jmax == 4) mainloop(std::integral_constant<int, 1>());
-  else mainloop(std::integral_constant<int, 2>());
+  else if (jmax == NJ) mainloop(std::integral_constant<int, NJ>());
+  else if (jmax == NJ - 1) mainloop(std::integral_constant<int, NJ - 1>());
+  else mainloop(std::integral_constant<int, -1>());
 
   // ---- epilogue: lane (g, t) holds C[8i + g][8j + 2t], C[8i + g][8j + 2t + 1] ----
   if (!warp_has_rows) return;
-  const int N8 = (a.N + 7) & ~7;
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     const int r = 32 * wr + 8 * i + g;
@@ -269,17 +279,17 @@ __global__ void __launch_bounds__(W_THREADS, W_CTAS) wide_gemm_kernel(const Wide
     if (UPDATE) {
       double *crow = a.C + (size_t)ids[r] * a.ldc;
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int c = c0 + 32 * wc + 8 * j + 2 * t;
-        if (c < N8) *reinterpret_cast<double2 *>(crow + c) = make_double2(acc[i][j][0], acc[i][j][1]);   // columns N .. N8-1: exact zeros
+      for (int j = 0; j < NJ; j++) {
+        const int c = c0 + 8 * (j_first + j) + 2 * t;
+        if (j < jmax) *reinterpret_cast<double2 *>(crow + c) = make_double2(acc[i][j][0], acc[i][j][1]);   // columns N .. N8-1: exact zeros
       }
     } else {
       double *cpos = a.C + (row0 + r);
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int c = c0 + 32 * wc + 8 * j + 2 * t;
-        if (c < a.N) cpos[(int64_t)c * a.ldc] = acc[i][j][0];
-        if (c + 1 < a.N) cpos[(int64_t)(c + 1) * a.ldc] = acc[i][j][1];
+      for (int j = 0; j < NJ; j++) {
+        const int c = c0 + 8 * (j_first + j) + 2 * t;
+        if (j < jmax && c < a.N) cpos[(int64_t)c * a.ldc] = acc[i][j][0];
+        if (j < jmax && c + 1 < a.N) cpos[(int64_t)(c + 1) * a.ldc] = acc[i][j][1];
       }
     }
   }
@@ -378,9 +388,16 @@ __global__ void wide_tables_kernel(const DimInfo *__restrict__ dims, const doubl
 }  // namespace
 
 cudaError_t wide_init(int) {
-  cudaError_t e = cudaFuncSetAttribute(wide_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W_SMEM);
+  cudaError_t e = cudaFuncSetAttribute(wide_gemm_kernel<true, W_NJ_UPDATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem_bytes(W_NJ_UPDATE));
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(wide_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W_SMEM);
+  return cudaFuncSetAttribute(wide_gemm_kernel<false, W_NJ_PDF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem_bytes(W_NJ_PDF));
+}
+
+// column tiling of `groups` 8-column groups with at most 2 nj groups per tile: as few tiles as possible, evenly filled
+static void wide_col_tiles(int groups, int nj, int &ncol, int &gpt) {
+  ncol = (groups + 2 * nj - 1) / (2 * nj);
+  if (ncol < 1) ncol = 1;
+  gpt = (groups + ncol - 1) / ncol;
 }
 
 cudaError_t wide_tables(const DimInfo *d_dims, int d, const double *xs, double *ih, double *rw, double *hr, cudaStream_t st) {
@@ -396,10 +413,9 @@ cudaError_t launch_wide_step(const WideArgs &w, cudaStream_t st) {
     g.A = w.Fin; g.lda = w.ldf; g.perm = w.perm; g.hist = w.hist_cur; g.nb = w.n0 - 1; g.w1 = w.w1; g.w2 = w.w2; g.rows = w.rows;
     g.B = w.core; g.ldb = (int64_t)w.r0 * w.n0; g.K = w.r0; g.N = w.r1;
     g.C = w.Fout; g.ldc = w.ldf;
-    const int n8 = (w.r1 + 7) & ~7;
-    g.ncol = (n8 + W_TN - 1) / W_TN;
+    wide_col_tiles((w.r1 + 7) >> 3, W_NJ_UPDATE, g.ncol, g.gpt);
     const unsigned grid = (unsigned)(row_tiles + (w.n0 - 1)) * (unsigned)g.ncol;   // at most rows / 64 + one ragged tile per interval
-    wide_gemm_kernel<true><<<grid, W_THREADS, W_SMEM, st>>>(g);
+    wide_gemm_kernel<true, W_NJ_UPDATE><<<grid, W_THREADS, wide_smem_bytes(W_NJ_UPDATE), st>>>(g);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
@@ -408,9 +424,9 @@ cudaError_t launch_wide_step(const WideArgs &w, cudaStream_t st) {
     g.A = w.Fout; g.lda = w.ldf; g.perm = nullptr; g.hist = nullptr; g.nb = 0; g.w1 = g.w2 = nullptr; g.rows = w.rows;
     g.B = w.pnext; g.ldb = w.r1; g.K = w.r1; g.N = w.n1;
     g.C = w.pb; g.ldc = w.rows;
-    g.ncol = (w.n1 + W_TN - 1) / W_TN;
+    wide_col_tiles((w.n1 + 7) >> 3, W_NJ_PDF, g.ncol, g.gpt);
     const unsigned grid = (unsigned)row_tiles * (unsigned)g.ncol;
-    wide_gemm_kernel<false><<<grid, W_THREADS, W_SMEM, st>>>(g);
+    wide_gemm_kernel<false, W_NJ_PDF><<<grid, W_THREADS, wide_smem_bytes(W_NJ_PDF), st>>>(g);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
