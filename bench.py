@@ -620,7 +620,10 @@ def other_configs(torch, peak_tflops):
     out = {}
     cases = [("configs[3] lorenz-40 shape, int64 ABI", 40, 33, 32, 22, 64, (-3.0, 3.0), 3, 3),
              ("configs[1] inverse-diffusion shape", 11, 17, 16, 20, 32, (-3.0 ** 0.5, 3.0 ** 0.5), 10, 3),
-             ("configs[0] shock-absorber shape", 8, 17, 8, 14, 32, (0.0, 1.0), 50, 5)]
+             ("configs[0] shock-absorber shape", 8, 17, 8, 14, 32, (0.0, 1.0), 50, 5),
+             # not a BASELINE config: a shape beyond the fused kernel (r > 64, n > 72), served by the unfused DMMA path of
+             # csrc/ttirt_wide.cu (the reference handles any shape on one code path, tt_irt1_int32.c:41-53)
+             ("wide shape d=8 n=129 r=128 (beyond the fused kernel)", 8, 129, 128, 18, 32, (-1.0, 1.0), 3, 2)]
     for name, d, n, r, log2m, width, (lo, hi), steps, warm in cases:
         try:
             M = 1 << log2m

@@ -201,6 +201,7 @@ struct WideArgs {
   double *Fout;              // ... of dimension k+1 (a different buffer)
   int ldf;
   double *pb;                // n1 x rows scratch: weighted signed pdf, node-major
+  double *mass_part;         // wide_mass_slots(nmax) x rows scratch: shares of the rows' masses
   const int *perm, *hist_cur;
   int *idx;
   double *w1, *w2, *lp, *lpd;
@@ -212,6 +213,7 @@ struct WideArgs {
   int *hist_next;
 };
 cudaError_t launch_wide_step(const WideArgs &a, cudaStream_t st);   // three launches
+int wide_mass_slots(int nmax);
 cudaError_t wide_init(int device);                  // opt in to the GEMM's dynamic shared memory
 cudaError_t wide_tables(const DimInfo *d_dims, int d, const double *xs, double *ih, double *rw, double *hr, cudaStream_t st);
 constexpr int kWideClass = 3;

@@ -110,6 +110,7 @@ struct Workspace {
   int *hist = nullptr;   // d x nbpad
   double *F2 = nullptr;  // wide path: second interface buffer (cap x ldf), weighted pdf (nmax x cap)
   double *pw = nullptr;
+  double *mp = nullptr;  // wide path: shares of the rows' masses (wide_mass_slots x cap)
   // strict scratch
   double *left = nullptr, *pbuf = nullptr, *cbuf = nullptr;
   // host-mode staging
@@ -179,7 +180,7 @@ static void ws_drop_graphs(Workspace &w) {
 static void ws_free(Workspace &w) {
   ws_drop_graphs(w);
   cudaFree(w.F); cudaFree(w.idx); cudaFree(w.perm); cudaFree(w.w1); cudaFree(w.w2); cudaFree(w.lp); cudaFree(w.lpd); cudaFree(w.lpe);
-  cudaFree(w.hist); cudaFree(w.F2); cudaFree(w.pw);
+  cudaFree(w.hist); cudaFree(w.F2); cudaFree(w.pw); cudaFree(w.mp);
   cudaFree(w.left); cudaFree(w.pbuf); cudaFree(w.cbuf);
   cudaFree(w.q); cudaFree(w.z); cudaFree(w.lpz); cudaFree(w.idx_out);
   if (w.stream) cudaStreamDestroy(w.stream);
@@ -203,6 +204,7 @@ static int ws_alloc(ttirt_model *md, Workspace &w, int64_t cap, bool s, bool h, 
     if (md->fast_cls == kWideClass) {
       CK(cudaMalloc(&w.F2, sizeof(double) * cap * md->ldf));
       CK(cudaMalloc(&w.pw, sizeof(double) * cap * md->nmax));
+      CK(cudaMalloc(&w.mp, sizeof(double) * cap * wide_mass_slots((int)md->nmax)));
     }
   }
   if (s) {
@@ -891,7 +893,7 @@ static int enqueue_chunk(ttirt_model *md, Workspace &w, int64_t rows, const doub
       wa.r0 = dk.r0; wa.n0 = dk.n; wa.r1 = dk.r1; wa.n1 = dn.n;
       wa.last = (k + 1 == d - 1); wa.rows = (int)rows;
       wa.Fin = (k & 1) ? w.F2 : w.F; wa.Fout = (k & 1) ? w.F : w.F2; wa.ldf = md->ldf;
-      wa.pb = w.pw; wa.perm = w.perm; wa.hist_cur = w.hist + (size_t)k * nbpad;
+      wa.pb = w.pw; wa.mass_part = w.mp; wa.perm = w.perm; wa.hist_cur = w.hist + (size_t)k * nbpad;
       wa.idx = w.idx; wa.w1 = w.w1; wa.w2 = w.w2; wa.lp = w.lp; wa.lpd = w.lpd; wa.lpe = w.lpe;
       wa.q = q + ldq * (k + 1); wa.z = z + ldz * (k + 1);
       wa.idx_out = idx_out ? idx_out + ldz * (k + 1) : nullptr;

@@ -38,7 +38,13 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 // CTA tile 64 rows x 64 columns, K in slices of 16; four warps, each 32 x 32 (4 x 4 DMMA tiles: 16 independent
 // accumulator chains).  One shared-memory stage; the next slice's global loads are in flight (registers) while the current
 // slice is multiplied, and three CTAs per SM cover each other's barriers.
-constexpr int W_TM = 64, W_KS = 16, W_THREADS = 128;
+#ifndef TTIRT_WIDE_KS
+#define TTIRT_WIDE_KS 16
+#endif
+constexpr int W_TM = 64, W_KS = TTIRT_WIDE_KS, W_THREADS = 128;
+constexpr int W_HK = W_KS / 2;            // k per thread and slice of the A tile (two threads per row)
+constexpr int W_CPT = W_THREADS / W_KS;   // B columns a pass of the CTA covers (lanes along k)
+static_assert(W_KS == 16 || W_KS == 32, "slices of 16 or 32");
 constexpr int W_NJ_UPDATE = 4, W_NJ_PDF = 5;
 // row pitch of the staged operands in doubles: 24 = 8 (mod 16), so the LDS.128 fragment loads of a quarter warp (rows g, g+1,
 // k pairs 2t) fall into eight different 16-byte slots of the 128-byte bank window: conflict-free without a swizzle
@@ -77,6 +83,7 @@ struct WideGemmArgs {
   int gpt;                // 8-column groups per column tile (<= 2 NJ; the last tile may hold fewer)
   double *C;              // UPDATE: C[id * ldc + c] for c < N rounded to 8; else C[c * ldc + position] for c < N
   int64_t ldc;
+  double *mass_part;      // pdf: per-row sums of |C| over the columns of one warp column, slot-major: [(2 tile + wc) * rows + position]
 };
 
 // The contraction index is consumed in a permuted order on BOTH operands (lane t of a quad takes k = 8j + 2t and 8j + 2t + 1
@@ -163,16 +170,16 @@ __global__ void __launch_bounds__(W_THREADS, W_CTAS) wide_gemm_kernel(const Wide
   const int srow = tid >> 1, h = tid & 1;
   const int my_id = ids[srow];
   const int K8 = (a.K + 7) & ~7;
-  const double *a_src = a.A + (size_t)(my_id >= 0 ? my_id : 0) * a.lda + 8 * h;     // + k0 per slice
-  const int a_lim = my_id >= 0 ? K8 - 8 * h : 0;                                    // pieces are valid while k0 < a_lim (K8, k0: multiples of 8)
-  const uint32_t a_dst = smem_u32(As + srow * W_PITCH + 8 * h);
-  const int bk = tid & 15, bc = tid >> 4;                                           // B: element k0 + bk of columns c0 + bc + 8 e
+  const double *a_src = a.A + (size_t)(my_id >= 0 ? my_id : 0) * a.lda + W_HK * h;  // + k0 per slice
+  const int a_lim = my_id >= 0 ? K8 - W_HK * h : 0;                                 // the 8-block at k0 + 8 b is valid while k0 + 8 b < a_lim (K8, k0: multiples of 8)
+  const uint32_t a_dst = smem_u32(As + srow * W_PITCH + W_HK * h);
+  const int bk = tid & (W_KS - 1), bc = tid / W_KS;                                 // B: element k0 + bk of columns c0 + bc + W_CPT e
   const double *b_src = a.B + (UPDATE ? (int64_t)bin * a.K : 0) + bk + (int64_t)min(c0 + bc, a.N - 1) * a.ldb;   // + phase * K + k0 per slice
-  const uint32_t b_stride = (uint32_t)(8 * a.ldb * sizeof(double));                 // bytes between a thread's columns (< 2^32: ldb <= 2^20)
+  const uint32_t b_stride = (uint32_t)(W_CPT * a.ldb * sizeof(double));                 // bytes between a thread's columns (< 2^32: ldb <= 2^20)
   const uint32_t b_dst = smem_u32(Bs + bc * W_PITCH + bk);
   int b_cols = 0;                                                                   // how many of the thread's columns bc + 8 e exist in this tile
 #pragma unroll
-  for (int e = 0; e < 2 * NJ; e++) b_cols += (e < gt && c0 + bc + 8 * e < a.N) ? 1 : 0;
+  for (int e = 0; e < TN / W_CPT; e++) b_cols += (bc + W_CPT * e < 8 * gt && c0 + bc + W_CPT * e < a.N) ? 1 : 0;
   const int b_lim = a.K - bk;                                                       // element valid while k0 < b_lim
   const int nks = (a.K + W_KS - 1) / W_KS;
   const int nsl = (UPDATE ? 2 : 1) * nks;
@@ -182,18 +189,21 @@ __global__ void __launch_bounds__(W_THREADS, W_CTAS) wide_gemm_kernel(const Wide
       const int k0 = (s - p * nks) * W_KS;
       const uint32_t st_a = (uint32_t)((s % W_STAGES) * (W_TM * W_PITCH) * sizeof(double)), st_b = (uint32_t)((s % W_STAGES) * (TN * W_PITCH) * sizeof(double));
       {
-        const int sz = k0 < a_lim ? 16 : 0;
         const char *src = reinterpret_cast<const char *>(a_src + k0);
 #pragma unroll
-        for (int u = 0; u < 4; u++)
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(a_dst + st_a + 16 * u), "l"(src + 16 * u), "r"(sz) : "memory");
+        for (int b = 0; b < W_HK / 8; b++) {
+          const int sz = k0 + 8 * b < a_lim ? 16 : 0;
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(a_dst + st_a + 64 * b + 16 * u), "l"(sz ? src + 64 * b + 16 * u : src), "r"(sz) : "memory");
+        }
       }
       {
         const int live = k0 < b_lim ? b_cols : 0;
         const char *src = reinterpret_cast<const char *>(b_src + (UPDATE ? p * a.K : 0) + k0);
 #pragma unroll
-        for (int e = 0; e < 2 * NJ; e++)
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(b_dst + st_b + (uint32_t)(8 * e * W_PITCH * sizeof(double))),
+        for (int e = 0; e < TN / W_CPT; e++)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(b_dst + st_b + (uint32_t)(W_CPT * e * W_PITCH * sizeof(double))),
                        "l"(e < live ? src + (size_t)e * b_stride : src), "r"(e < live ? 8 : 0) : "memory");
       }
     }
@@ -271,12 +281,12 @@ __global__ void __launch_bounds__(W_THREADS, W_CTAS) wide_gemm_kernel(const Wide
   else mainloop(std::integral_constant<int, -1>());
 
   // ---- epilogue: lane (g, t) holds C[8i + g][8j + 2t], C[8i + g][8j + 2t + 1] ----
-  if (!warp_has_rows) return;
+  if (UPDATE ? !warp_has_rows : 32 * wr >= nv) return;
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     const int r = 32 * wr + 8 * i + g;
-    if (r >= nv) continue;
     if (UPDATE) {
+      if (r >= nv) continue;
       double *crow = a.C + (size_t)ids[r] * a.ldc;
 #pragma unroll
       for (int j = 0; j < NJ; j++) {
@@ -284,13 +294,20 @@ __global__ void __launch_bounds__(W_THREADS, W_CTAS) wide_gemm_kernel(const Wide
         if (j < jmax) *reinterpret_cast<double2 *>(crow + c) = make_double2(acc[i][j][0], acc[i][j][1]);   // columns N .. N8-1: exact zeros
       }
     } else {
+      // the tail needs the row's mass sum_j |v_j| before it can search: every warp column leaves its share here, summed in a
+      // fixed order (columns ascending per lane, then the quad's four lanes), so the result does not depend on scheduling
+      const bool live = r < nv;
       double *cpos = a.C + (row0 + r);
+      double psum = 0.0;
 #pragma unroll
       for (int j = 0; j < NJ; j++) {
         const int c = c0 + 8 * (j_first + j) + 2 * t;
-        if (j < jmax && c < a.N) cpos[(int64_t)c * a.ldc] = acc[i][j][0];
-        if (j < jmax && c + 1 < a.N) cpos[(int64_t)(c + 1) * a.ldc] = acc[i][j][1];
+        if (live && j < jmax && c < a.N) { cpos[(int64_t)c * a.ldc] = acc[i][j][0]; psum += fabs(acc[i][j][0]); }
+        if (live && j < jmax && c + 1 < a.N) { cpos[(int64_t)(c + 1) * a.ldc] = acc[i][j][1]; psum += fabs(acc[i][j][1]); }
       }
+      psum += __shfl_xor_sync(FULL, psum, 1);
+      psum += __shfl_xor_sync(FULL, psum, 2);
+      if (live && t == 0) a.mass_part[(size_t)(2 * (blockIdx.x % (unsigned)a.ncol) + wc) * a.rows + row0 + r] = psum;
     }
   }
 }
@@ -298,6 +315,8 @@ __global__ void __launch_bounds__(W_THREADS, W_CTAS) wide_gemm_kernel(const Wide
 struct WideTailArgs {
   const double *pb;        // weighted signed pdf, node-major: pb[j * ldp + m]
   int64_t ldp;
+  const double *mass_part; // nslots shares of the row's mass, slot-major (left by the pdf GEMM): [s * rows + m]
+  int nslots;
   const double *x, *ih, *rw, *hr;   // grid of dimension k+1, 1 / cell width, 1 / node weight, h_{j-1} / node weight
   int n1, rows, last;
   const double *q;
@@ -311,7 +330,7 @@ struct WideTailArgs {
 };
 
 // v_j = w_j |p_j| (w_j the trapezoid node weight, see node_weight()):  cdf_j = R_j + (h_{j-1} / w_j) v_j with
-// R_j = sum_{i<j} v_i, mass = R_n.  Largest i0 <= n-2 with cdf_{i0} < q * mass (reference :134-142 on the unnormalised
+// R_j = sum_{i<j} v_i, mass = R_n (summed by the pdf GEMM's epilogue: one pass over the nodes here instead of two).  Largest i0 <= n-2 with cdf_{i0} < q * mass (reference :134-142 on the unnormalised
 // CDF; it is monotone, so the last node that passes the test is the answer), then the walk kernel's tail verbatim.
 __global__ void __launch_bounds__(256) wide_tail_kernel(const WideTailArgs a) {
   extern __shared__ int sh[];   // n1 - 1 interval counters
@@ -326,13 +345,24 @@ __global__ void __launch_bounds__(256) wide_tail_kernel(const WideTailArgs a) {
     const int64_t ld = a.ldp;
     const double qv = a.q[m];
     double total = 0.0;
-#pragma unroll 4
-    for (int j = 0; j < n1; j++) total += fabs(pv[j * ld]);
+    for (int s = 0; s < a.nslots; s++) total += a.mass_part[(size_t)s * a.rows + m];
     const double qt = qv * total;
     int i0 = 0;
     double dq = qt, Rj = fabs(pv[0]);
-#pragma unroll 4
-    for (int j = 1; j <= n1 - 2; j++) {
+    // eight nodes at a time: the loads of a batch are independent of the running sum and all in flight at once
+    int j = 1;
+    for (; j + 7 <= n1 - 2; j += 8) {
+      double v[8], hrj[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) { v[u] = fabs(pv[(j + u) * ld]); hrj[u] = a.hr[j + u]; }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const double dj = qt - fma(hrj[u], v[u], Rj);
+        if (__double_as_longlong(dj) > 0) { i0 = j + u; dq = dj; }
+        Rj += v[u];
+      }
+    }
+    for (; j <= n1 - 2; j++) {
       const double v = fabs(pv[j * ld]);
       const double dj = qt - fma(a.hr[j], v, Rj);
       if (__double_as_longlong(dj) > 0) { i0 = j; dq = dj; }
@@ -387,12 +417,6 @@ __global__ void wide_tables_kernel(const DimInfo *__restrict__ dims, const doubl
 
 }  // namespace
 
-cudaError_t wide_init(int) {
-  cudaError_t e = cudaFuncSetAttribute(wide_gemm_kernel<true, W_NJ_UPDATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem_bytes(W_NJ_UPDATE));
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(wide_gemm_kernel<false, W_NJ_PDF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem_bytes(W_NJ_PDF));
-}
-
 // column tiling of `groups` 8-column groups with at most 2 nj groups per tile: as few tiles as possible, evenly filled
 static void wide_col_tiles(int groups, int nj, int &ncol, int &gpt) {
   ncol = (groups + 2 * nj - 1) / (2 * nj);
@@ -405,14 +429,28 @@ cudaError_t wide_tables(const DimInfo *d_dims, int d, const double *xs, double *
   return cudaGetLastError();
 }
 
+// shares of a row's mass the pdf GEMM leaves for the tail (two warp columns per column tile), for grids up to nmax nodes
+int wide_mass_slots(int nmax) {
+  int ncol, gpt;
+  wide_col_tiles((nmax + 7) >> 3, W_NJ_PDF, ncol, gpt);
+  return 2 * ncol;
+}
+
+cudaError_t wide_init(int) {
+  cudaError_t e = cudaFuncSetAttribute(wide_gemm_kernel<true, W_NJ_UPDATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem_bytes(W_NJ_UPDATE));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(wide_gemm_kernel<false, W_NJ_PDF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem_bytes(W_NJ_PDF));
+}
+
 // One dimension step k -> k+1 of the wide path: three launches (update, pdf, tail) on st.
 cudaError_t launch_wide_step(const WideArgs &w, cudaStream_t st) {
   const int row_tiles = (w.rows + W_TM - 1) / W_TM;
+  int pdf_ncol = 1;
   {
     WideGemmArgs g;
     g.A = w.Fin; g.lda = w.ldf; g.perm = w.perm; g.hist = w.hist_cur; g.nb = w.n0 - 1; g.w1 = w.w1; g.w2 = w.w2; g.rows = w.rows;
     g.B = w.core; g.ldb = (int64_t)w.r0 * w.n0; g.K = w.r0; g.N = w.r1;
-    g.C = w.Fout; g.ldc = w.ldf;
+    g.C = w.Fout; g.ldc = w.ldf; g.mass_part = nullptr;
     wide_col_tiles((w.r1 + 7) >> 3, W_NJ_UPDATE, g.ncol, g.gpt);
     const unsigned grid = (unsigned)(row_tiles + (w.n0 - 1)) * (unsigned)g.ncol;   // at most rows / 64 + one ragged tile per interval
     wide_gemm_kernel<true, W_NJ_UPDATE><<<grid, W_THREADS, wide_smem_bytes(W_NJ_UPDATE), st>>>(g);
@@ -423,8 +461,9 @@ cudaError_t launch_wide_step(const WideArgs &w, cudaStream_t st) {
     WideGemmArgs g;
     g.A = w.Fout; g.lda = w.ldf; g.perm = nullptr; g.hist = nullptr; g.nb = 0; g.w1 = g.w2 = nullptr; g.rows = w.rows;
     g.B = w.pnext; g.ldb = w.r1; g.K = w.r1; g.N = w.n1;
-    g.C = w.pb; g.ldc = w.rows;
+    g.C = w.pb; g.ldc = w.rows; g.mass_part = w.mass_part;
     wide_col_tiles((w.n1 + 7) >> 3, W_NJ_PDF, g.ncol, g.gpt);
+    pdf_ncol = g.ncol;
     const unsigned grid = (unsigned)row_tiles * (unsigned)g.ncol;
     wide_gemm_kernel<false, W_NJ_PDF><<<grid, W_THREADS, wide_smem_bytes(W_NJ_PDF), st>>>(g);
     cudaError_t e = cudaGetLastError();
@@ -432,7 +471,7 @@ cudaError_t launch_wide_step(const WideArgs &w, cudaStream_t st) {
   }
   {
     WideTailArgs t;
-    t.pb = w.pb; t.ldp = w.rows; t.x = w.xnext; t.ih = w.ihnext; t.rw = w.rwnext; t.hr = w.hrnext;
+    t.pb = w.pb; t.ldp = w.rows; t.mass_part = w.mass_part; t.nslots = 2 * pdf_ncol; t.x = w.xnext; t.ih = w.ihnext; t.rw = w.rwnext; t.hr = w.hrnext;
     t.n1 = w.n1; t.rows = w.rows; t.last = w.last;
     t.q = w.q; t.z = w.z; t.idx_out = w.idx_out; t.lpz = w.lpz;
     t.idx = w.idx; t.w1 = w.w1; t.w2 = w.w2; t.lp = w.lp; t.lpd = w.lpd; t.lpe = w.lpe; t.hist_next = w.hist_next;
