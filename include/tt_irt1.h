@@ -56,6 +56,8 @@ extern "C" {
  * 2^22 seed points, at most all visible ones from TTIRT_DEVICE on -- a batch of M >= 2^22 * N is sharded over N GPUs,
  * a small one stays on one), TTIRT_DEVICE=<first ordinal> (default 0), TTIRT_CHUNK=<samples per chunk>, TTIRT_CACHE=0 (free all device
  * memory before returning), TTIRT_TRACE=1 (host-side phase times on stderr), TTIRT_VERBOSE=1.
+ * Shapes: any (as the reference, tt_irt1_int32.c:41-53).  Ranks <= 64 on grids <= 72 run the fused kernels, ranks and grids up
+ * to 1024 the unfused FP64 tensor-core path (TTIRT_WIDE=0: off), anything larger the one-thread-per-sample strict kernel.
  */
 TTIRT_API void tt_irt1(TTIRT_INT d, TTIRT_INT *n, double *xs, TTIRT_INT *ttrank, double *ttcore, TTIRT_INT M,
              double *q, double *z, double *lPz);
