@@ -19,6 +19,7 @@
 //                                (ttirt_walk.cu), the nodes streamed from HBM instead of held in registers.
 // HBM traffic per sample and dimension: F in (once per column tile) + F' out + V out + V in twice ~ 8 (3 r + 3 n) bytes
 // against 4 r^2 + 2 r n flops: FP64 tensor pipe bound from r ~ 48 on.
+#include <cstdio>
 #include <type_traits>
 
 #include "ttirt_common.cuh"
@@ -68,6 +69,14 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// -DTTIRT_WIDE_CHECK: every global address the GEMM touches is checked against the operand extents (compute-sanitizer is not
+// available on the GPU pool); a violation prints one line and traps
+#ifdef TTIRT_WIDE_CHECK
+#define W_CHECK(cond, what) do { if (!(cond)) { printf("ttirt_wide: bounds violation (%s) block %u thread %u\n", what, blockIdx.x, threadIdx.x); __trap(); } } while (0)
+#else
+#define W_CHECK(cond, what) do { } while (0)
+#endif
+
 struct WideGemmArgs {
   const double *A;        // rows of the A operand: A + id * lda, valid and zero-padded up to K rounded to 8
   int lda;
@@ -83,6 +92,7 @@ struct WideGemmArgs {
   int gpt;                // 8-column groups per column tile (<= 2 NJ; the last tile may hold fewer)
   double *C;              // UPDATE: C[id * ldc + c] for c < N rounded to 8; else C[c * ldc + position] for c < N
   int64_t ldc;
+  int64_t a_elems, b_elems, c_elems, m_elems;   // extents of A, B, C and mass_part in doubles (checked builds)
   double *mass_part;      // pdf: per-row sums of |C| over the columns of one warp column, slot-major: [(2 tile + wc) * rows + position]
 };
 
@@ -193,6 +203,7 @@ __global__ void __launch_bounds__(W_THREADS, W_CTAS) wide_gemm_kernel(const Wide
 #pragma unroll
         for (int b = 0; b < W_HK / 8; b++) {
           const int sz = k0 + 8 * b < a_lim ? 16 : 0;
+          W_CHECK(!sz || ((a_src + k0 + 8 * b) - a.A >= 0 && (a_src + k0 + 8 * b + 8) - a.A <= a.a_elems), "A");
 #pragma unroll
           for (int u = 0; u < 4; u++)
             asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(a_dst + st_a + 64 * b + 16 * u), "l"(sz ? src + 64 * b + 16 * u : src), "r"(sz) : "memory");
@@ -201,6 +212,12 @@ __global__ void __launch_bounds__(W_THREADS, W_CTAS) wide_gemm_kernel(const Wide
       {
         const int live = k0 < b_lim ? b_cols : 0;
         const char *src = reinterpret_cast<const char *>(b_src + (UPDATE ? p * a.K : 0) + k0);
+#ifdef TTIRT_WIDE_CHECK
+        for (int e = 0; e < live; e++) {
+          const int64_t off = (reinterpret_cast<const double *>(src + (size_t)e * b_stride)) - a.B;
+          W_CHECK(off >= 0 && off < a.b_elems, "B");
+        }
+#endif
 #pragma unroll
         for (int e = 0; e < TN / W_CPT; e++)
           asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(b_dst + st_b + (uint32_t)(W_CPT * e * W_PITCH * sizeof(double))),
@@ -291,6 +308,7 @@ __global__ void __launch_bounds__(W_THREADS, W_CTAS) wide_gemm_kernel(const Wide
 #pragma unroll
       for (int j = 0; j < NJ; j++) {
         const int c = c0 + 8 * (j_first + j) + 2 * t;
+        W_CHECK(j >= jmax || ((crow + c) - a.C >= 0 && (crow + c + 2) - a.C <= a.c_elems), "C update");
         if (j < jmax) *reinterpret_cast<double2 *>(crow + c) = make_double2(acc[i][j][0], acc[i][j][1]);   // columns N .. N8-1: exact zeros
       }
     } else {
@@ -302,11 +320,13 @@ __global__ void __launch_bounds__(W_THREADS, W_CTAS) wide_gemm_kernel(const Wide
 #pragma unroll
       for (int j = 0; j < NJ; j++) {
         const int c = c0 + 8 * (j_first + j) + 2 * t;
+        W_CHECK(!(live && j < jmax && c < a.N) || (cpos + (int64_t)(c + (c + 1 < a.N ? 1 : 0)) * a.ldc) - a.C < a.c_elems, "C pdf");
         if (live && j < jmax && c < a.N) { cpos[(int64_t)c * a.ldc] = acc[i][j][0]; psum += fabs(acc[i][j][0]); }
         if (live && j < jmax && c + 1 < a.N) { cpos[(int64_t)(c + 1) * a.ldc] = acc[i][j][1]; psum += fabs(acc[i][j][1]); }
       }
       psum += __shfl_xor_sync(FULL, psum, 1);
       psum += __shfl_xor_sync(FULL, psum, 2);
+      W_CHECK(!live || (int64_t)(2 * (blockIdx.x % (unsigned)a.ncol) + wc) * a.rows + row0 + r < a.m_elems, "mass");
       if (live && t == 0) a.mass_part[(size_t)(2 * (blockIdx.x % (unsigned)a.ncol) + wc) * a.rows + row0 + r] = psum;
     }
   }
@@ -451,6 +471,7 @@ cudaError_t launch_wide_step(const WideArgs &w, cudaStream_t st) {
     g.A = w.Fin; g.lda = w.ldf; g.perm = w.perm; g.hist = w.hist_cur; g.nb = w.n0 - 1; g.w1 = w.w1; g.w2 = w.w2; g.rows = w.rows;
     g.B = w.core; g.ldb = (int64_t)w.r0 * w.n0; g.K = w.r0; g.N = w.r1;
     g.C = w.Fout; g.ldc = w.ldf; g.mass_part = nullptr;
+    g.a_elems = (int64_t)w.rows * w.ldf; g.b_elems = (int64_t)w.r0 * w.n0 * w.r1; g.c_elems = (int64_t)w.rows * w.ldf; g.m_elems = 0;
     wide_col_tiles((w.r1 + 7) >> 3, W_NJ_UPDATE, g.ncol, g.gpt);
     const unsigned grid = (unsigned)(row_tiles + (w.n0 - 1)) * (unsigned)g.ncol;   // at most rows / 64 + one ragged tile per interval
     wide_gemm_kernel<true, W_NJ_UPDATE><<<grid, W_THREADS, wide_smem_bytes(W_NJ_UPDATE), st>>>(g);
@@ -462,8 +483,10 @@ cudaError_t launch_wide_step(const WideArgs &w, cudaStream_t st) {
     g.A = w.Fout; g.lda = w.ldf; g.perm = nullptr; g.hist = nullptr; g.nb = 0; g.w1 = g.w2 = nullptr; g.rows = w.rows;
     g.B = w.pnext; g.ldb = w.r1; g.K = w.r1; g.N = w.n1;
     g.C = w.pb; g.ldc = w.rows; g.mass_part = w.mass_part;
+    g.a_elems = (int64_t)w.rows * w.ldf; g.b_elems = (int64_t)w.r1 * w.n1; g.c_elems = (int64_t)w.rows * w.n1;
     wide_col_tiles((w.n1 + 7) >> 3, W_NJ_PDF, g.ncol, g.gpt);
     pdf_ncol = g.ncol;
+    g.m_elems = (int64_t)2 * g.ncol * w.rows;
     const unsigned grid = (unsigned)row_tiles * (unsigned)g.ncol;
     wide_gemm_kernel<false, W_NJ_PDF><<<grid, W_THREADS, wide_smem_bytes(W_NJ_PDF), st>>>(g);
     cudaError_t e = cudaGetLastError();
