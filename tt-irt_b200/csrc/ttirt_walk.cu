@@ -20,8 +20,6 @@
 // Dimension 0 (left rank 1) is the shared table of the stage-0 kernel, in the reference's operation order.
 // Served: every n = 17, every inner rank <= 16 (interface width 8 or 16, smaller ranks zero-padded), d >= 2; everything else
 // uses the per-dimension path.
-#include <cstdlib>
-
 #include "ttirt_common.cuh"
 
 namespace ttirt {
@@ -273,208 +271,13 @@ __global__ void __launch_bounds__(WALK_THREADS, 1) walk_kernel(const WalkArgs a)
   }
 }
 
-// ---- sorted variant -------------------------------------------------------------------------------------------------
-// The walk kernel above is bound by shared-memory wavefronts at r = 16: every lane reads the two slabs of ITS interval, 32
-// distinct 8-byte words per LDS.64 = two wavefronts for one warp-wide FMA operand.  Here the CTA's samples (one block of
-// 32 * WALK_WARPS consecutive samples per pass) are re-dealt to the lanes in the order of the interval chosen in dimension k
-// before the interface update of that dimension: a counting sort in shared memory (histogram by shared atomics, two CTA-wide
-// named barriers per dimension, the per-sample state -- interface, weights, log-density products, next seed, sample id --
-// travels through a record in shared memory).  A warp then holds one or two intervals, its slab loads are (nearly) uniform
-// addresses, i.e. broadcasts of one wavefront.  Samples stay inside their CTA's block, so the q reads and z writes of a CTA
-// still cover whole sectors of a 3.8 KB window.  Everything else is the walk kernel: same ring, same arithmetic per sample,
-// hence bit-identical results (the permutation only changes which lane computes a sample).
-template <int R>
-struct SortedLayout {
-  static constexpr int REC = R + 7;                 // f[R], w1, w2, lpN, lpD, next seed, (lpE, sample id), interval: odd stride
-  static constexpr int SAMPLES = 32 * WALK_WARPS;
-};
-__device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, %0;" ::"n"(32 * WALK_WARPS) : "memory"); }
-
-template <int R, int N>
-__global__ void __launch_bounds__(WALK_THREADS, 1) walk_sorted_kernel(const WalkArgs a) {
-  using L = WalkLayout<R, N>;
-  using SL = SortedLayout<R>;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  double *ring = reinterpret_cast<double *>(smem_raw);
-  uint64_t *full = reinterpret_cast<uint64_t *>(ring + WALK_STAGES * L::STAGE), *empty = full + WALK_STAGES;
-  double *exch = reinterpret_cast<double *>(empty + WALK_STAGES);            // SAMPLES records
-  int *hist = reinterpret_cast<int *>(exch + SL::SAMPLES * SL::REC);         // two histograms of 32 counters
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) {
-    for (int s = 0; s < WALK_STAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, WALK_WARPS); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  const int d = a.d;
-  const int passes = (a.rows + SL::SAMPLES - 1) / SL::SAMPLES;     // blocks of SAMPLES consecutive samples
-  const int iters = (passes + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int steps = iters * d;
-
-  if (warp == WALK_WARPS) {
-    if (lane == 0) {
-      for (int t = 0; t < steps; t++) {
-        const int s = t % WALK_STAGES, k = t % d;
-        if (t >= WALK_STAGES) mbar_wait(empty + s, ((t / WALK_STAGES) - 1) & 1);
-        const uint32_t bytes = 8u * (uint32_t)(k == 0 ? L::SIZE0 : (k == d - 1 ? L::SIZE_LAST : L::SIZE_MID));
-        mbar_expect_tx(full + s, bytes);
-        bulk_g2s(ring + s * L::STAGE, a.pack + (size_t)k * L::STAGE, bytes, full + s);
-      }
-    }
-    return;
-  }
-
-  int t = 0;
-  for (int it = 0; it < iters; it++) {
-    const int pass = blockIdx.x + gridDim.x * it;
-    const bool work = pass < passes;                               // CTA-uniform: the barriers below are taken by all or none
-    int64_t m = work ? (int64_t)pass * SL::SAMPLES + tid : -1;
-    if (m >= a.rows) m = -1;                                       // a lane without a sample sorts behind all intervals
-    double f[R];
-    double lpN = 1.0, lpD = 1.0;
-    int lpE = 0;
-    double qk = m >= 0 ? a.q[m] : 0.5;
-    if (work) {
-      if (tid < 64) hist[tid] = 0;
-      bar_consumers();
-    }
-    for (int k = 0; k < d; k++, t++) {
-      const int s = t % WALK_STAGES;
-      mbar_wait(full + s, (t / WALK_STAGES) & 1);
-      if (work) {
-        const double *blk = ring + s * L::STAGE;
-        double qn = (m >= 0 && k + 1 < d) ? a.q[m + a.ldq * (k + 1)] : 0.5;   // next seed, a whole dimension ahead
-        if (k == 0) {
-          const double *p0 = blk + L::P0, *c0 = blk + L::C0, *x0 = blk + L::X0, *cr = blk + L::CORE0;
-          const int lo = walk_search0(c0, N, qk);
-          const CellOut o = invert_cell(qk, c0[lo], p0[lo], p0[lo + 1], x0[lo], x0[lo + 1]);
-          if (m >= 0) {
-            a.z[m] = o.xk;
-            if (a.idx_out) a.idx_out[m] = lo;
-          }
-          lp_accumulate(lpN, lpD, lpE, fabs(__dadd_rn(__dmul_rn(p0[lo], o.w1), __dmul_rn(p0[lo + 1], o.w2))), 1.0);
-#pragma unroll
-          for (int b = 0; b < R; b++) f[b] = fma(o.w2, cr[(lo + 1) * R + b], o.w1 * cr[lo * R + b]);
-        } else {
-          double v[N];
-#pragma unroll
-          for (int j = 0; j < N; j++) v[j] = 0.0;
-#pragma unroll
-          for (int a2 = 0; a2 < R; a2 += 2) {
-#pragma unroll
-            for (int j = 0; j < N; j++) {
-              const double2 pw = *reinterpret_cast<const double2 *>(blk + L::PW + j * R + a2);
-              v[j] = fma(f[a2], pw.x, v[j]);
-              v[j] = fma(f[a2 + 1], pw.y, v[j]);
-            }
-          }
-          double total = 0.0;
-#pragma unroll
-          for (int j = 0; j < N; j++) { v[j] = fabs(v[j]); total += v[j]; }
-          const double qt = qk * total;
-          int i0 = 0;
-          double dq = qt, va = v[0], vb = v[1], Rj = v[0];
-          const double *hr = blk + L::HR;
-#pragma unroll
-          for (int j = 1; j <= N - 2; j++) {
-            const double dj = qt - fma(hr[j], v[j], Rj);
-            if (__double_as_longlong(dj) > 0) { i0 = j; dq = dj; va = v[j]; vb = v[j + 1]; }
-            Rj += v[j];
-          }
-          const double s2 = pow2_scale(total);
-          double c1 = va * blk[L::RW + i0] * s2, c2 = vb * blk[L::RW + i0 + 1] * s2;
-          double mass = total * s2;
-          dq *= s2;
-          if (total == 0.0) {
-            const double u = 1.0 / (double)(N - 1);
-            const double sf = 1.0 / ((double)(N - 1) * u);
-            int k0 = 0;
-            for (int j = 1; j <= N - 2; j++) k0 += (qk > ((double)j * u) * sf) ? 1 : 0;
-            i0 = k0; dq = qk - ((double)k0 * u) * sf; c1 = u * sf; c2 = u * sf; mass = 1.0;
-          }
-          const CellFast o = invert_cell_fast(dq, c1, c2, blk[L::X + i0], blk[L::X + i0 + 1], blk[L::IH + i0]);
-          lp_accumulate(lpN, lpD, lpE, o.dens, mass);
-          if (m >= 0) {
-            a.z[m + a.ldz * k] = o.xk;
-            if (a.idx_out) a.idx_out[m + a.ldz * k] = i0;
-          }
-          if (k + 1 < d) {
-            // ---- re-deal the CTA's samples to the lanes in interval order (counting sort through shared memory) ----
-            int *hcur = hist + (k & 1) * 32, *hnext = hist + ((k + 1) & 1) * 32;
-            const int bin = m >= 0 ? i0 : N - 1;
-            const int rank = atomicAdd(&hcur[bin], 1);
-            bar_consumers();                                       // counts are final; last dimension's records are all read
-            if (tid < 32) hnext[tid] = 0;                          // (its last readers passed the previous barrier)
-            int slot = rank;
-#pragma unroll
-            for (int b = 0; b < N - 1; b++) slot += b < bin ? hcur[b] : 0;
-            double *rec = exch + slot * SL::REC;
-#pragma unroll
-            for (int b = 0; b < R; b++) rec[b] = f[b];
-            rec[R] = o.w1; rec[R + 1] = o.w2; rec[R + 2] = lpN; rec[R + 3] = lpD; rec[R + 4] = qn;
-            rec[R + 5] = __hiloint2double(lpE, (int)m);
-            rec[R + 6] = __hiloint2double(0, i0);
-            bar_consumers();                                       // every record is in place
-            rec = exch + tid * SL::REC;
-#pragma unroll
-            for (int b = 0; b < R; b++) f[b] = rec[b];
-            const double w1 = rec[R], w2 = rec[R + 1];
-            lpN = rec[R + 2]; lpD = rec[R + 3]; qn = rec[R + 4];
-            lpE = __double2hiint(rec[R + 5]); m = __double2loint(rec[R + 5]);
-            const int iv = __double2loint(rec[R + 6]);
-            // ---- interface update with the slabs of the (now warp-uniform, up to a boundary) interval ----
-            const double *A = blk + L::CORE + iv * L::NS, *B = A + L::NS;
-            double fn[R];
-#pragma unroll
-            for (int b = 0; b < R; b++) fn[b] = 0.0;
-#pragma unroll
-            for (int aa = 0; aa < R; aa++) {
-              const double f1 = w1 * f[aa], f2 = w2 * f[aa];
-#pragma unroll
-              for (int b = 0; b < R; b++) {
-                fn[b] = fma(f1, A[aa * R + b], fn[b]);
-                fn[b] = fma(f2, B[aa * R + b], fn[b]);
-              }
-            }
-#pragma unroll
-            for (int b = 0; b < R; b++) f[b] = fn[b];
-          }
-        }
-        qk = qn;
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(empty + s);
-    }
-    if (m >= 0) a.lpz[m] = lp_finish(lpN, lpD, lpE);
-  }
-}
-
-// which interface widths use the sorted variant when TTIRT_WALK_SORT is unset
-constexpr bool walk_sorted_default(int r) { return false && r == 16; }
-
-template <int R, int N>
-constexpr size_t walk_sorted_smem() {
-  return WalkLayout<R, N>::smem_bytes + sizeof(double) * SortedLayout<R>::SAMPLES * SortedLayout<R>::REC + sizeof(int) * 64;
-}
-
 template <int R, int N>
 cudaError_t walk_init_one() {
-  cudaError_t e = cudaFuncSetAttribute(walk_sorted_kernel<R, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_sorted_smem<R, N>());
-  if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(walk_kernel<R, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WalkLayout<R, N>::smem_bytes);
 }
 
 template <int R, int N>
 cudaError_t walk_launch_one(const WalkArgs &a, int sm_count, cudaStream_t st) {
-  // TTIRT_WALK_SORT: 1 the sorted variant for every class, 0 never; default: per class as measured (walk_sorted_default)
-  static const int sort_env = getenv("TTIRT_WALK_SORT") ? atoi(getenv("TTIRT_WALK_SORT")) : -1;
-  const bool sorted = sort_env >= 0 ? sort_env != 0 : walk_sorted_default(R);
-  if (sorted) {
-    const int passes = (a.rows + SortedLayout<R>::SAMPLES - 1) / SortedLayout<R>::SAMPLES;
-    int grid = sm_count < passes ? sm_count : passes;
-    if (grid < 1) grid = 1;
-    walk_sorted_kernel<R, N><<<grid, WALK_THREADS, walk_sorted_smem<R, N>(), st>>>(a);
-    return cudaGetLastError();
-  }
   const int groups = (a.rows + 31) >> 5;
   int grid = sm_count < groups ? sm_count : groups;
   if (grid < 1) grid = 1;
