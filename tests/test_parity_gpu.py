@@ -513,6 +513,14 @@ Z1, l1 = tt_irt.tt_irt1(q, tt_irt.TTTensor(ns, rk, c), xs)
 os.environ["TTIRT_DEVICES"] = "3"
 Z3, l3 = tt_irt.tt_irt1(q, tt_irt.TTTensor(ns, rk, c), xs)
 assert np.array_equal(Z1, Z3) and np.array_equal(l1, l3)
+# a wide shape (csrc/ttirt_wide.cu) through the sharded call: chunk size, cores fan-out and scratch are per shape class
+ns, xs, rk, c = synth.make_tt(3, 80, 72, seed=5)
+q = synth.make_q(150000, 3, seed=6)
+os.environ["TTIRT_DEVICES"] = "1"
+Z1, l1 = tt_irt.tt_irt1(q, tt_irt.TTTensor(ns, rk, c), xs)
+os.environ["TTIRT_DEVICES"] = "3"
+Z3, l3 = tt_irt.tt_irt1(q, tt_irt.TTTensor(ns, rk, c), xs)
+assert np.isfinite(l1).all() and np.array_equal(Z1, Z3) and np.array_equal(l1, l3)
 print("virtual devices ok")
 """
 
