@@ -12,13 +12,15 @@
 //                                Different column tiles of F' read the same rows of F, so F is double-buffered in HBM.
 //   (2) wide_gemm_kernel<false>  conditional pdf on the grid of dimension k+1 (reference :103-105) with the trapezoid node
 //                                weights folded into P_{k+1}'s columns: V = F' Pw_{k+1}, written node-major (n x rows) so
-//                                that step (3) reads it coalesced.
-//   (3) wide_tail_kernel         one thread per sample: mass, unnormalised search on the running sums (:107-142), closed-form
+//                                that step (3) reads it coalesced; its epilogue also leaves every row's mass sum_j |v_j| in
+//                                a few shares (fixed summation order), so that step (3) reads the nodes once.
+//   (3) wide_tail_kernel         one thread per sample: unnormalised search on the running sums (:107-142), closed-form
 //                                quadratic inversion (:146-159), log-density in split form (:161-165), interval histogram
 //                                for the next counting sort.  Same scaled formulation as the walk kernel's tail
 //                                (ttirt_walk.cu), the nodes streamed from HBM instead of held in registers.
-// HBM traffic per sample and dimension: F in (once per column tile) + F' out + V out + V in twice ~ 8 (3 r + 3 n) bytes
-// against 4 r^2 + 2 r n flops: FP64 tensor pipe bound from r ~ 48 on.
+// HBM traffic per sample and dimension: F in (the column tiles of a row tile run side by side and share it in L2) + F' out
+// + F' in + V out + V in ~ 8 (3 r + 2 n) bytes against 4 r^2 + 2 r n flops: FP64 tensor pipe bound from r ~ 48 on.
+// Measured (profiles/r02_wide.md): 23 TFLOP/s = 62 % of the DMMA peak at d=8 n=129 r=128, 28 x the strict kernel.
 #include <cstdio>
 #include <type_traits>
 
@@ -36,9 +38,11 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
       : "d"(a), "d"(b));
 }
 
-// CTA tile 64 rows x 64 columns, K in slices of 16; four warps, each 32 x 32 (4 x 4 DMMA tiles: 16 independent
-// accumulator chains).  One shared-memory stage; the next slice's global loads are in flight (registers) while the current
-// slice is multiplied, and three CTAs per SM cover each other's barriers.
+// CTA tile: 64 rows x up to 16 NJ columns (NJ 8-column groups per warp at most), K in slices of W_KS; four warps in a 2 x 2
+// grid, each 32 rows x up to 8 NJ columns (4 x NJ DMMA tiles: 16 - 20 independent accumulator chains).  The operands go
+// through a ring of W_STAGES shared-memory stages filled by cp.async one slice ahead, ONE barrier per slice, and three CTAs
+// per SM cover each other's barriers.  Measured alternatives (profiles/r02_wide.md): four CTAs per SM, three stages, slices
+// of 32 -- all slower: next to a DMMA stream fewer non-DMMA instructions help, more resident warps do not.
 #ifndef TTIRT_WIDE_KS
 #define TTIRT_WIDE_KS 16
 #endif
@@ -60,11 +64,8 @@ constexpr int W_STAGES = TTIRT_WIDE_STAGES, W_CTAS = TTIRT_WIDE_CTAS;
 constexpr size_t wide_smem_bytes(int nj) { return sizeof(double) * W_STAGES * (W_TM + 16 * nj) * W_PITCH; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-// cp.async (LDGSTS) of BYTES (8 or 16) global -> shared; !valid: zero-fill (src-size 0, src still a mapped address)
-template <int BYTES>
-__device__ __forceinline__ void cp_async_zfill(void *dst, const void *src, bool valid) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(smem_u32(dst)), "l"(src), "n"(BYTES), "r"(valid ? BYTES : 0) : "memory");
-}
+// cp.async (LDGSTS) global -> shared: 16-byte (A rows) and 8-byte (B columns) pieces are issued inline by issue_slice();
+// src-size 0 zero-fills a piece (src still a mapped address)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
