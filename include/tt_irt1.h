@@ -113,6 +113,18 @@ TTIRT_API int ttirt_run_host(int64_t d, const int64_t *n, const double *xs, cons
 TTIRT_API int ttirt_shard_rows(int64_t M, int n_shards, int shard, int64_t *m0, int64_t *m1);
 TTIRT_API int ttirt_auto_devices(int64_t M, int visible);
 
+/* Which kernels the fast mode uses for a TT of this shape (host-side arithmetic, no device needed; the reference serves
+ * every shape on one code path, tt_irt1_int32.c:41-53 -- so does this library, through four): */
+enum {
+  TTIRT_PATH_STRICT = -1, /* one thread per sample, reference operation order (ranks or grids above 1024; TTIRT_MODE=strict) */
+  TTIRT_PATH_FUSED16 = 0, /* sort + fused transition kernel, r <= 16 and n <= 24 */
+  TTIRT_PATH_FUSED32 = 1, /* ... r <= 32 and n <= 40 */
+  TTIRT_PATH_FUSED64 = 2, /* ... r <= 64 and n <= 72 (the BASELINE metric shape) */
+  TTIRT_PATH_WIDE = 3,    /* sort + grouped DMMA GEMMs + streaming tail, ranks and grids up to 1024 (TTIRT_WIDE=0: strict) */
+  TTIRT_PATH_WALK = 4     /* one persistent launch for all dimensions: every n = 17, ranks <= 16, d >= 2 (TTIRT_WALK=0: fused) */
+};
+TTIRT_API int ttirt_path_for_shape(int64_t d, const int64_t *n, const int64_t *ttrank);
+
 /* Per-launch CUDA-event timing of the dominant kernel (the fused transition kernel) for calls to
  * ttirt_sample_device on this model: enable(1) clears and starts, read() synchronises and returns the summed
  * kernel time in ms, the number of launches timed and their algorithmic FP64 flops

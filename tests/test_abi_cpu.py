@@ -126,3 +126,34 @@ def test_flop_model_matches_survey():
     for (d, n, r, w) in [(32, 65, 64, 749826), (40, 33, 32, 238210), (8, 17, 8, 3506), (8, 17, 16, 10050), (11, 17, 16, 14754)]:
         ns, xs, rk, c = synth.make_tt(d, n, r, seed=0) if d * n * r * r < 2e6 else (np.full(d, n), None, np.array([1] + [r] * (d - 1) + [1]), None)
         assert synth.flops_per_sample(ns, rk) == w
+
+
+def test_path_for_shape_is_host_arithmetic(libs):
+    """ttirt_path_for_shape (no device needed): which kernels the fast mode uses for a TT shape -- the walk kernel for small
+    ranks on 17-point grids, the three fused classes by largest rank / grid, the wide path up to 1024, the strict kernel beyond
+    (the reference serves every shape on one path, tt_irt1_int32.c:41-53)."""
+    LL = ctypes.c_longlong
+    STRICT, F16, F32, F64, WIDE, WALK = -1, 0, 1, 2, 3, 4
+
+    def path(lib, ns, rk):
+        n = (LL * len(ns))(*ns); r = (LL * len(rk))(*rk)
+        lib.ttirt_path_for_shape.restype = ctypes.c_int
+        lib.ttirt_path_for_shape.argtypes = [LL, ctypes.POINTER(LL), ctypes.POINTER(LL)]
+        return lib.ttirt_path_for_shape(len(ns), n, r)
+
+    for lib in libs:
+        assert path(lib, [17] * 8, [1] + [8] * 7 + [1]) == WALK                 # BASELINE configs[0]
+        assert path(lib, [17] * 11, [1] + [16] * 10 + [1]) == WALK              # configs[1]
+        assert path(lib, [17] * 5, [1, 3, 16, 9, 2, 1]) == WALK                 # ragged ranks, zero-padded
+        assert path(lib, [17], [1, 1]) == F16                                   # d = 1: no walk
+        assert path(lib, [17, 16], [1, 8, 1]) == F16                            # grids differ
+        assert path(lib, [17] * 4, [1, 17, 17, 17, 1]) == F32                   # rank beyond the walk kernel
+        assert path(lib, [33] * 40, [1] + [32] * 39 + [1]) == F32               # configs[3]
+        assert path(lib, [65] * 32, [1] + [64] * 31 + [1]) == F64               # configs[2], [4]
+        assert path(lib, [72] * 3, [1, 64, 64, 1]) == F64
+        assert path(lib, [73] * 3, [1, 64, 64, 1]) == WIDE
+        assert path(lib, [9] * 3, [1, 65, 65, 1]) == WIDE
+        assert path(lib, [1024] * 2, [1, 1024, 1]) == WIDE
+        assert path(lib, [1025] * 2, [1, 4, 1]) == STRICT
+        assert path(lib, [9] * 2, [1, 1025, 1]) == STRICT
+        assert path(lib, [1, 9], [1, 2, 1]) == STRICT                           # a one-point grid is not a valid shape

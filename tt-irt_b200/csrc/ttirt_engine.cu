@@ -529,6 +529,25 @@ extern "C" int ttirt_auto_devices(int64_t M, int visible) {
   return (int)(want > visible ? visible : want);
 }
 
+// Which kernels serve a shape in fast mode: the same arithmetic model_build() applies (walk kernel for small TTs on 17-point
+// grids, else the fused class by largest rank / grid, else the wide path, else the strict kernel).  No device needed.
+static int walk_class_of_shape(int64_t d, const int64_t *n, int64_t rmax) {
+  static const bool walk_on = !(getenv("TTIRT_WALK") && atoi(getenv("TTIRT_WALK")) == 0);
+  bool uniform = d >= 2;                                      // one grid size throughout; ranks may differ (zero-padded)
+  for (int64_t k = 0; k < d && uniform; k++) uniform = n[k] == n[0];
+  return (walk_on && uniform) ? walk_class_for((int)rmax, (int)n[0]) : -1;
+}
+extern "C" int ttirt_path_for_shape(int64_t d, const int64_t *n, const int64_t *ttrank) {
+  if (d < 1 || !n || !ttrank) return TTIRT_PATH_STRICT;
+  int64_t rmax = 1, nmax = 2;
+  for (int64_t k = 0; k < d; k++) {
+    if (n[k] < 2 || ttrank[k + 1] < 1 || n[k] > (1 << 20) || ttrank[k + 1] > (1 << 14)) return TTIRT_PATH_STRICT;
+    rmax = std::max(rmax, ttrank[k + 1]); nmax = std::max(nmax, n[k]);
+  }
+  if (walk_class_of_shape(d, n, rmax) >= 0) return TTIRT_PATH_WALK;
+  return fast_class_for((int)rmax, (int)nmax);
+}
+
 extern "C" void ttirt_model_destroy(ttirt_model *md) {
   if (!md) return;
   cudaSetDevice(md->device);
@@ -767,10 +786,7 @@ static int model_build(ttirt_model *md, const int64_t *n, const int64_t *rk, con
   if (md->fast_cls == kWideClass) CK(wide_init(md->device));
   // small uniform-rank TTs: one persistent kernel for the whole walk (TTIRT_WALK=0: per-dimension path, for comparison)
   {
-    static const bool walk_on = !(getenv("TTIRT_WALK") && atoi(getenv("TTIRT_WALK")) == 0);
-    bool uniform = d >= 2;                                    // one grid size throughout; ranks may differ (zero-padded)
-    for (int64_t k = 0; k < d && uniform; k++) uniform = n[k] == n[0];
-    md->walk_cls = (walk_on && uniform) ? walk_class_for((int)md->rmax, (int)n[0]) : -1;
+    md->walk_cls = walk_class_of_shape(d, n, md->rmax);
     if (md->walk_cls >= 0) {
       CK(walk_init(md->device));
       CK(cudaMalloc(&md->d_walk, sizeof(double) * walk_pack_doubles(md->walk_cls, (int)d)));
