@@ -375,12 +375,13 @@ def test_device_resident_entry_point_matches_host_path():
         md.close()
 
 
-def test_device_api_two_stream_chunks_match_host_path():
+@pytest.mark.parametrize("d,n,r", [(3, 65, 64), (3, 75, 70)])
+def test_device_api_two_stream_chunks_match_host_path(d, n, r):
     """ttirt_sample_device on a call of several chunks: the chunks alternate two workspaces on two internal streams forked
     from / joined into the caller's stream.  Results equal the host pipeline's bit for bit, work issued on the caller's
-    stream afterwards sees them (the join), and a second call on ANOTHER stream reuses the workspaces safely."""
+    stream afterwards sees them (the join), and a second call on ANOTHER stream reuses the workspaces safely.  Second
+    shape: the wide path (its workspaces carry two interface buffers, the pdf and the mass shares)."""
     torch = pytest.importorskip("torch")
-    d, n, r = 3, 65, 64
     ns, xs, rk, c = synth.make_tt(d, n, r, seed=81)
     M = 5 * (1 << 12) + 7
     q = synth.make_q(M, d, seed=82)
@@ -406,6 +407,18 @@ def test_device_api_two_stream_chunks_match_host_path():
                 assert np.array_equal(zd.cpu().numpy().T, Zh) and np.array_equal(ld_.cpu().numpy(), lh)
                 assert np.array_equal(idd.cpu().numpy().T, ih)
                 assert float(zsum.item()) == float(torch.from_numpy(np.ascontiguousarray(Zh.T)).cuda().sum().item())
+            # per-launch profiling (bench.py's roofline): serialised pass, one timed step per chunk and dimension after the
+            # first, the algorithmic flops of SURVEY section 8(d), the same bits
+            st, zd, ld_, idd, _ = outs[0]
+            md.profile_enable(True)
+            with torch.cuda.stream(st):
+                md.sample_device(M, qd.data_ptr(), M, zd.data_ptr(), M, ld_.data_ptr(), idd.data_ptr(), tt_irt.MODE_FAST, st.cuda_stream)
+            st.synchronize()
+            ms, launches, flops = md.profile_read()
+            md.profile_enable(False)
+            assert launches == 6 * (d - 1) and ms > 0.0
+            assert flops == M * sum(4.0 * rk[k] * rk[k + 1] + 2.0 * rk[k + 1] * ns[k + 1] for k in range(d - 1))
+            assert np.array_equal(zd.cpu().numpy().T, Zh) and np.array_equal(ld_.cpu().numpy(), lh)
         finally:
             lib.ttirt_set_chunk(0)
     finally:
