@@ -1180,7 +1180,10 @@ static int64_t host_chunk_for(int cls, bool strict, bool walk, int64_t rows, int
   if (g_chunk.load() <= 0 && getenv("TTIRT_CHUNK") == nullptr && !strict && cls >= 0 && cls <= 1)
     chunk = cls == 0 ? (1 << 17) : (1 << 19);
   // a walk-kernel chunk is one launch: cut small calls finer, so that upload, kernel and download of neighbouring chunks overlap
-  if (rows < chunk * kSlots) chunk = std::max<int64_t>((rows + kSlots - 1) / kSlots, std::min<int64_t>(rows, walk ? (1 << 12) : (1 << 16)));
+  if (rows < chunk * kSlots) {
+    const int64_t fine = std::max<int64_t>((rows + kSlots - 1) / kSlots, std::min<int64_t>(rows, walk ? (1 << 12) : (1 << 16)));
+    chunk = (cls == kWideClass && !strict) ? std::min(chunk, fine) : fine;   // (the wide path's chunk bounds its per-sample scratch)
+  }
   return chunk;
 }
 
