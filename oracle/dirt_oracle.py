@@ -1,7 +1,8 @@
 """TEST INFRASTRUCTURE ONLY: numpy restatement of the DIRT sampler loop, /root/reference/matlab/samplers/tt_dirt_sample.m:1-82
 (spline interpolation, TT cross variants: the branch that calls tt_irt_sqr at :46 and :71), on top of
-oracle/tt_irt_sqr_oracle.py.  PARITY UNPINNED against a live reference (Matlab-only); pinned by the properties in
-tests/test_dirt_oracle.py.  Nothing under tt-irt_b200/ imports this file.
+oracle/tt_irt_sqr_oracle.py.  Pinned against the reference's own tt_dirt_sample.m / tt_dirt_inverse.m executed from source by
+oracle/mlite.py on a synthetic two-level DIRT (uniform and truncated-normal reference; tests/golden/matlab_dirt_*.npz,
+tests/test_matlab_pins.py) and by the properties in tests/test_dirt.py.  Nothing under tt-irt_b200/ imports this file.
 """
 import math
 import re

@@ -1,0 +1,65 @@
+"""TEST INFRASTRUCTURE ONLY: calls the reference's MEX function tracemult (matlab/utils/tracemult.c, compiled UNMODIFIED against
+the stand-in mex.h under oracle/mexstub/ into oracle/_ref/libref_tracemult.so by oracle/Makefile) from Python.
+
+    ref_tracemult(A, j)        C(i) = A(i, j(i))                      A: n x s
+    ref_tracemult(A, j, B)     C(:,:,i) = A(:,:,i) * B(:,:,j(i))      A: p x m x n, B: m x k x s   (tracemult.c:103-112, 131-136)
+Arrays go in and come out in Matlab's column-major order; j is 1-based, as the MEX file reads it.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def available():
+    return os.path.exists(os.path.join(_HERE, "_ref", "libref_tracemult.so"))
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        lib = ctypes.CDLL(os.path.join(_HERE, "_ref", "libref_tracemult.so"))
+        vp, sz = ctypes.c_void_p, ctypes.c_size_t
+        lib.mexstub_wrap.restype = vp
+        lib.mexstub_wrap.argtypes = [vp, sz, ctypes.POINTER(sz)]
+        lib.mexstub_free_wrapper.argtypes = [vp]
+        lib.mexstub_free_array.argtypes = [vp]
+        lib.mexstub_ndim.restype = sz
+        lib.mexstub_ndim.argtypes = [vp]
+        lib.mexstub_dim.restype = sz
+        lib.mexstub_dim.argtypes = [vp, sz]
+        lib.mexstub_data.restype = ctypes.POINTER(ctypes.c_double)
+        lib.mexstub_data.argtypes = [vp]
+        lib.mexstub_call1.restype = vp
+        lib.mexstub_call1.argtypes = [ctypes.c_int, ctypes.POINTER(vp)]
+        _LIB = lib
+    return _LIB
+
+
+def ref_tracemult(A, j, B=None):
+    lib = _lib()
+    keep, wrapped = [], []
+    for x in ([A, j] if B is None else [A, j, B]):
+        a = np.asfortranarray(np.asarray(x, dtype=np.float64))
+        if a.ndim < 2:
+            a = a.reshape((-1, 1), order="F")
+        keep.append(a)
+        dims = (ctypes.c_size_t * a.ndim)(*a.shape)
+        wrapped.append(lib.mexstub_wrap(a.ctypes.data_as(ctypes.c_void_p), a.ndim, dims))
+    prhs = (ctypes.c_void_p * len(wrapped))(*wrapped)
+    out = lib.mexstub_call1(len(wrapped), prhs)
+    for w in wrapped:
+        lib.mexstub_free_wrapper(w)
+    if not out:
+        raise RuntimeError("tracemult returned no output (it prints its complaint to stderr and returns)")
+    nd = int(lib.mexstub_ndim(out))
+    shape = [int(lib.mexstub_dim(out, i)) for i in range(nd)]
+    n = int(np.prod(shape))
+    res = np.ctypeslib.as_array(lib.mexstub_data(out), shape=(max(n, 1),))[:n].copy().reshape(shape, order="F")
+    lib.mexstub_free_array(out)
+    while res.ndim > 2 and res.shape[-1] == 1:
+        res = res.reshape(res.shape[:-1], order="F")
+    return np.asfortranarray(res)

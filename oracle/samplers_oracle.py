@@ -1,10 +1,13 @@
 """TEST INFRASTRUCTURE ONLY: CPU restatements (numpy) of the steps either side of tt_irt1 that the B200 library also
 offers on the device.  Each function cites the reference lines it follows.
 
-Parity pins: the reference's Matlab cannot run here (no Matlab / Octave) and it ships no golden vectors for these
-helpers, so these restatements are pinned by closed-form cases only (tests/test_samplers_oracle.py) -- "parity
-unpinned" against a live reference run.  The Philox4x32-10 generator is pinned by the published known-answer vectors
-of the Random123 distribution.
+Parity pins: the reference ships no golden vectors for these helpers and this image has neither Matlab nor Octave.  They are
+pinned (a) against the reference's own source files executed here -- qmcnodes.m, randref.m, essinv.m, hellinger.m, iw_prune.m
+and mcmc_prune.m run unmodified under oracle/mlite.py, a small interpreter for the Matlab subset they use (numpy numerics
+stand in for Matlab's; tests/golden/make_golden_matlab.py -> tests/golden/matlab_helpers.npz, tests/test_matlab_pins.py),
+mcmc_prune also against the reference's Python loop (tests/golden/make_golden_mh.py) -- and (b) by closed forms
+(tests/test_samplers_oracle.py).  The Philox4x32-10 generator, which the reference does not have, is pinned by the published
+known-answer vectors of the Random123 distribution.
 """
 import numpy as np
 from math import erf, sqrt

@@ -4,8 +4,12 @@ Follows /root/reference/matlab/samplers/tt_irt_sqr.m:1-208 statement by statemen
 matlab/utils/tracemult.c:103-112 for the batched product and :131-136 for the column pick).  Nothing under
 tt-irt_b200/ imports this file; only tests/, __graft_entry__.smoke() and the bench scripts' checker legs do.
 
-PARITY PARTLY PINNED.  The routine itself is Matlab-only (no Matlab / Octave in this image, no golden vectors in the
-reference), so it cannot be run here.  It is pinned against the UNMODIFIED reference C routine
+PARITY PINS.  The routine is Matlab-only and the reference ships no golden vectors for it; this image has
+neither Matlab nor Octave.  (a) The reference's own source files tt_irt_sqr.m and tt_rt_sqr.m are executed here, unmodified,
+by oracle/mlite.py (an interpreter for the Matlab subset they use; numpy / LAPACK numerics stand in for Matlab's), with the MEX
+function they call, tracemult.c, compiled unmodified against a stand-in mex.h (oracle/mexstub/): six seeded TTs -- cores with and
+without boundary nodes, a marginal, signed cores, seeds 0 and 1 -- agree with this file to 1e-12 (tests/golden/make_golden_matlab.py
+-> tests/golden/matlab_sqr_*.npz, tests/test_matlab_pins.py).  (b) Independently of any interpreter it is pinned against the UNMODIFIED reference C routine
 tt_irt1 (oracle/_ref) wherever the two transforms are the same map (tests/test_sqr_oracle.py): on separable (rank-1)
 sqrt-densities every output (Z and the log-density), and for general ranks the first coordinate, which exercises the whole
 backward sweep (core x R, weighted QR, Cartesian square) against tt_irt1's marginalisation of the Kronecker-squared TT.

@@ -1,5 +1,6 @@
 """The DIRT sampler loop (reference matlab/samplers/tt_dirt_sample.m, spline branch): CPU tests of its numpy restatement
-(oracle/dirt_oracle.py, parity unpinned: Matlab-only) and GPU tests of ttirt_dirt_sample_* against it.
+(oracle/dirt_oracle.py; pinned against the reference's tt_dirt_sample.m / tt_dirt_inverse.m executed from source in
+tests/test_matlab_pins.py) and GPU tests of ttirt_dirt_sample_* against it.
 
 GPU bar: the composition feeds one level's samples to the next as seeds, so a level's admitted 1e-12-class perturbation is
 amplified by the next level's inverse-CDF slope 1 / p (up to ~1e3 in the tails).  Per entry: |dZ| <= 1e-9 max(1, |Z|) and

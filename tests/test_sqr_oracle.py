@@ -1,6 +1,8 @@
 """CPU tests of the squared-density oracle (oracle/tt_irt_sqr_oracle.py, the numpy restatement of the Matlab-only
-reference matlab/samplers/tt_irt_sqr.m).  No live reference exists here (parity unpinned), so the oracle is pinned by
-closed forms and by properties the reference's construction implies; the committed tests/golden/sqr_*.npz freeze it."""
+reference matlab/samplers/tt_irt_sqr.m).  Matlab cannot run here; tests/test_matlab_pins.py pins the oracle against the reference's
+source executed by a small Matlab-subset interpreter.  This file pins it independently of any interpreter: against the
+unmodified reference C tt_irt1 where the two transforms coincide, by closed forms and by properties the reference's
+construction implies; the committed tests/golden/sqr_*.npz freeze it."""
 import hashlib
 import importlib.util
 import os
