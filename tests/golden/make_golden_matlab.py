@@ -10,6 +10,8 @@ without Matlab:
         matlab/samplers/essinv.m, hellinger.m, iw_prune.m, mcmc_prune.m   (consumers after the path,      rank 2)
         matlab/samplers/tt_irt_sqr.m, tt_rt_sqr.m                  (squared-density transforms,    rank 4)
         matlab/samplers/tt_dirt_sample.m, tt_dirt_inverse.m        (their callers, the DIRT sample / inverse loops)
+        matlab/samplers/tt_irt_lin.m                               (the Matlab implementation of tt_irt1's own transform: the
+                                                                    interpreter's cross-check against the compiled reference C)
     read from /root/reference at generation time (never copied into this repo);
   * the MEX function those transforms call, matlab/utils/tracemult.c, is the reference's own C, compiled unmodified against a
     stand-in mex.h (oracle/mexstub/, oracle/Makefile -> oracle/_ref/libref_tracemult.so) and called through oracle/mex_host.py.
@@ -169,6 +171,26 @@ def run_dirt(case):
     return {"z": np.asarray(z), "lFapp": np.asarray(lF).reshape(-1), "inv_q": np.asarray(q2), "inv_lFapp": np.asarray(lF2).reshape(-1)}
 
 
+LIN_CASES = [("d4_n9_r4", 4, 9, 4, 500, 2, "uniform"), ("shock_d8_n17_r8", 8, 17, 8, 1500, 3, "uniform"), ("d5_n17_r16_cheb", 5, 17, 16, 800, 4, "chebyshev")]
+
+
+def lin_inputs(case):
+    from tt_irt_py import synth
+    name, d, n, r, M, seed, grid = case
+    ns, xs, rk, c = synth.make_tt(d, n, r, seed=seed, grid=grid)
+    return ns, xs, rk, c, synth.make_q(M, d, seed=seed + 50)
+
+
+def run_lin(case):
+    """[xq, lFapp] = tt_irt_lin(xsf, f, q): the reference's MATLAB implementation of the transform its C routine tt_irt1 computes."""
+    from oracle import mex_host, mlite
+    ns, xs, rk, c, q = lin_inputs(case)
+    ip = mlite.Interp(externals={"tracemult": lambda ip_, args, nargout: mex_host.ref_tracemult(*args)})
+    ip.load_file(os.path.join(REF_M, "tt_irt_lin.m"))
+    xq, lF = ip.call("tt_irt_lin", [np.asarray(xs, dtype=np.float64).reshape(-1, 1), _cell_of_cores(mlite, ns, rk, c), np.asfortranarray(q)], 2)
+    return {"xq": np.asarray(xq), "lFapp": np.asarray(lF).reshape(-1)}
+
+
 def tracemult_inputs():
     rng = np.random.default_rng(77)
     A = rng.normal(size=(3, 4, 50))
@@ -196,6 +218,9 @@ def main():
     for case in DIRT_CASES:
         np.savez_compressed(os.path.join(HERE, "matlab_dirt_%s.npz" % case[0]), **run_dirt(case))
         print("wrote dirt", case[0])
+    for case in LIN_CASES:
+        np.savez_compressed(os.path.join(HERE, "matlab_lin_%s.npz" % case[0]), **run_lin(case))
+        print("wrote lin", case[0])
 
 
 if __name__ == "__main__":

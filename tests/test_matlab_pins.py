@@ -3,7 +3,9 @@ reference's own source files executed here (tests/golden/matlab_*.npz, generator
 
 The reference sources run under oracle/mlite.py (an interpreter for the Matlab subset they use; numpy / LAPACK numerics) and
 the MEX function tracemult.c runs as the reference's own C compiled against a stand-in mex.h.  Three layers:
-  1. the interpreter itself against Matlab semantics worked out by hand (indexing, growth, ranges, N-d arrays, precedence);
+  1. the interpreter itself against Matlab semantics worked out by hand (indexing, growth, ranges, N-d arrays, precedence), and
+     against an independent ground truth: the reference's Matlab implementation of tt_irt1's transform (tt_irt_lin.m), run by the
+     interpreter, lands on the results of the reference's compiled C routine;
   2. every oracle function against the committed fixtures (always; needs nothing but the repo);
   3. when /root/reference is present (the build container): the generation is repeated and must give the committed bits, so the
      fixtures are what the reference's sources produce today and not a stale or hand-made file.
@@ -137,6 +139,21 @@ def test_mlite_refuses_what_it_does_not_know():
         _run("function y = t(x)\ny = x * x;\nend\n", "t", [np.zeros((2, 3))])
 
 
+@pytest.mark.parametrize("case", gen.LIN_CASES, ids=[c[0] for c in gen.LIN_CASES])
+def test_mlite_runs_the_matlab_tt_irt_lin_into_the_compiled_reference_c(oracle_mod, case):
+    """The interpreter against an independent ground truth: the reference ships the SAME transform twice, as Matlab
+    (matlab/samplers/tt_irt_lin.m, 150 lines: cells, N-d arrays, spdiags, cumsum, logical indexing, the tracemult MEX) and as C
+    (tt_irt1_int32.c).  The Matlab file executed by oracle/mlite.py must land on the compiled C routine's results -- which the C
+    oracle reproduces bit for bit (tests/test_oracle.py) -- inside the parity protocol (the two differ in their root formula and
+    tt_irt_lin.m clamps x_k to its cell, tt_irt_lin.m:134-150)."""
+    g = _load("matlab_lin_" + case[0])
+    ns, xs, rk, c, q = gen.lin_inputs(case)
+    Zo, lo, io, kap, gap, cond, lsens = oracle_mod.oracle_run(ns, xs, rk, c, q, extras=True)
+    stats, fails = oracle_mod.parity.compare(g["xq"], g["lFapp"], None, Zo, lo, None, cond, gap, lsens=lsens)
+    assert not fails, (fails, stats)
+    assert np.abs(g["xq"] - Zo).max() < 1e-11 and np.abs(g["lFapp"] - lo).max() < 1e-11
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # 2. oracles against the committed outputs of the reference sources
 # ---------------------------------------------------------------------------------------------------------------------
@@ -239,6 +256,10 @@ def test_fixtures_are_what_the_reference_sources_produce_here():
         g = _load("matlab_sqr_" + case[0])
         for k in live:
             assert np.array_equal(live[k], g[k]), (case[0], k)
+    live = gen.run_lin(gen.LIN_CASES[0])
+    g = _load("matlab_lin_" + gen.LIN_CASES[0][0])
+    for k in live:
+        assert np.array_equal(live[k], g[k]), k
     live = gen.run_dirt(gen.DIRT_CASES[1])
     g = _load("matlab_dirt_" + gen.DIRT_CASES[1][0])
     for k in live:
