@@ -4,6 +4,12 @@ the stand-in mex.h under oracle/mexstub/ into oracle/_ref/libref_tracemult.so by
     ref_tracemult(A, j)        C(i) = A(i, j(i))                      A: n x s
     ref_tracemult(A, j, B)     C(:,:,i) = A(:,:,i) * B(:,:,j(i))      A: p x m x n, B: m x k x s   (tracemult.c:103-112, 131-136)
 Arrays go in and come out in Matlab's column-major order; j is 1-based, as the MEX file reads it.
+
+It also calls the reference's MEX GATEWAY of the hot path, matlab/utils/tt_irt_mex.c (what Matlab runs for
+[Z, lPz] = tt_irt_mex(f.n, cell2mat(xsf), f.r, f.core, Z), install.m:169), compiled unmodified twice by oracle/Makefile:
+    tt_irt_mex("reference", ...)   gateway + the reference's own tt_irt1_int64.c            (oracle/_ref/libref_tt_irt_mex.so)
+    tt_irt_mex("b200", ...)        the same gateway linked against tt-irt_b200/lib/libtt_irt1_int64.so instead, i.e. the swap
+                                   INTEGRATION.md describes to a maintainer                 (oracle/_ref/libref_tt_irt_mex_b200.so)
 """
 import ctypes
 import os
@@ -63,3 +69,60 @@ def ref_tracemult(A, j, B=None):
     while res.ndim > 2 and res.shape[-1] == 1:
         res = res.reshape(res.shape[:-1], order="F")
     return np.asfortranarray(res)
+
+
+_GATEWAYS = {"reference": "libref_tt_irt_mex.so", "b200": "libref_tt_irt_mex_b200.so"}
+_GW = {}
+
+
+def gateway_available(which):
+    return os.path.exists(os.path.join(_HERE, "_ref", _GATEWAYS[which]))
+
+
+def _gateway(which):
+    if which not in _GW:
+        lib = ctypes.CDLL(os.path.join(_HERE, "_ref", _GATEWAYS[which]))
+        vp, sz = ctypes.c_void_p, ctypes.c_size_t
+        lib.mexstub_wrap.restype = vp
+        lib.mexstub_wrap.argtypes = [vp, sz, ctypes.POINTER(sz)]
+        lib.mexstub_free_wrapper.argtypes = [vp]
+        lib.mexstub_free_array.argtypes = [vp]
+        lib.mexstub_ndim.restype = sz
+        lib.mexstub_ndim.argtypes = [vp]
+        lib.mexstub_dim.restype = sz
+        lib.mexstub_dim.argtypes = [vp, sz]
+        lib.mexstub_data.restype = ctypes.POINTER(ctypes.c_double)
+        lib.mexstub_data.argtypes = [vp]
+        lib.mexFunction.restype = None
+        lib.mexFunction.argtypes = [ctypes.c_int, ctypes.POINTER(vp), ctypes.c_int, ctypes.POINTER(vp)]
+        _GW[which] = lib
+    return _GW[which]
+
+
+def tt_irt_mex(which, n, xs, ttrank, ttcore, q):
+    """[Z, lPz] = tt_irt_mex(n, xs, ttrank, ttcore, q) through the reference's gateway source (tt_irt_mex.c:7-42): everything is
+    passed as Matlab passes it, double arrays (n and ttrank included; the gateway converts them to mwIndex, :23-29).
+    Returns Z (M x d, column-major) and lPz (M,)."""
+    lib = _gateway(which)
+    keep, wrapped = [], []
+    for x, as_col in ((n, True), (xs, True), (ttrank, True), (ttcore, True), (q, False)):
+        a = np.asfortranarray(np.asarray(x, dtype=np.float64))
+        if as_col or a.ndim < 2:
+            a = a.reshape((-1, 1), order="F")
+        keep.append(a)
+        dims = (ctypes.c_size_t * a.ndim)(*a.shape)
+        wrapped.append(lib.mexstub_wrap(a.ctypes.data_as(ctypes.c_void_p), a.ndim, dims))
+    prhs = (ctypes.c_void_p * 5)(*wrapped)
+    plhs = (ctypes.c_void_p * 2)(None, None)
+    lib.mexFunction(2, plhs, 5, prhs)
+    for w in wrapped:
+        lib.mexstub_free_wrapper(w)
+    if not plhs[0] or not plhs[1]:
+        raise RuntimeError("tt_irt_mex assigned no outputs (it prints its complaint and returns)")
+    outs = []
+    for o in (plhs[0], plhs[1]):
+        shape = [int(lib.mexstub_dim(o, i)) for i in range(int(lib.mexstub_ndim(o)))]
+        cnt = int(np.prod(shape))
+        outs.append(np.ctypeslib.as_array(lib.mexstub_data(o), shape=(max(cnt, 1),))[:cnt].copy().reshape(shape, order="F"))
+        lib.mexstub_free_array(o)
+    return np.asfortranarray(outs[0]), outs[1].reshape(-1)
