@@ -81,48 +81,61 @@ def gateway_available(which):
 
 def _gateway(which):
     if which not in _GW:
-        lib = ctypes.CDLL(os.path.join(_HERE, "_ref", _GATEWAYS[which]))
-        vp, sz = ctypes.c_void_p, ctypes.c_size_t
-        lib.mexstub_wrap.restype = vp
-        lib.mexstub_wrap.argtypes = [vp, sz, ctypes.POINTER(sz)]
-        lib.mexstub_free_wrapper.argtypes = [vp]
-        lib.mexstub_free_array.argtypes = [vp]
-        lib.mexstub_ndim.restype = sz
-        lib.mexstub_ndim.argtypes = [vp]
-        lib.mexstub_dim.restype = sz
-        lib.mexstub_dim.argtypes = [vp, sz]
-        lib.mexstub_data.restype = ctypes.POINTER(ctypes.c_double)
-        lib.mexstub_data.argtypes = [vp]
-        lib.mexFunction.restype = None
-        lib.mexFunction.argtypes = [ctypes.c_int, ctypes.POINTER(vp), ctypes.c_int, ctypes.POINTER(vp)]
-        _GW[which] = lib
+        _GW[which] = _bind(ctypes.CDLL(os.path.join(_HERE, "_ref", _GATEWAYS[which])))
     return _GW[which]
+
+
+def _bind(lib):
+    vp, sz = ctypes.c_void_p, ctypes.c_size_t
+    lib.mexstub_wrap.restype = vp
+    lib.mexstub_wrap.argtypes = [vp, sz, ctypes.POINTER(sz)]
+    lib.mexstub_free_wrapper.argtypes = [vp]
+    lib.mexstub_free_array.argtypes = [vp]
+    lib.mexstub_ndim.restype = sz
+    lib.mexstub_ndim.argtypes = [vp]
+    lib.mexstub_dim.restype = sz
+    lib.mexstub_dim.argtypes = [vp, sz]
+    lib.mexstub_data.restype = ctypes.POINTER(ctypes.c_double)
+    lib.mexstub_data.argtypes = [vp]
+    lib.mexFunction.restype = None
+    lib.mexFunction.argtypes = [ctypes.c_int, ctypes.POINTER(vp), ctypes.c_int, ctypes.POINTER(vp)]
+    return lib
+
+
+def call_mex(lib, args, nlhs):
+    """mexFunction(nlhs, plhs, nrhs, prhs) of a gateway built against oracle/mexstub/ (lib: ctypes.CDLL or a path); args: arrays,
+    handed over as double mxArrays in column-major order (1-d inputs become columns).  Returns the nlhs outputs as numpy arrays."""
+    if isinstance(lib, str):
+        lib = _bind(ctypes.CDLL(lib))
+    keep, wrapped = [], []
+    for x in args:
+        a = np.asfortranarray(np.asarray(x, dtype=np.float64))
+        if a.ndim < 2:
+            a = a.reshape((-1, 1), order="F")
+        keep.append(a)
+        dims = (ctypes.c_size_t * a.ndim)(*a.shape)
+        wrapped.append(lib.mexstub_wrap(a.ctypes.data_as(ctypes.c_void_p), a.ndim, dims))
+    prhs = (ctypes.c_void_p * len(wrapped))(*wrapped)
+    plhs = (ctypes.c_void_p * max(1, nlhs))(*([None] * max(1, nlhs)))
+    lib.mexFunction(nlhs, plhs, len(wrapped), prhs)
+    for w in wrapped:
+        lib.mexstub_free_wrapper(w)
+    if any(not plhs[i] for i in range(nlhs)):
+        raise RuntimeError("the MEX function assigned no outputs (it prints its complaint and returns)")
+    outs = []
+    for i in range(nlhs):
+        o = plhs[i]
+        shape = [int(lib.mexstub_dim(o, k)) for k in range(int(lib.mexstub_ndim(o)))]
+        cnt = int(np.prod(shape))
+        outs.append(np.asfortranarray(np.ctypeslib.as_array(lib.mexstub_data(o), shape=(max(cnt, 1),))[:cnt].copy().reshape(shape, order="F")))
+        lib.mexstub_free_array(o)
+    return outs
 
 
 def tt_irt_mex(which, n, xs, ttrank, ttcore, q):
     """[Z, lPz] = tt_irt_mex(n, xs, ttrank, ttcore, q) through the reference's gateway source (tt_irt_mex.c:7-42): everything is
     passed as Matlab passes it, double arrays (n and ttrank included; the gateway converts them to mwIndex, :23-29).
     Returns Z (M x d, column-major) and lPz (M,)."""
-    lib = _gateway(which)
-    keep, wrapped = [], []
-    for x, as_col in ((n, True), (xs, True), (ttrank, True), (ttcore, True), (q, False)):
-        a = np.asfortranarray(np.asarray(x, dtype=np.float64))
-        if as_col or a.ndim < 2:
-            a = a.reshape((-1, 1), order="F")
-        keep.append(a)
-        dims = (ctypes.c_size_t * a.ndim)(*a.shape)
-        wrapped.append(lib.mexstub_wrap(a.ctypes.data_as(ctypes.c_void_p), a.ndim, dims))
-    prhs = (ctypes.c_void_p * 5)(*wrapped)
-    plhs = (ctypes.c_void_p * 2)(None, None)
-    lib.mexFunction(2, plhs, 5, prhs)
-    for w in wrapped:
-        lib.mexstub_free_wrapper(w)
-    if not plhs[0] or not plhs[1]:
-        raise RuntimeError("tt_irt_mex assigned no outputs (it prints its complaint and returns)")
-    outs = []
-    for o in (plhs[0], plhs[1]):
-        shape = [int(lib.mexstub_dim(o, i)) for i in range(int(lib.mexstub_ndim(o)))]
-        cnt = int(np.prod(shape))
-        outs.append(np.ctypeslib.as_array(lib.mexstub_data(o), shape=(max(cnt, 1),))[:cnt].copy().reshape(shape, order="F"))
-        lib.mexstub_free_array(o)
-    return np.asfortranarray(outs[0]), outs[1].reshape(-1)
+    Z, l = call_mex(_gateway(which), [np.asarray(n, dtype=np.float64).reshape(-1, 1), np.asarray(xs, dtype=np.float64).reshape(-1, 1),
+                                      np.asarray(ttrank, dtype=np.float64).reshape(-1, 1), np.asarray(ttcore, dtype=np.float64).reshape(-1, 1), q], 2)
+    return Z, l.reshape(-1)

@@ -29,6 +29,11 @@ const mwSize *mxGetDimensions(const mxArray *a);
 bool mxIsComplex(const mxArray *a);
 mxArray *mxCreateNumericArray(mwSize ndim, const mwSize *dims, mxClassID cls, mxComplexity c);
 mxArray *mxCreateDoubleMatrix(mwSize m, mwSize n, mxComplexity c);
+size_t mxGetNumberOfElements(const mxArray *a);
+size_t mxGetM(const mxArray *a);
+size_t mxGetN(const mxArray *a);   /* product of the dimensions from the second on, as in Matlab */
+void *mxMalloc(size_t bytes);
+void mxFree(void *p);
 int mexPrintf(const char *fmt, ...);
 
 void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]);

@@ -27,6 +27,19 @@ mxArray *mxCreateDoubleMatrix(mwSize m, mwSize n, mxComplexity c) {
   const mwSize dims[2] = {m, n};
   return mxCreateNumericArray(2, dims, mxDOUBLE_CLASS, c);
 }
+size_t mxGetNumberOfElements(const mxArray *a) {
+  size_t t = 1;
+  for (mwSize i = 0; i < a->ndim; i++) t *= a->dims[i];
+  return t;
+}
+size_t mxGetM(const mxArray *a) { return a->dims[0]; }
+size_t mxGetN(const mxArray *a) {
+  size_t t = 1;
+  for (mwSize i = 1; i < a->ndim; i++) t *= a->dims[i];
+  return t;
+}
+void *mxMalloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
+void mxFree(void *p) { free(p); }
 int mexPrintf(const char *fmt, ...) {
   va_list ap;
   va_start(ap, fmt);

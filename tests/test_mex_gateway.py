@@ -63,3 +63,46 @@ def test_matlab_gateway_on_the_drop_in_library_matches_the_reference_gateway(ora
         assert not fails, (fails, stats)
         Zp, lp = tt_irt.run_host(ns, xs, rk, c, q)                          # the same library through its Python mirror
         assert np.array_equal(Zb, Zp) and np.array_equal(lb, lp)
+
+
+# ---- the gateway INTEGRATION.md proposes for the squared-density transform (examples/tt_irt_sqr_mex.c) ----
+def _build_sqr_gateway(tmp_path):
+    so = str(tmp_path / "tt_irt_sqr_mex.so")
+    lib64 = os.path.join(ROOT, "tt-irt_b200", "lib")
+    stub = os.path.join(ROOT, "oracle", "mexstub")
+    cmd = ["gcc", "-O2", "-fPIC", "-shared", "-Wl,-Bsymbolic", "-I" + stub, os.path.join(ROOT, "examples", "tt_irt_sqr_mex.c"),
+           os.path.join(stub, "mexstub.c"), "-L" + lib64, "-ltt_irt1_int64", "-Wl,-rpath," + lib64, "-lm", "-o", so]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    return so
+
+
+def test_sqr_gateway_example_compiles_and_links(tmp_path):
+    so = _build_sqr_gateway(tmp_path)
+    undefined = subprocess.run(["nm", "-D", "--undefined-only", so], capture_output=True, text=True).stdout
+    assert " tt_irt_sqr" in undefined
+    if tt_irt.device_count() < 1:
+        ns, xs, rk, c = synth.make_tt(3, 5, 3, seed=1)
+        xq, lF = mex_host.call_mex(so, [ns, xs, rk, c, synth.make_q(32, 3, seed=2)], 2)
+        assert xq.shape == (32, 3) and np.isnan(xq).all() and np.isnan(lF).all()     # no device: NaN-filled, no crash
+
+
+@pytest.mark.gpu
+def test_sqr_gateway_example_matches_the_reference_matlab_source(tmp_path):
+    """examples/tt_irt_sqr_mex.c on the B200 library against the outputs of the reference's tt_irt_sqr.m executed from source
+    (tests/golden/matlab_sqr_*.npz): cores with and without boundary nodes, a marginal (q with fewer columns)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden_matlab as gen
+    from oracle import parity
+    from oracle.tt_irt_sqr_oracle import tt_irt_sqr_oracle
+    if tt_irt.device_count() < 1:
+        pytest.fail("no CUDA device: the -m gpu tests need a B200 (there is no CPU fallback)")
+    so = _build_sqr_gateway(tmp_path)
+    for case in gen.SQR_CASES[:5]:
+        g = dict(np.load(os.path.join(ROOT, "tests", "golden", "matlab_sqr_%s.npz" % case[0])))
+        ns, xs, rk, c, q = gen.sqr_inputs(case)
+        xq, lF = mex_host.call_mex(so, [ns, xs, rk, c, q], 2)
+        _, _, io, cond, gap, lsens = tt_irt_sqr_oracle(ns, xs, rk, c, q, extras=True)
+        st, fails = parity.compare(xq, lF.reshape(-1), None, g["xq"], g["lFapp"], None, cond, gap, lsens)
+        assert not fails, (case[0], fails, st)
