@@ -850,7 +850,7 @@ class Interp(object):
                 vals = self.call(base[1], args, 1)
                 return vals[0] if vals else zeros((0, 0))
             b = self.eval(base, env)
-            if isinstance(b, MFunc):
+            if isinstance(b, MFunc) or (callable(b) and not isinstance(b, (np.ndarray, MCell, str, dict))):
                 return self.call_handle(b, self.eval_args(e[2], env, None, None))
             if isinstance(b, MCell):
                 idx = self.eval_args(e[2], env, b, "cell")
@@ -932,6 +932,8 @@ class Interp(object):
         raise MatlabError("expression %r" % (k,))
 
     def call_handle(self, h, args):
+        if not isinstance(h, MFunc):                 # a Python callable handed in as a function handle
+            return h(*args)
         if h.params is None:
             return self.call(h.body, args, 1)[0]
         env = dict(h.env)
@@ -1135,6 +1137,8 @@ def _b_cellfun(ip, args, nargout):
 
 def _b_isa(ip, args, nargout):
     x, cls = args[0], str(args[1])
+    if isinstance(x, dict):                      # a struct, or an object of a class the caller names in the field __class__
+        return np.array([[x.get("__class__", "struct") == cls]])
     actual = "cell" if isinstance(x, MCell) else ("char" if isinstance(x, MStr) else ("function_handle" if isinstance(x, MFunc) else ("logical" if mat(x).dtype == np.bool_ else "double")))
     return np.array([[actual == cls or (cls in ("numeric", "float") and actual == "double")]])
 
@@ -1173,6 +1177,15 @@ def _b_keyboard(ip, args, nargout):
     raise MatlabError("keyboard reached (the reference stops in the debugger here)")
 
 
+def _b_cell2mat(ip, args, nargout):
+    c = args[0]
+    if c.a.shape[1] == 1:
+        return np.asfortranarray(np.concatenate([mat(x) for x in c.a[:, 0]], axis=0))
+    if c.a.shape[0] == 1:
+        return np.asfortranarray(np.concatenate([mat(x) for x in c.a[0, :]], axis=1))
+    return np.asfortranarray(np.concatenate([np.concatenate([mat(x) for x in row], axis=1) for row in c.a], axis=0))
+
+
 def _special():
     from scipy import special
     return special
@@ -1194,6 +1207,10 @@ Interp.builtins = {
     "cellfun": _b_cellfun, "isa": _b_isa, "rand": _b_rand, "load": _b_load,
     "lower": lambda ip, a, n: MStr(str(a[0]).lower()), "double": lambda ip, a, n: mat(a[0]).astype(np.float64),
     "char": lambda ip, a, n: MStr("".join(chr(int(c)) for c in mat(a[0]).reshape(-1, order="F"))),
+    "true": lambda ip, a, n: np.array([[True]]), "false": lambda ip, a, n: np.array([[False]]),
+    "tic": lambda ip, a, n: np.array([[0.0]]), "toc": lambda ip, a, n: np.array([[0.0]]), "nan": lambda ip, a, n: np.array([[float("nan")]]),
+    "strcmpi": lambda ip, a, n: np.array([[isinstance(a[0], str) and isinstance(a[1], str) and str(a[0]).lower() == str(a[1]).lower()]]),
+    "cell2mat": _b_cell2mat,
     "strcmp": lambda ip, a, n: np.array([[isinstance(a[0], str) and isinstance(a[1], str) and str(a[0]) == str(a[1])]]),
     "warning": _b_fprintf,
     "str2double": _b_str2double, "fprintf": _b_fprintf, "error": _b_error, "keyboard": _b_keyboard,

@@ -12,6 +12,8 @@ without Matlab:
         matlab/samplers/tt_dirt_sample.m, tt_dirt_inverse.m        (their callers, the DIRT sample / inverse loops)
         matlab/samplers/tt_irt_lin.m                               (the Matlab implementation of tt_irt1's own transform: the
                                                                     interpreter's cross-check against the compiled reference C)
+        matlab/samplers/tt_irt_debias.m                            (the top-level driver: seeds -> sampler -> exact density ->
+                                                                    MH / IW correction; oracle/matlab_driver.py)
     read from /root/reference at generation time (never copied into this repo);
   * the MEX function those transforms call, matlab/utils/tracemult.c, is the reference's own C, compiled unmodified against a
     stand-in mex.h (oracle/mexstub/, oracle/Makefile -> oracle/_ref/libref_tracemult.so) and called through oracle/mex_host.py.
@@ -191,6 +193,18 @@ def run_lin(case):
     return {"xq": np.asarray(xq), "lFapp": np.asarray(lF).reshape(-1)}
 
 
+def run_debias():
+    """The reference's top-level driver tt_irt_debias.m end to end (oracle/matlab_driver.py), its sampler call patched to the MEX
+    gateway as install.m:160-169 does, served by the reference's own gateway + C: both corrections."""
+    from oracle import matlab_driver
+    compiled = matlab_driver.compile_reference()
+    out = {}
+    for corr in ("mcmc", "iw"):
+        r = matlab_driver.run_debias("reference", corr, compiled)
+        out.update({corr + "_" + k: v for k, v in r.items()})
+    return out
+
+
 def tracemult_inputs():
     rng = np.random.default_rng(77)
     A = rng.normal(size=(3, 4, 50))
@@ -221,6 +235,8 @@ def main():
     for case in LIN_CASES:
         np.savez_compressed(os.path.join(HERE, "matlab_lin_%s.npz" % case[0]), **run_lin(case))
         print("wrote lin", case[0])
+    np.savez_compressed(os.path.join(HERE, "matlab_debias.npz"), **run_debias())
+    print("wrote debias")
 
 
 if __name__ == "__main__":
