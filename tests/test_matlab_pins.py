@@ -33,6 +33,9 @@ def _load(name):
     return dict(np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False))
 
 
+needs_reference_early = pytest.mark.skipif(not gen.available(), reason="needs /root/reference and oracle/_ref/libref_tracemult.so (build container only)")
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # 1. the interpreter
 # ---------------------------------------------------------------------------------------------------------------------
@@ -232,6 +235,18 @@ def test_dirt_loops_against_the_reference_matlab_sources(case):
     np.testing.assert_allclose(q2, g["inv_q"], rtol=0, atol=tol)
     np.testing.assert_allclose(lF2, g["inv_lFapp"], rtol=tol, atol=tol * 10)
     np.testing.assert_allclose(g["inv_q"], q, rtol=0, atol=1e-9)        # the reference's own round trip
+
+
+@needs_reference_early
+def test_mlite_runs_the_matlab_tracemult_fallback_into_the_compiled_mex():
+    """A second independent ground truth for the interpreter: the reference ships tracemult twice as well, as a MEX C file
+    (matlab/utils/tracemult.c, compiled unmodified here) and as its pure-Matlab fallback (matlab/utils/tracemultm.m)."""
+    from oracle import mex_host
+    ip = mlite.Interp()
+    ip.load_file("/root/reference/matlab/utils/tracemultm.m")
+    A, B, j, A2, j2 = gen.tracemult_inputs()
+    np.testing.assert_allclose(ip.call("tracemultm", [A, j, B])[0], mex_host.ref_tracemult(A, j, B), rtol=1e-14, atol=1e-14)
+    assert np.array_equal(ip.call("tracemultm", [A2, j2])[0], mex_host.ref_tracemult(A2, j2))
 
 
 # ---------------------------------------------------------------------------------------------------------------------
