@@ -29,7 +29,9 @@ and demands the committed bits.
 import os
 import sys
 
-import numpy as np
+os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")   # as tests/conftest.py: one BLAS thread, reproducible bits
+
+import numpy as np  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
