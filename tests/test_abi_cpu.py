@@ -157,3 +157,49 @@ def test_path_for_shape_is_host_arithmetic(libs):
         assert path(lib, [1025] * 2, [1, 4, 1]) == STRICT
         assert path(lib, [9] * 2, [1, 1025, 1]) == STRICT
         assert path(lib, [1, 9], [1, 2, 1]) == STRICT                           # a one-point grid is not a valid shape
+
+
+REF_WRAPPER = "/root/reference/python/tt_irt_py/tt_irt.py"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_WRAPPER), reason="needs /root/reference (build container only)")
+def test_unmodified_reference_python_wrapper_finds_and_calls_the_drop_in_library(tmp_path):
+    """The reference's own ctypes wrapper (python/tt_irt_py/tt_irt.py, executed from its source, not copied) placed -- by way of
+    its __file__ -- in a directory that holds a library named tt_irt1*: it globs the library (:8-11), binds tt_irt1 with c_int
+    arguments (:25) and calls it (:51).  With the reference's own C behind the name (oracle/_ref) it reproduces the oracle bit for
+    bit; with the product library it gets what this box can give: NaN-filled outputs and one stderr line without a device (the
+    GPU tests call the same symbol through the same argument types).  `import tt` (ttpy, absent here) is satisfied by an empty
+    module: the wrapper only touches f.core / f.ps / f.d / f.n / f.r."""
+    import shutil
+    import sys
+    import types
+    from tt_irt_py import synth, tt_irt as mirror
+    import oracle
+    ns, xs, rk, c = synth.make_tt(4, 9, 4, seed=3)
+    q = synth.make_q(300, 4, seed=4)
+    f = mirror.TTTensor(ns, rk, c)
+    with open(REF_WRAPPER) as fh:
+        src = fh.read()
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libref_tt_irt1_int32_shim.so")
+    cases = [("product", LIB32)] + ([("reference", ref_so)] if os.path.exists(ref_so) else [])
+    had_tt = sys.modules.get("tt")
+    sys.modules["tt"] = types.ModuleType("tt")
+    try:
+        for tag, so in cases:
+            d = tmp_path / tag
+            d.mkdir()
+            shutil.copy(so, str(d / "tt_irt1_int32.so"))          # a library by that name next to the wrapper, as setup.py leaves it
+            g = {"__file__": str(d / "tt_irt.py"), "__name__": "ref_tt_irt_" + tag}
+            exec(compile(src, REF_WRAPPER, "exec"), g)
+            Z, lPz = g["tt_irt1"](q, f, xs)
+            assert Z.shape == q.shape and lPz.shape == (300,)
+            if tag == "reference":
+                Zo, lo = oracle.oracle_run(ns, xs, rk, c, q)[:2]
+                assert np.array_equal(Z, Zo) and np.array_equal(lPz, lo)
+            elif _gpu_count(ctypes.CDLL(LIB32)) < 1:
+                assert np.isnan(Z).all() and np.isnan(lPz).all()
+    finally:
+        if had_tt is None:
+            sys.modules.pop("tt", None)
+        else:
+            sys.modules["tt"] = had_tt
